@@ -1,0 +1,588 @@
+"""numpy half of the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package
+``spectre_b200`` never does.
+
+It restates the host-side pieces of the reference's DG evolution path --
+spectral matrices, Adams-Bashforth / Runge-Kutta stepping with the forward
+self-start, the periodic Brick domain, analytic initial data and the parity
+norms -- and wraps the C restatement in ``dg_oracle.c`` (heavy loops).
+Citations are to the reference checkout (v2024.09.29), file:line.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from fractions import Fraction
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    """Compile dg_oracle.c -> oracle/_build/liboracle.so (gcc, OpenMP)."""
+    out = os.path.join(_HERE, "_build", "liboracle.so")
+    src = os.path.join(_HERE, "dg_oracle.c")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-std=c11", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"]
+        )
+    return out
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.orc_num_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------
+# Spectral: NumericalAlgorithms/Spectral/Legendre.cpp:187-232 (LGL nodes and
+# weights, Kopriva Alg. 25), Spectral.cpp:84-104 (barycentric weights, Kopriva
+# Alg. 30), Spectral.cpp:431-445 (differentiation matrix).
+# ---------------------------------------------------------------------------
+def _q_and_L(poly_degree: int, x: float):
+    # Legendre.cpp:160-184 (EvaluateQandL): three-term recurrence up to
+    # L_{N+1}; q = L_{N+1} - L_{N-1}
+    L_nm2, L_nm1 = 1.0, x
+    L_n = x
+    for k in range(2, poly_degree + 1):
+        L_n = ((2.0 * k - 1.0) * x * L_nm1 - (k - 1.0) * L_nm2) / k
+        L_nm2, L_nm1 = L_nm1, L_n
+    k = poly_degree + 1
+    L_np1 = ((2.0 * k - 1.0) * x * L_n - (k - 1.0) * L_nm2) / k
+    return L_np1 - L_nm2, L_n
+
+
+def lgl_points_and_weights(num_points: int):
+    N = num_points - 1
+    x = np.zeros(num_points)
+    w = np.zeros(num_points)
+    if N == 1:
+        x[:] = [-1.0, 1.0]
+        w[:] = 1.0
+        return x, w
+    x[0], x[N] = -1.0, 1.0
+    w[0] = w[N] = 2.0 / (N * (N + 1.0))
+    for j in range(1, (N + 1) // 2):
+        lo = -math.cos((j - 0.25) * math.pi / N - 0.375 / (N * math.pi * (j - 0.25)))
+        hi = -math.cos((j + 0.75) * math.pi / N - 0.375 / (N * math.pi * (j + 0.75)))
+        # bracketing root find of q to full double precision (the reference
+        # uses TOMS748 with abs tol 6e-16)
+        flo = _q_and_L(N, lo)[0]
+        fhi = _q_and_L(N, hi)[0]
+        assert flo * fhi < 0.0
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            if mid == lo or mid == hi:
+                break
+            fm = _q_and_L(N, mid)[0]
+            if fm == 0.0:
+                lo = hi = mid
+                break
+            if (fm < 0) == (flo < 0):
+                lo, flo = mid, fm
+            else:
+                hi, fhi = mid, fm
+        root = 0.5 * (lo + hi)
+        # polish with a secant step (keeps |q| minimal)
+        L = _q_and_L(N, root)[1]
+        x[j] = root
+        x[N - j] = -root
+        w[j] = w[N - j] = 2.0 / (N * (N + 1.0) * L * L)
+    if N % 2 == 0:
+        L = _q_and_L(N, 0.0)[1]
+        x[N // 2] = 0.0
+        w[N // 2] = 2.0 / (N * (N + 1.0) * L * L)
+    return x, w
+
+
+def barycentric_weights(x):
+    n = len(x)
+    bw = np.ones(n)
+    for j in range(1, n):
+        for k in range(j):
+            bw[k] *= x[k] - x[j]
+            bw[j] *= x[j] - x[k]
+    return 1.0 / bw
+
+
+def differentiation_matrix(num_points: int):
+    """D[i, j]; row-major (the reference stores it column-major)."""
+    x, _ = lgl_points_and_weights(num_points)
+    bw = barycentric_weights(x)
+    D = np.zeros((num_points, num_points))
+    for i in range(num_points):
+        diag = 0.0
+        for j in range(num_points):
+            if i != j:
+                D[i, j] = bw[j] / (bw[i] * (x[i] - x[j]))
+                diag -= D[i, j]
+        D[i, i] = diag
+    return D
+
+
+# ---------------------------------------------------------------------------
+# Adams-Bashforth coefficients: Time/TimeSteppers/AdamsCoefficients.cpp:13-42
+# (constant-step table), :75-117 (variable_coefficients), AdamsCoefficients.hpp
+# :64-104 (selection logic).
+# ---------------------------------------------------------------------------
+_AB_CONST = {
+    1: [1.0],
+    2: [-0.5, 1.5],
+    3: [5.0 / 12.0, -4.0 / 3.0, 23.0 / 12.0],
+    4: [-3.0 / 8.0, 37.0 / 24.0, -59.0 / 24.0, 55.0 / 24.0],
+    5: [251.0 / 720.0, -637.0 / 360.0, 109.0 / 30.0, -1387.0 / 360.0, 1901.0 / 720.0],
+    6: [-95.0 / 288.0, 959.0 / 480.0, -3649.0 / 720.0, 4991.0 / 720.0, -2641.0 / 480.0,
+        4277.0 / 1440.0],
+}
+
+
+def variable_coefficients(control_times, step_start, step_end):
+    ct = [t - step_start for t in control_times]
+    order = len(ct)
+    result = []
+    for j in range(order):
+        poly = [0.0] * order
+        poly[0] = 1.0
+        for m in range(order):
+            if m == j:
+                continue
+            denom = 1.0 / (ct[j] - ct[m])
+            i = m + 1 if m < j else m
+            while i > 0:
+                poly[i] = (poly[i - 1] - poly[i] * ct[m]) * denom
+                i -= 1
+            poly[0] *= -ct[m] * denom
+        for m in range(order):
+            poly[m] /= m + 1
+        dt = step_end - step_start
+        val = 0.0
+        for c in reversed(poly):  # evaluate_polynomial: Horner
+            val = val * dt + c
+        result.append(dt * val)
+    return result
+
+
+def ab_coefficients(times, step_start, step_end):
+    """times: history times oldest first (floats or Fractions)."""
+    if not times:
+        return []
+    step_size = float(step_end - step_start)
+    constant = True
+    control = [0.0]
+    prev = times[0]
+    for t in times[1:]:
+        this_step = float(t - prev)
+        control.append(control[-1] + this_step)
+        if constant and abs(this_step - step_size) > 4.0 * np.finfo(float).eps * max(
+            abs(float(t)), abs(step_size), 1e-300
+        ):
+            constant = False
+        prev = t
+    if constant and step_start == prev:
+        return [c * step_size for c in _AB_CONST[len(control)]]
+    return variable_coefficients(
+        control, control[-1] + float(step_start - prev), control[-1] + float(step_end - prev)
+    )
+
+
+# ---------------------------------------------------------------------------
+# Domain: periodic Brick (Domain/Creators/Rectilinear.cpp + Affine map).
+# Element order: x fastest (index = ix + nx*(iy + ny*iz)).
+# ---------------------------------------------------------------------------
+class Brick:
+    def __init__(self, lower, upper, refinement, N, periodic=True):
+        self.lower = np.asarray(lower, float)
+        self.upper = np.asarray(upper, float)
+        self.ne = [2 ** r for r in refinement]
+        self.N = N
+        self.nelem = self.ne[0] * self.ne[1] * self.ne[2]
+        self.n = N ** 3
+        self.periodic = periodic
+        x1, _ = lgl_points_and_weights(N)
+        self.xi = x1
+
+    def element_bounds(self, e):
+        nx, ny, nz = self.ne
+        idx = (e % nx, (e // nx) % ny, e // (nx * ny))
+        h = (self.upper - self.lower) / np.asarray(self.ne)
+        lo = self.lower + h * np.asarray(idx)
+        return lo, lo + h
+
+    def coords(self):
+        """[nelem, 3, n] inertial coordinates."""
+        N, n = self.N, self.n
+        out = np.zeros((self.nelem, 3, n))
+        i = np.arange(n) % N
+        j = (np.arange(n) // N) % N
+        k = np.arange(n) // (N * N)
+        for e in range(self.nelem):
+            lo, hi = self.element_bounds(e)
+            for d, idx in enumerate((i, j, k)):
+                # Affine: x = (hi-lo)/2 * xi + (hi+lo)/2  (CoordinateMaps/Affine.cpp)
+                out[e, d] = 0.5 * (hi[d] - lo[d]) * self.xi[idx] + 0.5 * (hi[d] + lo[d])
+        return out
+
+    def inverse_jacobian(self):
+        """[nelem, 9, n], comp = ihat + 3*i."""
+        out = np.zeros((self.nelem, 9, self.n))
+        for e in range(self.nelem):
+            lo, hi = self.element_bounds(e)
+            for d in range(3):
+                out[e, d + 3 * d] = 2.0 / (hi[d] - lo[d])
+        return out
+
+    def neighbors(self):
+        nx, ny, nz = self.ne
+        nbr = np.full((self.nelem, 6), -1, dtype=np.int32)
+        for e in range(self.nelem):
+            ix, iy, iz = e % nx, (e // nx) % ny, e // (nx * ny)
+            for d in range(6):
+                dim, side = d // 2, d % 2
+                c = [ix, iy, iz]
+                c[dim] += 1 if side else -1
+                ext = [nx, ny, nz][dim]
+                if c[dim] < 0 or c[dim] >= ext:
+                    if not self.periodic:
+                        continue
+                    c[dim] %= ext
+                nbr[e, d] = c[0] + nx * (c[1] + ny * c[2])
+        return nbr
+
+
+# ---------------------------------------------------------------------------
+# Analytic data
+# ---------------------------------------------------------------------------
+def plane_wave(x, t, k=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0), amp=1.0, wavenumber=1.0,
+               phase=0.0):
+    """PointwiseFunctions/AnalyticSolutions/WaveEquation/PlaneWave.cpp:56-119
+    with a MathFunctions::Sinusoid profile.  x: [..., 3, n] -> u [..., 5, n]."""
+    k = np.asarray(k, float)
+    omega = math.sqrt(float(np.dot(k, k)))
+    u_arg = sum(k[i] * (x[..., i, :] - center[i]) for i in range(3)) - omega * t
+    prof = amp * np.sin(wavenumber * u_arg + phase)
+    dprof = amp * wavenumber * np.cos(wavenumber * u_arg + phase)
+    out = np.zeros(x.shape[:-2] + (5, x.shape[-1]))
+    out[..., 0, :] = prof
+    out[..., 1, :] = omega * dprof  # Pi = -dpsi/dt
+    for i in range(3):
+        out[..., 2 + i, :] = k[i] * dprof
+    return out
+
+
+def sym4(a, b):
+    if a > b:
+        a, b = b, a
+    return a * 4 - a * (a - 1) // 2 + (b - a)
+
+
+def gh_vars_from_metric(g, dtg, dg):
+    """g: [4,4,...], dtg: [4,4,...], dg: [3,4,4,...] -> u [50, ...].
+    Phi_iab = d_i g_ab, Pi_ab = -(d_t g_ab - shift^i Phi_iab)/lapse
+    (GeneralizedHarmonic/{Phi.cpp:25-48,Pi.cpp:26-55} composed with
+    SpacetimeMetric.cpp; identical up to rounding)."""
+    gam = g[1:, 1:]
+    inv_gam = np.linalg.inv(np.moveaxis(gam, (0, 1), (-2, -1)))
+    inv_gam = np.moveaxis(inv_gam, (-2, -1), (0, 1))
+    shift = np.einsum("ij...,j...->i...", inv_gam, g[1:, 0])
+    lapse = np.sqrt(-g[0, 0] + np.einsum("i...,i...->...", shift, g[1:, 0]))
+    pi = -(dtg - np.einsum("i...,iab...->ab...", shift, dg)) / lapse
+    u = np.zeros((50,) + g.shape[2:])
+    for a in range(4):
+        for b in range(a, 4):
+            s = sym4(a, b)
+            u[s] = g[a, b]
+            u[10 + s] = pi[a, b]
+            for i in range(3):
+                u[20 + i + 3 * s] = dg[i, a, b]
+    return u
+
+
+def gauge_wave_metric(x, t, amplitude=0.1, wavelength=1.0):
+    """AnalyticSolutions/GeneralRelativity/GaugeWave.hpp:34-50:
+    ds^2 = -H dt^2 + H dx^2 + dy^2 + dz^2, H = 1 - A sin(2 pi (x-t)/d).
+    x: [3, n]."""
+    omega = 2.0 * np.pi / wavelength
+    H = 1.0 - amplitude * np.sin(omega * (x[0] - t))
+    dH = -omega * amplitude * np.cos(omega * (x[0] - t))
+    n = x.shape[-1]
+    g = np.zeros((4, 4, n))
+    dtg = np.zeros((4, 4, n))
+    dg = np.zeros((3, 4, 4, n))
+    g[0, 0] = -H
+    g[1, 1] = H
+    g[2, 2] = 1.0
+    g[3, 3] = 1.0
+    dtg[0, 0] = dH
+    dtg[1, 1] = -dH
+    dg[0, 0, 0] = -dH
+    dg[0, 1, 1] = dH
+    return g, dtg, dg
+
+
+def kerr_schild_metric(x, mass=1.0, center=(0.0, 0.0, 0.0)):
+    """Non-spinning Kerr-Schild (AnalyticSolutions/GeneralRelativity/
+    KerrSchild.hpp:40-200 with a=0): g = eta + 2 H l l, H = M/r, l = (1, x/r)."""
+    n = x.shape[-1]
+    xc = np.stack([x[i] - center[i] for i in range(3)])
+    r = np.sqrt(np.sum(xc * xc, axis=0))
+    H = mass / r
+    l = np.zeros((4, n))
+    l[0] = 1.0
+    l[1:] = xc / r
+    dH = -mass * xc / r ** 3  # [3, n]
+    dl = np.zeros((3, 4, n))
+    for i in range(3):
+        for j in range(3):
+            dl[i, 1 + j] = ((1.0 if i == j else 0.0) - xc[i] * xc[j] / r ** 2) / r
+    eta = np.diag([-1.0, 1.0, 1.0, 1.0])
+    g = eta[:, :, None] + 2.0 * H * l[:, None] * l[None, :]
+    dg = np.zeros((3, 4, 4, n))
+    for i in range(3):
+        dg[i] = 2.0 * dH[i] * l[:, None] * l[None, :] + 2.0 * H * (
+            dl[i][:, None] * l[None, :] + l[:, None] * dl[i][None, :]
+        )
+    dtg = np.zeros((4, 4, n))
+    return g, dtg, dg
+
+
+def gaussian_plus_constant(x, constant, amplitude, width, center):
+    """ConstraintDamping/GaussianPlusConstant.cpp: C + A exp(-|x-x0|^2/w^2)."""
+    r2 = sum((x[..., i, :] - center[i]) ** 2 for i in range(3))
+    return constant + amplitude * np.exp(-r2 / width ** 2)
+
+
+# ---------------------------------------------------------------------------
+# C wrappers
+# ---------------------------------------------------------------------------
+GAUGE_HARMONIC = np.array([0.0, 0, 0, 0, 0, 0, 0, 0])
+GAUGE_GIVEN = np.array([1.0, 0, 0, 0, 0, 0, 0, 0])
+
+
+def partial_derivatives(N, u, invjac):
+    """u [C, n], invjac [9, n] -> du [3C, n]"""
+    C = u.shape[0]
+    D = _c(differentiation_matrix(N))
+    u, invjac = _c(u), _c(invjac)
+    du = np.zeros((3 * C, N ** 3))
+    lib().orc_partial_derivatives(N, C, _p(D), _p(u), _p(invjac), _p(du))
+    return du
+
+
+def sw_time_derivative(u, du, gamma2):
+    n = u.shape[1]
+    dt = np.zeros((5, n))
+    u, du, gamma2 = _c(u), _c(du), _c(gamma2)
+    lib().orc_sw_time_derivative(n, _p(u), _p(du), _p(gamma2), _p(dt))
+    return dt
+
+
+def gh_time_derivative(u, du, gamma0, gamma1, gamma2, gauge_params=GAUGE_HARMONIC, H=None,
+                       dH=None, coords=None):
+    n = u.shape[1]
+    dt = np.zeros((50, n))
+    args = [_c(a) for a in (u, du, gamma0, gamma1, gamma2, gauge_params)]
+    H = _c(H) if H is not None else np.zeros((4, n))
+    dH = _c(dH) if dH is not None else np.zeros((16, n))
+    coords = _c(coords) if coords is not None else None
+    lib().orc_gh_time_derivative(n, *[_p(a) for a in args], _p(H), _p(dH), _p(coords), _p(dt))
+    return dt
+
+
+def gh_geometry(u):
+    n = u.shape[1]
+    out = np.zeros((21, n))
+    u = _c(u)
+    lib().orc_gh_geometry(n, _p(u), _p(out))
+    return {"lapse": out[0], "shift": out[1:4], "inv_gamma": out[4:10], "inv_g": out[10:20],
+            "det_gamma": out[20]}
+
+
+def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC, coords=None,
+           volume_only=False):
+    """u [nelem, C, n]; returns dt_u of the same shape."""
+    nelem = u.shape[0]
+    D = _c(differentiation_matrix(N))
+    u, invjac, static_fields = _c(u), _c(invjac), _c(static_fields)
+    gp = _c(gauge_params)
+    nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+    coords = _c(coords) if coords is not None else None
+    dt = np.zeros_like(u)
+    if volume_only:
+        lib().orc_dg_volume(system, N, nelem, _p(D), _p(u), _p(invjac), _p(static_fields),
+                            _p(coords), _p(gp), _p(dt))
+    else:
+        lib().orc_dg_rhs(system, N, nelem, _p(D), _p(u), _p(invjac), _p(static_fields),
+                         _p(coords), _p(nbr), _p(gp), _p(dt))
+    return dt
+
+
+def analytic_christoffel_gauge(N, u_analytic, invjac):
+    """H_a = -Gamma_a of the analytic solution, d_i H_a by numerical
+    differentiation, d_t H_a = 0 (GaugeSourceFunctions/AnalyticChristoffel.cpp
+    :64-149).  u_analytic [50, n] -> H [4, n], dH [16, n] (d_a H_b at a+4b)."""
+    n = u_analytic.shape[1]
+    g = np.zeros((4, 4, n))
+    pi = np.zeros((4, 4, n))
+    phi = np.zeros((3, 4, 4, n))
+    for a in range(4):
+        for b in range(4):
+            s = sym4(a, b)
+            g[a, b] = u_analytic[s]
+            pi[a, b] = u_analytic[10 + s]
+            for i in range(3):
+                phi[i, a, b] = u_analytic[20 + i + 3 * s]
+    geo = gh_geometry(u_analytic)
+    inv_g = np.zeros((4, 4, n))
+    k = 0
+    for a in range(4):
+        for b in range(a, 4):
+            inv_g[a, b] = inv_g[b, a] = geo["inv_g"][k]
+            k += 1
+    dag = np.zeros((4, 4, 4, n))
+    dag[0] = -geo["lapse"] * pi + np.einsum("i...,iab...->ab...", geo["shift"], phi)
+    dag[1:] = phi
+    chr1 = 0.5 * (np.einsum("ijk...->kij...", dag) + np.einsum("jik...->kij...", dag) - dag)
+    H = -np.einsum("abc...,bc...->a...", chr1, inv_g)
+    dHs = partial_derivatives(N, H, invjac)  # [3*4, n], index 3*a + i
+    dH = np.zeros((16, n))
+    for b in range(4):
+        for i in range(3):
+            dH[(i + 1) + 4 * b] = dHs[3 * b + i]
+    return H, dH
+
+
+# ---------------------------------------------------------------------------
+# Time stepping (GTS): AdamsBashforth.cpp:120-201, Rk3HesthavenSsp.cpp:55-81,
+# self start Time/Actions/SelfStartActions.hpp:181-243,316-394 and the action
+# order of Evolution/Executables/.../step_actions.
+# Times are exact Fractions of the step (the reference uses rational Time).
+# ---------------------------------------------------------------------------
+class Evolution:
+    def __init__(self, rhs, u0, t0, dt, stepper="AB3"):
+        """rhs(u, t) -> dt_u.  stepper: 'AB<k>' or 'RK3' (Rk3HesthavenSsp)."""
+        self.rhs = rhs
+        self.u = u0.copy()
+        self.t0 = t0
+        self.dt = dt
+        self.stepper = stepper
+        self.step_index = 0  # completed full steps
+        self.history = []  # list of (time_fraction, u or None, dt_u), oldest first
+        self.rhs_evals = 0
+        if stepper.startswith("AB"):
+            self.order = int(stepper[2:])
+            self._self_start()
+
+    def _time(self, frac):
+        return self.t0 + float(frac) * self.dt
+
+    def _eval(self, frac):
+        self.rhs_evals += 1
+        return self.rhs(self.u, self._time(frac))
+
+    def _ab_update(self, order, step_start, step_end):
+        hist = self.history[-order:]
+        coefs = ab_coefficients_frac([h[0] for h in hist], step_start, step_end, self.dt)
+        u = hist[-1][1].copy()
+        for c, h in zip(coefs, hist):
+            u += c * h[2]
+        return u
+
+    def _clean(self, order):
+        while len(self.history) >= order:
+            self.history.pop(0)
+        if len(self.history) > 1:
+            t, _, d = self.history[-2]
+            self.history[-2] = (t, None, d)
+
+    def _self_start(self):
+        k = self.order
+        if k == 1:
+            return
+        u_init = self.u.copy()
+        h = Fraction(1, k)  # self-start step = dt / (values_needed + 1)
+        for order in range(1, k):
+            # reset to t0 (CheckForCompletion restores the initial value)
+            self.u = u_init.copy()
+            for s in range(order + 1):
+                t = s * h
+                d = self._eval(t)
+                self.history.append((t, self.u.copy(), d))
+                if s == order:
+                    # step_unused: UpdateU skipped, history order was bumped
+                    self._clean(order + 1)
+                    break
+                self.u = self._ab_update(order, t, t + h)
+                self._clean(order)
+        self.u = u_init.copy()
+
+    def step(self):
+        n = Fraction(self.step_index)
+        if self.stepper.startswith("AB"):
+            k = self.order
+            d = self._eval(n)
+            self.history.append((n, self.u.copy(), d))
+            self.u = self._ab_update(k, n, n + 1)
+            self._clean(k)
+        elif self.stepper == "RK3":
+            dt = self.dt
+            u0 = self.u.copy()
+            f0 = self._eval(n)
+            self.u = u0 + dt * f0
+            f1 = self._eval(n + 1)
+            u1 = self.u.copy()
+            self.u = 0.25 * (3.0 * u0 + u1 + dt * f1)
+            f2 = self._eval(n + Fraction(1, 2))
+            u2 = self.u.copy()
+            self.u = (1.0 / 3.0) * (u0 + 2.0 * u2 + 2.0 * dt * f2)
+        else:
+            raise ValueError(self.stepper)
+        self.step_index += 1
+
+    @property
+    def time(self):
+        return self._time(Fraction(self.step_index))
+
+
+def ab_coefficients_frac(times, step_start, step_end, dt):
+    """Same selection logic as AdamsCoefficients.hpp:64-104 with the history
+    times given as exact Fractions of the step dt (the reference's Time is an
+    exact rational of the slab)."""
+    order = len(times)
+    step = step_end - step_start
+    uniform = all(b - a == step for a, b in zip(times[:-1], times[1:])) and \
+        times[-1] == step_start
+    if uniform:
+        return [c * (float(step) * dt) for c in _AB_CONST[order]]
+    control = [0.0]
+    for a, b in zip(times[:-1], times[1:]):
+        control.append(control[-1] + float(b - a) * dt)
+    return variable_coefficients(control, control[-1] + float(step_start - times[-1]) * dt,
+                                 control[-1] + float(step_end - times[-1]) * dt)
+
+
+# ---------------------------------------------------------------------------
+# Norms: ParallelAlgorithms/Events/ObserveNorms.hpp:60-80
+# L2Norm with Components: Sum = sqrt( sum_points sum_comps v^2 / N_points )
+# ---------------------------------------------------------------------------
+def l2_norm(v):
+    """v [nelem, ncomp, n] (independent components only, like the reference)."""
+    npts = v.shape[0] * v.shape[2]
+    return math.sqrt(float(np.sum(v * v)) / npts)

@@ -1,0 +1,112 @@
+"""Generate golden input/output vectors by importing the REFERENCE's own numpy
+oracles (authoring container only; needs /root/reference):
+
+    python tests/golden/gen_python_goldens.py
+
+Writes tests/golden/upwind_penalty.npz: random per-point inputs and the outputs
+of tests/Unit/Evolution/Systems/{GeneralizedHarmonic,ScalarWave}/
+BoundaryCorrections/UpwindPenalty.py (dg_package_data, dg_boundary_terms).
+Seeds are fixed; the file travels to the GPU box, the reference does not.
+"""
+import importlib.util
+import os
+
+import numpy as np
+
+REF = "/root/reference/tests/Unit/Evolution/Systems"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def sym4(a, b):
+    if a > b:
+        a, b = b, a
+    return a * 4 - a * (a - 1) // 2 + (b - a)
+
+
+def pack_aa(t):  # [4,4] -> 10
+    return np.array([t[a, b] for a in range(4) for b in range(a, 4)])
+
+
+def pack_iaa(t):  # [3,4,4] -> 30 (i + 3*sym)
+    out = np.zeros(30)
+    for a in range(4):
+        for b in range(a, 4):
+            for i in range(3):
+                out[i + 3 * sym4(a, b)] = t[i, a, b]
+    return out
+
+
+def main():
+    gh = _load(f"{REF}/GeneralizedHarmonic/BoundaryCorrections/UpwindPenalty.py", "gh_up")
+    sw = _load(f"{REF}/ScalarWave/BoundaryCorrections/UpwindPenalty.py", "sw_up")
+    rng = np.random.default_rng(20240929)
+    npts = 64
+    out = {}
+    # ---- GH ----
+    gh_u = np.zeros((2, npts, 50)); gh_g1 = np.zeros((2, npts)); gh_g2 = np.zeros((2, npts))
+    gh_lapse = np.zeros((2, npts)); gh_shift = np.zeros((2, npts, 3))
+    gh_nlo = np.zeros((2, npts, 3)); gh_nup = np.zeros((2, npts, 3))
+    gh_pk = np.zeros((2, npts, 134)); gh_corr = np.zeros((npts, 50))
+    for p in range(npts):
+        packs = []
+        for side in range(2):
+            def symm(x):
+                return 0.5 * (x + x.T)
+            g = symm(rng.uniform(-1, 1, (4, 4)))
+            pi = symm(rng.uniform(-1, 1, (4, 4)))
+            phi = rng.uniform(-1, 1, (3, 4, 4))
+            phi = 0.5 * (phi + phi.transpose(0, 2, 1))
+            g1, g2 = rng.uniform(-1, 1), rng.uniform(-1, 1)
+            lapse = rng.uniform(0.2, 2.0)
+            shift = rng.uniform(-1.5, 1.5, 3)
+            nlo = rng.uniform(-1, 1, 3)
+            nup = rng.uniform(-1, 1, 3)
+            r = gh.dg_package_data(g, pi, phi, g1, g2, lapse, shift, nlo, nup, None, None)
+            pk = np.concatenate([pack_aa(r[0]), pack_iaa(r[1]), pack_aa(r[2]), pack_aa(r[3]),
+                                 pack_iaa(r[4]), pack_iaa(r[5]), pack_aa(r[6]), r[7]])
+            packs.append(r)
+            gh_u[side, p] = np.concatenate([pack_aa(g), pack_aa(pi), pack_iaa(phi)])
+            gh_g1[side, p], gh_g2[side, p] = g1, g2
+            gh_lapse[side, p] = lapse
+            gh_shift[side, p] = shift
+            gh_nlo[side, p], gh_nup[side, p] = nlo, nup
+            gh_pk[side, p] = pk
+        c = gh.dg_boundary_terms(*packs[0], *packs[1], True)
+        gh_corr[p] = np.concatenate([pack_aa(c[0]), pack_aa(c[1]), pack_iaa(c[2])])
+    out.update(gh_u=gh_u, gh_gamma1=gh_g1, gh_gamma2=gh_g2, gh_lapse=gh_lapse,
+               gh_shift=gh_shift, gh_nlo=gh_nlo, gh_nup=gh_nup, gh_packaged=gh_pk,
+               gh_corr=gh_corr)
+    # ---- SW ----
+    sw_u = np.zeros((2, npts, 5)); sw_g2 = np.zeros((2, npts)); sw_n = np.zeros((2, npts, 3))
+    sw_pk = np.zeros((2, npts, 16)); sw_corr = np.zeros((npts, 5))
+    for p in range(npts):
+        packs = []
+        for side in range(2):
+            psi, pi = rng.uniform(-1, 1), rng.uniform(-1, 1)
+            phi = rng.uniform(-1, 1, 3)
+            g2 = rng.uniform(0, 1)
+            n = rng.uniform(-1, 1, 3)
+            n /= np.linalg.norm(n)
+            r = sw.dg_package_data(psi, pi, phi, g2, n, None, None)
+            packs.append(r)
+            sw_u[side, p] = np.concatenate([[psi, pi], phi])
+            sw_g2[side, p] = g2
+            sw_n[side, p] = n
+            sw_pk[side, p] = np.concatenate([[r[0]], r[1], [r[2]], [r[3]], r[4], r[5], [r[6]],
+                                             r[7]])
+        c = sw.dg_boundary_terms(*packs[0], *packs[1], True)
+        sw_corr[p] = np.concatenate([[c[0]], [c[1]], c[2]])
+    out.update(sw_u=sw_u, sw_gamma2=sw_g2, sw_normal=sw_n, sw_packaged=sw_pk, sw_corr=sw_corr)
+    np.savez_compressed(os.path.join(HERE, "upwind_penalty.npz"), **out)
+    print("wrote upwind_penalty.npz")
+
+
+if __name__ == "__main__":
+    main()
