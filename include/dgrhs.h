@@ -1,0 +1,187 @@
+/*
+ * dgrhs.h -- C-ABI of the B200-native DG evolution right-hand side.
+ *
+ * This is the drop-in boundary for ONE path of SpECTRE (reference checkout
+ * v2024.09.29, paths relative to its root): per-element volume time derivative
+ * + boundary corrections + lift + time-stepper substep for the ScalarWave and
+ * GeneralizedHarmonic systems on Mesh<3>.
+ *
+ * Conventions
+ *  - every entry point returns 0 on success; on failure it returns non-zero and
+ *    dgrhs_last_error() holds a message.  The reference has no error codes on
+ *    this path (ASSERT/ERROR abort, Utilities/ErrorHandling/Error.hpp:68-77);
+ *    the C++ shims in spectre_b200/host/ turn non-zero into an exception.
+ *  - plain pointers and sizes only.  "host" pointers are ordinary host memory
+ *    in the reference's Variables layout (DataStructures/Variables.hpp:94-160):
+ *    per element one contiguous block, component-major, n = N^3 points per
+ *    component, grid index i + N*(j + N*k).  Tensor component order follows
+ *    Tensor/Structure.hpp:162-194 (see DESIGN.md "Data layout").
+ *  - evolved variables per point: ScalarWave 5 (Psi, Pi, Phi_i), GH 50
+ *    (g_ab 10, Pi_ab 10, Phi_iab 30).
+ *  - the library owns all device memory; element data stays resident in HBM.
+ *  - one context per GPU, driven from one host thread (the reference runs one
+ *    element per Charm++ PE, single-threaded: SURVEY.md 8b "Threading").
+ */
+#ifndef DGRHS_H
+#define DGRHS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dgrhs_ctx dgrhs_ctx;
+
+enum { DGRHS_SYSTEM_SCALAR_WAVE = 0, DGRHS_SYSTEM_GH = 1 };
+
+/* gh::gauges::GaugeCondition subclasses
+ * (Evolution/Systems/GeneralizedHarmonic/GaugeSourceFunctions/) */
+enum {
+  DGRHS_GAUGE_HARMONIC = 0,        /* Harmonic.cpp:25-39 */
+  DGRHS_GAUGE_FIELDS = 1,          /* H_a, d_a H_b supplied as per-point fields:
+                                      AnalyticChristoffel.cpp:64-149 evaluated by
+                                      the host (static solutions) */
+  DGRHS_GAUGE_DAMPED_HARMONIC = 2, /* DampedHarmonic.cpp:70-439 */
+  DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE = 3 /* AnalyticChristoffel with the GaugeWave
+                                      solution, re-evaluated on the device at the
+                                      time of every RHS call */
+};
+
+/* TimeSteppers (Time/TimeSteppers/) */
+enum {
+  DGRHS_STEPPER_ADAMS_BASHFORTH = 0, /* AdamsBashforth.cpp:120-201, order 1..6 */
+  DGRHS_STEPPER_RK3_HESTHAVEN = 1    /* Rk3HesthavenSsp.cpp:55-81 */
+};
+
+const char* dgrhs_last_error(void);
+
+/* Number of CUDA kernels this library has launched in this process so far
+ * (bench.py reports the difference over the timed region). */
+int64_t dgrhs_kernel_launch_count(void);
+
+/* ---- context ----------------------------------------------------------- */
+
+/* Replaces the per-element DataBox of the reference's DgElementArray
+ * (Evolution/DiscontinuousGalerkin/DgElementArray.hpp:68-100) by one batched
+ * structure-of-arrays block per GPU.  n_points_1d = N of the isotropic
+ * Legendre-Gauss-Lobatto Mesh<3> (ComputeTimeDerivative.hpp:415-430 asserts the
+ * same restriction).  n_ghost_faces = number of mortar faces whose neighbour
+ * lives on another rank (0 for single GPU). */
+int dgrhs_create(dgrhs_ctx** ctx, int system, int n_points_1d, int n_elements,
+                 int n_ghost_faces, int device);
+int dgrhs_destroy(dgrhs_ctx* ctx);
+
+/* Geometry consumed (not computed) by the path, SURVEY.md 8 a22:
+ *  inv_jacobian: host [n_elements][9][n], component ihat + 3*i  (=
+ *     domain::Tags::InverseJacobian<3, ElementLogical, Inertial>, TypeAliases
+ *     .hpp:444-447)
+ *  coords: host [n_elements][3][n] inertial coordinates, or NULL when no
+ *     consumer needs them
+ *  neighbors: host [n_elements][6], direction d = 2*dim + side (side 0 = lower):
+ *     >= 0 local element index of the aligned, conforming neighbour
+ *     (Domain/Structure/Element.hpp neighbours + OrientationMap::is_aligned);
+ *     -1 external boundary (no correction); <= -2: ghost face -(value+2), whose
+ *     neighbour data arrive through the halo buffers below. */
+int dgrhs_set_geometry(dgrhs_ctx* ctx, const double* inv_jacobian,
+                       const double* coords, const int32_t* neighbors);
+
+/* Static per-point fields: ScalarWave: gamma2 (1 component,
+ * ScalarWave/Initialize.hpp:48-49); GH: gamma0, gamma1, gamma2 (3 components,
+ * GeneralizedHarmonic/Initialize.hpp:59-71).  host [n_elements][ncomp][n]. */
+int dgrhs_set_static_fields(dgrhs_ctx* ctx, const double* fields, int ncomp);
+
+/* GH gauge condition.  params: DAMPED_HARMONIC: {width, amp_L1, amp_L2, amp_S,
+ * exp_L1, exp_L2, exp_S}; ANALYTIC_GAUGE_WAVE: {amplitude, wavelength}. */
+int dgrhs_set_gauge(dgrhs_ctx* ctx, int gauge, const double* params, int nparams);
+/* DGRHS_GAUGE_FIELDS: gauge_h host [n_elements][4][n]; d4_gauge_h host
+ * [n_elements][16][n] with d_a H_b at component a + 4*b (tnsr::ab). */
+int dgrhs_set_gauge_fields(dgrhs_ctx* ctx, const double* gauge_h,
+                           const double* d4_gauge_h);
+
+/* Evolved variables, host [n_elements][n_vars][n] (Variables layout). */
+int dgrhs_set_state(dgrhs_ctx* ctx, const double* u);
+int dgrhs_get_state(dgrhs_ctx* ctx, double* u);
+/* Last computed time derivative (after boundary corrections), same layout. */
+int dgrhs_get_time_derivative(dgrhs_ctx* ctx, double* dt_u);
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/* = evolution::dg::Actions::ComputeTimeDerivative (ComputeTimeDerivative.hpp:
+ * 383-650: partial_derivatives + System::TimeDerivative::apply, face
+ * projection, normals, dg_package_data) followed by
+ * ApplyBoundaryCorrectionsToTimeDerivative (ApplyBoundaryCorrections.hpp:
+ * 1093-1126: dg_boundary_terms, lift_flux, add_slice_to_data) for every element
+ * of the batch.  volume_only != 0 skips the boundary corrections (unit tests). */
+int dgrhs_compute_time_derivative(dgrhs_ctx* ctx, double time, int volume_only);
+
+/* Multi-GPU split of the same call: elements [0, n_interior)
+ * have no ghost faces.  Sequence per RHS: pack_halo -> exchange (caller, NCCL)
+ * -> compute(interior) may overlap -> compute(boundary) after the exchange. */
+int dgrhs_set_interior_count(dgrhs_ctx* ctx, int n_interior);
+int dgrhs_pack_halo(dgrhs_ctx* ctx);
+int dgrhs_compute_time_derivative_range(dgrhs_ctx* ctx, double time,
+                                        int elem_begin, int elem_end);
+/* Device pointers of the halo buffers: send[n_ghost_faces][halo_comps][N^2]
+ * and recv (same shape); ghost_send_map host [n_ghost_faces][2] = {local
+ * element, direction} whose face is packed into slot i.  Static neighbour-side
+ * face data (inverse-Jacobian row, gamma1, gamma2) travel in the same slots, so
+ * one exchange per RHS suffices. */
+int dgrhs_set_halo_map(dgrhs_ctx* ctx, const int32_t* ghost_send_map);
+void* dgrhs_halo_send_ptr(dgrhs_ctx* ctx);
+void* dgrhs_halo_recv_ptr(dgrhs_ctx* ctx);
+int dgrhs_halo_comps(dgrhs_ctx* ctx);
+
+/* ---- time stepping (Time/TimeSteppers, Time/Actions) ------------------- */
+
+/* Selects the stepper and resets time to t0, step to dt.  For Adams-Bashforth
+ * of order k > 1 the history is built by the reference's forward self-start
+ * (Time/Actions/SelfStartActions.hpp:181-243,316-394) on the first step. */
+int dgrhs_set_stepper(dgrhs_ctx* ctx, int stepper, int order, double t0,
+                      double dt);
+/* Take n_steps full steps: per substep ComputeTimeDerivative,
+ * ApplyBoundaryCorrections, RecordTimeStepperData, UpdateU, CleanHistory,
+ * AdvanceTime (step_actions, EvolveScalarWave.hpp:229-253). */
+int dgrhs_take_steps(dgrhs_ctx* ctx, int n_steps);
+double dgrhs_time(dgrhs_ctx* ctx);
+int64_t dgrhs_rhs_evaluations(dgrhs_ctx* ctx);
+/* multi-GPU stepping in pieces: same as take_steps(1) but the caller drives
+ * the RHS (so it can interleave the halo exchange).  begin_substep returns in
+ * *time the time at which the RHS must be evaluated; end_substep records the
+ * derivative and updates u. is_step_done is set when a full step completed. */
+int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
+int dgrhs_end_substep(dgrhs_ctx* ctx, int* is_step_done);
+
+/* Synchronise the context's stream. */
+int dgrhs_synchronize(dgrhs_ctx* ctx);
+/* cudaStream_t used by the context (for CUDA-event timing by the caller). */
+void* dgrhs_stream(dgrhs_ctx* ctx);
+/* Device pointer to the evolved variables [n_elements][n_vars][n_padded] and
+ * the padded per-component stride. */
+void* dgrhs_state_device_ptr(dgrhs_ctx* ctx);
+int dgrhs_padded_points(dgrhs_ctx* ctx);
+
+/* ---- single-operator entry points (host pointers, one element) --------- *
+ * Thin GPU forwards for the reference's operator surface, used by the C++
+ * shims in spectre_b200/host/ and by the parity tests.                      */
+
+/* partial_derivatives (LinearOperators/PartialDerivatives.tpp:191-241):
+ * u [n_comps][n], inv_jacobian [9][n] -> du [3*n_comps][n], d_i u_c at 3c+i */
+int dgrhs_partial_derivatives(int n_points_1d, int n_comps, const double* u,
+                              const double* inv_jacobian, double* du);
+/* Spectral::differentiation_matrix(Mesh<1>{N, Legendre, GaussLobatto})
+ * (Spectral.cpp:431-445), row-major D[i*N + j]; collocation points/weights
+ * (Legendre.cpp:187-232). */
+int dgrhs_differentiation_matrix(int n_points_1d, double* matrix);
+int dgrhs_collocation_points_and_weights(int n_points_1d, double* points,
+                                         double* weights);
+/* adams_coefficients::coefficients (AdamsCoefficients.hpp:64-104,
+ * AdamsCoefficients.cpp:13-42,75-117): history times oldest first. */
+int dgrhs_adams_bashforth_coefficients(int order, const double* history_times,
+                                       double step_start, double step_end,
+                                       double* coefficients);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGRHS_H */

@@ -1,0 +1,832 @@
+// Host side of the C-ABI in include/dgrhs.h: context, kernel launchers,
+// spectral matrices, time steppers (Adams-Bashforth with the reference's
+// forward self-start, Rk3HesthavenSsp) and the single-operator entry points.
+// Reference citations are in include/dgrhs.h next to each entry point.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "../../include/dgrhs.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+int64_t g_launches = 0;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return 1;
+}
+
+#define CU(call)                                                            \
+  do {                                                                      \
+    cudaError_t err__ = (call);                                             \
+    if (err__ != cudaSuccess)                                               \
+      return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+                  __FILE__, __LINE__);                                      \
+  } while (0)
+
+#define CHECK_CTX(ctx) \
+  if (!(ctx)) return fail("null context")
+
+// ---------------------------------------------------------------------------
+// Spectral quantities: Legendre-Gauss-Lobatto nodes/weights (Kopriva Alg. 25,
+// reference Legendre.cpp:187-232), barycentric weights (Alg. 30, Spectral.cpp:
+// 84-104), differentiation matrix (Spectral.cpp:431-445).
+// ---------------------------------------------------------------------------
+void q_and_L(int deg, double x, double* q, double* L) {
+  double Lm2 = 1.0, Lm1 = x, Ln = x;
+  for (int k = 2; k <= deg; ++k) {
+    Ln = ((2.0 * k - 1.0) * x * Lm1 - (k - 1.0) * Lm2) / k;
+    Lm2 = Lm1;
+    Lm1 = Ln;
+  }
+  const int k = deg + 1;
+  const double Lp1 = ((2.0 * k - 1.0) * x * Ln - (k - 1.0) * Lm2) / k;
+  *q = Lp1 - Lm2;
+  *L = Ln;
+}
+
+void lgl(int num_points, std::vector<double>& x, std::vector<double>& w) {
+  const int deg = num_points - 1;
+  x.assign(num_points, 0.0);
+  w.assign(num_points, 0.0);
+  if (deg == 1) {
+    x[0] = -1.0;
+    x[1] = 1.0;
+    w[0] = w[1] = 1.0;
+    return;
+  }
+  x[0] = -1.0;
+  x[deg] = 1.0;
+  w[0] = w[deg] = 2.0 / (deg * (deg + 1.0));
+  for (int j = 1; j < (deg + 1) / 2; ++j) {
+    double lo = -cos((j - 0.25) * M_PI / deg - 0.375 / (deg * M_PI * (j - 0.25)));
+    double hi = -cos((j + 0.75) * M_PI / deg - 0.375 / (deg * M_PI * (j + 0.75)));
+    double flo, fhi, L;
+    q_and_L(deg, lo, &flo, &L);
+    q_and_L(deg, hi, &fhi, &L);
+    for (int it = 0; it < 200; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (mid == lo || mid == hi) break;
+      double fm;
+      q_and_L(deg, mid, &fm, &L);
+      if (fm == 0.0) {
+        lo = hi = mid;
+        break;
+      }
+      if ((fm < 0) == (flo < 0)) {
+        lo = mid;
+        flo = fm;
+      } else {
+        hi = mid;
+        fhi = fm;
+      }
+    }
+    const double root = 0.5 * (lo + hi);
+    double q;
+    q_and_L(deg, root, &q, &L);
+    x[j] = root;
+    x[deg - j] = -root;
+    w[j] = w[deg - j] = 2.0 / (deg * (deg + 1.0) * L * L);
+  }
+  if (deg % 2 == 0) {
+    double q, L;
+    q_and_L(deg, 0.0, &q, &L);
+    x[deg / 2] = 0.0;
+    w[deg / 2] = 2.0 / (deg * (deg + 1.0) * L * L);
+  }
+}
+
+void diff_matrix(int N, std::vector<double>& D) {
+  std::vector<double> x, w;
+  lgl(N, x, w);
+  std::vector<double> bw(N, 1.0);
+  for (int j = 1; j < N; ++j)
+    for (int k = 0; k < j; ++k) {
+      bw[k] *= x[k] - x[j];
+      bw[j] *= x[j] - x[k];
+    }
+  for (int j = 0; j < N; ++j) bw[j] = 1.0 / bw[j];
+  D.assign((size_t)N * N, 0.0);
+  for (int i = 0; i < N; ++i) {
+    double diag = 0.0;
+    for (int j = 0; j < N; ++j)
+      if (i != j) {
+        D[i * N + j] = bw[j] / (bw[i] * (x[i] - x[j]));
+        diag -= D[i * N + j];
+      }
+    D[i * N + i] = diag;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Adams-Bashforth coefficients (AdamsCoefficients.cpp:13-42, :75-117)
+// ---------------------------------------------------------------------------
+const double kAbConst[7][6] = {
+    {},
+    {1.0},
+    {-0.5, 1.5},
+    {5.0 / 12.0, -4.0 / 3.0, 23.0 / 12.0},
+    {-3.0 / 8.0, 37.0 / 24.0, -59.0 / 24.0, 55.0 / 24.0},
+    {251.0 / 720.0, -637.0 / 360.0, 109.0 / 30.0, -1387.0 / 360.0, 1901.0 / 720.0},
+    {-95.0 / 288.0, 959.0 / 480.0, -3649.0 / 720.0, 4991.0 / 720.0, -2641.0 / 480.0,
+     4277.0 / 1440.0}};
+
+std::vector<double> variable_coefficients(std::vector<double> ct, double step_start,
+                                          double step_end) {
+  for (auto& t : ct) t -= step_start;
+  const size_t order = ct.size();
+  std::vector<double> result;
+  for (size_t j = 0; j < order; ++j) {
+    std::vector<double> poly(order, 0.0);
+    poly[0] = 1.0;
+    for (size_t m = 0; m < order; ++m) {
+      if (m == j) continue;
+      const double denom = 1.0 / (ct[j] - ct[m]);
+      for (size_t i = m < j ? m + 1 : m; i > 0; --i)
+        poly[i] = (poly[i - 1] - poly[i] * ct[m]) * denom;
+      poly[0] *= -ct[m] * denom;
+    }
+    for (size_t m = 0; m < order; ++m) poly[m] /= (double)(m + 1);
+    const double dt = step_end - step_start;
+    double val = 0.0;
+    for (size_t m = order; m-- > 0;) val = val * dt + poly[m];
+    result.push_back(dt * val);
+  }
+  return result;
+}
+
+// times in integer ticks of dt/tick_den
+std::vector<double> ab_coefficients_ticks(const std::vector<long long>& ticks,
+                                          long long start, long long end,
+                                          long long tick_den, double dt) {
+  const size_t order = ticks.size();
+  bool uniform = ticks.back() == start;
+  for (size_t i = 0; i + 1 < order; ++i)
+    if (ticks[i + 1] - ticks[i] != end - start) uniform = false;
+  auto frac = [&](long long t) { return (double)t / (double)tick_den; };
+  if (uniform) {
+    std::vector<double> c(order);
+    for (size_t i = 0; i < order; ++i) c[i] = kAbConst[order][i] * (frac(end - start) * dt);
+    return c;
+  }
+  std::vector<double> control{0.0};
+  for (size_t i = 0; i + 1 < order; ++i)
+    control.push_back(control.back() + frac(ticks[i + 1] - ticks[i]) * dt);
+  return variable_coefficients(control, control.back() + frac(start - ticks.back()) * dt,
+                               control.back() + frac(end - ticks.back()) * dt);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct HistoryEntry {
+  long long tick;
+  int slot;
+};
+
+struct SubstepOp {
+  enum Kind { kAbStep, kAbEvalOnly, kRestoreU0 } kind;
+  int order;
+  long long tick, tick_end;
+  bool regular = false;  // a step of the evolution proper (not self-start)
+};
+
+struct dgrhs_ctx {
+  int system = 0, N = 0, nelem = 0, nghost = 0, device = 0;
+  int C = 0, S = 0, HC = 0, n = 0, npad = 0, f = 0;
+  int n_interior = -1;
+  cudaStream_t stream = nullptr;
+  double *u = nullptr, *invjac = nullptr, *coords = nullptr, *stat = nullptr;
+  double *corr = nullptr, *D = nullptr, *gH = nullptr, *gdH = nullptr;
+  double *halo_send = nullptr, *halo_recv = nullptr;
+  int32_t *nbr = nullptr, *halo_map = nullptr;
+  std::vector<double*> dt_slots;  // derivative buffers (history ring)
+  double* u0 = nullptr;           // saved value (self-start / RK step start)
+  double* dt_last = nullptr;
+  int gauge = DGRHS_GAUGE_HARMONIC;
+  double gauge_params[8] = {0};
+  // stepping
+  int stepper = DGRHS_STEPPER_ADAMS_BASHFORTH, order = 1;
+  double t0 = 0.0, dt = 0.0;
+  long long tick_den = 1, step_index = 0;
+  std::deque<HistoryEntry> history;
+  std::deque<SubstepOp> pending;  // self-start program
+  std::vector<int> free_slots;
+  int rk_substep = 0;
+  int cur_slot = -1;
+  SubstepOp cur_op{};
+  bool in_substep = false;
+  int64_t rhs_evals = 0;
+  size_t state_len() const { return (size_t)nelem * C * npad; }
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+  CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  return 0;
+}
+
+// host [E][ncomp][n] <-> device [E][ncomp][npad]
+int upload(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
+  CU(cudaMemcpy2DAsync(dst, (size_t)c->npad * 8, src, (size_t)c->n * 8, (size_t)c->n * 8,
+                       (size_t)c->nelem * ncomp, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int download(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
+  CU(cudaMemcpy2DAsync(dst, (size_t)c->n * 8, src, (size_t)c->npad * 8, (size_t)c->n * 8,
+                       (size_t)c->nelem * ncomp, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+#define DG_FOR_EACH_N(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+
+template <int N>
+int launch_faces(dgrhs_ctx* c, int eb, int ee) {
+  if (ee <= eb) return 0;
+  dg::FaceArgs a{c->u, c->invjac, c->stat, c->nbr, c->halo_recv, c->corr, eb, ee};
+  const long long total = (long long)(ee - eb) * 6 * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  else
+    dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_gauge(dgrhs_ctx* c, double time) {
+  if (c->gauge != DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE) return 0;
+  if (!c->coords) return fail("AnalyticChristoffel(GaugeWave) gauge needs coordinates");
+  dg::GaugeWaveArgs g{c->coords, c->gH, c->gauge_params[0], c->gauge_params[1], time,
+                      c->nelem};
+  const long long total = (long long)c->nelem * c->n;
+  dg::gauge_wave_h_kernel<N><<<(int)((total + 255) / 256), 256, 0, c->stream>>>(g);
+  ++g_launches;
+  CU(cudaGetLastError());
+  // spatial derivative d_i H_b -> gdH component (i+1) + 4 b; d_0 H_b stays 0
+  dg::DerivArgs d{c->gH, c->invjac, c->gdH, c->D, 4, 16, 1, 4};
+  dg::partial_derivatives_kernel<N><<<c->nelem * 4, 256, 0, c->stream>>>(d);
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr) {
+  if (ee <= eb) return 0;
+  const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
+  if (c->system == DGRHS_SYSTEM_GH) {
+    dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
+                    c->gH, c->gdH, c->D, eb};
+    constexpr int smem = dg::gh_volume_smem_bytes<N>();
+    if (c->gauge == DGRHS_GAUGE_HARMONIC) {
+      auto k = dg::gh_volume_kernel<N, true>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+    } else {
+      auto k = dg::gh_volume_kernel<N, false>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+    }
+  } else {
+    dg::SwVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr, c->D, eb};
+    constexpr int smem = dg::sw_volume_smem_bytes<N>();
+    auto k = dg::sw_volume_kernel<N>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+  }
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_pack(dgrhs_ctx* c) {
+  if (c->nghost == 0) return 0;
+  dg::PackArgs a{c->u, c->invjac, c->stat, c->halo_map, c->halo_send, c->nghost};
+  const long long total = (long long)c->nghost * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::pack_halo_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(a);
+  else
+    dg::pack_halo_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(a);
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume_only,
+              bool do_gauge) {
+  if (c->system == DGRHS_SYSTEM_GH && c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC)
+    return fail("DampedHarmonic gauge is not implemented yet");
+  switch (c->N) {
+#define X(NN)                                                        \
+  case NN:                                                           \
+    if (do_gauge && launch_gauge<NN>(c, time)) return 1;             \
+    if (!volume_only && launch_faces<NN>(c, eb, ee)) return 1;       \
+    return launch_volume<NN>(c, dt, eb, ee, !volume_only);
+    DG_FOR_EACH_N(X)
+#undef X
+    default:
+      return fail("unsupported number of grid points per dimension: %d", c->N);
+  }
+}
+
+int lincomb(dgrhs_ctx* c, double* u, double a, const std::vector<double>& coef,
+            const std::vector<const double*>& v) {
+  if (coef.size() > 8) return fail("too many terms in linear combination");
+  dg::LincombArgs p;
+  p.u = u;
+  p.a = a;
+  p.nterms = (int)coef.size();
+  for (size_t i = 0; i < coef.size(); ++i) {
+    p.c[i] = coef[i];
+    p.v[i] = v[i];
+  }
+  p.len2 = (long long)(c->state_len() / 2);
+  const int blocks = (int)std::min<long long>((p.len2 + 255) / 256, 148LL * 16);
+  dg::lincomb_kernel<<<blocks, 256, 0, c->stream>>>(p);
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int ensure_slots(dgrhs_ctx* c, int count) {
+  while ((int)c->dt_slots.size() < count) {
+    double* p = nullptr;
+    if (dev_alloc(&p, c->state_len())) return 1;
+    c->free_slots.push_back((int)c->dt_slots.size());
+    c->dt_slots.push_back(p);
+  }
+  return 0;
+}
+
+void ab_clean(dgrhs_ctx* c, int order) {
+  while ((int)c->history.size() >= order) {
+    c->free_slots.push_back(c->history.front().slot);
+    c->history.pop_front();
+  }
+}
+
+int ab_update(dgrhs_ctx* c, int order, long long start, long long end) {
+  std::vector<long long> ticks;
+  std::vector<const double*> v;
+  const size_t h = c->history.size();
+  for (size_t i = h - order; i < h; ++i) {
+    ticks.push_back(c->history[i].tick);
+    v.push_back(c->dt_slots[c->history[i].slot]);
+  }
+  const auto coef = ab_coefficients_ticks(ticks, start, end, c->tick_den, c->dt);
+  return lincomb(c, c->u, 1.0, coef, v);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* dgrhs_last_error(void) { return g_error.c_str(); }
+int64_t dgrhs_kernel_launch_count(void) { return g_launches; }
+
+int dgrhs_create(dgrhs_ctx** out, int system, int N, int nelem, int nghost, int device) {
+  if (!out) return fail("null output pointer");
+  if (system != DGRHS_SYSTEM_SCALAR_WAVE && system != DGRHS_SYSTEM_GH)
+    return fail("unknown system %d", system);
+  if (N < 2 || N > 12) return fail("n_points_1d must be in [2, 12], got %d", N);
+  if (nelem < 1) return fail("n_elements must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available: this library has no CPU fallback");
+  CU(cudaSetDevice(device));
+  dgrhs_ctx* c = new dgrhs_ctx();
+  c->system = system;
+  c->N = N;
+  c->nelem = nelem;
+  c->nghost = nghost;
+  c->device = device;
+  c->C = system == DGRHS_SYSTEM_GH ? 50 : 5;
+  c->S = system == DGRHS_SYSTEM_GH ? 3 : 1;
+  c->HC = c->C + 3 + (system == DGRHS_SYSTEM_GH ? 2 : 1);
+  c->n = N * N * N;
+  c->f = N * N;
+  c->npad = dg::padded_points(N);
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (dev_alloc(&c->u, c->state_len())) return 1;
+  if (dev_alloc(&c->invjac, (size_t)nelem * 9 * c->npad)) return 1;
+  if (dev_alloc(&c->stat, (size_t)nelem * c->S * c->npad)) return 1;
+  if (dev_alloc(&c->corr, (size_t)nelem * 6 * c->C * c->f)) return 1;
+  if (dev_alloc(&c->nbr, (size_t)nelem * 6)) return 1;
+  if (dev_alloc(&c->D, (size_t)N * N)) return 1;
+  if (nghost > 0) {
+    if (dev_alloc(&c->halo_send, (size_t)nghost * c->HC * c->f)) return 1;
+    if (dev_alloc(&c->halo_recv, (size_t)nghost * c->HC * c->f)) return 1;
+    if (dev_alloc(&c->halo_map, (size_t)nghost * 2)) return 1;
+  }
+  std::vector<double> D;
+  diff_matrix(N, D);
+  CU(cudaMemcpy(c->D, D.data(), D.size() * 8, cudaMemcpyHostToDevice));
+  std::vector<int32_t> nb((size_t)nelem * 6, -1);
+  CU(cudaMemcpy(c->nbr, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice));
+  if (ensure_slots(c, 1)) return 1;
+  c->dt_last = c->dt_slots[0];
+  *out = c;
+  return 0;
+}
+
+int dgrhs_destroy(dgrhs_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (double* p : {c->u, c->invjac, c->coords, c->stat, c->corr, c->D, c->gH, c->gdH,
+                    c->halo_send, c->halo_recv, c->u0})
+    if (p) cudaFree(p);
+  for (double* p : c->dt_slots) cudaFree(p);
+  if (c->nbr) cudaFree(c->nbr);
+  if (c->halo_map) cudaFree(c->halo_map);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* coords,
+                       const int32_t* neighbors) {
+  CHECK_CTX(c);
+  if (!inv_jacobian || !neighbors) return fail("inv_jacobian and neighbors are required");
+  CU(cudaSetDevice(c->device));
+  for (size_t i = 0; i < (size_t)c->nelem * 6; ++i) {
+    const int v = neighbors[i];
+    if (v >= c->nelem) return fail("neighbor index %d out of range", v);
+    if (v <= -2 && -(v + 2) >= c->nghost) return fail("ghost face index out of range");
+  }
+  if (upload(c, c->invjac, inv_jacobian, 9)) return 1;
+  if (coords) {
+    if (!c->coords && dev_alloc(&c->coords, (size_t)c->nelem * 3 * c->npad)) return 1;
+    if (upload(c, c->coords, coords, 3)) return 1;
+  }
+  CU(cudaMemcpy(c->nbr, neighbors, (size_t)c->nelem * 6 * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dgrhs_set_static_fields(dgrhs_ctx* c, const double* fields, int ncomp) {
+  CHECK_CTX(c);
+  if (ncomp != c->S) return fail("expected %d static components, got %d", c->S, ncomp);
+  CU(cudaSetDevice(c->device));
+  return upload(c, c->stat, fields, ncomp);
+}
+
+int dgrhs_set_gauge(dgrhs_ctx* c, int gauge, const double* params, int nparams) {
+  CHECK_CTX(c);
+  if (c->system != DGRHS_SYSTEM_GH) return fail("gauge conditions only apply to GH");
+  if (gauge < 0 || gauge > 3) return fail("unknown gauge %d", gauge);
+  if (nparams > 8) return fail("too many gauge parameters");
+  CU(cudaSetDevice(c->device));
+  c->gauge = gauge;
+  for (int i = 0; i < nparams; ++i) c->gauge_params[i] = params[i];
+  if (gauge != DGRHS_GAUGE_HARMONIC && !c->gH) {
+    if (dev_alloc(&c->gH, (size_t)c->nelem * 4 * c->npad)) return 1;
+    if (dev_alloc(&c->gdH, (size_t)c->nelem * 16 * c->npad)) return 1;
+  }
+  if (gauge == DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE && nparams != 2)
+    return fail("AnalyticChristoffel(GaugeWave) needs {amplitude, wavelength}");
+  return 0;
+}
+
+int dgrhs_set_gauge_fields(dgrhs_ctx* c, const double* H, const double* dH) {
+  CHECK_CTX(c);
+  if (c->gauge != DGRHS_GAUGE_FIELDS) return fail("gauge is not DGRHS_GAUGE_FIELDS");
+  CU(cudaSetDevice(c->device));
+  if (upload(c, c->gH, H, 4)) return 1;
+  return upload(c, c->gdH, dH, 16);
+}
+
+int dgrhs_set_state(dgrhs_ctx* c, const double* u) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  return upload(c, c->u, u, c->C);
+}
+int dgrhs_get_state(dgrhs_ctx* c, double* u) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  return download(c, u, c->u, c->C);
+}
+int dgrhs_get_time_derivative(dgrhs_ctx* c, double* dt_u) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  return download(c, dt_u, c->dt_last, c->C);
+}
+
+int dgrhs_compute_time_derivative(dgrhs_ctx* c, double time, int volume_only) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (c->nghost > 0 && !volume_only)
+    return fail("context has ghost faces: use pack_halo + compute_time_derivative_range");
+  ++c->rhs_evals;
+  return rhs_range(c, time, c->dt_last, 0, c->nelem, volume_only != 0, true);
+}
+
+int dgrhs_set_interior_count(dgrhs_ctx* c, int n_interior) {
+  CHECK_CTX(c);
+  if (n_interior < 0 || n_interior > c->nelem) return fail("bad interior count");
+  c->n_interior = n_interior;
+  return 0;
+}
+
+int dgrhs_set_halo_map(dgrhs_ctx* c, const int32_t* map) {
+  CHECK_CTX(c);
+  if (c->nghost == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  for (int i = 0; i < c->nghost; ++i)
+    if (map[2 * i] < 0 || map[2 * i] >= c->nelem || map[2 * i + 1] < 0 || map[2 * i + 1] > 5)
+      return fail("bad halo map entry %d", i);
+  CU(cudaMemcpy(c->halo_map, map, (size_t)c->nghost * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dgrhs_pack_halo(dgrhs_ctx* c) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  switch (c->N) {
+#define X(NN) \
+  case NN:    \
+    return launch_pack<NN>(c);
+    DG_FOR_EACH_N(X)
+#undef X
+  }
+  return fail("unsupported N");
+}
+
+int dgrhs_compute_time_derivative_range(dgrhs_ctx* c, double time, int eb, int ee) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (eb < 0 || ee > c->nelem || eb > ee) return fail("bad element range");
+  if (eb == 0) ++c->rhs_evals;
+  return rhs_range(c, time, c->dt_last, eb, ee, false, eb == 0);
+}
+
+void* dgrhs_halo_send_ptr(dgrhs_ctx* c) { return c ? c->halo_send : nullptr; }
+void* dgrhs_halo_recv_ptr(dgrhs_ctx* c) { return c ? c->halo_recv : nullptr; }
+int dgrhs_halo_comps(dgrhs_ctx* c) { return c ? c->HC : 0; }
+
+// ---- time stepping --------------------------------------------------------
+
+int dgrhs_set_stepper(dgrhs_ctx* c, int stepper, int order, double t0, double dt) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
+    if (order < 1 || order > 6) return fail("Adams-Bashforth order must be in [1, 6]");
+  } else if (stepper == DGRHS_STEPPER_RK3_HESTHAVEN) {
+    order = 3;
+  } else {
+    return fail("unknown stepper %d", stepper);
+  }
+  c->stepper = stepper;
+  c->order = order;
+  c->t0 = t0;
+  c->dt = dt;
+  c->step_index = 0;
+  c->rk_substep = 0;
+  c->in_substep = false;
+  c->history.clear();
+  c->pending.clear();
+  c->free_slots.clear();
+  for (int i = 0; i < (int)c->dt_slots.size(); ++i) c->free_slots.push_back(i);
+  if (!c->u0 && dev_alloc(&c->u0, c->state_len())) return 1;
+  if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
+    c->tick_den = order;
+    if (ensure_slots(c, order)) return 1;
+    // forward self-start program (SelfStartActions.hpp; see oracle/oracle.py
+    // Evolution._self_start for the trace of the action list)
+    if (order > 1) {
+      for (int o = 1; o < order; ++o) {
+        c->pending.push_back({SubstepOp::kRestoreU0, o, 0, 0});
+        for (int s = 0; s <= o; ++s) {
+          if (s == o)
+            c->pending.push_back({SubstepOp::kAbEvalOnly, o, (long long)s, 0});
+          else
+            c->pending.push_back({SubstepOp::kAbStep, o, (long long)s, (long long)s + 1});
+        }
+      }
+      c->pending.push_back({SubstepOp::kRestoreU0, order, 0, 0});
+      CU(cudaMemcpyAsync(c->u0, c->u, c->state_len() * 8, cudaMemcpyDeviceToDevice,
+                         c->stream));
+    }
+  } else {
+    c->tick_den = 2;
+    if (ensure_slots(c, 1)) return 1;
+  }
+  return 0;
+}
+
+int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (c->in_substep) return fail("begin_substep called twice");
+  if (c->dt == 0.0) return fail("set_stepper has not been called");
+  if (c->stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
+    while (!c->pending.empty() && c->pending.front().kind == SubstepOp::kRestoreU0) {
+      CU(cudaMemcpyAsync(c->u, c->u0, c->state_len() * 8, cudaMemcpyDeviceToDevice,
+                         c->stream));
+      c->pending.pop_front();
+    }
+    if (!c->pending.empty()) {
+      c->cur_op = c->pending.front();
+      c->pending.pop_front();
+    } else {
+      const long long t = c->step_index * c->tick_den;
+      c->cur_op = {SubstepOp::kAbStep, c->order, t, t + c->tick_den, true};
+    }
+    if (c->free_slots.empty()) return fail("internal error: no free history slot");
+    c->cur_slot = c->free_slots.back();
+    c->free_slots.pop_back();
+    c->dt_last = c->dt_slots[c->cur_slot];
+    *time = c->t0 + ((double)c->cur_op.tick / (double)c->tick_den) * c->dt;
+  } else {
+    const long long base = c->step_index * 2;
+    const long long off[3] = {0, 2, 1};  // substep times t, t+dt, t+dt/2
+    c->cur_slot = 0;
+    c->dt_last = c->dt_slots[0];
+    *time = c->t0 + ((double)(base + off[c->rk_substep]) / 2.0) * c->dt;
+  }
+  c->in_substep = true;
+  return 0;
+}
+
+int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (!c->in_substep) return fail("end_substep without begin_substep");
+  c->in_substep = false;
+  int done = 0;
+  if (c->stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
+    const SubstepOp op = c->cur_op;
+    c->history.push_back({op.tick, c->cur_slot});  // RecordTimeStepperData
+    if (op.kind == SubstepOp::kAbEvalOnly) {
+      ab_clean(c, op.order + 1);  // history order was bumped, UpdateU skipped
+    } else {
+      if (ab_update(c, op.order, op.tick, op.tick_end)) return 1;  // UpdateU
+      ab_clean(c, op.order);                                       // CleanHistory
+      if (op.regular) {
+        ++c->step_index;
+        done = 1;
+      }
+    }
+  } else {
+    const double dt = c->dt;
+    const double* F = c->dt_slots[0];
+    // Rk3HesthavenSsp.cpp:63-81
+    if (c->rk_substep == 0) {
+      CU(cudaMemcpyAsync(c->u0, c->u, c->state_len() * 8, cudaMemcpyDeviceToDevice,
+                         c->stream));
+      if (lincomb(c, c->u, 1.0, {dt}, {F})) return 1;
+      c->rk_substep = 1;
+    } else if (c->rk_substep == 1) {
+      if (lincomb(c, c->u, 0.25, {0.75, 0.25 * dt}, {c->u0, F})) return 1;
+      c->rk_substep = 2;
+    } else {
+      if (lincomb(c, c->u, 2.0 / 3.0, {1.0 / 3.0, (2.0 / 3.0) * dt}, {c->u0, F})) return 1;
+      c->rk_substep = 0;
+      ++c->step_index;
+      done = 1;
+    }
+  }
+  if (is_step_done) *is_step_done = done;
+  return 0;
+}
+
+int dgrhs_take_steps(dgrhs_ctx* c, int n_steps) {
+  CHECK_CTX(c);
+  if (c->nghost > 0) return fail("context has ghost faces: drive substeps from the caller");
+  for (int s = 0; s < n_steps;) {
+    double t;
+    int done = 0;
+    if (dgrhs_begin_substep(c, &t)) return 1;
+    ++c->rhs_evals;
+    if (rhs_range(c, t, c->dt_last, 0, c->nelem, false, true)) return 1;
+    if (dgrhs_end_substep(c, &done)) return 1;
+    if (done) ++s;
+  }
+  return 0;
+}
+
+double dgrhs_time(dgrhs_ctx* c) { return c ? c->t0 + (double)c->step_index * c->dt : 0.0; }
+int64_t dgrhs_rhs_evaluations(dgrhs_ctx* c) { return c ? c->rhs_evals : 0; }
+
+int dgrhs_synchronize(dgrhs_ctx* c) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+void* dgrhs_stream(dgrhs_ctx* c) { return c ? (void*)c->stream : nullptr; }
+void* dgrhs_state_device_ptr(dgrhs_ctx* c) { return c ? c->u : nullptr; }
+int dgrhs_padded_points(dgrhs_ctx* c) { return c ? c->npad : 0; }
+
+// ---- single-operator entry points ----------------------------------------
+
+int dgrhs_differentiation_matrix(int N, double* matrix) {
+  if (N < 2) return fail("need at least two LGL points");
+  std::vector<double> D;
+  diff_matrix(N, D);
+  std::memcpy(matrix, D.data(), D.size() * 8);
+  return 0;
+}
+
+int dgrhs_collocation_points_and_weights(int N, double* points, double* weights) {
+  if (N < 2) return fail("need at least two LGL points");
+  std::vector<double> x, w;
+  lgl(N, x, w);
+  std::memcpy(points, x.data(), N * 8);
+  std::memcpy(weights, w.data(), N * 8);
+  return 0;
+}
+
+int dgrhs_adams_bashforth_coefficients(int order, const double* times, double step_start,
+                                       double step_end, double* coefficients) {
+  if (order < 1 || order > 6) return fail("order must be in [1, 6]");
+  const double step = step_end - step_start;
+  bool constant = true;
+  std::vector<double> control{0.0};
+  for (int i = 1; i < order; ++i) {
+    const double this_step = times[i] - times[i - 1];
+    control.push_back(control.back() + this_step);
+    // slab_rounding_error: a few ulp of the larger of |t| and the step
+    if (std::abs(this_step - step) >
+        4.0 * 2.220446049250313e-16 * std::max(std::abs(times[i]), std::abs(step)))
+      constant = false;
+  }
+  std::vector<double> r;
+  if (constant && step_start == times[order - 1]) {
+    for (int i = 0; i < order; ++i) r.push_back(kAbConst[order][i] * step);
+  } else {
+    r = variable_coefficients(control, control.back() + (step_start - times[order - 1]),
+                              control.back() + (step_end - times[order - 1]));
+  }
+  std::memcpy(coefficients, r.data(), order * 8);
+  return 0;
+}
+
+int dgrhs_partial_derivatives(int N, int C, const double* u, const double* invjac,
+                              double* du) {
+  if (N < 2 || N > 12) return fail("n_points_1d must be in [2, 12]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available: this library has no CPU fallback");
+  const int n = N * N * N, npad = dg::padded_points(N);
+  double *du_d = nullptr, *u_d = nullptr, *j_d = nullptr, *D_d = nullptr;
+  if (dev_alloc(&u_d, (size_t)C * npad) || dev_alloc(&j_d, (size_t)9 * npad) ||
+      dev_alloc(&du_d, (size_t)3 * C * npad) || dev_alloc(&D_d, (size_t)N * N))
+    return 1;
+  std::vector<double> D;
+  diff_matrix(N, D);
+  CU(cudaMemcpy(D_d, D.data(), D.size() * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy2D(u_d, (size_t)npad * 8, u, (size_t)n * 8, (size_t)n * 8, C,
+                  cudaMemcpyHostToDevice));
+  CU(cudaMemcpy2D(j_d, (size_t)npad * 8, invjac, (size_t)n * 8, (size_t)n * 8, 9,
+                  cudaMemcpyHostToDevice));
+  dg::DerivArgs a{u_d, j_d, du_d, D_d, C, 3 * C, 0, 3};
+  switch (N) {
+#define X(NN)                                                      \
+  case NN:                                                         \
+    dg::partial_derivatives_kernel<NN><<<C, 256>>>(a);             \
+    break;
+    DG_FOR_EACH_N(X)
+#undef X
+  }
+  ++g_launches;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy2D(du, (size_t)n * 8, du_d, (size_t)npad * 8, (size_t)n * 8, 3 * C,
+                  cudaMemcpyDeviceToHost));
+  cudaFree(u_d);
+  cudaFree(j_d);
+  cudaFree(du_d);
+  cudaFree(D_d);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,679 @@
+// CUDA kernels of the DG right-hand side for sm_100a.
+//
+// Data layout in HBM (all fp64): every per-point field of the batch is a
+// structure-of-arrays block  [element][component][npad]  with npad = N^3
+// rounded up to a multiple of 16 doubles (128 B), so that every component row
+// is 128-byte aligned: legal source for TMA bulk copies (cp.async.bulk needs
+// 16 B) and for 128-bit vector accesses.  Within a row the grid index is
+// i + N*(j + N*k) exactly as in the reference's Variables (xi fastest).
+//
+// Kernels (reference call sites: SURVEY.md 2.2 K1-K13):
+//   face_kernel      K5-K8,K10,K11  both sides of every mortar are packaged in
+//                    registers from the raw face values; the lifted correction
+//                    goes to a compact buffer corr[element][6][C][N^2]
+//   gh/sw_volume     K1-K3 fused: TMA-staged element tiles, sum-factorised
+//                    logical derivatives from shared memory, Jacobian folded
+//                    into the pointwise coefficients, corr added on face points,
+//                    dt_u written once
+//   lincomb_kernel   K12-K13: u <- a u + sum c_j v_j, 128-bit vectorised
+//   pack_halo        face slices for neighbours on other GPUs
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pointwise.cuh"
+
+namespace dg {
+
+// --------------------------------------------------------------------------
+// configuration
+// --------------------------------------------------------------------------
+template <int N>
+struct Cfg {
+  static constexpr int n = N * N * N;
+  static constexpr int f = N * N;
+  static constexpr int npad = (n + 15) / 16 * 16;
+  // volume kernel: one CTA per (element, chunk of <= 256 points)
+  static constexpr int nchunk = (n + 255) / 256;
+  static constexpr int T = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
+};
+
+__host__ __device__ constexpr int padded_points(int N) {
+  return (N * N * N + 15) / 16 * 16;
+}
+
+// volume index of face point (qa, qb) of direction d = 2*dim + side
+template <int N>
+__device__ __forceinline__ int face_point(int d, int qa, int qb) {
+  const int dim = d >> 1;
+  const int fixed = (d & 1) ? N - 1 : 0;
+  return dim == 0 ? fixed + N * (qa + N * qb)
+                  : dim == 1 ? qa + N * (fixed + N * qb) : qa + N * (qb + N * fixed);
+}
+
+// --------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src,
+                                             uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// --------------------------------------------------------------------------
+// sum-factorised logical derivatives of one component at one point from a
+// shared-memory tile (K1: PartialDerivatives.tpp:316-363 without the
+// transposes; the three "GEMMs" are N-term dot products along the grid lines)
+// --------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void logical_derivs(const double* __restrict__ tc,
+                                               int i, int j, int k,
+                                               const double (&Di)[N],
+                                               const double (&Dj)[N],
+                                               const double (&Dk)[N],
+                                               double (&d)[3]) {
+  const double* row = tc + N * (j + N * k);
+  const double* col = tc + i + N * N * k;
+  const double* pil = tc + i + N * j;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+  if constexpr (N % 2 == 0) {
+    const double2* row2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+      const double2 v = row2[m];
+      d0 = fma(Di[2 * m], v.x, d0);
+      d0 = fma(Di[2 * m + 1], v.y, d0);
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < N; ++m) d0 = fma(Di[m], row[m], d0);
+  }
+#pragma unroll
+  for (int m = 0; m < N; ++m) d1 = fma(Dj[m], col[N * m], d1);
+#pragma unroll
+  for (int m = 0; m < N; ++m) d2 = fma(Dk[m], pil[N * N * m], d2);
+  d[0] = d0;
+  d[1] = d1;
+  d[2] = d2;
+}
+
+// lifted boundary corrections of the faces this point lies on, added in
+// direction order 0..5 (add_slice_to_data, ApplyBoundaryCorrections.hpp:
+// 1038-1043; the reference's order is a hash-map order, i.e. unspecified)
+template <int N, int C>
+__device__ __forceinline__ double add_corrections(double v,
+                                                  const double* __restrict__ corr_e,
+                                                  int comp, int i, int j, int k) {
+  constexpr int f = N * N;
+  if (i == 0) v += corr_e[(0 * C + comp) * f + j + N * k];
+  if (i == N - 1) v += corr_e[(1 * C + comp) * f + j + N * k];
+  if (j == 0) v += corr_e[(2 * C + comp) * f + i + N * k];
+  if (j == N - 1) v += corr_e[(3 * C + comp) * f + i + N * k];
+  if (k == 0) v += corr_e[(4 * C + comp) * f + i + N * j];
+  if (k == N - 1) v += corr_e[(5 * C + comp) * f + i + N * j];
+  return v;
+}
+
+// --------------------------------------------------------------------------
+// GH volume kernel (K1+K2+K3+K11-add fused)
+// --------------------------------------------------------------------------
+struct GhVolArgs {
+  const double* u;       // [E][50][npad]
+  double* dt;            // [E][50][npad]
+  const double* invjac;  // [E][9][npad]
+  const double* stat;    // [E][3][npad]   gamma0, gamma1, gamma2
+  const double* corr;    // [E][6][50][f] or nullptr (volume only)
+  const double* gH;      // [E][4][npad]   gauge H_a      (non-harmonic)
+  const double* gdH;     // [E][16][npad]  d_a H_b, a+4b  (non-harmonic)
+  const double* D;       // [N*N] row-major differentiation matrix
+  int elem_begin;
+};
+
+template <int N>
+constexpr int gh_volume_smem_bytes() {
+  return (2 * 5 * Cfg<N>::npad + 10 * Cfg<N>::T + (N * N + 1) / 2 * 2) * 8 + 2 * 8;
+}
+
+template <int N, bool kHarmonic>
+__global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, T = Cfg<N>::T;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* tile0 = reinterpret_cast<double*>(smem_raw);
+  double* tile1 = tile0 + 5 * npad;
+  double* sQ = tile1 + 5 * npad;
+  double* sD = sQ + 10 * T;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (N * N + 1) / 2 * 2);
+
+  const int e = a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
+  const int chunk = blockIdx.x % Cfg<N>::nchunk;
+  const int tid = threadIdx.x;
+  const int pt = chunk * T + tid;
+  const bool active = pt < n;
+  const double* __restrict__ ue = a.u + (size_t)e * 50 * npad;
+
+  // stage the 5 components of pair s = (g_s, Pi_s, Phi_0s, Phi_1s, Phi_2s)
+  auto issue = [&](int s, int stage) {
+    double* t = stage ? tile1 : tile0;
+    mbar_expect_tx(&bars[stage], 5 * npad * 8);
+    tma_bulk_g2s(t, ue + (size_t)s * npad, npad * 8, &bars[stage]);
+    tma_bulk_g2s(t + npad, ue + (size_t)(10 + s) * npad, npad * 8, &bars[stage]);
+    tma_bulk_g2s(t + 2 * npad, ue + (size_t)(20 + 3 * s) * npad, 3 * npad * 8,
+                 &bars[stage]);
+  };
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    issue(0, 0);
+    issue(1, 1);
+  }
+  for (int idx = tid; idx < N * N; idx += T) sD[idx] = a.D[idx];
+
+  // ---- prologue: everything that needs all 50 components at the point ----
+  GhContext ctx;
+  if (active) {
+    double g[10], pi[10], phi[3][10], J[3][3], Q[10];
+#pragma unroll
+    for (int s = 0; s < 10; ++s) {
+      g[s] = __ldg(ue + (size_t)s * npad + pt);
+      pi[s] = __ldg(ue + (size_t)(10 + s) * npad + pt);
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+        phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad + pt);
+    }
+    const double* je = a.invjac + (size_t)e * 9 * npad + pt;
+#pragma unroll
+    for (int jh = 0; jh < 3; ++jh)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) J[jh][i] = __ldg(je + (size_t)(jh + 3 * i) * npad);
+    const double* se = a.stat + (size_t)e * 3 * npad + pt;
+    const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad),
+                 gamma2 = __ldg(se + 2 * npad);
+    GaugeH gh;
+    if constexpr (!kHarmonic) {
+      const double* he = a.gH + (size_t)e * 4 * npad + pt;
+      const double* dhe = a.gdH + (size_t)e * 16 * npad + pt;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        gh.H[x] = __ldg(he + (size_t)x * npad);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
+      }
+    }
+    gh_prologue<kHarmonic>(g, pi, phi, J, gamma0, gamma1, gamma2, &gh, ctx, Q);
+#pragma unroll
+    for (int s = 0; s < 10; ++s) sQ[s * T + tid] = Q[s];
+  }
+  __syncthreads();  // sD visible, barrier init visible to all waiters
+
+  const int i = pt % N, j = (pt / N) % N, k = pt / (N * N);
+  double Di[N], Dj[N], Dk[N];
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      Di[m] = sD[i * N + m];
+      Dj[m] = sD[j * N + m];
+      Dk[m] = sD[k * N + m];
+    }
+  }
+  double* __restrict__ dte = a.dt + (size_t)e * 50 * npad;
+  const double* __restrict__ corr_e =
+      a.corr ? a.corr + (size_t)e * 6 * 50 * (N * N) : nullptr;
+
+  // ---- stream the ten (mu,nu) pairs through the two-stage ring ----
+#pragma unroll 1
+  for (int s = 0; s < 10; ++s) {
+    const int stage = s & 1;
+    mbar_wait(&bars[stage], (s >> 1) & 1);
+    const double* t = stage ? tile1 : tile0;
+    if (active) {
+      double dg[3], dpi[3], dph[3][3], ph[3];
+      logical_derivs<N>(t, i, j, k, Di, Dj, Dk, dg);
+      logical_derivs<N>(t + npad, i, j, k, Di, Dj, Dk, dpi);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        logical_derivs<N>(t + (2 + m) * npad, i, j, k, Di, Dj, Dk, dph[m]);
+        ph[m] = t[(2 + m) * npad + pt];
+      }
+      double og, opi, oph[3];
+      gh_pair_rhs(ctx, sQ[s * T + tid], t[pt], t[npad + pt], ph, dg, dpi, dph, og,
+                  opi, oph);
+      if (corr_e) {
+        og = add_corrections<N, 50>(og, corr_e, s, i, j, k);
+        opi = add_corrections<N, 50>(opi, corr_e, 10 + s, i, j, k);
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          oph[m] = add_corrections<N, 50>(oph[m], corr_e, 20 + m + 3 * s, i, j, k);
+      }
+      dte[(size_t)s * npad + pt] = og;
+      dte[(size_t)(10 + s) * npad + pt] = opi;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) dte[(size_t)(20 + m + 3 * s) * npad + pt] = oph[m];
+    }
+    __syncthreads();  // every reader is done with this stage
+    if (tid == 0 && s + 2 < 10) issue(s + 2, stage);
+  }
+}
+
+// --------------------------------------------------------------------------
+// ScalarWave volume kernel (same structure, one tile of 5 components)
+// --------------------------------------------------------------------------
+struct SwVolArgs {
+  const double* u;       // [E][5][npad]
+  double* dt;            // [E][5][npad]
+  const double* invjac;  // [E][9][npad]
+  const double* stat;    // [E][1][npad] gamma2
+  const double* corr;    // [E][6][5][f] or nullptr
+  const double* D;
+  int elem_begin;
+};
+
+template <int N>
+constexpr int sw_volume_smem_bytes() {
+  return (5 * Cfg<N>::npad + (N * N + 1) / 2 * 2) * 8 + 8;
+}
+
+template <int N>
+__global__ void __launch_bounds__(Cfg<N>::T) sw_volume_kernel(SwVolArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, T = Cfg<N>::T;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);
+  double* sD = tile + 5 * npad;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sD + (N * N + 1) / 2 * 2);
+  const int e = a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
+  const int chunk = blockIdx.x % Cfg<N>::nchunk;
+  const int tid = threadIdx.x;
+  const int pt = chunk * T + tid;
+  const bool active = pt < n;
+  const double* __restrict__ ue = a.u + (size_t)e * 5 * npad;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, 5 * npad * 8);
+    tma_bulk_g2s(tile, ue, 5 * npad * 8, bar);
+  }
+  for (int idx = tid; idx < N * N; idx += T) sD[idx] = a.D[idx];
+  __syncthreads();
+  const int i = pt % N, j = (pt / N) % N, k = pt / (N * N);
+  double Di[N], Dj[N], Dk[N], J[3][3], gamma2 = 0.0;
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      Di[m] = sD[i * N + m];
+      Dj[m] = sD[j * N + m];
+      Dk[m] = sD[k * N + m];
+    }
+    const double* je = a.invjac + (size_t)e * 9 * npad + pt;
+#pragma unroll
+    for (int jh = 0; jh < 3; ++jh)
+#pragma unroll
+      for (int x = 0; x < 3; ++x) J[jh][x] = __ldg(je + (size_t)(jh + 3 * x) * npad);
+    gamma2 = __ldg(a.stat + (size_t)e * npad + pt);
+  }
+  mbar_wait(bar, 0);
+  if (active) {
+    double u[5], d[5][3], out[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      u[c] = tile[c * npad + pt];
+      logical_derivs<N>(tile + c * npad, i, j, k, Di, Dj, Dk, d[c]);
+    }
+    sw_point_rhs(u, d, J, gamma2, out);
+    double* __restrict__ dte = a.dt + (size_t)e * 5 * npad;
+    const double* corr_e = a.corr ? a.corr + (size_t)e * 6 * 5 * (N * N) : nullptr;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      double v = out[c];
+      if (corr_e) v = add_corrections<N, 5>(v, corr_e, c, i, j, k);
+      dte[(size_t)c * npad + pt] = v;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Face kernel: one thread per (element, direction, face point)
+// --------------------------------------------------------------------------
+struct FaceArgs {
+  const double* u;        // [E][C][npad]
+  const double* invjac;   // [E][9][npad]
+  const double* stat;     // [E][S][npad]
+  const int32_t* nbr;     // [E][6]
+  const double* ghost;    // [G][HC][f]   u (C) | J row (3) | gammas
+  double* corr;           // [E][6][C][f]
+  int elem_begin, elem_end;
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, HC = 55;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(a.elem_end - a.elem_begin) * 6 * f;
+  if (idx >= total) return;
+  const int q = (int)(idx % f);
+  const int d = (int)((idx / f) % 6);
+  const int e = a.elem_begin + (int)(idx / (6 * f));
+  const int qa = q % N, qb = q / N;
+  const int dim = d >> 1;
+  const double sign = (d & 1) ? 1.0 : -1.0;
+  double* __restrict__ corr = a.corr + ((size_t)e * 6 + d) * 50 * f + q;
+  const int nb = a.nbr[e * 6 + d];
+  if (nb == -1) {
+#pragma unroll 1
+    for (int c = 0; c < 50; ++c) corr[(size_t)c * f] = 0.0;
+    return;
+  }
+  const int p_own = face_point<N>(d, qa, qb);
+  const double* __restrict__ uo = a.u + (size_t)e * 50 * npad + p_own;
+  const double* __restrict__ un;  // neighbour values, component stride ns
+  size_t ns;
+  double unn_i[3], unn_e[3], g1e, g2e;
+  {
+    const double* jo = a.invjac + (size_t)e * 9 * npad + p_own;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) unn_i[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
+  }
+  if (nb >= 0) {
+    const int p_nb = face_point<N>(d ^ 1, qa, qb);
+    un = a.u + (size_t)nb * 50 * npad + p_nb;
+    ns = npad;
+    const double* jn = a.invjac + (size_t)nb * 9 * npad + p_nb;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) unn_e[x] = -sign * __ldg(jn + (size_t)(dim + 3 * x) * npad);
+    const double* sn = a.stat + (size_t)nb * 3 * npad + p_nb;
+    g1e = __ldg(sn + npad);
+    g2e = __ldg(sn + 2 * npad);
+  } else {
+    const int gi = -(nb + 2);
+    un = a.ghost + (size_t)gi * HC * f + q;
+    ns = f;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) unn_e[x] = -sign * __ldg(un + (size_t)(50 + x) * f);
+    g1e = __ldg(un + (size_t)53 * f);
+    g2e = __ldg(un + (size_t)54 * f);
+  }
+  const double* so = a.stat + (size_t)e * 3 * npad + p_own;
+  const double g1i = __ldg(so + npad), g2i = __ldg(so + 2 * npad);
+  GhFaceSide si, se;
+  {
+    double g[10];
+#pragma unroll
+    for (int s = 0; s < 10; ++s) g[s] = __ldg(uo + (size_t)s * npad);
+    gh_face_side(g, unn_i, g1i, g2i, si);
+#pragma unroll
+    for (int s = 0; s < 10; ++s) g[s] = __ldg(un + (size_t)s * ns);
+    gh_face_side(g, unn_e, g1e, g2e, se);
+  }
+  const double lift = -0.5 * (double)(N * (N - 1)) * si.mag;
+#pragma unroll 2
+  for (int s = 0; s < 10; ++s) {
+    double phi_i[3], phi_e[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      phi_i[m] = __ldg(uo + (size_t)(20 + m + 3 * s) * npad);
+      phi_e[m] = __ldg(un + (size_t)(20 + m + 3 * s) * ns);
+    }
+    GhPairPackaged ki, ke;
+    gh_pair_package(si, __ldg(uo + (size_t)s * npad), __ldg(uo + (size_t)(10 + s) * npad),
+                    phi_i, ki);
+    gh_pair_package(se, __ldg(un + (size_t)s * ns), __ldg(un + (size_t)(10 + s) * ns),
+                    phi_e, ke);
+    double cg, cp, cph[3];
+    gh_pair_boundary_terms(si, se, ki, ke, cg, cp, cph);
+    corr[(size_t)s * f] = cg * lift;
+    corr[(size_t)(10 + s) * f] = cp * lift;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) corr[(size_t)(20 + m + 3 * s) * f] = cph[m] * lift;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, HC = 9;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(a.elem_end - a.elem_begin) * 6 * f;
+  if (idx >= total) return;
+  const int q = (int)(idx % f);
+  const int d = (int)((idx / f) % 6);
+  const int e = a.elem_begin + (int)(idx / (6 * f));
+  const int qa = q % N, qb = q / N;
+  const int dim = d >> 1;
+  const double sign = (d & 1) ? 1.0 : -1.0;
+  double* __restrict__ corr = a.corr + ((size_t)e * 6 + d) * 5 * f + q;
+  const int nb = a.nbr[e * 6 + d];
+  if (nb == -1) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) corr[(size_t)c * f] = 0.0;
+    return;
+  }
+  const int p_own = face_point<N>(d, qa, qb);
+  const double* __restrict__ uo = a.u + (size_t)e * 5 * npad + p_own;
+  double ui[5], ue[5], ni[3], ne[3], g2e;
+  {
+    const double* jo = a.invjac + (size_t)e * 9 * npad + p_own;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) ni[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ui[c] = __ldg(uo + (size_t)c * npad);
+  }
+  if (nb >= 0) {
+    const int p_nb = face_point<N>(d ^ 1, qa, qb);
+    const double* un = a.u + (size_t)nb * 5 * npad + p_nb;
+    const double* jn = a.invjac + (size_t)nb * 9 * npad + p_nb;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ue[c] = __ldg(un + (size_t)c * npad);
+#pragma unroll
+    for (int x = 0; x < 3; ++x) ne[x] = -sign * __ldg(jn + (size_t)(dim + 3 * x) * npad);
+    g2e = __ldg(a.stat + (size_t)nb * npad + p_nb);
+  } else {
+    const int gi = -(nb + 2);
+    const double* un = a.ghost + (size_t)gi * HC * f + q;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ue[c] = __ldg(un + (size_t)c * f);
+#pragma unroll
+    for (int x = 0; x < 3; ++x) ne[x] = -sign * __ldg(un + (size_t)(5 + x) * f);
+    g2e = __ldg(un + (size_t)8 * f);
+  }
+  const double g2i = __ldg(a.stat + (size_t)e * npad + p_own);
+  // flat-space normalisation (NormalCovectorAndMagnitude.hpp:78-90)
+  double mi = sqrt(ni[0] * ni[0] + ni[1] * ni[1] + ni[2] * ni[2]);
+  double me = sqrt(ne[0] * ne[0] + ne[1] * ne[1] + ne[2] * ne[2]);
+  const double ii = 1.0 / mi, ie = 1.0 / me;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    ni[x] *= ii;
+    ne[x] *= ie;
+  }
+  double c5[5];
+  sw_face_correction(ui, g2i, ni, ue, g2e, ne, c5);
+  const double lift = -0.5 * (double)(N * (N - 1)) * mi;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) corr[(size_t)c * f] = c5[c] * lift;
+}
+
+// --------------------------------------------------------------------------
+// Halo pack: face slice of u + the static neighbour-side data
+// --------------------------------------------------------------------------
+struct PackArgs {
+  const double* u;
+  const double* invjac;
+  const double* stat;
+  const int32_t* map;  // [G][2] = element, direction
+  double* send;        // [G][HC][f]
+  int nghost;
+};
+
+template <int N, int C>
+__global__ void __launch_bounds__(128) pack_halo_kernel(PackArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N;
+  constexpr int S = (C == 50) ? 3 : 1;       // static comps per element
+  constexpr int HC = C + 3 + (C == 50 ? 2 : 1);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.nghost * f) return;
+  const int q = (int)(idx % f);
+  const int gi = (int)(idx / f);
+  const int e = a.map[2 * gi], d = a.map[2 * gi + 1];
+  const int p = face_point<N>(d, q % N, q / N);
+  const int dim = d >> 1;
+  double* out = a.send + (size_t)gi * HC * f + q;
+  const double* ue = a.u + (size_t)e * C * npad + p;
+#pragma unroll 5
+  for (int c = 0; c < C; ++c) out[(size_t)c * f] = __ldg(ue + (size_t)c * npad);
+  const double* je = a.invjac + (size_t)e * 9 * npad + p;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) out[(size_t)(C + x) * f] = __ldg(je + (size_t)(dim + 3 * x) * npad);
+  const double* se = a.stat + (size_t)e * S * npad + p;
+  if (C == 50) {
+    out[(size_t)(C + 3) * f] = __ldg(se + npad);
+    out[(size_t)(C + 4) * f] = __ldg(se + 2 * npad);
+  } else {
+    out[(size_t)(C + 3) * f] = __ldg(se);
+  }
+}
+
+// --------------------------------------------------------------------------
+// u <- a*u + sum_j c_j v_j   (K12+K13: UpdateU / History, flat over the block)
+// --------------------------------------------------------------------------
+struct LincombArgs {
+  double* u;
+  double a;
+  int nterms;
+  double c[8];
+  const double* v[8];
+  long long len2;  // number of double2
+};
+
+__global__ void __launch_bounds__(256) lincomb_kernel(LincombArgs p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double2* __restrict__ u2 = reinterpret_cast<double2*>(p.u);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.len2;
+       idx += stride) {
+    double2 r = u2[idx];
+    r.x *= p.a;
+    r.y *= p.a;
+    for (int j = 0; j < p.nterms; ++j) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(p.v[j]) + idx);
+      r.x = fma(p.c[j], v.x, r.x);
+      r.y = fma(p.c[j], v.y, r.y);
+    }
+    u2[idx] = r;
+  }
+}
+
+// --------------------------------------------------------------------------
+// Stand-alone partial_derivatives (operator API, gauge fields): one CTA per
+// (element, component): du[(ob + c*oc + i)] = J(jhat, i) d_jhat u_c
+// --------------------------------------------------------------------------
+struct DerivArgs {
+  const double* u;       // [E][C][npad]
+  const double* invjac;  // [E][9][npad]
+  double* du;            // [E][CO][npad]
+  const double* D;
+  int C, CO, out_base, out_cstride;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) partial_derivatives_kernel(DerivArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
+  __shared__ __align__(16) double tile[npad];
+  __shared__ double sD[N * N];
+  const int e = blockIdx.x / a.C, c = blockIdx.x % a.C;
+  const double* uc = a.u + ((size_t)e * a.C + c) * npad;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) tile[p] = uc[p];
+  for (int p = threadIdx.x; p < N * N; p += blockDim.x) sD[p] = a.D[p];
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const int i = p % N, j = (p / N) % N, k = p / (N * N);
+    double Di[N], Dj[N], Dk[N], d[3];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      Di[m] = sD[i * N + m];
+      Dj[m] = sD[j * N + m];
+      Dk[m] = sD[k * N + m];
+    }
+    logical_derivs<N>(tile, i, j, k, Di, Dj, Dk, d);
+    const double* je = a.invjac + (size_t)e * 9 * npad + p;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      double v = __ldg(je + (size_t)(0 + 3 * x) * npad) * d[0];
+      v += __ldg(je + (size_t)(1 + 3 * x) * npad) * d[1];
+      v += __ldg(je + (size_t)(2 + 3 * x) * npad) * d[2];
+      a.du[((size_t)e * a.CO + a.out_base + c * a.out_cstride + x) * npad + p] = v;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// AnalyticChristoffel gauge with the GaugeWave solution, evaluated at time t:
+// H_a = -Gamma_a[analytic(x, t)]  (AnalyticChristoffel.cpp:76-133,
+// GaugeWave.hpp:34-50).  The spatial derivative is then taken numerically by
+// partial_derivatives_kernel (:136-143), d_t H_a = 0 (:145-147).
+// --------------------------------------------------------------------------
+struct GaugeWaveArgs {
+  const double* coords;  // [E][3][npad]
+  double* gH;            // [E][4][npad]
+  double amplitude, wavelength, time;
+  int nelem;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) gauge_wave_h_kernel(GaugeWaveArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.nelem * n) return;
+  const int e = (int)(idx / n), p = (int)(idx % n);
+  const double x = a.coords[((size_t)e * 3) * npad + p];
+  const double omega = 2.0 * M_PI / a.wavelength;
+  const double H = 1.0 - a.amplitude * sin(omega * (x - a.time));
+  const double dH = -omega * a.amplitude * cos(omega * (x - a.time));
+  // g = diag(-H, H, 1, 1); d_t g_00 = dH, d_t g_11 = -dH, d_x g_00 = -dH,
+  // d_x g_11 = dH.  Gamma_a = g^{bc} Gamma_a,bc with g^{00} = -1/H, g^{11}=1/H
+  //   Gamma_0 = g^{00} Gamma_0,00 + g^{11} Gamma_0,11
+  //           = (-1/H)(1/2 d_t g_00) + (1/H)(d_x g_01.. - 1/2 d_t g_11)
+  const double G00 = -1.0 / H, G11 = 1.0 / H;
+  const double chr_0_00 = 0.5 * dH;             // 1/2 d_t g_00
+  const double chr_0_11 = -0.5 * (-dH);         // -1/2 d_t g_11
+  const double chr_1_00 = -0.5 * (-dH);         // -1/2 d_x g_00
+  const double chr_1_11 = 0.5 * dH;             // 1/2 d_x g_11
+  const double gam0 = G00 * chr_0_00 + G11 * chr_0_11;
+  const double gam1 = G00 * chr_1_00 + G11 * chr_1_11;
+  double* h = a.gH + (size_t)e * 4 * npad + p;
+  h[0] = -gam0;
+  h[(size_t)npad] = -gam1;
+  h[(size_t)2 * npad] = 0.0;
+  h[(size_t)3 * npad] = 0.0;
+}
+
+}  // namespace dg

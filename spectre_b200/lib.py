@@ -1,0 +1,232 @@
+"""ctypes binding of the C-ABI in include/dgrhs.h (libdgrhs.so, built in-tree by
+``__graft_entry__.build()``).  There is no CPU fallback: importing works without
+a GPU (so the symbol table can be checked), but creating a context without a
+CUDA device raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdgrhs.so")
+
+SYSTEM_SCALAR_WAVE, SYSTEM_GH = 0, 1
+GAUGE_HARMONIC, GAUGE_FIELDS, GAUGE_DAMPED_HARMONIC, GAUGE_ANALYTIC_GAUGE_WAVE = 0, 1, 2, 3
+STEPPER_ADAMS_BASHFORTH, STEPPER_RK3_HESTHAVEN = 0, 1
+
+# every symbol include/dgrhs.h declares
+EXPORTS = [
+    "dgrhs_last_error", "dgrhs_kernel_launch_count", "dgrhs_create", "dgrhs_destroy",
+    "dgrhs_set_geometry", "dgrhs_set_static_fields", "dgrhs_set_gauge",
+    "dgrhs_set_gauge_fields", "dgrhs_set_state", "dgrhs_get_state",
+    "dgrhs_get_time_derivative", "dgrhs_compute_time_derivative", "dgrhs_set_interior_count",
+    "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
+    "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
+    "dgrhs_take_steps", "dgrhs_time", "dgrhs_rhs_evaluations", "dgrhs_begin_substep",
+    "dgrhs_end_substep", "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
+    "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
+    "dgrhs_collocation_points_and_weights", "dgrhs_adams_bashforth_coefficients",
+]
+
+_lib = None
+
+
+class DgrhsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libdgrhs.so; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DgrhsError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.dgrhs_last_error.restype = ctypes.c_char_p
+        lib.dgrhs_kernel_launch_count.restype = ctypes.c_int64
+        lib.dgrhs_rhs_evaluations.restype = ctypes.c_int64
+        lib.dgrhs_time.restype = ctypes.c_double
+        for f in ("dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_stream",
+                  "dgrhs_state_device_ptr"):
+            getattr(lib, f).restype = ctypes.c_void_p
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise DgrhsError(load().dgrhs_last_error().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def kernel_launch_count() -> int:
+    return int(load().dgrhs_kernel_launch_count())
+
+
+def differentiation_matrix(N: int) -> np.ndarray:
+    D = np.zeros((N, N))
+    _check(load().dgrhs_differentiation_matrix(N, _ptr(D)))
+    return D
+
+
+def collocation_points_and_weights(N: int):
+    x, w = np.zeros(N), np.zeros(N)
+    _check(load().dgrhs_collocation_points_and_weights(N, _ptr(x), _ptr(w)))
+    return x, w
+
+
+def adams_bashforth_coefficients(times, step_start, step_end):
+    t = _f64(times)
+    c = np.zeros(len(t))
+    _check(load().dgrhs_adams_bashforth_coefficients(
+        len(t), _ptr(t), ctypes.c_double(step_start), ctypes.c_double(step_end), _ptr(c)))
+    return c
+
+
+def partial_derivatives(N: int, u: np.ndarray, inv_jacobian: np.ndarray) -> np.ndarray:
+    u, J = _f64(u), _f64(inv_jacobian)
+    C = u.shape[0]
+    du = np.zeros((3 * C, N ** 3))
+    _check(load().dgrhs_partial_derivatives(N, C, _ptr(u), _ptr(J), _ptr(du)))
+    return du
+
+
+class Context:
+    """One batched DG context per GPU (dgrhs_ctx)."""
+
+    def __init__(self, system: int, N: int, n_elements: int, n_ghost_faces: int = 0,
+                 device: int = 0):
+        self._lib = load()
+        self._h = ctypes.c_void_p()
+        self.system, self.N, self.n_elements = system, N, n_elements
+        self.n_ghost_faces = n_ghost_faces
+        self.n_vars = 50 if system == SYSTEM_GH else 5
+        self.n = N ** 3
+        _check(self._lib.dgrhs_create(ctypes.byref(self._h), system, N, n_elements,
+                                      n_ghost_faces, device))
+
+    def close(self):
+        if self._h:
+            self._lib.dgrhs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_geometry(self, inv_jacobian, coords, neighbors):
+        J = _f64(inv_jacobian)
+        X = _f64(coords) if coords is not None else None
+        nb = np.ascontiguousarray(neighbors, dtype=np.int32)
+        assert J.shape == (self.n_elements, 9, self.n)
+        assert nb.shape == (self.n_elements, 6)
+        _check(self._lib.dgrhs_set_geometry(self._h, _ptr(J), _ptr(X), _ptr(nb)))
+
+    def set_static_fields(self, fields):
+        F = _f64(fields)
+        assert F.shape[0] == self.n_elements and F.shape[2] == self.n
+        _check(self._lib.dgrhs_set_static_fields(self._h, _ptr(F), F.shape[1]))
+
+    def set_gauge(self, gauge, params=()):
+        p = _f64(list(params)) if len(params) else np.zeros(1)
+        _check(self._lib.dgrhs_set_gauge(self._h, gauge, _ptr(p), len(params)))
+
+    def set_gauge_fields(self, H, dH):
+        H, dH = _f64(H), _f64(dH)
+        assert H.shape == (self.n_elements, 4, self.n)
+        assert dH.shape == (self.n_elements, 16, self.n)
+        _check(self._lib.dgrhs_set_gauge_fields(self._h, _ptr(H), _ptr(dH)))
+
+    def set_state(self, u):
+        u = _f64(u)
+        assert u.shape == (self.n_elements, self.n_vars, self.n), u.shape
+        _check(self._lib.dgrhs_set_state(self._h, _ptr(u)))
+
+    def get_state(self):
+        u = np.zeros((self.n_elements, self.n_vars, self.n))
+        _check(self._lib.dgrhs_get_state(self._h, _ptr(u)))
+        return u
+
+    def get_time_derivative(self):
+        u = np.zeros((self.n_elements, self.n_vars, self.n))
+        _check(self._lib.dgrhs_get_time_derivative(self._h, _ptr(u)))
+        return u
+
+    def compute_time_derivative(self, time=0.0, volume_only=False):
+        _check(self._lib.dgrhs_compute_time_derivative(self._h, ctypes.c_double(time),
+                                                       int(volume_only)))
+
+    def compute_time_derivative_range(self, time, begin, end):
+        _check(self._lib.dgrhs_compute_time_derivative_range(self._h, ctypes.c_double(time),
+                                                             begin, end))
+
+    def set_halo_map(self, ghost_send_map):
+        m = np.ascontiguousarray(ghost_send_map, dtype=np.int32)
+        assert m.shape == (self.n_ghost_faces, 2)
+        _check(self._lib.dgrhs_set_halo_map(self._h, _ptr(m)))
+
+    def pack_halo(self):
+        _check(self._lib.dgrhs_pack_halo(self._h))
+
+    @property
+    def halo_comps(self):
+        return int(self._lib.dgrhs_halo_comps(self._h))
+
+    def halo_send_ptr(self):
+        return self._lib.dgrhs_halo_send_ptr(self._h)
+
+    def halo_recv_ptr(self):
+        return self._lib.dgrhs_halo_recv_ptr(self._h)
+
+    def set_stepper(self, stepper, order, t0, dt):
+        _check(self._lib.dgrhs_set_stepper(self._h, stepper, order, ctypes.c_double(t0),
+                                           ctypes.c_double(dt)))
+
+    def take_steps(self, n):
+        _check(self._lib.dgrhs_take_steps(self._h, n))
+
+    def begin_substep(self) -> float:
+        t = ctypes.c_double()
+        _check(self._lib.dgrhs_begin_substep(self._h, ctypes.byref(t)))
+        return t.value
+
+    def end_substep(self) -> bool:
+        done = ctypes.c_int()
+        _check(self._lib.dgrhs_end_substep(self._h, ctypes.byref(done)))
+        return bool(done.value)
+
+    @property
+    def time(self):
+        return float(self._lib.dgrhs_time(self._h))
+
+    @property
+    def rhs_evaluations(self):
+        return int(self._lib.dgrhs_rhs_evaluations(self._h))
+
+    def synchronize(self):
+        _check(self._lib.dgrhs_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.dgrhs_stream(self._h)
+
+    @property
+    def state_device_ptr(self):
+        return self._lib.dgrhs_state_device_ptr(self._h)
+
+    @property
+    def padded_points(self):
+        return int(self._lib.dgrhs_padded_points(self._h))

@@ -1,0 +1,120 @@
+// Test-only host harness: runs the per-point algebra of
+// spectre_b200/csrc/pointwise.cuh on the CPU so that it can be compared with
+// the oracle without a GPU.  NOT part of the product (never built into
+// libdgrhs.so, never imported by spectre_b200/).
+#include <cmath>
+using std::sqrt;
+#include "../../spectre_b200/csrc/pointwise.cuh"
+
+extern "C" {
+
+// u [50][n], dlog [150][n] (logical derivative jhat of comp c at 3c+jhat),
+// J [9][n] (jhat + 3 i), gam [3][n], H [4][n], dH [16][n] (a + 4 b)
+void h_gh_volume(int n, int harmonic, const double* u, const double* dlog,
+                 const double* J, const double* gam, const double* H,
+                 const double* dH, double* dt) {
+  for (int p = 0; p < n; ++p) {
+    double g[10], pi[10], phi[3][10], Jm[3][3], Q[10];
+    for (int s = 0; s < 10; ++s) {
+      g[s] = u[(size_t)s * n + p];
+      pi[s] = u[(size_t)(10 + s) * n + p];
+      for (int m = 0; m < 3; ++m) phi[m][s] = u[(size_t)(20 + m + 3 * s) * n + p];
+    }
+    for (int jh = 0; jh < 3; ++jh)
+      for (int i = 0; i < 3; ++i) Jm[jh][i] = J[(size_t)(jh + 3 * i) * n + p];
+    dg::GaugeH gh;
+    for (int a = 0; a < 4; ++a) {
+      gh.H[a] = H[(size_t)a * n + p];
+      for (int b = 0; b < 4; ++b) gh.dH[a][b] = dH[(size_t)(a + 4 * b) * n + p];
+    }
+    dg::GhContext ctx;
+    if (harmonic)
+      dg::gh_prologue<true>(g, pi, phi, Jm, gam[p], gam[n + p], gam[2 * n + p], &gh, ctx, Q);
+    else
+      dg::gh_prologue<false>(g, pi, phi, Jm, gam[p], gam[n + p], gam[2 * n + p], &gh, ctx, Q);
+    for (int s = 0; s < 10; ++s) {
+      double ph[3], dgl[3], dpl[3], dphl[3][3], og, op, oph[3];
+      for (int m = 0; m < 3; ++m) ph[m] = phi[m][s];
+      for (int jh = 0; jh < 3; ++jh) {
+        dgl[jh] = dlog[(size_t)(3 * s + jh) * n + p];
+        dpl[jh] = dlog[(size_t)(3 * (10 + s) + jh) * n + p];
+        for (int m = 0; m < 3; ++m)
+          dphl[m][jh] = dlog[(size_t)(3 * (20 + m + 3 * s) + jh) * n + p];
+      }
+      dg::gh_pair_rhs(ctx, Q[s], g[s], pi[s], ph, dgl, dpl, dphl, og, op, oph);
+      dt[(size_t)s * n + p] = og;
+      dt[(size_t)(10 + s) * n + p] = op;
+      for (int m = 0; m < 3; ++m) dt[(size_t)(20 + m + 3 * s) * n + p] = oph[m];
+    }
+  }
+}
+
+// faces: ui/ue [50][f]; unnorm_i/unnorm_e [3][f] (each side's own outward
+// unnormalised covector); gi/ge [2][f] = gamma1, gamma2; lift_n = N
+void h_gh_face(int f, int N, const double* ui, const double* ue,
+               const double* unnorm_i, const double* unnorm_e, const double* gi,
+               const double* ge, double* corr) {
+  for (int p = 0; p < f; ++p) {
+    double g_i[10], g_e[10], ni[3], ne[3];
+    for (int s = 0; s < 10; ++s) {
+      g_i[s] = ui[(size_t)s * f + p];
+      g_e[s] = ue[(size_t)s * f + p];
+    }
+    for (int i = 0; i < 3; ++i) {
+      ni[i] = unnorm_i[(size_t)i * f + p];
+      ne[i] = unnorm_e[(size_t)i * f + p];
+    }
+    dg::GhFaceSide si, se;
+    dg::gh_face_side(g_i, ni, gi[p], gi[f + p], si);
+    dg::gh_face_side(g_e, ne, ge[p], ge[f + p], se);
+    const double lift = -0.5 * (double)(N * (N - 1)) * si.mag;
+    for (int s = 0; s < 10; ++s) {
+      double phi_i[3], phi_e[3], cg, cp, cph[3];
+      for (int m = 0; m < 3; ++m) {
+        phi_i[m] = ui[(size_t)(20 + m + 3 * s) * f + p];
+        phi_e[m] = ue[(size_t)(20 + m + 3 * s) * f + p];
+      }
+      dg::GhPairPackaged ki, ke;
+      dg::gh_pair_package(si, g_i[s], ui[(size_t)(10 + s) * f + p], phi_i, ki);
+      dg::gh_pair_package(se, g_e[s], ue[(size_t)(10 + s) * f + p], phi_e, ke);
+      dg::gh_pair_boundary_terms(si, se, ki, ke, cg, cp, cph);
+      corr[(size_t)s * f + p] = cg * lift;
+      corr[(size_t)(10 + s) * f + p] = cp * lift;
+      for (int m = 0; m < 3; ++m) corr[(size_t)(20 + m + 3 * s) * f + p] = cph[m] * lift;
+    }
+  }
+}
+
+void h_sw_volume(int n, const double* u, const double* dlog, const double* J,
+                 const double* gamma2, double* dt) {
+  for (int p = 0; p < n; ++p) {
+    double up[5], d[5][3], Jm[3][3], out[5];
+    for (int c = 0; c < 5; ++c) {
+      up[c] = u[(size_t)c * n + p];
+      for (int jh = 0; jh < 3; ++jh) d[c][jh] = dlog[(size_t)(3 * c + jh) * n + p];
+    }
+    for (int jh = 0; jh < 3; ++jh)
+      for (int i = 0; i < 3; ++i) Jm[jh][i] = J[(size_t)(jh + 3 * i) * n + p];
+    dg::sw_point_rhs(up, d, Jm, gamma2[p], out);
+    for (int c = 0; c < 5; ++c) dt[(size_t)c * n + p] = out[c];
+  }
+}
+
+void h_sw_face(int f, const double* ui, const double* ue, const double* ni,
+               const double* ne, const double* g2i, const double* g2e,
+               double* corr) {
+  for (int p = 0; p < f; ++p) {
+    double a[5], b[5], na[3], nb[3], c[5];
+    for (int k = 0; k < 5; ++k) {
+      a[k] = ui[(size_t)k * f + p];
+      b[k] = ue[(size_t)k * f + p];
+    }
+    for (int i = 0; i < 3; ++i) {
+      na[i] = ni[(size_t)i * f + p];
+      nb[i] = ne[(size_t)i * f + p];
+    }
+    dg::sw_face_correction(a, g2i[p], na, b, g2e[p], nb, c);
+    for (int k = 0; k < 5; ++k) corr[(size_t)k * f + p] = c[k];
+  }
+}
+}

@@ -1,0 +1,51 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol that
+include/dgrhs.h declares, its host-only entry points agree with the oracle, and
+it fails loudly (no CPU fallback) when there is no CUDA device."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from spectre_b200 import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "dgrhs.h")).read()
+    declared = set(re.findall(r"\b(dgrhs_[a-z0-9_]+)\s*\(", header))
+    declared.discard("dgrhs_ctx")
+    assert declared == set(lib.EXPORTS)
+    handle = lib.load()
+    for name in declared:
+        assert getattr(handle, name) is not None
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 6, 8, 12])
+def test_spectral_host_functions_match_oracle(N):
+    x, w = lib.collocation_points_and_weights(N)
+    xo, wo = orc.lgl_points_and_weights(N)
+    np.testing.assert_allclose(x, xo, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(w, wo, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(lib.differentiation_matrix(N), orc.differentiation_matrix(N),
+                               rtol=1e-13, atol=1e-13)
+
+
+def test_adams_bashforth_coefficients_match_oracle():
+    for times, a, b in (([0.0, 1.0, 2.0], 2.0, 3.0), ([0.2, 0.4, 0.0], 0.0, 0.6),
+                        ([0.4, 0.0, 0.6], 0.6, 1.2), ([0.0, 0.7, 1.0, 1.9], 1.9, 2.5)):
+        got = lib.adams_bashforth_coefficients(times, a, b)
+        ref = orc.ab_coefficients(times, a, b)
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-15)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lib.DgrhsError, match="no CPU fallback"):
+        lib.Context(lib.SYSTEM_SCALAR_WAVE, 4, 8)
+    with pytest.raises(lib.DgrhsError, match="no CPU fallback"):
+        lib.partial_derivatives(4, np.zeros((1, 64)), np.zeros((9, 64)))

@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU
+oracle on the same seeded inputs.  Tolerance: 1e-12 relative in the max norm
+over each evolved tensor (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from spectre_b200 import analytic, domain, lib
+from tests.test_oracle_pins import _random_physical_gh_state
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _relerr(got, ref, blocks):
+    return max(np.max(np.abs(got[:, b] - ref[:, b])) / np.max(np.abs(ref[:, b])) for b in blocks)
+
+
+SW_BLOCKS = [slice(0, 1), slice(1, 2), slice(2, 5)]
+GH_BLOCKS = [slice(0, 10), slice(10, 20), slice(20, 50)]
+
+
+def _curved_jacobian(rng, brick):
+    """Full 3x3 inverse Jacobian with off-diagonal terms (a smooth, per-point
+    perturbation of the affine one) so that every J entry is exercised."""
+    J = brick.inverse_jacobian()
+    J = J + 0.1 * rng.uniform(-1, 1, J.shape)
+    return J
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 6, 7, 8])
+def test_partial_derivatives_operator(N):
+    rng = np.random.default_rng(N)
+    u = rng.uniform(-1, 1, (7, N ** 3))
+    J = rng.uniform(-1, 1, (9, N ** 3))
+    got = lib.partial_derivatives(N, u, J)
+    ref = orc.partial_derivatives(N, u, J)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < TOL
+
+
+@pytest.mark.parametrize("N,refine", [(2, 1), (3, 1), (5, 1), (6, 2), (7, 1), (8, 1), (9, 1),
+                                      (10, 1), (11, 0), (12, 1)])
+def test_scalar_wave_rhs(N, refine):
+    rng = np.random.default_rng(100 + N)
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [refine] * 3, N)
+    x = brick.coords()
+    u = analytic.plane_wave(x, 0.3) + 0.1 * rng.uniform(-1, 1, (brick.n_elements, 5, brick.n))
+    J = _curved_jacobian(rng, brick)
+    nb = brick.neighbors()
+    stat = rng.uniform(0, 1, (brick.n_elements, 1, brick.n))
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u)
+    for volume_only in (True, False):
+        ctx.compute_time_derivative(0.0, volume_only=volume_only)
+        got = ctx.get_time_derivative()
+        ref = orc.dg_rhs(0, N, u, J, stat, nb, volume_only=volume_only)
+        assert _relerr(got, ref, SW_BLOCKS) < TOL
+    np.testing.assert_array_equal(ctx.get_state(), u)  # round trip, bit exact
+    ctx.close()
+
+
+def _gh_problem(rng, N, refine, noise=1e-2):
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [refine] * 3, N)
+    x = brick.coords()
+    u = analytic.gauge_wave(x, 0.1)
+    u = u + noise * rng.uniform(-1, 1, u.shape)
+    J = _curved_jacobian(rng, brick)
+    stat = rng.uniform(-1, 1, (brick.n_elements, 3, brick.n))
+    return brick, x, u, J, stat
+
+
+@pytest.mark.parametrize("N,refine", [(2, 1), (3, 1), (4, 1), (5, 1), (6, 1), (7, 1), (8, 1),
+                                      (9, 0), (10, 1), (11, 0), (12, 1)])
+def test_gh_rhs_harmonic(N, refine):
+    rng = np.random.default_rng(200 + N)
+    brick, x, u, J, stat = _gh_problem(rng, N, refine)
+    nb = brick.neighbors()
+    ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u)
+    for volume_only in (True, False):
+        ctx.compute_time_derivative(0.0, volume_only=volume_only)
+        got = ctx.get_time_derivative()
+        ref = orc.dg_rhs(1, N, u, J, stat, nb, volume_only=volume_only)
+        assert _relerr(got, ref, GH_BLOCKS) < TOL
+    ctx.close()
+
+
+def test_gh_rhs_random_physical_state():
+    """Far-from-flat random physical metrics (like Test_DuDt.cpp:489-493), shift
+    large enough that characteristic speeds change sign on the faces."""
+    N = 5
+    rng = np.random.default_rng(77)
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N)
+    u = np.stack([_random_physical_gh_state(rng, brick.n) for _ in range(brick.n_elements)])
+    J = _curved_jacobian(rng, brick)
+    stat = rng.uniform(-1.5, 1, (brick.n_elements, 3, brick.n))
+    nb = brick.neighbors()
+    ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+    ctx.set_geometry(J, None, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u)
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    ref = orc.dg_rhs(1, N, u, J, stat, nb)
+    assert _relerr(got, ref, GH_BLOCKS) < TOL
+    ctx.close()
+
+
+def test_gh_rhs_gauge_fields():
+    N = 6
+    rng = np.random.default_rng(9)
+    brick, x, u, J, stat = _gh_problem(rng, N, 1)
+    nb = brick.neighbors()
+    H = rng.uniform(-1, 1, (brick.n_elements, 4, brick.n))
+    dH = rng.uniform(-1, 1, (brick.n_elements, 16, brick.n))
+    ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_gauge(lib.GAUGE_FIELDS)
+    ctx.set_gauge_fields(H, dH)
+    ctx.set_state(u)
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    ref = orc.dg_rhs(1, N, u, J, np.concatenate([stat, H, dH], axis=1), nb,
+                     gauge_params=orc.GAUGE_GIVEN)
+    assert _relerr(got, ref, GH_BLOCKS) < TOL
+    ctx.close()
+
+
+def test_external_boundaries_get_no_correction():
+    N = 4
+    rng = np.random.default_rng(4)
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N, periodic=(True, False, True))
+    x = brick.coords()
+    u = analytic.plane_wave(x, 0.0)
+    J = brick.inverse_jacobian()
+    stat = rng.uniform(0, 1, (brick.n_elements, 1, brick.n))
+    nb = brick.neighbors()
+    assert (nb == -1).any()
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u)
+    ctx.compute_time_derivative(0.0)
+    ref = orc.dg_rhs(0, N, u, J, stat, nb)
+    assert _relerr(ctx.get_time_derivative(), ref, SW_BLOCKS) < TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("stepper", ["AB1", "AB2", "AB3", "AB4", "RK3"])
+def test_scalar_wave_evolution(stepper):
+    """Config 1 at reduced size (2^3 elements, N = 6): self-start + 4 steps."""
+    N, dt = 6, 1e-3
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    u0 = analytic.plane_wave(x, 0.0)
+    stat = np.zeros((brick.n_elements, 1, brick.n))
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u0)
+    if stepper == "RK3":
+        ctx.set_stepper(lib.STEPPER_RK3_HESTHAVEN, 3, 0.0, dt)
+    else:
+        ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, int(stepper[2:]), 0.0, dt)
+    ctx.take_steps(4)
+    ev = orc.Evolution(lambda u, t: orc.dg_rhs(0, N, u, J, stat, nb), u0, 0.0, dt, stepper)
+    for _ in range(4):
+        ev.step()
+    got = ctx.get_state()
+    assert ctx.rhs_evaluations == ev.rhs_evals
+    assert abs(ctx.time - ev.time) < 1e-15
+    assert _relerr(got, ev.u, SW_BLOCKS) < TOL
+    # exact-solution error norm (PlaneWave3D.yaml observes Error(...) norms)
+    exact = analytic.plane_wave(x, ctx.time)
+    assert orc.l2_norm(got - exact) < 1e-5
+    ctx.close()
+
+
+def test_gh_gauge_wave_evolution_ab3():
+    """GaugeWave3D.yaml at its CI size (2^3 elements, N = 5, AB3, dt = 2e-4,
+    gamma0 = 1, gamma1 = -1, gamma2 = 1): self-start + 5 steps; evolved tensors
+    and the error norms against the exact solution."""
+    N, dt = 5, 2e-4
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N)
+    x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    u0 = analytic.gauge_wave(x, 0.0)
+    stat = np.zeros((brick.n_elements, 3, brick.n))
+    stat[:, 0], stat[:, 1], stat[:, 2] = 1.0, -1.0, 1.0
+    for gauge in (lib.GAUGE_HARMONIC, lib.GAUGE_ANALYTIC_GAUGE_WAVE):
+        ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+        ctx.set_geometry(J, x, nb)
+        ctx.set_static_fields(stat)
+        if gauge == lib.GAUGE_ANALYTIC_GAUGE_WAVE:
+            ctx.set_gauge(gauge, [0.1, 1.0])
+        ctx.set_state(u0)
+        ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 3, 0.0, dt)
+        ctx.take_steps(5)
+
+        def rhs(u, t):
+            if gauge == lib.GAUGE_HARMONIC:
+                return orc.dg_rhs(1, N, u, J, stat, nb)
+            H = np.zeros((brick.n_elements, 4, brick.n))
+            dH = np.zeros((brick.n_elements, 16, brick.n))
+            for e in range(brick.n_elements):
+                ua = orc.gh_vars_from_metric(*orc.gauge_wave_metric(x[e], t))
+                H[e], dH[e] = orc.analytic_christoffel_gauge(N, ua, J[e])
+            return orc.dg_rhs(1, N, u, J, np.concatenate([stat, H, dH], axis=1), nb,
+                              gauge_params=orc.GAUGE_GIVEN)
+
+        ev = orc.Evolution(rhs, u0, 0.0, dt, "AB3")
+        for _ in range(5):
+            ev.step()
+        got = ctx.get_state()
+        assert _relerr(got, ev.u, GH_BLOCKS) < TOL
+        exact = analytic.gauge_wave(x, ctx.time)
+        for b in GH_BLOCKS:
+            e_gpu = orc.l2_norm(got[:, b] - exact[:, b])
+            e_cpu = orc.l2_norm(ev.u[:, b] - exact[:, b])
+            assert abs(e_gpu - e_cpu) <= 1e-12 * max(1.0, e_cpu) + 1e-9 * e_cpu
+        ctx.close()
+
+
+def test_product_analytic_data_matches_oracle():
+    """The product-side initial data (spectre_b200.analytic) against the
+    oracle's independent restatement."""
+    N = 5
+    brick = domain.Brick([0.5, 0.5, 0.5], [2.5] * 3, [1, 1, 1], N)
+    x = brick.coords()
+    for e in range(brick.n_elements):
+        ref = orc.gh_vars_from_metric(*orc.gauge_wave_metric(x[e], 0.3))
+        np.testing.assert_allclose(analytic.gauge_wave(x[e], 0.3), ref, rtol=1e-13, atol=1e-14)
+        ref = orc.gh_vars_from_metric(*orc.kerr_schild_metric(x[e]))
+        np.testing.assert_allclose(analytic.kerr_schild(x[e]), ref, rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(analytic.plane_wave(x[e], 0.2), orc.plane_wave(x[e], 0.2),
+                                   rtol=1e-13, atol=1e-14)
