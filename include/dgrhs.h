@@ -152,6 +152,13 @@ int64_t dgrhs_rhs_evaluations(dgrhs_ctx* ctx);
 int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
 int dgrhs_end_substep(dgrhs_ctx* ctx, int* is_step_done);
 
+/* Measurement aid for bench.py (roofline of the individual kernels): runs the
+ * face kernel, the volume kernel and a k-term stepper update `reps` times
+ * each on the context's stream, bracketed by CUDA events, and returns the mean
+ * milliseconds per launch in ms[0..2].  Does not change u (the update runs on
+ * a scratch derivative slot). */
+int dgrhs_time_kernels(dgrhs_ctx* ctx, int reps, int update_terms, double* ms);
+
 /* Synchronise the context's stream. */
 int dgrhs_synchronize(dgrhs_ctx* ctx);
 /* cudaStream_t used by the context (for CUDA-event timing by the caller). */

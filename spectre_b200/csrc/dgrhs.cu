@@ -737,6 +737,49 @@ int dgrhs_take_steps(dgrhs_ctx* c, int n_steps) {
 double dgrhs_time(dgrhs_ctx* c) { return c ? c->t0 + (double)c->step_index * c->dt : 0.0; }
 int64_t dgrhs_rhs_evaluations(dgrhs_ctx* c) { return c ? c->rhs_evals : 0; }
 
+int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (reps < 1 || update_terms < 1 || update_terms > 6) return fail("bad arguments");
+  if (ensure_slots(c, update_terms + 1)) return 1;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double* scratch = c->dt_slots[update_terms];
+  for (int which = 0; which < 3; ++which) {
+    float total = 0.f;
+    for (int r = -1; r < reps; ++r) {  // r = -1: warm-up
+      CU(cudaEventRecord(e0, c->stream));
+      int rc = 0;
+      switch (c->N) {
+#define X(NN)                                                                     \
+  case NN:                                                                        \
+    if (which == 0) rc = launch_faces<NN>(c, 0, c->nelem);                        \
+    if (which == 1) rc = launch_volume<NN>(c, c->dt_last, 0, c->nelem, true);     \
+    break;
+        DG_FOR_EACH_N(X)
+#undef X
+      }
+      if (which == 2) {
+        std::vector<double> coef(update_terms, 0.0);
+        std::vector<const double*> v;
+        for (int j = 0; j < update_terms; ++j) v.push_back(c->dt_slots[j]);
+        rc = lincomb(c, scratch, 1.0, coef, v);
+      }
+      if (rc) return 1;
+      CU(cudaEventRecord(e1, c->stream));
+      CU(cudaEventSynchronize(e1));
+      float t;
+      CU(cudaEventElapsedTime(&t, e0, e1));
+      if (r >= 0) total += t;
+    }
+    ms[which] = total / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
 int dgrhs_synchronize(dgrhs_ctx* c) {
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));

@@ -79,23 +79,26 @@ class Brick:
         lo = self.lower + h * np.asarray(cell)
         return lo, lo + h
 
-    def coords(self):
+    def coords(self, ids=None):
+        """Inertial coordinates [len(ids), 3, n] (all elements if ids is None)."""
         N, n = self.N, self.n
+        ids = range(self.n_elements) if ids is None else ids
         p = np.arange(n)
         idx = (p % N, (p // N) % N, p // (N * N))
-        out = np.zeros((self.n_elements, 3, n))
-        for e, cell in enumerate(self.cells):
-            lo, hi = self._bounds(cell)
+        out = np.zeros((len(ids), 3, n))
+        for k, e in enumerate(ids):
+            lo, hi = self._bounds(self.cells[e])
             for d in range(3):
-                out[e, d] = 0.5 * (hi[d] - lo[d]) * self.xi[idx[d]] + 0.5 * (hi[d] + lo[d])
+                out[k, d] = 0.5 * (hi[d] - lo[d]) * self.xi[idx[d]] + 0.5 * (hi[d] + lo[d])
         return out
 
-    def inverse_jacobian(self):
-        out = np.zeros((self.n_elements, 9, self.n))
-        for e, cell in enumerate(self.cells):
-            lo, hi = self._bounds(cell)
+    def inverse_jacobian(self, ids=None):
+        ids = range(self.n_elements) if ids is None else ids
+        out = np.zeros((len(ids), 9, self.n))
+        for k, e in enumerate(ids):
+            lo, hi = self._bounds(self.cells[e])
             for d in range(3):
-                out[e, d + 3 * d] = 2.0 / (hi[d] - lo[d])
+                out[k, d + 3 * d] = 2.0 / (hi[d] - lo[d])
         return out
 
     def neighbors(self):

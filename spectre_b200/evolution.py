@@ -1,0 +1,170 @@
+"""Evolution driver on top of the C-ABI: problem set-up for the BASELINE.json
+configurations and the per-substep schedule, single- or multi-GPU.
+
+Multi-GPU: the Z-curve ordered element list is cut into one
+contiguous chunk per rank (spectre_b200.domain.Partition); per RHS the only
+communication is the exchange of the cut mortar faces -- the counterpart of
+the reference's send_data_for_fluxes / receive_boundary_data_global_time_stepping
+(ComputeTimeDerivative.hpp:652-774, ApplyBoundaryCorrections.hpp:205-380),
+except that raw face values (55 components) travel instead of the 134-component
+packaged data.  Schedule per substep:
+
+    pack_halo (ctx stream) -> NCCL send/recv (torch.distributed, async)
+    RHS of interior elements (overlaps the exchange)
+    wait -> RHS of boundary elements -> stepper update
+
+torch is used only for the process group and for wrapping the library's halo
+buffers as tensors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import analytic, domain, lib
+
+
+class _CudaArray:
+    """Expose a raw device pointer through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nelem_f64):
+        self.__cuda_array_interface__ = {
+            "shape": (nelem_f64,), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+            "strides": None,
+        }
+
+
+class Problem:
+    """A BASELINE.json configuration; per-element data are built on demand for
+    the element subset a rank owns (global arrays would not fit at 8 GPUs)."""
+
+    def __init__(self, system, brick, initial_data, static_values):
+        self.system, self.brick, self.N = system, brick, brick.N
+        self._initial_data, self._static_values = initial_data, static_values
+        self.neighbors = brick.neighbors()
+
+    def coords(self, ids=None):
+        return self.brick.coords(ids)
+
+    def inverse_jacobian(self, ids=None):
+        return self.brick.inverse_jacobian(ids)
+
+    def u0(self, ids=None, t=0.0):
+        return self._initial_data(self.coords(ids), t)
+
+    def static(self, ids=None):
+        ne = self.brick.n_elements if ids is None else len(ids)
+        out = np.empty((ne, len(self._static_values), self.brick.n))
+        for i, v in enumerate(self._static_values):
+            out[:, i] = v
+        return out
+
+
+def gh_gauge_wave_problem(refinement, N, lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0, 1.0),
+                          amplitude=0.1, wavelength=1.0, gammas=(1.0, -1.0, 1.0)):
+    """BASELINE.json configs[1] (GaugeWave3D.yaml: Brick [0,1]^3 periodic,
+    gamma0 = 1, gamma1 = -1, gamma2 = 1)."""
+    brick = domain.Brick(lower, upper, refinement, N)
+    return Problem(lib.SYSTEM_GH, brick,
+                   lambda x, t: analytic.gauge_wave(x, t, amplitude, wavelength), gammas)
+
+
+def scalar_wave_problem(refinement, N):
+    """BASELINE.json configs[0] (PlaneWave3D.yaml: Brick [0,2pi]^3 periodic,
+    gamma2 = 0)."""
+    brick = domain.Brick([0.0] * 3, [2 * np.pi] * 3, refinement, N)
+    return Problem(lib.SYSTEM_SCALAR_WAVE, brick, lambda x, t: analytic.plane_wave(x, t),
+                   (0.0,))
+
+
+class Evolution:
+    """GTS evolution of one rank's share of a problem."""
+
+    def __init__(self, problem, stepper=lib.STEPPER_ADAMS_BASHFORTH, order=3, dt=2e-4,
+                 t0=0.0, gauge=lib.GAUGE_HARMONIC, gauge_params=(), device=0, world=1, rank=0,
+                 process_group=None):
+        self.world, self.rank = world, rank
+        self.part = domain.Partition(problem.neighbors, world, rank)
+        ids = self.part.global_ids
+        self.ctx = lib.Context(problem.system, problem.N, self.part.n_local,
+                               self.part.n_ghost, device)
+        ctx = self.ctx
+        ctx.set_geometry(problem.inverse_jacobian(ids), problem.coords(ids),
+                         self.part.local_neighbors)
+        ctx.set_static_fields(problem.static(ids))
+        if problem.system == lib.SYSTEM_GH and gauge != lib.GAUGE_HARMONIC:
+            ctx.set_gauge(gauge, gauge_params)
+        ctx.set_state(problem.u0(ids, t0))
+        ctx.set_stepper(stepper, order, t0, dt)
+        self.n_points = self.part.n_local * problem.N ** 3
+        self._pg = process_group
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            self._torch, self._dist = torch, dist
+            ctx.set_halo_map(self.part.send_map)
+            f = problem.N ** 2
+            per_face = ctx.halo_comps * f
+            self._send = torch.as_tensor(
+                _CudaArray(ctx.halo_send_ptr(), self.part.n_ghost * per_face),
+                device=f"cuda:{device}")
+            self._recv = torch.as_tensor(
+                _CudaArray(ctx.halo_recv_ptr(), self.part.n_ghost * per_face),
+                device=f"cuda:{device}")
+            self._stream = torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{device}")
+            # per-peer contiguous segments (both sides order faces identically)
+            self._segments = []
+            so = ro = 0
+            for peer in range(world):
+                ns, nr = self.part.send_counts[peer], self.part.recv_counts[peer]
+                if ns or nr:
+                    self._segments.append((peer, so * per_face, ns * per_face, ro * per_face,
+                                           nr * per_face))
+                so += ns
+                ro += nr
+
+    # -- one RHS + update ------------------------------------------------
+    def _substep(self) -> bool:
+        ctx = self.ctx
+        t = ctx.begin_substep()
+        if self.world == 1:
+            ctx.compute_time_derivative_range(t, 0, self.part.n_local)
+        else:
+            torch, dist = self._torch, self._dist
+            ctx.pack_halo()
+            with torch.cuda.stream(self._stream):
+                ops = []
+                for peer, so, ns, ro, nr in self._segments:
+                    if nr:
+                        ops.append(dist.P2POp(dist.irecv, self._recv[ro:ro + nr], peer,
+                                              group=self._pg))
+                    if ns:
+                        ops.append(dist.P2POp(dist.isend, self._send[so:so + ns], peer,
+                                              group=self._pg))
+                works = dist.batch_isend_irecv(ops) if ops else []
+                if self.part.n_interior > 0:
+                    ctx.compute_time_derivative_range(t, 0, self.part.n_interior)
+                for w in works:
+                    w.wait()
+            ctx.compute_time_derivative_range(t, self.part.n_interior, self.part.n_local)
+        return ctx.end_substep()
+
+    def take_steps(self, n: int):
+        done = 0
+        while done < n:
+            if self._substep():
+                done += 1
+
+    def gather_state(self, n_global: int):
+        """Global state in global element order (rank 0 result; all ranks call)."""
+        local = self.ctx.get_state()
+        if self.world == 1:
+            out = np.empty_like(local)
+            out[self.part.global_ids] = local
+            return out
+        torch, dist = self._torch, self._dist
+        pieces = [None] * self.world
+        dist.all_gather_object(pieces, (self.part.global_ids, local), group=self._pg)
+        out = np.empty((n_global,) + local.shape[1:])
+        for ids, vals in pieces:
+            out[ids] = vals
+        return out

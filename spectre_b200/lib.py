@@ -25,7 +25,7 @@ EXPORTS = [
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
     "dgrhs_take_steps", "dgrhs_time", "dgrhs_rhs_evaluations", "dgrhs_begin_substep",
-    "dgrhs_end_substep", "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
+    "dgrhs_end_substep", "dgrhs_time_kernels", "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
     "dgrhs_collocation_points_and_weights", "dgrhs_adams_bashforth_coefficients",
 ]
@@ -215,6 +215,12 @@ class Context:
     @property
     def rhs_evaluations(self):
         return int(self._lib.dgrhs_rhs_evaluations(self._h))
+
+    def time_kernels(self, reps=5, update_terms=3):
+        """Mean ms per launch of (face kernel, volume kernel, stepper update)."""
+        ms = np.zeros(3)
+        _check(self._lib.dgrhs_time_kernels(self._h, reps, update_terms, _ptr(ms)))
+        return ms
 
     def synchronize(self):
         _check(self._lib.dgrhs_synchronize(self._h))

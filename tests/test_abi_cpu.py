@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from spectre_b200 import lib
+from spectre_b200 import analytic, domain, lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -49,3 +49,18 @@ def test_no_cpu_fallback():
         lib.Context(lib.SYSTEM_SCALAR_WAVE, 4, 8)
     with pytest.raises(lib.DgrhsError, match="no CPU fallback"):
         lib.partial_derivatives(4, np.zeros((1, 64)), np.zeros((9, 64)))
+
+
+def test_product_analytic_data_matches_oracle():
+    """The product-side initial data (spectre_b200.analytic) against the
+    oracle's independent restatement."""
+    N = 5
+    brick = domain.Brick([0.5, 0.5, 0.5], [2.5] * 3, [1, 1, 1], N)
+    x = brick.coords()
+    for e in range(brick.n_elements):
+        ref = orc.gh_vars_from_metric(*orc.gauge_wave_metric(x[e], 0.3))
+        np.testing.assert_allclose(analytic.gauge_wave(x[e], 0.3), ref, rtol=1e-13, atol=1e-14)
+        ref = orc.gh_vars_from_metric(*orc.kerr_schild_metric(x[e]))
+        np.testing.assert_allclose(analytic.kerr_schild(x[e]), ref, rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(analytic.plane_wave(x[e], 0.2), orc.plane_wave(x[e], 0.2),
+                                   rtol=1e-13, atol=1e-14)
