@@ -37,6 +37,13 @@ struct Cfg {
   // volume kernel: one CTA per (element, chunk of <= 256 points)
   static constexpr int nchunk = (n + 255) / 256;
   static constexpr int T = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
+  // GH volume kernel ring: one stage = the 5 component rows of a (mu,nu) pair
+  // plus that pair's block of lifted face corrections [6][5][f]
+  static constexpr int stage_doubles = 5 * npad + 30 * f;
+  static constexpr int fixed_bytes = (10 * T + (N * N + 1) / 2 * 2) * 8 + 64;
+  static constexpr int max_stages = (232448 - fixed_bytes) / (stage_doubles * 8);
+  static constexpr int nstage = max_stages >= 4 ? 4 : max_stages;
+  static_assert(nstage >= 2, "element too large for the shared-memory ring");
 };
 
 __host__ __device__ constexpr int padded_points(int N) {
@@ -155,7 +162,7 @@ struct GhVolArgs {
   double* dt;            // [E][50][npad]
   const double* invjac;  // [E][9][npad]
   const double* stat;    // [E][3][npad]   gamma0, gamma1, gamma2
-  const double* corr;    // [E][6][50][f] or nullptr (volume only)
+  const double* corr;    // [E][10][6][5][f] pair-major, or nullptr (volume only)
   const double* gH;      // [E][4][npad]   gauge H_a      (non-harmonic)
   const double* gdH;     // [E][16][npad]  d_a H_b, a+4b  (non-harmonic)
   const double* D;       // [N*N] row-major differentiation matrix
@@ -164,16 +171,16 @@ struct GhVolArgs {
 
 template <int N>
 constexpr int gh_volume_smem_bytes() {
-  return (2 * 5 * Cfg<N>::npad + 10 * Cfg<N>::T + (N * N + 1) / 2 * 2) * 8 + 2 * 8;
+  return Cfg<N>::nstage * Cfg<N>::stage_doubles * 8 + Cfg<N>::fixed_bytes;
 }
 
 template <int N, bool kHarmonic>
 __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
-  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, T = Cfg<N>::T;
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, T = Cfg<N>::T, f = N * N;
+  constexpr int NS = Cfg<N>::nstage, SD = Cfg<N>::stage_doubles;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* tile0 = reinterpret_cast<double*>(smem_raw);
-  double* tile1 = tile0 + 5 * npad;
-  double* sQ = tile1 + 5 * npad;
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  double* sQ = ring + NS * SD;
   double* sD = sQ + 10 * T;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (N * N + 1) / 2 * 2);
 
@@ -183,22 +190,26 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
   const int pt = chunk * T + tid;
   const bool active = pt < n;
   const double* __restrict__ ue = a.u + (size_t)e * 50 * npad;
+  const bool with_corr = a.corr != nullptr;
+  const double* __restrict__ ce = with_corr ? a.corr + (size_t)e * 10 * 30 * f : nullptr;
 
   // stage the 5 components of pair s = (g_s, Pi_s, Phi_0s, Phi_1s, Phi_2s)
+  // and the pair's face corrections
   auto issue = [&](int s, int stage) {
-    double* t = stage ? tile1 : tile0;
-    mbar_expect_tx(&bars[stage], 5 * npad * 8);
+    double* t = ring + stage * SD;
+    mbar_expect_tx(&bars[stage], (5 * npad + (with_corr ? 30 * f : 0)) * 8);
     tma_bulk_g2s(t, ue + (size_t)s * npad, npad * 8, &bars[stage]);
     tma_bulk_g2s(t + npad, ue + (size_t)(10 + s) * npad, npad * 8, &bars[stage]);
     tma_bulk_g2s(t + 2 * npad, ue + (size_t)(20 + 3 * s) * npad, 3 * npad * 8,
                  &bars[stage]);
+    if (with_corr) tma_bulk_g2s(t + 5 * npad, ce + (size_t)s * 30 * f, 30 * f * 8, &bars[stage]);
   };
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int st = 0; st < NS; ++st) mbar_init(&bars[st], 1);
     mbar_fence_init();
-    issue(0, 0);
-    issue(1, 1);
+#pragma unroll
+    for (int st = 0; st < NS; ++st) issue(st, st);
   }
   for (int idx = tid; idx < N * N; idx += T) sD[idx] = a.D[idx];
 
@@ -250,15 +261,13 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
     }
   }
   double* __restrict__ dte = a.dt + (size_t)e * 50 * npad;
-  const double* __restrict__ corr_e =
-      a.corr ? a.corr + (size_t)e * 6 * 50 * (N * N) : nullptr;
 
-  // ---- stream the ten (mu,nu) pairs through the two-stage ring ----
+  // ---- stream the ten (mu,nu) pairs through the ring ----
 #pragma unroll 1
   for (int s = 0; s < 10; ++s) {
-    const int stage = s & 1;
-    mbar_wait(&bars[stage], (s >> 1) & 1);
-    const double* t = stage ? tile1 : tile0;
+    const int stage = s % NS;
+    mbar_wait(&bars[stage], (s / NS) & 1);
+    const double* t = ring + stage * SD;
     if (active) {
       double dg[3], dpi[3], dph[3][3], ph[3];
       logical_derivs<N>(t, i, j, k, Di, Dj, Dk, dg);
@@ -268,23 +277,27 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
         logical_derivs<N>(t + (2 + m) * npad, i, j, k, Di, Dj, Dk, dph[m]);
         ph[m] = t[(2 + m) * npad + pt];
       }
-      double og, opi, oph[3];
-      gh_pair_rhs(ctx, sQ[s * T + tid], t[pt], t[npad + pt], ph, dg, dpi, dph, og,
-                  opi, oph);
-      if (corr_e) {
-        og = add_corrections<N, 50>(og, corr_e, s, i, j, k);
-        opi = add_corrections<N, 50>(opi, corr_e, 10 + s, i, j, k);
-#pragma unroll
-        for (int m = 0; m < 3; ++m)
-          oph[m] = add_corrections<N, 50>(oph[m], corr_e, 20 + m + 3 * s, i, j, k);
+      double o[5];
+      {
+        double oph[3];
+        gh_pair_rhs(ctx, sQ[s * T + tid], t[pt], t[npad + pt], ph, dg, dpi, dph, o[0],
+                    o[1], oph);
+        o[2] = oph[0];
+        o[3] = oph[1];
+        o[4] = oph[2];
       }
-      dte[(size_t)s * npad + pt] = og;
-      dte[(size_t)(10 + s) * npad + pt] = opi;
+      if (with_corr) {
+        const double* cs = t + 5 * npad;  // [6][5][f]
 #pragma unroll
-      for (int m = 0; m < 3; ++m) dte[(size_t)(20 + m + 3 * s) * npad + pt] = oph[m];
+        for (int c = 0; c < 5; ++c) o[c] = add_corrections<N, 5>(o[c], cs, c, i, j, k);
+      }
+      dte[(size_t)s * npad + pt] = o[0];
+      dte[(size_t)(10 + s) * npad + pt] = o[1];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) dte[(size_t)(20 + m + 3 * s) * npad + pt] = o[2 + m];
     }
     __syncthreads();  // every reader is done with this stage
-    if (tid == 0 && s + 2 < 10) issue(s + 2, stage);
+    if (tid == 0 && s + NS < 10) issue(s + NS, stage);
   }
 }
 
@@ -388,11 +401,15 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   const int qa = q % N, qb = q / N;
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
-  double* __restrict__ corr = a.corr + ((size_t)e * 6 + d) * 50 * f + q;
+  // pair-major layout [e][pair s][direction][5][f]: the volume kernel stages
+  // one pair block per TMA copy
+  double* __restrict__ corr = a.corr + (size_t)e * 10 * 30 * f + (size_t)d * 5 * f + q;
   const int nb = a.nbr[e * 6 + d];
   if (nb == -1) {
 #pragma unroll 1
-    for (int c = 0; c < 50; ++c) corr[(size_t)c * f] = 0.0;
+    for (int s = 0; s < 10; ++s)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) corr[((size_t)s * 30 + c) * f] = 0.0;
     return;
   }
   const int p_own = face_point<N>(d, qa, qb);
@@ -452,10 +469,11 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
                     phi_e, ke);
     double cg, cp, cph[3];
     gh_pair_boundary_terms(si, se, ki, ke, cg, cp, cph);
-    corr[(size_t)s * f] = cg * lift;
-    corr[(size_t)(10 + s) * f] = cp * lift;
+    double* cs = corr + (size_t)s * 30 * f;
+    cs[0] = cg * lift;
+    cs[(size_t)f] = cp * lift;
 #pragma unroll
-    for (int m = 0; m < 3; ++m) corr[(size_t)(20 + m + 3 * s) * f] = cph[m] * lift;
+    for (int m = 0; m < 3; ++m) cs[(size_t)(2 + m) * f] = cph[m] * lift;
   }
 }
 
