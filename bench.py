@@ -204,6 +204,9 @@ def main():
     ap.add_argument("--cpu-sample-refine", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="multi-GPU: compare the gathered state bit-for-bit with a single-GPU "
+                         "evolution of the same global problem on rank 0 (small configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -275,6 +278,21 @@ def main():
     exact = problem.u0(ev.part.global_ids[:8], ctx.time)
     err = float(np.max(np.abs(state[:8] - exact)))
     assert err < 1e-3, f"solution drifted from the exact gauge wave: {err}"
+
+    if args.verify and world > 1:
+        n_global = problem.brick.n_elements
+        steps_total = args.warmup + args.steps
+        gathered = ev.gather_state(n_global)
+        if rank == 0:
+            ref_ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, args.dt, 0.0,
+                                         gauge, (0.1, 1.0) if args.gauge == "analytic" else (),
+                                         local_rank)
+            ref_ev.take_steps(steps_total)
+            same = np.array_equal(ref_ev.gather_state(n_global), gathered)
+            print(f"[verify] {world}-rank state bit-identical to single-GPU state: {same}",
+                  file=sys.stderr)
+            assert same, "multi-GPU evolution differs from the single-GPU evolution"
+            ref_ev.ctx.close()
 
     # per-kernel roofline (CUDA events inside the library, same stream)
     kms = ctx.time_kernels(reps=5, update_terms=3)

@@ -33,6 +33,35 @@ class _CudaArray:
         }
 
 
+class HaloExchange:
+    """The one exchange step of the path: every cut mortar face travels to the
+    rank that owns the neighbouring element (point-to-point, no collective).
+    Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU
+    tests); buffers are flat float64 tensors [n_ghost * per_face]."""
+
+    def __init__(self, part, per_face, dist, group=None):
+        self.dist, self.group = dist, group
+        self.segments = []
+        so = ro = 0
+        for peer in range(part.world):
+            ns, nr = part.send_counts[peer], part.recv_counts[peer]
+            if ns or nr:
+                self.segments.append((peer, so * per_face, ns * per_face, ro * per_face,
+                                      nr * per_face))
+            so += ns
+            ro += nr
+
+    def start(self, send, recv):
+        dist = self.dist
+        ops = []
+        for peer, so, ns, ro, nr in self.segments:
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, recv[ro:ro + nr], peer, group=self.group))
+            if ns:
+                ops.append(dist.P2POp(dist.isend, send[so:so + ns], peer, group=self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+
 class Problem:
     """A BASELINE.json configuration; per-element data are built on demand for
     the element subset a rank owns (global arrays would not fit at 8 GPUs)."""
@@ -111,16 +140,7 @@ class Evolution:
                 _CudaArray(ctx.halo_recv_ptr(), self.part.n_ghost * per_face),
                 device=f"cuda:{device}")
             self._stream = torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{device}")
-            # per-peer contiguous segments (both sides order faces identically)
-            self._segments = []
-            so = ro = 0
-            for peer in range(world):
-                ns, nr = self.part.send_counts[peer], self.part.recv_counts[peer]
-                if ns or nr:
-                    self._segments.append((peer, so * per_face, ns * per_face, ro * per_face,
-                                           nr * per_face))
-                so += ns
-                ro += nr
+            self._halo = HaloExchange(self.part, per_face, dist, process_group)
 
     # -- one RHS + update ------------------------------------------------
     def _substep(self) -> bool:
@@ -132,15 +152,7 @@ class Evolution:
             torch, dist = self._torch, self._dist
             ctx.pack_halo()
             with torch.cuda.stream(self._stream):
-                ops = []
-                for peer, so, ns, ro, nr in self._segments:
-                    if nr:
-                        ops.append(dist.P2POp(dist.irecv, self._recv[ro:ro + nr], peer,
-                                              group=self._pg))
-                    if ns:
-                        ops.append(dist.P2POp(dist.isend, self._send[so:so + ns], peer,
-                                              group=self._pg))
-                works = dist.batch_isend_irecv(ops) if ops else []
+                works = self._halo.start(self._send, self._recv)
                 if self.part.n_interior > 0:
                     ctx.compute_time_derivative_range(t, 0, self.part.n_interior)
                 for w in works:

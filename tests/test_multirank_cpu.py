@@ -1,0 +1,119 @@
+"""World-size-2 (and 4) gloo tests of the multi-GPU host logic on CPU: the
+Z-curve partition, interior/boundary ordering, halo slot numbering and the
+point-to-point exchange schedule (spectre_b200.domain.Partition and
+spectre_b200.evolution.HaloExchange).  The face packing that the pack_halo
+kernel does on the GPU is emulated with numpy here."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spectre_b200 import domain
+from spectre_b200.evolution import HaloExchange
+
+N = 3
+F = N * N
+HC = 7  # components per face point in this test
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _face_points(d):
+    dim, side = d // 2, d % 2
+    fixed = N - 1 if side else 0
+    q = np.arange(F)
+    a, b = q % N, q // N
+    if dim == 0:
+        return fixed + N * (a + N * b)
+    if dim == 1:
+        return a + N * (fixed + N * b)
+    return a + N * (b + N * fixed)
+
+
+def _field(global_element, n_elements):
+    """Deterministic per-element data [HC, n] that identifies element and point."""
+    n = N ** 3
+    c = np.arange(HC)[:, None]
+    p = np.arange(n)[None, :]
+    return global_element * 1000.0 + c * 100.0 + p
+
+
+def _worker(rank, world, port, refinement, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    brick = domain.Brick([0, 0, 0], [1, 1, 1], refinement, N)
+    nb = brick.neighbors()
+    part = domain.Partition(nb, world, rank)
+    # local ordering: interior first, boundary last; ghosts only on boundary elements
+    ln = part.local_neighbors
+    assert (ln[:part.n_interior] >= -1).all()
+    assert ((ln[part.n_interior:] <= -2).any(axis=1)).all()
+    # pack (numpy emulation of pack_halo_kernel)
+    send = torch.zeros(part.n_ghost * HC * F, dtype=torch.float64)
+    sv = send.numpy().reshape(part.n_ghost, HC, F)
+    for slot, (le, d) in enumerate(part.send_map):
+        sv[slot] = _field(part.global_ids[le], brick.n_elements)[:, _face_points(d)]
+    recv = torch.full((part.n_ghost * HC * F,), -1.0, dtype=torch.float64)
+    halo = HaloExchange(part, HC * F, dist)
+    for w in halo.start(send, recv):
+        w.wait()
+    rv = recv.numpy().reshape(part.n_ghost, HC, F)
+    # every ghost slot must hold the face of the true neighbour, seen from its side
+    checked = 0
+    for le in range(part.n_local):
+        for d in range(6):
+            v = ln[le, d]
+            if v <= -2:
+                g_nb = nb[part.global_ids[le], d]
+                expect = _field(g_nb, brick.n_elements)[:, _face_points(d ^ 1)]
+                np.testing.assert_array_equal(rv[-(v + 2)], expect)
+                checked += 1
+            elif v >= 0:
+                assert part.global_ids[v] == nb[part.global_ids[le], d]
+    assert checked == part.n_ghost
+    # partitions tile the element list
+    counts = [None] * world
+    dist.all_gather_object(counts, (part.n_local, sorted(part.global_ids.tolist())))
+    if rank == 0:
+        all_ids = sorted(sum((c[1] for c in counts), []))
+        assert all_ids == list(range(brick.n_elements))
+        assert max(c[0] for c in counts) - min(c[0] for c in counts) <= 1
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,refinement", [(2, [1, 1, 1]), (2, [2, 1, 1]), (4, [2, 2, 1])])
+def test_partition_and_halo_exchange_gloo(world, refinement):
+    mp.spawn(_worker, args=(world, _free_port(), refinement, None), nprocs=world, join=True)
+
+
+def test_partition_single_rank_has_no_ghosts():
+    brick = domain.Brick([0, 0, 0], [1, 1, 1], [2, 2, 2], 4)
+    part = domain.Partition(brick.neighbors(), 1, 0)
+    assert part.n_ghost == 0 and part.n_interior == part.n_local == 64
+    np.testing.assert_array_equal(part.local_neighbors, brick.neighbors())
+
+
+def test_z_curve_order_matches_reference_bit_interleave():
+    """ZCurve.cpp:17-80: for equal refinement the index is the Morton code
+    with x as the least significant bit."""
+    for (ix, iy, iz) in [(1, 0, 0), (0, 1, 0), (0, 0, 1), (3, 2, 1), (5, 7, 2)]:
+        want = 0
+        for b in range(3):
+            want |= ((ix >> b) & 1) << (3 * b) | ((iy >> b) & 1) << (3 * b + 1) | \
+                ((iz >> b) & 1) << (3 * b + 2)
+        assert domain.z_curve_index(ix, iy, iz, (3, 3, 3)) == want
+    # unequal refinement: dimensions with level 0 are skipped
+    assert domain.z_curve_index(1, 0, 1, (1, 0, 1)) == 0b11
+    assert domain.z_curve_index(2, 0, 1, (2, 0, 1)) == 0b101
