@@ -176,6 +176,50 @@ int dgrhs_padded_points(dgrhs_ctx* ctx);
  * u [n_comps][n], inv_jacobian [9][n] -> du [3*n_comps][n], d_i u_c at 3c+i */
 int dgrhs_partial_derivatives(int n_points_1d, int n_comps, const double* u,
                               const double* inv_jacobian, double* du);
+/* gh::TimeDerivative<3>::apply (GeneralizedHarmonic/TimeDerivative.hpp:143-192,
+ * TimeDerivative.cpp:31-407) for n points of one element: u [50][n] (g, Pi,
+ * Phi), du [150][n] (d_i of component c at 3c+i, i.e. d_spacetime_metric,
+ * d_pi, d_phi), gamma0/1/2 [n]; harmonic != 0 selects gauges::Harmonic,
+ * otherwise H_a [4][n] and d_a H_b [16][n] (a + 4b) are the output of
+ * gauges::dispatch.  Output dt_u [50][n].  The 29 temporary tensors of the
+ * reference signature are not materialised. */
+int dgrhs_gh_time_derivative(int n, const double* u, const double* du,
+                             const double* gamma0, const double* gamma1,
+                             const double* gamma2, int harmonic,
+                             const double* gauge_h, const double* d4_gauge_h,
+                             double* dt_u);
+/* ScalarWave::TimeDerivative<3>::apply (ScalarWave/TimeDerivative.hpp:26-50,
+ * TimeDerivative.cpp:14-45): u [5][n], du [15][n], gamma2 [n] -> dt_u [5][n] */
+int dgrhs_sw_time_derivative(int n, const double* u, const double* du,
+                             const double* gamma2, double* dt_u);
+/* gh::BoundaryCorrections::UpwindPenalty<3>::dg_package_data
+ * (UpwindPenalty.hpp:226-262, UpwindPenalty.cpp:36-158) on f face points:
+ * packaged [134][f] in dg_package_field_tags order (v_g 10 | v_zero 30 |
+ * v_plus 10 | v_minus 10 | n v_plus 30 | n v_minus 30 | gamma2 v_g 10 |
+ * speeds 4); returns the max char speed like the reference. */
+int dgrhs_gh_package_data(int f, const double* u, const double* gamma1,
+                          const double* gamma2, const double* lapse,
+                          const double* shift, const double* normal_covector,
+                          const double* normal_vector, double* packaged,
+                          double* max_abs_char_speed);
+/* ...::dg_boundary_terms (UpwindPenalty.cpp:161-275): [134][f] x2 -> [50][f] */
+int dgrhs_gh_boundary_terms(int f, const double* packaged_int,
+                            const double* packaged_ext,
+                            double* boundary_correction);
+/* ScalarWave::BoundaryCorrections::UpwindPenalty<3> (UpwindPenalty.hpp:211-260,
+ * UpwindPenalty.cpp:36-205): packaged [16][f], correction [5][f] */
+int dgrhs_sw_package_data(int f, const double* u, const double* gamma2,
+                          const double* normal_covector, double* packaged,
+                          double* max_abs_char_speed);
+int dgrhs_sw_boundary_terms(int f, const double* packaged_int,
+                            const double* packaged_ext,
+                            double* boundary_correction);
+/* dg::lift_flux (NumericalAlgorithms/DiscontinuousGalerkin/LiftFlux.hpp:41-62),
+ * in place on [n_comps][f] */
+int dgrhs_lift_flux(int f, int n_comps, double* boundary_correction,
+                    int extent_perpendicular_to_boundary,
+                    const double* magnitude_of_face_normal);
+
 /* Spectral::differentiation_matrix(Mesh<1>{N, Legendre, GaussLobatto})
  * (Spectral.cpp:431-445), row-major D[i*N + j]; collocation points/weights
  * (Legendre.cpp:187-232). */

@@ -411,6 +411,10 @@ int ab_update(dgrhs_ctx* c, int order, long long start, long long end) {
 // ---------------------------------------------------------------------------
 extern "C" {
 
+// shared with operators.cu (not part of the public header)
+void dgrhs_internal_set_error(const char* msg) { g_error = msg; }
+void dgrhs_internal_count_launch(void) { ++g_launches; }
+
 const char* dgrhs_last_error(void) { return g_error.c_str(); }
 int64_t dgrhs_kernel_launch_count(void) { return g_launches; }
 

@@ -1,0 +1,415 @@
+// Single-operator entry points of include/dgrhs.h: GPU forwards with the
+// argument meaning of the reference's per-element operator surface
+// (TimeDerivative::apply, UpwindPenalty::dg_package_data / dg_boundary_terms,
+// lift_flux).  Host pointers in, host pointers out; the data make one round
+// trip over PCIe per call, so these are for drop-in use at operator
+// granularity and for parity tests that read like the reference's own unit
+// tests -- the batched context API is the fast path.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/dgrhs.h"
+#include "pointwise.cuh"
+
+extern "C" void dgrhs_internal_set_error(const char* msg);
+extern "C" void dgrhs_internal_count_launch(void);
+
+namespace {
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  dgrhs_internal_set_error(buf);
+  return 1;
+}
+
+#define CU(call)                                                             \
+  do {                                                                       \
+    cudaError_t err__ = (call);                                              \
+    if (err__ != cudaSuccess)                                                \
+      return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+                  __FILE__, __LINE__);                                       \
+  } while (0)
+
+int need_gpu() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available: this library has no CPU fallback");
+  return 0;
+}
+
+// RAII device staging of host arrays
+struct Staged {
+  std::vector<void*> ptrs;
+  ~Staged() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  double* in(const double* h, size_t count) {
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, std::max<size_t>(count, 1) * 8) != cudaSuccess) return nullptr;
+    ptrs.push_back(d);
+    if (h && cudaMemcpy(d, h, count * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return d;
+  }
+};
+
+// gh::TimeDerivative<3>::apply on given derivatives (TimeDerivative.cpp:31-407)
+template <bool kHarmonic>
+__global__ void gh_time_derivative_kernel(int n, const double* u, const double* du,
+                                          const double* g0, const double* g1,
+                                          const double* g2, const double* H,
+                                          const double* dH, double* dt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double g[10], pi[10], phi[3][10], J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, Q[10];
+#pragma unroll
+  for (int s = 0; s < 10; ++s) {
+    g[s] = u[(size_t)s * n + p];
+    pi[s] = u[(size_t)(10 + s) * n + p];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) phi[m][s] = u[(size_t)(20 + m + 3 * s) * n + p];
+  }
+  dg::GaugeH gh;
+  if (!kHarmonic) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      gh.H[a] = H[(size_t)a * n + p];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) gh.dH[a][b] = dH[(size_t)(a + 4 * b) * n + p];
+    }
+  }
+  dg::GhContext ctx;
+  dg::gh_prologue<kHarmonic>(g, pi, phi, J, g0[p], g1[p], g2[p], &gh, ctx, Q);
+#pragma unroll 1
+  for (int s = 0; s < 10; ++s) {
+    double ph[3], dgv[3], dpi[3], dph[3][3], og, op, oph[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) ph[m] = u[(size_t)(20 + m + 3 * s) * n + p];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      dgv[i] = du[(size_t)(3 * s + i) * n + p];
+      dpi[i] = du[(size_t)(3 * (10 + s) + i) * n + p];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) dph[m][i] = du[(size_t)(3 * (20 + m + 3 * s) + i) * n + p];
+    }
+    // Q is indexed dynamically: select from the register array
+    double Qs = Q[0];
+#pragma unroll
+    for (int t = 1; t < 10; ++t) Qs = (s == t) ? Q[t] : Qs;
+    dg::gh_pair_rhs(ctx, Qs, u[(size_t)s * n + p], u[(size_t)(10 + s) * n + p], ph, dgv, dpi,
+                    dph, og, op, oph);
+    dt[(size_t)s * n + p] = og;
+    dt[(size_t)(10 + s) * n + p] = op;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) dt[(size_t)(20 + m + 3 * s) * n + p] = oph[m];
+  }
+}
+
+__global__ void sw_time_derivative_kernel(int n, const double* u, const double* du,
+                                          const double* gamma2, double* dt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double up[5], d[5][3], out[5];
+  const double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    up[c] = u[(size_t)c * n + p];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[c][i] = du[(size_t)(3 * c + i) * n + p];
+  }
+  dg::sw_point_rhs(up, d, J, gamma2[p], out);
+#pragma unroll
+  for (int c = 0; c < 5; ++c) dt[(size_t)c * n + p] = out[c];
+}
+
+// gh UpwindPenalty::dg_package_data with lapse, shift and both normals given
+// (UpwindPenalty.cpp:36-158); packaged order of dg_package_field_tags
+__global__ void gh_package_kernel(int f, const double* u, const double* g1,
+                                  const double* g2, const double* lapse,
+                                  const double* shift, const double* n_lo,
+                                  const double* n_up, double* pk, double* max_speed) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f) return;
+  dg::GhFaceSide s;
+  double sdn = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.n_lo[i] = n_lo[(size_t)i * f + p];
+    s.n_up[i] = n_up[(size_t)i * f + p];
+    sdn += shift[(size_t)i * f + p] * s.n_lo[i];
+  }
+  sdn = -sdn;
+  s.speed[1] = sdn;
+  s.speed[0] = (1.0 + g1[p]) * sdn;
+  s.speed[2] = lapse[p] + sdn;
+  s.speed[3] = -lapse[p] + sdn;
+  s.gamma2 = g2[p];
+  s.mag = 1.0;
+#pragma unroll 1
+  for (int a = 0; a < 10; ++a) {
+    double ph[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) ph[m] = u[(size_t)(20 + m + 3 * a) * f + p];
+    dg::GhPairPackaged k;
+    dg::gh_pair_package(s, u[(size_t)a * f + p], u[(size_t)(10 + a) * f + p], ph, k);
+    pk[(size_t)a * f + p] = k.v_g;
+    pk[(size_t)(40 + a) * f + p] = k.v_plus;
+    pk[(size_t)(50 + a) * f + p] = k.v_minus;
+    pk[(size_t)(120 + a) * f + p] = k.g2_v_g;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      pk[(size_t)(10 + m + 3 * a) * f + p] = k.v_zero[m];
+      pk[(size_t)(60 + m + 3 * a) * f + p] = k.v_plus * s.n_lo[m];
+      pk[(size_t)(90 + m + 3 * a) * f + p] = k.v_minus * s.n_lo[m];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) pk[(size_t)(130 + c) * f + p] = s.speed[c];
+  max_speed[p] = fmax(fmax(s.speed[0], s.speed[1]), fmax(s.speed[2], s.speed[3]));
+}
+
+// gh UpwindPenalty::dg_boundary_terms (UpwindPenalty.cpp:161-275)
+__global__ void gh_boundary_terms_kernel(int f, const double* in, const double* ex,
+                                         double* corr) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f) return;
+  double wi[4], we[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    wi[c] = dg::step_function(-in[(size_t)(130 + c) * f + p]);
+    we[c] = -dg::step_function(ex[(size_t)(130 + c) * f + p]);
+  }
+#pragma unroll 1
+  for (int a = 0; a < 10; ++a) {
+    auto I = [&](int c) { return in[(size_t)c * f + p]; };
+    auto E = [&](int c) { return ex[(size_t)c * f + p]; };
+    corr[(size_t)a * f + p] = we[0] * E(a) - wi[0] * I(a);
+    corr[(size_t)(10 + a) * f + p] =
+        0.5 * (we[2] * E(40 + a) + we[3] * E(50 + a)) + we[0] * E(120 + a) -
+        0.5 * (wi[2] * I(40 + a) + wi[3] * I(50 + a)) - wi[0] * I(120 + a);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int k = d + 3 * a;
+      corr[(size_t)(20 + k) * f + p] =
+          -0.5 * (we[3] * E(90 + k) - we[2] * E(60 + k)) + we[1] * E(10 + k) -
+          0.5 * (wi[2] * I(60 + k) - wi[3] * I(90 + k)) - wi[1] * I(10 + k);
+    }
+  }
+}
+
+// ScalarWave UpwindPenalty (UpwindPenalty.cpp:36-205), packaged order of
+// dg_package_field_tags: v_psi, v_zero(3), v_plus, v_minus, n v_plus(3),
+// n v_minus(3), gamma2 v_psi, speeds(3)
+__global__ void sw_package_kernel(int f, const double* u, const double* gamma2,
+                                  const double* n, double* pk, double* max_speed) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f) return;
+  const double psi = u[p], pi = u[(size_t)f + p];
+  double phi[3], nn[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    phi[i] = u[(size_t)(2 + i) * f + p];
+    nn[i] = n[(size_t)i * f + p];
+  }
+  const double cs[3] = {0.0, 1.0, -1.0};
+  const double g2psi = gamma2[p] * psi;
+  double ndphi = nn[0] * phi[0];
+  ndphi += nn[1] * phi[1];
+  ndphi += nn[2] * phi[2];
+  const double vp = cs[1] * (pi + ndphi - g2psi), vm = cs[2] * (pi - ndphi - g2psi);
+  pk[p] = cs[0] * psi;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    pk[(size_t)(1 + i) * f + p] = cs[0] * (phi[i] - nn[i] * ndphi);
+    pk[(size_t)(6 + i) * f + p] = vp * nn[i];
+    pk[(size_t)(9 + i) * f + p] = vm * nn[i];
+    pk[(size_t)(13 + i) * f + p] = cs[i];
+  }
+  pk[(size_t)4 * f + p] = vp;
+  pk[(size_t)5 * f + p] = vm;
+  pk[(size_t)12 * f + p] = g2psi * cs[0];
+  max_speed[p] = 1.0;
+}
+
+__global__ void sw_boundary_terms_kernel(int f, const double* in, const double* ex,
+                                         double* corr) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f) return;
+  auto I = [&](int c) { return in[(size_t)c * f + p]; };
+  auto E = [&](int c) { return ex[(size_t)c * f + p]; };
+  const double w0i = dg::step_function(-I(13)), w0e = -dg::step_function(E(13));
+  const double wpi = dg::step_function(-I(14)), wpe = -dg::step_function(E(14));
+  const double wmi = dg::step_function(-I(15)), wme = -dg::step_function(E(15));
+  corr[p] = w0e * E(0) - w0i * I(0);
+  corr[(size_t)f + p] = 0.5 * (wpe * E(4) + wme * E(5)) + w0e * E(12) -
+                        0.5 * (wpi * I(4) + wmi * I(5)) - w0i * I(12);
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    corr[(size_t)(2 + d) * f + p] = 0.5 * (wpe * E(6 + d) - wme * E(9 + d)) + w0e * E(1 + d) -
+                                    0.5 * (wpi * I(6 + d) - wmi * I(9 + d)) - w0i * I(1 + d);
+}
+
+// dg::lift_flux (LiftFlux.hpp:57-61)
+__global__ void lift_flux_kernel(int f, int ncomp, double* corr, int extent,
+                                 const double* mag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f) return;
+  const double s = -0.5 * (double)(extent * (extent - 1)) * mag[p];
+  for (int c = 0; c < ncomp; ++c) corr[(size_t)c * f + p] *= s;
+}
+
+int grid(int n) { return (n + 127) / 128; }
+
+}  // namespace
+
+extern "C" {
+
+int dgrhs_gh_time_derivative(int n, const double* u, const double* du,
+                             const double* gamma0, const double* gamma1,
+                             const double* gamma2, int harmonic, const double* gauge_h,
+                             const double* d4_gauge_h, double* dt_u) {
+  if (need_gpu()) return 1;
+  if (n < 1) return fail("n must be positive");
+  if (!harmonic && (!gauge_h || !d4_gauge_h)) return fail("gauge fields required");
+  Staged st;
+  double* d_u = st.in(u, (size_t)50 * n);
+  double* d_du = st.in(du, (size_t)150 * n);
+  double* d_g0 = st.in(gamma0, n);
+  double* d_g1 = st.in(gamma1, n);
+  double* d_g2 = st.in(gamma2, n);
+  double* d_H = st.in(harmonic ? nullptr : gauge_h, (size_t)4 * n);
+  double* d_dH = st.in(harmonic ? nullptr : d4_gauge_h, (size_t)16 * n);
+  double* d_dt = st.in(nullptr, (size_t)50 * n);
+  if (!d_u || !d_du || !d_g0 || !d_g1 || !d_g2 || !d_H || !d_dH || !d_dt)
+    return fail("device staging failed");
+  if (harmonic)
+    gh_time_derivative_kernel<true><<<grid(n), 128>>>(n, d_u, d_du, d_g0, d_g1, d_g2, d_H, d_dH, d_dt);
+  else
+    gh_time_derivative_kernel<false><<<grid(n), 128>>>(n, d_u, d_du, d_g0, d_g1, d_g2, d_H, d_dH, d_dt);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(dt_u, d_dt, (size_t)50 * n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dgrhs_sw_time_derivative(int n, const double* u, const double* du,
+                             const double* gamma2, double* dt_u) {
+  if (need_gpu()) return 1;
+  if (n < 1) return fail("n must be positive");
+  Staged st;
+  double* d_u = st.in(u, (size_t)5 * n);
+  double* d_du = st.in(du, (size_t)15 * n);
+  double* d_g2 = st.in(gamma2, n);
+  double* d_dt = st.in(nullptr, (size_t)5 * n);
+  if (!d_u || !d_du || !d_g2 || !d_dt) return fail("device staging failed");
+  sw_time_derivative_kernel<<<grid(n), 128>>>(n, d_u, d_du, d_g2, d_dt);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(dt_u, d_dt, (size_t)5 * n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dgrhs_gh_package_data(int f, const double* u, const double* gamma1,
+                          const double* gamma2, const double* lapse, const double* shift,
+                          const double* normal_covector, const double* normal_vector,
+                          double* packaged, double* max_abs_char_speed) {
+  if (need_gpu()) return 1;
+  if (f < 1) return fail("f must be positive");
+  Staged st;
+  double* d_u = st.in(u, (size_t)50 * f);
+  double* d_g1 = st.in(gamma1, f);
+  double* d_g2 = st.in(gamma2, f);
+  double* d_l = st.in(lapse, f);
+  double* d_s = st.in(shift, (size_t)3 * f);
+  double* d_nl = st.in(normal_covector, (size_t)3 * f);
+  double* d_nu = st.in(normal_vector, (size_t)3 * f);
+  double* d_pk = st.in(nullptr, (size_t)134 * f);
+  double* d_ms = st.in(nullptr, f);
+  if (!d_u || !d_g1 || !d_g2 || !d_l || !d_s || !d_nl || !d_nu || !d_pk || !d_ms)
+    return fail("device staging failed");
+  gh_package_kernel<<<grid(f), 128>>>(f, d_u, d_g1, d_g2, d_l, d_s, d_nl, d_nu, d_pk, d_ms);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(packaged, d_pk, (size_t)134 * f * 8, cudaMemcpyDeviceToHost));
+  if (max_abs_char_speed) {
+    std::vector<double> ms(f);
+    CU(cudaMemcpy(ms.data(), d_ms, (size_t)f * 8, cudaMemcpyDeviceToHost));
+    double m = ms[0];
+    for (double v : ms) m = v > m ? v : m;
+    *max_abs_char_speed = m;
+  }
+  return 0;
+}
+
+int dgrhs_gh_boundary_terms(int f, const double* packaged_int, const double* packaged_ext,
+                            double* boundary_correction) {
+  if (need_gpu()) return 1;
+  Staged st;
+  double* d_i = st.in(packaged_int, (size_t)134 * f);
+  double* d_e = st.in(packaged_ext, (size_t)134 * f);
+  double* d_c = st.in(nullptr, (size_t)50 * f);
+  if (!d_i || !d_e || !d_c) return fail("device staging failed");
+  gh_boundary_terms_kernel<<<grid(f), 128>>>(f, d_i, d_e, d_c);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(boundary_correction, d_c, (size_t)50 * f * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dgrhs_sw_package_data(int f, const double* u, const double* gamma2,
+                          const double* normal_covector, double* packaged,
+                          double* max_abs_char_speed) {
+  if (need_gpu()) return 1;
+  Staged st;
+  double* d_u = st.in(u, (size_t)5 * f);
+  double* d_g2 = st.in(gamma2, f);
+  double* d_n = st.in(normal_covector, (size_t)3 * f);
+  double* d_pk = st.in(nullptr, (size_t)16 * f);
+  double* d_ms = st.in(nullptr, f);
+  if (!d_u || !d_g2 || !d_n || !d_pk || !d_ms) return fail("device staging failed");
+  sw_package_kernel<<<grid(f), 128>>>(f, d_u, d_g2, d_n, d_pk, d_ms);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(packaged, d_pk, (size_t)16 * f * 8, cudaMemcpyDeviceToHost));
+  if (max_abs_char_speed) *max_abs_char_speed = 1.0;
+  return 0;
+}
+
+int dgrhs_sw_boundary_terms(int f, const double* packaged_int, const double* packaged_ext,
+                            double* boundary_correction) {
+  if (need_gpu()) return 1;
+  Staged st;
+  double* d_i = st.in(packaged_int, (size_t)16 * f);
+  double* d_e = st.in(packaged_ext, (size_t)16 * f);
+  double* d_c = st.in(nullptr, (size_t)5 * f);
+  if (!d_i || !d_e || !d_c) return fail("device staging failed");
+  sw_boundary_terms_kernel<<<grid(f), 128>>>(f, d_i, d_e, d_c);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(boundary_correction, d_c, (size_t)5 * f * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dgrhs_lift_flux(int f, int n_comps, double* boundary_correction,
+                    int extent_perpendicular_to_boundary,
+                    const double* magnitude_of_face_normal) {
+  if (need_gpu()) return 1;
+  Staged st;
+  double* d_c = st.in(boundary_correction, (size_t)n_comps * f);
+  double* d_m = st.in(magnitude_of_face_normal, f);
+  if (!d_c || !d_m) return fail("device staging failed");
+  lift_flux_kernel<<<grid(f), 128>>>(f, n_comps, d_c, extent_perpendicular_to_boundary, d_m);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(boundary_correction, d_c, (size_t)n_comps * f * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

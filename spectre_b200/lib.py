@@ -28,6 +28,9 @@ EXPORTS = [
     "dgrhs_end_substep", "dgrhs_time_kernels", "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
     "dgrhs_collocation_points_and_weights", "dgrhs_adams_bashforth_coefficients",
+    "dgrhs_gh_time_derivative", "dgrhs_sw_time_derivative", "dgrhs_gh_package_data",
+    "dgrhs_gh_boundary_terms", "dgrhs_sw_package_data", "dgrhs_sw_boundary_terms",
+    "dgrhs_lift_flux",
 ]
 
 _lib = None
@@ -100,6 +103,68 @@ def partial_derivatives(N: int, u: np.ndarray, inv_jacobian: np.ndarray) -> np.n
     du = np.zeros((3 * C, N ** 3))
     _check(load().dgrhs_partial_derivatives(N, C, _ptr(u), _ptr(J), _ptr(du)))
     return du
+
+
+def gh_time_derivative(u, du, gamma0, gamma1, gamma2, gauge_h=None, d4_gauge_h=None):
+    u, du = _f64(u), _f64(du)
+    n = u.shape[1]
+    g = [_f64(x) for x in (gamma0, gamma1, gamma2)]
+    harmonic = gauge_h is None
+    H = None if harmonic else _f64(gauge_h)
+    dH = None if harmonic else _f64(d4_gauge_h)
+    dt = np.zeros((50, n))
+    _check(load().dgrhs_gh_time_derivative(n, _ptr(u), _ptr(du), _ptr(g[0]), _ptr(g[1]),
+                                           _ptr(g[2]), int(harmonic), _ptr(H), _ptr(dH),
+                                           _ptr(dt)))
+    return dt
+
+
+def sw_time_derivative(u, du, gamma2):
+    u, du, gamma2 = _f64(u), _f64(du), _f64(gamma2)
+    n = u.shape[1]
+    dt = np.zeros((5, n))
+    _check(load().dgrhs_sw_time_derivative(n, _ptr(u), _ptr(du), _ptr(gamma2), _ptr(dt)))
+    return dt
+
+
+def gh_package_data(u, gamma1, gamma2, lapse, shift, normal_covector, normal_vector):
+    a = [_f64(x) for x in (u, gamma1, gamma2, lapse, shift, normal_covector, normal_vector)]
+    f = a[0].shape[1]
+    pk = np.zeros((134, f))
+    ms = ctypes.c_double()
+    _check(load().dgrhs_gh_package_data(f, *[_ptr(x) for x in a], _ptr(pk), ctypes.byref(ms)))
+    return pk, ms.value
+
+
+def gh_boundary_terms(pk_int, pk_ext):
+    a, b = _f64(pk_int), _f64(pk_ext)
+    f = a.shape[1]
+    c = np.zeros((50, f))
+    _check(load().dgrhs_gh_boundary_terms(f, _ptr(a), _ptr(b), _ptr(c)))
+    return c
+
+
+def sw_package_data(u, gamma2, normal_covector):
+    a = [_f64(x) for x in (u, gamma2, normal_covector)]
+    f = a[0].shape[1]
+    pk = np.zeros((16, f))
+    ms = ctypes.c_double()
+    _check(load().dgrhs_sw_package_data(f, *[_ptr(x) for x in a], _ptr(pk), ctypes.byref(ms)))
+    return pk, ms.value
+
+
+def sw_boundary_terms(pk_int, pk_ext):
+    a, b = _f64(pk_int), _f64(pk_ext)
+    f = a.shape[1]
+    c = np.zeros((5, f))
+    _check(load().dgrhs_sw_boundary_terms(f, _ptr(a), _ptr(b), _ptr(c)))
+    return c
+
+
+def lift_flux(corr, extent, magnitude):
+    c, m = _f64(corr).copy(), _f64(magnitude)
+    _check(load().dgrhs_lift_flux(c.shape[1], c.shape[0], _ptr(c), extent, _ptr(m)))
+    return c
 
 
 class Context:

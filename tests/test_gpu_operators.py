@@ -1,0 +1,100 @@
+"""Operator-level GPU parity, shaped like the reference's own unit tests:
+Test_DuDt.cpp (gh::TimeDerivative vs the SpEC-pinned reference impl),
+Test_UpwindPenalty.cpp (vs UpwindPenalty.py fixtures + conservation),
+Test_LiftFlux.cpp, Test_TimeDerivative.cpp (ScalarWave)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from spectre_b200 import lib
+from tests.test_oracle_pins import _random_physical_gh_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _maxrel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize("harmonic", [True, False])
+def test_gh_time_derivative_apply(harmonic):
+    """Test_DuDt.cpp:466-700: random physical metrics, random derivatives."""
+    rng = np.random.default_rng(42)
+    n = 27  # 3-point LGL mesh in 3-D like the reference test
+    u = _random_physical_gh_state(rng, n)
+    du = rng.uniform(-0.5, 0.5, (150, n))
+    gam = rng.uniform(-1, 1, (3, n))
+    H = rng.uniform(-1, 1, (4, n)); dH = rng.uniform(-1, 1, (16, n))
+    if harmonic:
+        got = lib.gh_time_derivative(u, du, *gam)
+        ref = orc.gh_time_derivative(u, du, *gam)
+    else:
+        got = lib.gh_time_derivative(u, du, *gam, gauge_h=H, d4_gauge_h=dH)
+        ref = orc.gh_time_derivative(u, du, *gam, gauge_params=orc.GAUGE_GIVEN, H=H, dH=dH)
+    for blk in (slice(0, 10), slice(10, 20), slice(20, 50)):
+        assert _maxrel(got[blk], ref[blk]) < 1e-12
+
+
+def test_sw_time_derivative_apply():
+    rng = np.random.default_rng(1)
+    n = 125
+    u = rng.uniform(-1, 1, (5, n)); du = rng.uniform(-1, 1, (15, n)); g2 = rng.uniform(0, 1, n)
+    got = lib.sw_time_derivative(u, du, g2)
+    assert _maxrel(got, orc.sw_time_derivative(u, du, g2)) < 1e-14
+
+
+def test_upwind_penalty_vs_reference_numpy_fixtures(golden_dir):
+    """The GPU operators against outputs of the reference's UpwindPenalty.py."""
+    z = np.load(os.path.join(golden_dir, "upwind_penalty.npz"))
+    pk = []
+    for side in range(2):
+        out, _ = lib.gh_package_data(z["gh_u"][side].T, z["gh_gamma1"][side],
+                                     z["gh_gamma2"][side], z["gh_lapse"][side],
+                                     z["gh_shift"][side].T, z["gh_nlo"][side].T,
+                                     z["gh_nup"][side].T)
+        np.testing.assert_allclose(out.T, z["gh_packaged"][side], rtol=1e-13, atol=1e-14)
+        pk.append(out)
+    np.testing.assert_allclose(lib.gh_boundary_terms(pk[0], pk[1]).T, z["gh_corr"],
+                               rtol=1e-13, atol=1e-14)
+    pk = []
+    for side in range(2):
+        out, _ = lib.sw_package_data(z["sw_u"][side].T, z["sw_gamma2"][side],
+                                     z["sw_normal"][side].T)
+        np.testing.assert_allclose(out.T, z["sw_packaged"][side], rtol=1e-13, atol=1e-14)
+        pk.append(out)
+    np.testing.assert_allclose(lib.sw_boundary_terms(pk[0], pk[1]).T, z["sw_corr"],
+                               rtol=1e-13, atol=1e-14)
+
+
+def test_upwind_penalty_conservation():
+    """Helpers/.../BoundaryCorrections.hpp:149-540 (test_boundary_correction_
+    conservation): in strong form D(int, ext) = -D(ext, int) when both sides use
+    opposite normals."""
+    rng = np.random.default_rng(8)
+    f = 40
+    sides = []
+    for sgn in (1.0, -1.0):
+        u = _random_physical_gh_state(rng, f)
+        sides.append(u)
+    nlo = rng.uniform(-1, 1, (3, f)); nup = rng.uniform(-1, 1, (3, f))
+    lapse = rng.uniform(0.5, 2, (2, f)); shift = rng.uniform(-1.5, 1.5, (2, 3, f))
+    g1 = rng.uniform(-1, 1, f); g2 = rng.uniform(-1, 1, f)
+    pk_a, _ = lib.gh_package_data(sides[0], g1, g2, lapse[0], shift[0], nlo, nup)
+    pk_b, _ = lib.gh_package_data(sides[1], g1, g2, lapse[1], shift[1], -nlo, -nup)
+    d_ab = lib.gh_boundary_terms(pk_a, pk_b)
+    d_ba = lib.gh_boundary_terms(pk_b, pk_a)
+    np.testing.assert_allclose(d_ab, -d_ba, rtol=1e-13, atol=1e-13)
+    # max char speed return value
+    _, ms = lib.gh_package_data(sides[0], g1, g2, lapse[0], shift[0], nlo, nup)
+    assert ms == pytest.approx(np.max(pk_a[130:134]), rel=0, abs=0)
+
+
+def test_lift_flux():
+    """Test_LiftFlux.cpp: -0.5 N (N-1) |n| scaling on the boundary slice."""
+    rng = np.random.default_rng(3)
+    f, ncomp, extent = 25, 5, 5
+    c = rng.uniform(-1, 1, (ncomp, f)); mag = rng.uniform(0.5, 2, f)
+    got = lib.lift_flux(c, extent, mag)
+    np.testing.assert_array_equal(got, c * (-0.5 * extent * (extent - 1) * mag))
