@@ -68,27 +68,29 @@ def test_upwind_penalty_vs_reference_numpy_fixtures(golden_dir):
                                rtol=1e-13, atol=1e-14)
 
 
-def test_upwind_penalty_conservation():
-    """Helpers/.../BoundaryCorrections.hpp:149-540 (test_boundary_correction_
-    conservation): in strong form D(int, ext) = -D(ext, int) when both sides use
-    opposite normals."""
+def test_upwind_penalty_zero_on_smooth_solution():
+    """Helpers/Evolution/DiscontinuousGalerkin/BoundaryCorrections.hpp:432-480
+    (ZeroOnSmoothSolution::Yes): if the solution is the same on both sides and
+    the exterior normals are minus the interior ones, the StrongInertial
+    correction is identically zero."""
     rng = np.random.default_rng(8)
     f = 40
-    sides = []
-    for sgn in (1.0, -1.0):
-        u = _random_physical_gh_state(rng, f)
-        sides.append(u)
+    u = _random_physical_gh_state(rng, f)
     nlo = rng.uniform(-1, 1, (3, f)); nup = rng.uniform(-1, 1, (3, f))
-    lapse = rng.uniform(0.5, 2, (2, f)); shift = rng.uniform(-1.5, 1.5, (2, 3, f))
+    lapse = rng.uniform(0.5, 2, f); shift = rng.uniform(-1.5, 1.5, (3, f))
     g1 = rng.uniform(-1, 1, f); g2 = rng.uniform(-1, 1, f)
-    pk_a, _ = lib.gh_package_data(sides[0], g1, g2, lapse[0], shift[0], nlo, nup)
-    pk_b, _ = lib.gh_package_data(sides[1], g1, g2, lapse[1], shift[1], -nlo, -nup)
-    d_ab = lib.gh_boundary_terms(pk_a, pk_b)
-    d_ba = lib.gh_boundary_terms(pk_b, pk_a)
-    np.testing.assert_allclose(d_ab, -d_ba, rtol=1e-13, atol=1e-13)
-    # max char speed return value
-    _, ms = lib.gh_package_data(sides[0], g1, g2, lapse[0], shift[0], nlo, nup)
-    assert ms == pytest.approx(np.max(pk_a[130:134]), rel=0, abs=0)
+    pk_a, ms = lib.gh_package_data(u, g1, g2, lapse, shift, nlo, nup)
+    pk_b, _ = lib.gh_package_data(u, g1, g2, lapse, shift, -nlo, -nup)
+    corr = lib.gh_boundary_terms(pk_a, pk_b)
+    assert np.max(np.abs(corr)) < 1e-12 * np.max(np.abs(pk_a))
+    # the return value of dg_package_data is the largest characteristic speed
+    assert ms == np.max(pk_a[130:134])
+    # ScalarWave
+    us = rng.uniform(-1, 1, (5, f)); n = rng.uniform(-1, 1, (3, f)); n /= np.linalg.norm(n, axis=0)
+    g2s = rng.uniform(0, 1, f)
+    pa, _ = lib.sw_package_data(us, g2s, n)
+    pb, _ = lib.sw_package_data(us, g2s, -n)
+    assert np.max(np.abs(lib.sw_boundary_terms(pa, pb))) < 1e-14
 
 
 def test_lift_flux():
