@@ -1,0 +1,485 @@
+// SpectreShims.hpp -- C++ host-side mirror of the reference's operator surface
+// for the DG right-hand-side path, forwarding to the C-ABI in include/dgrhs.h.
+//
+// Same names, argument order and meaning as the reference (v2024.09.29):
+//   DataVector                         DataStructures/DataVector.hpp:48, VectorImpl.hpp:222-322
+//   Scalar, tnsr::{i,I,ii,II,a,ab,aa,iaa,ijaa}   DataStructures/Tensor/TypeAliases.hpp,
+//                                      storage order Tensor/Structure.hpp:162-194
+//   Mesh<3>                            NumericalAlgorithms/Spectral/Mesh.hpp:52-244
+//   ElementId<3>                       Domain/Structure/ElementId.hpp:29-110
+//   partial_derivatives                NumericalAlgorithms/LinearOperators/PartialDerivatives.hpp
+//   ScalarWave::TimeDerivative<3>      Evolution/Systems/ScalarWave/TimeDerivative.hpp:26-50
+//   gh::TimeDerivative<3>              Evolution/Systems/GeneralizedHarmonic/TimeDerivative.hpp:143-192
+//   {ScalarWave,gh}::BoundaryCorrections::UpwindPenalty<3>   .../BoundaryCorrections/UpwindPenalty.hpp
+//   dg::lift_flux                      NumericalAlgorithms/DiscontinuousGalerkin/LiftFlux.hpp:41-62
+//   TimeSteppers::AdamsBashforth       Time/TimeSteppers/AdamsBashforth.hpp (coefficients only)
+//
+// Error behaviour: the reference ERRORs (aborts with a message); here a non-zero
+// C-ABI status becomes a std::runtime_error carrying dgrhs_last_error().
+// The header is self-contained (no Blaze/Charm++); a maintainer of the
+// reference would keep SpECTRE's own types and only take the bodies, see
+// INTEGRATION.md.
+#pragma once
+
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/dgrhs.h"
+
+namespace spectre_b200 {
+
+inline void check(int status) {
+  if (status != 0) throw std::runtime_error(dgrhs_last_error());
+}
+
+// ---- DataVector: owning or non-owning span of doubles ------------------------
+class DataVector {
+ public:
+  DataVector() = default;
+  explicit DataVector(size_t n, double v = 0.0) : owned_(n, v), data_(owned_.data()), size_(n) {}
+  DataVector(double* p, size_t n) : data_(p), size_(n) {}  // non-owning view
+  DataVector(const DataVector& o) : owned_(o.data_, o.data_ + o.size_), data_(owned_.data()), size_(o.size_) {}
+  DataVector& operator=(const DataVector& o) {
+    if (this == &o) return *this;
+    if (is_owning() || data_ == nullptr) {
+      owned_.assign(o.data_, o.data_ + o.size_);
+      data_ = owned_.data();
+      size_ = o.size_;
+    } else {  // assignment through a view writes into the viewed memory
+      if (size_ != o.size_) throw std::runtime_error("DataVector view size mismatch");
+      for (size_t i = 0; i < size_; ++i) data_[i] = o.data_[i];
+    }
+    return *this;
+  }
+  void set_data_ref(double* p, size_t n) {
+    owned_.clear();
+    data_ = p;
+    size_ = n;
+  }
+  bool is_owning() const { return !owned_.empty() && data_ == owned_.data(); }
+  size_t size() const { return size_; }
+  double* data() { return data_; }
+  const double* data() const { return data_; }
+  double& operator[](size_t i) { return data_[i]; }
+  const double& operator[](size_t i) const { return data_[i]; }
+
+ private:
+  std::vector<double> owned_;
+  double* data_ = nullptr;
+  size_t size_ = 0;
+};
+
+// ---- tensors (independent components in the reference's storage order) -------
+constexpr size_t sym4(size_t a, size_t b) {
+  return a <= b ? a * 4 - a * (a - 1) / 2 + (b - a) : b * 4 - b * (b - 1) / 2 + (a - b);
+}
+constexpr size_t sym3(size_t a, size_t b) {
+  return a <= b ? a * 3 - a * (a - 1) / 2 + (b - a) : b * 3 - b * (b - 1) / 2 + (a - b);
+}
+
+template <size_t K>
+struct TensorBase {
+  std::array<DataVector, K> c;
+  TensorBase() = default;
+  explicit TensorBase(size_t n, double v = 0.0) {
+    for (auto& x : c) x = DataVector(n, v);
+  }
+  static constexpr size_t size() { return K; }
+  DataVector& operator[](size_t s) { return c[s]; }
+  const DataVector& operator[](size_t s) const { return c[s]; }
+  auto begin() { return c.begin(); }
+  auto end() { return c.end(); }
+  auto begin() const { return c.begin(); }
+  auto end() const { return c.end(); }
+  // gather into / scatter from a contiguous [K][n] block (Variables layout)
+  std::vector<double> flat() const {
+    const size_t n = c[0].size();
+    std::vector<double> out(K * n);
+    for (size_t s = 0; s < K; ++s)
+      for (size_t p = 0; p < n; ++p) out[s * n + p] = c[s][p];
+    return out;
+  }
+  void from_flat(const double* in, size_t n) {
+    for (size_t s = 0; s < K; ++s) {
+      if (c[s].size() != n) c[s] = DataVector(n);
+      for (size_t p = 0; p < n; ++p) c[s][p] = in[s * n + p];
+    }
+  }
+};
+
+struct ScalarDV : TensorBase<1> {
+  using TensorBase<1>::TensorBase;
+  DataVector& get() { return c[0]; }
+  const DataVector& get() const { return c[0]; }
+};
+template <typename T = DataVector>
+using Scalar = ScalarDV;
+inline DataVector& get(ScalarDV& s) { return s.get(); }
+inline const DataVector& get(const ScalarDV& s) { return s.get(); }
+
+namespace tnsr {
+struct i3 : TensorBase<3> {  // tnsr::i / tnsr::I
+  using TensorBase<3>::TensorBase;
+  DataVector& get(size_t i) { return c[i]; }
+  const DataVector& get(size_t i) const { return c[i]; }
+};
+struct a4 : TensorBase<4> {  // tnsr::a / tnsr::A
+  using TensorBase<4>::TensorBase;
+  DataVector& get(size_t a) { return c[a]; }
+  const DataVector& get(size_t a) const { return c[a]; }
+};
+struct ij9 : TensorBase<9> {  // tnsr::ij, first index fastest
+  using TensorBase<9>::TensorBase;
+  DataVector& get(size_t i, size_t j) { return c[i + 3 * j]; }
+  const DataVector& get(size_t i, size_t j) const { return c[i + 3 * j]; }
+};
+struct ii6 : TensorBase<6> {  // tnsr::ii / tnsr::II
+  using TensorBase<6>::TensorBase;
+  DataVector& get(size_t i, size_t j) { return c[sym3(i, j)]; }
+  const DataVector& get(size_t i, size_t j) const { return c[sym3(i, j)]; }
+};
+struct ab16 : TensorBase<16> {  // tnsr::ab, first index fastest
+  using TensorBase<16>::TensorBase;
+  DataVector& get(size_t a, size_t b) { return c[a + 4 * b]; }
+  const DataVector& get(size_t a, size_t b) const { return c[a + 4 * b]; }
+};
+struct aa10 : TensorBase<10> {  // tnsr::aa / tnsr::AA
+  using TensorBase<10>::TensorBase;
+  DataVector& get(size_t a, size_t b) { return c[sym4(a, b)]; }
+  const DataVector& get(size_t a, size_t b) const { return c[sym4(a, b)]; }
+};
+struct iaa30 : TensorBase<30> {  // tnsr::iaa
+  using TensorBase<30>::TensorBase;
+  DataVector& get(size_t i, size_t a, size_t b) { return c[i + 3 * sym4(a, b)]; }
+  const DataVector& get(size_t i, size_t a, size_t b) const { return c[i + 3 * sym4(a, b)]; }
+};
+struct ijaa90 : TensorBase<90> {  // tnsr::ijaa
+  using TensorBase<90>::TensorBase;
+  DataVector& get(size_t i, size_t j, size_t a, size_t b) { return c[i + 3 * (j + 3 * sym4(a, b))]; }
+  const DataVector& get(size_t i, size_t j, size_t a, size_t b) const {
+    return c[i + 3 * (j + 3 * sym4(a, b))];
+  }
+};
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using i = i3;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using I = i3;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using a = a4;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using ij = ij9;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using ii = ii6;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using II = ii6;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using ab = ab16;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using aa = aa10;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using iaa = iaa30;
+template <typename T = DataVector, size_t Dim = 3, typename Fr = void> using ijaa = ijaa90;
+}  // namespace tnsr
+
+// InverseJacobian<DataVector, 3, ElementLogical, Inertial>: get(ihat, i) at ihat + 3 i
+using InverseJacobian3 = tnsr::ij9;
+
+// ---- Mesh<3>, ElementId<3> -------------------------------------------------------
+namespace Spectral {
+enum class Basis : uint8_t { Legendre = 1 };
+enum class Quadrature : uint8_t { GaussLobatto = 2 };
+// Spectral::differentiation_matrix / collocation_points / quadrature_weights
+inline std::vector<double> differentiation_matrix(size_t n) {
+  std::vector<double> D(n * n);
+  check(dgrhs_differentiation_matrix(static_cast<int>(n), D.data()));
+  return D;  // row-major D[i * n + j]
+}
+inline std::vector<double> collocation_points(size_t n) {
+  std::vector<double> x(n), w(n);
+  check(dgrhs_collocation_points_and_weights(static_cast<int>(n), x.data(), w.data()));
+  return x;
+}
+inline std::vector<double> quadrature_weights(size_t n) {
+  std::vector<double> x(n), w(n);
+  check(dgrhs_collocation_points_and_weights(static_cast<int>(n), x.data(), w.data()));
+  return w;
+}
+}  // namespace Spectral
+
+template <size_t Dim>
+class Mesh {
+ public:
+  Mesh() = default;
+  Mesh(size_t isotropic_extents, Spectral::Basis b, Spectral::Quadrature q) : basis_(b), quadrature_(q) {
+    extents_.fill(static_cast<uint8_t>(isotropic_extents));
+  }
+  size_t extents(size_t d) const { return extents_[d]; }
+  size_t number_of_grid_points() const {
+    size_t n = 1;
+    for (auto e : extents_) n *= e;
+    return n;
+  }
+  bool is_isotropic() const {
+    for (auto e : extents_)
+      if (e != extents_[0]) return false;
+    return true;
+  }
+
+ private:
+  std::array<uint8_t, Dim> extents_{};
+  Spectral::Basis basis_ = Spectral::Basis::Legendre;
+  Spectral::Quadrature quadrature_ = Spectral::Quadrature::GaussLobatto;
+};
+
+template <size_t Dim>
+class ElementId {
+ public:
+  ElementId(size_t block, std::array<std::pair<size_t, size_t>, Dim> level_and_index, size_t grid = 0) {
+    bits_ = (block & 0xFF) | ((grid & 0xF) << 8);
+    size_t shift = 16;
+    for (auto [lev, idx] : level_and_index) {
+      bits_ |= static_cast<uint64_t>(idx & 0xFFF) << shift;
+      bits_ |= static_cast<uint64_t>(lev & 0xF) << (shift + 12);
+      shift += 16;
+    }
+  }
+  uint64_t bits() const { return bits_; }
+  size_t block_id() const { return bits_ & 0xFF; }
+
+ private:
+  uint64_t bits_ = 0;
+};
+
+// ---- partial_derivatives ---------------------------------------------------------
+// du[3 c + i] = d_i u_c for a block of n_comps components (Variables layout)
+inline void partial_derivatives(std::vector<double>* du, const std::vector<double>& u, size_t n_comps,
+                                const Mesh<3>& mesh, const InverseJacobian3& inverse_jacobian) {
+  if (!mesh.is_isotropic()) throw std::runtime_error("isotropic meshes only on this path");
+  const size_t n = mesh.number_of_grid_points();
+  du->resize(3 * n_comps * n);
+  const auto J = inverse_jacobian.flat();
+  check(dgrhs_partial_derivatives(static_cast<int>(mesh.extents(0)), static_cast<int>(n_comps), u.data(),
+                                  J.data(), du->data()));
+}
+
+namespace dg {
+enum class Formulation { StrongInertial, WeakInertial };
+// dg::lift_flux on a Variables-like block [n_comps][f]
+inline void lift_flux(std::vector<double>* boundary_correction_terms, size_t n_comps,
+                      size_t extent_perpendicular_to_boundary, const ScalarDV& magnitude_of_face_normal) {
+  const size_t f = magnitude_of_face_normal.get().size();
+  check(dgrhs_lift_flux(static_cast<int>(f), static_cast<int>(n_comps), boundary_correction_terms->data(),
+                        static_cast<int>(extent_perpendicular_to_boundary),
+                        magnitude_of_face_normal.get().data()));
+}
+}  // namespace dg
+
+// ---- ScalarWave ------------------------------------------------------------------
+namespace ScalarWave {
+template <size_t Dim>
+struct TimeDerivative {
+  static_assert(Dim == 3);
+  static void apply(ScalarDV* dt_psi, ScalarDV* dt_pi, tnsr::i3* dt_phi, ScalarDV* result_gamma2,
+                    const tnsr::i3& d_psi, const tnsr::i3& d_pi, const tnsr::ij9& d_phi, const ScalarDV& pi,
+                    const tnsr::i3& phi, const ScalarDV& gamma2) {
+    const size_t n = pi.get().size();
+    std::vector<double> u(5 * n, 0.0), du(15 * n), dt(5 * n);
+    // psi itself does not enter the ScalarWave RHS
+    for (size_t p = 0; p < n; ++p) {
+      u[1 * n + p] = pi.get()[p];
+      for (size_t d = 0; d < 3; ++d) {
+        u[(2 + d) * n + p] = phi.get(d)[p];
+        du[(3 * 0 + d) * n + p] = d_psi.get(d)[p];
+        du[(3 * 1 + d) * n + p] = d_pi.get(d)[p];
+        for (size_t j = 0; j < 3; ++j) du[(3 * (2 + j) + d) * n + p] = d_phi.get(d, j)[p];
+      }
+    }
+    check(dgrhs_sw_time_derivative(static_cast<int>(n), u.data(), du.data(), gamma2.get().data(), dt.data()));
+    *result_gamma2 = gamma2;
+    dt_psi->from_flat(dt.data(), n);
+    dt_pi->from_flat(dt.data() + n, n);
+    dt_phi->from_flat(dt.data() + 2 * n, n);
+  }
+};
+
+namespace BoundaryCorrections {
+template <size_t Dim>
+class UpwindPenalty {
+ public:
+  static_assert(Dim == 3);
+  // packaged fields as one Variables<dg_package_field_tags> block [16][f]
+  double dg_package_data(std::vector<double>* packaged, const ScalarDV& psi, const ScalarDV& pi,
+                         const tnsr::i3& phi, const ScalarDV& constraint_gamma2,
+                         const tnsr::i3& normal_covector,
+                         const std::optional<tnsr::i3>& mesh_velocity,
+                         const std::optional<ScalarDV>& normal_dot_mesh_velocity) const {
+    if (mesh_velocity.has_value() || normal_dot_mesh_velocity.has_value())
+      throw std::runtime_error("moving meshes are out of scope of this path");
+    const size_t f = psi.get().size();
+    std::vector<double> u(5 * f);
+    for (size_t p = 0; p < f; ++p) {
+      u[p] = psi.get()[p];
+      u[f + p] = pi.get()[p];
+      for (size_t d = 0; d < 3; ++d) u[(2 + d) * f + p] = phi.get(d)[p];
+    }
+    packaged->resize(16 * f);
+    double max_speed = 0.0;
+    const auto nrm = normal_covector.flat();
+    check(dgrhs_sw_package_data(static_cast<int>(f), u.data(), constraint_gamma2.get().data(), nrm.data(),
+                                packaged->data(), &max_speed));
+    return max_speed;
+  }
+  void dg_boundary_terms(std::vector<double>* boundary_corrections, const std::vector<double>& packaged_int,
+                         const std::vector<double>& packaged_ext, dg::Formulation /*formulation*/) const {
+    const size_t f = packaged_int.size() / 16;
+    boundary_corrections->resize(5 * f);
+    check(dgrhs_sw_boundary_terms(static_cast<int>(f), packaged_int.data(), packaged_ext.data(),
+                                  boundary_corrections->data()));
+  }
+};
+}  // namespace BoundaryCorrections
+}  // namespace ScalarWave
+
+// ---- GeneralizedHarmonic ------------------------------------------------------------
+namespace gh {
+namespace gauges {
+struct GaugeCondition {
+  virtual ~GaugeCondition() = default;
+  virtual bool is_harmonic() const = 0;
+};
+struct Harmonic : GaugeCondition {
+  bool is_harmonic() const override { return true; }
+};
+// gauge source function evaluated by the caller (AnalyticChristoffel on a
+// static solution, or the output of gauges::dispatch)
+struct Fields : GaugeCondition {
+  tnsr::a4 gauge_h;
+  tnsr::ab16 d4_gauge_h;
+  bool is_harmonic() const override { return false; }
+};
+}  // namespace gauges
+
+template <size_t Dim>
+struct TimeDerivative {
+  static_assert(Dim == 3);
+  // Outputs, then the temporaries that feed the face projection
+  // (dg_package_data_temporary_tags: gamma1, gamma2; lapse/shift/inverse spatial
+  // metric are recomputed on the faces by the batched path), then derivatives and
+  // arguments in the reference's order.  The other scratch temporaries of the
+  // reference signature are private to the GPU kernel and not materialised.
+  static void apply(tnsr::aa10* dt_spacetime_metric, tnsr::aa10* dt_pi, tnsr::iaa30* dt_phi,
+                    ScalarDV* temp_gamma1, ScalarDV* temp_gamma2, const tnsr::iaa30& d_spacetime_metric,
+                    const tnsr::iaa30& d_pi, const tnsr::ijaa90& d_phi, const tnsr::aa10& spacetime_metric,
+                    const tnsr::aa10& pi, const tnsr::iaa30& phi, const ScalarDV& gamma0,
+                    const ScalarDV& gamma1, const ScalarDV& gamma2,
+                    const gauges::GaugeCondition& gauge_condition) {
+    const size_t n = gamma0.get().size();
+    std::vector<double> u(50 * n), du(150 * n), dt(50 * n);
+    const auto pack = [n](double* dst, const auto& t) {
+      for (size_t s = 0; s < t.size(); ++s)
+        for (size_t p = 0; p < n; ++p) dst[s * n + p] = t[s][p];
+    };
+    pack(u.data(), spacetime_metric);
+    pack(u.data() + 10 * n, pi);
+    pack(u.data() + 20 * n, phi);
+    // derivative tensors prepend the derivative index: component 3 c + i
+    pack(du.data(), d_spacetime_metric);
+    pack(du.data() + 30 * n, d_pi);
+    pack(du.data() + 60 * n, d_phi);
+    const bool harmonic = gauge_condition.is_harmonic();
+    std::vector<double> H, dH;
+    if (!harmonic) {
+      const auto& g = dynamic_cast<const gauges::Fields&>(gauge_condition);
+      H = g.gauge_h.flat();
+      dH = g.d4_gauge_h.flat();
+    }
+    check(dgrhs_gh_time_derivative(static_cast<int>(n), u.data(), du.data(), gamma0.get().data(),
+                                   gamma1.get().data(), gamma2.get().data(), harmonic ? 1 : 0,
+                                   harmonic ? nullptr : H.data(), harmonic ? nullptr : dH.data(), dt.data()));
+    *temp_gamma1 = gamma1;
+    *temp_gamma2 = gamma2;
+    dt_spacetime_metric->from_flat(dt.data(), n);
+    dt_pi->from_flat(dt.data() + 10 * n, n);
+    dt_phi->from_flat(dt.data() + 20 * n, n);
+  }
+};
+
+namespace BoundaryCorrections {
+template <size_t Dim>
+class UpwindPenalty {
+ public:
+  static_assert(Dim == 3);
+  // packaged: Variables<dg_package_field_tags> as one block [134][f]
+  double dg_package_data(std::vector<double>* packaged, const tnsr::aa10& spacetime_metric,
+                         const tnsr::aa10& pi, const tnsr::iaa30& phi, const ScalarDV& constraint_gamma1,
+                         const ScalarDV& constraint_gamma2, const ScalarDV& lapse, const tnsr::i3& shift,
+                         const tnsr::i3& normal_covector, const tnsr::i3& normal_vector,
+                         const std::optional<tnsr::i3>& mesh_velocity,
+                         const std::optional<ScalarDV>& normal_dot_mesh_velocity) const {
+    if (mesh_velocity.has_value() || normal_dot_mesh_velocity.has_value())
+      throw std::runtime_error("moving meshes are out of scope of this path");
+    const size_t f = lapse.get().size();
+    std::vector<double> u(50 * f);
+    const auto pack = [f](double* dst, const auto& t) {
+      for (size_t s = 0; s < t.size(); ++s)
+        for (size_t p = 0; p < f; ++p) dst[s * f + p] = t[s][p];
+    };
+    pack(u.data(), spacetime_metric);
+    pack(u.data() + 10 * f, pi);
+    pack(u.data() + 20 * f, phi);
+    packaged->resize(134 * f);
+    double max_speed = 0.0;
+    const auto sh = shift.flat(), nl = normal_covector.flat(), nu = normal_vector.flat();
+    check(dgrhs_gh_package_data(static_cast<int>(f), u.data(), constraint_gamma1.get().data(),
+                                constraint_gamma2.get().data(), lapse.get().data(), sh.data(), nl.data(),
+                                nu.data(), packaged->data(), &max_speed));
+    return max_speed;
+  }
+  void dg_boundary_terms(std::vector<double>* boundary_corrections, const std::vector<double>& packaged_int,
+                         const std::vector<double>& packaged_ext, dg::Formulation /*formulation*/) const {
+    const size_t f = packaged_int.size() / 134;
+    boundary_corrections->resize(50 * f);
+    check(dgrhs_gh_boundary_terms(static_cast<int>(f), packaged_int.data(), packaged_ext.data(),
+                                  boundary_corrections->data()));
+  }
+};
+}  // namespace BoundaryCorrections
+}  // namespace gh
+
+// ---- TimeSteppers ------------------------------------------------------------------
+namespace TimeSteppers {
+namespace adams_coefficients {
+// coefficients for a step from step_start to step_end given the history times
+// (oldest first): AdamsCoefficients.hpp:64-104
+inline std::vector<double> coefficients(const std::vector<double>& history_times, double step_start,
+                                        double step_end) {
+  std::vector<double> c(history_times.size());
+  check(dgrhs_adams_bashforth_coefficients(static_cast<int>(history_times.size()), history_times.data(),
+                                           step_start, step_end, c.data()));
+  return c;
+}
+}  // namespace adams_coefficients
+}  // namespace TimeSteppers
+
+// ---- batched evolution: the replacement of DgElementArray + step_actions ------------
+class DgEvolution {
+ public:
+  DgEvolution(int system, const Mesh<3>& mesh, int n_elements, int device = 0) {
+    check(dgrhs_create(&ctx_, system, static_cast<int>(mesh.extents(0)), n_elements, 0, device));
+  }
+  ~DgEvolution() { dgrhs_destroy(ctx_); }
+  DgEvolution(const DgEvolution&) = delete;
+  DgEvolution& operator=(const DgEvolution&) = delete;
+  void set_geometry(const double* inv_jacobian, const double* coords, const int32_t* neighbors) {
+    check(dgrhs_set_geometry(ctx_, inv_jacobian, coords, neighbors));
+  }
+  void set_static_fields(const double* fields, int ncomp) { check(dgrhs_set_static_fields(ctx_, fields, ncomp)); }
+  void set_variables(const double* u) { check(dgrhs_set_state(ctx_, u)); }
+  void get_variables(double* u) { check(dgrhs_get_state(ctx_, u)); }
+  void set_time_stepper(int stepper, int order, double t0, double dt) {
+    check(dgrhs_set_stepper(ctx_, stepper, order, t0, dt));
+  }
+  void take_steps(int n) { check(dgrhs_take_steps(ctx_, n)); }
+  double time() const { return dgrhs_time(ctx_); }
+  dgrhs_ctx* handle() { return ctx_; }
+
+ private:
+  dgrhs_ctx* ctx_ = nullptr;
+};
+
+}  // namespace spectre_b200

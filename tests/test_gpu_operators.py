@@ -100,3 +100,18 @@ def test_lift_flux():
     c = rng.uniform(-1, 1, (ncomp, f)); mag = rng.uniform(0.5, 2, f)
     got = lib.lift_flux(c, extent, mag)
     np.testing.assert_array_equal(got, c * (-0.5 * extent * (extent - 1) * mag))
+
+
+def test_cpp_shims_on_gpu():
+    """spectre_b200/host/SpectreShims.hpp (the C++ mirror of the reference's
+    operator classes) compiled with g++ -std=c++20 against libdgrhs.so."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "shim_test")
+    src = os.path.join(root, "tests", "helpers", "shim_test.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-o", exe, src, "-L",
+                           os.path.join(root, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(root, "spectre_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "SHIM OK" in out.stdout, out.stdout + out.stderr
