@@ -981,16 +981,157 @@ void orc_lincomb(long long len, double a, double* u, int nterms,
   }
 }
 
-/* DampedHarmonic gauge: restatement pending (DampedHarmonic.cpp:70-439); the
- * oracle refuses to run rather than guess. */
+/* ------------------------------------------------------------------------
+ * DampedHarmonic gauge without roll-on: damped_harmonic_impl<false>
+ * Evolution/Systems/GeneralizedHarmonic/GaugeSourceFunctions/
+ *   DampedHarmonic.cpp:70-439, DampedWaveHelpers.cpp:26-62
+ * (spatial_weight_function W = exp(-r^2/sigma_r^2), its spacetime derivative,
+ * log_factor_metric_lapse).  Pinned by fixtures made with the reference's
+ * DampedHarmonic.py (tests/golden/damped_harmonic.npz).
+ * d4_g[a][b][c] = d_a g_bc; d4H[a][b] = d_a H_b.
+ * ---------------------------------------------------------------------- */
+static double integer_pow(double x, int e) {
+  double r = 1.0;
+  for (int i = 0; i < e; ++i) r *= x;
+  return r;
+}
+
 static void damped_harmonic_gauge(
     const DampedHarmonicParams* prm, const double x[3], double lapse,
     const double shift[3], double sqrt_det_gamma, const double inv_gamma[3][3],
     const double d4_g[4][4][4], double half_pi_two_normals,
     const double half_phi_two_normals[3], const double g[4][4],
     const double phi[3][4][4], double H[4], double d4H[4][4]) {
-  (void)prm; (void)x; (void)lapse; (void)shift; (void)sqrt_det_gamma;
-  (void)inv_gamma; (void)d4_g; (void)half_pi_two_normals;
-  (void)half_phi_two_normals; (void)g; (void)phi; (void)H; (void)d4H;
-  abort();
+  const double amp_L1 = prm->amp[0], amp_L2 = prm->amp[1], amp_S = prm->amp[2];
+  const int exp_L1 = prm->exp[0], exp_L2 = prm->exp[1], exp_S = prm->exp[2];
+  const double sigma_r = prm->width;
+  const double one_over_lapse = 1.0 / lapse;
+  const double log_fac_1 = log(sqrt_det_gamma / lapse); /* exponent 0.5 */
+  const double log_fac_2 = -log(lapse);                 /* exponent 0   */
+  /* DampedWaveHelpers.cpp:26-47 */
+  const double r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  const double weight = exp(-r2 / (sigma_r * sigma_r));
+  double d4_weight[4];
+  d4_weight[0] = 0.0;
+  for (int i = 0; i < 3; ++i)
+    d4_weight[i + 1] = -2.0 * weight / (sigma_r * sigma_r) * x[i];
+  double pow1 = integer_pow(log_fac_1, exp_L1);
+  double pow2 = integer_pow(log_fac_1, exp_S);
+  double pow3 = integer_pow(log_fac_2, exp_L2);
+  const double mu_L1 = amp_L1 * weight * pow1;
+  const double mu_S = amp_S * weight * pow2;
+  const double mu_L2 = amp_L2 * weight * pow3;
+  const double mu_S_over_lapse = mu_S * one_over_lapse;
+  const double mu1 = mu_L1 * log_fac_1;
+  const double mu2 = mu_L2 * log_fac_2;
+  const double prefac = mu_L1 * log_fac_1 + mu_L2 * log_fac_2;
+  double g_dot_shift[4];
+  for (int a = 0; a < 4; ++a) {
+    g_dot_shift[a] = g[a][1] * shift[0];
+    for (int i = 1; i < 3; ++i) g_dot_shift[a] += g[a][i + 1] * shift[i];
+  }
+  for (int a = 0; a < 4; ++a) H[a] = -mu_S_over_lapse * g_dot_shift[a];
+  H[0] -= prefac * lapse;
+
+  /* d_t lapse and d_a lapse / lapse (:262-270) */
+  double sh_hphi = 0.0;
+  for (int i = 0; i < 3; ++i) sh_hphi += shift[i] * half_phi_two_normals[i];
+  const double dt_lapse = lapse * (lapse * half_pi_two_normals - sh_hphi);
+  double d_lapse_by_lapse[4];
+  d_lapse_by_lapse[0] = one_over_lapse * dt_lapse;
+  for (int i = 0; i < 3; ++i) d_lapse_by_lapse[i + 1] = -half_phi_two_normals[i];
+  /* d_a det(gamma) / det(gamma) = gamma^{jk} d_a gamma_jk (:271-277) */
+  double d_g_by_det[4];
+  for (int a = 0; a < 4; ++a) {
+    double v = 0.0;
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) v += inv_gamma[j][k] * d4_g[a][j + 1][k + 1];
+    d_g_by_det[a] = v;
+  }
+  double d4_log_fac_mu1[4], d4_log_fac_muS[4], d4_log_fac_mu2[4];
+  for (int a = 0; a < 4; ++a) {
+    const double d_logfac_1 = 0.5 * d_g_by_det[a] - d_lapse_by_lapse[a];
+    const double d_logfac_2 = -d_lapse_by_lapse[a];
+    d4_log_fac_mu1[a] = (double)(exp_L1 + 1) * integer_pow(log_fac_1, exp_L1) * d_logfac_1;
+    d4_log_fac_muS[a] = (double)exp_S * integer_pow(log_fac_1, exp_S - 1) * d_logfac_1;
+    d4_log_fac_mu2[a] = (double)(exp_L2 + 1) * integer_pow(log_fac_2, exp_L2) * d_logfac_2;
+  }
+  pow1 *= log_fac_1 * amp_L1;
+  pow2 *= amp_S;
+  pow3 *= log_fac_2 * amp_L2;
+  double d4_mu1[4], d4_mu_S[4], d4_mu2[4];
+  for (int a = 0; a < 4; ++a) {
+    d4_mu1[a] = pow1 * d4_weight[a] + amp_L1 * weight * d4_log_fac_mu1[a];
+    d4_mu_S[a] = d4_weight[a] * pow2 + amp_S * weight * d4_log_fac_muS[a];
+    d4_mu2[a] = pow3 * d4_weight[a] + amp_L2 * weight * d4_log_fac_mu2[a];
+  }
+  /* :359-379 */
+  double d4_muS_over_lapse[4], dT2[4];
+  d4_muS_over_lapse[0] = dt_lapse;
+  dT2[0] = -(d4_mu1[0] + d4_mu2[0]) * lapse - (mu1 + mu2) * d4_muS_over_lapse[0];
+  for (int i = 0; i < 3; ++i)
+    dT2[i + 1] = -(d4_mu1[i + 1] + d4_mu2[i + 1]) * lapse +
+                 (mu1 + mu2) * lapse * half_phi_two_normals[i];
+  d4_muS_over_lapse[0] *= -mu_S * one_over_lapse;
+  d4_muS_over_lapse[0] += d4_mu_S[0];
+  d4_muS_over_lapse[0] *= one_over_lapse;
+  for (int i = 0; i < 3; ++i)
+    d4_muS_over_lapse[i + 1] =
+        one_over_lapse * (d4_mu_S[i + 1] + mu_S * half_phi_two_normals[i]);
+  /* :397-421 */
+  for (int a = 0; a < 4; ++a) {
+    double dT3[4];
+    for (int j = 0; j < 3; ++j) dT3[j + 1] = d4_g[a][0][j + 1];
+    dT3[0] = d4_g[a][0][1] * shift[0];
+    for (int j = 1; j < 3; ++j) dT3[0] += d4_g[a][0][j + 1] * shift[j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = i + 1; j < 3; ++j)
+        dT3[0] -= shift[i] * shift[j] * d4_g[a][i + 1][j + 1];
+    dT3[0] *= 2.0;
+    for (int i = 0; i < 3; ++i) dT3[0] -= shift[i] * shift[i] * d4_g[a][i + 1][i + 1];
+    for (int b = 0; b < 4; ++b) {
+      dT3[b] *= -mu_S_over_lapse;
+      dT3[b] -= d4_muS_over_lapse[a] * g_dot_shift[b];
+      d4H[a][b] = dT3[b];
+    }
+    d4H[a][0] += dT2[a];
+  }
+  (void)phi;
+}
+
+/* stand-alone evaluation for the pin test: g, pi, phi dense arrays at a point */
+void orc_damped_harmonic(const double* g_, const double* pi_, const double* phi_,
+                         const double* x, const double* gauge_params, double* H,
+                         double* d4H_) {
+  const double(*g)[4] = (const double(*)[4])g_;
+  const double(*pi)[4] = (const double(*)[4])pi_;
+  const double(*phi)[4][4] = (const double(*)[4][4])phi_;
+  double(*d4H)[4] = (double(*)[4])d4H_;
+  GhGaugeSpec gs;
+  gauge_from_params(gauge_params, &gs);
+  GhGeom q;
+  gh_geometry(g, &q);
+  double da_g[4][4][4];
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      double v = -q.lapse * pi[a][b];
+      for (int m = 0; m < 3; ++m) v += q.shift[m] * phi[m][a][b];
+      da_g[0][a][b] = v;
+      for (int i = 0; i < 3; ++i) da_g[i + 1][a][b] = phi[i][a][b];
+    }
+  double pon[4], hpnn = 0.0, hphinn[3];
+  for (int a = 0; a < 4; ++a) {
+    pon[a] = 0.0;
+    for (int b = 0; b < 4; ++b) pon[a] += q.normal_vec[b] * pi[b][a];
+  }
+  for (int a = 0; a < 4; ++a) hpnn += q.normal_vec[a] * pon[a];
+  hpnn *= 0.5;
+  for (int n = 0; n < 3; ++n) {
+    double v = 0.0;
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) v += q.normal_vec[a] * q.normal_vec[b] * phi[n][a][b];
+    hphinn[n] = 0.5 * v;
+  }
+  damped_harmonic_gauge(&gs.dh, x, q.lapse, q.shift, sqrt(q.det_gamma), q.inv_gamma, da_g,
+                        hpnn, hphinn, g, phi, H, d4H);
 }

@@ -301,14 +301,21 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr) {
   const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
   if (c->system == DGRHS_SYSTEM_GH) {
     dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
-                    c->gH, c->gdH, c->D, eb};
+                    c->gH, c->gdH, c->D, c->coords, {}, eb};
     constexpr int smem = dg::gh_volume_smem_bytes<N>();
     if (c->gauge == DGRHS_GAUGE_HARMONIC) {
-      auto k = dg::gh_volume_kernel<N, true>;
+      auto k = dg::gh_volume_kernel<N, 0>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+    } else if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+      if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
+      const double* p = c->gauge_params;
+      a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+      auto k = dg::gh_volume_kernel<N, 2>;
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
     } else {
-      auto k = dg::gh_volume_kernel<N, false>;
+      auto k = dg::gh_volume_kernel<N, 1>;
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
     }
@@ -341,8 +348,6 @@ int launch_pack(dgrhs_ctx* c) {
 
 int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume_only,
               bool do_gauge) {
-  if (c->system == DGRHS_SYSTEM_GH && c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC)
-    return fail("DampedHarmonic gauge is not implemented yet");
   switch (c->N) {
 #define X(NN)                                                        \
   case NN:                                                           \
@@ -512,7 +517,9 @@ int dgrhs_set_gauge(dgrhs_ctx* c, int gauge, const double* params, int nparams) 
   CU(cudaSetDevice(c->device));
   c->gauge = gauge;
   for (int i = 0; i < nparams; ++i) c->gauge_params[i] = params[i];
-  if (gauge != DGRHS_GAUGE_HARMONIC && !c->gH) {
+  if (gauge == DGRHS_GAUGE_DAMPED_HARMONIC && nparams != 7)
+    return fail("DampedHarmonic needs {width, amp_L1, amp_L2, amp_S, exp_L1, exp_L2, exp_S}");
+  if ((gauge == DGRHS_GAUGE_FIELDS || gauge == DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE) && !c->gH) {
     if (dev_alloc(&c->gH, (size_t)c->nelem * 4 * c->npad)) return 1;
     if (dev_alloc(&c->gdH, (size_t)c->nelem * 16 * c->npad)) return 1;
   }

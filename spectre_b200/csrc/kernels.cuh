@@ -166,6 +166,8 @@ struct GhVolArgs {
   const double* gH;      // [E][4][npad]   gauge H_a      (non-harmonic)
   const double* gdH;     // [E][16][npad]  d_a H_b, a+4b  (non-harmonic)
   const double* D;       // [N*N] row-major differentiation matrix
+  const double* coords;  // [E][3][npad] (DampedHarmonic gauge)
+  DampedHarmonicParams dh;
   int elem_begin;
 };
 
@@ -174,7 +176,8 @@ constexpr int gh_volume_smem_bytes() {
   return Cfg<N>::nstage * Cfg<N>::stage_doubles * 8 + Cfg<N>::fixed_bytes;
 }
 
-template <int N, bool kHarmonic>
+// kGauge: 0 Harmonic, 1 gauge fields from memory, 2 DampedHarmonic
+template <int N, int kGauge>
 __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
   constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, T = Cfg<N>::T, f = N * N;
   constexpr int NS = Cfg<N>::nstage, SD = Cfg<N>::stage_doubles;
@@ -234,7 +237,15 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
     const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad),
                  gamma2 = __ldg(se + 2 * npad);
     GaugeH gh;
-    if constexpr (!kHarmonic) {
+    GaugeInput gin;
+    gin.fields = &gh;
+    if constexpr (kGauge == 2) {
+      gin.dh = a.dh;
+      const double* xe = a.coords + (size_t)e * 3 * npad + pt;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) gin.x[x] = __ldg(xe + (size_t)x * npad);
+    }
+    if constexpr (kGauge == 1) {
       const double* he = a.gH + (size_t)e * 4 * npad + pt;
       const double* dhe = a.gdH + (size_t)e * 16 * npad + pt;
 #pragma unroll
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
         for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
       }
     }
-    gh_prologue<kHarmonic>(g, pi, phi, J, gamma0, gamma1, gamma2, &gh, ctx, Q);
+    gh_prologue<kGauge>(g, pi, phi, J, gamma0, gamma1, gamma2, gin, ctx, Q);
 #pragma unroll
     for (int s = 0; s < 10; ++s) sQ[s * T + tid] = Q[s];
   }

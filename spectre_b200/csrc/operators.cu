@@ -86,7 +86,9 @@ __global__ void gh_time_derivative_kernel(int n, const double* u, const double* 
     }
   }
   dg::GhContext ctx;
-  dg::gh_prologue<kHarmonic>(g, pi, phi, J, g0[p], g1[p], g2[p], &gh, ctx, Q);
+  dg::GaugeInput gin;
+  gin.fields = &gh;
+  dg::gh_prologue<kHarmonic ? 0 : 1>(g, pi, phi, J, g0[p], g1[p], g2[p], gin, ctx, Q);
 #pragma unroll 1
   for (int s = 0; s < 10; ++s) {
     double ph[3], dgv[3], dpi[3], dph[3][3], og, op, oph[3];

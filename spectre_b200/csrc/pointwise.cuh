@@ -93,16 +93,134 @@ struct GaugeH {
   double dH[4][4];
 };
 
+// DampedHarmonic gauge parameters (GaugeSourceFunctions/DampedHarmonic.hpp)
+struct DampedHarmonicParams {
+  double sigma_r;
+  double amp_L1, amp_L2, amp_S;
+  int exp_L1, exp_L2, exp_S;
+};
+
+DG_HD double integer_pow(double x, int e) {
+  double r = 1.0;
+  for (int i = 0; i < e; ++i) r *= x;
+  return r;
+}
+
+// damped_harmonic_impl<UseRollon = false> (DampedHarmonic.cpp:70-439,
+// DampedWaveHelpers.cpp:26-62) at one point.  dag[a][sym4(b,c)] = d_a g_bc.
+DG_HD void damped_harmonic_gauge(const DampedHarmonicParams& prm, const double (&x)[3],
+                                 double lapse, const double (&shift)[3], double sqrt_det,
+                                 const double (&ig)[6], const double (&dag)[4][10],
+                                 double half_pi_nn, const double (&half_phi_nn)[3],
+                                 const double (&g)[10], GaugeH& out) {
+  const double one_over_lapse = 1.0 / lapse;
+  const double log_fac_1 = log(sqrt_det / lapse);
+  const double log_fac_2 = -log(lapse);
+  const double inv_s2 = 1.0 / (prm.sigma_r * prm.sigma_r);
+  const double weight = exp(-(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) * inv_s2);
+  double d4_weight[4];
+  d4_weight[0] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d4_weight[i + 1] = -2.0 * weight * inv_s2 * x[i];
+  double pow1 = integer_pow(log_fac_1, prm.exp_L1);
+  double pow2 = integer_pow(log_fac_1, prm.exp_S);
+  double pow3 = integer_pow(log_fac_2, prm.exp_L2);
+  const double mu_L1 = prm.amp_L1 * weight * pow1;
+  const double mu_S = prm.amp_S * weight * pow2;
+  const double mu_L2 = prm.amp_L2 * weight * pow3;
+  const double mu_S_over_lapse = mu_S * one_over_lapse;
+  const double mu1 = mu_L1 * log_fac_1, mu2 = mu_L2 * log_fac_2;
+  const double prefac = mu1 + mu2;
+  double g_dot_shift[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double v = g[sym4(a, 1)] * shift[0];
+    v += g[sym4(a, 2)] * shift[1];
+    v += g[sym4(a, 3)] * shift[2];
+    g_dot_shift[a] = v;
+    out.H[a] = -mu_S_over_lapse * v;
+  }
+  out.H[0] -= prefac * lapse;
+  double sh_hphi = shift[0] * half_phi_nn[0];
+  sh_hphi += shift[1] * half_phi_nn[1];
+  sh_hphi += shift[2] * half_phi_nn[2];
+  const double dt_lapse = lapse * (lapse * half_pi_nn - sh_hphi);
+  double dlbl[4];
+  dlbl[0] = one_over_lapse * dt_lapse;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dlbl[i + 1] = -half_phi_nn[i];
+  const double c1 = (double)(prm.exp_L1 + 1) * integer_pow(log_fac_1, prm.exp_L1);
+  const double cS = (double)prm.exp_S * integer_pow(log_fac_1, prm.exp_S - 1);
+  const double c2 = (double)(prm.exp_L2 + 1) * integer_pow(log_fac_2, prm.exp_L2);
+  pow1 *= log_fac_1 * prm.amp_L1;
+  pow2 *= prm.amp_S;
+  pow3 *= log_fac_2 * prm.amp_L2;
+  double d4_mu12[4], d4_mu_S[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double dgd = 0.0;  // gamma^{jk} d_a gamma_jk
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = j; k < 3; ++k)
+        dgd += (j == k ? 1.0 : 2.0) * ig[sym3(j, k)] * dag[a][sym4(j + 1, k + 1)];
+    const double d_logfac_1 = 0.5 * dgd - dlbl[a];
+    const double d_logfac_2 = -dlbl[a];
+    const double d4_mu1 = pow1 * d4_weight[a] + prm.amp_L1 * weight * (c1 * d_logfac_1);
+    const double d4_mu2 = pow3 * d4_weight[a] + prm.amp_L2 * weight * (c2 * d_logfac_2);
+    d4_mu12[a] = d4_mu1 + d4_mu2;
+    d4_mu_S[a] = d4_weight[a] * pow2 + prm.amp_S * weight * (cS * d_logfac_1);
+  }
+  double d4_muS_ol[4], dT2[4];
+  dT2[0] = -d4_mu12[0] * lapse - prefac * dt_lapse;
+  d4_muS_ol[0] = (dt_lapse * (-mu_S * one_over_lapse) + d4_mu_S[0]) * one_over_lapse;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    dT2[i + 1] = -d4_mu12[i + 1] * lapse + prefac * lapse * half_phi_nn[i];
+    d4_muS_ol[i + 1] = one_over_lapse * (d4_mu_S[i + 1] + mu_S * half_phi_nn[i]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double dT3[4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dT3[j + 1] = dag[a][sym4(0, j + 1)];
+    double v = dag[a][sym4(0, 1)] * shift[0];
+    v += dag[a][sym4(0, 2)] * shift[1];
+    v += dag[a][sym4(0, 3)] * shift[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 3; ++j) v -= shift[i] * shift[j] * dag[a][sym4(i + 1, j + 1)];
+    v *= 2.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v -= shift[i] * shift[i] * dag[a][sym4(i + 1, i + 1)];
+    dT3[0] = v;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      out.dH[a][b] = dT3[b] * (-mu_S_over_lapse) - d4_muS_ol[a] * g_dot_shift[b];
+    out.dH[a][0] += dT2[a];
+  }
+}
+
+// what the gauge condition needs at a point
+struct GaugeInput {
+  const GaugeH* fields;          // kGauge == 1
+  DampedHarmonicParams dh;       // kGauge == 2
+  double x[3];                   // kGauge == 2: inertial coordinates
+};
+
 // Computes the context and Q[10], the part of the bracket of the dt Pi
 // equation that contains no derivatives and is not linear in the pair's own
 // components (TimeDerivative.cpp:308-372): constraint-damping n_a terms, the
 // three quadratic contractions and the gauge terms.
 //   g, pi: sym4 order; phi[m][sym4]; J[jhat][i]
-template <bool kHarmonic>
+// kGauge: 0 Harmonic, 1 fields supplied, 2 DampedHarmonic
+template <int kGauge>
 DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
                        const double (&phi)[3][10], const double (&J)[3][3],
                        double gamma0, double gamma1, double gamma2,
-                       const GaugeH* gauge, GhContext& ctx, double (&Q)[10]) {
+                       const GaugeInput& gin, GhContext& ctx, double (&Q)[10]) {
+  constexpr bool kHarmonic = kGauge == 0;
   Geom3p1 q;
   geom_from_metric(g, q);
   const double lapse = q.lapse;
@@ -171,6 +289,13 @@ DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
   // are formed on the fly: chr(k,i,j) = 1/2 (d_i g_jk + d_j g_ik - d_k g_ij)
 #define DG_CHR(k, i, j) \
   (0.5 * (dag[i][sym4(j, k)] + dag[j][sym4(i, k)] - dag[k][sym4(i, j)]))
+  GaugeH gauge_local;
+  const GaugeH* gauge = gin.fields;
+  if constexpr (kGauge == 2) {
+    damped_harmonic_gauge(gin.dh, gin.x, lapse, q.shift, sqrt(q.det), q.ig, dag,
+                          ctx.half_pi_nn, ctx.half_phi_nn, g, gauge_local);
+    gauge = &gauge_local;
+  }
   // gauge constraint C_a = Gamma_a + H_a, Gamma_a = G^{bc} Gamma_a,bc
   double Ca[4];
 #pragma unroll

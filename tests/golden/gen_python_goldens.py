@@ -110,3 +110,42 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def damped_harmonic():
+    """tests/golden/damped_harmonic.npz from the reference's
+    tests/Unit/Evolution/Systems/GeneralizedHarmonic/GaugeSourceFunctions/
+    DampedHarmonic.py (exponents are hard-coded to 4 there).  The reference
+    functions modify their metric argument in place (g_00 -= 1, g_ii += 1); the
+    fixture stores the metric AFTER that shift, i.e. the metric the formulas see."""
+    import sys
+    sys.path.insert(0, "/root/reference/tests/Unit")
+    from Evolution.Systems.GeneralizedHarmonic.GaugeSourceFunctions import DampedHarmonic as dh
+    rng = np.random.default_rng(4242)
+    npts = 48
+    G = np.zeros((npts, 4, 4)); PI = np.zeros((npts, 4, 4)); PHI = np.zeros((npts, 3, 4, 4))
+    X = np.zeros((npts, 3)); PRM = np.zeros((npts, 4)); Hs = np.zeros((npts, 4))
+    dHs = np.zeros((npts, 4, 4))
+    for p in range(npts):
+        g = rng.uniform(-0.1, 0.1, (4, 4)); g = 0.5 * (g + g.T)
+        pi = rng.uniform(-0.5, 0.5, (4, 4)); pi = 0.5 * (pi + pi.T)
+        phi = rng.uniform(-0.5, 0.5, (3, 4, 4)); phi = 0.5 * (phi + phi.transpose(0, 2, 1))
+        x = rng.uniform(-3, 3, 3)
+        aL1, aL2, aS = rng.uniform(0.5, 2, 3)
+        sigma = rng.uniform(5, 20)
+        g_in = g.copy()
+        H = dh.damped_harmonic_gauge_source_function(g_in, pi, phi, x, aL1, aL2, aS, sigma)
+        g_in2 = g.copy()
+        dH = dh.spacetime_deriv_damped_harmonic_gauge_source_function(g_in2, pi, phi, x, aL1, aL2,
+                                                                      aS, sigma)
+        assert np.array_equal(g_in, g_in2)
+        G[p], PI[p], PHI[p], X[p] = g_in, pi, phi, x
+        PRM[p] = (sigma, aL1, aL2, aS)
+        Hs[p], dHs[p] = H, dH
+    np.savez_compressed(os.path.join(HERE, "damped_harmonic.npz"), g=G, pi=PI, phi=PHI, x=X,
+                        params=PRM, H=Hs, dH=dHs)
+    print("wrote damped_harmonic.npz")
+
+
+if __name__ == "__main__":
+    damped_harmonic()

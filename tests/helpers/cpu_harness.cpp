@@ -3,6 +3,8 @@
 // the oracle without a GPU.  NOT part of the product (never built into
 // libdgrhs.so, never imported by spectre_b200/).
 #include <cmath>
+using std::exp;
+using std::log;
 using std::sqrt;
 #include "../../spectre_b200/csrc/pointwise.cuh"
 
@@ -10,9 +12,12 @@ extern "C" {
 
 // u [50][n], dlog [150][n] (logical derivative jhat of comp c at 3c+jhat),
 // J [9][n] (jhat + 3 i), gam [3][n], H [4][n], dH [16][n] (a + 4 b)
-void h_gh_volume(int n, int harmonic, const double* u, const double* dlog,
+// gauge: 0 harmonic, 1 fields (H, dH), 2 damped harmonic (dhp = {sigma_r, amp L1,
+// L2, S, exp L1, L2, S}, coords [3][n])
+void h_gh_volume(int n, int gauge, const double* u, const double* dlog,
                  const double* J, const double* gam, const double* H,
-                 const double* dH, double* dt) {
+                 const double* dH, const double* dhp, const double* coords,
+                 double* dt) {
   for (int p = 0; p < n; ++p) {
     double g[10], pi[10], phi[3][10], Jm[3][3], Q[10];
     for (int s = 0; s < 10; ++s) {
@@ -28,10 +33,18 @@ void h_gh_volume(int n, int harmonic, const double* u, const double* dlog,
       for (int b = 0; b < 4; ++b) gh.dH[a][b] = dH[(size_t)(a + 4 * b) * n + p];
     }
     dg::GhContext ctx;
-    if (harmonic)
-      dg::gh_prologue<true>(g, pi, phi, Jm, gam[p], gam[n + p], gam[2 * n + p], &gh, ctx, Q);
+    dg::GaugeInput gin;
+    gin.fields = &gh;
+    if (gauge == 2) {
+      gin.dh = {dhp[0], dhp[1], dhp[2], dhp[3], (int)dhp[4], (int)dhp[5], (int)dhp[6]};
+      for (int i = 0; i < 3; ++i) gin.x[i] = coords[(size_t)i * n + p];
+    }
+    if (gauge == 0)
+      dg::gh_prologue<0>(g, pi, phi, Jm, gam[p], gam[n + p], gam[2 * n + p], gin, ctx, Q);
+    else if (gauge == 1)
+      dg::gh_prologue<1>(g, pi, phi, Jm, gam[p], gam[n + p], gam[2 * n + p], gin, ctx, Q);
     else
-      dg::gh_prologue<false>(g, pi, phi, Jm, gam[p], gam[n + p], gam[2 * n + p], &gh, ctx, Q);
+      dg::gh_prologue<2>(g, pi, phi, Jm, gam[p], gam[n + p], gam[2 * n + p], gin, ctx, Q);
     for (int s = 0; s < 10; ++s) {
       double ph[3], dgl[3], dpl[3], dphl[3][3], og, op, oph[3];
       for (int m = 0; m < 3; ++m) ph[m] = phi[m][s];

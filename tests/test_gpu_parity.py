@@ -308,3 +308,27 @@ def test_partitioned_evolution_matches_single_context(system, world):
         got[part.global_ids] = c.get_state()
         assert c.rhs_evaluations == single.ctx.rhs_evaluations
     np.testing.assert_array_equal(got, ref)
+
+
+def test_gh_rhs_damped_harmonic():
+    """DampedHarmonic gauge (DampedHarmonic.cpp:70-439) inside the fused volume
+    kernel vs the oracle (pinned by the reference's DampedHarmonic.py); the
+    parameters are those of Test_DuDt.cpp's DampedHarmonic{100, {1.2, 1.5, 1.7},
+    {2, 4, 6}} with a smaller width so that the spatial weight varies."""
+    N = 6
+    rng = np.random.default_rng(31)
+    brick, x, u, J, stat = _gh_problem(rng, N, 1, noise=5e-2)
+    nb = brick.neighbors()
+    params = [3.0, 1.2, 1.5, 1.7, 2, 4, 6]
+    ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_gauge(lib.GAUGE_DAMPED_HARMONIC, params)
+    ctx.set_state(u)
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    ref = orc.dg_rhs(1, N, u, J, stat, nb, gauge_params=np.array([2.0] + params), coords=x)
+    ref_h = orc.dg_rhs(1, N, u, J, stat, nb)
+    assert _relerr(got, ref, GH_BLOCKS) < TOL
+    assert _relerr(ref_h, ref, GH_BLOCKS) > 1e-6  # the gauge terms do matter here
+    ctx.close()

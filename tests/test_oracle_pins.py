@@ -262,3 +262,21 @@ def test_adams_coefficients():
     for p in range(4):
         exact = (2.5 ** (p + 1) - 1.9 ** (p + 1)) / (p + 1)
         assert abs(sum(ci * t ** p for ci, t in zip(c, times)) - exact) < 1e-12
+
+
+def test_damped_harmonic_vs_reference_numpy(golden_dir):
+    """DampedHarmonic H_a, d_a H_b vs fixtures from the reference's
+    DampedHarmonic.py (Test_DampedHarmonic.cpp compares the C++ with the same
+    python at the pypp default tolerance)."""
+    z = np.load(os.path.join(golden_dir, "damped_harmonic.npz"))
+    L = orc.lib()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for p in range(z["g"].shape[0]):
+        sigma, aL1, aL2, aS = z["params"][p]
+        gp = np.array([2.0, sigma, aL1, aL2, aS, 4, 4, 4])
+        H = np.zeros(4); dH = np.zeros((4, 4))
+        g = np.ascontiguousarray(z["g"][p]); pi = np.ascontiguousarray(z["pi"][p])
+        phi = np.ascontiguousarray(z["phi"][p]); x = np.ascontiguousarray(z["x"][p])
+        L.orc_damped_harmonic(P(g), P(pi), P(phi), P(x), P(gp), P(H), P(dH))
+        np.testing.assert_allclose(H, z["H"][p], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(dH, z["dH"][p], rtol=1e-11, atol=1e-12)

@@ -42,9 +42,9 @@ def _du_from_logical(dlog, J, C, n):
     return du
 
 
-@pytest.mark.parametrize("harmonic", [1, 0])
-def test_gh_volume_algebra(harness, harmonic):
-    rng = np.random.default_rng(11 + harmonic)
+@pytest.mark.parametrize("gauge", [0, 1, 2])
+def test_gh_volume_algebra(harness, gauge):
+    rng = np.random.default_rng(11 + gauge)
     n = 64
     u = _random_physical_gh_state(rng, n)
     dlog = rng.uniform(-0.5, 0.5, (150, n))
@@ -52,11 +52,14 @@ def test_gh_volume_algebra(harness, harmonic):
     gam = rng.uniform(-1, 1, (3, n))
     H = rng.uniform(-1, 1, (4, n)); dH = rng.uniform(-1, 1, (16, n))
     dt = np.zeros((50, n))
-    harness.h_gh_volume(n, harmonic, P(u), P(dlog), P(J), P(gam), P(H), P(dH), P(dt))
+    dhp = np.array([12.0, 1.2, 1.5, 1.7, 2, 4, 6])  # like Test_DuDt.cpp's DampedHarmonic
+    coords = rng.uniform(-3, 3, (3, n))
+    harness.h_gh_volume(n, gauge, P(u), P(dlog), P(J), P(gam), P(H), P(dH), P(dhp), P(coords),
+                        P(dt))
     du = _du_from_logical(dlog, J, 50, n)
-    ref = orc.gh_time_derivative(u, du, gam[0], gam[1], gam[2],
-                                 gauge_params=orc.GAUGE_HARMONIC if harmonic else orc.GAUGE_GIVEN,
-                                 H=H, dH=dH)
+    gp = [orc.GAUGE_HARMONIC, orc.GAUGE_GIVEN, np.concatenate([[2.0], dhp])][gauge]
+    ref = orc.gh_time_derivative(u, du, gam[0], gam[1], gam[2], gauge_params=gp, H=H, dH=dH,
+                                 coords=coords)
     for blk in (slice(0, 10), slice(10, 20), slice(20, 50)):
         assert _maxrel(dt[blk], ref[blk]) < 1e-13
 
