@@ -159,6 +159,14 @@ int dgrhs_end_substep(dgrhs_ctx* ctx, int* is_step_done);
  * a scratch derivative slot). */
 int dgrhs_time_kernels(dgrhs_ctx* ctx, int reps, int update_terms, double* ms);
 
+/* GH constraint diagnostics of the current state, as the
+ * L2Norm with Components: Sum of ObserveNorms (ParallelAlgorithms/Events/
+ * ObserveNorms.hpp:60-80) over this context's elements: norms[0] gauge
+ * constraint C_a = H_a + Gamma_a (GeneralizedHarmonic/Constraints.cpp:965-1000),
+ * norms[1] three-index constraint d_i g_ab - Phi_iab (:935-962), norms[2]
+ * four-index constraint eps_ijk d_j Phi_kab (:1070-1100). */
+int dgrhs_gh_constraint_norms(dgrhs_ctx* ctx, double* norms);
+
 /* Synchronise the context's stream. */
 int dgrhs_synchronize(dgrhs_ctx* ctx);
 /* cudaStream_t used by the context (for CUDA-event timing by the caller). */

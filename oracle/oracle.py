@@ -586,3 +586,33 @@ def l2_norm(v):
     """v [nelem, ncomp, n] (independent components only, like the reference)."""
     npts = v.shape[0] * v.shape[2]
     return math.sqrt(float(np.sum(v * v)) / npts)
+
+
+def gh_constraint_norms(N, u, invjac, H=None):
+    """L2 norms (ObserveNorms.hpp:60-80, Components: Sum) of the GH gauge
+    constraint C_a = H_a + Gamma_a (Constraints.cpp:965-1000), the three-index
+    constraint d_i g_ab - Phi_iab (:935-962) and the four-index constraint
+    eps_ijk d_j Phi_kab (:1070-1100; python twin TestFunctions.py:295-300).
+    u [nelem, 50, n], invjac [nelem, 9, n]."""
+    nelem, _, n = u.shape
+    sums = np.zeros(3)
+    eps = np.zeros((3, 3, 3))
+    eps[0, 1, 2] = eps[1, 2, 0] = eps[2, 0, 1] = 1.0
+    eps[0, 2, 1] = eps[2, 1, 0] = eps[1, 0, 2] = -1.0
+    for e in range(nelem):
+        Hg, _ = analytic_christoffel_gauge(N, u[e], invjac[e])  # = -Gamma_a
+        gam = -Hg
+        c1 = gam + (H[e] if H is not None else 0.0)
+        sums[0] += np.sum(c1 * c1)
+        du = partial_derivatives(N, u[e], invjac[e])
+        for s in range(10):
+            for i in range(3):
+                c3 = du[3 * s + i] - u[e, 20 + i + 3 * s]
+                sums[1] += np.sum(c3 * c3)
+            dphi = np.zeros((3, 3, n))  # [j, k] = d_j Phi_k
+            for j in range(3):
+                for k in range(3):
+                    dphi[j, k] = du[3 * (20 + k + 3 * s) + j]
+            c4 = np.einsum("ijk,jk...->i...", eps, dphi)
+            sums[2] += np.sum(c4 * c4)
+    return np.sqrt(sums / (nelem * n))

@@ -791,6 +791,35 @@ int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
   return 0;
 }
 
+int dgrhs_gh_constraint_norms(dgrhs_ctx* c, double* norms) {
+  CHECK_CTX(c);
+  if (c->system != DGRHS_SYSTEM_GH) return fail("constraint norms are defined for GH only");
+  if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC)
+    return fail("gauge-constraint norm with the DampedHarmonic gauge is not implemented");
+  CU(cudaSetDevice(c->device));
+  double* sums = nullptr;
+  if (dev_alloc(&sums, 3)) return 1;
+  dg::ConstraintArgs a{c->u, c->invjac, c->gauge == DGRHS_GAUGE_HARMONIC ? nullptr : c->gH,
+                       c->D, sums};
+  switch (c->N) {
+#define X(NN)                                                                 \
+  case NN:                                                                    \
+    dg::gh_constraints_kernel<NN><<<c->nelem, 256, 0, c->stream>>>(a);        \
+    break;
+    DG_FOR_EACH_N(X)
+#undef X
+  }
+  ++g_launches;
+  CU(cudaGetLastError());
+  double h[3];
+  CU(cudaMemcpyAsync(h, sums, 24, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(sums);
+  const double npts = (double)c->nelem * c->n;
+  for (int i = 0; i < 3; ++i) norms[i] = std::sqrt(h[i] / npts);
+  return 0;
+}
+
 int dgrhs_synchronize(dgrhs_ctx* c) {
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));

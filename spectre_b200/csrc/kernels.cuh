@@ -665,6 +665,109 @@ __global__ void __launch_bounds__(256) partial_derivatives_kernel(DerivArgs a) {
 }
 
 // --------------------------------------------------------------------------
+// GH constraint diagnostics for the parity norms: sums over all
+// points of |C_a|^2 (gauge constraint, Constraints.cpp:965-1000, harmonic or
+// field gauge), |C_iab|^2 (three-index, :935-962) and |C_iab|^2 of the
+// four-index constraint eps_ijk d_j Phi_kab (:1070-1100), independent components
+// only, like ObserveNorms' L2Norm with Components: Sum.  Not on the hot path.
+// --------------------------------------------------------------------------
+struct ConstraintArgs {
+  const double* u;
+  const double* invjac;
+  const double* gH;  // or nullptr (H = 0)
+  const double* D;
+  double* sums;      // [3]
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) gh_constraints_kernel(ConstraintArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
+  __shared__ __align__(16) double tile[4 * npad];
+  __shared__ double sD[N * N];
+  __shared__ double red[3][8];
+  const int e = blockIdx.x;
+  const double* ue = a.u + (size_t)e * 50 * npad;
+  for (int p = threadIdx.x; p < N * N; p += blockDim.x) sD[p] = a.D[p];
+  double acc[3] = {0.0, 0.0, 0.0};
+  // gauge constraint
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    double g[10], pi[10], phi[3][10], Gam[4];
+#pragma unroll
+    for (int s = 0; s < 10; ++s) {
+      g[s] = ue[(size_t)s * npad + p];
+      pi[s] = ue[(size_t)(10 + s) * npad + p];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) phi[m][s] = ue[(size_t)(20 + m + 3 * s) * npad + p];
+    }
+    gh_trace_christoffel(g, pi, phi, Gam);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const double c = Gam[x] + (a.gH ? a.gH[((size_t)e * 4 + x) * npad + p] : 0.0);
+      acc[0] += c * c;
+    }
+  }
+  // three- and four-index constraints, pair by pair
+  for (int s = 0; s < 10; ++s) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+      tile[p] = ue[(size_t)s * npad + p];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) tile[(1 + m) * npad + p] = ue[(size_t)(20 + m + 3 * s) * npad + p];
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+      const int i = p % N, j = (p / N) % N, k = p / (N * N);
+      double Di[N], Dj[N], Dk[N], dl[4][3], J[3][3];
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        Di[m] = sD[i * N + m];
+        Dj[m] = sD[j * N + m];
+        Dk[m] = sD[k * N + m];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) logical_derivs<N>(tile + c * npad, i, j, k, Di, Dj, Dk, dl[c]);
+      const double* je = a.invjac + (size_t)e * 9 * npad + p;
+#pragma unroll
+      for (int jh = 0; jh < 3; ++jh)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) J[jh][x] = je[(size_t)(jh + 3 * x) * npad];
+      double d[4][3];  // inertial derivatives d_x of g_s, Phi_0s, Phi_1s, Phi_2s
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          double v = J[0][x] * dl[c][0];
+          v += J[1][x] * dl[c][1];
+          v += J[2][x] * dl[c][2];
+          d[c][x] = v;
+        }
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        const double c3 = d[0][x] - tile[(1 + x) * npad + p];
+        acc[1] += c3 * c3;
+      }
+      const double c40 = d[3][1] - d[2][2];  // eps_0jk d_j Phi_k = d_1 Phi_2 - d_2 Phi_1
+      const double c41 = d[1][2] - d[3][0];
+      const double c42 = d[2][0] - d[1][1];
+      acc[2] += c40 * c40 + c41 * c41 + c42 * c42;
+    }
+  }
+  // block reduction
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+    atomicAdd(a.sums + threadIdx.x, v);
+  }
+}
+
+// --------------------------------------------------------------------------
 // AnalyticChristoffel gauge with the GaugeWave solution, evaluated at time t:
 // H_a = -Gamma_a[analytic(x, t)]  (AnalyticChristoffel.cpp:76-133,
 // GaugeWave.hpp:34-50).  The spatial derivative is then taken numerically by

@@ -470,6 +470,46 @@ DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
   }
 }
 
+// Gamma_a = g^{bc} Gamma_a,bc from the evolved variables (the trace that
+// gh::TimeDerivative forms at TimeDerivative.cpp:125-128); the gauge constraint
+// is C_a = H_a + Gamma_a (Constraints.cpp:965-1000).
+DG_HD void gh_trace_christoffel(const double (&g)[10], const double (&pi)[10],
+                                const double (&phi)[3][10], double (&Gam)[4]) {
+  Geom3p1 q;
+  geom_from_metric(g, q);
+  double G[10];
+  const double m1ol2 = -1.0 / (q.lapse * q.lapse);
+  G[0] = m1ol2;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) G[sym4(0, i + 1)] = -q.shift[i] * m1ol2;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      G[sym4(i + 1, j + 1)] = q.ig[sym3(i, j)] + q.shift[i] * q.shift[j] * m1ol2;
+  double dag[4][10];
+#pragma unroll
+  for (int s = 0; s < 10; ++s) {
+    double v = -q.lapse * pi[s];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) v += q.shift[m] * phi[m][s];
+    dag[0][s] = v;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) dag[m + 1][s] = phi[m][s];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double v = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = b; c < 4; ++c)
+        v += (b == c ? 1.0 : 2.0) * G[sym4(b, c)] * 0.5 *
+             (dag[b][sym4(c, a)] + dag[c][sym4(b, a)] - dag[a][sym4(b, c)]);
+    Gam[a] = v;
+  }
+}
+
 // One (mu,nu) pair: the pair's own five components, their 15 logical
 // derivatives (d*[jhat]) and Q -> the five time derivatives
 // (TimeDerivative.cpp:296-306, 342-392, 394-412).

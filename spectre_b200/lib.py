@@ -25,7 +25,8 @@ EXPORTS = [
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
     "dgrhs_take_steps", "dgrhs_time", "dgrhs_rhs_evaluations", "dgrhs_begin_substep",
-    "dgrhs_end_substep", "dgrhs_time_kernels", "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
+    "dgrhs_end_substep", "dgrhs_time_kernels", "dgrhs_gh_constraint_norms",
+    "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
     "dgrhs_collocation_points_and_weights", "dgrhs_adams_bashforth_coefficients",
     "dgrhs_gh_time_derivative", "dgrhs_sw_time_derivative", "dgrhs_gh_package_data",
@@ -286,6 +287,12 @@ class Context:
         ms = np.zeros(3)
         _check(self._lib.dgrhs_time_kernels(self._h, reps, update_terms, _ptr(ms)))
         return ms
+
+    def gh_constraint_norms(self):
+        """L2 norms of the (gauge, three-index, four-index) constraints."""
+        out = np.zeros(3)
+        _check(self._lib.dgrhs_gh_constraint_norms(self._h, _ptr(out)))
+        return out
 
     def synchronize(self):
         _check(self._lib.dgrhs_synchronize(self._h))

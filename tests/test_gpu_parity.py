@@ -332,3 +332,33 @@ def test_gh_rhs_damped_harmonic():
     assert _relerr(got, ref, GH_BLOCKS) < TOL
     assert _relerr(ref_h, ref, GH_BLOCKS) > 1e-6  # the gauge terms do matter here
     ctx.close()
+
+
+def test_gh_constraint_norms():
+    """GH constraint norms (north_star parity metric): device diagnostics vs the
+    oracle on a perturbed gauge wave, and after a short evolution the norms of
+    the GPU state equal those of the oracle state to 1e-12 relative."""
+    N, dt = 5, 2e-4
+    rng = np.random.default_rng(12)
+    brick, x, u, J, stat = _gh_problem(rng, N, 1, noise=1e-3)
+    J = brick.inverse_jacobian()
+    nb = brick.neighbors()
+    stat[:, 0], stat[:, 1], stat[:, 2] = 1.0, -1.0, 1.0
+    ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u)
+    got = ctx.gh_constraint_norms()
+    ref = orc.gh_constraint_norms(N, u, J)
+    np.testing.assert_allclose(got, ref, rtol=1e-11)
+    assert (ref > 1e-6).all()
+    ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 3, 0.0, dt)
+    ctx.take_steps(3)
+    ev = orc.Evolution(lambda v, t: orc.dg_rhs(1, N, v, J, stat, nb), u, 0.0, dt, "AB3")
+    for _ in range(3):
+        ev.step()
+    np.testing.assert_allclose(ctx.gh_constraint_norms(), orc.gh_constraint_norms(N, ev.u, J),
+                               rtol=1e-11)
+    np.testing.assert_allclose(orc.gh_constraint_norms(N, ctx.get_state(), J),
+                               orc.gh_constraint_norms(N, ev.u, J), rtol=1e-12)
+    ctx.close()
