@@ -802,10 +802,13 @@ int dgrhs_gh_constraint_norms(dgrhs_ctx* c, double* norms) {
   dg::ConstraintArgs a{c->u, c->invjac, c->gauge == DGRHS_GAUGE_HARMONIC ? nullptr : c->gH,
                        c->D, sums};
   switch (c->N) {
-#define X(NN)                                                                 \
-  case NN:                                                                    \
-    dg::gh_constraints_kernel<NN><<<c->nelem, 256, 0, c->stream>>>(a);        \
-    break;
+#define X(NN)                                                                       \
+  case NN: {                                                                        \
+    constexpr int smem = (4 * dg::Cfg<NN>::npad + NN * NN) * 8;                     \
+    auto k = dg::gh_constraints_kernel<NN>;                                         \
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    k<<<c->nelem, 256, smem, c->stream>>>(a);                                       \
+  } break;
     DG_FOR_EACH_N(X)
 #undef X
   }

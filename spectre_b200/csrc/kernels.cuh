@@ -682,8 +682,9 @@ struct ConstraintArgs {
 template <int N>
 __global__ void __launch_bounds__(256) gh_constraints_kernel(ConstraintArgs a) {
   constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
-  __shared__ __align__(16) double tile[4 * npad];
-  __shared__ double sD[N * N];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);  // [4][npad]
+  double* sD = tile + 4 * npad;                        // [N*N]
   __shared__ double red[3][8];
   const int e = blockIdx.x;
   const double* ue = a.u + (size_t)e * 50 * npad;
