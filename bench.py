@@ -298,19 +298,26 @@ def main():
     kms = ctx.time_kernels(reps=5, update_terms=3)
     peak, peak_src = peaks()
     kb = kernel_alg_bytes(N)
-    names = ["face", "volume", "update"]
-    dom = int(np.argmax(kms))
+    kb["volume_update_fused"] = kb["volume"] + kb["update"]
+    names = ["face", "volume", "update", "volume_update_fused"]
+    # the step launches the face kernel and the fused volume+update kernel; the
+    # separate volume / update timings are reported for comparison only
+    in_step = ["face", "volume_update_fused"]
+    kms_d = {n: float(m) for n, m in zip(names, kms)}
+    dom_name = max(in_step, key=lambda n: kms_d[n])
     pts_local = ev.n_points
-    achieved = kb[names[dom]] * pts_local / (kms[dom] * 1e-3) / 1e9
+    achieved = kb[dom_name] * pts_local / (kms_d[dom_name] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": {"face": "gh_face_kernel", "volume": "gh_volume_kernel",
-                                    "update": "lincomb_kernel"}[names[dom]],
+        "bound": "hbm",
+        "kernel": {"face": "gh_face_kernel",
+                   "volume_update_fused": "gh_volume_kernel (stepper update fused)"}[dom_name],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None, "peak_source": peak_src,
-        "alg_bytes_per_launch": kb[names[dom]] * pts_local,
-        "kernels_ms": {n: float(m) for n, m in zip(names, kms)},
-        "kernels_frac": {n: kb[n] * pts_local / (m * 1e-3) / 1e9 / peak
-                         for n, m in zip(names, kms)},
+        "alg_bytes_per_launch": kb[dom_name] * pts_local,
+        "alg_bytes_note": "SURVEY 8(d) accounting: volume group + update group (the fused "
+                          "kernel actually moves less: u and dt_u are not re-read)",
+        "kernels_ms": kms_d,
+        "kernels_frac": {n: kb[n] * pts_local / (kms_d[n] * 1e-3) / 1e9 / peak for n in names},
         "step": {"b_alg_bytes_per_update": b_alg(N), "achieved": value / world * b_alg(N) / 1e9,
                  "frac": value / world * b_alg(N) / 1e9 / peak,
                  "note": "whole step per GPU against SURVEY.md 8(d) B_alg"},

@@ -150,13 +150,20 @@ int64_t dgrhs_rhs_evaluations(dgrhs_ctx* ctx);
  * *time the time at which the RHS must be evaluated; end_substep records the
  * derivative and updates u. is_step_done is set when a full step completed. */
 int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
+/* UpdateU (Time/Actions/UpdateU.hpp:82-89) is fused into the volume kernel by
+ * default: u_new = a*u + sum_j c_j v_j, same coefficients and term order as the
+ * separate update, written to a second state buffer that becomes the state at
+ * end_substep (so dgrhs_state_device_ptr changes from step to step).
+ * enable = 0 selects the separate update kernel (bit-identical results). */
+int dgrhs_set_fused_update(dgrhs_ctx* ctx, int enable);
 int dgrhs_end_substep(dgrhs_ctx* ctx, int* is_step_done);
 
 /* Measurement aid for bench.py (roofline of the individual kernels): runs the
  * face kernel, the volume kernel and a k-term stepper update `reps` times
  * each on the context's stream, bracketed by CUDA events, and returns the mean
- * milliseconds per launch in ms[0..2].  Does not change u (the update runs on
- * a scratch derivative slot). */
+ * milliseconds per launch in ms[0..2]; ms[3] is the volume kernel with the
+ * stepper update fused in (the kernel the steppers actually use).  Does not
+ * change u (updates go to scratch buffers). */
 int dgrhs_time_kernels(dgrhs_ctx* ctx, int reps, int update_terms, double* ms);
 
 /* GH constraint diagnostics of the current state, as the

@@ -219,6 +219,10 @@ struct dgrhs_ctx {
   int32_t *nbr = nullptr, *halo_map = nullptr;
   std::vector<double*> dt_slots;  // derivative buffers (history ring)
   double* u0 = nullptr;           // saved value (self-start / RK step start)
+  double* u_alt = nullptr;        // second state buffer for the fused update
+  bool fuse_update = true;        // fuse UpdateU into the volume kernel
+  dg::UpdateArgs pending_upd{};   // filled by begin_substep when fusing
+  bool upd_active = false;
   double* dt_last = nullptr;
   int gauge = DGRHS_GAUGE_HARMONIC;
   double gauge_params[8] = {0};
@@ -296,12 +300,13 @@ int launch_gauge(dgrhs_ctx* c, double time) {
 }
 
 template <int N>
-int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr) {
+int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
+                  const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
   if (ee <= eb) return 0;
   const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
   if (c->system == DGRHS_SYSTEM_GH) {
     dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
-                    c->gH, c->gdH, c->D, c->coords, {}, eb};
+                    c->gH, c->gdH, c->D, c->coords, {}, eb, upd};
     constexpr int smem = dg::gh_volume_smem_bytes<N>();
     if (c->gauge == DGRHS_GAUGE_HARMONIC) {
       auto k = dg::gh_volume_kernel<N, 0>;
@@ -320,7 +325,8 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr) {
       k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
     }
   } else {
-    dg::SwVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr, c->D, eb};
+    dg::SwVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr, c->D, eb,
+                    upd};
     constexpr int smem = dg::sw_volume_smem_bytes<N>();
     auto k = dg::sw_volume_kernel<N>;
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -347,13 +353,13 @@ int launch_pack(dgrhs_ctx* c) {
 }
 
 int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume_only,
-              bool do_gauge) {
+              bool do_gauge, const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
   switch (c->N) {
 #define X(NN)                                                        \
   case NN:                                                           \
     if (do_gauge && launch_gauge<NN>(c, time)) return 1;             \
     if (!volume_only && launch_faces<NN>(c, eb, ee)) return 1;       \
-    return launch_volume<NN>(c, dt, eb, ee, !volume_only);
+    return launch_volume<NN>(c, dt, eb, ee, !volume_only, upd);
     DG_FOR_EACH_N(X)
 #undef X
     default:
@@ -407,6 +413,57 @@ int ab_update(dgrhs_ctx* c, int order, long long start, long long end) {
   }
   const auto coef = ab_coefficients_ticks(ticks, start, end, c->tick_den, c->dt);
   return lincomb(c, c->u, 1.0, coef, v);
+}
+
+// Prepare the stepper update that the volume kernel will fuse for the substep
+// that begin_substep just set up.  Same coefficients and term order as the
+// unfused ab_update / RK path, so the result is bit-identical.
+int prepare_fused_update(dgrhs_ctx* c) {
+  c->upd_active = false;
+  if (!c->fuse_update) return 0;
+  if (!c->u_alt && dev_alloc(&c->u_alt, c->state_len())) return 1;
+  dg::UpdateArgs up{};
+  up.u_new = c->u_alt;
+  if (c->stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
+    const SubstepOp& op = c->cur_op;
+    if (op.kind != SubstepOp::kAbStep || op.order > 4) return 0;
+    const size_t h = c->history.size();
+    const size_t older = (size_t)op.order - 1;
+    if (h < older) return fail("internal error: history too short for fused update");
+    std::vector<long long> ticks;
+    for (size_t i = h - older; i < h; ++i) ticks.push_back(c->history[i].tick);
+    ticks.push_back(op.tick);
+    const auto coef = ab_coefficients_ticks(ticks, op.tick, op.tick_end, c->tick_den, c->dt);
+    up.a = 1.0;
+    up.nterms = (int)older;
+    for (size_t j = 0; j < older; ++j) {
+      up.c[j] = coef[j];
+      up.v[j] = c->dt_slots[c->history[h - older + j].slot];
+    }
+    up.c_new = coef.back();
+  } else {
+    const double dt = c->dt;
+    if (c->rk_substep == 0) {
+      up.a = 1.0;
+      up.nterms = 0;
+      up.c_new = dt;
+    } else if (c->rk_substep == 1) {
+      up.a = 0.25;
+      up.nterms = 1;
+      up.c[0] = 0.75;
+      up.v[0] = c->u0;
+      up.c_new = 0.25 * dt;
+    } else {
+      up.a = 2.0 / 3.0;
+      up.nterms = 1;
+      up.c[0] = 1.0 / 3.0;
+      up.v[0] = c->u0;
+      up.c_new = (2.0 / 3.0) * dt;
+    }
+  }
+  c->pending_upd = up;
+  c->upd_active = true;
+  return 0;
 }
 
 }  // namespace
@@ -473,7 +530,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (double* p : {c->u, c->invjac, c->coords, c->stat, c->corr, c->D, c->gH, c->gdH,
-                    c->halo_send, c->halo_recv, c->u0})
+                    c->halo_send, c->halo_recv, c->u0, c->u_alt})
     if (p) cudaFree(p);
   for (double* p : c->dt_slots) cudaFree(p);
   if (c->nbr) cudaFree(c->nbr);
@@ -597,7 +654,8 @@ int dgrhs_compute_time_derivative_range(dgrhs_ctx* c, double time, int eb, int e
   CU(cudaSetDevice(c->device));
   if (eb < 0 || ee > c->nelem || eb > ee) return fail("bad element range");
   if (eb == 0) ++c->rhs_evals;
-  return rhs_range(c, time, c->dt_last, eb, ee, false, eb == 0);
+  return rhs_range(c, time, c->dt_last, eb, ee, false, eb == 0,
+                   (c->in_substep && c->upd_active) ? c->pending_upd : dg::UpdateArgs{});
 }
 
 void* dgrhs_halo_send_ptr(dgrhs_ctx* c) { return c ? c->halo_send : nullptr; }
@@ -685,6 +743,13 @@ int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
     *time = c->t0 + ((double)(base + off[c->rk_substep]) / 2.0) * c->dt;
   }
   c->in_substep = true;
+  return prepare_fused_update(c);
+}
+
+int dgrhs_set_fused_update(dgrhs_ctx* c, int enable) {
+  CHECK_CTX(c);
+  if (c->in_substep) return fail("cannot change the update mode inside a substep");
+  c->fuse_update = enable != 0;
   return 0;
 }
 
@@ -700,7 +765,11 @@ int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
     if (op.kind == SubstepOp::kAbEvalOnly) {
       ab_clean(c, op.order + 1);  // history order was bumped, UpdateU skipped
     } else {
-      if (ab_update(c, op.order, op.tick, op.tick_end)) return 1;  // UpdateU
+      if (c->upd_active) {
+        std::swap(c->u, c->u_alt);  // UpdateU was fused into the volume kernel
+      } else if (ab_update(c, op.order, op.tick, op.tick_end)) {  // UpdateU
+        return 1;
+      }
       ab_clean(c, op.order);                                       // CleanHistory
       if (op.regular) {
         ++c->step_index;
@@ -711,7 +780,22 @@ int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
     const double dt = c->dt;
     const double* F = c->dt_slots[0];
     // Rk3HesthavenSsp.cpp:63-81
-    if (c->rk_substep == 0) {
+    if (c->upd_active) {
+      // the fused kernel wrote the substep result to u_alt
+      if (c->rk_substep == 0) {
+        double* old_u = c->u;  // becomes the saved step-start value, no copy
+        c->u = c->u_alt;
+        c->u_alt = c->u0;
+        c->u0 = old_u;
+      } else {
+        std::swap(c->u, c->u_alt);
+      }
+      if (c->rk_substep == 2) {
+        ++c->step_index;
+        done = 1;
+      }
+      c->rk_substep = (c->rk_substep + 1) % 3;
+    } else if (c->rk_substep == 0) {
       CU(cudaMemcpyAsync(c->u0, c->u, c->state_len() * 8, cudaMemcpyDeviceToDevice,
                          c->stream));
       if (lincomb(c, c->u, 1.0, {dt}, {F})) return 1;
@@ -726,6 +810,7 @@ int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
       done = 1;
     }
   }
+  c->upd_active = false;
   if (is_step_done) *is_step_done = done;
   return 0;
 }
@@ -738,7 +823,9 @@ int dgrhs_take_steps(dgrhs_ctx* c, int n_steps) {
     int done = 0;
     if (dgrhs_begin_substep(c, &t)) return 1;
     ++c->rhs_evals;
-    if (rhs_range(c, t, c->dt_last, 0, c->nelem, false, true)) return 1;
+    if (rhs_range(c, t, c->dt_last, 0, c->nelem, false, true,
+                  c->upd_active ? c->pending_upd : dg::UpdateArgs{}))
+      return 1;
     if (dgrhs_end_substep(c, &done)) return 1;
     if (done) ++s;
   }
@@ -757,7 +844,17 @@ int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
   double* scratch = c->dt_slots[update_terms];
-  for (int which = 0; which < 3; ++which) {
+  if (!c->u_alt && dev_alloc(&c->u_alt, c->state_len())) return 1;
+  dg::UpdateArgs fused{};
+  fused.u_new = c->u_alt;
+  fused.a = 1.0;
+  fused.c_new = 0.0;
+  fused.nterms = std::min(update_terms - 1, 3);
+  for (int j = 0; j < fused.nterms; ++j) {
+    fused.c[j] = 0.0;
+    fused.v[j] = c->dt_slots[j];
+  }
+  for (int which = 0; which < 4; ++which) {
     float total = 0.f;
     for (int r = -1; r < reps; ++r) {  // r = -1: warm-up
       CU(cudaEventRecord(e0, c->stream));
@@ -767,6 +864,7 @@ int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
   case NN:                                                                        \
     if (which == 0) rc = launch_faces<NN>(c, 0, c->nelem);                        \
     if (which == 1) rc = launch_volume<NN>(c, c->dt_last, 0, c->nelem, true);     \
+    if (which == 3) rc = launch_volume<NN>(c, scratch, 0, c->nelem, true, fused); \
     break;
         DG_FOR_EACH_N(X)
 #undef X

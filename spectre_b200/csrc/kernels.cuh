@@ -155,6 +155,28 @@ __device__ __forceinline__ double add_corrections(double v,
 }
 
 // --------------------------------------------------------------------------
+// Stepper update fused into the volume kernels (K12+K13 without a separate
+// pass): u_new = a*u + sum_j c_j v_j + c_new*dt_u, accumulated oldest term
+// first exactly like lincomb_kernel, written to a second state buffer (the
+// element tile of u is still being read by the other chunks of the element).
+// --------------------------------------------------------------------------
+struct UpdateArgs {
+  double* u_new;   // nullptr: no fused update
+  double a, c_new;
+  int nterms;      // older terms (<= 3)
+  double c[3];
+  const double* v[3];
+};
+
+__device__ __forceinline__ void fused_update(const UpdateArgs& up, size_t idx, double u,
+                                             double dt_new) {
+  double r = u * up.a;
+  for (int j = 0; j < up.nterms; ++j) r = fma(up.c[j], __ldg(up.v[j] + idx), r);
+  r = fma(up.c_new, dt_new, r);
+  up.u_new[idx] = r;
+}
+
+// --------------------------------------------------------------------------
 // GH volume kernel (K1+K2+K3+K11-add fused)
 // --------------------------------------------------------------------------
 struct GhVolArgs {
@@ -169,6 +191,7 @@ struct GhVolArgs {
   const double* coords;  // [E][3][npad] (DampedHarmonic gauge)
   DampedHarmonicParams dh;
   int elem_begin;
+  UpdateArgs upd;
 };
 
 template <int N>
@@ -306,6 +329,14 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
       dte[(size_t)(10 + s) * npad + pt] = o[1];
 #pragma unroll
       for (int m = 0; m < 3; ++m) dte[(size_t)(20 + m + 3 * s) * npad + pt] = o[2 + m];
+      if (a.upd.u_new) {
+        const size_t base = (size_t)e * 50 * npad + pt;
+        fused_update(a.upd, base + (size_t)s * npad, t[pt], o[0]);
+        fused_update(a.upd, base + (size_t)(10 + s) * npad, t[npad + pt], o[1]);
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          fused_update(a.upd, base + (size_t)(20 + m + 3 * s) * npad, ph[m], o[2 + m]);
+      }
     }
     __syncthreads();  // every reader is done with this stage
     if (tid == 0 && s + NS < 10) issue(s + NS, stage);
@@ -323,6 +354,7 @@ struct SwVolArgs {
   const double* corr;    // [E][6][5][f] or nullptr
   const double* D;
   int elem_begin;
+  UpdateArgs upd;
 };
 
 template <int N>
@@ -383,6 +415,7 @@ __global__ void __launch_bounds__(Cfg<N>::T) sw_volume_kernel(SwVolArgs a) {
       double v = out[c];
       if (corr_e) v = add_corrections<N, 5>(v, corr_e, c, i, j, k);
       dte[(size_t)c * npad + pt] = v;
+      if (a.upd.u_new) fused_update(a.upd, ((size_t)e * 5 + c) * npad + pt, u[c], v);
     }
   }
 }

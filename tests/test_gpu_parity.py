@@ -362,3 +362,26 @@ def test_gh_constraint_norms():
     np.testing.assert_allclose(orc.gh_constraint_norms(N, ctx.get_state(), J),
                                orc.gh_constraint_norms(N, ev.u, J), rtol=1e-12)
     ctx.close()
+
+
+@pytest.mark.parametrize("system,stepper", [("gh", "AB3"), ("gh", "RK3"), ("sw", "AB4"),
+                                            ("sw", "RK3"), ("gh", "AB1")])
+def test_fused_update_is_bit_identical_to_separate_update(system, stepper):
+    """UpdateU fused into the volume kernel (default) vs the separate
+    lincomb_kernel: same coefficients, same term order -> identical bits."""
+    from spectre_b200 import evolution
+    N = 5
+    problem = (evolution.gh_gauge_wave_problem([1, 1, 1], N) if system == "gh"
+               else evolution.scalar_wave_problem([1, 1, 1], N))
+    dt = 2e-4 if system == "gh" else 1e-3
+    states = []
+    for fused in (True, False):
+        if stepper == "RK3":
+            ev = evolution.Evolution(problem, lib.STEPPER_RK3_HESTHAVEN, 3, dt)
+        else:
+            ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, int(stepper[2:]), dt)
+        ev.ctx.set_fused_update(fused)
+        ev.ctx.take_steps(4)
+        states.append(ev.ctx.get_state())
+        ev.ctx.close()
+    np.testing.assert_array_equal(states[0], states[1])
