@@ -168,10 +168,19 @@ struct UpdateArgs {
   const double* v[3];
 };
 
+// the older terms are fetched early (hv) so that their latency hides behind
+// the derivative work of the pair
+__device__ __forceinline__ void fused_prefetch(const UpdateArgs& up, size_t idx,
+                                               double (&hv)[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) hv[j] = (j < up.nterms) ? __ldg(up.v[j] + idx) : 0.0;
+}
 __device__ __forceinline__ void fused_update(const UpdateArgs& up, size_t idx, double u,
-                                             double dt_new) {
+                                             const double (&hv)[3], double dt_new) {
   double r = u * up.a;
-  for (int j = 0; j < up.nterms; ++j) r = fma(up.c[j], __ldg(up.v[j] + idx), r);
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    if (j < up.nterms) r = fma(up.c[j], hv[j], r);
   r = fma(up.c_new, dt_new, r);
   up.u_new[idx] = r;
 }
@@ -300,6 +309,16 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
 #pragma unroll 1
   for (int s = 0; s < 10; ++s) {
     const int stage = s % NS;
+    const bool do_upd = a.upd.u_new != nullptr;
+    const size_t ubase = (size_t)e * 50 * npad + pt;
+    double hv[5][3];
+    if (active && do_upd) {
+      fused_prefetch(a.upd, ubase + (size_t)s * npad, hv[0]);
+      fused_prefetch(a.upd, ubase + (size_t)(10 + s) * npad, hv[1]);
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+        fused_prefetch(a.upd, ubase + (size_t)(20 + m + 3 * s) * npad, hv[2 + m]);
+    }
     mbar_wait(&bars[stage], (s / NS) & 1);
     const double* t = ring + stage * SD;
     if (active) {
@@ -329,13 +348,13 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
       dte[(size_t)(10 + s) * npad + pt] = o[1];
 #pragma unroll
       for (int m = 0; m < 3; ++m) dte[(size_t)(20 + m + 3 * s) * npad + pt] = o[2 + m];
-      if (a.upd.u_new) {
-        const size_t base = (size_t)e * 50 * npad + pt;
-        fused_update(a.upd, base + (size_t)s * npad, t[pt], o[0]);
-        fused_update(a.upd, base + (size_t)(10 + s) * npad, t[npad + pt], o[1]);
+      if (do_upd) {
+        fused_update(a.upd, ubase + (size_t)s * npad, t[pt], hv[0], o[0]);
+        fused_update(a.upd, ubase + (size_t)(10 + s) * npad, t[npad + pt], hv[1], o[1]);
 #pragma unroll
         for (int m = 0; m < 3; ++m)
-          fused_update(a.upd, base + (size_t)(20 + m + 3 * s) * npad, ph[m], o[2 + m]);
+          fused_update(a.upd, ubase + (size_t)(20 + m + 3 * s) * npad, ph[m], hv[2 + m],
+                       o[2 + m]);
       }
     }
     __syncthreads();  // every reader is done with this stage
@@ -399,6 +418,11 @@ __global__ void __launch_bounds__(Cfg<N>::T) sw_volume_kernel(SwVolArgs a) {
       for (int x = 0; x < 3; ++x) J[jh][x] = __ldg(je + (size_t)(jh + 3 * x) * npad);
     gamma2 = __ldg(a.stat + (size_t)e * npad + pt);
   }
+  double hv[5][3];
+  if (active && a.upd.u_new) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) fused_prefetch(a.upd, ((size_t)e * 5 + c) * npad + pt, hv[c]);
+  }
   mbar_wait(bar, 0);
   if (active) {
     double u[5], d[5][3], out[5];
@@ -415,7 +439,7 @@ __global__ void __launch_bounds__(Cfg<N>::T) sw_volume_kernel(SwVolArgs a) {
       double v = out[c];
       if (corr_e) v = add_corrections<N, 5>(v, corr_e, c, i, j, k);
       dte[(size_t)c * npad + pt] = v;
-      if (a.upd.u_new) fused_update(a.upd, ((size_t)e * 5 + c) * npad + pt, u[c], v);
+      if (a.upd.u_new) fused_update(a.upd, ((size_t)e * 5 + c) * npad + pt, u[c], hv[c], v);
     }
   }
 }
