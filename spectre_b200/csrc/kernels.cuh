@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
   // ---- prologue: everything that needs all 50 components at the point ----
   GhContext ctx;
   if (active) {
-    double g[10], pi[10], phi[3][10], J[3][3], Q[10];
+    double g[10], pi[10], phi[3][10], Q[10], ig[6];
 #pragma unroll
     for (int s = 0; s < 10; ++s) {
       g[s] = __ldg(ue + (size_t)s * npad + pt);
@@ -260,11 +260,6 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
       for (int m = 0; m < 3; ++m)
         phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad + pt);
     }
-    const double* je = a.invjac + (size_t)e * 9 * npad + pt;
-#pragma unroll
-    for (int jh = 0; jh < 3; ++jh)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) J[jh][i] = __ldg(je + (size_t)(jh + 3 * i) * npad);
     const double* se = a.stat + (size_t)e * 3 * npad + pt;
     const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad),
                  gamma2 = __ldg(se + 2 * npad);
@@ -287,9 +282,19 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
         for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
       }
     }
-    gh_prologue<kGauge>(g, pi, phi, J, gamma0, gamma1, gamma2, gin, ctx, Q);
+    gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig);
 #pragma unroll
     for (int s = 0; s < 10; ++s) sQ[s * T + tid] = Q[s];
+    // the inverse Jacobian is fetched only now: keeping its 9 values out of
+    // the register-critical part of the prologue avoids spills
+    asm volatile("" ::: "memory");
+    double J[3][3];
+    const double* je = a.invjac + (size_t)e * 9 * npad + pt;
+#pragma unroll
+    for (int jh = 0; jh < 3; ++jh)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) J[jh][i] = __ldg(je + (size_t)(jh + 3 * i) * npad);
+    gh_context_set_jacobian(ctx, J, ig);
   }
   __syncthreads();  // sD visible, barrier init visible to all waiters
 

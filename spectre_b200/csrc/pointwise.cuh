@@ -215,11 +215,49 @@ struct GaugeInput {
 // three quadratic contractions and the gauge terms.
 //   g, pi: sym4 order; phi[m][sym4]; J[jhat][i]
 // kGauge: 0 Harmonic, 1 fields supplied, 2 DampedHarmonic
+// Folds the inverse Jacobian into the linear coefficients of the context
+// (shift_hat, Gj, J); ig = gamma^{ij} as returned by gh_prologue_core.
+DG_HD void gh_context_set_jacobian(GhContext& ctx, const double (&J)[3][3],
+                                   const double (&ig)[6]) {
+#pragma unroll
+  for (int jh = 0; jh < 3; ++jh) {
+    double v = J[jh][0] * ctx.shift[0];
+    v += J[jh][1] * ctx.shift[1];
+    v += J[jh][2] * ctx.shift[2];
+    ctx.shift_hat[jh] = v;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      double s = J[jh][0] * ig[sym3(0, n)];
+      s += J[jh][1] * ig[sym3(1, n)];
+      s += J[jh][2] * ig[sym3(2, n)];
+      ctx.Gj[jh][n] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ctx.J[jh][i] = J[jh][i];
+  }
+}
+
+template <int kGauge>
+DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
+                            const double (&phi)[3][10], double gamma0, double gamma1,
+                            double gamma2, const GaugeInput& gin, GhContext& ctx,
+                            double (&Q)[10], double (&ig_out)[6]);
+
 template <int kGauge>
 DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
                        const double (&phi)[3][10], const double (&J)[3][3],
                        double gamma0, double gamma1, double gamma2,
                        const GaugeInput& gin, GhContext& ctx, double (&Q)[10]) {
+  double ig[6];
+  gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig);
+  gh_context_set_jacobian(ctx, J, ig);
+}
+
+template <int kGauge>
+DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
+                            const double (&phi)[3][10], double gamma0, double gamma1,
+                            double gamma2, const GaugeInput& gin, GhContext& ctx,
+                            double (&Q)[10], double (&ig_out)[6]) {
   constexpr bool kHarmonic = kGauge == 0;
   Geom3p1 q;
   geom_from_metric(g, q);
@@ -396,11 +434,11 @@ DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
       }
   }
   // T3_{mu nu} = tr(Gamma_mu G Gamma_nu G) = Gamma_nu,ab C_mu^{ab},
-  // C_mu = G Gamma_mu G (symmetric)  (:360-364)
-  {
-    double C[4][10];
+  // C_mu = G Gamma_mu G (symmetric)  (:360-364).  One C_mu is live at a time.
 #pragma unroll
-    for (int mu = 0; mu < 4; ++mu) {
+  for (int mu = 0; mu < 4; ++mu) {
+    double C[10];
+    {
       double A[4][4];  // A[a][d] = Gamma_mu,a,b G^{b d}
 #pragma unroll
       for (int a = 0; a < 4; ++a)
@@ -418,20 +456,18 @@ DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
           double v = G[sym4(e, 0)] * A[0][d];
 #pragma unroll
           for (int a = 1; a < 4; ++a) v += G[sym4(e, a)] * A[a][d];
-          C[mu][sym4(e, d)] = (e == d) ? v : 2.0 * v;
+          C[sym4(e, d)] = (e == d) ? v : 2.0 * v;
         }
     }
 #pragma unroll
-    for (int mu = 0; mu < 4; ++mu)
+    for (int nu = mu; nu < 4; ++nu) {
+      double v = 0.0;
 #pragma unroll
-      for (int nu = mu; nu < 4; ++nu) {
-        double v = 0.0;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = a; b < 4; ++b) v += DG_CHR(nu, a, b) * C[mu][sym4(a, b)];
-        Q[sym4(mu, nu)] -= 2.0 * v;
-      }
+        for (int b = a; b < 4; ++b) v += DG_CHR(nu, a, b) * C[sym4(a, b)];
+      Q[sym4(mu, nu)] -= 2.0 * v;
+    }
   }
 #undef DG_CHR
   // linear-coefficient context
@@ -453,21 +489,7 @@ DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
       ctx.V[i][m] = v;
     }
 #pragma unroll
-  for (int jh = 0; jh < 3; ++jh) {
-    double v = J[jh][0] * q.shift[0];
-    v += J[jh][1] * q.shift[1];
-    v += J[jh][2] * q.shift[2];
-    ctx.shift_hat[jh] = v;
-#pragma unroll
-    for (int n = 0; n < 3; ++n) {
-      double s = J[jh][0] * q.ig[sym3(0, n)];
-      s += J[jh][1] * q.ig[sym3(1, n)];
-      s += J[jh][2] * q.ig[sym3(2, n)];
-      ctx.Gj[jh][n] = s;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) ctx.J[jh][i] = J[jh][i];
-  }
+  for (int x = 0; x < 6; ++x) ig_out[x] = q.ig[x];
 }
 
 // Gamma_a = g^{bc} Gamma_a,bc from the evolved variables (the trace that
