@@ -156,6 +156,13 @@ int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
  * end_substep (so dgrhs_state_device_ptr changes from step to step).
  * enable = 0 selects the separate update kernel (bit-identical results). */
 int dgrhs_set_fused_update(dgrhs_ctx* ctx, int enable);
+/* GH volume work as two kernels (pointwise context kernel + high-occupancy
+ * streaming kernel at 16 warps/SM; opt-in, N <= 10) instead of the single
+ * fused kernel (default).  Results agree to rounding.  Measured on B200
+ * (config 2): 0.60 + 1.18 ms vs 1.74 ms for the fused kernel -- the streaming
+ * kernel becomes shared-memory bound (70 % of LSU wavefront peak), see
+ * profiles/. */
+int dgrhs_set_split_volume(dgrhs_ctx* ctx, int enable);
 int dgrhs_end_substep(dgrhs_ctx* ctx, int* is_step_done);
 
 /* Measurement aid for bench.py (roofline of the individual kernels): runs the

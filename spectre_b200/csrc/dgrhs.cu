@@ -220,6 +220,8 @@ struct dgrhs_ctx {
   std::vector<double*> dt_slots;  // derivative buffers (history ring)
   double* u0 = nullptr;           // saved value (self-start / RK step start)
   double* u_alt = nullptr;        // second state buffer for the fused update
+  double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
+  bool split_volume = false;      // context + streaming kernels (opt-in, N <= 10)
   bool fuse_update = true;        // fuse UpdateU into the volume kernel
   dg::UpdateArgs pending_upd{};   // filled by begin_substep when fusing
   bool upd_active = false;
@@ -299,6 +301,25 @@ int launch_gauge(dgrhs_ctx* c, double time) {
   return 0;
 }
 
+template <int N, int kGauge>
+int launch_gh_split(dgrhs_ctx* c, const dg::GhVolArgs& a, int eb, int ee) {
+  if (!c->ctxbuf &&
+      dev_alloc(&c->ctxbuf, (size_t)c->nelem * dg::kGhCtxComps * c->npad))
+    return 1;
+  dg::GhCtxArgs ca{c->u, c->stat, c->gH, c->gdH, c->coords, c->ctxbuf, a.dh, eb, ee};
+  const long long pts = (long long)(ee - eb) * c->n;
+  dg::gh_context_kernel<N, kGauge><<<(int)((pts + 255) / 256), 256, 0, c->stream>>>(ca);
+  ++g_launches;
+  CU(cudaGetLastError());
+  constexpr int smem = dg::SCfg<N>::smem_bytes;
+  auto k = dg::gh_stream_kernel<N>;
+  CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k<<<(ee - eb) * dg::Cfg<N>::nchunk, dg::Cfg<N>::T, smem, c->stream>>>(a, c->ctxbuf);
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <int N>
 int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
                   const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
@@ -307,6 +328,18 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
   if (c->system == DGRHS_SYSTEM_GH) {
     dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
                     c->gH, c->gdH, c->D, c->coords, {}, eb, upd};
+    if constexpr (dg::SCfg<N>::fits && N <= 10) {
+      if (c->split_volume) {
+        if (c->gauge == DGRHS_GAUGE_HARMONIC) return launch_gh_split<N, 0>(c, a, eb, ee);
+        if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+          if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
+          const double* p = c->gauge_params;
+          a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+          return launch_gh_split<N, 2>(c, a, eb, ee);
+        }
+        return launch_gh_split<N, 1>(c, a, eb, ee);
+      }
+    }
     constexpr int smem = dg::gh_volume_smem_bytes<N>();
     if (c->gauge == DGRHS_GAUGE_HARMONIC) {
       auto k = dg::gh_volume_kernel<N, 0>;
@@ -530,7 +563,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (double* p : {c->u, c->invjac, c->coords, c->stat, c->corr, c->D, c->gH, c->gdH,
-                    c->halo_send, c->halo_recv, c->u0, c->u_alt})
+                    c->halo_send, c->halo_recv, c->u0, c->u_alt, c->ctxbuf})
     if (p) cudaFree(p);
   for (double* p : c->dt_slots) cudaFree(p);
   if (c->nbr) cudaFree(c->nbr);
@@ -744,6 +777,12 @@ int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
   }
   c->in_substep = true;
   return prepare_fused_update(c);
+}
+
+int dgrhs_set_split_volume(dgrhs_ctx* c, int enable) {
+  CHECK_CTX(c);
+  c->split_volume = enable != 0;
+  return 0;
 }
 
 int dgrhs_set_fused_update(dgrhs_ctx* c, int enable) {

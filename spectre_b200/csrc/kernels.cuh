@@ -154,6 +154,30 @@ __device__ __forceinline__ double add_corrections(double v,
   return v;
 }
 
+// Same, with the point's (at most three) faces resolved once per thread:
+// off[d] = offset of the point inside a [6][C][f] block for dimension d, or -1.
+template <int N, int C>
+struct FaceSlots {
+  int off[3];
+  __device__ __forceinline__ void init(int i, int j, int k) {
+    constexpr int f = N * N;
+    off[0] = i == 0 ? (0 * C) * f + j + N * k : (i == N - 1 ? (1 * C) * f + j + N * k : -1);
+    off[1] = j == 0 ? (2 * C) * f + i + N * k : (j == N - 1 ? (3 * C) * f + i + N * k : -1);
+    off[2] = k == 0 ? (4 * C) * f + i + N * j : (k == N - 1 ? (5 * C) * f + i + N * j : -1);
+  }
+  // N >= 2, so lower and upper face of a dimension are distinct points
+  __device__ __forceinline__ double add(double v, const double* __restrict__ blk,
+                                        int comp) const {
+    constexpr int f = N * N;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double c = off[d] >= 0 ? blk[off[d] + comp * f] : 0.0;
+      v += c;
+    }
+    return v;
+  }
+};
+
 // --------------------------------------------------------------------------
 // Stepper update fused into the volume kernels (K12+K13 without a separate
 // pass): u_new = a*u + sum_j c_j v_j + c_new*dt_u, accumulated oldest term
@@ -309,6 +333,8 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
     }
   }
   double* __restrict__ dte = a.dt + (size_t)e * 50 * npad;
+  FaceSlots<N, 5> slots;
+  slots.init(i, j, k);
 
   // ---- stream the ten (mu,nu) pairs through the ring ----
 #pragma unroll 1
@@ -347,7 +373,7 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
       if (with_corr) {
         const double* cs = t + 5 * npad;  // [6][5][f]
 #pragma unroll
-        for (int c = 0; c < 5; ++c) o[c] = add_corrections<N, 5>(o[c], cs, c, i, j, k);
+        for (int c = 0; c < 5; ++c) o[c] = slots.add(o[c], cs, c);
       }
       dte[(size_t)s * npad + pt] = o[0];
       dte[(size_t)(10 + s) * npad + pt] = o[1];
@@ -363,6 +389,287 @@ __global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
       }
     }
     __syncthreads();  // every reader is done with this stage
+    if (tid == 0 && s + NS < 10) issue(s + NS, stage);
+  }
+}
+
+// --------------------------------------------------------------------------
+// Two-kernel GH volume path (N <= 10): gh_context_kernel + gh_stream_kernel.
+// The single fused kernel above needs 254 registers for its prologue and is
+// therefore limited to 8 warps/SM for the streaming phase as well.  Here the
+// prologue runs as its own pointwise kernel (255 registers, pure streaming)
+// and leaves 26 doubles per point in HBM; the streaming kernel then fits in
+// 128 registers, i.e. two CTAs (16 warps) per SM.
+// --------------------------------------------------------------------------
+struct GhCtxArgs {
+  const double* u;
+  const double* stat;
+  const double* gH;
+  const double* gdH;
+  const double* coords;
+  double* ctxbuf;  // [E][26][npad]
+  DampedHarmonicParams dh;
+  int elem_begin, elem_end;
+};
+
+template <int N, int kGauge>
+__global__ void __launch_bounds__(256, 1) gh_context_kernel(GhCtxArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(a.elem_end - a.elem_begin) * n) return;
+  const int e = a.elem_begin + (int)(idx / n);
+  const int pt = (int)(idx % n);
+  const double* __restrict__ ue = a.u + (size_t)e * 50 * npad + pt;
+  double g[10], pi[10], phi[3][10], Q[10], ig[6];
+#pragma unroll
+  for (int s = 0; s < 10; ++s) {
+    g[s] = __ldg(ue + (size_t)s * npad);
+    pi[s] = __ldg(ue + (size_t)(10 + s) * npad);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad);
+  }
+  const double* se = a.stat + (size_t)e * 3 * npad + pt;
+  const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad), gamma2 = __ldg(se + 2 * npad);
+  GaugeH gh;
+  GaugeInput gin;
+  gin.fields = &gh;
+  if constexpr (kGauge == 2) {
+    gin.dh = a.dh;
+    const double* xe = a.coords + (size_t)e * 3 * npad + pt;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) gin.x[x] = __ldg(xe + (size_t)x * npad);
+  }
+  if constexpr (kGauge == 1) {
+    const double* he = a.gH + (size_t)e * 4 * npad + pt;
+    const double* dhe = a.gdH + (size_t)e * 16 * npad + pt;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      gh.H[x] = __ldg(he + (size_t)x * npad);
+#pragma unroll
+      for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
+    }
+  }
+  GhContext ctx;
+  gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig);
+  double* __restrict__ out = a.ctxbuf + (size_t)e * kGhCtxComps * npad + pt;
+#pragma unroll
+  for (int s = 0; s < 10; ++s) out[(size_t)s * npad] = Q[s];
+  out[(size_t)10 * npad] = ctx.half_pi_nn;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    out[(size_t)(11 + m) * npad] = ctx.w[m];
+    out[(size_t)(14 + m) * npad] = ctx.half_phi_nn[m];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) out[(size_t)(17 + 3 * m + x) * npad] = ctx.V[m][x];
+  }
+}
+
+template <int N>
+struct SCfg {
+  static constexpr int T = Cfg<N>::T;
+  static constexpr int npad = Cfg<N>::npad;
+  static constexpr int stage_doubles = Cfg<N>::stage_doubles;
+  static constexpr int nstage = 2;
+  // ring | per-thread J (9) and V (9) | D | barriers
+  static constexpr int smem_bytes =
+      (nstage * stage_doubles + 18 * T + (N * N + 1) / 2 * 2) * 8 + 64;
+  static constexpr bool fits = smem_bytes <= 232448;
+  static constexpr int min_blocks = (2 * (smem_bytes + 1024) <= 233472) ? 2 : 1;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int N>
+__global__ void __launch_bounds__(SCfg<N>::T, SCfg<N>::min_blocks)
+    gh_stream_kernel(GhVolArgs a, const double* __restrict__ ctxbuf) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, T = Cfg<N>::T, f = N * N;
+  constexpr int NS = SCfg<N>::nstage, SD = SCfg<N>::stage_doubles;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  double* sVJ = ring + NS * SD;  // [18][T]: J (jh + 3 i), then V (3 i + m)
+  double* sD = sVJ + 18 * T;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (N * N + 1) / 2 * 2);
+
+  const int e = a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
+  const int chunk = blockIdx.x % Cfg<N>::nchunk;
+  const int tid = threadIdx.x;
+  const int pt = chunk * T + tid;
+  const bool active = pt < n;
+  const double* __restrict__ ue = a.u + (size_t)e * 50 * npad;
+  const bool with_corr = a.corr != nullptr;
+  const double* __restrict__ ce = with_corr ? a.corr + (size_t)e * 10 * 30 * f : nullptr;
+
+  auto issue = [&](int s, int stage) {
+    double* t = ring + stage * SD;
+    mbar_expect_tx(&bars[stage], (5 * npad + (with_corr ? 30 * f : 0)) * 8);
+    tma_bulk_g2s(t, ue + (size_t)s * npad, npad * 8, &bars[stage]);
+    tma_bulk_g2s(t + npad, ue + (size_t)(10 + s) * npad, npad * 8, &bars[stage]);
+    tma_bulk_g2s(t + 2 * npad, ue + (size_t)(20 + 3 * s) * npad, 3 * npad * 8,
+                 &bars[stage]);
+    if (with_corr) tma_bulk_g2s(t + 5 * npad, ce + (size_t)s * 30 * f, 30 * f * 8, &bars[stage]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < NS; ++st) mbar_init(&bars[st], 1);
+    mbar_fence_init();
+#pragma unroll
+    for (int st = 0; st < NS; ++st) issue(st, st);
+  }
+  for (int idx = tid; idx < N * N; idx += T) sD[idx] = a.D[idx];
+
+  // ---- per-point context: geometry from g, the rest from the context kernel
+  GhStreamCtx c;
+  const double* __restrict__ cb = ctxbuf + (size_t)e * kGhCtxComps * npad + pt;
+  if (active) {
+    double g[10];
+#pragma unroll
+    for (int s = 0; s < 10; ++s) g[s] = __ldg(ue + (size_t)s * npad + pt);
+    Geom3p1 q;
+    geom_from_metric(g, q);
+    c.lapse = q.lapse;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) c.shift[x] = q.shift[x];
+#pragma unroll
+    for (int x = 0; x < 6; ++x) c.ig[x] = q.ig[x];
+    const double* se = a.stat + (size_t)e * 3 * npad + pt;
+    c.gamma1 = __ldg(se + npad);
+    c.gamma2 = __ldg(se + 2 * npad);
+    c.half_pi_nn = __ldg(cb + (size_t)10 * npad);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      c.w[m] = __ldg(cb + (size_t)(11 + m) * npad);
+      c.half_phi_nn[m] = __ldg(cb + (size_t)(14 + m) * npad);
+    }
+    const double* je = a.invjac + (size_t)e * 9 * npad + pt;
+#pragma unroll
+    for (int x = 0; x < 9; ++x) {
+      sVJ[x * T + tid] = __ldg(je + (size_t)x * npad);
+      sVJ[(9 + x) * T + tid] = __ldg(cb + (size_t)(17 + x) * npad);
+    }
+  }
+  __syncthreads();  // sD and the barrier initialisation are visible
+
+  const int i = pt % N, j = (pt / N) % N, k = pt / (N * N);
+  double* __restrict__ dte = a.dt + (size_t)e * 50 * npad;
+  const bool do_upd = a.upd.u_new != nullptr;
+  const size_t ubase = (size_t)e * 50 * npad + pt;
+
+#pragma unroll 1
+  for (int s = 0; s < 10; ++s) {
+    const int stage = s % NS;
+    double Qs = 0.0;
+    if (active) {
+      Qs = __ldg(cb + (size_t)s * npad);
+      if (do_upd) {
+        // the older derivative terms of the fused update: warm L2 now, load later
+        for (int jt = 0; jt < a.upd.nterms; ++jt) {
+          prefetch_l2(a.upd.v[jt] + ubase + (size_t)s * npad);
+          prefetch_l2(a.upd.v[jt] + ubase + (size_t)(10 + s) * npad);
+#pragma unroll
+          for (int m = 0; m < 3; ++m)
+            prefetch_l2(a.upd.v[jt] + ubase + (size_t)(20 + m + 3 * s) * npad);
+        }
+      }
+    }
+    mbar_wait(&bars[stage], (s / NS) & 1);
+    const double* t = ring + stage * SD;
+    if (active) {
+      // sum-factorised logical derivatives of the pair's five components; the
+      // D rows come from shared memory and are shared by the five components
+      double acc[5][3];
+#pragma unroll
+      for (int cc = 0; cc < 5; ++cc) acc[cc][0] = acc[cc][1] = acc[cc][2] = 0.0;
+      const int row = N * (j + N * k);
+      if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int m2 = 0; m2 < N / 2; ++m2) {
+          const double2 dm = *reinterpret_cast<const double2*>(sD + i * N + 2 * m2);
+#pragma unroll
+          for (int cc = 0; cc < 5; ++cc) {
+            const double2 v = *reinterpret_cast<const double2*>(t + cc * npad + row + 2 * m2);
+            acc[cc][0] = fma(dm.x, v.x, acc[cc][0]);
+            acc[cc][0] = fma(dm.y, v.y, acc[cc][0]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          const double dm = sD[i * N + m];
+#pragma unroll
+          for (int cc = 0; cc < 5; ++cc) acc[cc][0] = fma(dm, t[cc * npad + row + m], acc[cc][0]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const double dm = sD[j * N + m];
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc)
+          acc[cc][1] = fma(dm, t[cc * npad + i + N * (m + N * k)], acc[cc][1]);
+      }
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const double dm = sD[k * N + m];
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc)
+          acc[cc][2] = fma(dm, t[cc * npad + i + N * (j + N * m)], acc[cc][2]);
+      }
+      // inertial derivatives d_x = J(jhat, x) d_jhat (PartialDerivatives.tpp:79-109)
+      double di[5][3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        const double j0 = sVJ[(0 + 3 * x) * T + tid], j1 = sVJ[(1 + 3 * x) * T + tid],
+                     j2 = sVJ[(2 + 3 * x) * T + tid];
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) {
+          double v = j0 * acc[cc][0];
+          v = fma(j1, acc[cc][1], v);
+          v = fma(j2, acc[cc][2], v);
+          di[cc][x] = v;
+        }
+      }
+      double V[3][3], ph[3], dphi[3][3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        ph[m] = t[(2 + m) * npad + pt];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          V[m][x] = sVJ[(9 + 3 * m + x) * T + tid];
+          dphi[m][x] = di[2 + m][x];
+        }
+      }
+      double o[5];
+      {
+        double oph[3];
+        gh_pair_rhs_inertial(c, V, Qs, t[pt], t[npad + pt], ph, di[0], di[1], dphi, o[0], o[1],
+                             oph);
+        o[2] = oph[0];
+        o[3] = oph[1];
+        o[4] = oph[2];
+      }
+      if (with_corr) {
+        const double* cs = t + 5 * npad;
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) o[cc] = add_corrections<N, 5>(o[cc], cs, cc, i, j, k);
+      }
+      dte[(size_t)s * npad + pt] = o[0];
+      dte[(size_t)(10 + s) * npad + pt] = o[1];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) dte[(size_t)(20 + m + 3 * s) * npad + pt] = o[2 + m];
+      if (do_upd) {
+        const size_t off[5] = {(size_t)s * npad, (size_t)(10 + s) * npad,
+                               (size_t)(20 + 3 * s) * npad, (size_t)(21 + 3 * s) * npad,
+                               (size_t)(22 + 3 * s) * npad};
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) {
+          double hv[3];
+          fused_prefetch(a.upd, ubase + off[cc], hv);
+          fused_update(a.upd, ubase + off[cc], t[cc * npad + pt], hv, o[cc]);
+        }
+      }
+    }
+    __syncthreads();
     if (tid == 0 && s + NS < 10) issue(s + NS, stage);
   }
 }

@@ -577,6 +577,59 @@ DG_HD void gh_pair_rhs(const GhContext& c, double Qs, double g, double pi,
 }
 
 // ---------------------------------------------------------------------------
+// Two-kernel variant of the GH volume work (context kernel + streaming kernel):
+// the context kernel stores, per point, the 26 values that need all 50
+// components (Q, and the normal contractions raised with gamma^{ij}); the
+// streaming kernel recomputes lapse/shift/gamma^{ij} from g and works with
+// inertial derivatives.
+// ---------------------------------------------------------------------------
+constexpr int kGhCtxComps = 26;  // Q 10 | half_pi_nn | w 3 | half_phi_nn 3 | V 9
+
+struct GhStreamCtx {
+  double lapse, shift[3], ig[6];
+  double gamma1, gamma2, half_pi_nn;
+  double w[3], half_phi_nn[3];
+};
+
+// same equations as gh_pair_rhs, with inertial derivatives:
+//   dgi[i] = d_i g, dpii[i] = d_i Pi, dphi[n][i] = d_i Phi_n; V[i][m]
+DG_HD void gh_pair_rhs_inertial(const GhStreamCtx& c, const double (&V)[3][3], double Qs,
+                                double g, double pi, const double (&ph)[3],
+                                const double (&dgi)[3], const double (&dpii)[3],
+                                const double (&dphi)[3][3], double& out_g, double& out_pi,
+                                double (&out_phi)[3]) {
+  double sphi = c.shift[0] * ph[0];
+  sphi += c.shift[1] * ph[1];
+  sphi += c.shift[2] * ph[2];
+  double sg = c.shift[0] * dgi[0];
+  sg += c.shift[1] * dgi[1];
+  sg += c.shift[2] * dgi[2];
+  const double c3s = sg - sphi;
+  out_g = (-c.lapse * pi + sphi) + (1.0 + c.gamma1) * c3s;
+  double t = Qs - c.half_pi_nn * pi;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) t -= c.w[m] * ph[m];
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+#pragma unroll
+    for (int n = 0; n < 3; ++n) t -= c.ig[sym3(m, n)] * dphi[n][m];
+  double o = c.lapse * t + (c.gamma1 * c.gamma2) * c3s;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) o += c.shift[m] * dpii[m];
+  out_pi = o;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double v = pi * c.half_phi_nn[i] - dpii[i] + c.gamma2 * (dgi[i] - ph[i]);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) v += V[i][m] * ph[m];
+    v *= c.lapse;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) v += c.shift[m] * dphi[i][m];
+    out_phi[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Faces.  One side of an interface at one face point.
 // ---------------------------------------------------------------------------
 struct GhFaceSide {

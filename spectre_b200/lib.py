@@ -25,7 +25,7 @@ EXPORTS = [
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
     "dgrhs_take_steps", "dgrhs_time", "dgrhs_rhs_evaluations", "dgrhs_begin_substep",
-    "dgrhs_end_substep", "dgrhs_set_fused_update", "dgrhs_time_kernels", "dgrhs_gh_constraint_norms",
+    "dgrhs_end_substep", "dgrhs_set_fused_update", "dgrhs_set_split_volume", "dgrhs_time_kernels", "dgrhs_gh_constraint_norms",
     "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
     "dgrhs_collocation_points_and_weights", "dgrhs_adams_bashforth_coefficients",
@@ -260,6 +260,9 @@ class Context:
     def set_stepper(self, stepper, order, t0, dt):
         _check(self._lib.dgrhs_set_stepper(self._h, stepper, order, ctypes.c_double(t0),
                                            ctypes.c_double(dt)))
+
+    def set_split_volume(self, enable: bool):
+        _check(self._lib.dgrhs_set_split_volume(self._h, int(enable)))
 
     def set_fused_update(self, enable: bool):
         _check(self._lib.dgrhs_set_fused_update(self._h, int(enable)))

@@ -62,6 +62,53 @@ void h_gh_volume(int n, int gauge, const double* u, const double* dlog,
   }
 }
 
+// two-kernel variant: context (26 values) -> streaming with inertial derivatives
+void h_gh_volume_split(int n, const double* u, const double* dlog, const double* J,
+                       const double* gam, double* dt) {
+  for (int p = 0; p < n; ++p) {
+    double g[10], pi[10], phi[3][10], Jm[3][3], Q[10], ig[6];
+    for (int s = 0; s < 10; ++s) {
+      g[s] = u[(size_t)s * n + p];
+      pi[s] = u[(size_t)(10 + s) * n + p];
+      for (int m = 0; m < 3; ++m) phi[m][s] = u[(size_t)(20 + m + 3 * s) * n + p];
+    }
+    for (int jh = 0; jh < 3; ++jh)
+      for (int i = 0; i < 3; ++i) Jm[jh][i] = J[(size_t)(jh + 3 * i) * n + p];
+    dg::GhContext ctx;
+    dg::GaugeInput gin;
+    gin.fields = nullptr;
+    dg::gh_prologue_core<0>(g, pi, phi, gam[p], gam[n + p], gam[2 * n + p], gin, ctx, Q, ig);
+    // what the streaming kernel rebuilds from g and the stored context
+    dg::Geom3p1 q;
+    dg::geom_from_metric(g, q);
+    dg::GhStreamCtx sc;
+    sc.lapse = q.lapse;
+    for (int i = 0; i < 3; ++i) sc.shift[i] = q.shift[i];
+    for (int i = 0; i < 6; ++i) sc.ig[i] = q.ig[i];
+    sc.gamma1 = gam[n + p];
+    sc.gamma2 = gam[2 * n + p];
+    sc.half_pi_nn = ctx.half_pi_nn;
+    for (int i = 0; i < 3; ++i) { sc.w[i] = ctx.w[i]; sc.half_phi_nn[i] = ctx.half_phi_nn[i]; }
+    for (int s = 0; s < 10; ++s) {
+      double ph[3], dl[5][3], di[5][3], og, op, oph[3];
+      for (int m = 0; m < 3; ++m) ph[m] = phi[m][s];
+      const int comps[5] = {s, 10 + s, 20 + 3 * s, 21 + 3 * s, 22 + 3 * s};
+      for (int c = 0; c < 5; ++c)
+        for (int jh = 0; jh < 3; ++jh) dl[c][jh] = dlog[(size_t)(3 * comps[c] + jh) * n + p];
+      for (int c = 0; c < 5; ++c)
+        for (int i = 0; i < 3; ++i)
+          di[c][i] = Jm[0][i] * dl[c][0] + Jm[1][i] * dl[c][1] + Jm[2][i] * dl[c][2];
+      double dphi[3][3];
+      for (int m = 0; m < 3; ++m)
+        for (int i = 0; i < 3; ++i) dphi[m][i] = di[2 + m][i];
+      dg::gh_pair_rhs_inertial(sc, ctx.V, Q[s], g[s], pi[s], ph, di[0], di[1], dphi, og, op, oph);
+      dt[(size_t)s * n + p] = og;
+      dt[(size_t)(10 + s) * n + p] = op;
+      for (int m = 0; m < 3; ++m) dt[(size_t)(20 + m + 3 * s) * n + p] = oph[m];
+    }
+  }
+}
+
 // faces: ui/ue [50][f]; unnorm_i/unnorm_e [3][f] (each side's own outward
 // unnormalised covector); gi/ge [2][f] = gamma1, gamma2; lift_n = N
 void h_gh_face(int f, int N, const double* ui, const double* ue,

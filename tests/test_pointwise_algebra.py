@@ -125,3 +125,19 @@ def test_sw_algebra(harness):
     L.orc_sw_package_data(n, P(ue), P(g2e), P(ne), P(pke))
     L.orc_sw_boundary_terms(n, P(pki), P(pke), P(ref))
     assert _maxrel(corr, ref) < 1e-14
+
+
+def test_gh_volume_split_algebra(harness):
+    """The context-kernel + streaming-kernel split (inertial derivatives, context
+    rebuilt from g) against the oracle."""
+    rng = np.random.default_rng(21)
+    n = 64
+    u = _random_physical_gh_state(rng, n)
+    dlog = rng.uniform(-0.5, 0.5, (150, n))
+    J = rng.uniform(-1, 1, (9, n))
+    gam = rng.uniform(-1, 1, (3, n))
+    dt = np.zeros((50, n))
+    harness.h_gh_volume_split(n, P(u), P(dlog), P(J), P(gam), P(dt))
+    ref = orc.gh_time_derivative(u, _du_from_logical(dlog, J, 50, n), gam[0], gam[1], gam[2])
+    for blk in (slice(0, 10), slice(10, 20), slice(20, 50)):
+        assert _maxrel(dt[blk], ref[blk]) < 1e-13
