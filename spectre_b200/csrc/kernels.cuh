@@ -555,6 +555,8 @@ __global__ void __launch_bounds__(SCfg<N>::T, SCfg<N>::min_blocks)
   double* __restrict__ dte = a.dt + (size_t)e * 50 * npad;
   const bool do_upd = a.upd.u_new != nullptr;
   const size_t ubase = (size_t)e * 50 * npad + pt;
+  FaceSlots<N, 5> slots;
+  slots.init(i, j, k);
 
 #pragma unroll 1
   for (int s = 0; s < 10; ++s) {
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(SCfg<N>::T, SCfg<N>::min_blocks)
       if (with_corr) {
         const double* cs = t + 5 * npad;
 #pragma unroll
-        for (int cc = 0; cc < 5; ++cc) o[cc] = add_corrections<N, 5>(o[cc], cs, cc, i, j, k);
+        for (int cc = 0; cc < 5; ++cc) o[cc] = slots.add(o[cc], cs, cc);
       }
       dte[(size_t)s * npad + pt] = o[0];
       dte[(size_t)(10 + s) * npad + pt] = o[1];
@@ -746,10 +748,12 @@ __global__ void __launch_bounds__(Cfg<N>::T) sw_volume_kernel(SwVolArgs a) {
     sw_point_rhs(u, d, J, gamma2, out);
     double* __restrict__ dte = a.dt + (size_t)e * 5 * npad;
     const double* corr_e = a.corr ? a.corr + (size_t)e * 6 * 5 * (N * N) : nullptr;
+    FaceSlots<N, 5> slots;
+    slots.init(i, j, k);
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
       double v = out[c];
-      if (corr_e) v = add_corrections<N, 5>(v, corr_e, c, i, j, k);
+      if (corr_e) v = slots.add(v, corr_e, c);
       dte[(size_t)c * npad + pt] = v;
       if (a.upd.u_new) fused_update(a.upd, ((size_t)e * 5 + c) * npad + pt, u[c], hv[c], v);
     }
