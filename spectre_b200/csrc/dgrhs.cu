@@ -271,8 +271,22 @@ int download(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
 template <int N>
 int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   if (ee <= eb) return 0;
-  dg::FaceArgs a{c->u, c->invjac, c->stat, c->nbr, c->halo_recv, c->corr, eb, ee};
-  const long long total = (long long)(ee - eb) * 6 * N * N;
+  // whole batch: every interface once; element ranges: the interior / boundary
+  // split of the multi-GPU schedule (see FaceArgs::pass)
+  int pass = 0, n_int = c->nelem;
+  if (!(eb == 0 && ee == c->nelem)) {
+    if (c->n_interior < 0)
+      return fail("element ranges need dgrhs_set_interior_count (interior elements first)");
+    n_int = c->n_interior;
+    if (eb == 0 && ee == n_int)
+      pass = 1;
+    else if (eb == n_int && ee == c->nelem)
+      pass = 2;
+    else
+      return fail("element range must be [0, n_interior) or [n_interior, n_elements)");
+  }
+  dg::FaceArgs a{c->u, c->invjac, c->stat, c->nbr, c->halo_recv, c->corr, c->nelem, n_int, pass};
+  const long long total = (long long)c->nelem * 6 * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)
     dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
@@ -583,6 +597,13 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
     if (v >= c->nelem) return fail("neighbor index %d out of range", v);
     if (v <= -2 && -(v + 2) >= c->nghost) return fail("ghost face index out of range");
   }
+  // conforming aligned interfaces: the neighbour's opposite face points back
+  for (int e = 0; e < c->nelem; ++e)
+    for (int d = 0; d < 6; ++d) {
+      const int v = neighbors[(size_t)e * 6 + d];
+      if (v >= 0 && neighbors[(size_t)v * 6 + (d ^ 1)] != e)
+        return fail("neighbor table is not symmetric at element %d direction %d", e, d);
+    }
   if (upload(c, c->invjac, inv_jacobian, 9)) return 1;
   if (coords) {
     if (!c->coords && dev_alloc(&c->coords, (size_t)c->nelem * 3 * c->npad)) return 1;

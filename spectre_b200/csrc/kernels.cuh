@@ -769,26 +769,54 @@ struct FaceArgs {
   const double* stat;     // [E][S][npad]
   const int32_t* nbr;     // [E][6]
   const double* ghost;    // [G][HC][f]   u (C) | J row (3) | gammas
-  double* corr;           // [E][6][C][f]
-  int elem_begin, elem_end;
+  double* corr;           // GH: [E][10][6][5][f] pair-major; SW: [E][6][5][f]
+  int nelem;
+  // Interfaces between two local elements are evaluated once, by the thread of
+  // the lower-side face, which writes the lifted corrections of BOTH elements
+  // (the packaged data of the two sides are shared; the reference evaluates
+  // dg_boundary_terms once per element and mortar, ApplyBoundaryCorrections.hpp
+  // :882-886).  pass: 0 = every interface; 1 = interfaces that touch an element
+  // below n_interior (+ external faces of those elements); 2 = the rest (incl.
+  // ghost faces) -- used to overlap the halo exchange.
+  int n_interior, pass;
 };
+
+// returns false if this (element, direction) task is not to be evaluated
+__device__ __forceinline__ bool face_task(const FaceArgs& a, int e, int d, int nb,
+                                          bool& two_sided) {
+  if (nb >= 0) {
+    if (d & 1) return false;  // handled by the neighbour's lower-face task
+    const bool in_int = e < a.n_interior || nb < a.n_interior;
+    if ((a.pass == 1 && !in_int) || (a.pass == 2 && in_int)) return false;
+    two_sided = true;
+  } else {
+    const bool e_int = e < a.n_interior;
+    if ((a.pass == 1 && !e_int) || (a.pass == 2 && e_int)) return false;
+    two_sided = false;
+  }
+  return true;
+}
 
 template <int N>
 __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   constexpr int npad = Cfg<N>::npad, f = N * N, HC = 55;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)(a.elem_end - a.elem_begin) * 6 * f;
+  const long long total = (long long)a.nelem * 6 * f;
   if (idx >= total) return;
   const int q = (int)(idx % f);
   const int d = (int)((idx / f) % 6);
-  const int e = a.elem_begin + (int)(idx / (6 * f));
+  const int e = (int)(idx / (6 * f));
   const int qa = q % N, qb = q / N;
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
+  const int nb = a.nbr[e * 6 + d];
+  bool two_sided;
+  if (!face_task(a, e, d, nb, two_sided)) return;
   // pair-major layout [e][pair s][direction][5][f]: the volume kernel stages
   // one pair block per TMA copy
   double* __restrict__ corr = a.corr + (size_t)e * 10 * 30 * f + (size_t)d * 5 * f + q;
-  const int nb = a.nbr[e * 6 + d];
+  double* __restrict__ corr_nb =
+      two_sided ? a.corr + (size_t)nb * 10 * 30 * f + (size_t)(d ^ 1) * 5 * f + q : nullptr;
   if (nb == -1) {
 #pragma unroll 1
     for (int s = 0; s < 10; ++s)
@@ -838,6 +866,7 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
     gh_face_side(g, unn_e, g1e, g2e, se);
   }
   const double lift = -0.5 * (double)(N * (N - 1)) * si.mag;
+  const double lift_nb = -0.5 * (double)(N * (N - 1)) * se.mag;
 #pragma unroll 2
   for (int s = 0; s < 10; ++s) {
     double phi_i[3], phi_e[3];
@@ -858,6 +887,15 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
     cs[(size_t)f] = cp * lift;
 #pragma unroll
     for (int m = 0; m < 3; ++m) cs[(size_t)(2 + m) * f] = cph[m] * lift;
+    if (two_sided) {
+      // the neighbour's correction from the same packaged data, roles swapped
+      gh_pair_boundary_terms(se, si, ke, ki, cg, cp, cph);
+      double* cn = corr_nb + (size_t)s * 30 * f;
+      cn[0] = cg * lift_nb;
+      cn[(size_t)f] = cp * lift_nb;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) cn[(size_t)(2 + m) * f] = cph[m] * lift_nb;
+    }
   }
 }
 
@@ -865,16 +903,18 @@ template <int N>
 __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   constexpr int npad = Cfg<N>::npad, f = N * N, HC = 9;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)(a.elem_end - a.elem_begin) * 6 * f;
+  const long long total = (long long)a.nelem * 6 * f;
   if (idx >= total) return;
   const int q = (int)(idx % f);
   const int d = (int)((idx / f) % 6);
-  const int e = a.elem_begin + (int)(idx / (6 * f));
+  const int e = (int)(idx / (6 * f));
   const int qa = q % N, qb = q / N;
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
-  double* __restrict__ corr = a.corr + ((size_t)e * 6 + d) * 5 * f + q;
   const int nb = a.nbr[e * 6 + d];
+  bool two_sided;
+  if (!face_task(a, e, d, nb, two_sided)) return;
+  double* __restrict__ corr = a.corr + ((size_t)e * 6 + d) * 5 * f + q;
   if (nb == -1) {
 #pragma unroll
     for (int c = 0; c < 5; ++c) corr[(size_t)c * f] = 0.0;
@@ -923,6 +963,13 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   const double lift = -0.5 * (double)(N * (N - 1)) * mi;
 #pragma unroll
   for (int c = 0; c < 5; ++c) corr[(size_t)c * f] = c5[c] * lift;
+  if (two_sided) {
+    double* __restrict__ corr_nb = a.corr + ((size_t)nb * 6 + (d ^ 1)) * 5 * f + q;
+    sw_face_correction(ue, g2e, ne, ui, g2i, ni, c5);
+    const double lift_nb = -0.5 * (double)(N * (N - 1)) * me;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) corr_nb[(size_t)c * f] = c5[c] * lift_nb;
+  }
 }
 
 // --------------------------------------------------------------------------

@@ -123,6 +123,7 @@ class Evolution:
         if problem.system == lib.SYSTEM_GH and gauge != lib.GAUGE_HARMONIC:
             ctx.set_gauge(gauge, gauge_params)
         ctx.set_state(problem.u0(ids, t0))
+        ctx.set_interior_count(self.part.n_interior)
         ctx.set_stepper(stepper, order, t0, dt)
         self.n_points = self.part.n_local * problem.N ** 3
         self._pg = process_group
@@ -147,6 +148,8 @@ class Evolution:
         ctx = self.ctx
         t = ctx.begin_substep()
         if self.world == 1:
+            ctx.compute_time_derivative_range(t, 0, self.part.n_local)
+        elif self.part.n_ghost == 0:
             ctx.compute_time_derivative_range(t, 0, self.part.n_local)
         else:
             torch, dist = self._torch, self._dist

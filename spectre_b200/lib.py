@@ -239,6 +239,9 @@ class Context:
         _check(self._lib.dgrhs_compute_time_derivative_range(self._h, ctypes.c_double(time),
                                                              begin, end))
 
+    def set_interior_count(self, n_interior):
+        _check(self._lib.dgrhs_set_interior_count(self._h, int(n_interior)))
+
     def set_halo_map(self, ghost_send_map):
         m = np.ascontiguousarray(ghost_send_map, dtype=np.int32)
         assert m.shape == (self.n_ghost_faces, 2)

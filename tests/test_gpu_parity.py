@@ -263,6 +263,7 @@ def test_partitioned_evolution_matches_single_context(system, world):
         ctx.set_static_fields(problem.static(ids))
         ctx.set_state(problem.u0(ids, 0.0))
         ctx.set_halo_map(part.send_map)
+        ctx.set_interior_count(part.n_interior)
         ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 3, 0.0, dt)
         ctxs.append(ctx)
     per_face = ctxs[0].halo_comps * f
