@@ -98,6 +98,11 @@ int dgrhs_set_gauge(dgrhs_ctx* ctx, int gauge, const double* params, int nparams
  * [n_elements][16][n] with d_a H_b at component a + 4*b (tnsr::ab). */
 int dgrhs_set_gauge_fields(dgrhs_ctx* ctx, const double* gauge_h,
                            const double* d4_gauge_h);
+/* AnalyticChristoffel gauge for a STATIC analytic solution (AnalyticChristoffel
+ * .cpp:64-149): u_analytic host [n_elements][50][n] = the solution's (g, Pi,
+ * Phi); H_a = -Gamma_a and its numerical spatial derivative are evaluated once
+ * on the device and kept as gauge fields (d_t H_a = 0).  Needs set_geometry. */
+int dgrhs_set_gauge_analytic_christoffel(dgrhs_ctx* ctx, const double* u_analytic);
 
 /* Evolved variables, host [n_elements][n_vars][n] (Variables layout). */
 int dgrhs_set_state(dgrhs_ctx* ctx, const double* u);
@@ -123,11 +128,24 @@ int dgrhs_pack_halo(dgrhs_ctx* ctx);
 int dgrhs_compute_time_derivative_range(dgrhs_ctx* ctx, double time,
                                         int elem_begin, int elem_end);
 /* Device pointers of the halo buffers: send[n_ghost_faces][halo_comps][N^2]
- * and recv (same shape); ghost_send_map host [n_ghost_faces][2] = {local
- * element, direction} whose face is packed into slot i.  Static neighbour-side
+ * and recv (same shape); ghost_send_map host [n_send][2] = {local element,
+ * direction} whose face is packed into send slot i (n_send <= n_ghost_faces;
+ * receive slots beyond the exchanged ones hold boundary-condition data).  Static neighbour-side
  * face data (inverse-Jacobian row, gamma1, gamma2) travel in the same slots, so
  * one exchange per RHS suffices. */
-int dgrhs_set_halo_map(dgrhs_ctx* ctx, const int32_t* ghost_send_map);
+int dgrhs_set_halo_map(dgrhs_ctx* ctx, const int32_t* ghost_send_map, int n_send);
+/* External boundaries with a ghost boundary condition (SURVEY 8f rank 1:
+ * apply_boundary_conditions_on_all_external_faces, BoundaryConditionsImpl.hpp:
+ * 672-764, with BoundaryCondition::dg_ghost such as GeneralizedHarmonic/
+ * BoundaryConditions/DirichletAnalytic.cpp:58-117): the face is given a ghost
+ * slot (neighbors entry <= -2) that the exchange never overwrites, and the
+ * caller supplies the exterior state once (static solutions) or per step:
+ * data host [n_slots][halo_comps][N^2] = exterior evolved variables | the
+ * interior element's inverse-Jacobian row of that face (3) | interior gamma1,
+ * gamma2 (GH) or gamma2 (ScalarWave).  The kernel then normalises minus the
+ * interior normal with the exterior metric exactly like :545-560. */
+int dgrhs_set_boundary_ghost_data(dgrhs_ctx* ctx, int slot_begin, int n_slots,
+                                  const double* data);
 void* dgrhs_halo_send_ptr(dgrhs_ctx* ctx);
 void* dgrhs_halo_recv_ptr(dgrhs_ctx* ctx);
 int dgrhs_halo_comps(dgrhs_ctx* ctx);

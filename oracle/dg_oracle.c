@@ -839,10 +839,33 @@ static int face_index(int N, int d, int a, int b) {
   }
 }
 
+/*
+ * External boundaries with a ghost boundary condition (DirichletAnalytic):
+ * nbr <= -2 selects slot -(nbr+2) of ext_u [nslots][C][f], the exterior
+ * evolved variables returned by BoundaryCondition::dg_ghost
+ * (GeneralizedHarmonic/BoundaryConditions/DirichletAnalytic.cpp:58-117).
+ * Following BoundaryConditionsImpl.hpp:427-560: gamma1/gamma2 are copied from
+ * the interior, lapse/shift/inverse spatial metric come from the exterior
+ * metric, and the exterior normal is minus the interior UNIT normal covector
+ * re-normalised with the exterior inverse spatial metric.
+ */
+void orc_dg_rhs_bc(int system, int N, int nelem, const double* D, const double* u,
+                   const double* invjac, const double* static_fields,
+                   const double* coords, const int* nbr,
+                   const double* gauge_params, const double* ext_u, double* dt_u);
+
 void orc_dg_rhs(int system, int N, int nelem, const double* D, const double* u,
                 const double* invjac, const double* static_fields,
                 const double* coords, const int* nbr,
                 const double* gauge_params, double* dt_u) {
+  orc_dg_rhs_bc(system, N, nelem, D, u, invjac, static_fields, coords, nbr, gauge_params,
+                NULL, dt_u);
+}
+
+void orc_dg_rhs_bc(int system, int N, int nelem, const double* D, const double* u,
+                   const double* invjac, const double* static_fields,
+                   const double* coords, const int* nbr,
+                   const double* gauge_params, const double* ext_u, double* dt_u) {
   const int n = N * N * N, f = N * N;
   const int C = system == 0 ? 5 : 50;
   const int PK = system == 0 ? 16 : 134;
@@ -908,19 +931,51 @@ void orc_dg_rhs(int system, int N, int nelem, const double* D, const double* u,
       double* dte = dt_u + (size_t)e * C * n;
       for (int d = 0; d < 6; ++d) {
         const int ne = nbr[e * 6 + d];
-        if (ne < 0) continue;
+        if (ne == -1 || (ne < -1 && ext_u == NULL)) continue;
         const int dn = d ^ 1; /* neighbour's face pointing back at us */
         const double* pki = pk_all + ((size_t)e * 6 + d) * PK * f;
-        const double* pke = pk_all + ((size_t)ne * 6 + dn) * PK * f;
+        const double* pke = ne >= 0 ? pk_all + ((size_t)ne * 6 + dn) * PK * f : NULL;
         const double* mag = mag_all + ((size_t)e * 6 + d) * f;
+        const double* ue = u + (size_t)e * C * n;
+        const double* je = invjac + (size_t)e * 9 * n;
+        const double* se = static_fields + (size_t)e * nstatic * n;
         for (int b = 0; b < N; ++b)
           for (int a = 0; a < N; ++a) {
             const int q = a + N * b;
             const int p = face_index(N, d, a, b);
             double in[134], ex[134], corr[50];
-            for (int c = 0; c < PK; ++c) {
-              in[c] = pki[(size_t)c * f + q];
-              ex[c] = pke[(size_t)c * f + q];
+            for (int c = 0; c < PK; ++c) in[c] = pki[(size_t)c * f + q];
+            if (ne >= 0) {
+              for (int c = 0; c < PK; ++c) ex[c] = pke[(size_t)c * f + q];
+            } else {
+              /* ghost boundary condition: package the exterior state */
+              const double* xu = ext_u + (size_t)(-(ne + 2)) * C * f;
+              double uex[50], unnorm[3], n_lo_i[3], n_up_i[3], mag_i, neg[3], n_lo[3],
+                  n_up[3], mag_e;
+              const int dim = d / 2;
+              const double sign = (d % 2) ? 1.0 : -1.0;
+              for (int c = 0; c < C; ++c) uex[c] = xu[(size_t)c * f + q];
+              for (int i = 0; i < 3; ++i) unnorm[i] = sign * je[(size_t)(dim + 3 * i) * n + p];
+              if (system == 0) {
+                face_normal(unnorm, 0, NULL, n_lo_i, n_up_i, &mag_i);
+                for (int i = 0; i < 3; ++i) n_lo[i] = -n_lo_i[i];
+                sw_package_point(uex, se[p], n_lo, ex);
+              } else {
+                double g[4][4], gi[4][4];
+                GhGeom qe, qi;
+                for (int a4 = 0; a4 < 4; ++a4)
+                  for (int b4 = 0; b4 < 4; ++b4) {
+                    g[a4][b4] = uex[SYM4(a4, b4)];
+                    gi[a4][b4] = ue[(size_t)SYM4(a4, b4) * n + p];
+                  }
+                gh_geometry(gi, &qi);
+                face_normal(unnorm, 1, qi.inv_gamma, n_lo_i, n_up_i, &mag_i);
+                gh_geometry(g, &qe);
+                for (int i = 0; i < 3; ++i) neg[i] = -n_lo_i[i];
+                face_normal(neg, 1, qe.inv_gamma, n_lo, n_up, &mag_e);
+                gh_package_point(uex, se[n + p], se[2 * n + p], qe.lapse, qe.shift, n_lo, n_up,
+                                 ex);
+              }
             }
             if (system == 0)
               sw_boundary_terms_point(in, ex, corr);

@@ -416,8 +416,9 @@ def gh_geometry(u):
 
 
 def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC, coords=None,
-           volume_only=False):
-    """u [nelem, C, n]; returns dt_u of the same shape."""
+           volume_only=False, ext_u=None):
+    """u [nelem, C, n]; returns dt_u of the same shape.  ext_u [nslots, C, f]:
+    exterior states of ghost boundary conditions (nbr <= -2 -> slot -(nbr+2))."""
     nelem = u.shape[0]
     D = _c(differentiation_matrix(N))
     u, invjac, static_fields = _c(u), _c(invjac), _c(static_fields)
@@ -429,8 +430,9 @@ def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC
         lib().orc_dg_volume(system, N, nelem, _p(D), _p(u), _p(invjac), _p(static_fields),
                             _p(coords), _p(gp), _p(dt))
     else:
-        lib().orc_dg_rhs(system, N, nelem, _p(D), _p(u), _p(invjac), _p(static_fields),
-                         _p(coords), _p(nbr), _p(gp), _p(dt))
+        ext = _c(ext_u) if ext_u is not None else None
+        lib().orc_dg_rhs_bc(system, N, nelem, _p(D), _p(u), _p(invjac), _p(static_fields),
+                            _p(coords), _p(nbr), _p(gp), _p(ext), _p(dt))
     return dt
 
 

@@ -212,6 +212,7 @@ struct dgrhs_ctx {
   int system = 0, N = 0, nelem = 0, nghost = 0, device = 0;
   int C = 0, S = 0, HC = 0, n = 0, npad = 0, f = 0;
   int n_interior = -1;
+  int n_send = 0;  // faces packed for other ranks (0: no exchange needed)
   cudaStream_t stream = nullptr;
   double *u = nullptr, *invjac = nullptr, *coords = nullptr, *stat = nullptr;
   double *corr = nullptr, *D = nullptr, *gH = nullptr, *gdH = nullptr;
@@ -386,9 +387,9 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
 
 template <int N>
 int launch_pack(dgrhs_ctx* c) {
-  if (c->nghost == 0) return 0;
-  dg::PackArgs a{c->u, c->invjac, c->stat, c->halo_map, c->halo_send, c->nghost};
-  const long long total = (long long)c->nghost * N * N;
+  if (c->n_send == 0) return 0;
+  dg::PackArgs a{c->u, c->invjac, c->stat, c->halo_map, c->halo_send, c->n_send};
+  const long long total = (long long)c->n_send * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)
     dg::pack_halo_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(a);
@@ -639,6 +640,36 @@ int dgrhs_set_gauge(dgrhs_ctx* c, int gauge, const double* params, int nparams) 
   return 0;
 }
 
+int dgrhs_set_gauge_analytic_christoffel(dgrhs_ctx* c, const double* u_analytic) {
+  CHECK_CTX(c);
+  if (c->system != DGRHS_SYSTEM_GH) return fail("gauge conditions only apply to GH");
+  CU(cudaSetDevice(c->device));
+  if (dgrhs_set_gauge(c, DGRHS_GAUGE_FIELDS, nullptr, 0)) return 1;
+  double* tmp = nullptr;
+  if (dev_alloc(&tmp, c->state_len())) return 1;
+  if (upload(c, tmp, u_analytic, c->C)) return 1;
+  dg::GaugeFromStateArgs g{tmp, c->gH, c->nelem};
+  const long long total = (long long)c->nelem * c->n;
+  int rc = 0;
+  switch (c->N) {
+#define X(NN)                                                                             \
+  case NN: {                                                                              \
+    dg::gauge_h_from_state_kernel<NN><<<(int)((total + 255) / 256), 256, 0, c->stream>>>(g); \
+    dg::DerivArgs d{c->gH, c->invjac, c->gdH, c->D, 4, 16, 1, 4};                         \
+    dg::partial_derivatives_kernel<NN><<<c->nelem * 4, 256, 0, c->stream>>>(d);           \
+  } break;
+    DG_FOR_EACH_N(X)
+#undef X
+    default:
+      rc = 1;
+  }
+  g_launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(tmp);
+  return rc ? fail("unsupported N") : 0;
+}
+
 int dgrhs_set_gauge_fields(dgrhs_ctx* c, const double* H, const double* dH) {
   CHECK_CTX(c);
   if (c->gauge != DGRHS_GAUGE_FIELDS) return fail("gauge is not DGRHS_GAUGE_FIELDS");
@@ -666,8 +697,9 @@ int dgrhs_get_time_derivative(dgrhs_ctx* c, double* dt_u) {
 int dgrhs_compute_time_derivative(dgrhs_ctx* c, double time, int volume_only) {
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));
-  if (c->nghost > 0 && !volume_only)
-    return fail("context has ghost faces: use pack_halo + compute_time_derivative_range");
+  if (c->n_send > 0 && !volume_only)
+    return fail("context exchanges faces with other ranks: use pack_halo + "
+                "compute_time_derivative_range");
   ++c->rhs_evals;
   return rhs_range(c, time, c->dt_last, 0, c->nelem, volume_only != 0, true);
 }
@@ -679,14 +711,29 @@ int dgrhs_set_interior_count(dgrhs_ctx* c, int n_interior) {
   return 0;
 }
 
-int dgrhs_set_halo_map(dgrhs_ctx* c, const int32_t* map) {
+int dgrhs_set_halo_map(dgrhs_ctx* c, const int32_t* map, int n_send) {
   CHECK_CTX(c);
-  if (c->nghost == 0) return 0;
+  if (n_send < 0 || n_send > c->nghost) return fail("n_send must be in [0, n_ghost_faces]");
+  c->n_send = n_send;
+  if (n_send == 0) return 0;
   CU(cudaSetDevice(c->device));
-  for (int i = 0; i < c->nghost; ++i)
+  for (int i = 0; i < n_send; ++i)
     if (map[2 * i] < 0 || map[2 * i] >= c->nelem || map[2 * i + 1] < 0 || map[2 * i + 1] > 5)
       return fail("bad halo map entry %d", i);
-  CU(cudaMemcpy(c->halo_map, map, (size_t)c->nghost * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->halo_map, map, (size_t)n_send * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dgrhs_set_boundary_ghost_data(dgrhs_ctx* c, int slot_begin, int n_slots,
+                                  const double* data) {
+  CHECK_CTX(c);
+  if (slot_begin < 0 || n_slots < 0 || slot_begin + n_slots > c->nghost)
+    return fail("ghost slots [%d, %d) out of range", slot_begin, slot_begin + n_slots);
+  if (n_slots == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  const size_t per = (size_t)c->HC * c->f;
+  CU(cudaMemcpy(c->halo_recv + (size_t)slot_begin * per, data, (size_t)n_slots * per * 8,
+                cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -877,7 +924,8 @@ int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
 
 int dgrhs_take_steps(dgrhs_ctx* c, int n_steps) {
   CHECK_CTX(c);
-  if (c->nghost > 0) return fail("context has ghost faces: drive substeps from the caller");
+  if (c->n_send > 0)
+    return fail("context exchanges faces with other ranks: drive substeps from the caller");
   for (int s = 0; s < n_steps;) {
     double t;
     int done = 0;

@@ -1194,6 +1194,35 @@ __global__ void __launch_bounds__(256) gh_constraints_kernel(ConstraintArgs a) {
 // GaugeWave.hpp:34-50).  The spatial derivative is then taken numerically by
 // partial_derivatives_kernel (:136-143), d_t H_a = 0 (:145-147).
 // --------------------------------------------------------------------------
+// AnalyticChristoffel for a static analytic solution (AnalyticChristoffel.cpp:
+// 76-147): H_a = -Gamma_a of the analytic (g, Pi, Phi); the spatial derivative
+// is then taken by partial_derivatives_kernel, d_t H_a = 0.
+struct GaugeFromStateArgs {
+  const double* u;  // analytic state [E][50][npad]
+  double* gH;       // [E][4][npad]
+  int nelem;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) gauge_h_from_state_kernel(GaugeFromStateArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.nelem * n) return;
+  const int e = (int)(idx / n), p = (int)(idx % n);
+  const double* ue = a.u + (size_t)e * 50 * npad + p;
+  double g[10], pi[10], phi[3][10], Gam[4];
+#pragma unroll
+  for (int s = 0; s < 10; ++s) {
+    g[s] = ue[(size_t)s * npad];
+    pi[s] = ue[(size_t)(10 + s) * npad];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) phi[m][s] = ue[(size_t)(20 + m + 3 * s) * npad];
+  }
+  gh_trace_christoffel(g, pi, phi, Gam);
+#pragma unroll
+  for (int x = 0; x < 4; ++x) a.gH[((size_t)e * 4 + x) * npad + p] = -Gam[x];
+}
+
 struct GaugeWaveArgs {
   const double* coords;  // [E][3][npad]
   double* gH;            // [E][4][npad]

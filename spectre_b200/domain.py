@@ -127,7 +127,11 @@ class Partition:
     (local element, direction) list; the sender packs in the same order.
     """
 
-    def __init__(self, neighbors: np.ndarray, world: int, rank: int):
+    def __init__(self, neighbors: np.ndarray, world: int, rank: int,
+                 boundary_slots: bool = False):
+        """boundary_slots: give every external face (neighbour -1) of a local
+        element a ghost slot after the exchanged ones, to be filled with the
+        exterior state of a ghost boundary condition (DirichletAnalytic)."""
         ne = neighbors.shape[0]
         bounds = [(ne * r) // world for r in range(world + 1)]
         owner = np.zeros(ne, dtype=np.int64)
@@ -162,7 +166,16 @@ class Partition:
         for slot, (peer, v, dn, le, d) in enumerate(recv):
             local_nb[le, d] = -(slot + 2)
             self.recv_counts[peer] += 1
-        self.n_ghost = len(recv)
+        self.n_recv = len(recv)
+        self.external_faces = []  # (local element, direction, slot)
+        if boundary_slots:
+            for le, g in enumerate(order):
+                for d in range(6):
+                    if int(neighbors[g, d]) == -1:
+                        slot = self.n_recv + len(self.external_faces)
+                        self.external_faces.append((le, d, slot))
+                        local_nb[le, d] = -(slot + 2)
+        self.n_ghost = self.n_recv + len(self.external_faces)
         self.local_neighbors = local_nb
         # send list: my faces that some peer needs = faces of my elements whose
         # neighbour is remote; ordered by (peer, my global element, my direction)

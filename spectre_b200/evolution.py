@@ -66,9 +66,17 @@ class Problem:
     """A BASELINE.json configuration; per-element data are built on demand for
     the element subset a rank owns (global arrays would not fit at 8 GPUs)."""
 
-    def __init__(self, system, brick, initial_data, static_values):
+    def __init__(self, system, brick, initial_data, static_values, dirichlet_analytic=False,
+                 analytic_christoffel_gauge=False):
+        """static_values: one number or one callable(x) -> array per static field.
+        dirichlet_analytic: external faces get the analytic solution as exterior
+        state (DirichletAnalytic ghost boundary condition).
+        analytic_christoffel_gauge: AnalyticChristoffel gauge of the (static)
+        analytic solution instead of the harmonic gauge."""
         self.system, self.brick, self.N = system, brick, brick.N
         self._initial_data, self._static_values = initial_data, static_values
+        self.dirichlet_analytic = dirichlet_analytic
+        self.analytic_christoffel_gauge = analytic_christoffel_gauge
         self.neighbors = brick.neighbors()
 
     def coords(self, ids=None):
@@ -83,8 +91,13 @@ class Problem:
     def static(self, ids=None):
         ne = self.brick.n_elements if ids is None else len(ids)
         out = np.empty((ne, len(self._static_values), self.brick.n))
+        x = None
         for i, v in enumerate(self._static_values):
-            out[:, i] = v
+            if callable(v):
+                x = self.coords(ids) if x is None else x
+                out[:, i] = v(x)
+            else:
+                out[:, i] = v
         return out
 
 
@@ -95,6 +108,22 @@ def gh_gauge_wave_problem(refinement, N, lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0,
     brick = domain.Brick(lower, upper, refinement, N)
     return Problem(lib.SYSTEM_GH, brick,
                    lambda x, t: analytic.gauge_wave(x, t, amplitude, wavelength), gammas)
+
+
+def gh_kerr_schild_problem(refinement, N, lower=(2.0, 2.0, 2.0), upper=(4.0, 4.0, 4.0),
+                           mass=1.0):
+    """Kerr-Schild black hole (M = 1, a = 0; KerrSchild.yaml:73-78) on a Brick
+    that does not contain the singularity, DirichletAnalytic on all external
+    faces, AnalyticChristoffel gauge, GaussianPlusConstant damping functions of
+    KerrSchild.yaml:108-125 -- the Brick-lattice stand-in for BASELINE.json
+    configs[2]/[3] (the Sphere domain with wedges is not built yet)."""
+    brick = domain.Brick(lower, upper, refinement, N, periodic=(False, False, False))
+    w = 11.313708499
+    gam = (lambda x: analytic.gaussian_plus_constant(x, 0.001, 3.0, w),
+           -1.0,
+           lambda x: analytic.gaussian_plus_constant(x, 0.001, 1.0, w))
+    return Problem(lib.SYSTEM_GH, brick, lambda x, t: analytic.kerr_schild(x, mass), gam,
+                   dirichlet_analytic=True, analytic_christoffel_gauge=True)
 
 
 def scalar_wave_problem(refinement, N):
@@ -112,7 +141,8 @@ class Evolution:
                  t0=0.0, gauge=lib.GAUGE_HARMONIC, gauge_params=(), device=0, world=1, rank=0,
                  process_group=None):
         self.world, self.rank = world, rank
-        self.part = domain.Partition(problem.neighbors, world, rank)
+        self.part = domain.Partition(problem.neighbors, world, rank,
+                                     boundary_slots=problem.dirichlet_analytic)
         ids = self.part.global_ids
         self.ctx = lib.Context(problem.system, problem.N, self.part.n_local,
                                self.part.n_ghost, device)
@@ -120,9 +150,13 @@ class Evolution:
         ctx.set_geometry(problem.inverse_jacobian(ids), problem.coords(ids),
                          self.part.local_neighbors)
         ctx.set_static_fields(problem.static(ids))
-        if problem.system == lib.SYSTEM_GH and gauge != lib.GAUGE_HARMONIC:
+        if problem.system == lib.SYSTEM_GH and problem.analytic_christoffel_gauge:
+            ctx.set_gauge_analytic_christoffel(problem.u0(ids, t0))
+        elif problem.system == lib.SYSTEM_GH and gauge != lib.GAUGE_HARMONIC:
             ctx.set_gauge(gauge, gauge_params)
         ctx.set_state(problem.u0(ids, t0))
+        if self.part.external_faces:
+            ctx.set_boundary_ghost_data(self.part.n_recv, self.boundary_ghost_data(problem, t0))
         ctx.set_interior_count(self.part.n_interior)
         ctx.set_stepper(stepper, order, t0, dt)
         self.n_points = self.part.n_local * problem.N ** 3
@@ -135,13 +169,40 @@ class Evolution:
             f = problem.N ** 2
             per_face = ctx.halo_comps * f
             self._send = torch.as_tensor(
-                _CudaArray(ctx.halo_send_ptr(), self.part.n_ghost * per_face),
+                _CudaArray(ctx.halo_send_ptr(), max(self.part.n_ghost, 1) * per_face),
                 device=f"cuda:{device}")
             self._recv = torch.as_tensor(
-                _CudaArray(ctx.halo_recv_ptr(), self.part.n_ghost * per_face),
+                _CudaArray(ctx.halo_recv_ptr(), max(self.part.n_ghost, 1) * per_face),
                 device=f"cuda:{device}")
             self._stream = torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{device}")
             self._halo = HaloExchange(self.part, per_face, dist, process_group)
+
+    def boundary_ghost_data(self, problem, t):
+        """[n_external][halo_comps][N^2]: exterior state = analytic solution on the
+        face, then the interior element's inverse-Jacobian row and gammas."""
+        N, f = problem.N, problem.N ** 2
+        C = 50 if problem.system == lib.SYSTEM_GH else 5
+        hc = self.ctx.halo_comps
+        ids = self.part.global_ids
+        out = np.zeros((len(self.part.external_faces), hc, f))
+        q = np.arange(f)
+        a, b = q % N, q // N
+        elems = sorted({le for le, _, _ in self.part.external_faces})
+        x = dict(zip(elems, problem.coords(ids[elems])))
+        J = dict(zip(elems, problem.inverse_jacobian(ids[elems])))
+        S = dict(zip(elems, problem.static(ids[elems])))
+        for k, (le, d, slot) in enumerate(self.part.external_faces):
+            dim, fixed = d // 2, (N - 1 if d % 2 else 0)
+            p = [fixed + N * (a + N * b), a + N * (fixed + N * b), a + N * (b + N * fixed)][dim]
+            out[k, :C] = problem._initial_data(x[le][:, p], t)
+            for i in range(3):
+                out[k, C + i] = J[le][dim + 3 * i, p]
+            if problem.system == lib.SYSTEM_GH:
+                out[k, C + 3] = S[le][1, p]
+                out[k, C + 4] = S[le][2, p]
+            else:
+                out[k, C + 3] = S[le][0, p]
+        return out
 
     # -- one RHS + update ------------------------------------------------
     def _substep(self) -> bool:
@@ -149,7 +210,7 @@ class Evolution:
         t = ctx.begin_substep()
         if self.world == 1:
             ctx.compute_time_derivative_range(t, 0, self.part.n_local)
-        elif self.part.n_ghost == 0:
+        elif self.part.n_recv == 0:
             ctx.compute_time_derivative_range(t, 0, self.part.n_local)
         else:
             torch, dist = self._torch, self._dist

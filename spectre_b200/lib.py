@@ -20,7 +20,8 @@ STEPPER_ADAMS_BASHFORTH, STEPPER_RK3_HESTHAVEN = 0, 1
 EXPORTS = [
     "dgrhs_last_error", "dgrhs_kernel_launch_count", "dgrhs_create", "dgrhs_destroy",
     "dgrhs_set_geometry", "dgrhs_set_static_fields", "dgrhs_set_gauge",
-    "dgrhs_set_gauge_fields", "dgrhs_set_state", "dgrhs_get_state",
+    "dgrhs_set_gauge_fields", "dgrhs_set_gauge_analytic_christoffel",
+    "dgrhs_set_boundary_ghost_data", "dgrhs_set_state", "dgrhs_get_state",
     "dgrhs_get_time_derivative", "dgrhs_compute_time_derivative", "dgrhs_set_interior_count",
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
@@ -243,9 +244,18 @@ class Context:
         _check(self._lib.dgrhs_set_interior_count(self._h, int(n_interior)))
 
     def set_halo_map(self, ghost_send_map):
-        m = np.ascontiguousarray(ghost_send_map, dtype=np.int32)
-        assert m.shape == (self.n_ghost_faces, 2)
-        _check(self._lib.dgrhs_set_halo_map(self._h, _ptr(m)))
+        m = np.ascontiguousarray(ghost_send_map, dtype=np.int32).reshape(-1, 2)
+        _check(self._lib.dgrhs_set_halo_map(self._h, _ptr(m) if len(m) else None, len(m)))
+
+    def set_boundary_ghost_data(self, slot_begin, data):
+        d = _f64(data)
+        assert d.shape[1:] == (self.halo_comps, self.N ** 2), d.shape
+        _check(self._lib.dgrhs_set_boundary_ghost_data(self._h, slot_begin, d.shape[0], _ptr(d)))
+
+    def set_gauge_analytic_christoffel(self, u_analytic):
+        u = _f64(u_analytic)
+        assert u.shape == (self.n_elements, 50, self.n)
+        _check(self._lib.dgrhs_set_gauge_analytic_christoffel(self._h, _ptr(u)))
 
     def pack_halo(self):
         _check(self._lib.dgrhs_pack_halo(self._h))
