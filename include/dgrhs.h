@@ -174,6 +174,16 @@ int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
  * end_substep (so dgrhs_state_device_ptr changes from step to step).
  * enable = 0 selects the separate update kernel (bit-identical results). */
 int dgrhs_set_fused_update(dgrhs_ctx* ctx, int enable);
+/* dg::Actions::Filter<Filters::Exponential<0>> after UpdateU (ParallelAlgorithms/
+ * Actions/FilterAction.hpp, NumericalAlgorithms/LinearOperators/
+ * ExponentialFilter.cpp:45-76; KerrSchild.yaml:127-132 uses Alpha 36, HalfPower
+ * 64): every evolved component of every element is multiplied by the filter
+ * matrix along xi, eta, zeta after each substep update.  Disabled by default. */
+int dgrhs_set_exponential_filter(dgrhs_ctx* ctx, int enable, double alpha, int half_power);
+/* Spectral::filtering::exponential_filter(Mesh<1>{N, Legendre, GaussLobatto},
+ * alpha, half_power) (Spectral/Filtering.cpp:20-32), row-major [N*N]. */
+int dgrhs_exponential_filter_matrix(int n_points_1d, double alpha, int half_power,
+                                    double* matrix);
 /* GH volume work as two kernels (pointwise context kernel + high-occupancy
  * streaming kernel at 16 warps/SM; opt-in, N <= 10) instead of the single
  * fused kernel (default).  Results agree to rounding.  Measured on B200

@@ -138,6 +138,32 @@ def differentiation_matrix(num_points: int):
     return D
 
 
+def exponential_filter_matrix(num_points: int, alpha: float, half_power: int):
+    """Spectral::filtering::exponential_filter (Spectral/Filtering.cpp:20-32):
+    V diag(exp(-alpha (i/(N-1))^(2 half_power))) V^-1 with the Legendre
+    Vandermonde matrix at the LGL points (Spectral.cpp:498-523; the inverse is
+    numerical there too)."""
+    x, _ = lgl_points_and_weights(num_points)
+    V = np.zeros((num_points, num_points))
+    for j in range(num_points):
+        c = np.zeros(j + 1)
+        c[j] = 1.0
+        V[:, j] = np.polynomial.legendre.legval(x, c)
+    order = num_points - 1.0
+    lam = np.exp(-alpha * (np.arange(num_points) / order) ** (2 * half_power))
+    return V @ np.diag(lam) @ np.linalg.inv(V)
+
+
+def apply_filter(N, u, F):
+    """apply_matrices(u, {F, F, F}) on every component: u [..., n]."""
+    shp = u.shape
+    v = u.reshape(-1, N, N, N)  # [.., k, j, i]
+    v = np.einsum("im,...kjm->...kji", F, v)
+    v = np.einsum("jm,...kmi->...kji", F, v)
+    v = np.einsum("km,...mji->...kji", F, v)
+    return v.reshape(shp)
+
+
 # ---------------------------------------------------------------------------
 # Adams-Bashforth coefficients: Time/TimeSteppers/AdamsCoefficients.cpp:13-42
 # (constant-step table), :75-117 (variable_coefficients), AdamsCoefficients.hpp
@@ -478,8 +504,10 @@ def analytic_christoffel_gauge(N, u_analytic, invjac):
 # Times are exact Fractions of the step (the reference uses rational Time).
 # ---------------------------------------------------------------------------
 class Evolution:
-    def __init__(self, rhs, u0, t0, dt, stepper="AB3"):
-        """rhs(u, t) -> dt_u.  stepper: 'AB<k>' or 'RK3' (Rk3HesthavenSsp)."""
+    def __init__(self, rhs, u0, t0, dt, stepper="AB3", post_update=None):
+        """rhs(u, t) -> dt_u.  stepper: 'AB<k>' or 'RK3' (Rk3HesthavenSsp).
+        post_update(u) -> u: action after UpdateU in step_actions (the filter)."""
+        self.post = post_update if post_update is not None else (lambda v: v)
         self.rhs = rhs
         self.u = u0.copy()
         self.t0 = t0
@@ -531,7 +559,7 @@ class Evolution:
                     # step_unused: UpdateU skipped, history order was bumped
                     self._clean(order + 1)
                     break
-                self.u = self._ab_update(order, t, t + h)
+                self.u = self.post(self._ab_update(order, t, t + h))
                 self._clean(order)
         self.u = u_init.copy()
 
@@ -541,19 +569,19 @@ class Evolution:
             k = self.order
             d = self._eval(n)
             self.history.append((n, self.u.copy(), d))
-            self.u = self._ab_update(k, n, n + 1)
+            self.u = self.post(self._ab_update(k, n, n + 1))
             self._clean(k)
         elif self.stepper == "RK3":
             dt = self.dt
             u0 = self.u.copy()
             f0 = self._eval(n)
-            self.u = u0 + dt * f0
+            self.u = self.post(u0 + dt * f0)
             f1 = self._eval(n + 1)
             u1 = self.u.copy()
-            self.u = 0.25 * (3.0 * u0 + u1 + dt * f1)
+            self.u = self.post(0.25 * (3.0 * u0 + u1 + dt * f1))
             f2 = self._eval(n + Fraction(1, 2))
             u2 = self.u.copy()
-            self.u = (1.0 / 3.0) * (u0 + 2.0 * u2 + 2.0 * dt * f2)
+            self.u = self.post((1.0 / 3.0) * (u0 + 2.0 * u2 + 2.0 * dt * f2))
         else:
             raise ValueError(self.stepper)
         self.step_index += 1

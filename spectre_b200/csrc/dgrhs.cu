@@ -133,6 +133,68 @@ void diff_matrix(int N, std::vector<double>& D) {
   }
 }
 
+// Exponential filter matrix V diag(exp(-alpha (i/(N-1))^(2 half_power))) V^-1
+// with the Legendre Vandermonde matrix V(i,j) = P_j(x_i) at the LGL points and
+// its numerical inverse (Spectral/Filtering.cpp:20-32, Spectral.cpp:498-523).
+void exponential_filter_matrix(int N, double alpha, unsigned half_power,
+                               std::vector<double>& F) {
+  std::vector<double> x, w;
+  lgl(N, x, w);
+  std::vector<double> V((size_t)N * N), Vi((size_t)N * N, 0.0), A;
+  for (int i = 0; i < N; ++i) {
+    double pm2 = 1.0, pm1 = x[i];
+    for (int j = 0; j < N; ++j) {
+      double pj;
+      if (j == 0) {
+        pj = 1.0;
+      } else if (j == 1) {
+        pj = x[i];
+      } else {
+        pj = ((2.0 * j - 1.0) * x[i] * pm1 - (j - 1.0) * pm2) / j;
+        pm2 = pm1;
+        pm1 = pj;
+      }
+      V[(size_t)i * N + j] = pj;
+    }
+  }
+  // Gauss-Jordan with partial pivoting
+  A = V;
+  for (int i = 0; i < N; ++i) Vi[(size_t)i * N + i] = 1.0;
+  for (int c = 0; c < N; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < N; ++r)
+      if (std::abs(A[(size_t)r * N + c]) > std::abs(A[(size_t)piv * N + c])) piv = r;
+    for (int k = 0; k < N; ++k) {
+      std::swap(A[(size_t)c * N + k], A[(size_t)piv * N + k]);
+      std::swap(Vi[(size_t)c * N + k], Vi[(size_t)piv * N + k]);
+    }
+    const double d = 1.0 / A[(size_t)c * N + c];
+    for (int k = 0; k < N; ++k) {
+      A[(size_t)c * N + k] *= d;
+      Vi[(size_t)c * N + k] *= d;
+    }
+    for (int r = 0; r < N; ++r) {
+      if (r == c) continue;
+      const double fct = A[(size_t)r * N + c];
+      if (fct == 0.0) continue;
+      for (int k = 0; k < N; ++k) {
+        A[(size_t)r * N + k] -= fct * A[(size_t)c * N + k];
+        Vi[(size_t)r * N + k] -= fct * Vi[(size_t)c * N + k];
+      }
+    }
+  }
+  F.assign((size_t)N * N, 0.0);
+  const double order = N - 1.0;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < N; ++k)
+        s += V[(size_t)i * N + k] * std::exp(-alpha * std::pow(k / order, 2.0 * half_power)) *
+             Vi[(size_t)k * N + j];
+      F[(size_t)i * N + j] = s;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Adams-Bashforth coefficients (AdamsCoefficients.cpp:13-42, :75-117)
 // ---------------------------------------------------------------------------
@@ -222,6 +284,7 @@ struct dgrhs_ctx {
   double* u0 = nullptr;           // saved value (self-start / RK step start)
   double* u_alt = nullptr;        // second state buffer for the fused update
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
+  double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
   bool split_volume = false;      // context + streaming kernels (opt-in, N <= 10)
   bool fuse_update = true;        // fuse UpdateU into the volume kernel
   dg::UpdateArgs pending_upd{};   // filled by begin_substep when fusing
@@ -434,6 +497,22 @@ int lincomb(dgrhs_ctx* c, double* u, double a, const std::vector<double>& coef,
   return 0;
 }
 
+int apply_filter(dgrhs_ctx* c) {
+  if (!c->filterF) return 0;
+  dg::FilterArgs a{c->u, c->filterF, c->C};
+  switch (c->N) {
+#define X(NN)                                                                              \
+  case NN:                                                                                 \
+    dg::exponential_filter_kernel<NN><<<c->nelem * c->C, 256, 0, c->stream>>>(a);          \
+    break;
+    DG_FOR_EACH_N(X)
+#undef X
+  }
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int ensure_slots(dgrhs_ctx* c, int count) {
   while ((int)c->dt_slots.size() < count) {
     double* p = nullptr;
@@ -578,7 +657,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (double* p : {c->u, c->invjac, c->coords, c->stat, c->corr, c->D, c->gH, c->gdH,
-                    c->halo_send, c->halo_recv, c->u0, c->u_alt, c->ctxbuf})
+                    c->halo_send, c->halo_recv, c->u0, c->u_alt, c->ctxbuf, c->filterF})
     if (p) cudaFree(p);
   for (double* p : c->dt_slots) cudaFree(p);
   if (c->nbr) cudaFree(c->nbr);
@@ -847,6 +926,30 @@ int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
   return prepare_fused_update(c);
 }
 
+int dgrhs_set_exponential_filter(dgrhs_ctx* c, int enable, double alpha, int half_power) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (!enable) {
+    if (c->filterF) cudaFree(c->filterF);
+    c->filterF = nullptr;
+    return 0;
+  }
+  if (half_power < 1) return fail("half_power must be positive");
+  std::vector<double> F;
+  exponential_filter_matrix(c->N, alpha, (unsigned)half_power, F);
+  if (!c->filterF && dev_alloc(&c->filterF, F.size())) return 1;
+  CU(cudaMemcpy(c->filterF, F.data(), F.size() * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dgrhs_exponential_filter_matrix(int N, double alpha, int half_power, double* matrix) {
+  if (N < 2 || half_power < 1) return fail("bad arguments");
+  std::vector<double> F;
+  exponential_filter_matrix(N, alpha, (unsigned)half_power, F);
+  std::memcpy(matrix, F.data(), F.size() * 8);
+  return 0;
+}
+
 int dgrhs_set_split_volume(dgrhs_ctx* c, int enable) {
   CHECK_CTX(c);
   c->split_volume = enable != 0;
@@ -917,6 +1020,11 @@ int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
       done = 1;
     }
   }
+  // dg::Actions::Filter runs after UpdateU in step_actions; a self-start
+  // substep whose update is skipped leaves u untouched (and is reset anyway)
+  const bool updated = !(c->stepper == DGRHS_STEPPER_ADAMS_BASHFORTH &&
+                         c->cur_op.kind == SubstepOp::kAbEvalOnly);
+  if (updated && apply_filter(c)) return 1;
   c->upd_active = false;
   if (is_step_done) *is_step_done = done;
   return 0;

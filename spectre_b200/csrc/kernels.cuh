@@ -1194,6 +1194,54 @@ __global__ void __launch_bounds__(256) gh_constraints_kernel(ConstraintArgs a) {
 // GaugeWave.hpp:34-50).  The spatial derivative is then taken numerically by
 // partial_derivatives_kernel (:136-143), d_t H_a = 0 (:145-147).
 // --------------------------------------------------------------------------
+// --------------------------------------------------------------------------
+// Exponential filter after the substep: dg::Actions::Filter<
+// Filters::Exponential<0>> = apply_matrices(u, {F, F, F}) on every evolved
+// component (LinearOperators/ExponentialFilter.cpp:45-76, Spectral/Filtering.cpp
+// :20-32).  One CTA per (element, component); xi, eta, zeta in that order like
+// ApplyMatrices.cpp.
+// --------------------------------------------------------------------------
+struct FilterArgs {
+  double* u;        // [E][C][npad]
+  const double* F;  // [N*N] row-major filter matrix
+  int C;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) exponential_filter_kernel(FilterArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
+  __shared__ __align__(16) double t0[npad];
+  __shared__ __align__(16) double t1[npad];
+  __shared__ double sF[N * N];
+  double* uc = a.u + (size_t)blockIdx.x * npad;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) t0[p] = uc[p];
+  for (int p = threadIdx.x; p < N * N; p += blockDim.x) sF[p] = a.F[p];
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const int i = p % N, rest = p / N;
+    double v = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) v = fma(sF[i * N + m], t0[m + N * rest], v);
+    t1[p] = v;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const int i = p % N, j = (p / N) % N, k = p / (N * N);
+    double v = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) v = fma(sF[j * N + m], t1[i + N * (m + N * k)], v);
+    t0[p] = v;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const int ij = p % (N * N), k = p / (N * N);
+    double v = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) v = fma(sF[k * N + m], t0[ij + N * N * m], v);
+    uc[p] = v;
+  }
+}
+
 // AnalyticChristoffel for a static analytic solution (AnalyticChristoffel.cpp:
 // 76-147): H_a = -Gamma_a of the analytic (g, Pi, Phi); the spatial derivative
 // is then taken by partial_derivatives_kernel, d_t H_a = 0.

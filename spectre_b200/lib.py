@@ -26,7 +26,8 @@ EXPORTS = [
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
     "dgrhs_take_steps", "dgrhs_time", "dgrhs_rhs_evaluations", "dgrhs_begin_substep",
-    "dgrhs_end_substep", "dgrhs_set_fused_update", "dgrhs_set_split_volume", "dgrhs_time_kernels", "dgrhs_gh_constraint_norms",
+    "dgrhs_end_substep", "dgrhs_set_exponential_filter", "dgrhs_exponential_filter_matrix",
+    "dgrhs_set_fused_update", "dgrhs_set_split_volume", "dgrhs_time_kernels", "dgrhs_gh_constraint_norms",
     "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
     "dgrhs_collocation_points_and_weights", "dgrhs_adams_bashforth_coefficients",
@@ -89,6 +90,12 @@ def collocation_points_and_weights(N: int):
     x, w = np.zeros(N), np.zeros(N)
     _check(load().dgrhs_collocation_points_and_weights(N, _ptr(x), _ptr(w)))
     return x, w
+
+
+def exponential_filter_matrix(N: int, alpha: float, half_power: int) -> np.ndarray:
+    F = np.zeros((N, N))
+    _check(load().dgrhs_exponential_filter_matrix(N, ctypes.c_double(alpha), half_power, _ptr(F)))
+    return F
 
 
 def adams_bashforth_coefficients(times, step_start, step_end):
@@ -273,6 +280,10 @@ class Context:
     def set_stepper(self, stepper, order, t0, dt):
         _check(self._lib.dgrhs_set_stepper(self._h, stepper, order, ctypes.c_double(t0),
                                            ctypes.c_double(dt)))
+
+    def set_exponential_filter(self, enable: bool, alpha: float = 36.0, half_power: int = 64):
+        _check(self._lib.dgrhs_set_exponential_filter(self._h, int(enable),
+                                                      ctypes.c_double(alpha), half_power))
 
     def set_split_volume(self, enable: bool):
         _check(self._lib.dgrhs_set_split_volume(self._h, int(enable)))

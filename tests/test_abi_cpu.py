@@ -64,3 +64,17 @@ def test_product_analytic_data_matches_oracle():
         np.testing.assert_allclose(analytic.kerr_schild(x[e]), ref, rtol=1e-13, atol=1e-14)
         np.testing.assert_allclose(analytic.plane_wave(x[e], 0.2), orc.plane_wave(x[e], 0.2),
                                    rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize("N", [3, 5, 8, 12])
+def test_exponential_filter_matrix(N):
+    """Filter matrix vs the oracle; with KerrSchild.yaml's (36, 64) only the top
+    Legendre mode is damped, so polynomials of degree < N-1 pass unchanged
+    (Test_ExponentialFilter.cpp checks the same property)."""
+    F = lib.exponential_filter_matrix(N, 36.0, 64)
+    np.testing.assert_allclose(F, orc.exponential_filter_matrix(N, 36.0, 64), atol=1e-12)
+    x, _ = lib.collocation_points_and_weights(N)
+    for p in range(N - 1):
+        np.testing.assert_allclose(F @ x ** p, x ** p, atol=1e-12)
+    top = np.polynomial.legendre.legval(x, [0] * (N - 1) + [1])
+    assert np.max(np.abs(F @ top)) < 1e-14
