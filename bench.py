@@ -327,12 +327,20 @@ def main():
     dom_name = max(in_step, key=lambda n: kms_d[n])
     pts_local = ev.n_points
     achieved = kb[dom_name] * pts_local / (kms_d[dom_name] * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        kname = {"face": "gh_face_kernel",
+                 "volume_update_fused": "gh_volume_kernel (stepper update fused)"}[dom_name]
+        traffic = tj.get(f"{kname}|{N}|{ev.part.n_local}")
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm",
         "kernel": {"face": "gh_face_kernel",
                    "volume_update_fused": "gh_volume_kernel (stepper update fused)"}[dom_name],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
         "alg_bytes_per_launch": kb[dom_name] * pts_local,
         "alg_bytes_note": "SURVEY 8(d) accounting: volume group + update group (the fused "
                           "kernel actually moves less: u and dt_u are not re-read)",
