@@ -180,7 +180,8 @@ def workload_config(args, world, cpu=False):
     ref = weak_refinement(world, args.refine)
     names = {
         "gauge-wave": "BASELINE.json configs[1]: GeneralizedHarmonic gauge wave (A=0.1, "
-                      "lambda=1), periodic Brick [0,1]^3, AB3, dt=2e-4, UpwindPenalty, "
+                      "lambda=1), periodic Brick [0,1]^3 per GPU (the domain grows by whole "
+                      "wavelengths with the GPU count), AB3, dt=2e-4, UpwindPenalty, "
                       "gamma0/1/2=1/-1/1",
         "kerr-schild": "BASELINE.json configs[2]/[3] stand-in: GeneralizedHarmonic Kerr-Schild "
                        "(M=1, a=0) on a Brick lattice (elements of edge M/8 from x=2M), "
@@ -249,7 +250,10 @@ def main():
         problem = evolution.gh_kerr_schild_problem(
             refinement, N, lower=(2.0, 2.0, 2.0), upper=tuple(2.0 + 0.125 * n for n in ne))
     else:
-        problem = evolution.gh_gauge_wave_problem(refinement, N)
+        # weak scaling keeps the element size of the single-GPU run (1/2^refine): the
+        # periodic domain grows by whole wavelengths, so dt stays inside the AB3 limit
+        upper = tuple(float(2 ** (r - args.refine)) for r in refinement)
+        problem = evolution.gh_gauge_wave_problem(refinement, N, upper=upper)
     gauge = lib.GAUGE_HARMONIC if args.gauge == "harmonic" else lib.GAUGE_ANALYTIC_GAUGE_WAVE
     ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, args.dt, 0.0, gauge,
                              (0.1, 1.0) if args.gauge == "analytic" else (), local_rank, world,

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgrhs.so")
+# DGRHS_LIB lets a developer point at an experimental build of the same C-ABI
+LIB_PATH = os.environ.get("DGRHS_LIB") or os.path.join(_HERE, "libdgrhs.so")
 
 SYSTEM_SCALAR_WAVE, SYSTEM_GH = 0, 1
 GAUGE_HARMONIC, GAUGE_FIELDS, GAUGE_DAMPED_HARMONIC, GAUGE_ANALYTIC_GAUGE_WAVE = 0, 1, 2, 3
