@@ -34,14 +34,24 @@ struct Cfg {
   static constexpr int n = N * N * N;
   static constexpr int f = N * N;
   static constexpr int npad = (n + 15) / 16 * 16;
-  // volume kernel: one CTA per (element, chunk of <= 256 points)
-  static constexpr int nchunk = (n + 255) / 256;
-  static constexpr int T = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
   // GH volume kernel ring: one stage = the 5 component rows of a (mu,nu) pair
   // plus that pair's block of lifted face corrections [6][5][f]
   static constexpr int stage_doubles = 5 * npad + 30 * f;
+  // Volume kernels: one CTA per (element, chunk of points), one thread per
+  // point, 255 registers.  Preferred: chunks of <= 128 points and TWO CTAs per
+  // SM -- the two CTAs run out of phase (one in its FMA-bound prologue while the
+  // other streams from shared memory), measured 1.34 -> 1.15 ms on config 2.
+  // That needs two 2-stage rings per SM; larger elements (N >= 10) fall back to
+  // chunks of <= 256 points and one CTA per SM.
+  static constexpr int fixed128 = (10 * 128 + (N * N + 1) / 2 * 2) * 8 + 64;
+  static constexpr bool two_cta = 2 * (2 * stage_doubles * 8 + fixed128 + 1024) <= 232448;
+  static constexpr int chunk_max = two_cta ? 128 : 256;
+  static constexpr int nchunk = (n + chunk_max - 1) / chunk_max;
+  static constexpr int T = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
+  static constexpr int min_blocks = two_cta ? 2 : 1;
   static constexpr int fixed_bytes = (10 * T + (N * N + 1) / 2 * 2) * 8 + 64;
-  static constexpr int max_stages = (232448 - fixed_bytes) / (stage_doubles * 8);
+  static constexpr int max_stages =
+      (232448 / min_blocks - 1024 - fixed_bytes) / (stage_doubles * 8);
   static constexpr int nstage = max_stages >= 4 ? 4 : max_stages;
   static_assert(nstage >= 2, "element too large for the shared-memory ring");
 };
@@ -234,7 +244,7 @@ constexpr int gh_volume_smem_bytes() {
 
 // kGauge: 0 Harmonic, 1 gauge fields from memory, 2 DampedHarmonic
 template <int N, int kGauge>
-__global__ void __launch_bounds__(Cfg<N>::T, 1) gh_volume_kernel(GhVolArgs a) {
+__global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kernel(GhVolArgs a) {
   constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, T = Cfg<N>::T, f = N * N;
   constexpr int NS = Cfg<N>::nstage, SD = Cfg<N>::stage_doubles;
   extern __shared__ __align__(128) unsigned char smem_raw[];
