@@ -469,3 +469,51 @@ def test_exponential_filter_evolution():
     for _ in range(3):
         ev.step()
     assert np.max(np.abs(ev.u - results[0])) > 1e-6
+
+
+def test_config1_full_size_scalar_wave_rk3():
+    """BASELINE.json configs[0] at full size: ScalarWave plane wave, periodic
+    Brick [0,2pi]^3, 8^3 elements, N = 6, Rk3HesthavenSsp, dt = 1e-3."""
+    from spectre_b200 import evolution
+    N, dt = 6, 1e-3
+    problem = evolution.scalar_wave_problem([3, 3, 3], N)
+    ev = evolution.Evolution(problem, lib.STEPPER_RK3_HESTHAVEN, 3, dt)
+    ev.take_steps(3)
+    got = ev.ctx.get_state()
+    x, J = problem.coords(), problem.inverse_jacobian()
+    stat, nb = problem.static(), problem.neighbors
+    o = orc.Evolution(lambda u, t: orc.dg_rhs(0, N, u, J, stat, nb), problem.u0(), 0.0, dt, "RK3")
+    for _ in range(3):
+        o.step()
+    assert _relerr(got, o.u, SW_BLOCKS) < TOL
+    exact = analytic.plane_wave(x, ev.ctx.time)
+    assert orc.l2_norm(got - exact) < 1e-6
+    ev.ctx.close()
+
+
+def test_config2_full_size_gauge_wave():
+    """BASELINE.json configs[1] at full size (16^3 elements, N = 8): one RHS
+    against the oracle, then size-independent properties of a 5-step AB3
+    evolution: the error against the exact gauge wave stays at truncation level,
+    the solution is invariant under translation by one element in y and z
+    (the data depend on x only), and the constraint norms stay small."""
+    from spectre_b200 import evolution
+    N, dt = 8, 2e-4
+    problem = evolution.gh_gauge_wave_problem([4, 4, 4], N)
+    ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, dt)
+    ctx = ev.ctx
+    u0 = problem.u0()
+    J, stat, nb = problem.inverse_jacobian(), problem.static(), problem.neighbors
+    ctx.compute_time_derivative(0.0)
+    ref = orc.dg_rhs(1, N, u0, J, stat, nb)
+    assert _relerr(ctx.get_time_derivative(), ref, GH_BLOCKS) < TOL
+    ev.take_steps(5)
+    got = ctx.get_state()
+    exact = analytic.gauge_wave(problem.coords(), ctx.time)
+    assert np.max(np.abs(got - exact)) < 1e-9
+    cells = problem.brick.cells
+    index_of = problem.brick.index_of
+    shifted = np.array([index_of[(c[0], (c[1] + 1) % 16, (c[2] + 3) % 16)] for c in cells])
+    assert np.max(np.abs(got - got[shifted])) < 1e-13
+    assert (ctx.gh_constraint_norms() < 1e-8).all()
+    ctx.close()
