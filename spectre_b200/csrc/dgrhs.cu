@@ -811,8 +811,10 @@ int dgrhs_set_boundary_ghost_data(dgrhs_ctx* c, int slot_begin, int n_slots,
   if (n_slots == 0) return 0;
   CU(cudaSetDevice(c->device));
   const size_t per = (size_t)c->HC * c->f;
-  CU(cudaMemcpy(c->halo_recv + (size_t)slot_begin * per, data, (size_t)n_slots * per * 8,
-                cudaMemcpyHostToDevice));
+  // ordered after the kernels already queued on the context's stream
+  CU(cudaMemcpyAsync(c->halo_recv + (size_t)slot_begin * per, data, (size_t)n_slots * per * 8,
+                     cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -9,14 +9,18 @@
 //
 // Kernels (reference call sites: SURVEY.md 2.2 K1-K13):
 //   face_kernel      K5-K8,K10,K11  both sides of every mortar are packaged in
-//                    registers from the raw face values; the lifted correction
-//                    goes to a compact buffer corr[element][6][C][N^2]
-//   gh/sw_volume     K1-K3 fused: TMA-staged element tiles, sum-factorised
-//                    logical derivatives from shared memory, Jacobian folded
-//                    into the pointwise coefficients, corr added on face points,
-//                    dt_u written once
-//   lincomb_kernel   K12-K13: u <- a u + sum c_j v_j, 128-bit vectorised
+//                    registers from the raw face values; every local interface
+//                    is evaluated once and the lifted corrections of both
+//                    elements go to a compact pair-major buffer
+//   gh/sw_volume     K1-K3 + K12-K13 fused: TMA-staged element tiles,
+//                    sum-factorised logical derivatives from shared memory,
+//                    Jacobian folded into the pointwise coefficients, corrections
+//                    added on face points, dt_u written once, stepper update
+//                    u_new = a u + sum c_j v_j written to the second state buffer
+//   lincomb_kernel   K12-K13 as a separate pass (only when fusion is disabled)
 //   pack_halo        face slices for neighbours on other GPUs
+//   others           stand-alone partial_derivatives, gauge sources, exponential
+//                    filter, constraint norms
 #pragma once
 
 #include <cuda_runtime.h>
@@ -147,24 +151,10 @@ __device__ __forceinline__ void logical_derivs(const double* __restrict__ tc,
   d[2] = d2;
 }
 
-// lifted boundary corrections of the faces this point lies on, added in
-// direction order 0..5 (add_slice_to_data, ApplyBoundaryCorrections.hpp:
-// 1038-1043; the reference's order is a hash-map order, i.e. unspecified)
-template <int N, int C>
-__device__ __forceinline__ double add_corrections(double v,
-                                                  const double* __restrict__ corr_e,
-                                                  int comp, int i, int j, int k) {
-  constexpr int f = N * N;
-  if (i == 0) v += corr_e[(0 * C + comp) * f + j + N * k];
-  if (i == N - 1) v += corr_e[(1 * C + comp) * f + j + N * k];
-  if (j == 0) v += corr_e[(2 * C + comp) * f + i + N * k];
-  if (j == N - 1) v += corr_e[(3 * C + comp) * f + i + N * k];
-  if (k == 0) v += corr_e[(4 * C + comp) * f + i + N * j];
-  if (k == N - 1) v += corr_e[(5 * C + comp) * f + i + N * j];
-  return v;
-}
-
-// Same, with the point's (at most three) faces resolved once per thread:
+// Lifted boundary corrections of the faces a point lies on are added in
+// direction order xi, eta, zeta (add_slice_to_data, ApplyBoundaryCorrections.hpp:
+// 1038-1043; the reference's order is a hash-map order, i.e. unspecified).
+// The point's (at most three) faces are resolved once per thread:
 // off[d] = offset of the point inside a [6][C][f] block for dimension d, or -1.
 template <int N, int C>
 struct FaceSlots {

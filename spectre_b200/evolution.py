@@ -77,6 +77,9 @@ class Problem:
         self._initial_data, self._static_values = initial_data, static_values
         self.dirichlet_analytic = dirichlet_analytic
         self.analytic_christoffel_gauge = analytic_christoffel_gauge
+        # a time-dependent analytic solution on the boundary is re-evaluated at the
+        # time of every RHS (DirichletAnalytic.cpp:80-96 passes `time`)
+        self.boundary_time_dependent = False
         self.neighbors = brick.neighbors()
 
     def coords(self, ids=None):
@@ -126,6 +129,19 @@ def gh_kerr_schild_problem(refinement, N, lower=(2.0, 2.0, 2.0), upper=(4.0, 4.0
                    dirichlet_analytic=True, analytic_christoffel_gauge=True)
 
 
+def gh_gauge_wave_dirichlet_problem(refinement, N, amplitude=0.1, wavelength=1.0,
+                                    gammas=(1.0, -1.0, 1.0)):
+    """Gauge wave on the Brick [0,1]^3 that is periodic in y and z only; the x
+    faces carry DirichletAnalytic with the (time-dependent) exact solution."""
+    brick = domain.Brick((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), refinement, N,
+                         periodic=(False, True, True))
+    p = Problem(lib.SYSTEM_GH, brick,
+                lambda x, t: analytic.gauge_wave(x, t, amplitude, wavelength), gammas,
+                dirichlet_analytic=True)
+    p.boundary_time_dependent = True
+    return p
+
+
 def scalar_wave_problem(refinement, N):
     """BASELINE.json configs[0] (PlaneWave3D.yaml: Brick [0,2pi]^3 periodic,
     gamma2 = 0)."""
@@ -141,6 +157,7 @@ class Evolution:
                  t0=0.0, gauge=lib.GAUGE_HARMONIC, gauge_params=(), device=0, world=1, rank=0,
                  process_group=None):
         self.world, self.rank = world, rank
+        self.problem = problem
         self.part = domain.Partition(problem.neighbors, world, rank,
                                      boundary_slots=problem.dirichlet_analytic)
         ids = self.part.global_ids
@@ -208,6 +225,9 @@ class Evolution:
     def _substep(self) -> bool:
         ctx = self.ctx
         t = ctx.begin_substep()
+        if self.part.external_faces and self.problem.boundary_time_dependent:
+            ctx.set_boundary_ghost_data(self.part.n_recv,
+                                        self.boundary_ghost_data(self.problem, t))
         if self.world == 1:
             ctx.compute_time_derivative_range(t, 0, self.part.n_local)
         elif self.part.n_recv == 0:

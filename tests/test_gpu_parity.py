@@ -517,3 +517,53 @@ def test_config2_full_size_gauge_wave():
     assert np.max(np.abs(got - got[shifted])) < 1e-13
     assert (ctx.gh_constraint_norms() < 1e-8).all()
     ctx.close()
+
+
+def test_time_dependent_dirichlet_analytic_gauge_wave():
+    """DirichletAnalytic with a time-dependent solution: the exterior state is
+    re-evaluated at the time of every RHS (incl. the self-start substeps)."""
+    from spectre_b200 import evolution
+    N, dt = 5, 2e-4
+    problem = evolution.gh_gauge_wave_dirichlet_problem([1, 1, 1], N)
+    ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, dt)
+    part = ev.part
+    assert len(part.external_faces) == 8
+    ev.take_steps(4)
+    got = ev.ctx.get_state()
+    ids = part.global_ids
+    J, stat = problem.inverse_jacobian(ids), problem.static(ids)
+
+    def rhs(u, t):
+        ext = ev.boundary_ghost_data(problem, t)[:, :50]
+        return orc.dg_rhs(1, N, u, J, stat, part.local_neighbors, ext_u=ext)
+
+    o = orc.Evolution(rhs, problem.u0(ids, 0.0), 0.0, dt, "AB3")
+    for _ in range(4):
+        o.step()
+    assert _relerr(got, o.u, GH_BLOCKS) < TOL
+    exact = problem.u0(ids, ev.ctx.time)
+    assert np.max(np.abs(got - exact)) < 1e-5
+    ev.ctx.close()
+
+
+@pytest.mark.parametrize("order", [5, 6])
+def test_high_order_adams_bashforth(order):
+    """AB5/AB6 (more old terms than the fused update carries: separate update
+    kernel) incl. the self-start, vs the oracle."""
+    N, dt = 4, 1e-3
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    u0 = analytic.plane_wave(x, 0.0)
+    stat = np.zeros((brick.n_elements, 1, brick.n))
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u0)
+    ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, order, 0.0, dt)
+    ctx.take_steps(3)
+    ev = orc.Evolution(lambda u, t: orc.dg_rhs(0, N, u, J, stat, nb), u0, 0.0, dt, f"AB{order}")
+    for _ in range(3):
+        ev.step()
+    assert ctx.rhs_evaluations == ev.rhs_evals
+    assert _relerr(ctx.get_state(), ev.u, SW_BLOCKS) < TOL
+    ctx.close()
