@@ -86,6 +86,19 @@ int dgrhs_destroy(dgrhs_ctx* ctx);
 int dgrhs_set_geometry(dgrhs_ctx* ctx, const double* inv_jacobian,
                        const double* coords, const int32_t* neighbors);
 
+/* Non-aligned neighbours (rotated blocks, e.g. the wedges of a Sphere): the
+ * face-restricted OrientationMap of every neighbour (Domain/Structure/
+ * OrientationMap.hpp, orient_variables_on_slice in OrientationMapHelpers.cpp:25-
+ * 120).  neighbor_direction host [n_elements][6]: the neighbour's direction
+ * (0..5) whose face touches ours; face_permutation host [n_elements][6]: how our
+ * face point (qa, qb) -- the two remaining logical dimensions in increasing
+ * order -- maps to the neighbour's: bit0 swap (qa, qb), bit1 / bit2 reverse the
+ * neighbour's first / second face coordinate.  Evolved tensors have inertial
+ * components, so only the point index is transformed.  Optional: without this
+ * call neighbours are aligned (direction d^1, identity).  Same N on both sides. */
+int dgrhs_set_neighbor_orientations(dgrhs_ctx* ctx, const int32_t* neighbor_direction,
+                                    const int32_t* face_permutation);
+
 /* Static per-point fields: ScalarWave: gamma2 (1 component,
  * ScalarWave/Initialize.hpp:48-49); GH: gamma0, gamma1, gamma2 (3 components,
  * GeneralizedHarmonic/Initialize.hpp:59-71).  host [n_elements][ncomp][n]. */

@@ -275,11 +275,13 @@ struct dgrhs_ctx {
   int C = 0, S = 0, HC = 0, n = 0, npad = 0, f = 0;
   int n_interior = -1;
   int n_send = 0;  // faces packed for other ranks (0: no exchange needed)
+  bool aligned_table_ok = true;
   cudaStream_t stream = nullptr;
   double *u = nullptr, *invjac = nullptr, *coords = nullptr, *stat = nullptr;
   double *corr = nullptr, *D = nullptr, *gH = nullptr, *gdH = nullptr;
   double *halo_send = nullptr, *halo_recv = nullptr;
-  int32_t *nbr = nullptr, *halo_map = nullptr;
+  int32_t *nbr = nullptr, *halo_map = nullptr, *nbr_face = nullptr;
+  std::vector<int32_t> nbr_host;
   std::vector<double*> dt_slots;  // derivative buffers (history ring)
   double* u0 = nullptr;           // saved value (self-start / RK step start)
   double* u_alt = nullptr;        // second state buffer for the fused update
@@ -335,6 +337,9 @@ int download(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
 template <int N>
 int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   if (ee <= eb) return 0;
+  if (!c->nbr_face && !c->aligned_table_ok)
+    return fail("neighbor table is not that of aligned blocks: call "
+                "dgrhs_set_neighbor_orientations");
   // whole batch: every interface once; element ranges: the interior / boundary
   // split of the multi-GPU schedule (see FaceArgs::pass)
   int pass = 0, n_int = c->nelem;
@@ -349,7 +354,8 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
     else
       return fail("element range must be [0, n_interior) or [n_interior, n_elements)");
   }
-  dg::FaceArgs a{c->u, c->invjac, c->stat, c->nbr, c->halo_recv, c->corr, c->nelem, n_int, pass};
+  dg::FaceArgs a{c->u,    c->invjac, c->stat, c->nbr, c->nbr_face, c->halo_recv,
+                 c->corr, c->nelem,  n_int,   pass};
   const long long total = (long long)c->nelem * 6 * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)
@@ -661,6 +667,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
     if (p) cudaFree(p);
   for (double* p : c->dt_slots) cudaFree(p);
   if (c->nbr) cudaFree(c->nbr);
+  if (c->nbr_face) cudaFree(c->nbr_face);
   if (c->halo_map) cudaFree(c->halo_map);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -678,11 +685,16 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
     if (v <= -2 && -(v + 2) >= c->nghost) return fail("ghost face index out of range");
   }
   // conforming aligned interfaces: the neighbour's opposite face points back
-  for (int e = 0; e < c->nelem; ++e)
+  // (a table for rotated blocks is validated by dgrhs_set_neighbor_orientations,
+  // which must then follow before the first right-hand side)
+  c->aligned_table_ok = true;
+  for (int e = 0; e < c->nelem && c->aligned_table_ok; ++e)
     for (int d = 0; d < 6; ++d) {
       const int v = neighbors[(size_t)e * 6 + d];
-      if (v >= 0 && neighbors[(size_t)v * 6 + (d ^ 1)] != e)
-        return fail("neighbor table is not symmetric at element %d direction %d", e, d);
+      if (v >= 0 && neighbors[(size_t)v * 6 + (d ^ 1)] != e) {
+        c->aligned_table_ok = false;
+        break;
+      }
     }
   if (upload(c, c->invjac, inv_jacobian, 9)) return 1;
   if (coords) {
@@ -690,6 +702,52 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
     if (upload(c, c->coords, coords, 3)) return 1;
   }
   CU(cudaMemcpy(c->nbr, neighbors, (size_t)c->nelem * 6 * 4, cudaMemcpyHostToDevice));
+  c->nbr_host.assign(neighbors, neighbors + (size_t)c->nelem * 6);
+  // a new neighbour table resets the orientations to "aligned"
+  if (c->nbr_face) cudaFree(c->nbr_face);
+  c->nbr_face = nullptr;
+  return 0;
+}
+
+int dgrhs_set_neighbor_orientations(dgrhs_ctx* c, const int32_t* neighbor_direction,
+                                    const int32_t* face_permutation) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (c->nbr_host.empty()) return fail("call dgrhs_set_geometry first");
+  std::vector<int32_t> packed((size_t)c->nelem * 6);
+  auto apply = [&](int perm, int qa, int qb, int& na, int& nb) {
+    na = (perm & 1) ? qb : qa;
+    nb = (perm & 1) ? qa : qb;
+    if (perm & 2) na = c->N - 1 - na;
+    if (perm & 4) nb = c->N - 1 - nb;
+  };
+  for (int e = 0; e < c->nelem; ++e)
+    for (int d = 0; d < 6; ++d) {
+      const size_t k = (size_t)e * 6 + d;
+      const int nd = neighbor_direction[k], perm = face_permutation[k];
+      if (nd < 0 || nd > 5 || perm < 0 || perm > 7)
+        return fail("bad orientation at element %d direction %d", e, d);
+      packed[k] = nd | (perm << 3);
+      const int v = c->nbr_host[k];
+      if (v < 0) continue;
+      // the neighbour must point back at us with the inverse face map
+      const size_t kn = (size_t)v * 6 + nd;
+      if (c->nbr_host[kn] != e || neighbor_direction[kn] != d)
+        return fail("orientations are not symmetric at element %d direction %d", e, d);
+      for (int qb = 0; qb < c->N; ++qb)
+        for (int qa = 0; qa < c->N; ++qa) {
+          int na, nb, ba, bb;
+          apply(perm, qa, qb, na, nb);
+          apply(face_permutation[kn], na, nb, ba, bb);
+          if (ba != qa || bb != qb)
+            return fail("face permutations of element %d direction %d and its neighbour are "
+                        "not inverse to each other", e, d);
+        }
+    }
+  // the aligned default needs the opposite-face rule checked in set_geometry;
+  // with explicit orientations that check is replaced by the one above
+  if (!c->nbr_face && dev_alloc(&c->nbr_face, packed.size())) return 1;
+  CU(cudaMemcpy(c->nbr_face, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
   return 0;
 }
 

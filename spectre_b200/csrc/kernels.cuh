@@ -768,6 +768,14 @@ struct FaceArgs {
   const double* invjac;   // [E][9][npad]
   const double* stat;     // [E][S][npad]
   const int32_t* nbr;     // [E][6]
+  // orientation of the neighbour across each face (OrientationMap,
+  // Domain/Structure/OrientationMapHelpers.cpp:25-120, restricted to the face):
+  // nbr_face[e*6+d] = nd | (perm << 3), nd = the neighbour's direction that
+  // touches this face, perm bit0 = swap the two face coordinates, bit1/bit2 =
+  // reverse the neighbour's first/second face coordinate.  nullptr = aligned
+  // (nd = d^1, perm = 0).  Tensor components are inertial, so only the point
+  // index is transformed (orient_variables_on_slice).
+  const int32_t* nbr_face;
   const double* ghost;    // [G][HC][f]   u (C) | J row (3) | gammas
   double* corr;           // GH: [E][10][6][5][f] pair-major; SW: [E][6][5][f]
   int nelem;
@@ -781,11 +789,23 @@ struct FaceArgs {
   int n_interior, pass;
 };
 
-// returns false if this (element, direction) task is not to be evaluated
-__device__ __forceinline__ bool face_task(const FaceArgs& a, int e, int d, int nb,
+// neighbour-side face coordinates of our face point (qa, qb)
+template <int N>
+__device__ __forceinline__ void orient_face_point(int perm, int qa, int qb, int& na,
+                                                  int& nb) {
+  na = (perm & 1) ? qb : qa;
+  nb = (perm & 1) ? qa : qb;
+  if (perm & 2) na = N - 1 - na;
+  if (perm & 4) nb = N - 1 - nb;
+}
+
+// returns false if this (element, direction) task is not to be evaluated;
+// nd = the neighbour's direction touching this face
+__device__ __forceinline__ bool face_task(const FaceArgs& a, int e, int d, int nb, int nd,
                                           bool& two_sided) {
   if (nb >= 0) {
-    if (d & 1) return false;  // handled by the neighbour's lower-face task
+    // a local interface is owned by its side with the smaller face id
+    if (e * 6 + d > nb * 6 + nd) return false;
     const bool in_int = e < a.n_interior || nb < a.n_interior;
     if ((a.pass == 1 && !in_int) || (a.pass == 2 && in_int)) return false;
     two_sided = true;
@@ -810,13 +830,20 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
+  const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
+  const int nd = nf & 7;
+  int na_, nb_;
+  orient_face_point<N>(nf >> 3, qa, qb, na_, nb_);
+  const int qn = na_ + N * nb_;  // the same point in the neighbour's face ordering
   bool two_sided;
-  if (!face_task(a, e, d, nb, two_sided)) return;
+  if (!face_task(a, e, d, nb, nd, two_sided)) return;
   // pair-major layout [e][pair s][direction][5][f]: the volume kernel stages
   // one pair block per TMA copy
   double* __restrict__ corr = a.corr + (size_t)e * 10 * 30 * f + (size_t)d * 5 * f + q;
   double* __restrict__ corr_nb =
-      two_sided ? a.corr + (size_t)nb * 10 * 30 * f + (size_t)(d ^ 1) * 5 * f + q : nullptr;
+      two_sided ? a.corr + (size_t)nb * 10 * 30 * f + (size_t)nd * 5 * f + qn : nullptr;
+  const int dim_n = nd >> 1;
+  const double sign_n = (nd & 1) ? 1.0 : -1.0;
   if (nb == -1) {
 #pragma unroll 1
     for (int s = 0; s < 10; ++s)
@@ -835,21 +862,22 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
     for (int x = 0; x < 3; ++x) unn_i[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
   }
   if (nb >= 0) {
-    const int p_nb = face_point<N>(d ^ 1, qa, qb);
+    const int p_nb = face_point<N>(nd, na_, nb_);
     un = a.u + (size_t)nb * 50 * npad + p_nb;
     ns = npad;
     const double* jn = a.invjac + (size_t)nb * 9 * npad + p_nb;
 #pragma unroll
-    for (int x = 0; x < 3; ++x) unn_e[x] = -sign * __ldg(jn + (size_t)(dim + 3 * x) * npad);
+    for (int x = 0; x < 3; ++x) unn_e[x] = sign_n * __ldg(jn + (size_t)(dim_n + 3 * x) * npad);
     const double* sn = a.stat + (size_t)nb * 3 * npad + p_nb;
     g1e = __ldg(sn + npad);
     g2e = __ldg(sn + 2 * npad);
   } else {
+    // ghost slot: the sender's face in ITS ordering, with its own J row
     const int gi = -(nb + 2);
-    un = a.ghost + (size_t)gi * HC * f + q;
+    un = a.ghost + (size_t)gi * HC * f + qn;
     ns = f;
 #pragma unroll
-    for (int x = 0; x < 3; ++x) unn_e[x] = -sign * __ldg(un + (size_t)(50 + x) * f);
+    for (int x = 0; x < 3; ++x) unn_e[x] = sign_n * __ldg(un + (size_t)(50 + x) * f);
     g1e = __ldg(un + (size_t)53 * f);
     g2e = __ldg(un + (size_t)54 * f);
   }
@@ -912,8 +940,15 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
+  const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
+  const int nd = nf & 7;
+  int na_, nb_;
+  orient_face_point<N>(nf >> 3, qa, qb, na_, nb_);
+  const int qn = na_ + N * nb_;
+  const int dim_n = nd >> 1;
+  const double sign_n = (nd & 1) ? 1.0 : -1.0;
   bool two_sided;
-  if (!face_task(a, e, d, nb, two_sided)) return;
+  if (!face_task(a, e, d, nb, nd, two_sided)) return;
   double* __restrict__ corr = a.corr + ((size_t)e * 6 + d) * 5 * f + q;
   if (nb == -1) {
 #pragma unroll
@@ -931,21 +966,21 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
     for (int c = 0; c < 5; ++c) ui[c] = __ldg(uo + (size_t)c * npad);
   }
   if (nb >= 0) {
-    const int p_nb = face_point<N>(d ^ 1, qa, qb);
+    const int p_nb = face_point<N>(nd, na_, nb_);
     const double* un = a.u + (size_t)nb * 5 * npad + p_nb;
     const double* jn = a.invjac + (size_t)nb * 9 * npad + p_nb;
 #pragma unroll
     for (int c = 0; c < 5; ++c) ue[c] = __ldg(un + (size_t)c * npad);
 #pragma unroll
-    for (int x = 0; x < 3; ++x) ne[x] = -sign * __ldg(jn + (size_t)(dim + 3 * x) * npad);
+    for (int x = 0; x < 3; ++x) ne[x] = sign_n * __ldg(jn + (size_t)(dim_n + 3 * x) * npad);
     g2e = __ldg(a.stat + (size_t)nb * npad + p_nb);
   } else {
     const int gi = -(nb + 2);
-    const double* un = a.ghost + (size_t)gi * HC * f + q;
+    const double* un = a.ghost + (size_t)gi * HC * f + qn;
 #pragma unroll
     for (int c = 0; c < 5; ++c) ue[c] = __ldg(un + (size_t)c * f);
 #pragma unroll
-    for (int x = 0; x < 3; ++x) ne[x] = -sign * __ldg(un + (size_t)(5 + x) * f);
+    for (int x = 0; x < 3; ++x) ne[x] = sign_n * __ldg(un + (size_t)(5 + x) * f);
     g2e = __ldg(un + (size_t)8 * f);
   }
   const double g2i = __ldg(a.stat + (size_t)e * npad + p_own);
@@ -964,7 +999,7 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
 #pragma unroll
   for (int c = 0; c < 5; ++c) corr[(size_t)c * f] = c5[c] * lift;
   if (two_sided) {
-    double* __restrict__ corr_nb = a.corr + ((size_t)nb * 6 + (d ^ 1)) * 5 * f + q;
+    double* __restrict__ corr_nb = a.corr + ((size_t)nb * 6 + nd) * 5 * f + qn;
     sw_face_correction(ue, g2e, ne, ui, g2i, ni, c5);
     const double lift_nb = -0.5 * (double)(N * (N - 1)) * me;
 #pragma unroll

@@ -20,7 +20,7 @@ STEPPER_ADAMS_BASHFORTH, STEPPER_RK3_HESTHAVEN = 0, 1
 # every symbol include/dgrhs.h declares
 EXPORTS = [
     "dgrhs_last_error", "dgrhs_kernel_launch_count", "dgrhs_create", "dgrhs_destroy",
-    "dgrhs_set_geometry", "dgrhs_set_static_fields", "dgrhs_set_gauge",
+    "dgrhs_set_geometry", "dgrhs_set_neighbor_orientations", "dgrhs_set_static_fields", "dgrhs_set_gauge",
     "dgrhs_set_gauge_fields", "dgrhs_set_gauge_analytic_christoffel",
     "dgrhs_set_boundary_ghost_data", "dgrhs_set_state", "dgrhs_get_state",
     "dgrhs_get_time_derivative", "dgrhs_compute_time_derivative", "dgrhs_set_interior_count",
@@ -209,6 +209,12 @@ class Context:
         assert J.shape == (self.n_elements, 9, self.n)
         assert nb.shape == (self.n_elements, 6)
         _check(self._lib.dgrhs_set_geometry(self._h, _ptr(J), _ptr(X), _ptr(nb)))
+
+    def set_neighbor_orientations(self, neighbor_direction, face_permutation):
+        nd = np.ascontiguousarray(neighbor_direction, dtype=np.int32)
+        pm = np.ascontiguousarray(face_permutation, dtype=np.int32)
+        assert nd.shape == pm.shape == (self.n_elements, 6)
+        _check(self._lib.dgrhs_set_neighbor_orientations(self._h, _ptr(nd), _ptr(pm)))
 
     def set_static_fields(self, fields):
         F = _f64(fields)
