@@ -51,7 +51,12 @@ enum {
 /* TimeSteppers (Time/TimeSteppers/) */
 enum {
   DGRHS_STEPPER_ADAMS_BASHFORTH = 0, /* AdamsBashforth.cpp:120-201, order 1..6 */
-  DGRHS_STEPPER_RK3_HESTHAVEN = 1    /* Rk3HesthavenSsp.cpp:55-81 */
+  DGRHS_STEPPER_RK3_HESTHAVEN = 1,   /* Rk3HesthavenSsp.cpp:55-81 */
+  /* RungeKutta::update_u_impl with a Butcher tableau (RungeKutta.cpp:69-122) */
+  DGRHS_STEPPER_RK3_OWREN = 2,       /* Rk3Owren.cpp:17-34 */
+  DGRHS_STEPPER_RK3_KENNEDY = 3,     /* Rk3Kennedy.cpp:18-43 (explicit part) */
+  DGRHS_STEPPER_RK4 = 4,             /* ClassicalRungeKutta4.cpp:24-49 */
+  DGRHS_STEPPER_DORMAND_PRINCE5 = 5  /* DormandPrince5.cpp:21-50 */
 };
 
 const char* dgrhs_last_error(void);

@@ -503,6 +503,34 @@ def analytic_christoffel_gauge(N, u_analytic, invjac):
 # order of Evolution/Executables/.../step_actions.
 # Times are exact Fractions of the step (the reference uses rational Time).
 # ---------------------------------------------------------------------------
+# Butcher tableaus (substep times c, substep coefficients A, result b) of the
+# reference's RungeKutta steppers: Rk3Owren.cpp:17-34, Rk3Kennedy.cpp:18-43,
+# ClassicalRungeKutta4.cpp:24-49, DormandPrince5.cpp:21-50.
+RK_TABLEAUS = {
+    "Rk3Owren": ([12.0 / 23.0, 4.0 / 5.0],
+                 [[12.0 / 23.0], [-68.0 / 375.0, 368.0 / 375.0]],
+                 [31.0 / 144.0, 529.0 / 1152.0, 125.0 / 384.0]),
+    "Rk3Kennedy": ([1767732205903.0 / 2027836641118.0, 3.0 / 5.0, 1.0],
+                   [[1767732205903.0 / 2027836641118.0],
+                    [5535828885825.0 / 10492691773637.0, 788022342437.0 / 10882634858940.0],
+                    [6485989280629.0 / 16251701735622.0, -4246266847089.0 / 9704473918619.0,
+                     10755448449292.0 / 10357097424841.0]],
+                   [1471266399579.0 / 7840856788654.0, -4482444167858.0 / 7529755066697.0,
+                    11266239266428.0 / 11593286722821.0, 1767732205903.0 / 4055673282236.0]),
+    "RK4": ([1.0 / 2.0, 1.0 / 2.0, 1.0, 3.0 / 4.0],
+            [[1.0 / 2.0], [0.0, 1.0 / 2.0], [0.0, 0.0, 1.0],
+             [5.0 / 32.0, 7.0 / 32.0, 13.0 / 32.0, -1.0 / 32.0]],
+            [1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0]),
+    "DP5": ([1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0, 1.0, 1.0],
+            [[1.0 / 5.0], [3.0 / 40.0, 9.0 / 40.0], [44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0],
+             [19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0],
+             [9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0,
+              -5103.0 / 18656.0],
+             [35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0]],
+            [35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0]),
+}
+
+
 class Evolution:
     def __init__(self, rhs, u0, t0, dt, stepper="AB3", post_update=None):
         """rhs(u, t) -> dt_u.  stepper: 'AB<k>' or 'RK3' (Rk3HesthavenSsp).
@@ -582,6 +610,23 @@ class Evolution:
             f2 = self._eval(n + Fraction(1, 2))
             u2 = self.u.copy()
             self.u = self.post((1.0 / 3.0) * (u0 + 2.0 * u2 + 2.0 * dt * f2))
+        elif self.stepper in RK_TABLEAUS:
+            # RungeKutta.cpp:69-122: u = u_start + dt sum_i coef_i f_i, the last
+            # substep with the result coefficients; substep k > 0 at t + c[k-1] dt
+            c, A, b = RK_TABLEAUS[self.stepper]
+            nsub = len(b)
+            u_start = self.u.copy()
+            fs = []
+            for k in range(nsub):
+                tk = float(n) + (0.0 if k == 0 else c[k - 1])
+                self.rhs_evals += 1
+                fs.append(self.rhs(self.u, self.t0 + tk * self.dt))
+                row = b if k == nsub - 1 else A[k]
+                u = u_start.copy()
+                for coef, f in zip(row, fs):
+                    if coef != 0.0:
+                        u += coef * self.dt * f
+                self.u = self.post(u)
         else:
             raise ValueError(self.stepper)
         self.step_index += 1

@@ -232,6 +232,57 @@ std::vector<double> variable_coefficients(std::vector<double> ct, double step_st
   return result;
 }
 
+// Butcher tableaus of the reference's RungeKutta steppers (RungeKutta.hpp:41-95):
+// Rk3Owren.cpp:17-34, Rk3Kennedy.cpp:18-43, ClassicalRungeKutta4.cpp:24-49,
+// DormandPrince5.cpp:21-50.  Only what the GTS path without error control uses:
+// substep times c, substep coefficients A, result coefficients b; the number of
+// substeps is b.size().
+struct ButcherTableau {
+  std::vector<double> substep_times;
+  std::vector<std::vector<double>> substep_coefficients;
+  std::vector<double> result_coefficients;
+};
+
+const ButcherTableau& butcher_tableau(int stepper) {
+  static const ButcherTableau owren{
+      {12.0 / 23.0, 4.0 / 5.0},
+      {{12.0 / 23.0}, {-68.0 / 375.0, 368.0 / 375.0}},
+      {31.0 / 144.0, 529.0 / 1152.0, 125.0 / 384.0}};
+  static const ButcherTableau kennedy{
+      {1767732205903.0 / 2027836641118.0, 3.0 / 5.0, 1.0},
+      {{1767732205903.0 / 2027836641118.0},
+       {5535828885825.0 / 10492691773637.0, 788022342437.0 / 10882634858940.0},
+       {6485989280629.0 / 16251701735622.0, -4246266847089.0 / 9704473918619.0,
+        10755448449292.0 / 10357097424841.0}},
+      {1471266399579.0 / 7840856788654.0, -4482444167858.0 / 7529755066697.0,
+       11266239266428.0 / 11593286722821.0, 1767732205903.0 / 4055673282236.0}};
+  static const ButcherTableau rk4{
+      {1.0 / 2.0, 1.0 / 2.0, 1.0, 3.0 / 4.0},
+      {{1.0 / 2.0}, {0.0, 1.0 / 2.0}, {0.0, 0.0, 1.0},
+       {5.0 / 32.0, 7.0 / 32.0, 13.0 / 32.0, -1.0 / 32.0}},
+      {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0}};
+  static const ButcherTableau dp5{
+      {1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0, 1.0, 1.0},
+      {{1.0 / 5.0},
+       {3.0 / 40.0, 9.0 / 40.0},
+       {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0},
+       {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0},
+       {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0},
+       {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}},
+      {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
+  switch (stepper) {
+    case DGRHS_STEPPER_RK3_OWREN: return owren;
+    case DGRHS_STEPPER_RK3_KENNEDY: return kennedy;
+    case DGRHS_STEPPER_RK4: return rk4;
+    default: return dp5;
+  }
+}
+
+bool is_tableau_stepper(int stepper) {
+  return stepper == DGRHS_STEPPER_RK3_OWREN || stepper == DGRHS_STEPPER_RK3_KENNEDY ||
+         stepper == DGRHS_STEPPER_RK4 || stepper == DGRHS_STEPPER_DORMAND_PRINCE5;
+}
+
 // times in integer ticks of dt/tick_den
 std::vector<double> ab_coefficients_ticks(const std::vector<long long>& ticks,
                                           long long start, long long end,
@@ -557,6 +608,7 @@ int prepare_fused_update(dgrhs_ctx* c) {
   if (!c->u_alt && dev_alloc(&c->u_alt, c->state_len())) return 1;
   dg::UpdateArgs up{};
   up.u_new = c->u_alt;
+  if (is_tableau_stepper(c->stepper)) return 0;  // separate update (up to 7 terms)
   if (c->stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
     const SubstepOp& op = c->cur_op;
     if (op.kind != SubstepOp::kAbStep || op.order > 4) return 0;
@@ -911,6 +963,8 @@ int dgrhs_set_stepper(dgrhs_ctx* c, int stepper, int order, double t0, double dt
     if (order < 1 || order > 6) return fail("Adams-Bashforth order must be in [1, 6]");
   } else if (stepper == DGRHS_STEPPER_RK3_HESTHAVEN) {
     order = 3;
+  } else if (is_tableau_stepper(stepper)) {
+    order = (int)butcher_tableau(stepper).result_coefficients.size();  // substeps
   } else {
     return fail("unknown stepper %d", stepper);
   }
@@ -945,6 +999,9 @@ int dgrhs_set_stepper(dgrhs_ctx* c, int stepper, int order, double t0, double dt
       CU(cudaMemcpyAsync(c->u0, c->u, c->state_len() * 8, cudaMemcpyDeviceToDevice,
                          c->stream));
     }
+  } else if (is_tableau_stepper(stepper)) {
+    c->tick_den = 1;
+    if (ensure_slots(c, order)) return 1;  // one derivative slot per substep
   } else {
     c->tick_den = 2;
     if (ensure_slots(c, 1)) return 1;
@@ -975,6 +1032,14 @@ int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
     c->free_slots.pop_back();
     c->dt_last = c->dt_slots[c->cur_slot];
     *time = c->t0 + ((double)c->cur_op.tick / (double)c->tick_den) * c->dt;
+  } else if (is_tableau_stepper(c->stepper)) {
+    // RungeKutta::next_time_id (RungeKutta.cpp:37-59): substep k > 0 is at
+    // t + dt * substep_times[k-1]
+    const ButcherTableau& tab = butcher_tableau(c->stepper);
+    const double frac = c->rk_substep == 0 ? 0.0 : tab.substep_times[c->rk_substep - 1];
+    c->cur_slot = c->rk_substep;
+    c->dt_last = c->dt_slots[c->cur_slot];
+    *time = c->t0 + ((double)c->step_index + frac) * c->dt;
   } else {
     const long long base = c->step_index * 2;
     const long long off[3] = {0, 2, 1};  // substep times t, t+dt, t+dt/2
@@ -1045,6 +1110,31 @@ int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
         ++c->step_index;
         done = 1;
       }
+    }
+  } else if (is_tableau_stepper(c->stepper)) {
+    // RungeKutta.cpp:69-122 (compute_substep): u = u_start + dt sum_i coef_i f_i
+    const ButcherTableau& tab = butcher_tableau(c->stepper);
+    const int nsub = (int)tab.result_coefficients.size();
+    const int k = c->rk_substep;
+    if (k == 0)
+      CU(cudaMemcpyAsync(c->u0, c->u, c->state_len() * 8, cudaMemcpyDeviceToDevice,
+                         c->stream));
+    const std::vector<double>& row =
+        k == nsub - 1 ? tab.result_coefficients : tab.substep_coefficients[k];
+    std::vector<double> coef{1.0};
+    std::vector<const double*> v{c->u0};
+    for (size_t i = 0; i < row.size(); ++i)
+      if (row[i] != 0.0) {
+        coef.push_back(row[i] * c->dt);
+        v.push_back(c->dt_slots[i]);
+      }
+    if (lincomb(c, c->u, 0.0, coef, v)) return 1;
+    if (k == nsub - 1) {
+      c->rk_substep = 0;
+      ++c->step_index;
+      done = 1;
+    } else {
+      c->rk_substep = k + 1;
     }
   } else {
     const double dt = c->dt;

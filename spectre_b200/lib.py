@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("DGRHS_LIB") or os.path.join(_HERE, "libdgrhs.so")
 SYSTEM_SCALAR_WAVE, SYSTEM_GH = 0, 1
 GAUGE_HARMONIC, GAUGE_FIELDS, GAUGE_DAMPED_HARMONIC, GAUGE_ANALYTIC_GAUGE_WAVE = 0, 1, 2, 3
 STEPPER_ADAMS_BASHFORTH, STEPPER_RK3_HESTHAVEN = 0, 1
+STEPPER_RK3_OWREN, STEPPER_RK3_KENNEDY, STEPPER_RK4, STEPPER_DORMAND_PRINCE5 = 2, 3, 4, 5
 
 # every symbol include/dgrhs.h declares
 EXPORTS = [

@@ -568,3 +568,29 @@ def test_high_order_adams_bashforth(order):
     assert ctx.rhs_evaluations == ev.rhs_evals
     assert _relerr(ctx.get_state(), ev.u, SW_BLOCKS) < TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("name,stepper", [("Rk3Owren", lib.STEPPER_RK3_OWREN),
+                                          ("Rk3Kennedy", lib.STEPPER_RK3_KENNEDY),
+                                          ("RK4", lib.STEPPER_RK4),
+                                          ("DP5", lib.STEPPER_DORMAND_PRINCE5)])
+def test_butcher_tableau_steppers(name, stepper):
+    """RungeKutta::update_u_impl with the reference's tableaus vs the oracle."""
+    N, dt = 5, 1e-3
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    u0 = analytic.plane_wave(x, 0.0)
+    stat = np.zeros((brick.n_elements, 1, brick.n))
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u0)
+    ctx.set_stepper(stepper, 0, 0.0, dt)
+    ctx.take_steps(3)
+    ev = orc.Evolution(lambda u, t: orc.dg_rhs(0, N, u, J, stat, nb), u0, 0.0, dt, name)
+    for _ in range(3):
+        ev.step()
+    assert ctx.rhs_evaluations == ev.rhs_evals
+    assert abs(ctx.time - ev.time) < 1e-15
+    assert _relerr(ctx.get_state(), ev.u, SW_BLOCKS) < TOL
+    ctx.close()

@@ -280,3 +280,21 @@ def test_damped_harmonic_vs_reference_numpy(golden_dir):
         L.orc_damped_harmonic(P(g), P(pi), P(phi), P(x), P(gp), P(H), P(dH))
         np.testing.assert_allclose(H, z["H"][p], rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(dH, z["dH"][p], rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,order", [("Rk3Owren", 3), ("Rk3Kennedy", 3), ("RK4", 4),
+                                        ("DP5", 5), ("RK3", 3), ("AB3", 3)])
+def test_stepper_convergence_order(name, order):
+    """Test_{Rk3Owren,ClassicalRungeKutta4,DormandPrince5,...}.cpp check the
+    convergence order with TimeStepperTestUtils: integrate y' = -y + cos t."""
+    def run(dt, nsteps):
+        y0 = np.array([1.0])
+        ev = orc.Evolution(lambda y, t: -y + np.cos(t), y0, 0.0, dt, name)
+        for _ in range(nsteps):
+            ev.step()
+        t = ev.time
+        exact = 0.5 * (np.exp(-t) + np.cos(t) + np.sin(t))
+        return abs(ev.u[0] - exact)
+    e1, e2 = run(0.1, 10), run(0.05, 20)
+    measured = np.log2(e1 / e2)
+    assert measured > order - 0.35, (e1, e2, measured)
