@@ -216,6 +216,9 @@ def main():
     ap.add_argument("--cpu-sample-refine", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--volume-variant", type=int, default=0,
+                    help="dgrhs_set_split_volume: 0 default, 1 split kernels, 2 pair-staged "
+                         "kernel for N >= 10 (A/B comparisons)")
     ap.add_argument("--verify", action="store_true",
                     help="multi-GPU: compare the gathered state bit-for-bit with a single-GPU "
                          "evolution of the same global problem on rank 0 (small configs)")
@@ -259,6 +262,8 @@ def main():
                              (0.1, 1.0) if args.gauge == "analytic" else (), local_rank, world,
                              rank, pg)
     ctx = ev.ctx
+    if args.volume_variant:
+        ctx.set_split_volume(args.volume_variant)
     stream = torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{local_rank}")
 
     def barrier():

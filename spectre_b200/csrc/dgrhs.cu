@@ -338,7 +338,8 @@ struct dgrhs_ctx {
   double* u_alt = nullptr;        // second state buffer for the fused update
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
-  bool split_volume = false;      // context + streaming kernels (opt-in, N <= 10)
+  int volume_variant = 0;         // 0 default, 1 context + streaming kernels (N <= 10),
+                                  // 2 DFMA pair-staged kernel also for N = 12
   bool fuse_update = true;        // fuse UpdateU into the volume kernel
   dg::UpdateArgs pending_upd{};   // filled by begin_substep when fusing
   bool upd_active = false;
@@ -383,7 +384,9 @@ int download(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
   return 0;
 }
 
+#ifndef DG_FOR_EACH_N  // (a build with -D'DG_FOR_EACH_N(X)=X(12)' compiles faster for experiments)
 #define DG_FOR_EACH_N(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+#endif
 
 template <int N>
 int launch_faces(dgrhs_ctx* c, int eb, int ee) {
@@ -464,7 +467,7 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
     dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
                     c->gH, c->gdH, c->D, c->coords, {}, eb, upd};
     if constexpr (dg::SCfg<N>::fits && N <= 10) {
-      if (c->split_volume) {
+      if (c->volume_variant == 1) {
         if (c->gauge == DGRHS_GAUGE_HARMONIC) return launch_gh_split<N, 0>(c, a, eb, ee);
         if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
           if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
@@ -474,6 +477,11 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
         }
         return launch_gh_split<N, 1>(c, a, eb, ee);
       }
+    }
+    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+      if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
+      const double* p = c->gauge_params;
+      a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
     }
     constexpr int smem = dg::gh_volume_smem_bytes<N>();
     if (c->gauge == DGRHS_GAUGE_HARMONIC) {
@@ -1077,7 +1085,8 @@ int dgrhs_exponential_filter_matrix(int N, double alpha, int half_power, double*
 
 int dgrhs_set_split_volume(dgrhs_ctx* c, int enable) {
   CHECK_CTX(c);
-  c->split_volume = enable != 0;
+  if (enable < 0 || enable > 2) return fail("volume variant must be 0, 1 or 2");
+  c->volume_variant = enable;
   return 0;
 }
 

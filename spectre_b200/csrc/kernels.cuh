@@ -114,6 +114,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // --------------------------------------------------------------------------
 // sum-factorised logical derivatives of one component at one point from a
 // shared-memory tile (K1: PartialDerivatives.tpp:316-363 without the
@@ -129,6 +133,33 @@ __device__ __forceinline__ void logical_derivs(const double* __restrict__ tc,
   const double* row = tc + N * (j + N * k);
   const double* col = tc + i + N * N * k;
   const double* pil = tc + i + N * j;
+  // N = 12: two partial sums per direction (even and odd m) halve the length of
+  // the dependent DFMA chains; measured 6.61 -> 6.38 ms per fused launch on the
+  // Kerr-Schild workload (4096 elements), but slower for N = 10 (3.24 -> 3.36 ms)
+  if constexpr (N >= 12 && N % 2 == 0) {
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, o0 = 0.0, o1 = 0.0, o2 = 0.0;
+    const double2* row2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+      const double2 v = row2[m];
+      e0 = fma(Di[2 * m], v.x, e0);
+      o0 = fma(Di[2 * m + 1], v.y, o0);
+    }
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+      e1 = fma(Dj[2 * m], col[N * (2 * m)], e1);
+      o1 = fma(Dj[2 * m + 1], col[N * (2 * m + 1)], o1);
+    }
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+      e2 = fma(Dk[2 * m], pil[N * N * (2 * m)], e2);
+      o2 = fma(Dk[2 * m + 1], pil[N * N * (2 * m + 1)], o2);
+    }
+    d[0] = e0 + o0;
+    d[1] = e1 + o1;
+    d[2] = e2 + o2;
+    return;
+  }
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   if constexpr (N % 2 == 0) {
     const double2* row2 = reinterpret_cast<const double2*>(row);
@@ -232,6 +263,62 @@ constexpr int gh_volume_smem_bytes() {
   return Cfg<N>::nstage * Cfg<N>::stage_doubles * 8 + Cfg<N>::fixed_bytes;
 }
 
+// Prologue of the GH volume kernels at one point: everything that needs all 50
+// components (3+1 geometry, normal contractions, gauge source, Q_{mu nu}); the
+// Jacobian is folded into the linear-coefficient context.  Q goes to shared
+// memory (sQ_pt[s * q_stride]).
+template <int N, int kGauge>
+__device__ __forceinline__ void gh_point_prologue(const GhVolArgs& a, int e, int pt,
+                                                  double* __restrict__ sQ_pt, int q_stride,
+                                                  GhContext& ctx) {
+  constexpr int npad = Cfg<N>::npad;
+  const double* __restrict__ ue = a.u + (size_t)e * 50 * npad;
+  double g[10], pi[10], phi[3][10], Q[10], ig[6];
+#pragma unroll
+  for (int s = 0; s < 10; ++s) {
+    g[s] = __ldg(ue + (size_t)s * npad + pt);
+    pi[s] = __ldg(ue + (size_t)(10 + s) * npad + pt);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad + pt);
+  }
+  const double* se = a.stat + (size_t)e * 3 * npad + pt;
+  const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad),
+               gamma2 = __ldg(se + 2 * npad);
+  GaugeH gh;
+  GaugeInput gin;
+  gin.fields = &gh;
+  if constexpr (kGauge == 2) {
+    gin.dh = a.dh;
+    const double* xe = a.coords + (size_t)e * 3 * npad + pt;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) gin.x[x] = __ldg(xe + (size_t)x * npad);
+  }
+  if constexpr (kGauge == 1) {
+    const double* he = a.gH + (size_t)e * 4 * npad + pt;
+    const double* dhe = a.gdH + (size_t)e * 16 * npad + pt;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      gh.H[x] = __ldg(he + (size_t)x * npad);
+#pragma unroll
+      for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
+    }
+  }
+  gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig);
+#pragma unroll
+  for (int s = 0; s < 10; ++s) sQ_pt[s * q_stride] = Q[s];
+  // the inverse Jacobian is fetched only now: keeping its 9 values out of
+  // the register-critical part of the prologue avoids spills
+  asm volatile("" ::: "memory");
+  double J[3][3];
+  const double* je = a.invjac + (size_t)e * 9 * npad + pt;
+#pragma unroll
+  for (int jh = 0; jh < 3; ++jh)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) J[jh][i] = __ldg(je + (size_t)(jh + 3 * i) * npad);
+  gh_context_set_jacobian(ctx, J, ig);
+}
+
 // kGauge: 0 Harmonic, 1 gauge fields from memory, 2 DampedHarmonic
 template <int N, int kGauge>
 __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kernel(GhVolArgs a) {
@@ -274,52 +361,7 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
 
   // ---- prologue: everything that needs all 50 components at the point ----
   GhContext ctx;
-  if (active) {
-    double g[10], pi[10], phi[3][10], Q[10], ig[6];
-#pragma unroll
-    for (int s = 0; s < 10; ++s) {
-      g[s] = __ldg(ue + (size_t)s * npad + pt);
-      pi[s] = __ldg(ue + (size_t)(10 + s) * npad + pt);
-#pragma unroll
-      for (int m = 0; m < 3; ++m)
-        phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad + pt);
-    }
-    const double* se = a.stat + (size_t)e * 3 * npad + pt;
-    const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad),
-                 gamma2 = __ldg(se + 2 * npad);
-    GaugeH gh;
-    GaugeInput gin;
-    gin.fields = &gh;
-    if constexpr (kGauge == 2) {
-      gin.dh = a.dh;
-      const double* xe = a.coords + (size_t)e * 3 * npad + pt;
-#pragma unroll
-      for (int x = 0; x < 3; ++x) gin.x[x] = __ldg(xe + (size_t)x * npad);
-    }
-    if constexpr (kGauge == 1) {
-      const double* he = a.gH + (size_t)e * 4 * npad + pt;
-      const double* dhe = a.gdH + (size_t)e * 16 * npad + pt;
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        gh.H[x] = __ldg(he + (size_t)x * npad);
-#pragma unroll
-        for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
-      }
-    }
-    gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig);
-#pragma unroll
-    for (int s = 0; s < 10; ++s) sQ[s * T + tid] = Q[s];
-    // the inverse Jacobian is fetched only now: keeping its 9 values out of
-    // the register-critical part of the prologue avoids spills
-    asm volatile("" ::: "memory");
-    double J[3][3];
-    const double* je = a.invjac + (size_t)e * 9 * npad + pt;
-#pragma unroll
-    for (int jh = 0; jh < 3; ++jh)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) J[jh][i] = __ldg(je + (size_t)(jh + 3 * i) * npad);
-    gh_context_set_jacobian(ctx, J, ig);
-  }
+  if (active) gh_point_prologue<N, kGauge>(a, e, pt, sQ + tid, T, ctx);
   __syncthreads();  // sD visible, barrier init visible to all waiters
 
   const int i = pt % N, j = (pt / N) % N, k = pt / (N * N);
@@ -476,10 +518,6 @@ struct SCfg {
   static constexpr bool fits = smem_bytes <= 232448;
   static constexpr int min_blocks = (2 * (smem_bytes + 1024) <= 233472) ? 2 : 1;
 };
-
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
 template <int N>
 __global__ void __launch_bounds__(SCfg<N>::T, SCfg<N>::min_blocks)

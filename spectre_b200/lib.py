@@ -293,8 +293,10 @@ class Context:
         _check(self._lib.dgrhs_set_exponential_filter(self._h, int(enable),
                                                       ctypes.c_double(alpha), half_power))
 
-    def set_split_volume(self, enable: bool):
-        _check(self._lib.dgrhs_set_split_volume(self._h, int(enable)))
+    def set_split_volume(self, variant):
+        """0 default kernels, 1 context + streaming kernels (N <= 10), 2 pair-staged
+        kernel also for N >= 10 (instead of the component-slot kernel)."""
+        _check(self._lib.dgrhs_set_split_volume(self._h, int(variant)))
 
     def set_fused_update(self, enable: bool):
         _check(self._lib.dgrhs_set_fused_update(self._h, int(enable)))
