@@ -186,6 +186,20 @@ int64_t dgrhs_rhs_evaluations(dgrhs_ctx* ctx);
  * *time the time at which the RHS must be evaluated; end_substep records the
  * derivative and updates u. is_step_done is set when a full step completed. */
 int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
+/* gh::BoundaryConditions::DemandOutgoingCharSpeeds on every external face
+ * without a ghost state (neighbor -1), GeneralizedHarmonic/BoundaryConditions/
+ * DemandOutgoingCharSpeeds.cpp:37-76 (applied by BoundaryConditionsImpl.hpp:
+ * 672-764 for Type::DemandOutgoingCharSpeeds): no boundary correction is added
+ * on such a face, and every RHS evaluation checks that the four characteristic
+ * speeds (gh::characteristic_speeds, Characteristics.cpp:24-40) with respect to
+ * the outward unit normal are non-negative at every face point.  The reference
+ * ERRORs at once; here the violation is latched on the device and
+ * dgrhs_check_outgoing_char_speeds returns non-zero (with the reference's
+ * message in dgrhs_last_error) at the caller's next check.  enable = 0 is the
+ * reference's `None`-like behaviour (no correction, no check). */
+int dgrhs_set_demand_outgoing_char_speeds(dgrhs_ctx* ctx, int enable);
+int dgrhs_check_outgoing_char_speeds(dgrhs_ctx* ctx, long long* n_violations,
+                                     double* min_speed);
 /* UpdateU (Time/Actions/UpdateU.hpp:82-89) is fused into the volume kernel by
  * default: u_new = a*u + sum_j c_j v_j, same coefficients and term order as the
  * separate update, written to a second state buffer that becomes the state at

@@ -849,23 +849,42 @@ static int face_index(int N, int d, int a, int b) {
  * metric, and the exterior normal is minus the interior UNIT normal covector
  * re-normalised with the exterior inverse spatial metric.
  */
-void orc_dg_rhs_bc(int system, int N, int nelem, const double* D, const double* u,
-                   const double* invjac, const double* static_fields,
-                   const double* coords, const int* nbr,
-                   const double* gauge_params, const double* ext_u, double* dt_u);
+void orc_dg_rhs_oriented(int system, int N, int nelem, const double* D, const double* u,
+                         const double* invjac, const double* static_fields,
+                         const double* coords, const int* nbr, const int* nbr_face,
+                         const double* gauge_params, const double* ext_u, double* dt_u);
 
 void orc_dg_rhs(int system, int N, int nelem, const double* D, const double* u,
                 const double* invjac, const double* static_fields,
                 const double* coords, const int* nbr,
                 const double* gauge_params, double* dt_u) {
-  orc_dg_rhs_bc(system, N, nelem, D, u, invjac, static_fields, coords, nbr, gauge_params,
-                NULL, dt_u);
+  orc_dg_rhs_oriented(system, N, nelem, D, u, invjac, static_fields, coords, nbr, NULL,
+                      gauge_params, NULL, dt_u);
 }
 
 void orc_dg_rhs_bc(int system, int N, int nelem, const double* D, const double* u,
                    const double* invjac, const double* static_fields,
                    const double* coords, const int* nbr,
                    const double* gauge_params, const double* ext_u, double* dt_u) {
+  orc_dg_rhs_oriented(system, N, nelem, D, u, invjac, static_fields, coords, nbr, NULL,
+                      gauge_params, ext_u, dt_u);
+}
+
+/*
+ * Non-aligned neighbours: the packaged data a neighbour sends are re-ordered
+ * into the receiver's frame before dg_boundary_terms is called
+ * (orient_variables_on_slice, Domain/Structure/OrientationMapHelpers.cpp:25-120;
+ * call site ComputeTimeDerivative.hpp:712-721).  All packaged fields are
+ * scalars or INERTIAL tensor components, so only the face-point index changes.
+ * nbr_face[e*6+d] = nd | (perm << 3): nd = the neighbour's direction touching
+ * this face; perm bit 0 = the two face coordinates are swapped, bit 1 / bit 2 =
+ * the neighbour's first / second face coordinate runs backwards.  NULL = aligned
+ * (nd = d ^ 1, perm = 0).
+ */
+void orc_dg_rhs_oriented(int system, int N, int nelem, const double* D, const double* u,
+                         const double* invjac, const double* static_fields,
+                         const double* coords, const int* nbr, const int* nbr_face,
+                         const double* gauge_params, const double* ext_u, double* dt_u) {
   const int n = N * N * N, f = N * N;
   const int C = system == 0 ? 5 : 50;
   const int PK = system == 0 ? 16 : 134;
@@ -932,7 +951,9 @@ void orc_dg_rhs_bc(int system, int N, int nelem, const double* D, const double* 
       for (int d = 0; d < 6; ++d) {
         const int ne = nbr[e * 6 + d];
         if (ne == -1 || (ne < -1 && ext_u == NULL)) continue;
-        const int dn = d ^ 1; /* neighbour's face pointing back at us */
+        /* neighbour's face pointing back at us, and the face-point permutation */
+        const int nf = (nbr_face && ne >= 0) ? nbr_face[e * 6 + d] : (d ^ 1);
+        const int dn = nf & 7, perm = nf >> 3;
         const double* pki = pk_all + ((size_t)e * 6 + d) * PK * f;
         const double* pke = ne >= 0 ? pk_all + ((size_t)ne * 6 + dn) * PK * f : NULL;
         const double* mag = mag_all + ((size_t)e * 6 + d) * f;
@@ -946,7 +967,11 @@ void orc_dg_rhs_bc(int system, int N, int nelem, const double* D, const double* 
             double in[134], ex[134], corr[50];
             for (int c = 0; c < PK; ++c) in[c] = pki[(size_t)c * f + q];
             if (ne >= 0) {
-              for (int c = 0; c < PK; ++c) ex[c] = pke[(size_t)c * f + q];
+              int na = (perm & 1) ? b : a, nb2 = (perm & 1) ? a : b;
+              if (perm & 2) na = N - 1 - na;
+              if (perm & 4) nb2 = N - 1 - nb2;
+              const int qn = na + N * nb2;
+              for (int c = 0; c < PK; ++c) ex[c] = pke[(size_t)c * f + qn];
             } else {
               /* ghost boundary condition: package the exterior state */
               const double* xu = ext_u + (size_t)(-(ne + 2)) * C * f;

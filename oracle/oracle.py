@@ -442,9 +442,12 @@ def gh_geometry(u):
 
 
 def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC, coords=None,
-           volume_only=False, ext_u=None):
+           volume_only=False, ext_u=None, nbr_dir=None, face_perm=None):
     """u [nelem, C, n]; returns dt_u of the same shape.  ext_u [nslots, C, f]:
-    exterior states of ghost boundary conditions (nbr <= -2 -> slot -(nbr+2))."""
+    exterior states of ghost boundary conditions (nbr <= -2 -> slot -(nbr+2)).
+    nbr_dir / face_perm [nelem, 6]: orientation of non-aligned neighbours (the
+    neighbour's direction touching the face and the face-point permutation code,
+    see orc_dg_rhs_oriented)."""
     nelem = u.shape[0]
     D = _c(differentiation_matrix(N))
     u, invjac, static_fields = _c(u), _c(invjac), _c(static_fields)
@@ -457,9 +460,54 @@ def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC
                             _p(coords), _p(gp), _p(dt))
     else:
         ext = _c(ext_u) if ext_u is not None else None
-        lib().orc_dg_rhs_bc(system, N, nelem, _p(D), _p(u), _p(invjac), _p(static_fields),
-                            _p(coords), _p(nbr), _p(gp), _p(ext), _p(dt))
+        nf = None
+        if nbr_dir is not None:
+            nf = np.ascontiguousarray(np.asarray(nbr_dir) | (np.asarray(face_perm) << 3),
+                                      dtype=np.int32)
+        lib().orc_dg_rhs_oriented(system, N, nelem, _p(D), _p(u), _p(invjac),
+                                  _p(static_fields), _p(coords), _p(nbr), _p(nf), _p(gp),
+                                  _p(ext), _p(dt))
     return dt
+
+
+def gh_characteristic_speeds(gamma1, lapse, shift, unit_normal_one_form):
+    """gh::characteristic_speeds without mesh velocity (GeneralizedHarmonic/
+    Characteristics.cpp:24-40): lambda(VSpacetimeMetric, VZero, VPlus, VMinus)."""
+    sdn = np.dot(shift, unit_normal_one_form)
+    return np.array([-(1.0 + gamma1) * sdn, -sdn, -sdn + lapse, -sdn - lapse])
+
+
+def demand_outgoing_char_speeds(N, u, invjac, gamma1, nbr):
+    """DemandOutgoingCharSpeeds::dg_demand_outgoing_char_speeds (GeneralizedHarmonic/
+    BoundaryConditions/DemandOutgoingCharSpeeds.cpp:37-76) on every face with
+    nbr == -1: returns (number of face points with an ingoing speed, most negative
+    speed).  Normal: NormalCovectorAndMagnitude.hpp:47-92."""
+    n_bad, worst = 0, 0.0
+    for e in range(u.shape[0]):
+        for d in range(6):
+            if nbr[e, d] != -1:
+                continue
+            dim, sign = d // 2, (1.0 if d % 2 else -1.0)
+            a, b = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+            fixed = N - 1 if d % 2 else 0
+            pts = ([fixed + N * (a + N * b), a + N * (fixed + N * b), a + N * (b + N * fixed)][dim]
+                   ).ravel()
+            geo = gh_geometry(u[e][:, pts])
+            for k, p in enumerate(pts):
+                unnorm = sign * np.array([invjac[e][dim + 3 * i][p] for i in range(3)])
+                ig = np.zeros((3, 3))
+                c = 0
+                for i in range(3):
+                    for j in range(i, 3):
+                        ig[i, j] = ig[j, i] = geo["inv_gamma"][c][k]
+                        c += 1
+                mag = np.sqrt(unnorm @ ig @ unnorm)
+                lam = gh_characteristic_speeds(gamma1[e][p], geo["lapse"][k],
+                                               geo["shift"][:, k], unnorm / mag)
+                if lam.min() < 0.0:
+                    n_bad += 1
+                    worst = min(worst, lam.min())
+    return n_bad, worst
 
 
 def analytic_christoffel_gauge(N, u_analytic, invjac):

@@ -338,6 +338,7 @@ struct dgrhs_ctx {
   double* u_alt = nullptr;        // second state buffer for the fused update
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
+  unsigned long long* violations = nullptr;  // DemandOutgoingCharSpeeds status (device)
   int volume_variant = 0;         // 0 default, 1 context + streaming kernels (N <= 10),
                                   // 2 DFMA pair-staged kernel also for N = 12
   bool fuse_update = true;        // fuse UpdateU into the volume kernel
@@ -409,7 +410,7 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
       return fail("element range must be [0, n_interior) or [n_interior, n_elements)");
   }
   dg::FaceArgs a{c->u,    c->invjac, c->stat, c->nbr, c->nbr_face, c->halo_recv,
-                 c->corr, c->nelem,  n_int,   pass};
+                 c->corr, c->nelem,  n_int,   pass,   c->violations};
   const long long total = (long long)c->nelem * 6 * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)
@@ -728,6 +729,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   for (double* p : c->dt_slots) cudaFree(p);
   if (c->nbr) cudaFree(c->nbr);
   if (c->nbr_face) cudaFree(c->nbr_face);
+  if (c->violations) cudaFree(c->violations);
   if (c->halo_map) cudaFree(c->halo_map);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1087,6 +1089,40 @@ int dgrhs_set_split_volume(dgrhs_ctx* c, int enable) {
   CHECK_CTX(c);
   if (enable < 0 || enable > 2) return fail("volume variant must be 0, 1 or 2");
   c->volume_variant = enable;
+  return 0;
+}
+
+int dgrhs_set_demand_outgoing_char_speeds(dgrhs_ctx* c, int enable) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (c->system != DGRHS_SYSTEM_GH)
+    return fail("DemandOutgoingCharSpeeds is a GeneralizedHarmonic boundary condition");
+  if (enable && !c->violations) {
+    CU(cudaMalloc(&c->violations, 2 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(c->violations, 0, 2 * sizeof(unsigned long long), c->stream));
+  } else if (!enable && c->violations) {
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->violations);
+    c->violations = nullptr;
+  }
+  return 0;
+}
+
+int dgrhs_check_outgoing_char_speeds(dgrhs_ctx* c, long long* n_violations,
+                                     double* min_speed) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (!c->violations) return fail("DemandOutgoingCharSpeeds is not enabled");
+  unsigned long long h[2];
+  CU(cudaMemcpyAsync(h, c->violations, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double mn = 0.0;
+  std::memcpy(&mn, &h[1], 8);
+  if (n_violations) *n_violations = (long long)h[0];
+  if (min_speed) *min_speed = h[0] ? mn : 0.0;
+  if (h[0])
+    return fail("DemandOutgoingCharSpeeds boundary condition violated at %llu face points, "
+                "most ingoing speed: %.17g", h[0], mn);
   return 0;
 }
 

@@ -825,7 +825,19 @@ struct FaceArgs {
   // below n_interior (+ external faces of those elements); 2 = the rest (incl.
   // ghost faces) -- used to overlap the halo exchange.
   int n_interior, pass;
+  // DemandOutgoingCharSpeeds on external faces without a ghost state (nbr = -1),
+  // GeneralizedHarmonic/BoundaryConditions/DemandOutgoingCharSpeeds.cpp:37-76:
+  // violations[0] counts face points where a characteristic speed (w.r.t. the
+  // outward unit normal) is negative, violations[1] holds the most negative
+  // speed seen (as a double).  nullptr = no check (BoundaryCondition `None`).
+  unsigned long long* violations;
 };
+
+// most negative value seen so far (doubles <= 0 only: their bit patterns order
+// in reverse as unsigned integers)
+__device__ __forceinline__ void atomic_min_negative(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
 
 // neighbour-side face coordinates of our face point (qa, qb)
 template <int N>
@@ -882,15 +894,32 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
       two_sided ? a.corr + (size_t)nb * 10 * 30 * f + (size_t)nd * 5 * f + qn : nullptr;
   const int dim_n = nd >> 1;
   const double sign_n = (nd & 1) ? 1.0 : -1.0;
+  const int p_own = face_point<N>(d, qa, qb);
+  const double* __restrict__ uo = a.u + (size_t)e * 50 * npad + p_own;
   if (nb == -1) {
+    // no boundary correction on this face (outflow)
 #pragma unroll 1
     for (int s = 0; s < 10; ++s)
 #pragma unroll
       for (int c = 0; c < 5; ++c) corr[((size_t)s * 30 + c) * f] = 0.0;
+    if (a.violations) {
+      double g[10], unn[3];
+      const double* jo = a.invjac + (size_t)e * 9 * npad + p_own;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
+#pragma unroll
+      for (int s = 0; s < 10; ++s) g[s] = __ldg(uo + (size_t)s * npad);
+      const double* so = a.stat + (size_t)e * 3 * npad + p_own;
+      GhFaceSide sd;
+      gh_face_side(g, unn, __ldg(so + npad), __ldg(so + 2 * npad), sd);
+      double mn = fmin(fmin(sd.speed[0], sd.speed[1]), fmin(sd.speed[2], sd.speed[3]));
+      if (mn < 0.0) {
+        atomicAdd(a.violations, 1ULL);
+        atomic_min_negative(a.violations + 1, mn);
+      }
+    }
     return;
   }
-  const int p_own = face_point<N>(d, qa, qb);
-  const double* __restrict__ uo = a.u + (size_t)e * 50 * npad + p_own;
   const double* __restrict__ un;  // neighbour values, component stride ns
   size_t ns;
   double unn_i[3], unn_e[3], g1e, g2e;

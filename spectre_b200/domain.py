@@ -1,5 +1,7 @@
 """Host-side domain data model for the DG path: a periodic/non-periodic Brick
-of 2^L elements per dimension, elements ordered along the per-block Z-curve
+of 2^L elements per dimension and the spherical shell of six Wedge blocks per
+radial layer (Domain/Creators/Sphere.cpp with an excised interior), elements
+ordered along the per-block Z-curve
 (Morton order) like the reference places them (Domain/Structure/ZCurve.cpp:
 17-80, DgElementArray.hpp:53-66), and the contiguous equal-cost partition of
 that order over ranks (ElementDistribution.hpp:33-47 with NumGridPoints
@@ -117,6 +119,222 @@ class Brick:
         return nb
 
 
+# ---------------------------------------------------------------------------
+# Wedge<3> (Domain/CoordinateMaps/Wedge.cpp:67-130 constructor constants,
+# :251-291 cap functions, :327-360 1/rho, :362-435 radial functions, :476-537
+# forward map) for a centred wedge with spherical inner and outer surfaces
+# (sphericity 1, no focal offset), and the six orientations of
+# orientations_for_sphere_wrappings (Domain/DomainHelpers.cpp:553-578).
+# ---------------------------------------------------------------------------
+# WEDGE_ORIENTATIONS[w][i] = (source dimension, sign): discrete_rotation
+# (Domain/Structure/OrientationMap.cpp:219-234) sets
+# new_coords[i] = sign * source_coords[dimension].
+WEDGE_ORIENTATIONS = (
+    ((0, 1), (1, 1), (2, 1)),     # upper z: aligned
+    ((0, 1), (1, -1), (2, -1)),   # lower z: (upper_xi, lower_eta, lower_zeta)
+    ((0, 1), (2, 1), (1, -1)),    # upper y: (upper_xi, upper_zeta, lower_eta)
+    ((0, 1), (2, -1), (1, 1)),    # lower y: (upper_xi, lower_zeta, upper_eta)
+    ((2, 1), (0, 1), (1, 1)),     # upper x: (upper_zeta, upper_xi, upper_eta)
+    ((2, -1), (0, -1), (1, 1)),   # lower x: (lower_zeta, lower_xi, upper_eta)
+)
+
+
+def wedge_map(xi, eta, zeta, r_in, r_out, wedge, equiangular=True, distribution="Linear"):
+    """Block-logical coordinates in [-1,1]^3 -> (x [3,...], jacobian [3,3,...])
+    with jacobian[i][j] = d x^i / d xi^j.  wedge: index into WEDGE_ORIENTATIONS
+    or an orientation ((dim, sign) x 3) itself."""
+    orientation = WEDGE_ORIENTATIONS[wedge] if isinstance(wedge, int) else wedge
+    xi, eta, zeta = (np.asarray(v, float) for v in (xi, eta, zeta))
+    if equiangular:
+        cap = [np.tan(0.25 * np.pi * xi), np.tan(0.25 * np.pi * eta)]
+        dcap = [0.25 * np.pi / np.cos(0.25 * np.pi * xi) ** 2,
+                0.25 * np.pi / np.cos(0.25 * np.pi * eta) ** 2]
+    else:
+        cap = [xi, eta]
+        dcap = [np.ones_like(xi), np.ones_like(eta)]
+    one_over_rho = 1.0 / np.sqrt(1.0 + cap[0] ** 2 + cap[1] ** 2)
+    if distribution == "Linear":
+        s = 0.5 * (r_out + r_in) + 0.5 * (r_out - r_in) * zeta
+        ds = 0.5 * (r_out - r_in) * np.ones_like(zeta)
+    elif distribution == "Logarithmic":
+        s = np.exp(0.5 * np.log(r_out * r_in) + 0.5 * np.log(r_out / r_in) * zeta)
+        ds = 0.5 * s * np.log(r_out / r_in)
+    elif distribution == "Inverse":
+        s = 2.0 / ((1.0 + zeta) / r_out + (1.0 - zeta) / r_in)
+        ds = 2.0 * (r_in * r_out ** 2 - r_in ** 2 * r_out) / \
+            (r_in + r_out + zeta * (r_in - r_out)) ** 2
+    else:
+        raise ValueError(f"unsupported radial distribution {distribution}")
+    z = s * one_over_rho                     # generalized z
+    # source frame: (polar, azimuth, radial) = z * (cap0, cap1, 1)
+    dz = [-s * one_over_rho ** 3 * cap[0] * dcap[0],
+          -s * one_over_rho ** 3 * cap[1] * dcap[1],
+          ds * one_over_rho]
+    src = [z * cap[0], z * cap[1], z]
+    dsrc = [[z * dcap[0] + cap[0] * dz[0], cap[0] * dz[1], cap[0] * dz[2]],
+            [cap[1] * dz[0], z * dcap[1] + cap[1] * dz[1], cap[1] * dz[2]],
+            [dz[0], dz[1], dz[2]]]
+    x, jac = [], []
+    for i in range(3):
+        dim, sign = orientation[i]
+        x.append(sign * src[dim])
+        jac.append([sign * dsrc[dim][j] for j in range(3)])
+    return np.array(x), np.array(jac)
+
+
+def _face_point_indices(N, d):
+    """Volume indices of the face points of direction d = 2 dim + side, in the
+    face's own ordering (first remaining dimension fastest)."""
+    dim, fixed = d // 2, (N - 1 if d % 2 else 0)
+    q = np.arange(N * N)
+    a, b = q % N, q // N
+    return [fixed + N * (a + N * b), a + N * (fixed + N * b), a + N * (b + N * fixed)][dim]
+
+
+def connectivity_from_geometry(coords, N, tol=1e-9):
+    """Neighbour table of a conforming multi-block mesh from the coincidence of
+    element faces: returns (neighbors, neighbor_direction, face_permutation),
+    each [n_elements, 6].  neighbors = -1 on external faces.  The permutation
+    code is the OrientationMap between the two blocks restricted to the face
+    (Domain/Structure/OrientationMapHelpers.cpp:25-120): bit 0 = the two face
+    coordinates are swapped, bit 1 / bit 2 = the neighbour's first / second face
+    coordinate runs backwards."""
+    from scipy.spatial import cKDTree
+    ne = coords.shape[0]
+    fp = [_face_point_indices(N, d) for d in range(6)]
+    centers = np.empty((ne * 6, 3))
+    for d in range(6):
+        centers[d::6] = coords[:, :, fp[d]].mean(axis=2)
+    scale = np.abs(coords).max()
+    tree = cKDTree(centers)
+    pairs = tree.query_pairs(tol * scale, output_type="ndarray")
+    nbr = np.full((ne, 6), -1, dtype=np.int32)
+    nd = np.tile((np.arange(6) ^ 1).astype(np.int32), (ne, 1))
+    perm = np.zeros((ne, 6), dtype=np.int32)
+    q = np.arange(N * N)
+    qa, qb = q % N, q // N
+    targets = []
+    for code in range(8):
+        na = np.where(code & 1, qb, qa)
+        nb = np.where(code & 1, qa, qb)
+        if code & 2:
+            na = N - 1 - na
+        if code & 4:
+            nb = N - 1 - nb
+        targets.append(na + N * nb)
+
+    def match(e, d, e2, d2):
+        mine = coords[e][:, fp[d]]
+        theirs = coords[e2][:, fp[d2]]
+        for code in range(8):
+            if np.max(np.abs(mine - theirs[:, targets[code]])) < tol * scale:
+                return code
+        raise ValueError(f"faces ({e},{d}) and ({e2},{d2}) coincide but their points do not")
+
+    for i, j in pairs:
+        e, d, e2, d2 = i // 6, i % 6, j // 6, j % 6
+        if nbr[e, d] != -1 or nbr[e2, d2] != -1:
+            raise ValueError("a face has more than one neighbour (non-conforming mesh)")
+        nbr[e, d], nd[e, d], perm[e, d] = e2, d2, match(e, d, e2, d2)
+        nbr[e2, d2], nd[e2, d2], perm[e2, d2] = e, d, match(e2, d2, e, d)
+    return nbr, nd, perm
+
+
+class SphericalShell:
+    """DomainCreator Sphere with an excised interior (Domain/Creators/Sphere.cpp,
+    `Interior: ExciseWithBoundaryCondition`): per radial layer six Wedge<3> blocks
+    (upper/lower z, y, x in the order of sph_wedge_coordinate_maps,
+    Domain/DomainHelpers.cpp:596-700), layers ordered inside-out, every block
+    refined to 2^L_angular x 2^L_angular x 2^L_radial elements."""
+
+    def __init__(self, inner_radius, outer_radius, refinement, N, radial_partitioning=(),
+                 radial_distribution="Logarithmic", equiangular=True):
+        """refinement: int or (angular, radial) initial refinement levels."""
+        if isinstance(refinement, int):
+            refinement = (refinement, refinement)
+        self.levels = (int(refinement[0]), int(refinement[0]), int(refinement[1]))
+        self.ne = tuple(2 ** r for r in self.levels)
+        self.N = int(N)
+        self.n = self.N ** 3
+        self.radii = [float(inner_radius), *map(float, radial_partitioning), float(outer_radius)]
+        self.n_layers = len(self.radii) - 1
+        if isinstance(radial_distribution, str):
+            radial_distribution = [radial_distribution] * self.n_layers
+        self.distributions = list(radial_distribution)
+        self.equiangular = bool(equiangular)
+        self.n_blocks = 6 * self.n_layers
+        nx, ny, nz = self.ne
+        cells = [(ix, iy, iz) for iz in range(nz) for iy in range(ny) for ix in range(nx)]
+        cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], self.levels))
+        self.block_cells = cells
+        self.cells = [(b, c) for b in range(self.n_blocks) for c in cells]  # element index
+        self.n_elements = len(self.cells)
+        self.xi, self.weights = lib.collocation_points_and_weights(self.N)
+        self._conn = None
+
+    def element_ids(self):
+        return [element_id(b, c, self.levels) for b, c in self.cells]
+
+    def _geometry(self, ids):
+        N, n = self.N, self.n
+        p = np.arange(n)
+        idx = (p % N, (p // N) % N, p // (N * N))
+        X = np.empty((len(ids), 3, n))
+        Jinv = np.empty((len(ids), 9, n))
+        for k, e in enumerate(ids):
+            b, cell = self.cells[e]
+            layer, wedge = b // 6, b % 6
+            blk, half = [], []
+            for d in range(3):
+                h = 2.0 / self.ne[d]
+                lo = -1.0 + h * cell[d]
+                blk.append(lo + 0.5 * h * (self.xi[idx[d]] + 1.0))
+                half.append(0.5 * h)
+            x, jac = wedge_map(blk[0], blk[1], blk[2], self.radii[layer], self.radii[layer + 1],
+                               wedge, self.equiangular, self.distributions[layer])
+            X[k] = x
+            for j in range(3):
+                jac[:, j] *= half[j]          # element logical -> block logical
+            inv = np.linalg.inv(np.moveaxis(jac, -1, 0))   # [n, jhat, i] = d xi^jhat / d x^i
+            for jh in range(3):
+                for i in range(3):
+                    Jinv[k, jh + 3 * i] = inv[:, jh, i]
+        return X, Jinv
+
+    def coords(self, ids=None):
+        ids = range(self.n_elements) if ids is None else ids
+        return self._geometry(list(ids))[0]
+
+    def inverse_jacobian(self, ids=None):
+        ids = range(self.n_elements) if ids is None else ids
+        return self._geometry(list(ids))[1]
+
+    def _connectivity(self):
+        # the topology does not depend on the polynomial order: match the faces of
+        # the 2-point (corner) mesh, whose 2 x 2 face points still tell the eight
+        # face permutations apart
+        if self._conn is None:
+            corners = SphericalShell(self.radii[0], self.radii[-1],
+                                     (self.levels[0], self.levels[2]), 2, self.radii[1:-1],
+                                     self.distributions, self.equiangular)
+            self._conn = connectivity_from_geometry(corners.coords(), 2)
+        return self._conn
+
+    def neighbors(self):
+        return self._connectivity()[0]
+
+    def neighbor_orientations(self):
+        """(neighbor_direction, face_permutation), see connectivity_from_geometry."""
+        c = self._connectivity()
+        return c[1], c[2]
+
+    def external_boundary(self, e, d):
+        """'inner' (excision) or 'outer' for an external face."""
+        b, cell = self.cells[e]
+        assert d // 2 == 2
+        return "inner" if d == 4 else "outer"
+
+
 class Partition:
     """Contiguous split of the (Z-curve ordered) element list over `world`
     ranks and the halo bookkeeping of one rank.
@@ -128,11 +346,19 @@ class Partition:
     """
 
     def __init__(self, neighbors: np.ndarray, world: int, rank: int,
-                 boundary_slots: bool = False):
-        """boundary_slots: give every external face (neighbour -1) of a local
-        element a ghost slot after the exchanged ones, to be filled with the
-        exterior state of a ghost boundary condition (DirichletAnalytic)."""
+                 boundary_slots=False, neighbor_direction=None, face_permutation=None):
+        """boundary_slots: give external faces (neighbour -1) of local elements a
+        ghost slot after the exchanged ones, to be filled with the exterior state
+        of a ghost boundary condition (DirichletAnalytic); True = every external
+        face, or a predicate (global element, direction) -> bool.
+        neighbor_direction / face_permutation [n_elements, 6]: orientation of
+        non-aligned neighbours (default: aligned, neighbour direction d ^ 1)."""
         ne = neighbors.shape[0]
+        if neighbor_direction is None:
+            neighbor_direction = np.tile((np.arange(6) ^ 1).astype(np.int32), (ne, 1))
+            face_permutation = np.zeros((ne, 6), dtype=np.int32)
+        self.oriented = bool((neighbor_direction != (np.arange(6) ^ 1)[None, :]).any()
+                             or face_permutation.any())
         bounds = [(ne * r) // world for r in range(world + 1)]
         owner = np.zeros(ne, dtype=np.int64)
         for r in range(world):
@@ -150,15 +376,20 @@ class Partition:
         # receive list: (peer, neighbour global element, neighbour direction, local e, d)
         recv = []
         local_nb = np.full((self.n_local, 6), -1, dtype=np.int32)
+        self.local_neighbor_direction = np.tile((np.arange(6) ^ 1).astype(np.int32),
+                                                (self.n_local, 1))
+        self.local_face_permutation = np.zeros((self.n_local, 6), dtype=np.int32)
         for le, g in enumerate(order):
             for d in range(6):
                 v = int(neighbors[g, d])
                 if v < 0:
                     continue
+                self.local_neighbor_direction[le, d] = neighbor_direction[g, d]
+                self.local_face_permutation[le, d] = face_permutation[g, d]
                 if owner[v] == rank:
                     local_nb[le, d] = g2l[v]
                 else:
-                    recv.append((int(owner[v]), v, d ^ 1, le, d))
+                    recv.append((int(owner[v]), v, int(neighbor_direction[g, d]), le, d))
         # canonical order shared by both sides: by (peer, global element of the
         # SENDER, sender direction)
         recv.sort(key=lambda t: (t[0], t[1], t[2]))
@@ -169,9 +400,10 @@ class Partition:
         self.n_recv = len(recv)
         self.external_faces = []  # (local element, direction, slot)
         if boundary_slots:
+            wanted = boundary_slots if callable(boundary_slots) else (lambda g, d: True)
             for le, g in enumerate(order):
                 for d in range(6):
-                    if int(neighbors[g, d]) == -1:
+                    if int(neighbors[g, d]) == -1 and wanted(int(g), d):
                         slot = self.n_recv + len(self.external_faces)
                         self.external_faces.append((le, d, slot))
                         local_nb[le, d] = -(slot + 2)

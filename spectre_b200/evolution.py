@@ -67,16 +67,24 @@ class Problem:
     the element subset a rank owns (global arrays would not fit at 8 GPUs)."""
 
     def __init__(self, system, brick, initial_data, static_values, dirichlet_analytic=False,
-                 analytic_christoffel_gauge=False):
-        """static_values: one number or one callable(x) -> array per static field.
+                 analytic_christoffel_gauge=False, demand_outgoing=None):
+        """brick: the domain (domain.Brick or domain.SphericalShell).
+        static_values: one number or one callable(x) -> array per static field.
         dirichlet_analytic: external faces get the analytic solution as exterior
-        state (DirichletAnalytic ghost boundary condition).
+        state (DirichletAnalytic ghost boundary condition); True = all of them, or
+        a predicate (global element, direction) -> bool.
+        demand_outgoing: DemandOutgoingCharSpeeds on the remaining external faces
+        (no correction, characteristic speeds checked); None = off.
         analytic_christoffel_gauge: AnalyticChristoffel gauge of the (static)
         analytic solution instead of the harmonic gauge."""
         self.system, self.brick, self.N = system, brick, brick.N
         self._initial_data, self._static_values = initial_data, static_values
         self.dirichlet_analytic = dirichlet_analytic
+        self.demand_outgoing = bool(demand_outgoing)
         self.analytic_christoffel_gauge = analytic_christoffel_gauge
+        # non-aligned neighbours (multi-block domains)
+        self.orientations = (brick.neighbor_orientations()
+                             if hasattr(brick, "neighbor_orientations") else (None, None))
         # a time-dependent analytic solution on the boundary is re-evaluated at the
         # time of every RHS (DirichletAnalytic.cpp:80-96 passes `time`)
         self.boundary_time_dependent = False
@@ -129,6 +137,34 @@ def gh_kerr_schild_problem(refinement, N, lower=(2.0, 2.0, 2.0), upper=(4.0, 4.0
                    dirichlet_analytic=True, analytic_christoffel_gauge=True)
 
 
+def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2.3,
+                                 radial_partitioning=(), mass=1.0,
+                                 inner_boundary="DirichletAnalytic",
+                                 radial_distribution="Logarithmic"):
+    """BASELINE.json configs[2]: Kerr-Schild black hole (M = 1, a = 0) on the
+    spherical shell of KerrSchild.yaml:80-98 (Sphere, InnerRadius 1.9, OuterRadius
+    2.3, equiangular wedges, Logarithmic radial distribution, excised interior),
+    DirichletAnalytic on the outer boundary and DirichletAnalytic (as in the input
+    file) or DemandOutgoingCharSpeeds (as in EvolveGhSingleBlackHole set-ups, the
+    excision surface lies inside the horizon) on the excision boundary,
+    AnalyticChristoffel gauge, GaussianPlusConstant damping (:108-125)."""
+    shell = domain.SphericalShell(inner_radius, outer_radius, refinement, N,
+                                  radial_partitioning, radial_distribution)
+    w = 11.313708499
+    gam = (lambda x: analytic.gaussian_plus_constant(x, 0.001, 3.0, w),
+           -1.0,
+           lambda x: analytic.gaussian_plus_constant(x, 0.001, 1.0, w))
+    if inner_boundary == "DirichletAnalytic":
+        ghost, outgoing = True, False
+    elif inner_boundary == "DemandOutgoingCharSpeeds":
+        ghost, outgoing = (lambda g, d: d == 5), True
+    else:
+        raise ValueError(inner_boundary)
+    return Problem(lib.SYSTEM_GH, shell, lambda x, t: analytic.kerr_schild(x, mass), gam,
+                   dirichlet_analytic=ghost, analytic_christoffel_gauge=True,
+                   demand_outgoing=outgoing)
+
+
 def gh_gauge_wave_dirichlet_problem(refinement, N, amplitude=0.1, wavelength=1.0,
                                     gammas=(1.0, -1.0, 1.0)):
     """Gauge wave on the Brick [0,1]^3 that is periodic in y and z only; the x
@@ -159,13 +195,20 @@ class Evolution:
         self.world, self.rank = world, rank
         self.problem = problem
         self.part = domain.Partition(problem.neighbors, world, rank,
-                                     boundary_slots=problem.dirichlet_analytic)
+                                     boundary_slots=problem.dirichlet_analytic,
+                                     neighbor_direction=problem.orientations[0],
+                                     face_permutation=problem.orientations[1])
         ids = self.part.global_ids
         self.ctx = lib.Context(problem.system, problem.N, self.part.n_local,
                                self.part.n_ghost, device)
         ctx = self.ctx
         ctx.set_geometry(problem.inverse_jacobian(ids), problem.coords(ids),
                          self.part.local_neighbors)
+        if self.part.oriented:
+            ctx.set_neighbor_orientations(self.part.local_neighbor_direction,
+                                          self.part.local_face_permutation)
+        if problem.demand_outgoing:
+            ctx.set_demand_outgoing_char_speeds(True)
         ctx.set_static_fields(problem.static(ids))
         if problem.system == lib.SYSTEM_GH and problem.analytic_christoffel_gauge:
             ctx.set_gauge_analytic_christoffel(problem.u0(ids, t0))

@@ -29,6 +29,7 @@ EXPORTS = [
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
     "dgrhs_take_steps", "dgrhs_time", "dgrhs_rhs_evaluations", "dgrhs_begin_substep",
     "dgrhs_end_substep", "dgrhs_set_exponential_filter", "dgrhs_exponential_filter_matrix",
+    "dgrhs_set_demand_outgoing_char_speeds", "dgrhs_check_outgoing_char_speeds",
     "dgrhs_set_fused_update", "dgrhs_set_split_volume", "dgrhs_time_kernels", "dgrhs_gh_constraint_norms",
     "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
@@ -292,6 +293,17 @@ class Context:
     def set_exponential_filter(self, enable: bool, alpha: float = 36.0, half_power: int = 64):
         _check(self._lib.dgrhs_set_exponential_filter(self._h, int(enable),
                                                       ctypes.c_double(alpha), half_power))
+
+    def set_demand_outgoing_char_speeds(self, enable=True):
+        _check(self._lib.dgrhs_set_demand_outgoing_char_speeds(self._h, int(enable)))
+
+    def check_outgoing_char_speeds(self):
+        """Raises DgrhsError if a DemandOutgoingCharSpeeds face saw an ingoing
+        characteristic speed since the check was enabled."""
+        n = ctypes.c_longlong(0)
+        mn = ctypes.c_double(0.0)
+        _check(self._lib.dgrhs_check_outgoing_char_speeds(self._h, ctypes.byref(n),
+                                                          ctypes.byref(mn)))
 
     def set_split_volume(self, variant):
         """0 default kernels, 1 context + streaming kernels (N <= 10), 2 pair-staged

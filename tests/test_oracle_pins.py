@@ -298,3 +298,15 @@ def test_stepper_convergence_order(name, order):
     e1, e2 = run(0.1, 10), run(0.05, 20)
     measured = np.log2(e1 / e2)
     assert measured > order - 0.35, (e1, e2, measured)
+
+
+def test_demand_outgoing_char_speeds_vs_reference_numpy(golden_dir):
+    """gh::characteristic_speeds and the DemandOutgoingCharSpeeds verdict against
+    fixtures made by importing the reference's DemandOutgoingCharSpeeds.py
+    (tests/golden/gen_demand_outgoing_golden.py)."""
+    z = np.load(os.path.join(golden_dir, "demand_outgoing.npz"))
+    for k in range(len(z["gamma1"])):
+        lam = orc.gh_characteristic_speeds(z["gamma1"][k], z["lapse"][k], z["shift"][k],
+                                           z["normal"][k])
+        np.testing.assert_allclose(lam, z["speeds"][k], rtol=1e-14, atol=1e-15)
+        assert (lam.min() < 0.0) == bool(z["violated"][k])

@@ -1,0 +1,181 @@
+"""Spherical-shell domain (Sphere creator with excision): the Wedge<3> map, the
+element geometry, the multi-block connectivity with non-aligned neighbours and
+the oracle's handling of orientations -- all on the CPU.
+
+Reference: Domain/CoordinateMaps/Wedge.cpp, Domain/DomainHelpers.cpp:553-578
+(orientations_for_sphere_wrappings), Domain/Creators/Sphere.cpp,
+Domain/Structure/OrientationMapHelpers.cpp:25-120; pins from
+tests/Unit/Domain/CoordinateMaps/Test_Wedge3D.cpp:175-283."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from spectre_b200 import analytic, domain
+
+# all_wedge_directions(), tests/Unit/Helpers/Domain/CoordinateMaps/TestMapHelpers.hpp:871-892
+TEST_WEDGE_DIRECTIONS = [
+    ((0, 1), (1, 1), (2, 1)), ((0, 1), (1, -1), (2, -1)),
+    ((1, 1), (2, 1), (0, 1)), ((1, 1), (2, -1), (0, -1)),
+    ((2, 1), (0, 1), (1, 1)), ((2, -1), (0, -1), (1, 1)),
+]
+
+
+@pytest.mark.parametrize("equiangular", [True, False])
+@pytest.mark.parametrize("distribution", ["Linear", "Logarithmic", "Inverse"])
+def test_wedge_alignment_known_answers(equiangular, distribution):
+    """test_wedge3d_alignment (Test_Wedge3D.cpp:175-283): where the logical axes
+    and the lowest corner of the six wedges land (inner radius sqrt 3, outer
+    radius 2 sqrt 3)."""
+    r3 = np.sqrt(3.0)
+
+    def m(w, p):
+        return domain.wedge_map(*p, r3, 2 * r3, TEST_WEDGE_DIRECTIONS[w], equiangular,
+                                distribution)[0]
+    lowest, ax, ae, az = (-1, -1, -1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)
+    # wedge: (component, value) reached along xi, eta, zeta; lowest physical corner
+    expected = {
+        0: ((0, 1.0), (1, 1.0), (2, 2.0), (-1, -1, 1)),     # upper zeta: +X, +Y, +Z
+        2: ((2, 1.0), (0, 1.0), (1, 2.0), (-1, 1, -1)),     # upper eta:  +Z, +X, +Y
+        4: ((1, 1.0), (2, 1.0), (0, 2.0), (1, -1, -1)),     # upper xi:   +Y, +Z, +X
+        1: ((0, 1.0), (1, -1.0), (2, -2.0), (-1, 1, -1)),   # lower zeta: +X, -Y, -Z
+        3: ((2, -1.0), (0, 1.0), (1, -2.0), (-1, -1, 1)),   # lower eta:  -Z, +X, -Y
+        5: ((1, -1.0), (2, 1.0), (0, -2.0), (-1, 1, -1)),   # lower xi:   -Y, +Z, -X
+    }
+    for w, (a, b, c, corner) in expected.items():
+        assert m(w, ax)[a[0]] == pytest.approx(a[1], abs=1e-13)
+        assert m(w, ae)[b[0]] == pytest.approx(b[1], abs=1e-13)
+        assert m(w, az)[c[0]] == pytest.approx(c[1], abs=1e-13)
+        np.testing.assert_allclose(m(w, lowest), corner, atol=1e-13)
+
+
+@pytest.mark.parametrize("distribution", ["Linear", "Logarithmic", "Inverse"])
+def test_wedge_jacobian_and_radii(distribution):
+    """The analytic Jacobian against centred differences (as test_jacobian /
+    test_inv_jacobian in TestMapHelpers.hpp do), and |x| = r(zeta) on spherical
+    wedges (test_wedge3d_random_radii, Test_Wedge3D.cpp:390-430)."""
+    rng = np.random.default_rng(5)
+    r_in, r_out = 1.7, 5.3
+    for w in range(6):
+        p = rng.uniform(-1, 1, 3)
+        x, jac = domain.wedge_map(*p, r_in, r_out, w, True, distribution)
+        h = 1e-6
+        for j in range(3):
+            dp = np.zeros(3)
+            dp[j] = h
+            xp = domain.wedge_map(*(p + dp), r_in, r_out, w, True, distribution)[0]
+            xm = domain.wedge_map(*(p - dp), r_in, r_out, w, True, distribution)[0]
+            np.testing.assert_allclose(jac[:, j], (xp - xm) / (2 * h), rtol=1e-8, atol=1e-8)
+        for zeta, r in ((-1.0, r_in), (1.0, r_out)):
+            x = domain.wedge_map(p[0], p[1], zeta, r_in, r_out, w, True, distribution)[0]
+            assert np.linalg.norm(x) == pytest.approx(r, rel=1e-14)
+        assert np.linalg.det(jac) > 0  # handedness is preserved by the six rotations
+
+
+def test_shell_geometry_and_connectivity():
+    """KerrSchild.yaml:80-98 (6 wedges, r in [1.9, 2.3]) refined once with two
+    layers: every angular face has exactly one neighbour, the radial ones are
+    the excision / outer boundary or the next layer, and the orientation table is
+    made of inverse pairs."""
+    N = 4
+    sh = domain.SphericalShell(1.9, 2.5, (1, 1), N, radial_partitioning=(2.2,))
+    assert sh.n_blocks == 12 and sh.n_elements == 12 * 8
+    x, J = sh.coords(), sh.inverse_jacobian()
+    r = np.sqrt((x ** 2).sum(axis=1))
+    assert r.min() == pytest.approx(1.9, rel=1e-14) and r.max() == pytest.approx(2.5, rel=1e-14)
+    nbr, nd, perm = sh.neighbors(), *sh.neighbor_orientations()
+    assert (nbr[:, :4] >= 0).all()
+    assert (nbr == -1).sum() == 2 * 6 * 4       # inner + outer sphere, 4 elements per wedge
+    assert (perm != 0).any() and (nd != (np.arange(6) ^ 1)[None, :]).any()
+    q = np.arange(N * N)
+    qa, qb = q % N, q // N
+
+    def point_map(code):
+        na, nb_ = np.where(code & 1, qb, qa), np.where(code & 1, qa, qb)
+        if code & 2:
+            na = N - 1 - na
+        if code & 4:
+            nb_ = N - 1 - nb_
+        return na + N * nb_
+    for e in range(sh.n_elements):
+        for d in range(6):
+            v = nbr[e, d]
+            if v < 0:
+                assert d >= 4
+                continue
+            assert nbr[v, nd[e, d]] == e and nd[v, nd[e, d]] == d
+            there = point_map(perm[e, d])
+            back = point_map(perm[v, nd[e, d]])
+            assert np.array_equal(back[there], q)
+            # the coordinates of matched face points coincide
+            mine = x[e][:, domain._face_point_indices(N, d)]
+            theirs = x[v][:, domain._face_point_indices(N, nd[e, d])][:, there]
+            np.testing.assert_allclose(mine, theirs, atol=1e-13)
+    # element ids: block index in the low byte, refinement levels per dimension
+    ids = sh.element_ids()
+    assert len(set(ids)) == sh.n_elements and (ids[8] & 0xFF) == 1
+    # the numerical derivative of the coordinates with the inverse Jacobian is the
+    # identity up to the truncation error of the (non-polynomial) map
+    errs = []
+    for Np in (4, 8):
+        shp = domain.SphericalShell(1.9, 2.5, (1, 1), Np, radial_partitioning=(2.2,))
+        xe, Je = shp.coords([3, 40]), shp.inverse_jacobian([3, 40])
+        err = 0.0
+        for k in range(2):
+            du = orc.partial_derivatives(Np, xe[k], Je[k])     # [3 comps][3 derivs][n]
+            du = np.asarray(du).reshape(3, 3, -1)
+            for c in range(3):
+                for i in range(3):
+                    err = max(err, np.max(np.abs(du[c, i] - (1.0 if c == i else 0.0))))
+        errs.append(err)
+    # spectral convergence: 1.2e-2 at N = 4, 8.2e-6 at N = 8
+    assert errs[0] < 5e-2 and errs[1] < 5e-5 and errs[1] < errs[0] * 2e-3
+
+
+def _rotated_problem():
+    from tests.test_gpu_orientation import _rotate_problem, _signed_perms
+    N = 3
+    rng = np.random.default_rng(12)
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N)
+    x, nbr = brick.coords(), brick.neighbors()
+    J = brick.inverse_jacobian() + 0.1 * rng.uniform(-1, 1, (brick.n_elements, 9, N ** 3))
+    u = analytic.gauge_wave(x, 0.1) + 1e-2 * rng.uniform(-1, 1, (brick.n_elements, 50, N ** 3))
+    stat = rng.uniform(-1, 1, (brick.n_elements, 3, N ** 3))
+    all48 = _signed_perms()
+    frames = [all48[k] for k in rng.choice(48, brick.n_elements, replace=False)]
+    return N, u, J, stat, nbr, _rotate_problem(N, u, J, stat, nbr, frames)
+
+
+def test_oracle_orientation_matches_aligned_mesh():
+    """orient_variables_on_slice in the oracle: the right-hand side on a mesh
+    whose elements carry random ones of the 48 cube orientations equals the
+    aligned one after mapping back (the data are inertial tensor components)."""
+    N, u, J, stat, nbr, (u_r, J_r, s_r, nbr_r, nd_r, perm_r, pm) = _rotated_problem()
+    ref = orc.dg_rhs(1, N, u, J, stat, nbr)
+    got_r = orc.dg_rhs(1, N, u_r, J_r, s_r, nbr_r, nbr_dir=nd_r, face_perm=perm_r)
+    got = np.empty_like(got_r)
+    for e in range(u.shape[0]):
+        got[e] = got_r[e][:, pm[e]]
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-13
+
+
+def test_partition_of_shell_keeps_orientations():
+    """Partition of a multi-block domain: ghost faces carry the neighbour's
+    direction and permutation, send and receive lists agree pairwise."""
+    sh = domain.SphericalShell(1.9, 2.3, (1, 0), 3)
+    nbr, (nd, perm) = sh.neighbors(), sh.neighbor_orientations()
+    world = 3
+    parts = [domain.Partition(nbr, world, r, boundary_slots=True, neighbor_direction=nd,
+                              face_permutation=perm) for r in range(world)]
+    assert sum(p.n_local for p in parts) == sh.n_elements
+    for r, p in enumerate(parts):
+        assert p.oriented
+        for peer in range(world):
+            assert p.recv_counts[peer] == parts[peer].send_counts[r]
+        for le, g in enumerate(p.global_ids):
+            for d in range(6):
+                if nbr[g, d] >= 0:
+                    assert p.local_neighbor_direction[le, d] == nd[g, d]
+                    assert p.local_face_permutation[le, d] == perm[g, d]
+                else:
+                    assert p.local_neighbors[le, d] <= -2   # DirichletAnalytic slot
+                    assert p.local_neighbor_direction[le, d] == d ^ 1
