@@ -187,16 +187,41 @@ def workload_config(args, world, cpu=False):
                        "(M=1, a=0) on a Brick lattice (elements of edge M/8 from x=2M), "
                        "DirichletAnalytic boundaries, AnalyticChristoffel gauge, "
                        "GaussianPlusConstant damping (KerrSchild.yaml), AB3, dt=2e-4",
+        "kerr-schild-shell": "BASELINE.json configs[2]/[3]: GeneralizedHarmonic Kerr-Schild "
+                             "(M=1, a=0) on the Sphere domain with excision (six equiangular "
+                             "wedges per layer, Logarithmic radial distribution, inner radius "
+                             "1.9 M, h-refined: 4^L angular x 2^Lr radial elements per wedge, "
+                             "the shell grows outwards with the GPU count and is cut at constant radius), "
+                             "DirichletAnalytic "
+                             "boundaries, AnalyticChristoffel gauge, GaussianPlusConstant "
+                             "damping (KerrSchild.yaml), AB3, dt=2e-4",
     }
+    workload = getattr(args, "workload", "gauge-wave")
+    if workload == "kerr-schild-shell":
+        lr = shell_radial_level(args, world)
+        n_el = 6 * 4 ** args.refine * 2 ** lr // world
+        ref = [args.refine, args.refine, lr]
+    else:
+        n_el = (2 ** args.refine) ** 3
     return {
-        "workload": names[getattr(args, "workload", "gauge-wave")],
-        "elements_per_gpu": (2 ** args.refine) ** 3, "refinement": ref,
+        "workload": names[workload],
+        "elements_per_gpu": n_el, "refinement": ref,
         "points_per_dim": args.points, "gauge": args.gauge, "stepper": "AdamsBashforth(3)",
         "parallelism": f"elements partitioned along the block Z-curve over {world} GPU(s), "
                        "mortar-face halo exchange (NCCL send/recv)",
         "cache": "inputs larger than L2 (state 0.84 GB + 3 history slots per GPU; no flush "
                  "needed)" if not cpu else "n/a (CPU arm)",
     }
+
+
+def shell_radial_level(args, world):
+    """Radial refinement level of the shell workload: 2^(refine+1) radial elements
+    on one GPU, doubled with the GPU count (weak scaling)."""
+    lr, w = args.refine + 1, world
+    while w > 1:
+        lr += 1
+        w //= 2
+    return lr
 
 
 def main():
@@ -209,7 +234,7 @@ def main():
     ap.add_argument("--points", type=int, default=8, help="LGL points per dimension (N = P+1)")
     ap.add_argument("--dt", type=float, default=2e-4)
     ap.add_argument("--gauge", default="harmonic", choices=["harmonic", "analytic"])
-    ap.add_argument("--workload", default="gauge-wave", choices=["gauge-wave", "kerr-schild"],
+    ap.add_argument("--workload", default="gauge-wave", choices=["gauge-wave", "kerr-schild", "kerr-schild-shell"],
                     help="gauge-wave: BASELINE configs[1] (default, the headline); kerr-schild: "
                          "configs[2]/[3] stand-in (Kerr-Schild on a Brick lattice with "
                          "DirichletAnalytic boundaries, AnalyticChristoffel gauge)")
@@ -247,7 +272,16 @@ def main():
         pg = dist.group.WORLD
     N = args.points
     refinement = weak_refinement(world, args.refine)
-    if args.workload == "kerr-schild":
+    if args.workload == "kerr-schild-shell":
+        # radial element ratio q such that elements are a quarter as deep as they are
+        # wide at every radius; the outer radius grows with the number of radial
+        # elements (4.1 M on one GPU, 868 M on eight for --refine 3)
+        lr = shell_radial_level(args, world)
+        q = 1.0 + 0.125 * np.pi / 2 ** args.refine
+        problem = evolution.gh_kerr_schild_shell_problem(
+            (args.refine, lr), N, inner_radius=1.9, outer_radius=1.9 * q ** (2 ** lr),
+            order="radial")
+    elif args.workload == "kerr-schild":
         # element size fixed (1/8 M per element edge), lattice grows with the GPU count
         ne = [2 ** r for r in refinement]
         problem = evolution.gh_kerr_schild_problem(
@@ -325,7 +359,7 @@ def main():
     peak, peak_src = peaks()
     # static per-point fields read by the volume kernel: 3 damping fields, +20
     # when the gauge source function comes from memory (G = 23)
-    G = 23 if (args.workload == "kerr-schild" or args.gauge == "analytic") else 3
+    G = 23 if (args.workload.startswith("kerr-schild") or args.gauge == "analytic") else 3
     kb = kernel_alg_bytes(N, n_static=G)
     kb["volume_update_fused"] = kb["volume"] + kb["update"]
     names = ["face", "volume", "update", "volume_update_fused"]

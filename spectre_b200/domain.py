@@ -205,9 +205,16 @@ def connectivity_from_geometry(coords, N, tol=1e-9):
     centers = np.empty((ne * 6, 3))
     for d in range(6):
         centers[d::6] = coords[:, :, fp[d]].mean(axis=2)
-    scale = np.abs(coords).max()
+    # coincident faces come in pairs: the nearest other face centre is the partner
+    # if it is closer than tol relative to the local length scale (the domain may
+    # span many orders of magnitude in radius)
     tree = cKDTree(centers)
-    pairs = tree.query_pairs(tol * scale, output_type="ndarray")
+    dist, idx = tree.query(centers, k=2)
+    me = np.arange(len(centers))
+    partner = np.where(idx[:, 0] == me, idx[:, 1], idx[:, 0])   # (self may come second)
+    local_scale = np.maximum(np.linalg.norm(centers, axis=1), 1e-300)
+    is_pair = dist[:, 1] < tol * local_scale
+    pairs = [(int(i), int(partner[i])) for i in np.nonzero(is_pair)[0] if i < partner[i]]
     nbr = np.full((ne, 6), -1, dtype=np.int32)
     nd = np.tile((np.arange(6) ^ 1).astype(np.int32), (ne, 1))
     perm = np.zeros((ne, 6), dtype=np.int32)
@@ -226,6 +233,7 @@ def connectivity_from_geometry(coords, N, tol=1e-9):
     def match(e, d, e2, d2):
         mine = coords[e][:, fp[d]]
         theirs = coords[e2][:, fp[d2]]
+        scale = np.abs(mine).max()
         for code in range(8):
             if np.max(np.abs(mine - theirs[:, targets[code]])) < tol * scale:
                 return code
@@ -233,7 +241,7 @@ def connectivity_from_geometry(coords, N, tol=1e-9):
 
     for i, j in pairs:
         e, d, e2, d2 = i // 6, i % 6, j // 6, j % 6
-        if nbr[e, d] != -1 or nbr[e2, d2] != -1:
+        if partner[j] != i or not is_pair[j]:
             raise ValueError("a face has more than one neighbour (non-conforming mesh)")
         nbr[e, d], nd[e, d], perm[e, d] = e2, d2, match(e, d, e2, d2)
         nbr[e2, d2], nd[e2, d2], perm[e2, d2] = e, d, match(e2, d2, e, d)
@@ -248,8 +256,13 @@ class SphericalShell:
     refined to 2^L_angular x 2^L_angular x 2^L_radial elements."""
 
     def __init__(self, inner_radius, outer_radius, refinement, N, radial_partitioning=(),
-                 radial_distribution="Logarithmic", equiangular=True):
-        """refinement: int or (angular, radial) initial refinement levels."""
+                 radial_distribution="Logarithmic", equiangular=True, order="block"):
+        """refinement: int or (angular, radial) initial refinement levels.
+        order: "block" = block-major, Z-curve inside a block (the reference's element
+        placement, ElementDistribution.hpp:33-47); "radial" = spherical layers of
+        elements inside-out (all six wedges of a radial index together, Z-curve in
+        the angular directions), so that a contiguous partition cuts the shell at
+        constant radius and the halo is 2 x 6 x 4^L faces per rank."""
         if isinstance(refinement, int):
             refinement = (refinement, refinement)
         self.levels = (int(refinement[0]), int(refinement[0]), int(refinement[1]))
@@ -268,6 +281,13 @@ class SphericalShell:
         cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], self.levels))
         self.block_cells = cells
         self.cells = [(b, c) for b in range(self.n_blocks) for c in cells]  # element index
+        if order == "radial":
+            self.cells.sort(key=lambda bc: ((bc[0] // 6) * nz + bc[1][2], bc[0] % 6,
+                                            z_curve_index(bc[1][0], bc[1][1], 0,
+                                                          (self.levels[0], self.levels[1], 0))))
+        elif order != "block":
+            raise ValueError(order)
+        self.order = order
         self.n_elements = len(self.cells)
         self.xi, self.weights = lib.collocation_points_and_weights(self.N)
         self._conn = None
@@ -316,7 +336,7 @@ class SphericalShell:
         if self._conn is None:
             corners = SphericalShell(self.radii[0], self.radii[-1],
                                      (self.levels[0], self.levels[2]), 2, self.radii[1:-1],
-                                     self.distributions, self.equiangular)
+                                     self.distributions, self.equiangular, self.order)
             self._conn = connectivity_from_geometry(corners.coords(), 2)
         return self._conn
 

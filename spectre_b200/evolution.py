@@ -140,7 +140,7 @@ def gh_kerr_schild_problem(refinement, N, lower=(2.0, 2.0, 2.0), upper=(4.0, 4.0
 def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2.3,
                                  radial_partitioning=(), mass=1.0,
                                  inner_boundary="DirichletAnalytic",
-                                 radial_distribution="Logarithmic"):
+                                 radial_distribution="Logarithmic", order="block"):
     """BASELINE.json configs[2]: Kerr-Schild black hole (M = 1, a = 0) on the
     spherical shell of KerrSchild.yaml:80-98 (Sphere, InnerRadius 1.9, OuterRadius
     2.3, equiangular wedges, Logarithmic radial distribution, excised interior),
@@ -149,7 +149,7 @@ def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2
     excision surface lies inside the horizon) on the excision boundary,
     AnalyticChristoffel gauge, GaussianPlusConstant damping (:108-125)."""
     shell = domain.SphericalShell(inner_radius, outer_radius, refinement, N,
-                                  radial_partitioning, radial_distribution)
+                                  radial_partitioning, radial_distribution, order=order)
     w = 11.313708499
     gam = (lambda x: analytic.gaussian_plus_constant(x, 0.001, 3.0, w),
            -1.0,

@@ -179,3 +179,19 @@ def test_partition_of_shell_keeps_orientations():
                 else:
                     assert p.local_neighbors[le, d] <= -2   # DirichletAnalytic slot
                     assert p.local_neighbor_direction[le, d] == d ^ 1
+
+
+def test_radial_element_order_cuts_the_shell_at_constant_radius():
+    """order="radial": a contiguous partition of the element list cuts the shell
+    into spherical layers; the halo of a rank is two spheres of element faces."""
+    sh = domain.SphericalShell(1.9, 30.0, (1, 3), 3, order="radial")
+    nbr, (nd, perm) = sh.neighbors(), sh.neighbor_orientations()
+    assert sorted(sh.cells) == sorted(domain.SphericalShell(1.9, 30.0, (1, 3), 3).cells)
+    world = 4
+    for r in range(world):
+        p = domain.Partition(nbr, world, r, boundary_slots=True, neighbor_direction=nd,
+                             face_permutation=perm)
+        assert p.n_local == 6 * 4 * 2
+        assert p.n_recv == (1 if r in (0, world - 1) else 2) * 6 * 4
+        radial = {sh.cells[g][1][2] for g in p.global_ids}
+        assert radial == {2 * r, 2 * r + 1}
