@@ -130,6 +130,7 @@ def weak_refinement(world, base):
 # ---------------------------------------------------------------------------
 def cpu_oracle_run(N, sample_refine, steps, warmup, dt, budget_s=25.0):
     from oracle import oracle as orc
+    orc.use_optimized_build()   # -O3 -march=native timing build (never used for parity)
     b = orc.Brick([0, 0, 0], [1, 1, 1], [sample_refine] * 3, N)
     x, J, nb = b.coords(), b.inverse_jacobian(), b.neighbors()
     u = np.stack([orc.gh_vars_from_metric(*orc.gauge_wave_metric(x[e], 0.0))
@@ -151,7 +152,8 @@ def cpu_oracle_run(N, sample_refine, steps, warmup, dt, budget_s=25.0):
     return {"value": pts * done / el, "unit": UNIT, "cores": int(orc.lib().orc_num_threads()),
             "kind": "port",
             "sample": f"{b.nelem} elements (refinement {sample_refine}), N={N}, {done} AB3 steps "
-                      f"in {el:.1f} s, oracle/dg_oracle.c + numpy update, OpenMP over elements",
+                      f"in {el:.1f} s, oracle/dg_oracle.c (gcc -O3 -march=native) + numpy update, "
+                      f"OpenMP over elements",
             "steps": done, "ms_per_step": 1e3 * el / done}
 
 

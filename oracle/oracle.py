@@ -24,14 +24,28 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
-def build(force: bool = False) -> str:
-    """Compile dg_oracle.c -> oracle/_build/liboracle.so (gcc, OpenMP)."""
-    out = os.path.join(_HERE, "_build", "liboracle.so")
+def build(force: bool = False, optimized: bool = False) -> str:
+    """Compile dg_oracle.c -> oracle/_build/liboracle.so (gcc, OpenMP).
+    optimized=False: the checker (-O2, no FMA contraction, so that the operation
+    order of the restatement is what the compiler emits); optimized=True: the
+    timing build of bench.py's CPU arm (-O3 -march=native) in
+    oracle/_build/liboracle_fast_<cpu>.so -- never used for parity."""
+    name = "liboracle.so"
+    if optimized:
+        # -march=native code must not travel to a different CPU: key it by the flags
+        import hashlib
+        try:
+            flags_line = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+        except (OSError, StopIteration):
+            flags_line = "unknown"
+        name = f"liboracle_fast_{hashlib.sha1(flags_line.encode()).hexdigest()[:10]}.so"
+    flags = ["-O3", "-march=native"] if optimized else ["-O2", "-ffp-contract=off"]
+    out = os.path.join(_HERE, "_build", name)
     src = os.path.join(_HERE, "dg_oracle.c")
     if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(
-            ["gcc", "-std=c11", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"]
+            ["gcc", "-std=c11", *flags, "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"]
         )
     return out
 
@@ -41,6 +55,14 @@ def lib():
     if _LIB is None:
         _LIB = ctypes.CDLL(build())
         _LIB.orc_num_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def use_optimized_build():
+    """Switch this process to the -O3 -march=native build (bench.py CPU arm only)."""
+    global _LIB
+    _LIB = ctypes.CDLL(build(optimized=True))
+    _LIB.orc_num_threads.restype = ctypes.c_int
     return _LIB
 
 

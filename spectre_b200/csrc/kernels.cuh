@@ -1204,7 +1204,7 @@ struct ConstraintArgs {
 template <int N>
 __global__ void __launch_bounds__(256) gh_constraints_kernel(ConstraintArgs a) {
   constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* tile = reinterpret_cast<double*>(smem_raw);  // [4][npad]
   double* sD = tile + 4 * npad;                        // [N*N]
   __shared__ double red[3][8];
