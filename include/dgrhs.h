@@ -186,6 +186,28 @@ int64_t dgrhs_rhs_evaluations(dgrhs_ctx* ctx);
  * *time the time at which the RHS must be evaluated; end_substep records the
  * derivative and updates u. is_step_done is set when a full step completed. */
 int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
+/* Non-conforming (h-refined, 2:1) mortars, aligned blocks, equal N on both sides.
+ * Faces on either side of such an interface carry DGRHS_NEIGHBOR_HANGING in the
+ * neighbor table of dgrhs_set_geometry (Element<3>::neighbors() holds several
+ * ids for that direction); the mortar table lists, per mortar (= fine face), the
+ * row {coarse element, its direction, fine element, its direction, size_a,
+ * size_b}: Spectral::MortarSize of the fine face inside the coarse face per face
+ * dimension (first remaining dimension first; 0 Full, 1 LowerHalf, 2 UpperHalf),
+ * i.e. dg::mortar_size(coarse, fine, dimension, orientation)
+ * (NumericalAlgorithms/DiscontinuousGalerkin/MortarHelpers.cpp:51-77).
+ * Semantics: InternalMortarDataImpl.hpp:230-320 (package on the face, then
+ * dg::project_to_mortar, MortarHelpers.hpp:74-98) and ApplyBoundaryCorrections.hpp:
+ * 797-1045 (dg_boundary_terms on the mortar, dg::project_from_mortar,
+ * MortarHelpers.hpp:100-129, lift_flux with the face normal magnitude,
+ * add_slice_to_data; the mortars of one coarse face are summed in table order).
+ * A context with mortars must hold both sides of every mortar (single rank). */
+#define DGRHS_NEIGHBOR_HANGING (-2147483647 - 1)
+int dgrhs_set_mortars(dgrhs_ctx* ctx, int n_mortars, const int32_t* mortars);
+/* Spectral::projection_matrix_parent_to_child (child_to_parent = 0; Projection.cpp:
+ * 279-362) / projection_matrix_child_to_parent (= 1; :57-262, operand not massive)
+ * for Legendre-Gauss-Lobatto meshes with n_points_1d points on both sides,
+ * row-major [target point][source point]. */
+int dgrhs_projection_matrix(int n_points_1d, int child_to_parent, int size, double* matrix);
 /* gh::BoundaryConditions::DemandOutgoingCharSpeeds on every external face
  * without a ghost state (neighbor -1), GeneralizedHarmonic/BoundaryConditions/
  * DemandOutgoingCharSpeeds.cpp:37-76 (applied by BoundaryConditionsImpl.hpp:

@@ -853,6 +853,12 @@ void orc_dg_rhs_oriented(int system, int N, int nelem, const double* D, const do
                          const double* invjac, const double* static_fields,
                          const double* coords, const int* nbr, const int* nbr_face,
                          const double* gauge_params, const double* ext_u, double* dt_u);
+void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const double* u,
+                        const double* invjac, const double* static_fields,
+                        const double* coords, const int* nbr, const int* nbr_face,
+                        const double* gauge_params, const double* ext_u, int n_mortars,
+                        const int* mortars, const double* P, const double* R,
+                        double* dt_u);
 
 void orc_dg_rhs(int system, int N, int nelem, const double* D, const double* u,
                 const double* invjac, const double* static_fields,
@@ -885,6 +891,35 @@ void orc_dg_rhs_oriented(int system, int N, int nelem, const double* D, const do
                          const double* invjac, const double* static_fields,
                          const double* coords, const int* nbr, const int* nbr_face,
                          const double* gauge_params, const double* ext_u, double* dt_u) {
+  orc_dg_rhs_mortars(system, N, nelem, D, u, invjac, static_fields, coords, nbr, nbr_face,
+                     gauge_params, ext_u, 0, NULL, NULL, NULL, dt_u);
+}
+
+/*
+ * Non-conforming (h-refined, 2:1) mortars.  A face whose neighbour table entry
+ * is ORC_HANGING is skipped by the conforming loop; its corrections come from
+ * the mortar table: row m = {coarse element, its direction, fine element, its
+ * direction, size_a, size_b} with the MortarSize of the fine face inside the
+ * coarse face per face dimension (0 Full, 1 LowerHalf, 2 UpperHalf;
+ * dg::mortar_size, MortarHelpers.cpp:51-77; blocks aligned).  The mortar mesh
+ * is the fine face.  Following InternalMortarDataImpl.hpp:230-320 and
+ * ApplyBoundaryCorrections.hpp:797-1045: each side packages on its own FACE; the
+ * coarse side's packaged data are interpolated to the mortar
+ * (project_to_mortar, projection_matrix_parent_to_child: P[size] row-major
+ * [child point][parent point]); dg_boundary_terms is evaluated on the mortar for
+ * both elements; the coarse element's correction is L2-projected back to its
+ * face (project_from_mortar, projection_matrix_child_to_parent: R[size]
+ * row-major [parent point][child point]); each side lifts with the normal
+ * magnitude on its own face (LiftFlux.hpp:57-61) and adds the slice.
+ */
+#define ORC_HANGING (-2147483647 - 1)
+
+void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const double* u,
+                        const double* invjac, const double* static_fields,
+                        const double* coords, const int* nbr, const int* nbr_face,
+                        const double* gauge_params, const double* ext_u, int n_mortars,
+                        const int* mortars, const double* P, const double* R,
+                        double* dt_u) {
   const int n = N * N * N, f = N * N;
   const int C = system == 0 ? 5 : 50;
   const int PK = system == 0 ? 16 : 134;
@@ -950,7 +985,7 @@ void orc_dg_rhs_oriented(int system, int N, int nelem, const double* D, const do
       double* dte = dt_u + (size_t)e * C * n;
       for (int d = 0; d < 6; ++d) {
         const int ne = nbr[e * 6 + d];
-        if (ne == -1 || (ne < -1 && ext_u == NULL)) continue;
+        if (ne == -1 || ne == ORC_HANGING || (ne < -1 && ext_u == NULL)) continue;
         /* neighbour's face pointing back at us, and the face-point permutation */
         const int nf = (nbr_face && ne >= 0) ? nbr_face[e * 6 + d] : (d ^ 1);
         const int dn = nf & 7, perm = nf >> 3;
@@ -1012,6 +1047,82 @@ void orc_dg_rhs_oriented(int system, int N, int nelem, const double* D, const do
           }
       }
     }
+  }
+  /* non-conforming mortars (serial: several mortars add to one coarse face) */
+  for (int m = 0; m < n_mortars; ++m) {
+    const int ec = mortars[6 * m], dc = mortars[6 * m + 1], ef = mortars[6 * m + 2],
+              df = mortars[6 * m + 3], sa = mortars[6 * m + 4], sb = mortars[6 * m + 5];
+    const double* Pa = P + (size_t)sa * N * N;
+    const double* Pb = P + (size_t)sb * N * N;
+    const double* Ra = R + (size_t)sa * N * N;
+    const double* Rb = R + (size_t)sb * N * N;
+    const double* pkC = pk_all + ((size_t)ec * 6 + dc) * PK * f;
+    const double* pkF = pk_all + ((size_t)ef * 6 + df) * PK * f;
+    const double* magC = mag_all + ((size_t)ec * 6 + dc) * f;
+    const double* magF = mag_all + ((size_t)ef * 6 + df) * f;
+    double* pkCm = (double*)malloc(sizeof(double) * (size_t)PK * f);
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)f);
+    double* corrC = (double*)malloc(sizeof(double) * (size_t)C * f);
+    /* project_to_mortar: apply_matrices, first face dimension then the second */
+    for (int c = 0; c < PK; ++c) {
+      for (int b = 0; b < N; ++b)
+        for (int a2 = 0; a2 < N; ++a2) {
+          double v = 0.0;
+          for (int a = 0; a < N; ++a) v += Pa[a2 * N + a] * pkC[(size_t)c * f + a + N * b];
+          tmp[a2 + N * b] = v;
+        }
+      for (int b2 = 0; b2 < N; ++b2)
+        for (int a2 = 0; a2 < N; ++a2) {
+          double v = 0.0;
+          for (int b = 0; b < N; ++b) v += Pb[b2 * N + b] * tmp[a2 + N * b];
+          pkCm[(size_t)c * f + a2 + N * b2] = v;
+        }
+    }
+    double* dtF = dt_u + (size_t)ef * C * n;
+    double* dtC = dt_u + (size_t)ec * C * n;
+    for (int b = 0; b < N; ++b)
+      for (int a = 0; a < N; ++a) {
+        const int q = a + N * b;
+        double pc[134], pf[134], corr[50];
+        for (int c = 0; c < PK; ++c) {
+          pc[c] = pkCm[(size_t)c * f + q];
+          pf[c] = pkF[(size_t)c * f + q];
+        }
+        /* the fine element: its face is the mortar */
+        if (system == 0)
+          sw_boundary_terms_point(pf, pc, corr);
+        else
+          gh_boundary_terms_point(pf, pc, corr);
+        const int p = face_index(N, df, a, b);
+        const double lift = -0.5 * (double)(N * (N - 1)) * magF[q];
+        for (int c = 0; c < C; ++c) dtF[(size_t)c * n + p] += corr[c] * lift;
+        /* the coarse element's correction on the mortar */
+        if (system == 0)
+          sw_boundary_terms_point(pc, pf, corr);
+        else
+          gh_boundary_terms_point(pc, pf, corr);
+        for (int c = 0; c < C; ++c) corrC[(size_t)c * f + q] = corr[c];
+      }
+    /* project_from_mortar, lift on the coarse face, add_slice_to_data */
+    for (int c = 0; c < C; ++c) {
+      for (int b2 = 0; b2 < N; ++b2)
+        for (int a = 0; a < N; ++a) {
+          double v = 0.0;
+          for (int a2 = 0; a2 < N; ++a2) v += Ra[a * N + a2] * corrC[(size_t)c * f + a2 + N * b2];
+          tmp[a + N * b2] = v;
+        }
+      for (int b = 0; b < N; ++b)
+        for (int a = 0; a < N; ++a) {
+          double v = 0.0;
+          for (int b2 = 0; b2 < N; ++b2) v += Rb[b * N + b2] * tmp[a + N * b2];
+          const int q = a + N * b;
+          const int p = face_index(N, dc, a, b);
+          dtC[(size_t)c * n + p] += v * (-0.5 * (double)(N * (N - 1)) * magC[q]);
+        }
+    }
+    free(pkCm);
+    free(tmp);
+    free(corrC);
   }
   free(pk_all);
   free(mag_all);

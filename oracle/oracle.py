@@ -464,12 +464,14 @@ def gh_geometry(u):
 
 
 def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC, coords=None,
-           volume_only=False, ext_u=None, nbr_dir=None, face_perm=None):
+           volume_only=False, ext_u=None, nbr_dir=None, face_perm=None, mortars=None):
     """u [nelem, C, n]; returns dt_u of the same shape.  ext_u [nslots, C, f]:
     exterior states of ghost boundary conditions (nbr <= -2 -> slot -(nbr+2)).
     nbr_dir / face_perm [nelem, 6]: orientation of non-aligned neighbours (the
     neighbour's direction touching the face and the face-point permutation code,
-    see orc_dg_rhs_oriented)."""
+    see orc_dg_rhs_oriented).  mortars [n, 6]: non-conforming (2:1) mortars
+    (coarse element, direction, fine element, direction, size_a, size_b); the
+    faces involved carry HANGING in nbr (see orc_dg_rhs_mortars)."""
     nelem = u.shape[0]
     D = _c(differentiation_matrix(N))
     u, invjac, static_fields = _c(u), _c(invjac), _c(static_fields)
@@ -486,9 +488,17 @@ def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC
         if nbr_dir is not None:
             nf = np.ascontiguousarray(np.asarray(nbr_dir) | (np.asarray(face_perm) << 3),
                                       dtype=np.int32)
-        lib().orc_dg_rhs_oriented(system, N, nelem, _p(D), _p(u), _p(invjac),
-                                  _p(static_fields), _p(coords), _p(nbr), _p(nf), _p(gp),
-                                  _p(ext), _p(dt))
+        nm, mt, P, R = 0, None, None, None
+        if mortars is not None and len(mortars):
+            mt = np.ascontiguousarray(mortars, dtype=np.int32)
+            nm = len(mt)
+            P = _c(np.stack([np.eye(N)] + [projection_matrix_parent_to_child(N, N, sz)
+                                           for sz in (MORTAR_LOWER_HALF, MORTAR_UPPER_HALF)]))
+            R = _c(np.stack([np.eye(N)] + [projection_matrix_child_to_parent(N, N, sz)
+                                           for sz in (MORTAR_LOWER_HALF, MORTAR_UPPER_HALF)]))
+        lib().orc_dg_rhs_mortars(system, N, nelem, _p(D), _p(u), _p(invjac),
+                                 _p(static_fields), _p(coords), _p(nbr), _p(nf), _p(gp),
+                                 _p(ext), nm, _p(mt), _p(P), _p(R), _p(dt))
     return dt
 
 
@@ -761,3 +771,84 @@ def gh_constraint_norms(N, u, invjac, H=None):
             c4 = np.einsum("ijk,jk...->i...", eps, dphi)
             sums[2] += np.sum(c4 * c4)
     return np.sqrt(sums / (nelem * n))
+
+
+# ---------------------------------------------------------------------------
+# Non-conforming mortars: NumericalAlgorithms/Spectral/Projection.cpp and
+# NumericalAlgorithms/DiscontinuousGalerkin/MortarHelpers.hpp:74-129.
+# ChildSize / MortarSize codes: 0 Full, 1 LowerHalf, 2 UpperHalf.
+# ---------------------------------------------------------------------------
+MORTAR_FULL, MORTAR_LOWER_HALF, MORTAR_UPPER_HALF = 0, 1, 2
+HANGING = -2 ** 31   # neighbour-table entry of a face that is handled by the mortar table
+
+
+def legendre_vandermonde(num_points):
+    """modal_to_nodal_matrix (Spectral.cpp:499-516): V_ij = P_j(x_i)."""
+    x, _ = lgl_points_and_weights(num_points)
+    V = np.zeros((num_points, num_points))
+    for j in range(num_points):
+        V[:, j] = np.polynomial.legendre.legval(x, [0.0] * j + [1.0])
+    return V
+
+
+def interpolation_matrix(num_points, targets):
+    """Spectral::interpolation_matrix (Spectral.cpp:625-680, Kopriva Alg. 32):
+    barycentric Lagrange interpolation from the LGL points to `targets`."""
+    x, _ = lgl_points_and_weights(num_points)
+    bw = barycentric_weights(x)
+    targets = np.atleast_1d(np.asarray(targets, float))
+    M = np.zeros((len(targets), num_points))
+    for k, t in enumerate(targets):
+        match = [j for j in range(num_points)
+                 if abs(t - x[j]) <= 1e-15 * max(1.0, abs(t), abs(x[j])) * 16]
+        if match:
+            M[k, match[0]] = 1.0
+            continue
+        row = bw / (t - x)
+        M[k] = row / row.sum()
+    return M
+
+
+def projection_matrix_parent_to_child(n_parent, n_child, size):
+    """Projection.cpp:279-362: interpolation from the parent's points to the
+    child's points mapped into the parent interval (x, (x+1)/2 or (x-1)/2)."""
+    xc, _ = lgl_points_and_weights(n_child)
+    t = {MORTAR_FULL: xc, MORTAR_UPPER_HALF: 0.5 * (xc + 1.0),
+         MORTAR_LOWER_HALF: 0.5 * (xc - 1.0)}[size]
+    return interpolation_matrix(n_parent, t)
+
+
+def _spectral_transformation(large_index, small_index):
+    """Projection.cpp:158-186: the (large, small) entry of the map from the
+    Legendre modes on the half interval to the modes on the whole interval."""
+    assert large_index >= small_index
+    result = 1.0
+    for i in range((large_index - small_index) // 2, 0, -1):
+        result = 1.0 - result * float(
+            (large_index + small_index + 3 - 2 * i) * (large_index + small_index + 2 - 2 * i) *
+            (large_index - small_index + 2 - 2 * i) * (large_index - small_index + 1 - 2 * i)) / \
+            float(2 * i * (2 * large_index + 1 - 2 * i) * (large_index + 2 - 2 * i) *
+                  (large_index + 1 - 2 * i))
+    for i in range(1, large_index - small_index + 1):
+        result *= 1.0 + float(large_index + small_index + 1) / i
+    result /= 2.0 ** (large_index + 1)
+    return result
+
+
+def projection_matrix_child_to_parent(n_child, n_parent, size):
+    """Projection.cpp:57-262 (operand not massive): the L2 projection from the
+    child (mortar) to the parent (element face), done in modal space."""
+    assert n_parent <= n_child
+    V_el = legendre_vandermonde(n_parent)
+    Vinv_mortar = np.linalg.inv(legendre_vandermonde(n_child))
+    if size == MORTAR_FULL:
+        # truncation of the modes
+        return V_el @ Vinv_mortar[:n_parent, :]
+    if size == MORTAR_UPPER_HALF:
+        temp = np.zeros((n_parent, n_parent))
+        for j in range(n_parent):
+            for k in range(j, n_parent):
+                temp[:, j] += V_el[:, k] * _spectral_transformation(k, j)
+        return temp @ Vinv_mortar[:n_parent, :]
+    upper = projection_matrix_child_to_parent(n_child, n_parent, MORTAR_UPPER_HALF)
+    return upper[::-1, ::-1].copy()

@@ -339,6 +339,12 @@ struct dgrhs_ctx {
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
   unsigned long long* violations = nullptr;  // DemandOutgoingCharSpeeds status (device)
+  // non-conforming mortars (dgrhs_set_mortars)
+  int n_mortar_faces = 0;
+  int32_t* mortar_faces = nullptr;   // [n_mortar_faces][4]
+  int32_t* mortar_table = nullptr;   // [n_mortars][4]
+  double* mortar_P = nullptr;        // [3][N*N]
+  double* mortar_R = nullptr;        // [3][N*N]
   int volume_variant = 0;         // 0 default, 1 context + streaming kernels (N <= 10),
                                   // 2 DFMA pair-staged kernel also for N = 12
   bool fuse_update = true;        // fuse UpdateU into the volume kernel
@@ -419,6 +425,25 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
     dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
   ++g_launches;
   CU(cudaGetLastError());
+  // non-conforming mortars: with the pass that covers the boundary elements (all
+  // mortars of a context are evaluated at once)
+  if (c->n_mortar_faces > 0 && pass != 1) {
+    dg::MortarArgs m{c->u, c->invjac, c->stat, c->corr, c->mortar_faces, c->mortar_table,
+                     c->mortar_P, c->mortar_R};
+    constexpr int msmem = dg::mortar_smem_bytes<N>();
+    constexpr int mT = (N * N + 31) / 32 * 32;
+    if (c->system == DGRHS_SYSTEM_GH) {
+      auto k = dg::mortar_kernel<N, 1>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+      k<<<c->n_mortar_faces, mT, msmem, c->stream>>>(m);
+    } else {
+      auto k = dg::mortar_kernel<N, 0>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+      k<<<c->n_mortar_faces, mT, msmem, c->stream>>>(m);
+    }
+    ++g_launches;
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -730,6 +755,10 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   if (c->nbr) cudaFree(c->nbr);
   if (c->nbr_face) cudaFree(c->nbr_face);
   if (c->violations) cudaFree(c->violations);
+  if (c->mortar_faces) cudaFree(c->mortar_faces);
+  if (c->mortar_table) cudaFree(c->mortar_table);
+  if (c->mortar_P) cudaFree(c->mortar_P);
+  if (c->mortar_R) cudaFree(c->mortar_R);
   if (c->halo_map) cudaFree(c->halo_map);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -743,6 +772,7 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   CU(cudaSetDevice(c->device));
   for (size_t i = 0; i < (size_t)c->nelem * 6; ++i) {
     const int v = neighbors[i];
+    if (v == DGRHS_NEIGHBOR_HANGING) continue;  // non-conforming face: dgrhs_set_mortars
     if (v >= c->nelem) return fail("neighbor index %d out of range", v);
     if (v <= -2 && -(v + 2) >= c->nghost) return fail("ghost face index out of range");
   }
@@ -765,9 +795,10 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   }
   CU(cudaMemcpy(c->nbr, neighbors, (size_t)c->nelem * 6 * 4, cudaMemcpyHostToDevice));
   c->nbr_host.assign(neighbors, neighbors + (size_t)c->nelem * 6);
-  // a new neighbour table resets the orientations to "aligned"
+  // a new neighbour table resets the orientations to "aligned" and drops the mortars
   if (c->nbr_face) cudaFree(c->nbr_face);
   c->nbr_face = nullptr;
+  c->n_mortar_faces = 0;
   return 0;
 }
 
@@ -791,7 +822,7 @@ int dgrhs_set_neighbor_orientations(dgrhs_ctx* c, const int32_t* neighbor_direct
         return fail("bad orientation at element %d direction %d", e, d);
       packed[k] = nd | (perm << 3);
       const int v = c->nbr_host[k];
-      if (v < 0) continue;
+      if (v < 0) continue;  // external, ghost or hanging
       // the neighbour must point back at us with the inverse face map
       const size_t kn = (size_t)v * 6 + nd;
       if (c->nbr_host[kn] != e || neighbor_direction[kn] != d)
@@ -810,6 +841,199 @@ int dgrhs_set_neighbor_orientations(dgrhs_ctx* c, const int32_t* neighbor_direct
   // with explicit orientations that check is replaced by the one above
   if (!c->nbr_face && dev_alloc(&c->nbr_face, packed.size())) return 1;
   CU(cudaMemcpy(c->nbr_face, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Non-conforming mortars: projection matrices (Spectral/Projection.cpp) and the
+// mortar table.  The matrices are computed independently of the reference's
+// closed forms: parent->child is barycentric interpolation at the child's LGL
+// points mapped into the parent interval; child->parent is the exact L2
+// projection V T V^-1 with T_kj = (2k+1)/2 int_child P_j(x_child) P_k(x) dx
+// evaluated with an (N+1)-point LGL rule on the child interval (exact: the
+// integrand has degree 2N-2).
+// ---------------------------------------------------------------------------
+namespace {
+double legendre_p(int k, double x) {
+  double pm2 = 1.0, pm1 = x;
+  if (k == 0) return 1.0;
+  if (k == 1) return x;
+  double pk = 0.0;
+  for (int j = 2; j <= k; ++j) {
+    pk = ((2.0 * j - 1.0) * x * pm1 - (j - 1.0) * pm2) / j;
+    pm2 = pm1;
+    pm1 = pk;
+  }
+  return pk;
+}
+
+void invert(std::vector<double> A, int N, std::vector<double>& inv) {
+  inv.assign((size_t)N * N, 0.0);
+  for (int i = 0; i < N; ++i) inv[(size_t)i * N + i] = 1.0;
+  for (int c = 0; c < N; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < N; ++r)
+      if (std::abs(A[(size_t)r * N + c]) > std::abs(A[(size_t)piv * N + c])) piv = r;
+    for (int k = 0; k < N; ++k) {
+      std::swap(A[(size_t)c * N + k], A[(size_t)piv * N + k]);
+      std::swap(inv[(size_t)c * N + k], inv[(size_t)piv * N + k]);
+    }
+    const double d = 1.0 / A[(size_t)c * N + c];
+    for (int k = 0; k < N; ++k) {
+      A[(size_t)c * N + k] *= d;
+      inv[(size_t)c * N + k] *= d;
+    }
+    for (int r = 0; r < N; ++r) {
+      if (r == c) continue;
+      const double fct = A[(size_t)r * N + c];
+      if (fct == 0.0) continue;
+      for (int k = 0; k < N; ++k) {
+        A[(size_t)r * N + k] -= fct * A[(size_t)c * N + k];
+        inv[(size_t)r * N + k] -= fct * inv[(size_t)c * N + k];
+      }
+    }
+  }
+}
+
+// size: 0 Full, 1 LowerHalf, 2 UpperHalf; same number of points on both meshes
+void projection_matrix(int N, bool child_to_parent, int size, std::vector<double>& M) {
+  M.assign((size_t)N * N, 0.0);
+  if (size == 0) {
+    for (int i = 0; i < N; ++i) M[(size_t)i * N + i] = 1.0;
+    return;
+  }
+  std::vector<double> x, w;
+  lgl(N, x, w);
+  const double shift = size == 2 ? 1.0 : -1.0;  // child point xc sits at (xc + shift) / 2
+  if (!child_to_parent) {
+    std::vector<double> bw(N, 1.0);
+    for (int j = 1; j < N; ++j)
+      for (int k = 0; k < j; ++k) {
+        bw[k] *= x[k] - x[j];
+        bw[j] *= x[j] - x[k];
+      }
+    for (int j = 0; j < N; ++j) bw[j] = 1.0 / bw[j];
+    for (int k = 0; k < N; ++k) {
+      const double t = 0.5 * (x[k] + shift);
+      int match = -1;
+      for (int j = 0; j < N; ++j)
+        if (std::abs(t - x[j]) < 1e-14) match = j;
+      if (match >= 0) {
+        M[(size_t)k * N + match] = 1.0;
+        continue;
+      }
+      double sum = 0.0;
+      for (int j = 0; j < N; ++j) {
+        M[(size_t)k * N + j] = bw[j] / (t - x[j]);
+        sum += M[(size_t)k * N + j];
+      }
+      for (int j = 0; j < N; ++j) M[(size_t)k * N + j] /= sum;
+    }
+    return;
+  }
+  std::vector<double> V((size_t)N * N), Vi, xq, wq;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) V[(size_t)i * N + j] = legendre_p(j, x[i]);
+  invert(V, N, Vi);
+  lgl(N + 1, xq, wq);
+  std::vector<double> T((size_t)N * N, 0.0);
+  for (int k = 0; k < N; ++k)
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      for (int q = 0; q <= N; ++q)  // child coordinate xq, parent coordinate (xq + shift)/2
+        s += 0.5 * wq[q] * legendre_p(j, xq[q]) * legendre_p(k, 0.5 * (xq[q] + shift));
+      T[(size_t)k * N + j] = 0.5 * (2.0 * k + 1.0) * s;
+    }
+  std::vector<double> VT((size_t)N * N, 0.0);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < N; ++k) s += V[(size_t)i * N + k] * T[(size_t)k * N + j];
+      VT[(size_t)i * N + j] = s;
+    }
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < N; ++k) s += VT[(size_t)i * N + k] * Vi[(size_t)k * N + j];
+      M[(size_t)i * N + j] = s;
+    }
+}
+}  // namespace
+
+int dgrhs_projection_matrix(int N, int child_to_parent, int size, double* matrix) {
+  if (N < 2 || N > 12) return fail("n_points_1d must be in [2, 12]");
+  if (size < 0 || size > 2) return fail("mortar size must be 0 (Full), 1 (LowerHalf) or 2 (UpperHalf)");
+  std::vector<double> M;
+  projection_matrix(N, child_to_parent != 0, size, M);
+  std::memcpy(matrix, M.data(), M.size() * 8);
+  return 0;
+}
+
+int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (c->nbr_host.empty()) return fail("call dgrhs_set_geometry first");
+  if (n_mortars < 0 || (n_mortars > 0 && !mortars)) return fail("bad mortar table");
+  // group the mortars by coarse face, keeping the caller's order inside a face
+  std::vector<int> order(n_mortars);
+  for (int m = 0; m < n_mortars; ++m) order[m] = m;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    const int32_t* a = mortars + 6 * (size_t)x;
+    const int32_t* b = mortars + 6 * (size_t)y;
+    return a[0] != b[0] ? a[0] < b[0] : a[1] < b[1];
+  });
+  std::vector<int32_t> faces, table;
+  std::vector<char> fine_seen((size_t)c->nelem * 6, 0);
+  for (int k = 0; k < n_mortars; ++k) {
+    const int32_t* m = mortars + 6 * (size_t)order[k];
+    const int ec = m[0], dc = m[1], ef = m[2], df = m[3], sa = m[4], sb = m[5];
+    if (ec < 0 || ec >= c->nelem || ef < 0 || ef >= c->nelem || dc < 0 || dc > 5 || df < 0 ||
+        df > 5)
+      return fail("mortar %d: element or direction out of range", order[k]);
+    if (df != (dc ^ 1))
+      return fail("mortar %d: only aligned blocks are supported (fine direction must be the "
+                  "opposite of the coarse direction)", order[k]);
+    if (sa < 0 || sa > 2 || sb < 0 || sb > 2 || (sa == 0 && sb == 0))
+      return fail("mortar %d: bad mortar size (%d, %d)", order[k], sa, sb);
+    if (c->nbr_host[(size_t)ec * 6 + dc] != DGRHS_NEIGHBOR_HANGING ||
+        c->nbr_host[(size_t)ef * 6 + df] != DGRHS_NEIGHBOR_HANGING)
+      return fail("mortar %d: both faces must be marked DGRHS_NEIGHBOR_HANGING in the "
+                  "neighbor table", order[k]);
+    if (fine_seen[(size_t)ef * 6 + df]++)
+      return fail("mortar %d: fine face listed twice", order[k]);
+    if (faces.empty() || faces[faces.size() - 4] != ec || faces[faces.size() - 3] != dc) {
+      faces.insert(faces.end(), {ec, dc, k, 0});
+    }
+    ++faces[faces.size() - 1];
+    table.insert(table.end(), {ef, df, sa, sb});
+  }
+  // every hanging face must be covered, or the volume kernel would add stale data
+  size_t hanging = 0;
+  for (int v : c->nbr_host) hanging += v == DGRHS_NEIGHBOR_HANGING;
+  if (hanging != faces.size() / 4 + (size_t)n_mortars)
+    return fail("%zu faces are marked hanging but the mortar table covers %zu", hanging,
+                faces.size() / 4 + (size_t)n_mortars);
+  if (c->mortar_faces) cudaFree(c->mortar_faces);
+  if (c->mortar_table) cudaFree(c->mortar_table);
+  c->mortar_faces = c->mortar_table = nullptr;
+  c->n_mortar_faces = (int)(faces.size() / 4);
+  if (n_mortars == 0) return 0;
+  CU(cudaMalloc(&c->mortar_faces, faces.size() * 4));
+  CU(cudaMalloc(&c->mortar_table, table.size() * 4));
+  CU(cudaMemcpy(c->mortar_faces, faces.data(), faces.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->mortar_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
+  const int N = c->N;
+  std::vector<double> P, R, M;
+  for (int size = 0; size < 3; ++size) {
+    projection_matrix(N, false, size, M);
+    P.insert(P.end(), M.begin(), M.end());
+    projection_matrix(N, true, size, M);
+    R.insert(R.end(), M.begin(), M.end());
+  }
+  if (!c->mortar_P && dev_alloc(&c->mortar_P, P.size())) return 1;
+  if (!c->mortar_R && dev_alloc(&c->mortar_R, R.size())) return 1;
+  CU(cudaMemcpy(c->mortar_P, P.data(), P.size() * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->mortar_R, R.data(), R.size() * 8, cudaMemcpyHostToDevice));
   return 0;
 }
 

@@ -839,6 +839,10 @@ __device__ __forceinline__ void atomic_min_negative(unsigned long long* addr, do
   atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
 
+// neighbour-table entry of a face that belongs to a non-conforming (2:1) mortar:
+// the face kernels skip it, mortar_kernel writes its corrections
+constexpr int32_t kHangingFace = INT32_MIN;
+
 // neighbour-side face coordinates of our face point (qa, qb)
 template <int N>
 __device__ __forceinline__ void orient_face_point(int perm, int qa, int qb, int& na,
@@ -880,6 +884,7 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
+  if (nb == kHangingFace) return;  // corrections come from mortar_kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
   int na_, nb_;
@@ -1007,6 +1012,7 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
+  if (nb == kHangingFace) return;  // corrections come from mortar_kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
   int na_, nb_;
@@ -1071,6 +1077,246 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
     const double lift_nb = -0.5 * (double)(N * (N - 1)) * me;
 #pragma unroll
     for (int c = 0; c < 5; ++c) corr_nb[(size_t)c * f] = c5[c] * lift_nb;
+  }
+}
+
+// --------------------------------------------------------------------------
+// Non-conforming (2:1 h-refined) mortars: one CTA per coarse face, one thread
+// per face / mortar point.  Reference data flow (InternalMortarDataImpl.hpp:
+// 230-320, ApplyBoundaryCorrections.hpp:797-1045, MortarHelpers.hpp:74-129):
+//   each side packages on its own face; the coarse side's packaged data (incl.
+//   the characteristic speeds and the n_i v^+- fields) are interpolated to the
+//   mortar = the fine neighbour's face (project_to_mortar: two 1-d passes with
+//   the parent->child matrices); dg_boundary_terms on the mortar for both
+//   elements; the fine element lifts on its face; the coarse element's
+//   correction is L2-projected back (project_from_mortar: child->parent
+//   matrices), lifted with |n| on the coarse face and summed over the mortars
+//   of the face in the order of the mortar table (deterministic).
+// ScalarWave runs through the same code as one "pair": with a flat unit normal
+// and the speeds (0, 0, 1, -1) gh_pair_package is ScalarWave's dg_package_data.
+// --------------------------------------------------------------------------
+struct MortarArgs {
+  const double* u;
+  const double* invjac;
+  const double* stat;
+  double* corr;
+  const int32_t* faces;    // [n_coarse_faces][4] = coarse element, direction, first mortar, count
+  const int32_t* mortars;  // [n_mortars][4]      = fine element, direction, size_a, size_b
+  const double* P;         // [3][N*N] parent->child, row-major [child point][parent point]
+  const double* R;         // [3][N*N] child->parent, row-major [parent point][child point]
+};
+
+// dg_boundary_terms of one pair from PACKAGED values (the n_i v^+- fields are
+// packaged fields of their own: on a mortar they are interpolated, not rebuilt)
+// pk: 0 v_g, 1 gamma2 v_g, 2 v_plus, 3 v_minus, 4-6 v_zero, 7-9 n v_plus, 10-12 n v_minus
+DG_HD void pair_boundary_terms_packaged(const double (&si)[4], const double (&ki)[13],
+                                        const double (&se)[4], const double (&ke)[13],
+                                        double (&c)[5]) {
+  const double w_g_i = step_function(-si[0]), w_g_e = -step_function(se[0]);
+  const double w_0_i = step_function(-si[1]), w_0_e = -step_function(se[1]);
+  const double w_p_i = step_function(-si[2]), w_p_e = -step_function(se[2]);
+  const double w_m_i = step_function(-si[3]), w_m_e = -step_function(se[3]);
+  c[0] = w_g_e * ke[0] - w_g_i * ki[0];
+  c[1] = 0.5 * (w_p_e * ke[2] + w_m_e * ke[3]) + w_g_e * ke[1] -
+         0.5 * (w_p_i * ki[2] + w_m_i * ki[3]) - w_g_i * ki[1];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    c[2 + d] = -0.5 * (w_m_e * ke[10 + d] - w_p_e * ke[7 + d]) + w_0_e * ke[4 + d] -
+               0.5 * (w_p_i * ki[7 + d] - w_m_i * ki[10 + d]) - w_0_i * ki[4 + d];
+}
+
+template <int N>
+constexpr int mortar_smem_bytes() {
+  return (6 + 17 + 17 + 5 + 5) * N * N * 8;
+}
+
+template <int N, int kSystem>
+__global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, T = (N * N + 31) / 32 * 32;
+  constexpr int C = kSystem == 1 ? 50 : 5, NP = kSystem == 1 ? 10 : 1;
+  constexpr int S = kSystem == 1 ? 3 : 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using Mat = double[N * N];
+  using Row = double[f];
+  Mat* sP = reinterpret_cast<Mat*>(smem_raw);  // [3]
+  Mat* sR = sP + 3;                            // [3]
+  Row* sA = reinterpret_cast<Row*>(sR + 3);    // [17] coarse packaged values (+ 4 speeds)
+  Row* sB = sA + 17;                           // [17] after the first interpolation pass
+  Row* sE = sB + 17;                           // [5]  coarse correction on the mortar
+  Row* sF = sE + 5;                            // [5]  after the first projection pass
+  const int tid = threadIdx.x;
+  const bool active = tid < f;
+  const int qa = tid % N, qb = active ? tid / N : 0;
+  const int32_t* fc = a.faces + 4 * blockIdx.x;
+  const int ec = fc[0], dc = fc[1], m0 = fc[2], nm = fc[3];
+  for (int i = tid; i < 3 * N * N; i += T) {
+    (&sP[0][0])[i] = a.P[i];
+    (&sR[0][0])[i] = a.R[i];
+  }
+
+  // one side of the interface at this thread's point of face d of element e
+  auto make_side = [&](int e, int d, int p, GhFaceSide& sd) {
+    const double sign = (d & 1) ? 1.0 : -1.0;
+    const int dim = d >> 1;
+    double unn[3];
+    const double* jo = a.invjac + (size_t)e * 9 * npad + p;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
+    const double* so = a.stat + (size_t)e * S * npad + p;
+    if constexpr (kSystem == 1) {
+      double g[10];
+      const double* uo = a.u + (size_t)e * C * npad + p;
+#pragma unroll
+      for (int s = 0; s < 10; ++s) g[s] = __ldg(uo + (size_t)s * npad);
+      gh_face_side(g, unn, __ldg(so + npad), __ldg(so + 2 * npad), sd);
+    } else {
+      // flat-space normalisation (NormalCovectorAndMagnitude.hpp:78-90), speeds
+      // lambda_psi = lambda_0 = 0, lambda_+- = +-1 (UpwindPenalty.cpp:60-75)
+      sd.mag = sqrt(unn[0] * unn[0] + unn[1] * unn[1] + unn[2] * unn[2]);
+      const double inv = 1.0 / sd.mag;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) sd.n_lo[x] = sd.n_up[x] = unn[x] * inv;
+      sd.gamma2 = __ldg(so);
+      sd.speed[0] = 0.0;
+      sd.speed[1] = 0.0;
+      sd.speed[2] = 1.0;
+      sd.speed[3] = -1.0;
+    }
+  };
+  // packaged values of pair s on one side
+  auto package = [&](const GhFaceSide& sd, int e, int p, int s, double (&pk)[13]) {
+    const double* uo = a.u + (size_t)e * C * npad + p;
+    double g, pi, ph[3];
+    if constexpr (kSystem == 1) {
+      g = __ldg(uo + (size_t)s * npad);
+      pi = __ldg(uo + (size_t)(10 + s) * npad);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) ph[m] = __ldg(uo + (size_t)(20 + m + 3 * s) * npad);
+    } else {
+      g = __ldg(uo);
+      pi = __ldg(uo + npad);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) ph[m] = __ldg(uo + (size_t)(2 + m) * npad);
+    }
+    GhPairPackaged k;
+    gh_pair_package(sd, g, pi, ph, k);
+    pk[0] = k.v_g;
+    pk[1] = k.g2_v_g;
+    pk[2] = k.v_plus;
+    pk[3] = k.v_minus;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      pk[4 + m] = k.v_zero[m];
+      pk[7 + m] = k.v_plus * sd.n_lo[m];
+      pk[10 + m] = k.v_minus * sd.n_lo[m];
+    }
+  };
+  auto corr_ptr = [&](int e, int s, int d) {
+    return kSystem == 1 ? a.corr + (size_t)e * 10 * 30 * f + (size_t)s * 30 * f + (size_t)d * 5 * f
+                        : a.corr + ((size_t)e * 6 + d) * 5 * f;
+  };
+
+  GhFaceSide sC;
+  const int pC = active ? face_point<N>(dc, qa, qb) : 0;
+  if (active) {
+    make_side(ec, dc, pC, sC);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) sA[13 + x][tid] = sC.speed[x];
+  }
+  const double liftC = active ? -0.5 * (double)(N * (N - 1)) * sC.mag : 0.0;
+  __syncthreads();
+
+#pragma unroll 1
+  for (int mi = 0; mi < nm; ++mi) {
+    const int32_t* mt = a.mortars + 4 * (m0 + mi);
+    const int ef = mt[0], df = mt[1], sa = mt[2], sb = mt[3];
+    const double* Pa = sP[sa];
+    const double* Pb = sP[sb];
+    const double* Ra = sR[sa];
+    const double* Rb = sR[sb];
+    GhFaceSide sFn;
+    const int pF = active ? face_point<N>(df, qa, qb) : 0;
+    if (active) make_side(ef, df, pF, sFn);
+    const double liftF = active ? -0.5 * (double)(N * (N - 1)) * sFn.mag : 0.0;
+    double spC[4] = {0.0, 0.0, 0.0, 0.0};  // coarse characteristic speeds on the mortar
+#pragma unroll 1
+    for (int s = 0; s < NP; ++s) {
+      const int c_lo = 0, c_hi = s == 0 ? 17 : 13;
+      if (active) {
+        double pk[13];
+        package(sC, ec, pC, s, pk);
+#pragma unroll
+        for (int c = 0; c < 13; ++c) sA[c][tid] = pk[c];
+      }
+      __syncthreads();
+      // project_to_mortar, first face dimension: thread = (a', b)
+      if (active) {
+        for (int c = c_lo; c < c_hi; ++c) {
+          double v = 0.0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) v += Pa[qa * N + m] * sA[c][m + N * qb];
+          sB[c][tid] = v;
+        }
+      }
+      __syncthreads();
+      double cF[5], cC[5];
+      if (active) {
+        // second face dimension: thread = (a', b')
+        double pkC[13];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) {
+          double v = 0.0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) v += Pb[qb * N + m] * sB[c][qa + N * m];
+          pkC[c] = v;
+        }
+        if (s == 0) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) v += Pb[qb * N + m] * sB[13 + x][qa + N * m];
+            spC[x] = v;
+          }
+        }
+        double pkF[13];
+        package(sFn, ef, pF, s, pkF);
+        pair_boundary_terms_packaged(sFn.speed, pkF, spC, pkC, cF);
+        pair_boundary_terms_packaged(spC, pkC, sFn.speed, pkF, cC);
+        double* cf = corr_ptr(ef, s, df) + tid;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          cf[(size_t)c * f] = cF[c] * liftF;
+          sE[c][tid] = cC[c];
+        }
+      }
+      __syncthreads();
+      // project_from_mortar, first face dimension: thread = (a, b')
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          double v = 0.0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) v += Ra[qa * N + m] * sE[c][m + N * qb];
+          sF[c][tid] = v;
+        }
+      }
+      __syncthreads();
+      if (active) {
+        double* cc = corr_ptr(ec, s, dc) + tid;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          double v = 0.0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) v += Rb[qb * N + m] * sF[c][qa + N * m];
+          v *= liftC;
+          if (mi == 0)
+            cc[(size_t)c * f] = v;
+          else
+            cc[(size_t)c * f] += v;
+        }
+      }
+    }
   }
 }
 

@@ -119,6 +119,139 @@ class Brick:
         return nb
 
 
+HANGING = -2 ** 31   # neighbour-table entry of a face handled by the mortar table
+MORTAR_FULL, MORTAR_LOWER_HALF, MORTAR_UPPER_HALF = 0, 1, 2
+
+
+class RefinedBrick:
+    """A Brick whose coarse cells (2^L per dimension) are individually h-refined
+    once (split into 2 x 2 x 2 children), as AMR or per-block `InitialRefinement`
+    differences produce: element faces between a coarse element and a refined
+    cell are non-conforming 2:1 mortars (dg::mortar_size, NumericalAlgorithms/
+    DiscontinuousGalerkin/MortarHelpers.cpp:51-77; Element<3>::neighbors() then
+    holds four neighbour ids for that direction, Domain/Structure/Neighbors.hpp).
+
+    neighbors(): [n_elements, 6] with HANGING on both sides of such faces;
+    mortars(): rows (coarse element, its direction, fine element, its direction,
+    size_a, size_b), the MortarSize of the fine face inside the coarse face per
+    face dimension (first remaining dimension first)."""
+
+    def __init__(self, lower, upper, refinement, N, refined_cells, periodic=(True, True, True)):
+        self.lower = np.asarray(lower, float)
+        self.upper = np.asarray(upper, float)
+        self.levels = tuple(int(r) for r in refinement)
+        self.ne = tuple(2 ** r for r in self.levels)
+        self.N = int(N)
+        self.n = self.N ** 3
+        self.periodic = tuple(periodic) if not isinstance(periodic, bool) else (periodic,) * 3
+        self.refined = {tuple(c) for c in refined_cells}
+        nx, ny, nz = self.ne
+        cells = [(ix, iy, iz) for iz in range(nz) for iy in range(ny) for ix in range(nx)]
+        cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], self.levels))
+        # element = (coarse cell, child or None); children in Z order
+        self.elements = []
+        for c in cells:
+            if c in self.refined:
+                for k in range(8):
+                    self.elements.append((c, (k & 1, (k >> 1) & 1, (k >> 2) & 1)))
+            else:
+                self.elements.append((c, None))
+        self.index_of = {el: i for i, el in enumerate(self.elements)}
+        self.n_elements = len(self.elements)
+        self.xi, self.weights = lib.collocation_points_and_weights(self.N)
+        self._tables = None
+
+    def element_ids(self):
+        out = []
+        for c, ch in self.elements:
+            if ch is None:
+                out.append(element_id(0, c, self.levels))
+            else:
+                out.append(element_id(0, [2 * c[d] + ch[d] for d in range(3)],
+                                      [l + 1 for l in self.levels]))
+        return out
+
+    def _bounds(self, el):
+        c, ch = el
+        h = (self.upper - self.lower) / np.asarray(self.ne)
+        lo = self.lower + h * np.asarray(c)
+        if ch is not None:
+            h = 0.5 * h
+            lo = lo + h * np.asarray(ch)
+        return lo, lo + h
+
+    def coords(self, ids=None):
+        N, n = self.N, self.n
+        ids = range(self.n_elements) if ids is None else ids
+        p = np.arange(n)
+        idx = (p % N, (p // N) % N, p // (N * N))
+        out = np.zeros((len(ids), 3, n))
+        for k, e in enumerate(ids):
+            lo, hi = self._bounds(self.elements[e])
+            for d in range(3):
+                out[k, d] = 0.5 * (hi[d] - lo[d]) * self.xi[idx[d]] + 0.5 * (hi[d] + lo[d])
+        return out
+
+    def inverse_jacobian(self, ids=None):
+        ids = range(self.n_elements) if ids is None else ids
+        out = np.zeros((len(ids), 9, self.n))
+        for k, e in enumerate(ids):
+            lo, hi = self._bounds(self.elements[e])
+            for d in range(3):
+                out[k, d + 3 * d] = 2.0 / (hi[d] - lo[d])
+        return out
+
+    def _build(self):
+        nb = np.full((self.n_elements, 6), -1, dtype=np.int64)
+        mortars = []
+        for e, (c, ch) in enumerate(self.elements):
+            for d in range(6):
+                dim, side = d // 2, d % 2
+                if ch is not None and ch[dim] != side:
+                    # sibling inside the same refined cell
+                    sib = list(ch)
+                    sib[dim] = side
+                    nb[e, d] = self.index_of[(c, tuple(sib))]
+                    continue
+                nc = list(c)
+                nc[dim] += 1 if side else -1
+                if nc[dim] < 0 or nc[dim] >= self.ne[dim]:
+                    if not self.periodic[dim]:
+                        continue
+                    nc[dim] %= self.ne[dim]
+                nc = tuple(nc)
+                if ch is None and nc not in self.refined:
+                    nb[e, d] = self.index_of[(nc, None)]
+                elif ch is not None and nc in self.refined:
+                    other = list(ch)
+                    other[dim] = 1 - side
+                    nb[e, d] = self.index_of[(nc, tuple(other))]
+                elif ch is not None:
+                    nb[e, d] = HANGING          # the coarse side lists the mortar
+                else:
+                    nb[e, d] = HANGING
+                    fd = [x for x in range(3) if x != dim]
+                    for kb in range(2):
+                        for ka in range(2):
+                            child = [0, 0, 0]
+                            child[dim] = 1 - side
+                            child[fd[0]], child[fd[1]] = ka, kb
+                            mortars.append((e, d, self.index_of[(nc, tuple(child))], d ^ 1,
+                                            MORTAR_UPPER_HALF if ka else MORTAR_LOWER_HALF,
+                                            MORTAR_UPPER_HALF if kb else MORTAR_LOWER_HALF))
+        self._tables = (nb.astype(np.int32), np.asarray(mortars, dtype=np.int32).reshape(-1, 6))
+
+    def neighbors(self):
+        if self._tables is None:
+            self._build()
+        return self._tables[0]
+
+    def mortars(self):
+        if self._tables is None:
+            self._build()
+        return self._tables[1]
+
+
 # ---------------------------------------------------------------------------
 # Wedge<3> (Domain/CoordinateMaps/Wedge.cpp:67-130 constructor constants,
 # :251-291 cap functions, :327-360 1/rho, :362-435 radial functions, :476-537

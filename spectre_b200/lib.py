@@ -30,6 +30,7 @@ EXPORTS = [
     "dgrhs_take_steps", "dgrhs_time", "dgrhs_rhs_evaluations", "dgrhs_begin_substep",
     "dgrhs_end_substep", "dgrhs_set_exponential_filter", "dgrhs_exponential_filter_matrix",
     "dgrhs_set_demand_outgoing_char_speeds", "dgrhs_check_outgoing_char_speeds",
+    "dgrhs_set_mortars", "dgrhs_projection_matrix",
     "dgrhs_set_fused_update", "dgrhs_set_split_volume", "dgrhs_time_kernels", "dgrhs_gh_constraint_norms",
     "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
@@ -40,6 +41,17 @@ EXPORTS = [
 ]
 
 _lib = None
+
+
+HANGING = -2 ** 31   # DGRHS_NEIGHBOR_HANGING
+
+
+def projection_matrix(N, child_to_parent, size):
+    """Spectral::projection_matrix_{parent_to_child,child_to_parent}; size 0 Full,
+    1 LowerHalf, 2 UpperHalf (host function, no GPU needed)."""
+    M = np.zeros((N, N))
+    _check(load().dgrhs_projection_matrix(N, int(child_to_parent), size, _ptr(M)))
+    return M
 
 
 class DgrhsError(RuntimeError):
@@ -293,6 +305,12 @@ class Context:
     def set_exponential_filter(self, enable: bool, alpha: float = 36.0, half_power: int = 64):
         _check(self._lib.dgrhs_set_exponential_filter(self._h, int(enable),
                                                       ctypes.c_double(alpha), half_power))
+
+    def set_mortars(self, mortars):
+        """[n, 6] rows (coarse element, direction, fine element, direction, size_a,
+        size_b); the faces involved carry HANGING in the neighbour table."""
+        m = np.ascontiguousarray(mortars, dtype=np.int32).reshape(-1, 6)
+        _check(self._lib.dgrhs_set_mortars(self._h, len(m), _ptr(m)))
 
     def set_demand_outgoing_char_speeds(self, enable=True):
         _check(self._lib.dgrhs_set_demand_outgoing_char_speeds(self._h, int(enable)))

@@ -1,0 +1,130 @@
+"""Non-conforming (2:1 h-refined) mortars on the GPU: mortar_kernel through the
+C-ABI against the oracle's restatement of InternalMortarDataImpl.hpp:230-320 /
+ApplyBoundaryCorrections.hpp:797-1045 (project_to_mortar, dg_boundary_terms on
+the mortar, project_from_mortar, lift, add)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from spectre_b200 import analytic, domain, lib
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+GH_BLOCKS = [slice(0, 10), slice(10, 20), slice(20, 50)]
+SW_BLOCKS = [slice(0, 1), slice(1, 2), slice(2, 5)]
+
+
+def _relerr(a, b, blocks):
+    return max(np.max(np.abs(a[:, s] - b[:, s])) / np.max(np.abs(b[:, s])) for s in blocks)
+
+
+def _setup(system, N, refined, periodic=True, seed=0):
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N, refined,
+                             periodic=(periodic,) * 3)
+    x, nb, mt = rb.coords(), rb.neighbors(), rb.mortars()
+    rng = np.random.default_rng(seed)
+    # a full, per-point perturbed inverse Jacobian (faces of neighbours need not
+    # see the same J: each side uses its own normal, as on a curved mesh)
+    J = rb.inverse_jacobian() + 0.05 * rng.uniform(-1, 1, (rb.n_elements, 9, N ** 3))
+    if system == "gh":
+        u = analytic.gauge_wave(x, 0.1) + 1e-2 * rng.uniform(-1, 1, (rb.n_elements, 50, N ** 3))
+        stat = rng.uniform(-1, 1, (rb.n_elements, 3, N ** 3))
+        sysid = lib.SYSTEM_GH
+    else:
+        u = analytic.plane_wave(x, 0.3) + 0.1 * rng.uniform(-1, 1, (rb.n_elements, 5, N ** 3))
+        stat = rng.uniform(0, 1, (rb.n_elements, 1, N ** 3))
+        sysid = lib.SYSTEM_SCALAR_WAVE
+    ctx = lib.Context(sysid, N, rb.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_mortars(mt)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u)
+    return rb, ctx, u, J, stat, nb, mt
+
+
+@pytest.mark.parametrize("system,N", [("sw", 2), ("sw", 4), ("sw", 7), ("gh", 3), ("gh", 6),
+                                      ("gh", 8), ("gh", 12)])
+def test_rhs_with_mortars_matches_oracle(system, N):
+    refined = [(0, 0, 0), (1, 1, 0)] if N < 12 else [(1, 0, 1)]
+    rb, ctx, u, J, stat, nb, mt = _setup(system, N, refined, seed=N)
+    assert len(mt) > 0
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    sid = 1 if system == "gh" else 0
+    ref = orc.dg_rhs(sid, N, u, J, stat, nb, mortars=mt)
+    blocks = GH_BLOCKS if system == "gh" else SW_BLOCKS
+    assert _relerr(got, ref, blocks) < TOL
+    # the mortars matter: dropping them changes the answer
+    nomortar = orc.dg_rhs(sid, N, u, J, stat, np.where(nb == domain.HANGING, -1, nb))
+    assert _relerr(nomortar, ref, blocks) > 1e-4
+    ctx.close()
+
+
+@pytest.mark.parametrize("system", ["sw", "gh"])
+def test_evolution_with_mortars(system):
+    N, dt = 4, 2e-4
+    rb, ctx, u, J, stat, nb, mt = _setup(system, N, [(1, 0, 0)], seed=3)
+    sid = 1 if system == "gh" else 0
+    ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 3, 0.0, dt)
+    ctx.take_steps(2)
+    ev = orc.Evolution(lambda v, t: orc.dg_rhs(sid, N, v, J, stat, nb, mortars=mt), u, 0.0, dt,
+                       "AB3")
+    ev.step()
+    ev.step()
+    assert ctx.rhs_evaluations == ev.rhs_evals
+    assert _relerr(ctx.get_state(), ev.u, GH_BLOCKS if system == "gh" else SW_BLOCKS) < TOL
+    ctx.close()
+
+
+def test_smooth_solution_sees_refinement_only_at_truncation_level():
+    """A resolved plane wave on the refined mesh: the right-hand side on the
+    coarse elements next to the refined cell differs from the conforming mesh's
+    only by the (small) interpolation error."""
+    N = 8
+    rb = domain.RefinedBrick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N, [(0, 0, 0)])
+    base = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    out = {}
+    for name, dom in (("refined", rb), ("base", base)):
+        x, J, nb = dom.coords(), dom.inverse_jacobian(), dom.neighbors()
+        ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, dom.n_elements)
+        ctx.set_geometry(J, x, nb)
+        if name == "refined":
+            ctx.set_mortars(dom.mortars())
+        ctx.set_static_fields(np.zeros((dom.n_elements, 1, N ** 3)))
+        ctx.set_state(analytic.plane_wave(x, 0.0))
+        ctx.compute_time_derivative(0.0)
+        out[name] = ctx.get_time_derivative()
+        ctx.close()
+    worst = 0.0
+    for e, (c, ch) in enumerate(rb.elements):
+        if ch is None:
+            worst = max(worst, np.max(np.abs(out["refined"][e] - out["base"][base.index_of[c]])))
+    # 4e-4 for 8 points per half wavelength-and-a-half; the right-hand side itself is O(1)
+    assert 0.0 < worst < 2e-3, worst
+
+
+def test_mortar_table_validation():
+    N = 3
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N, [(0, 0, 0)])
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, rb.n_elements)
+    with pytest.raises(lib.DgrhsError, match="call dgrhs_set_geometry first"):
+        ctx.set_mortars(rb.mortars())
+    ctx.set_geometry(rb.inverse_jacobian(), rb.coords(), rb.neighbors())
+    mt = rb.mortars().copy()
+    with pytest.raises(lib.DgrhsError, match="marked hanging but the mortar table covers"):
+        ctx.set_mortars(mt[:-1])
+    bad = mt.copy()
+    bad[0, 3] = bad[0, 1]
+    with pytest.raises(lib.DgrhsError, match="only aligned blocks"):
+        ctx.set_mortars(bad)
+    bad = mt.copy()
+    bad[0, 4] = 3
+    with pytest.raises(lib.DgrhsError, match="bad mortar size"):
+        ctx.set_mortars(bad)
+    bad = mt.copy()
+    bad[1, 2] = bad[0, 2]
+    with pytest.raises(lib.DgrhsError, match="listed twice"):
+        ctx.set_mortars(bad)
+    ctx.set_mortars(mt)
+    ctx.close()

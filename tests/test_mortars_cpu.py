@@ -1,0 +1,136 @@
+"""Non-conforming (2:1 h-refined) mortars on the CPU: the projection matrices of
+Spectral/Projection.cpp (oracle restatement of the reference's closed forms vs
+the library's independent computation), their defining properties as tested by
+tests/Unit/NumericalAlgorithms/Spectral/Test_Projection.cpp, and the oracle's
+mortar path (InternalMortarDataImpl.hpp:230-320, ApplyBoundaryCorrections.hpp:
+797-1045) on an h-refined Brick."""
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from spectre_b200 import analytic, domain, lib
+
+SIZES = (orc.MORTAR_LOWER_HALF, orc.MORTAR_UPPER_HALF)
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 8, 12])
+def test_projection_matrices(N):
+    x, w = orc.lgl_points_and_weights(N)
+    total = np.zeros((N, N))
+    for size in SIZES:
+        P = orc.projection_matrix_parent_to_child(N, N, size)
+        R = orc.projection_matrix_child_to_parent(N, N, size)
+        # the library computes both differently (barycentric formula; exact
+        # quadrature of the L2 projection instead of the closed-form recurrence)
+        np.testing.assert_allclose(lib.projection_matrix(N, False, size), P, atol=1e-13)
+        np.testing.assert_allclose(lib.projection_matrix(N, True, size), R, atol=2e-13)
+        # prolongation is exact for polynomials of the parent space
+        # (Test_Projection.cpp:140-165)
+        xc = 0.5 * (x + (1.0 if size == orc.MORTAR_UPPER_HALF else -1.0))
+        for k in range(N):
+            np.testing.assert_allclose(P @ x ** k, xc ** k, atol=1e-13)
+        # restriction is the L2 projection of (f on the child's half, 0 on the other
+        # half) onto the parent space: the error is orthogonal to every parent
+        # polynomial over the whole parent interval (Test_Projection.cpp:230-260)
+        rng = np.random.default_rng(N + size)
+        f_child = rng.uniform(-1, 1, N)
+        xg, wg = np.polynomial.legendre.leggauss(N + 1)
+        sgn = 1.0 if size == orc.MORTAR_UPPER_HALF else -1.0
+        x_here, x_other = 0.5 * (xg + sgn), 0.5 * (xg - sgn)   # parent coordinates
+        f_here = orc.interpolation_matrix(N, xg) @ f_child     # child nodal -> Gauss points
+        proj = R @ f_child
+        p_here = orc.interpolation_matrix(N, x_here) @ proj
+        p_other = orc.interpolation_matrix(N, x_other) @ proj
+        for k in range(N):
+            residual = np.sum(0.5 * wg * (f_here - p_here) * x_here ** k) + \
+                np.sum(0.5 * wg * (0.0 - p_other) * x_other ** k)
+            assert abs(residual) < 1e-12
+        total += R @ P
+    # restricting the prolongation of both halves gives the parent back
+    # (Test_Projection.cpp:395-442)
+    np.testing.assert_allclose(total, np.eye(N), atol=1e-12)
+    np.testing.assert_array_equal(lib.projection_matrix(N, True, orc.MORTAR_FULL), np.eye(N))
+    # lower and upper half are mirror images (Projection.cpp:246-253)
+    np.testing.assert_allclose(orc.projection_matrix_child_to_parent(N, N, 1),
+                               orc.projection_matrix_child_to_parent(N, N, 2)[::-1, ::-1])
+
+
+def _poly(x):
+    X, Y, Z = x[:, 0], x[:, 1], x[:, 2]
+    psi = 1 + X + 2 * Y ** 2 - Z ** 3 + X * Y * Z
+    pi = 0.5 - X ** 2 + Y * Z
+    phi = [1 + Y * Z, 4 * Y + X * Z, -3 * Z ** 2 + X * Y]
+    return np.stack([psi, pi] + phi, axis=1)
+
+
+def test_refined_brick_tables():
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], 3, [(0, 0, 0), (1, 1, 0)])
+    nb, mt = rb.neighbors(), rb.mortars()
+    assert rb.n_elements == 6 + 16 and len(set(rb.element_ids())) == rb.n_elements
+    coarse = Counter((m[0], m[1]) for m in mt)
+    fine = Counter((m[2], m[3]) for m in mt)
+    assert all(v == 4 for v in coarse.values()) and all(v == 1 for v in fine.values())
+    assert len(coarse) + len(fine) == (nb == domain.HANGING).sum()
+    x = rb.coords()
+    for ec, dc, ef, df, sa, sb in mt:
+        assert nb[ec, dc] == domain.HANGING and nb[ef, df] == domain.HANGING and df == dc ^ 1
+        # the fine face is the stated quarter of the coarse face
+        fc = x[ec][:, domain._face_point_indices(3, dc)]
+        ff = x[ef][:, domain._face_point_indices(3, df)]
+        fd = [d for d in range(3) if d != dc // 2]
+        for dim, size in zip(fd, (sa, sb)):
+            lo, hi = fc[dim].min(), fc[dim].max()
+            mid = 0.5 * (lo + hi)
+            want = (lo, mid) if size == domain.MORTAR_LOWER_HALF else (mid, hi)
+            assert ff[dim].min() == pytest.approx(want[0]) and ff[dim].max() == pytest.approx(want[1])
+    # conforming entries are symmetric
+    for e in range(rb.n_elements):
+        for d in range(6):
+            if nb[e, d] >= 0:
+                assert nb[nb[e, d], d ^ 1] == e
+
+
+@pytest.mark.parametrize("N", [3, 5])
+def test_oracle_mortars_consistency(N):
+    """(1) Continuous polynomial data of the element's own degree: projection to
+    the mortar is exact and every boundary correction vanishes.  (2) A jump that
+    is a polynomial on the coarse face: the coarse element's correction, projected
+    back from its four mortars, equals the conforming correction of an unrefined
+    mesh with the same face data (the L2 projection reproduces polynomials of
+    the parent space)."""
+    refined = [(0, 0, 0)]
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N, refined, periodic=(False,) * 3)
+    x, J, nb, mt = rb.coords(), rb.inverse_jacobian(), rb.neighbors(), rb.mortars()
+    stat = np.full((rb.n_elements, 1, N ** 3), 0.3)
+    u = _poly(x) if N >= 4 else _poly(x) * 0 + np.stack(
+        [1 + x[:, 0] + x[:, 1] * x[:, 2], 0.5 - x[:, 1], 1 + x[:, 2], 4 * x[:, 1],
+         x[:, 0] * x[:, 1]], axis=1)
+    full = orc.dg_rhs(0, N, u, J, stat, nb, mortars=mt)
+    vol = orc.dg_rhs(0, N, u, J, stat, nb, volume_only=True)
+    assert np.max(np.abs(full - vol)) < 1e-12
+    # (2) unrefined reference mesh; add a polynomial offset to every element that
+    # lies inside the coarse cell (0,0,0) -> a polynomial jump across its faces
+    base = domain.Brick([0, 0, 0], [1, 1, 1], [1, 1, 1], N, periodic=(False,) * 3)
+    xb, Jb, nbb = base.coords(), base.inverse_jacobian(), base.neighbors()
+    statb = np.full((base.n_elements, 1, N ** 3), 0.3)
+
+    def data(xx, inside):
+        v = np.stack([1 + xx[:, 0] + xx[:, 1] * xx[:, 2], 0.5 - xx[:, 1], 1 + xx[:, 2],
+                      4 * xx[:, 1], xx[:, 0] * xx[:, 1]], axis=1)
+        off = np.stack([0.3 + 0.2 * xx[:, 1], -0.1 + xx[:, 2] * 0.5, 0.2 * xx[:, 0],
+                        0.1 + 0.0 * xx[:, 0], -0.3 * xx[:, 1]], axis=1)
+        return v + off * inside[:, None, None]
+    in_ref = np.array([c == (0, 0, 0) for c, ch in rb.elements], float)
+    in_base = np.array([c == (0, 0, 0) for c in base.cells], float)
+    r_ref = orc.dg_rhs(0, N, data(x, in_ref), J, stat, nb, mortars=mt)
+    r_base = orc.dg_rhs(0, N, data(xb, in_base), Jb, statb, nbb)
+    # compare on the coarse neighbours of the refined cell (they exist in both meshes)
+    checked = 0
+    for e, (c, ch) in enumerate(rb.elements):
+        if ch is None and (nb[e] == domain.HANGING).any():
+            eb = base.index_of[c]
+            np.testing.assert_allclose(r_ref[e], r_base[eb], atol=1e-11)
+            checked += 1
+    assert checked == 3
