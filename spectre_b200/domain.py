@@ -385,39 +385,55 @@ class SphericalShell:
     """DomainCreator Sphere with an excised interior (Domain/Creators/Sphere.cpp,
     `Interior: ExciseWithBoundaryCondition`): per radial layer six Wedge<3> blocks
     (upper/lower z, y, x in the order of sph_wedge_coordinate_maps,
-    Domain/DomainHelpers.cpp:596-700), layers ordered inside-out, every block
-    refined to 2^L_angular x 2^L_angular x 2^L_radial elements."""
+    Domain/DomainHelpers.cpp:596-700), layers ordered inside-out, every block of a
+    layer refined to 2^L_angular x 2^L_angular x 2^L_radial elements.  The
+    refinement may differ from layer to layer by one angular level (the creator's
+    per-block `InitialRefinement`): the spherical interface between such layers
+    is made of non-conforming 2:1 mortars (neighbors() = HANGING, mortars())."""
 
     def __init__(self, inner_radius, outer_radius, refinement, N, radial_partitioning=(),
                  radial_distribution="Logarithmic", equiangular=True, order="block"):
-        """refinement: int or (angular, radial) initial refinement levels.
+        """refinement: int, (angular, radial) initial refinement levels, or a list of
+        (angular, radial) per layer.
         order: "block" = block-major, Z-curve inside a block (the reference's element
         placement, ElementDistribution.hpp:33-47); "radial" = spherical layers of
         elements inside-out (all six wedges of a radial index together, Z-curve in
         the angular directions), so that a contiguous partition cuts the shell at
         constant radius and the halo is 2 x 6 x 4^L faces per rank."""
-        if isinstance(refinement, int):
-            refinement = (refinement, refinement)
-        self.levels = (int(refinement[0]), int(refinement[0]), int(refinement[1]))
-        self.ne = tuple(2 ** r for r in self.levels)
         self.N = int(N)
         self.n = self.N ** 3
         self.radii = [float(inner_radius), *map(float, radial_partitioning), float(outer_radius)]
         self.n_layers = len(self.radii) - 1
+        if isinstance(refinement, int):
+            refinement = (refinement, refinement)
+        if not isinstance(refinement[0], (tuple, list)):
+            refinement = [tuple(refinement)] * self.n_layers
+        assert len(refinement) == self.n_layers
+        self.refinement = [(int(r[0]), int(r[1])) for r in refinement]
+        self.layer_levels = [(r[0], r[0], r[1]) for r in self.refinement]
+        self.levels = self.layer_levels[0]
+        self.ne = tuple(2 ** r for r in self.levels)
         if isinstance(radial_distribution, str):
             radial_distribution = [radial_distribution] * self.n_layers
         self.distributions = list(radial_distribution)
         self.equiangular = bool(equiangular)
         self.n_blocks = 6 * self.n_layers
-        nx, ny, nz = self.ne
-        cells = [(ix, iy, iz) for iz in range(nz) for iy in range(ny) for ix in range(nx)]
-        cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], self.levels))
-        self.block_cells = cells
-        self.cells = [(b, c) for b in range(self.n_blocks) for c in cells]  # element index
+        self.cells = []  # element index -> (block, cell)
+        radial_offset, off = [], 0
+        for layer, lev in enumerate(self.layer_levels):
+            nx, ny, nz = (2 ** l for l in lev)
+            cells = [(ix, iy, iz) for iz in range(nz) for iy in range(ny) for ix in range(nx)]
+            cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], lev))
+            for w in range(6):
+                self.cells += [(6 * layer + w, c) for c in cells]
+            radial_offset.append(off)
+            off += nz
         if order == "radial":
-            self.cells.sort(key=lambda bc: ((bc[0] // 6) * nz + bc[1][2], bc[0] % 6,
-                                            z_curve_index(bc[1][0], bc[1][1], 0,
-                                                          (self.levels[0], self.levels[1], 0))))
+            self.cells.sort(key=lambda bc: (
+                radial_offset[bc[0] // 6] + bc[1][2], bc[0] % 6,
+                z_curve_index(bc[1][0], bc[1][1], 0,
+                              (self.layer_levels[bc[0] // 6][0], self.layer_levels[bc[0] // 6][1],
+                               0))))
         elif order != "block":
             raise ValueError(order)
         self.order = order
@@ -426,28 +442,34 @@ class SphericalShell:
         self._conn = None
 
     def element_ids(self):
-        return [element_id(b, c, self.levels) for b, c in self.cells]
+        return [element_id(b, c, self.layer_levels[b // 6]) for b, c in self.cells]
+
+    def map_points(self, e, xi):
+        """Element-logical points xi [3, m] of element e -> (x [3, m], jacobian
+        [3, 3, m] = d x^i / d xi^j with respect to the ELEMENT-logical coordinates)."""
+        b, cell = self.cells[e]
+        layer, wedge = b // 6, b % 6
+        blk, half = [], []
+        for d in range(3):
+            h = 2.0 / 2 ** self.layer_levels[layer][d]
+            blk.append(-1.0 + h * cell[d] + 0.5 * h * (np.asarray(xi[d], float) + 1.0))
+            half.append(0.5 * h)
+        x, jac = wedge_map(blk[0], blk[1], blk[2], self.radii[layer], self.radii[layer + 1],
+                           wedge, self.equiangular, self.distributions[layer])
+        for j in range(3):
+            jac[:, j] *= half[j]
+        return x, jac
 
     def _geometry(self, ids):
         N, n = self.N, self.n
         p = np.arange(n)
         idx = (p % N, (p // N) % N, p // (N * N))
+        xi = [self.xi[idx[d]] for d in range(3)]
         X = np.empty((len(ids), 3, n))
         Jinv = np.empty((len(ids), 9, n))
         for k, e in enumerate(ids):
-            b, cell = self.cells[e]
-            layer, wedge = b // 6, b % 6
-            blk, half = [], []
-            for d in range(3):
-                h = 2.0 / self.ne[d]
-                lo = -1.0 + h * cell[d]
-                blk.append(lo + 0.5 * h * (self.xi[idx[d]] + 1.0))
-                half.append(0.5 * h)
-            x, jac = wedge_map(blk[0], blk[1], blk[2], self.radii[layer], self.radii[layer + 1],
-                               wedge, self.equiangular, self.distributions[layer])
+            x, jac = self.map_points(e, xi)
             X[k] = x
-            for j in range(3):
-                jac[:, j] *= half[j]          # element logical -> block logical
             inv = np.linalg.inv(np.moveaxis(jac, -1, 0))   # [n, jhat, i] = d xi^jhat / d x^i
             for jh in range(3):
                 for i in range(3):
@@ -467,10 +489,12 @@ class SphericalShell:
         # the 2-point (corner) mesh, whose 2 x 2 face points still tell the eight
         # face permutations apart
         if self._conn is None:
-            corners = SphericalShell(self.radii[0], self.radii[-1],
-                                     (self.levels[0], self.levels[2]), 2, self.radii[1:-1],
-                                     self.distributions, self.equiangular, self.order)
-            self._conn = connectivity_from_geometry(corners.coords(), 2)
+            corners = SphericalShell(self.radii[0], self.radii[-1], self.refinement, 2,
+                                     self.radii[1:-1], self.distributions, self.equiangular,
+                                     self.order)
+            nbr, nd, perm = connectivity_from_geometry(corners.coords(), 2)
+            mortars = find_hanging_faces(corners, nbr)
+            self._conn = (nbr, nd, perm, mortars)
         return self._conn
 
     def neighbors(self):
@@ -481,11 +505,63 @@ class SphericalShell:
         c = self._connectivity()
         return c[1], c[2]
 
+    def mortars(self):
+        """Non-conforming mortars between layers of different angular refinement,
+        rows (coarse element, direction, fine element, direction, size_a, size_b)."""
+        return self._connectivity()[3]
+
     def external_boundary(self, e, d):
         """'inner' (excision) or 'outer' for an external face."""
         b, cell = self.cells[e]
         assert d // 2 == 2
         return "inner" if d == 4 else "outer"
+
+
+def find_hanging_faces(dom, nbr, tol=1e-9):
+    """2:1 non-conforming faces of a multi-block domain with `map_points`: a face
+    without a conforming partner whose four logical quarter centres are the
+    centres of four (likewise unmatched) faces is a coarse face with four
+    mortars.  Marks both sides HANGING in nbr (in place) and returns the mortar
+    table.  Only aligned faces are supported (as between the layers of a shell)."""
+    from scipy.spatial import cKDTree
+    free = [(e, d) for e in range(nbr.shape[0]) for d in range(6) if nbr[e, d] == -1]
+    if not free:
+        return np.zeros((0, 6), dtype=np.int32)
+
+    def face_point(d, a, b):
+        xi = np.zeros(3)
+        xi[d // 2] = 1.0 if d % 2 else -1.0
+        fd = [x for x in range(3) if x != d // 2]
+        xi[fd[0]], xi[fd[1]] = a, b
+        return xi
+    centers = np.array([dom.map_points(e, face_point(d, 0.0, 0.0)[:, None])[0][:, 0]
+                        for e, d in free])
+    tree = cKDTree(centers)
+    mortars = []
+    for k, (e, d) in enumerate(free):
+        found = []
+        for kb in range(2):
+            for ka in range(2):
+                q = dom.map_points(e, face_point(d, ka - 0.5, kb - 0.5)[:, None])[0][:, 0]
+                dist, j = tree.query(q)
+                if dist < tol * max(np.linalg.norm(q), 1e-300) and j != k:
+                    found.append((ka, kb, free[j]))
+        if len(found) != 4:
+            continue
+        for ka, kb, (e2, d2) in found:
+            if d2 != d ^ 1:
+                raise NotImplementedError("non-aligned non-conforming faces")
+            # the fine face must run parallel to the coarse one (no permutation)
+            fine = dom.map_points(e2, face_point(d2, -1.0, 1.0)[:, None])[0][:, 0]
+            mine = dom.map_points(e, face_point(d, ka - 1.0, kb * 1.0)[:, None])[0][:, 0]
+            if np.linalg.norm(fine - mine) > tol * max(np.linalg.norm(mine), 1e-300):
+                raise NotImplementedError("non-aligned non-conforming faces")
+            mortars.append((e, d, e2, d2, MORTAR_UPPER_HALF if ka else MORTAR_LOWER_HALF,
+                            MORTAR_UPPER_HALF if kb else MORTAR_LOWER_HALF))
+    for e, d, e2, d2, _, _ in mortars:
+        nbr[e, d] = HANGING
+        nbr[e2, d2] = HANGING
+    return np.asarray(mortars, dtype=np.int32).reshape(-1, 6)
 
 
 class Partition:
@@ -517,6 +593,8 @@ class Partition:
         for r in range(world):
             owner[bounds[r]:bounds[r + 1]] = r
         mine = np.arange(bounds[rank], bounds[rank + 1])
+        if world > 1 and (neighbors == HANGING).any():
+            raise NotImplementedError("non-conforming mortars across ranks")
         nb_mine = neighbors[mine]
         remote = (nb_mine >= 0) & (owner[np.clip(nb_mine, 0, ne - 1)] != rank)
         is_boundary = remote.any(axis=1)
@@ -535,6 +613,8 @@ class Partition:
         for le, g in enumerate(order):
             for d in range(6):
                 v = int(neighbors[g, d])
+                if v == HANGING:
+                    local_nb[le, d] = HANGING
                 if v < 0:
                     continue
                 self.local_neighbor_direction[le, d] = neighbor_direction[g, d]

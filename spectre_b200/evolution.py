@@ -89,6 +89,8 @@ class Problem:
         # time of every RHS (DirichletAnalytic.cpp:80-96 passes `time`)
         self.boundary_time_dependent = False
         self.neighbors = brick.neighbors()
+        # non-conforming (2:1) mortars of h-refined domains
+        self.mortars = brick.mortars() if hasattr(brick, "mortars") else np.zeros((0, 6), int)
 
     def coords(self, ids=None):
         return self.brick.coords(ids)
@@ -207,6 +209,14 @@ class Evolution:
         if self.part.oriented:
             ctx.set_neighbor_orientations(self.part.local_neighbor_direction,
                                           self.part.local_face_permutation)
+        if len(problem.mortars):
+            if world > 1:
+                raise NotImplementedError("non-conforming mortars across ranks")
+            g2l = {int(g): i for i, g in enumerate(ids)}
+            local = np.array([[g2l[m[0]], m[1], g2l[m[2]], m[3], m[4], m[5]]
+                              for m in problem.mortars.tolist()], dtype=np.int32)
+            self.local_mortars = local
+            ctx.set_mortars(local)
         if problem.demand_outgoing:
             ctx.set_demand_outgoing_char_speeds(True)
         ctx.set_static_fields(problem.static(ids))

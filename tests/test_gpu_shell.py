@@ -245,3 +245,40 @@ def test_partitioned_shell_matches_single_context():
         out[ev.part.global_ids] = ev.ctx.get_state()
         ev.ctx.close()
     np.testing.assert_array_equal(out, ref)
+
+
+def test_shell_with_layers_of_different_refinement():
+    """Sphere with per-layer InitialRefinement (inner layer one angular level
+    finer): the spherical interface between the layers consists of non-conforming
+    2:1 mortars, next to non-aligned conforming neighbours between the wedges and
+    DirichletAnalytic ghosts on both boundaries -- all face kinds in one RHS."""
+    N = 5
+    problem = evolution.gh_kerr_schild_shell_problem([(2, 0), (1, 0)], N,
+                                                     radial_partitioning=(2.1,))
+    assert len(problem.mortars) == 6 * 16
+    ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, 1e-4)
+    ctx, part = ev.ctx, ev.part
+    ids = part.global_ids
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    u0 = problem.u0(ids, 0.0)
+    u = u0 + 1e-3 * np.random.default_rng(4).uniform(-1, 1, u0.shape)
+    ctx.set_state(u)
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    H, dH = _gauge_fields(N, x, J, u0)
+    ext = ev.boundary_ghost_data(problem, 0.0)[:, :50]
+    sf = np.concatenate([stat, H, dH], axis=1)
+    kw = dict(gauge_params=orc.GAUGE_GIVEN, ext_u=ext, nbr_dir=part.local_neighbor_direction,
+              face_perm=part.local_face_permutation)
+    ref = orc.dg_rhs(1, N, u, J, sf, part.local_neighbors, mortars=ev.local_mortars, **kw)
+    assert _relerr(got, ref, GH_BLOCKS) < TOL
+    without = orc.dg_rhs(1, N, u, J, sf,
+                         np.where(part.local_neighbors == domain.HANGING, -1,
+                                  part.local_neighbors), **kw)
+    assert _relerr(without, ref, GH_BLOCKS) > 1e-6
+    # the static solution stays put on the non-conforming shell
+    ctx.set_state(u0)
+    ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 3, 0.0, 1e-4)
+    ev.take_steps(3)
+    assert np.max(np.abs(ctx.get_state() - u0)) < 1e-4
+    ctx.close()

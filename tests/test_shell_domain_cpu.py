@@ -195,3 +195,25 @@ def test_radial_element_order_cuts_the_shell_at_constant_radius():
         assert p.n_recv == (1 if r in (0, world - 1) else 2) * 6 * 4
         radial = {sh.cells[g][1][2] for g in p.global_ids}
         assert radial == {2 * r, 2 * r + 1}
+
+
+def test_shell_layers_of_different_refinement_have_mortars():
+    """Per-layer refinement: the inner layer one angular level finer than the
+    outer one -> every element face on the interface sphere is a 2:1 mortar."""
+    sh = domain.SphericalShell(1.9, 2.9, [(2, 0), (1, 0)], 3, radial_partitioning=(2.3,))
+    nb, mt = sh.neighbors(), sh.mortars()
+    assert sh.n_elements == 6 * 16 + 6 * 4
+    assert (nb == domain.HANGING).sum() == 6 * 16 + 6 * 4 and len(mt) == 6 * 16
+    assert (nb == -1).sum() == 6 * 16 + 6 * 4      # excision sphere + outer sphere
+    x = sh.coords()
+    P = [np.eye(3), orc.projection_matrix_parent_to_child(3, 3, 1),
+         orc.projection_matrix_parent_to_child(3, 3, 2)]
+    for ec, dc, ef, df, sa, sb in mt:
+        assert dc == 4 and df == 5       # the coarse (outer) layer looks inwards
+        # interpolating the coarse face's coordinates to the mortar gives the fine
+        # face's points up to the interpolation error of the (non-polynomial) map
+        fc = x[ec][:, domain._face_point_indices(3, dc)].reshape(3, 3, 3)   # [xyz, b, a]
+        ff = x[ef][:, domain._face_point_indices(3, df)].reshape(3, 3, 3)
+        interp = np.einsum("Bb,Aa,xba->xBA", P[sb], P[sa], fc)
+        assert np.max(np.abs(interp - ff)) < 2e-2
+        np.testing.assert_allclose(np.linalg.norm(ff, axis=0), 2.3, rtol=1e-13)
