@@ -310,3 +310,40 @@ def test_demand_outgoing_char_speeds_vs_reference_numpy(golden_dir):
                                            z["normal"][k])
         np.testing.assert_allclose(lam, z["speeds"][k], rtol=1e-14, atol=1e-15)
         assert (lam.min() < 0.0) == bool(z["violated"][k])
+
+
+def test_bjorhus_constraint_preserving_vs_reference_numpy(golden_dir):
+    """two_index_constraint, f_constraint and the ConstraintPreserving Bjorhus
+    corrections to dt(g, Pi, Phi) against fixtures made by importing the
+    reference's Bjorhus.py / TestFunctions.py with independent random tensors for
+    every argument, as Test_Bjorhus.cpp feeds them
+    (tests/golden/gen_bjorhus_golden.py)."""
+    from oracle import bjorhus as bj
+    z = np.load(os.path.join(golden_dir, "bjorhus.npz"))
+    n = len(z["in_lapse"])
+    incoming = 0
+    for p in range(n):
+        I = {k[3:]: z[k][p] for k in z.files if k.startswith("in_")}
+        t_lo = np.zeros(4)
+        t_lo[0] = -I["lapse"]
+        ipsi, t_up = I["inverse_spacetime_metric"], I["spacetime_unit_normal_vector"]
+        ig = ipsi[1:, 1:] + np.outer(I["shift"], I["shift"]) / I["lapse"] ** 2
+        args = (t_lo, t_up, ig, ipsi, I["pi"], I["phi"], I["d_pi"], I["d_phi"], I["gamma2"],
+                I["three_index_constraint"])
+        c2 = bj.two_index_constraint(I["spacetime_deriv_gauge_source"], *args)
+        np.testing.assert_allclose(c2, z["out_two_index_constraint"][p], rtol=1e-12, atol=1e-12)
+        fc = bj.f_constraint(I["gauge_source"], I["spacetime_deriv_gauge_source"], *args)
+        np.testing.assert_allclose(fc, z["out_f_constraint"][p], rtol=1e-12, atol=1e-12)
+        speeds = bj.characteristic_speeds(I["gamma1"], I["lapse"], I["shift"],
+                                          I["normal_covector"])
+        np.testing.assert_allclose(speeds, z["out_char_speeds"][p], rtol=1e-14, atol=1e-15)
+        incoming += speeds.min() < 0
+        cg, cp, cph = bj.bjorhus_constraint_preserving(
+            I["normal_covector"], I["spacetime_metric"], I["pi"], I["phi"], I["coords"],
+            I["gamma1"], I["gamma2"], I["lapse"], I["shift"], ipsi, t_up,
+            I["three_index_constraint"], I["gauge_source"], I["spacetime_deriv_gauge_source"],
+            I["dt_spacetime_metric"], I["dt_pi"], I["dt_phi"], I["d_pi"], I["d_phi"])
+        np.testing.assert_allclose(cg, z["out_corr_g"][p], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(cp, z["out_corr_pi"][p], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(cph, z["out_corr_phi"][p], rtol=1e-12, atol=1e-12)
+    assert 0 < incoming < n + 1
