@@ -499,7 +499,74 @@ def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC
         lib().orc_dg_rhs_mortars(system, N, nelem, _p(D), _p(u), _p(invjac),
                                  _p(static_fields), _p(coords), _p(nbr), _p(nf), _p(gp),
                                  _p(ext), nm, _p(mt), _p(P), _p(R), _p(dt))
+        if (nbr == BJORHUS).any():
+            dt += bjorhus_corrections(N, u, invjac, static_fields, coords, nbr, gauge_params)
     return dt
+
+
+def bjorhus_corrections(N, u, invjac, static_fields, coords, nbr, gauge_params=GAUGE_HARMONIC):
+    """TimeDerivative-type boundary condition ConstraintPreservingBjorhus on the
+    faces marked BJORHUS (BoundaryConditionsImpl.hpp:566-670): the volume time
+    derivative and the volume partial derivatives are sliced to the face, the
+    condition returns corrections to dt(g, Pi, Phi) which are added on the face
+    points (no lifting).  Returns the array to add to the right-hand side."""
+    from . import bjorhus as bj
+    nelem, n = u.shape[0], N ** 3
+    given = static_fields.shape[1] >= 23
+    vol = dg_rhs(1, N, u, invjac, static_fields, nbr, gauge_params, coords, volume_only=True)
+    out = np.zeros_like(u)
+    unpack = lambda v: np.array([[v[sym4(a, b)] for b in range(4)] for a in range(4)])
+    for e in range(nelem):
+        faces = [d for d in range(6) if nbr[e, d] == BJORHUS]
+        if not faces:
+            continue
+        du = np.asarray(partial_derivatives(N, u[e], invjac[e])).reshape(50, 3, n)
+        geo = gh_geometry(u[e])
+        for d in faces:
+            dim, sign = d // 2, (1.0 if d % 2 else -1.0)
+            a, b = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+            fixed = N - 1 if d % 2 else 0
+            pts = [fixed + N * (a + N * b), a + N * (fixed + N * b), a + N * (b + N * fixed)][dim]
+            for p in pts.ravel():
+                ig = np.zeros((3, 3))
+                c = 0
+                for i in range(3):
+                    for j in range(i, 3):
+                        ig[i, j] = ig[j, i] = geo["inv_gamma"][c][p]
+                        c += 1
+                unnorm = sign * np.array([invjac[e][dim + 3 * i][p] for i in range(3)])
+                n_lo = unnorm / np.sqrt(unnorm @ ig @ unnorm)
+                lapse, shift = geo["lapse"][p], geo["shift"][:, p]
+                ipsi = unpack(geo["inv_g"][:, p])
+                t_up = np.concatenate([[1.0 / lapse], -shift / lapse])
+                g = unpack(u[e][0:10, p])
+                pi = unpack(u[e][10:20, p])
+                tens3 = lambda arr: np.array([unpack(np.array([arr[20 + m + 3 * s]
+                                                               for s in range(10)]))
+                                              for m in range(3)])
+                phi = tens3(u[e][:, p])
+                dt_g, dt_pi = unpack(vol[e][0:10, p]), unpack(vol[e][10:20, p])
+                dt_phi = tens3(vol[e][:, p])
+                d_g = np.array([unpack(du[0:10, i, p]) for i in range(3)])
+                d_pi = np.array([unpack(du[10:20, i, p]) for i in range(3)])
+                d_phi = np.array([[unpack(np.array([du[20 + m + 3 * s, i, p] for s in range(10)]))
+                                   for m in range(3)] for i in range(3)])
+                if given:
+                    H = static_fields[e][3:7, p]
+                    dH = np.array([[static_fields[e][7 + aa + 4 * bb, p] for bb in range(4)]
+                                   for aa in range(4)])
+                else:
+                    H, dH = np.zeros(4), np.zeros((4, 4))
+                cg, cp, cph = bj.bjorhus_constraint_preserving(
+                    n_lo, g, pi, phi, coords[e][:, p], static_fields[e][1, p],
+                    static_fields[e][2, p], lapse, shift, ipsi, t_up, d_g - phi, H, dH,
+                    dt_g, dt_pi, dt_phi, d_pi, d_phi)
+                for s_, (aa, bb) in enumerate([(x, y) for x in range(4) for y in range(x, 4)]):
+                    out[e][s_, p] += cg[aa, bb]
+                    out[e][10 + s_, p] += cp[aa, bb]
+                    for m in range(3):
+                        out[e][20 + m + 3 * s_, p] += cph[m, aa, bb]
+    return out
 
 
 def gh_characteristic_speeds(gamma1, lapse, shift, unit_normal_one_form):
@@ -780,6 +847,7 @@ def gh_constraint_norms(N, u, invjac, H=None):
 # ---------------------------------------------------------------------------
 MORTAR_FULL, MORTAR_LOWER_HALF, MORTAR_UPPER_HALF = 0, 1, 2
 HANGING = -2 ** 31   # neighbour-table entry of a face that is handled by the mortar table
+BJORHUS = -2 ** 31 + 1   # external face with ConstraintPreservingBjorhus
 
 
 def legendre_vandermonde(num_points):

@@ -339,6 +339,9 @@ struct dgrhs_ctx {
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
   unsigned long long* violations = nullptr;  // DemandOutgoingCharSpeeds status (device)
+  // ConstraintPreservingBjorhus faces (DGRHS_NEIGHBOR_BJORHUS in the neighbour table)
+  int n_bjorhus_faces = 0;
+  int32_t* bjorhus_faces = nullptr;  // [n][2]
   // non-conforming mortars (dgrhs_set_mortars)
   int n_mortar_faces = 0;
   int32_t* mortar_faces = nullptr;   // [n_mortar_faces][4]
@@ -425,6 +428,18 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
     dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
   ++g_launches;
   CU(cudaGetLastError());
+  // ConstraintPreservingBjorhus faces (all at once, with the boundary-element pass)
+  if (c->n_bjorhus_faces > 0 && pass != 1) {
+    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC)
+      return fail("ConstraintPreservingBjorhus with the DampedHarmonic gauge is not implemented");
+    dg::BjorhusArgs b{c->u, c->invjac, c->stat, c->gH, c->gdH, c->coords, c->D, c->corr,
+                      c->bjorhus_faces};
+    constexpr int bT = (N * N + 31) / 32 * 32;
+    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->stream>>>(
+        b, c->gauge == DGRHS_GAUGE_HARMONIC);
+    ++g_launches;
+    CU(cudaGetLastError());
+  }
   // non-conforming mortars: with the pass that covers the boundary elements (all
   // mortars of a context are evaluated at once)
   if (c->n_mortar_faces > 0 && pass != 1) {
@@ -755,6 +770,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   if (c->nbr) cudaFree(c->nbr);
   if (c->nbr_face) cudaFree(c->nbr_face);
   if (c->violations) cudaFree(c->violations);
+  if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
   if (c->mortar_faces) cudaFree(c->mortar_faces);
   if (c->mortar_table) cudaFree(c->mortar_table);
   if (c->mortar_P) cudaFree(c->mortar_P);
@@ -773,6 +789,12 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   for (size_t i = 0; i < (size_t)c->nelem * 6; ++i) {
     const int v = neighbors[i];
     if (v == DGRHS_NEIGHBOR_HANGING) continue;  // non-conforming face: dgrhs_set_mortars
+    if (v == DGRHS_NEIGHBOR_BJORHUS) {
+      if (c->system != DGRHS_SYSTEM_GH)
+        return fail("ConstraintPreservingBjorhus is a GeneralizedHarmonic boundary condition");
+      if (!coords) return fail("ConstraintPreservingBjorhus needs inertial coordinates");
+      continue;
+    }
     if (v >= c->nelem) return fail("neighbor index %d out of range", v);
     if (v <= -2 && -(v + 2) >= c->nghost) return fail("ghost face index out of range");
   }
@@ -799,6 +821,18 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   if (c->nbr_face) cudaFree(c->nbr_face);
   c->nbr_face = nullptr;
   c->n_mortar_faces = 0;
+  // external faces with the Bjorhus boundary condition
+  std::vector<int32_t> bj;
+  for (int e = 0; e < c->nelem; ++e)
+    for (int d = 0; d < 6; ++d)
+      if (neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS) bj.insert(bj.end(), {e, d});
+  if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
+  c->bjorhus_faces = nullptr;
+  c->n_bjorhus_faces = (int)(bj.size() / 2);
+  if (!bj.empty()) {
+    CU(cudaMalloc(&c->bjorhus_faces, bj.size() * 4));
+    CU(cudaMemcpy(c->bjorhus_faces, bj.data(), bj.size() * 4, cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 

@@ -27,6 +27,7 @@
 #include <stdint.h>
 
 #include "pointwise.cuh"
+#include "bjorhus.cuh"
 
 namespace dg {
 
@@ -842,6 +843,9 @@ __device__ __forceinline__ void atomic_min_negative(unsigned long long* addr, do
 // neighbour-table entry of a face that belongs to a non-conforming (2:1) mortar:
 // the face kernels skip it, mortar_kernel writes its corrections
 constexpr int32_t kHangingFace = INT32_MIN;
+// external face with the ConstraintPreservingBjorhus boundary condition: skipped
+// by the face kernels, gh_bjorhus_kernel writes its (unlifted) dt corrections
+constexpr int32_t kBjorhusFace = INT32_MIN + 1;
 
 // neighbour-side face coordinates of our face point (qa, qb)
 template <int N>
@@ -884,7 +888,7 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
-  if (nb == kHangingFace) return;  // corrections come from mortar_kernel
+  if (nb == kHangingFace || nb == kBjorhusFace) return;  // written by mortar / Bjorhus kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
   int na_, nb_;
@@ -1012,7 +1016,7 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
-  if (nb == kHangingFace) return;  // corrections come from mortar_kernel
+  if (nb == kHangingFace || nb == kBjorhusFace) return;  // written by mortar / Bjorhus kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
   int na_, nb_;
@@ -1317,6 +1321,203 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
         }
       }
     }
+  }
+}
+
+// --------------------------------------------------------------------------
+// ConstraintPreservingBjorhus (Type ConstraintPreserving) on external faces:
+// a TimeDerivative-type boundary condition (BoundaryConditionsImpl.hpp:566-670):
+// the reference slices the volume time derivative and the volume partial
+// derivatives to the face and adds the returned corrections to dt on the face
+// points, without lifting.  One CTA per Bjorhus face, one thread per face point:
+// the thread forms the 150 logical derivatives at its point from global memory,
+// re-evaluates the volume time derivative there with the same per-point code as
+// the volume kernel (the volume kernel runs later and adds the corrections in
+// the same pass), evaluates the boundary condition (bjorhus.cuh) and writes the
+// corrections into the face's corr slots.  kGauge: 0 Harmonic, 1 fields.
+// --------------------------------------------------------------------------
+struct BjorhusArgs {
+  const double* u;
+  const double* invjac;
+  const double* stat;
+  const double* gH;
+  const double* gdH;
+  const double* coords;
+  const double* D;
+  double* corr;
+  const int32_t* faces;  // [n][2] = element, direction
+};
+
+// Everything that does not depend on N: volume time derivative at the point,
+// the boundary condition's inputs, the condition itself.  One (not inlined) copy.
+// d = face direction, dlog[c][jhat] = logical derivatives, corr[50] in Variables
+// component order.
+static __device__ __noinline__ void gh_bjorhus_point(bool harmonic, int d, const double (&g)[10],
+                                                     const double (&pi)[10],
+                                                     const double (&phi)[3][10],
+                                                     const double (&J)[3][3], double gamma0,
+                                                     double gamma1, double gamma2,
+                                                     const GaugeH& gh, const double (&x)[3],
+                                                     const double (&dlog)[50][3],
+                                                     double (&corr)[50]) {
+  GhContext ctx;
+  double Q[10], dtv[50];
+  {
+    GaugeInput gin;
+    gin.fields = &gh;
+    if (harmonic)
+      gh_prologue<0>(g, pi, phi, J, gamma0, gamma1, gamma2, gin, ctx, Q);
+    else
+      gh_prologue<1>(g, pi, phi, J, gamma0, gamma1, gamma2, gin, ctx, Q);
+#pragma unroll 1
+    for (int s = 0; s < 10; ++s) {
+      double ph[3], dph[3][3], oph[3];
+      for (int m = 0; m < 3; ++m) {
+        ph[m] = phi[m][s];
+        for (int xx = 0; xx < 3; ++xx) dph[m][xx] = dlog[20 + m + 3 * s][xx];
+      }
+      gh_pair_rhs(ctx, Q[s], g[s], pi[s], ph, dlog[s], dlog[10 + s], dph, dtv[s], dtv[10 + s],
+                  oph);
+      for (int m = 0; m < 3; ++m) dtv[20 + m + 3 * s] = oph[m];
+    }
+  }
+  BjorhusInput in;
+  {
+    const double sign = (d & 1) ? 1.0 : -1.0;
+    const int dim = d >> 1;
+    double unn[3];
+    for (int xx = 0; xx < 3; ++xx) unn[xx] = sign * J[dim][xx];
+    GhFaceSide sd;
+    gh_face_side(g, unn, gamma1, gamma2, sd);
+    Geom3p1 q;
+    geom_from_metric(g, q);
+    in.lapse = q.lapse;
+    in.gamma1 = gamma1;
+    in.gamma2 = gamma2;
+    const double il2 = 1.0 / (q.lapse * q.lapse);
+    in.ipsi[0][0] = -il2;
+    in.t_up[0] = 1.0 / q.lapse;
+    for (int xx = 0; xx < 3; ++xx) {
+      in.n_lo[xx] = sd.n_lo[xx];
+      in.shift[xx] = q.shift[xx];
+      in.x[xx] = x[xx];
+      in.ipsi[0][xx + 1] = in.ipsi[xx + 1][0] = q.shift[xx] * il2;
+      in.t_up[xx + 1] = -q.shift[xx] / q.lapse;
+      for (int y = 0; y < 3; ++y)
+        in.ipsi[xx + 1][y + 1] = q.ig[sym3(xx, y)] - q.shift[xx] * q.shift[y] * il2;
+    }
+#pragma unroll 1
+    for (int aa = 0; aa < 4; ++aa) {
+      in.H[aa] = gh.H[aa];
+#pragma unroll 1
+      for (int bb = 0; bb < 4; ++bb) {
+        const int s = sym4(aa, bb);
+        in.dH[aa][bb] = gh.dH[aa][bb];
+        in.g[aa][bb] = g[s];
+        in.pi[aa][bb] = pi[s];
+        in.dt_g[aa][bb] = dtv[s];
+        in.dt_pi[aa][bb] = dtv[10 + s];
+        for (int m = 0; m < 3; ++m) {
+          in.phi[m][aa][bb] = phi[m][s];
+          in.dt_phi[m][aa][bb] = dtv[20 + m + 3 * s];
+        }
+        // inertial derivatives d_x = J(jhat, x) d_jhat (PartialDerivatives.tpp:79-109)
+        for (int xx = 0; xx < 3; ++xx) {
+          double dgx = 0.0, dpx = 0.0;
+          for (int jh = 0; jh < 3; ++jh) {
+            dgx += J[jh][xx] * dlog[s][jh];
+            dpx += J[jh][xx] * dlog[10 + s][jh];
+          }
+          in.c3[xx][aa][bb] = dgx - phi[xx][s];   // three-index constraint
+          in.d_pi[xx][aa][bb] = dpx;
+          for (int m = 0; m < 3; ++m) {
+            double v = 0.0;
+            for (int jh = 0; jh < 3; ++jh) v += J[jh][xx] * dlog[20 + m + 3 * s][jh];
+            in.d_phi[xx][m][aa][bb] = v;
+          }
+        }
+      }
+    }
+  }
+  BjorhusOutput out;
+  bjorhus_constraint_preserving(in, out);
+  for (int aa = 0; aa < 4; ++aa)
+    for (int bb = aa; bb < 4; ++bb) {
+      const int s = sym4(aa, bb);
+      corr[s] = out.g[aa][bb];
+      corr[10 + s] = out.pi[aa][bb];
+      for (int m = 0; m < 3; ++m) corr[20 + m + 3 * s] = out.phi[m][aa][bb];
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__((N * N + 31) / 32 * 32)
+    gh_bjorhus_kernel(BjorhusArgs a, bool harmonic) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, T = (N * N + 31) / 32 * 32;
+  __shared__ double sD[N * N];
+  for (int idx = threadIdx.x; idx < N * N; idx += T) sD[idx] = a.D[idx];
+  __syncthreads();
+  const int tid = threadIdx.x;
+  if (tid >= f) return;
+  const int e = a.faces[2 * blockIdx.x], d = a.faces[2 * blockIdx.x + 1];
+  const int qa = tid % N, qb = tid / N;
+  const int p = face_point<N>(d, qa, qb);
+  const int i = p % N, j = (p / N) % N, k = p / (N * N);
+  const double* __restrict__ ue = a.u + (size_t)e * 50 * npad;
+
+  double g[10], pi[10], phi[3][10];
+  for (int s = 0; s < 10; ++s) {
+    g[s] = __ldg(ue + (size_t)s * npad + p);
+    pi[s] = __ldg(ue + (size_t)(10 + s) * npad + p);
+    for (int m = 0; m < 3; ++m) phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad + p);
+  }
+  double J[3][3], x[3];
+  const double* je = a.invjac + (size_t)e * 9 * npad + p;
+  const double* xe = a.coords + (size_t)e * 3 * npad + p;
+  for (int jh = 0; jh < 3; ++jh) {
+    x[jh] = __ldg(xe + (size_t)jh * npad);
+    for (int xx = 0; xx < 3; ++xx) J[jh][xx] = __ldg(je + (size_t)(jh + 3 * xx) * npad);
+  }
+  const double* se = a.stat + (size_t)e * 3 * npad + p;
+  const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad), gamma2 = __ldg(se + 2 * npad);
+  GaugeH gh;
+  for (int xx = 0; xx < 4; ++xx) {
+    gh.H[xx] = 0.0;
+    for (int y = 0; y < 4; ++y) gh.dH[xx][y] = 0.0;
+  }
+  if (!harmonic) {
+    const double* he = a.gH + (size_t)e * 4 * npad + p;
+    const double* dhe = a.gdH + (size_t)e * 16 * npad + p;
+    for (int xx = 0; xx < 4; ++xx) {
+      gh.H[xx] = __ldg(he + (size_t)xx * npad);
+      for (int y = 0; y < 4; ++y) gh.dH[xx][y] = __ldg(dhe + (size_t)(xx + 4 * y) * npad);
+    }
+  }
+  // logical derivatives of all 50 components at the point (K1)
+  double dlog[50][3];
+#pragma unroll 1
+  for (int c = 0; c < 50; ++c) {
+    const double* tc = ue + (size_t)c * npad;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      d0 = fma(sD[i * N + m], __ldg(tc + m + N * (j + N * k)), d0);
+      d1 = fma(sD[j * N + m], __ldg(tc + i + N * (m + N * k)), d1);
+      d2 = fma(sD[k * N + m], __ldg(tc + i + N * (j + N * m)), d2);
+    }
+    dlog[c][0] = d0;
+    dlog[c][1] = d1;
+    dlog[c][2] = d2;
+  }
+  double corr[50];
+  gh_bjorhus_point(harmonic, d, g, pi, phi, J, gamma0, gamma1, gamma2, gh, x, dlog, corr);
+  double* cf = a.corr + (size_t)e * 10 * 30 * f + (size_t)d * 5 * f + tid;
+#pragma unroll 1
+  for (int s = 0; s < 10; ++s) {
+    double* cs = cf + (size_t)s * 30 * f;
+    cs[0] = corr[s];
+    cs[(size_t)f] = corr[10 + s];
+    for (int m = 0; m < 3; ++m) cs[(size_t)(2 + m) * f] = corr[20 + m + 3 * s];
   }
 }
 

@@ -67,7 +67,7 @@ class Problem:
     the element subset a rank owns (global arrays would not fit at 8 GPUs)."""
 
     def __init__(self, system, brick, initial_data, static_values, dirichlet_analytic=False,
-                 analytic_christoffel_gauge=False, demand_outgoing=None):
+                 analytic_christoffel_gauge=False, demand_outgoing=None, bjorhus=None):
         """brick: the domain (domain.Brick or domain.SphericalShell).
         static_values: one number or one callable(x) -> array per static field.
         dirichlet_analytic: external faces get the analytic solution as exterior
@@ -75,8 +75,11 @@ class Problem:
         a predicate (global element, direction) -> bool.
         demand_outgoing: DemandOutgoingCharSpeeds on the remaining external faces
         (no correction, characteristic speeds checked); None = off.
+        bjorhus: predicate (global element, direction) -> bool selecting external
+        faces with ConstraintPreservingBjorhus (Type ConstraintPreserving).
         analytic_christoffel_gauge: AnalyticChristoffel gauge of the (static)
         analytic solution instead of the harmonic gauge."""
+        self.bjorhus = bjorhus
         self.system, self.brick, self.N = system, brick, brick.N
         self._initial_data, self._static_values = initial_data, static_values
         self.dirichlet_analytic = dirichlet_analytic
@@ -142,7 +145,8 @@ def gh_kerr_schild_problem(refinement, N, lower=(2.0, 2.0, 2.0), upper=(4.0, 4.0
 def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2.3,
                                  radial_partitioning=(), mass=1.0,
                                  inner_boundary="DirichletAnalytic",
-                                 radial_distribution="Logarithmic", order="block"):
+                                 radial_distribution="Logarithmic", order="block",
+                                 outer_boundary="DirichletAnalytic"):
     """BASELINE.json configs[2]: Kerr-Schild black hole (M = 1, a = 0) on the
     spherical shell of KerrSchild.yaml:80-98 (Sphere, InnerRadius 1.9, OuterRadius
     2.3, equiangular wedges, Logarithmic radial distribution, excised interior),
@@ -156,15 +160,18 @@ def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2
     gam = (lambda x: analytic.gaussian_plus_constant(x, 0.001, 3.0, w),
            -1.0,
            lambda x: analytic.gaussian_plus_constant(x, 0.001, 1.0, w))
-    if inner_boundary == "DirichletAnalytic":
-        ghost, outgoing = True, False
-    elif inner_boundary == "DemandOutgoingCharSpeeds":
-        ghost, outgoing = (lambda g, d: d == 5), True
-    else:
+    if inner_boundary not in ("DirichletAnalytic", "DemandOutgoingCharSpeeds"):
         raise ValueError(inner_boundary)
+    if outer_boundary not in ("DirichletAnalytic", "ConstraintPreservingBjorhus"):
+        raise ValueError(outer_boundary)
+    ghost_dirs = {d for d, bc in ((4, inner_boundary), (5, outer_boundary))
+                  if bc == "DirichletAnalytic"}
+    outgoing = inner_boundary == "DemandOutgoingCharSpeeds"
+    bjorhus = (lambda g, d: d == 5) if outer_boundary == "ConstraintPreservingBjorhus" else None
+    ghost = (lambda g, d: d in ghost_dirs) if ghost_dirs else False
     return Problem(lib.SYSTEM_GH, shell, lambda x, t: analytic.kerr_schild(x, mass), gam,
                    dirichlet_analytic=ghost, analytic_christoffel_gauge=True,
-                   demand_outgoing=outgoing)
+                   demand_outgoing=outgoing, bjorhus=bjorhus)
 
 
 def gh_gauge_wave_dirichlet_problem(refinement, N, amplitude=0.1, wavelength=1.0,
@@ -204,6 +211,12 @@ class Evolution:
         self.ctx = lib.Context(problem.system, problem.N, self.part.n_local,
                                self.part.n_ghost, device)
         ctx = self.ctx
+        if problem.bjorhus is not None:
+            ln = self.part.local_neighbors
+            for le, g in enumerate(ids):
+                for d in range(6):
+                    if ln[le, d] == -1 and problem.bjorhus(int(g), d):
+                        ln[le, d] = lib.BJORHUS
         ctx.set_geometry(problem.inverse_jacobian(ids), problem.coords(ids),
                          self.part.local_neighbors)
         if self.part.oriented:

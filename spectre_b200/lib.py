@@ -44,6 +44,7 @@ _lib = None
 
 
 HANGING = -2 ** 31   # DGRHS_NEIGHBOR_HANGING
+BJORHUS = -2 ** 31 + 1   # DGRHS_NEIGHBOR_BJORHUS
 
 
 def projection_matrix(N, child_to_parent, size):

@@ -7,6 +7,7 @@ using std::exp;
 using std::log;
 using std::sqrt;
 #include "../../spectre_b200/csrc/pointwise.cuh"
+#include "../../spectre_b200/csrc/bjorhus.cuh"
 
 extern "C" {
 
@@ -175,6 +176,50 @@ void h_sw_face(int f, const double* ui, const double* ue, const double* ni,
     }
     dg::sw_face_correction(a, g2i[p], na, b, g2e[p], nb, c);
     for (int k = 0; k < 5; ++k) corr[(size_t)k * f + p] = c[k];
+  }
+}
+
+// ConstraintPreservingBjorhus at npts independent points; every array is
+// [npts][...] in C order with the argument list of the reference's
+// dt_*_ConstraintPreserving_static_mesh twins.
+void h_bjorhus_cp(int npts, const double* n_lo, const double* g, const double* pi,
+                  const double* phi, const double* x, const double* gamma1,
+                  const double* gamma2, const double* lapse, const double* shift,
+                  const double* ipsi, const double* t_up, const double* c3, const double* H,
+                  const double* dH, const double* dt_g, const double* dt_pi,
+                  const double* dt_phi, const double* d_pi, const double* d_phi,
+                  double* out_g, double* out_pi, double* out_phi) {
+  for (int p = 0; p < npts; ++p) {
+    dg::BjorhusInput in;
+    dg::BjorhusOutput out;
+    auto cp = [&](double* dst, const double* src, int n) {
+      for (int k = 0; k < n; ++k) dst[k] = src[(size_t)p * n + k];
+    };
+    cp(in.n_lo, n_lo, 3);
+    cp(&in.g[0][0], g, 16);
+    cp(&in.pi[0][0], pi, 16);
+    cp(&in.phi[0][0][0], phi, 48);
+    cp(in.x, x, 3);
+    in.gamma1 = gamma1[p];
+    in.gamma2 = gamma2[p];
+    in.lapse = lapse[p];
+    cp(in.shift, shift, 3);
+    cp(&in.ipsi[0][0], ipsi, 16);
+    cp(in.t_up, t_up, 4);
+    cp(&in.c3[0][0][0], c3, 48);
+    cp(in.H, H, 4);
+    cp(&in.dH[0][0], dH, 16);
+    cp(&in.dt_g[0][0], dt_g, 16);
+    cp(&in.dt_pi[0][0], dt_pi, 16);
+    cp(&in.dt_phi[0][0][0], dt_phi, 48);
+    cp(&in.d_pi[0][0][0], d_pi, 48);
+    cp(&in.d_phi[0][0][0][0], d_phi, 144);
+    dg::bjorhus_constraint_preserving(in, out);
+    for (int k = 0; k < 16; ++k) {
+      out_g[(size_t)p * 16 + k] = (&out.g[0][0])[k];
+      out_pi[(size_t)p * 16 + k] = (&out.pi[0][0])[k];
+    }
+    for (int k = 0; k < 48; ++k) out_phi[(size_t)p * 48 + k] = (&out.phi[0][0][0])[k];
   }
 }
 }

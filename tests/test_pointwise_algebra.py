@@ -141,3 +141,27 @@ def test_gh_volume_split_algebra(harness):
     ref = orc.gh_time_derivative(u, _du_from_logical(dlog, J, 50, n), gam[0], gam[1], gam[2])
     for blk in (slice(0, 10), slice(10, 20), slice(20, 50)):
         assert _maxrel(dt[blk], ref[blk]) < 1e-13
+
+
+def test_bjorhus_algebra_vs_reference_fixtures(harness, golden_dir):
+    """The product's pointwise ConstraintPreservingBjorhus algebra
+    (spectre_b200/csrc/bjorhus.cuh, compiled for the host) against the fixtures
+    made from the reference's Bjorhus.py with independent random tensors for every
+    argument, and against the oracle."""
+    from oracle import bjorhus as bj
+    z = np.load(os.path.join(golden_dir, "bjorhus.npz"))
+    n = len(z["in_lapse"])
+    c = np.ascontiguousarray
+    P = lambda a: c(a, dtype=np.float64).ctypes.data_as(ctypes.c_void_p)
+    out_g, out_pi, out_phi = np.zeros((n, 4, 4)), np.zeros((n, 4, 4)), np.zeros((n, 3, 4, 4))
+    keys = ["normal_covector", "spacetime_metric", "pi", "phi", "coords", "gamma1", "gamma2",
+            "lapse", "shift", "inverse_spacetime_metric", "spacetime_unit_normal_vector",
+            "three_index_constraint", "gauge_source", "spacetime_deriv_gauge_source",
+            "dt_spacetime_metric", "dt_pi", "dt_phi", "d_pi", "d_phi"]
+    arrays = [c(z["in_" + k], dtype=np.float64) for k in keys]
+    harness.h_bjorhus_cp(n, *[a.ctypes.data_as(ctypes.c_void_p) for a in arrays],
+                         P(out_g), P(out_pi), P(out_phi))
+    scale = np.abs(z["out_corr_pi"]).max()
+    assert np.max(np.abs(out_g - z["out_corr_g"])) < 1e-12 * scale
+    assert np.max(np.abs(out_pi - z["out_corr_pi"])) < 1e-12 * scale
+    assert np.max(np.abs(out_phi - z["out_corr_phi"])) < 1e-12 * scale
