@@ -203,15 +203,16 @@ int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
  * A context with mortars must hold both sides of every mortar (single rank). */
 #define DGRHS_NEIGHBOR_HANGING (-2147483647 - 1)
 /* Neighbor-table entry of an EXTERNAL face with gh::BoundaryConditions::
- * ConstraintPreservingBjorhus, Type ConstraintPreserving (GeneralizedHarmonic/
+ * ConstraintPreservingBjorhus, Type ConstraintPreserving (DGRHS_NEIGHBOR_BJORHUS)
+ * or ConstraintPreservingPhysical (DGRHS_NEIGHBOR_BJORHUS_PHYSICAL) (GeneralizedHarmonic/
  * BoundaryConditions/Bjorhus.cpp:104-391, BjorhusImpl.cpp; a TimeDerivative-type
  * condition applied by BoundaryConditionsImpl.hpp:566-670): the corrections
  * computed from the volume time derivative, the volume partial derivatives, the
  * gauge source and the constraint fields on the face are added to dt(g, Pi,
  * Phi) on the face points.  Needs inertial coordinates (dgrhs_set_geometry) and
- * the Harmonic gauge or gauge fields; static mesh.  Type
- * ConstraintPreservingPhysical is not implemented. */
+ * the Harmonic gauge or gauge fields; static mesh. */
 #define DGRHS_NEIGHBOR_BJORHUS (-2147483647)
+#define DGRHS_NEIGHBOR_BJORHUS_PHYSICAL (-2147483646)
 int dgrhs_set_mortars(dgrhs_ctx* ctx, int n_mortars, const int32_t* mortars);
 /* Spectral::projection_matrix_parent_to_child (child_to_parent = 0; Projection.cpp:
  * 279-362) / projection_matrix_child_to_parent (= 1; :57-262, operand not massive)

@@ -1,6 +1,7 @@
 """CPU restatement (numpy, one grid point at a time) of the constraint-preserving
 Bjorhus boundary condition of the GeneralizedHarmonic system, type
-`ConstraintPreserving` -- TEST INFRASTRUCTURE ONLY (see oracle/oracle.py).
+`ConstraintPreserving` and `ConstraintPreservingPhysical` -- TEST INFRASTRUCTURE
+ONLY (see oracle/oracle.py).
 
 Follows the reference (sxs-collaboration/spectre v2024.09.29):
   GeneralizedHarmonic/BoundaryConditions/Bjorhus.cpp:104-391 (dg_time_derivative),
@@ -123,10 +124,73 @@ def evolved_fields_from_characteristic_fields(gamma2, v_psi, v_zero, v_plus, v_m
             np.einsum("i,ab->iab", n_lo, 0.5 * (v_plus - v_minus)) + v_zero)
 
 
+def physical_terms(gamma2, n_lo, n_up, t_up, p_lo, p_mix, p_up, ig, g, ipsi, c3, rhs_minus, pi,
+                   phi, d_phi, d_pi, speeds):
+    """add_physical_terms_to_dt_v_minus (BjorhusImpl.cpp:223-494, mu_phys = 0,
+    adjust_phys_using_c4, gamma2_in_phys): the incoming Weyl propagating mode
+    U^{3-} (WeylPropagating.cpp) from the spatial Ricci tensor of the GH variables
+    (GeneralizedHarmonic/Ricci.cpp), the extrinsic curvature (ExtrinsicCurvature.cpp)
+    and its covariant derivative (CovariantDerivOfExtrinsicCurvature.cpp)."""
+    phis = phi[:, 1:, :]                                 # Phi_{i j a}
+    dg3 = phi[:, 1:, 1:]                                 # d_k g_ij
+    K = 0.5 * pi[1:, 1:] + 0.5 * (np.einsum("ija,a->ij", phis, t_up)
+                                  + np.einsum("jia,a->ij", phis, t_up))
+    # Christoffel symbols of the spatial metric: Gamma_{c ab} = (d_b g_ca + d_a g_cb - d_c g_ab)/2
+    chr1 = 0.5 * (np.einsum("bca->cab", dg3) + np.einsum("acb->cab", dg3) - dg3)
+    chr2 = np.einsum("ij,jkl->ikl", ig, chr1)
+    # covariant derivative of K_ij
+    w = np.einsum("ca,kcb,b->ka", ipsi, phi, t_up) \
+        + 0.5 * np.outer(np.einsum("kcb,c,b->k", phi, t_up, t_up), t_up)
+    dphis = d_phi[:, :, 1:, :]                           # d_k Phi_{i j a}
+    cdk = (d_pi[:, 1:, 1:] + np.einsum("kija,a->kij", dphis, t_up)
+           + np.einsum("kjia,a->kij", dphis, t_up)
+           - np.einsum("ija,ka->kij", phis, w) - np.einsum("jia,ka->kij", phis, w))
+    cov_dK = 0.5 * cdk - np.einsum("lik,lj->kij", chr2, K) - np.einsum("ljk,li->kij", chr2, K)
+    # spatial Ricci tensor from Phi and d Phi
+    d3 = d_phi[:, :, 1:, 1:]                             # d_k Phi_{l i j}
+    ricci = 0.25 * (np.einsum("kl,jlki->ij", ig, d3) + np.einsum("kl,ilkj->ij", ig, d3)
+                    - np.einsum("kl,jikl->ij", ig, d3) - np.einsum("kl,ijkl->ij", ig, d3)
+                    + np.einsum("kl,kijl->ij", ig, d3) + np.einsum("kl,kjil->ij", ig, d3)
+                    - 2.0 * np.einsum("kl,lkij->ij", ig, d3))
+    phi_Ijj = 0.5 * np.einsum("kl,lij->kij", ig, dg3)
+    phi_ijK = 0.5 * np.einsum("kl,ijl->ijk", ig, dg3)
+    dm2b = np.einsum("kl,lii->k", ig, phi_ijK) - 2.0 * np.einsum("kl,iil->k", ig, phi_Ijj)
+    ricci = ricci + 0.5 * (np.einsum("ijk,k->ij", dg3, dm2b) + np.einsum("jik,k->ij", dg3, dm2b)
+                           - np.einsum("kij,k->ij", dg3, dm2b)) \
+        + np.einsum("ikl,jlk->ij", phi_ijK, phi_ijK) \
+        + 2.0 * np.einsum("kil,kjl->ij", phi_Ijj, phi_ijK) \
+        - 2.0 * np.einsum("kli,lkj->ij", phi_Ijj, phi_Ijj)
+    # adjust_phys_using_c4: add multiples of the four-index constraint
+    ricci = ricci + 0.25 * (np.einsum("kl,iklj->ij", ig, d3) - np.einsum("kl,kilj->ij", ig, d3)
+                            + np.einsum("kl,jkli->ij", ig, d3) - np.einsum("kl,kjli->ij", ig, d3))
+    ricci = ricci + 0.5 * (np.einsum("k,a,ikja->ij", n_up, t_up, dphis)
+                           - np.einsum("k,a,kija->ij", n_up, t_up, dphis)
+                           + np.einsum("k,a,jkia->ij", n_up, t_up, dphis)
+                           - np.einsum("k,a,kjia->ij", n_up, t_up, dphis))
+    # Weyl electric part and the incoming propagating mode (sign = -1)
+    weyl_e = ricci + np.einsum("kl,kl->", K, ig) * K - np.einsum("il,kl,kj->ij", K, ig, K)
+    sign = -1.0
+    tmp = weyl_e - sign * np.einsum("k,kij->ij", n_up, cov_dK) \
+        + sign * 0.5 * np.einsum("k,jik->ij", n_up, cov_dK) \
+        + sign * 0.5 * np.einsum("k,ijk->ij", n_up, cov_dK)
+    sp_up = ig - np.outer(n_up, n_up)
+    sp_lo = g[1:, 1:] - np.outer(n_lo, n_lo)
+    sp_mix = np.eye(3) - np.outer(n_up, n_lo)
+    weyl_minus = np.einsum("ki,lj,kl->ij", sp_mix, sp_mix, tmp) \
+        - 0.5 * np.einsum("kl,kl->", sp_up, tmp) * sp_lo
+    u3_minus = 2.0 * np.einsum("ia,jb,ij->ab", p_mix[1:, :], p_mix[1:, :], weyl_minus)
+    t = speeds[3] * u3_minus - speeds[3] * gamma2 * np.einsum("i,iab->ab", n_up, c3)
+    total = rhs_minus + t
+    return np.einsum("ac,bd,ab->cd", p_mix, p_mix, total) \
+        - 0.5 * np.einsum("ab,ab->", p_up, total) * p_lo
+
+
 def bjorhus_constraint_preserving(n_lo, g, pi, phi, coords, gamma1, gamma2, lapse, shift, ipsi,
-                                  t_up, c3, gauge, d_gauge, dt_g, dt_pi, dt_phi, d_pi, d_phi):
+                                  t_up, c3, gauge, d_gauge, dt_g, dt_pi, dt_phi, d_pi, d_phi,
+                                  physical=False):
     """ConstraintPreservingBjorhus::dg_time_derivative for Type ConstraintPreserving
-    on a static mesh, at one face point.  Arguments as the reference passes them
+    (physical=False) or ConstraintPreservingPhysical (physical=True) on a static
+    mesh, at one face point.  Arguments as the reference passes them
     (Bjorhus.cpp:104-148); returns the corrections (dt g, dt Pi, dt Phi) that are
     ADDED to the volume time derivative on the boundary points."""
     t_lo = np.zeros(4)
@@ -189,6 +253,9 @@ def bjorhus_constraint_preserving(n_lo, g, pi, phi, coords, gamma1, gamma2, laps
     s4 = uBv * np.outer(out_lo, in_lo)
     s5 = np.einsum("c,d,cd->", out_up, out_up, B) * np.outer(in_lo, in_lo)
     bc_minus = bc_minus + prefac * (s1 + s2 - s3 - s4 - s5) - rhs_minus
+    if physical:  # BjorhusImpl.cpp:534-593
+        bc_minus = bc_minus + physical_terms(gamma2, n_lo, n_up, t_up, p_lo, p_mix, p_up, ig, g,
+                                             ipsi, c3, rhs_minus, pi, phi, d_phi, d_pi, speeds)
     # only incoming characteristic fields are corrected (Bjorhus.cpp:38-47, :345-352)
     if speeds[0] > 0.0:
         bc_psi = np.zeros_like(bc_psi)

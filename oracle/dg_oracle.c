@@ -916,6 +916,7 @@ void orc_dg_rhs_oriented(int system, int N, int nelem, const double* D, const do
 /* external face with a TimeDerivative-type boundary condition (Bjorhus): no
  * boundary correction here, the caller adds the condition's dt corrections */
 #define ORC_BJORHUS (-2147483647)
+#define ORC_BJORHUS_PHYSICAL (-2147483646)
 
 void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const double* u,
                         const double* invjac, const double* static_fields,
@@ -988,7 +989,8 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
       double* dte = dt_u + (size_t)e * C * n;
       for (int d = 0; d < 6; ++d) {
         const int ne = nbr[e * 6 + d];
-        if (ne == -1 || ne == ORC_HANGING || ne == ORC_BJORHUS || (ne < -1 && ext_u == NULL))
+        if (ne == -1 || ne == ORC_HANGING || ne == ORC_BJORHUS || ne == ORC_BJORHUS_PHYSICAL ||
+            (ne < -1 && ext_u == NULL))
           continue;
         /* neighbour's face pointing back at us, and the face-point permutation */
         const int nf = (nbr_face && ne >= 0) ? nbr_face[e * 6 + d] : (d ^ 1);

@@ -499,7 +499,7 @@ def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC
         lib().orc_dg_rhs_mortars(system, N, nelem, _p(D), _p(u), _p(invjac),
                                  _p(static_fields), _p(coords), _p(nbr), _p(nf), _p(gp),
                                  _p(ext), nm, _p(mt), _p(P), _p(R), _p(dt))
-        if (nbr == BJORHUS).any():
+        if (nbr == BJORHUS).any() or (nbr == BJORHUS_PHYSICAL).any():
             dt += bjorhus_corrections(N, u, invjac, static_fields, coords, nbr, gauge_params)
     return dt
 
@@ -517,7 +517,7 @@ def bjorhus_corrections(N, u, invjac, static_fields, coords, nbr, gauge_params=G
     out = np.zeros_like(u)
     unpack = lambda v: np.array([[v[sym4(a, b)] for b in range(4)] for a in range(4)])
     for e in range(nelem):
-        faces = [d for d in range(6) if nbr[e, d] == BJORHUS]
+        faces = [d for d in range(6) if nbr[e, d] in (BJORHUS, BJORHUS_PHYSICAL)]
         if not faces:
             continue
         du = np.asarray(partial_derivatives(N, u[e], invjac[e])).reshape(50, 3, n)
@@ -560,7 +560,7 @@ def bjorhus_corrections(N, u, invjac, static_fields, coords, nbr, gauge_params=G
                 cg, cp, cph = bj.bjorhus_constraint_preserving(
                     n_lo, g, pi, phi, coords[e][:, p], static_fields[e][1, p],
                     static_fields[e][2, p], lapse, shift, ipsi, t_up, d_g - phi, H, dH,
-                    dt_g, dt_pi, dt_phi, d_pi, d_phi)
+                    dt_g, dt_pi, dt_phi, d_pi, d_phi, physical=nbr[e, d] == BJORHUS_PHYSICAL)
                 for s_, (aa, bb) in enumerate([(x, y) for x in range(4) for y in range(x, 4)]):
                     out[e][s_, p] += cg[aa, bb]
                     out[e][10 + s_, p] += cp[aa, bb]
@@ -847,7 +847,8 @@ def gh_constraint_norms(N, u, invjac, H=None):
 # ---------------------------------------------------------------------------
 MORTAR_FULL, MORTAR_LOWER_HALF, MORTAR_UPPER_HALF = 0, 1, 2
 HANGING = -2 ** 31   # neighbour-table entry of a face that is handled by the mortar table
-BJORHUS = -2 ** 31 + 1   # external face with ConstraintPreservingBjorhus
+BJORHUS = -2 ** 31 + 1   # external face with ConstraintPreservingBjorhus (ConstraintPreserving)
+BJORHUS_PHYSICAL = -2 ** 31 + 2   # ... Type ConstraintPreservingPhysical
 
 
 def legendre_vandermonde(num_points):

@@ -1,5 +1,6 @@
 // Pointwise algebra of gh::BoundaryConditions::ConstraintPreservingBjorhus,
-// Type ConstraintPreserving, static mesh (GeneralizedHarmonic/BoundaryConditions/
+// Types ConstraintPreserving and ConstraintPreservingPhysical, static mesh
+// (GeneralizedHarmonic/BoundaryConditions/
 // Bjorhus.cpp:104-391, compute_intermediate_vars :393-545, BjorhusImpl.cpp:26-221,
 // 496-532; constraints: Constraints.hpp Eq. (43)/(44) of Lindblom et al. 2005 as
 // implemented in Constraints.cpp:25-280 and :282-1262; characteristic fields
@@ -26,6 +27,7 @@ struct BjorhusInput {
   double H[4], dH[4][4];   // gauge source H_a and d_a H_b
   double dt_g[4][4], dt_pi[4][4], dt_phi[3][4][4];  // volume time derivative
   double d_pi[3][4][4], d_phi[3][3][4][4];          // d_i Pi_ab, d_i Phi_jab
+  bool physical;           // Type ConstraintPreservingPhysical (else ConstraintPreserving)
 };
 
 struct BjorhusOutput {
@@ -418,6 +420,134 @@ DG_HD_NOINLINE void bjorhus_constraint_preserving(const BjorhusInput& in, Bjorhu
         bc_minus[a][b] = v - rhs_minus[a][b];
       }
     (void)nc2;
+  }
+  if (in.physical) {
+    // add_physical_terms_to_dt_v_minus (BjorhusImpl.cpp:223-494; mu_phys = 0,
+    // adjust_phys_using_c4, gamma2_in_phys): incoming Weyl propagating mode U^{3-}
+    double K[3][3], chr2[3][3][3], w[3][4], cov_dK[3][3][3], ricci[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        K[i][j] = 0.5 * in.pi[i + 1][j + 1] + 0.5 * (phi_t[i][j + 1] + phi_t[j][i + 1]);
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k)
+        for (int l = 0; l < 3; ++l) {
+          double v = 0.0;
+          for (int j = 0; j < 3; ++j)   // Gamma_{j kl} = (d_l g_jk + d_k g_jl - d_j g_kl) / 2
+            v += ig[i][j] * 0.5 * (in.phi[l][j + 1][k + 1] + in.phi[k][j + 1][l + 1] -
+                                   in.phi[j][k + 1][l + 1]);
+          chr2[i][k][l] = v;
+        }
+    for (int k = 0; k < 3; ++k)
+      for (int a = 0; a < 4; ++a) {
+        double v = 0.5 * in.t_up[a] * phi_tt[k];
+        for (int c = 0; c < 4; ++c) v += in.ipsi[c][a] * phi_t[k][c];
+        w[k][a] = v;
+      }
+    for (int k = 0; k < 3; ++k)
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double v = in.d_pi[k][i + 1][j + 1];
+          for (int a = 0; a < 4; ++a) {
+            v += (in.d_phi[k][i][j + 1][a] + in.d_phi[k][j][i + 1][a]) * in.t_up[a];
+            v -= (in.phi[i][j + 1][a] + in.phi[j][i + 1][a]) * w[k][a];
+          }
+          v *= 0.5;
+          for (int l = 0; l < 3; ++l) v -= chr2[l][i][k] * K[l][j] + chr2[l][j][k] * K[l][i];
+          cov_dK[k][i][j] = v;
+        }
+    {
+      // spatial Ricci tensor of the GH variables (GeneralizedHarmonic/Ricci.cpp)
+      double pI[3][3][3], pK[3][3][3], dm2b[3];   // 1/2 g^{kl} d_l g_ij, 1/2 g^{kl} d_i g_jl
+      for (int k = 0; k < 3; ++k)
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) {
+            double v1 = 0.0, v2 = 0.0;
+            for (int l = 0; l < 3; ++l) {
+              v1 += ig[k][l] * in.phi[l][i + 1][j + 1];
+              v2 += ig[k][l] * in.phi[i][j + 1][l + 1];
+            }
+            pI[k][i][j] = 0.5 * v1;
+            pK[i][j][k] = 0.5 * v2;
+          }
+      for (int k = 0; k < 3; ++k) {
+        double v = 0.0;
+        for (int l = 0; l < 3; ++l)
+          for (int i = 0; i < 3; ++i) v += ig[k][l] * (pK[l][i][i] - 2.0 * pI[i][i][l]);
+        dm2b[k] = v;
+      }
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double v = 0.0;
+          for (int k = 0; k < 3; ++k)
+            for (int l = 0; l < 3; ++l) {
+              // d3[x][y][z][u] = d_x Phi_{y z u} (spatial)
+#define D3(x, y, z, u) in.d_phi[x][y][(z) + 1][(u) + 1]
+              v += 0.25 * ig[k][l] *
+                   (D3(j, l, k, i) + D3(i, l, k, j) - D3(j, i, k, l) - D3(i, j, k, l) +
+                    D3(k, i, j, l) + D3(k, j, i, l) - 2.0 * D3(l, k, i, j));
+              // adjust_phys_using_c4
+              v += 0.25 * ig[k][l] *
+                   (D3(i, k, l, j) - D3(k, i, l, j) + D3(j, k, l, i) - D3(k, j, l, i));
+#undef D3
+              v += pK[i][k][l] * pK[j][l][k] + 2.0 * pI[k][i][l] * pK[k][j][l] -
+                   2.0 * pI[k][l][i] * pI[l][k][j];
+            }
+          for (int k = 0; k < 3; ++k) {
+            v += 0.5 * (in.phi[i][j + 1][k + 1] + in.phi[j][i + 1][k + 1] -
+                        in.phi[k][i + 1][j + 1]) * dm2b[k];
+            double c4t = 0.0;
+            for (int a = 0; a < 4; ++a)
+              c4t += in.t_up[a] * (in.d_phi[i][k][j + 1][a] - in.d_phi[k][i][j + 1][a] +
+                                   in.d_phi[j][k][i + 1][a] - in.d_phi[k][j][i + 1][a]);
+            v += 0.5 * n_up[k] * c4t;
+          }
+          ricci[i][j] = v;
+        }
+    }
+    double trK = 0.0;
+    for (int k = 0; k < 3; ++k)
+      for (int l = 0; l < 3; ++l) trK += K[k][l] * ig[k][l];
+    double tmp[3][3], tr_tmp = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double v = ricci[i][j] + trK * K[i][j];
+        for (int k = 0; k < 3; ++k)
+          for (int l = 0; l < 3; ++l) v -= K[i][l] * ig[k][l] * K[k][j];
+        // incoming mode: sign = -1 (WeylPropagating.cpp)
+        for (int k = 0; k < 3; ++k)
+          v += n_up[k] * (cov_dK[k][i][j] - 0.5 * cov_dK[j][i][k] - 0.5 * cov_dK[i][j][k]);
+        tmp[i][j] = v;
+      }
+    for (int k = 0; k < 3; ++k)
+      for (int l = 0; l < 3; ++l) tr_tmp += (ig[k][l] - n_up[k] * n_up[l]) * tmp[k][l];
+    double weyl[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double v = 0.0;
+        for (int k = 0; k < 3; ++k)
+          for (int l = 0; l < 3; ++l)
+            v += ((k == i ? 1.0 : 0.0) - n_up[k] * in.n_lo[i]) *
+                 ((l == j ? 1.0 : 0.0) - n_up[l] * in.n_lo[j]) * tmp[k][l];
+        weyl[i][j] = v - 0.5 * tr_tmp * (in.g[i + 1][j + 1] - in.n_lo[i] * in.n_lo[j]);
+      }
+    double total[4][4], tr_total = 0.0;
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) {
+        double u3 = 0.0, nc = 0.0;
+        for (int i = 0; i < 3; ++i) {
+          nc += n_up[i] * in.c3[i][a][b];
+          for (int j = 0; j < 3; ++j) u3 += p_mix[i + 1][a] * p_mix[j + 1][b] * weyl[i][j];
+        }
+        total[a][b] = rhs_minus[a][b] + speed[3] * (2.0 * u3 - in.gamma2 * nc);
+        tr_total += p_up[a][b] * total[a][b];
+      }
+    for (int c = 0; c < 4; ++c)
+      for (int d = 0; d < 4; ++d) {
+        double v = 0.0;
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) v += p_mix[a][c] * p_mix[b][d] * total[a][b];
+        bc_minus[c][d] += v - 0.5 * tr_total * p_lo[c][d];
+      }
   }
   // only incoming fields are corrected (Bjorhus.cpp:38-47, :345-352)
   const double k0 = speed[0] > 0.0 ? 0.0 : 1.0, k1 = speed[1] > 0.0 ? 0.0 : 1.0,

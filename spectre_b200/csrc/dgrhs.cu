@@ -341,7 +341,7 @@ struct dgrhs_ctx {
   unsigned long long* violations = nullptr;  // DemandOutgoingCharSpeeds status (device)
   // ConstraintPreservingBjorhus faces (DGRHS_NEIGHBOR_BJORHUS in the neighbour table)
   int n_bjorhus_faces = 0;
-  int32_t* bjorhus_faces = nullptr;  // [n][2]
+  int32_t* bjorhus_faces = nullptr;  // [n][3] element, direction, physical
   // non-conforming mortars (dgrhs_set_mortars)
   int n_mortar_faces = 0;
   int32_t* mortar_faces = nullptr;   // [n_mortar_faces][4]
@@ -789,7 +789,7 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   for (size_t i = 0; i < (size_t)c->nelem * 6; ++i) {
     const int v = neighbors[i];
     if (v == DGRHS_NEIGHBOR_HANGING) continue;  // non-conforming face: dgrhs_set_mortars
-    if (v == DGRHS_NEIGHBOR_BJORHUS) {
+    if (v == DGRHS_NEIGHBOR_BJORHUS || v == DGRHS_NEIGHBOR_BJORHUS_PHYSICAL) {
       if (c->system != DGRHS_SYSTEM_GH)
         return fail("ConstraintPreservingBjorhus is a GeneralizedHarmonic boundary condition");
       if (!coords) return fail("ConstraintPreservingBjorhus needs inertial coordinates");
@@ -825,10 +825,13 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   std::vector<int32_t> bj;
   for (int e = 0; e < c->nelem; ++e)
     for (int d = 0; d < 6; ++d)
-      if (neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS) bj.insert(bj.end(), {e, d});
+      if (neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS ||
+          neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS_PHYSICAL)
+        bj.insert(bj.end(),
+                  {e, d, neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS_PHYSICAL});
   if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
   c->bjorhus_faces = nullptr;
-  c->n_bjorhus_faces = (int)(bj.size() / 2);
+  c->n_bjorhus_faces = (int)(bj.size() / 3);
   if (!bj.empty()) {
     CU(cudaMalloc(&c->bjorhus_faces, bj.size() * 4));
     CU(cudaMemcpy(c->bjorhus_faces, bj.data(), bj.size() * 4, cudaMemcpyHostToDevice));

@@ -845,7 +845,8 @@ __device__ __forceinline__ void atomic_min_negative(unsigned long long* addr, do
 constexpr int32_t kHangingFace = INT32_MIN;
 // external face with the ConstraintPreservingBjorhus boundary condition: skipped
 // by the face kernels, gh_bjorhus_kernel writes its (unlifted) dt corrections
-constexpr int32_t kBjorhusFace = INT32_MIN + 1;
+constexpr int32_t kBjorhusFace = INT32_MIN + 1;          // Type ConstraintPreserving
+constexpr int32_t kBjorhusPhysicalFace = INT32_MIN + 2;  // Type ConstraintPreservingPhysical
 
 // neighbour-side face coordinates of our face point (qa, qb)
 template <int N>
@@ -888,7 +889,8 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
-  if (nb == kHangingFace || nb == kBjorhusFace) return;  // written by mortar / Bjorhus kernel
+  if (nb == kHangingFace || nb == kBjorhusFace || nb == kBjorhusPhysicalFace)
+    return;  // written by the mortar / Bjorhus kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
   int na_, nb_;
@@ -1016,7 +1018,8 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
-  if (nb == kHangingFace || nb == kBjorhusFace) return;  // written by mortar / Bjorhus kernel
+  if (nb == kHangingFace || nb == kBjorhusFace || nb == kBjorhusPhysicalFace)
+    return;  // written by the mortar / Bjorhus kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
   int na_, nb_;
@@ -1325,7 +1328,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
 }
 
 // --------------------------------------------------------------------------
-// ConstraintPreservingBjorhus (Type ConstraintPreserving) on external faces:
+// ConstraintPreservingBjorhus (both types) on external faces:
 // a TimeDerivative-type boundary condition (BoundaryConditionsImpl.hpp:566-670):
 // the reference slices the volume time derivative and the volume partial
 // derivatives to the face and adds the returned corrections to dt on the face
@@ -1345,14 +1348,15 @@ struct BjorhusArgs {
   const double* coords;
   const double* D;
   double* corr;
-  const int32_t* faces;  // [n][2] = element, direction
+  const int32_t* faces;  // [n][3] = element, direction, physical (0/1)
 };
 
 // Everything that does not depend on N: volume time derivative at the point,
 // the boundary condition's inputs, the condition itself.  One (not inlined) copy.
 // d = face direction, dlog[c][jhat] = logical derivatives, corr[50] in Variables
 // component order.
-static __device__ __noinline__ void gh_bjorhus_point(bool harmonic, int d, const double (&g)[10],
+static __device__ __noinline__ void gh_bjorhus_point(bool harmonic, bool physical, int d,
+                                                     const double (&g)[10],
                                                      const double (&pi)[10],
                                                      const double (&phi)[3][10],
                                                      const double (&J)[3][3], double gamma0,
@@ -1382,6 +1386,7 @@ static __device__ __noinline__ void gh_bjorhus_point(bool harmonic, int d, const
     }
   }
   BjorhusInput in;
+  in.physical = physical;
   {
     const double sign = (d & 1) ? 1.0 : -1.0;
     const int dim = d >> 1;
@@ -1459,7 +1464,8 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32)
   __syncthreads();
   const int tid = threadIdx.x;
   if (tid >= f) return;
-  const int e = a.faces[2 * blockIdx.x], d = a.faces[2 * blockIdx.x + 1];
+  const int e = a.faces[3 * blockIdx.x], d = a.faces[3 * blockIdx.x + 1];
+  const bool physical = a.faces[3 * blockIdx.x + 2] != 0;
   const int qa = tid % N, qb = tid / N;
   const int p = face_point<N>(d, qa, qb);
   const int i = p % N, j = (p / N) % N, k = p / (N * N);
@@ -1510,7 +1516,8 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32)
     dlog[c][2] = d2;
   }
   double corr[50];
-  gh_bjorhus_point(harmonic, d, g, pi, phi, J, gamma0, gamma1, gamma2, gh, x, dlog, corr);
+  gh_bjorhus_point(harmonic, physical, d, g, pi, phi, J, gamma0, gamma1, gamma2, gh, x, dlog,
+                   corr);
   double* cf = a.corr + (size_t)e * 10 * 30 * f + (size_t)d * 5 * f + tid;
 #pragma unroll 1
   for (int s = 0; s < 10; ++s) {

@@ -75,8 +75,9 @@ class Problem:
         a predicate (global element, direction) -> bool.
         demand_outgoing: DemandOutgoingCharSpeeds on the remaining external faces
         (no correction, characteristic speeds checked); None = off.
-        bjorhus: predicate (global element, direction) -> bool selecting external
-        faces with ConstraintPreservingBjorhus (Type ConstraintPreserving).
+        bjorhus: function (global element, direction) -> None / "ConstraintPreserving" /
+        "ConstraintPreservingPhysical" selecting external faces with
+        ConstraintPreservingBjorhus of that type.
         analytic_christoffel_gauge: AnalyticChristoffel gauge of the (static)
         analytic solution instead of the harmonic gauge."""
         self.bjorhus = bjorhus
@@ -150,9 +151,10 @@ def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2
     """BASELINE.json configs[2]: Kerr-Schild black hole (M = 1, a = 0) on the
     spherical shell of KerrSchild.yaml:80-98 (Sphere, InnerRadius 1.9, OuterRadius
     2.3, equiangular wedges, Logarithmic radial distribution, excised interior),
-    DirichletAnalytic on the outer boundary and DirichletAnalytic (as in the input
-    file) or DemandOutgoingCharSpeeds (as in EvolveGhSingleBlackHole set-ups, the
-    excision surface lies inside the horizon) on the excision boundary,
+    DirichletAnalytic (as in the input file) or ConstraintPreservingBjorhus of type
+    "ConstraintPreserving" / "ConstraintPreservingPhysical" on the outer boundary and
+    DirichletAnalytic or DemandOutgoingCharSpeeds (as in EvolveGhSingleBlackHole
+    set-ups, the excision surface lies inside the horizon) on the excision boundary,
     AnalyticChristoffel gauge, GaussianPlusConstant damping (:108-125)."""
     shell = domain.SphericalShell(inner_radius, outer_radius, refinement, N,
                                   radial_partitioning, radial_distribution, order=order)
@@ -162,12 +164,14 @@ def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2
            lambda x: analytic.gaussian_plus_constant(x, 0.001, 1.0, w))
     if inner_boundary not in ("DirichletAnalytic", "DemandOutgoingCharSpeeds"):
         raise ValueError(inner_boundary)
-    if outer_boundary not in ("DirichletAnalytic", "ConstraintPreservingBjorhus"):
+    if outer_boundary not in ("DirichletAnalytic", "ConstraintPreserving",
+                              "ConstraintPreservingPhysical"):
         raise ValueError(outer_boundary)
     ghost_dirs = {d for d, bc in ((4, inner_boundary), (5, outer_boundary))
                   if bc == "DirichletAnalytic"}
     outgoing = inner_boundary == "DemandOutgoingCharSpeeds"
-    bjorhus = (lambda g, d: d == 5) if outer_boundary == "ConstraintPreservingBjorhus" else None
+    bjorhus = ((lambda g, d: outer_boundary if d == 5 else None)
+               if outer_boundary != "DirichletAnalytic" else None)
     ghost = (lambda g, d: d in ghost_dirs) if ghost_dirs else False
     return Problem(lib.SYSTEM_GH, shell, lambda x, t: analytic.kerr_schild(x, mass), gam,
                    dirichlet_analytic=ghost, analytic_christoffel_gauge=True,
@@ -215,8 +219,10 @@ class Evolution:
             ln = self.part.local_neighbors
             for le, g in enumerate(ids):
                 for d in range(6):
-                    if ln[le, d] == -1 and problem.bjorhus(int(g), d):
-                        ln[le, d] = lib.BJORHUS
+                    kind = problem.bjorhus(int(g), d) if ln[le, d] == -1 else None
+                    if kind:
+                        ln[le, d] = (lib.BJORHUS_PHYSICAL if kind == "ConstraintPreservingPhysical"
+                                     else lib.BJORHUS)
         ctx.set_geometry(problem.inverse_jacobian(ids), problem.coords(ids),
                          self.part.local_neighbors)
         if self.part.oriented:

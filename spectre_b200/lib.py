@@ -44,7 +44,8 @@ _lib = None
 
 
 HANGING = -2 ** 31   # DGRHS_NEIGHBOR_HANGING
-BJORHUS = -2 ** 31 + 1   # DGRHS_NEIGHBOR_BJORHUS
+BJORHUS = -2 ** 31 + 1   # DGRHS_NEIGHBOR_BJORHUS (Type ConstraintPreserving)
+BJORHUS_PHYSICAL = -2 ** 31 + 2   # DGRHS_NEIGHBOR_BJORHUS_PHYSICAL
 
 
 def projection_matrix(N, child_to_parent, size):

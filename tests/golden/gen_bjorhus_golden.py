@@ -9,7 +9,8 @@ test tree and writes tests/golden/bjorhus.npz: random per-point inputs (the
 argument list of dt_*_ConstraintPreserving_static_mesh, as the reference's
 Test_Bjorhus.cpp feeds them: every argument an independent random tensor) and
 the outputs: two_index_constraint, f_constraint, and the corrections to
-dt spacetime_metric / Pi / Phi.
+dt spacetime_metric / Pi / Phi for both types (ConstraintPreserving and
+ConstraintPreservingPhysical).
 """
 import os
 import sys
@@ -36,7 +37,7 @@ def main():
             "d_spacetime_metric", "d_pi", "d_phi"]
     data = {k: [] for k in keys}
     out = {k: [] for k in ("two_index_constraint", "f_constraint", "corr_g", "corr_pi", "corr_phi",
-                           "char_speeds")}
+                           "char_speeds", "phys_corr_pi", "phys_corr_phi")}
     u = lambda *shape: rng.uniform(-1.0, 1.0, shape)
     for p in range(npts):
         d = {
@@ -57,6 +58,11 @@ def main():
         out["corr_pi"].append(bj.dt_pi_ConstraintPreserving_static_mesh(*[
             a.copy() if isinstance(a, np.ndarray) else a for a in args]))
         out["corr_phi"].append(bj.dt_phi_ConstraintPreserving_static_mesh(*[
+            a.copy() if isinstance(a, np.ndarray) else a for a in args]))
+        # Type ConstraintPreservingPhysical (dt g is the same for both types)
+        out["phys_corr_pi"].append(bj.dt_pi_ConstraintPreservingPhysical_static_mesh(*[
+            a.copy() if isinstance(a, np.ndarray) else a for a in args]))
+        out["phys_corr_phi"].append(bj.dt_phi_ConstraintPreservingPhysical_static_mesh(*[
             a.copy() if isinstance(a, np.ndarray) else a for a in args]))
         t_lo = np.zeros(4)
         t_lo[0] = -d["lapse"]

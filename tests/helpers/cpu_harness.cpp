@@ -182,7 +182,7 @@ void h_sw_face(int f, const double* ui, const double* ue, const double* ni,
 // ConstraintPreservingBjorhus at npts independent points; every array is
 // [npts][...] in C order with the argument list of the reference's
 // dt_*_ConstraintPreserving_static_mesh twins.
-void h_bjorhus_cp(int npts, const double* n_lo, const double* g, const double* pi,
+void h_bjorhus_cp(int npts, int physical, const double* n_lo, const double* g, const double* pi,
                   const double* phi, const double* x, const double* gamma1,
                   const double* gamma2, const double* lapse, const double* shift,
                   const double* ipsi, const double* t_up, const double* c3, const double* H,
@@ -214,6 +214,7 @@ void h_bjorhus_cp(int npts, const double* n_lo, const double* g, const double* p
     cp(&in.dt_phi[0][0][0], dt_phi, 48);
     cp(&in.d_pi[0][0][0], d_pi, 48);
     cp(&in.d_phi[0][0][0][0], d_phi, 144);
+    in.physical = physical != 0;
     dg::bjorhus_constraint_preserving(in, out);
     for (int k = 0; k < 16; ++k) {
       out_g[(size_t)p * 16 + k] = (&out.g[0][0])[k];

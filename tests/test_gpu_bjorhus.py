@@ -1,4 +1,5 @@
-"""ConstraintPreservingBjorhus (Type ConstraintPreserving) through the C-ABI:
+"""ConstraintPreservingBjorhus (Types ConstraintPreserving and
+ConstraintPreservingPhysical) through the C-ABI:
 gh_bjorhus_kernel against the oracle (oracle/bjorhus.py, pinned to the
 reference's Bjorhus.py), on a Brick and on the outer boundary of the Kerr-Schild
 shell.  Reference: GeneralizedHarmonic/BoundaryConditions/Bjorhus.cpp,
@@ -20,8 +21,9 @@ def _relerr(a, b, blocks):
     return max(np.max(np.abs(a[:, s] - b[:, s])) / np.max(np.abs(b[:, s])) for s in blocks)
 
 
-@pytest.mark.parametrize("N", [3, 6])
-def test_bjorhus_on_brick_faces_matches_oracle(N):
+@pytest.mark.parametrize("N,kind", [(3, lib.BJORHUS), (6, lib.BJORHUS), (4, lib.BJORHUS_PHYSICAL),
+                                    (7, lib.BJORHUS_PHYSICAL)])
+def test_bjorhus_on_brick_faces_matches_oracle(N, kind):
     """Gauge wave on a Brick away from the origin, periodic in y and z, Bjorhus on
     both x faces, harmonic gauge, perturbed state and Jacobian."""
     rng = np.random.default_rng(N)
@@ -29,7 +31,7 @@ def test_bjorhus_on_brick_faces_matches_oracle(N):
                          periodic=(False, True, True))
     x, nbr = brick.coords(), brick.neighbors().copy()
     assert (nbr == -1).sum() == 8
-    nbr[nbr == -1] = lib.BJORHUS
+    nbr[nbr == -1] = kind
     J = brick.inverse_jacobian() + 0.05 * rng.uniform(-1, 1, (brick.n_elements, 9, N ** 3))
     u = analytic.gauge_wave(x, 0.1) + 1e-2 * rng.uniform(-1, 1, (brick.n_elements, 50, N ** 3))
     stat = rng.uniform(-1, 1, (brick.n_elements, 3, N ** 3))
@@ -42,7 +44,10 @@ def test_bjorhus_on_brick_faces_matches_oracle(N):
     ref = orc.dg_rhs(1, N, u, J, stat, nbr, coords=x)
     assert _relerr(got, ref, GH_BLOCKS) < TOL
     # the boundary condition matters
-    plain = orc.dg_rhs(1, N, u, J, stat, np.where(nbr == lib.BJORHUS, -1, nbr), coords=x)
+    plain = orc.dg_rhs(1, N, u, J, stat, np.where(nbr == kind, -1, nbr), coords=x)
+    other = lib.BJORHUS if kind == lib.BJORHUS_PHYSICAL else lib.BJORHUS_PHYSICAL
+    assert _relerr(orc.dg_rhs(1, N, u, J, stat, np.where(nbr == kind, other, nbr), coords=x),
+                   ref, GH_BLOCKS) > 1e-3      # the two types differ
     assert _relerr(plain, ref, GH_BLOCKS) > 1e-3
     # and an AB2 evolution
     dt = 1e-4
@@ -55,17 +60,19 @@ def test_bjorhus_on_brick_faces_matches_oracle(N):
     ctx.close()
 
 
-def test_bjorhus_on_kerr_schild_shell():
+@pytest.mark.parametrize("kind", ["ConstraintPreserving", "ConstraintPreservingPhysical"])
+def test_bjorhus_on_kerr_schild_shell(kind):
     """Kerr-Schild shell with DemandOutgoingCharSpeeds on the excision sphere and
     ConstraintPreservingBjorhus on the outer sphere (the boundary conditions of
     the single-black-hole executables), AnalyticChristoffel gauge (gauge fields)."""
     N = 5
     problem = evolution.gh_kerr_schild_shell_problem(
         (0, 0), N, inner_radius=1.9, outer_radius=6.0,
-        inner_boundary="DemandOutgoingCharSpeeds", outer_boundary="ConstraintPreservingBjorhus")
+        inner_boundary="DemandOutgoingCharSpeeds", outer_boundary=kind)
     ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, 1e-4)
     ctx, part = ev.ctx, ev.part
-    assert (part.local_neighbors == lib.BJORHUS).sum() == 6 and not part.external_faces
+    code = lib.BJORHUS_PHYSICAL if kind == "ConstraintPreservingPhysical" else lib.BJORHUS
+    assert (part.local_neighbors == code).sum() == 6 and not part.external_faces
     ids = part.global_ids
     x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
     u0 = problem.u0(ids, 0.0)

@@ -347,3 +347,22 @@ def test_bjorhus_constraint_preserving_vs_reference_numpy(golden_dir):
         np.testing.assert_allclose(cp, z["out_corr_pi"][p], rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(cph, z["out_corr_phi"][p], rtol=1e-12, atol=1e-12)
     assert 0 < incoming < n + 1
+
+
+def test_bjorhus_physical_vs_reference_numpy(golden_dir):
+    """Type ConstraintPreservingPhysical (Weyl propagating mode U^{3-}, spatial
+    Ricci tensor and covariant derivative of the extrinsic curvature from the GH
+    variables) against the reference's Bjorhus.py."""
+    from oracle import bjorhus as bj
+    z = np.load(os.path.join(golden_dir, "bjorhus.npz"))
+    for p in range(len(z["in_lapse"])):
+        I = {k[3:]: z[k][p] for k in z.files if k.startswith("in_")}
+        cg, cp, cph = bj.bjorhus_constraint_preserving(
+            I["normal_covector"], I["spacetime_metric"], I["pi"], I["phi"], I["coords"],
+            I["gamma1"], I["gamma2"], I["lapse"], I["shift"], I["inverse_spacetime_metric"],
+            I["spacetime_unit_normal_vector"], I["three_index_constraint"], I["gauge_source"],
+            I["spacetime_deriv_gauge_source"], I["dt_spacetime_metric"], I["dt_pi"], I["dt_phi"],
+            I["d_pi"], I["d_phi"], physical=True)
+        np.testing.assert_allclose(cg, z["out_corr_g"][p], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(cp, z["out_phys_corr_pi"][p], rtol=1e-12, atol=2e-12)
+        np.testing.assert_allclose(cph, z["out_phys_corr_phi"][p], rtol=1e-12, atol=2e-12)

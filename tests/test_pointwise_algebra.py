@@ -143,12 +143,12 @@ def test_gh_volume_split_algebra(harness):
         assert _maxrel(dt[blk], ref[blk]) < 1e-13
 
 
-def test_bjorhus_algebra_vs_reference_fixtures(harness, golden_dir):
+@pytest.mark.parametrize("physical", [False, True])
+def test_bjorhus_algebra_vs_reference_fixtures(harness, golden_dir, physical):
     """The product's pointwise ConstraintPreservingBjorhus algebra
-    (spectre_b200/csrc/bjorhus.cuh, compiled for the host) against the fixtures
-    made from the reference's Bjorhus.py with independent random tensors for every
-    argument, and against the oracle."""
-    from oracle import bjorhus as bj
+    (spectre_b200/csrc/bjorhus.cuh, compiled for the host), both types, against
+    the fixtures made from the reference's Bjorhus.py with independent random
+    tensors for every argument."""
     z = np.load(os.path.join(golden_dir, "bjorhus.npz"))
     n = len(z["in_lapse"])
     c = np.ascontiguousarray
@@ -159,9 +159,11 @@ def test_bjorhus_algebra_vs_reference_fixtures(harness, golden_dir):
             "three_index_constraint", "gauge_source", "spacetime_deriv_gauge_source",
             "dt_spacetime_metric", "dt_pi", "dt_phi", "d_pi", "d_phi"]
     arrays = [c(z["in_" + k], dtype=np.float64) for k in keys]
-    harness.h_bjorhus_cp(n, *[a.ctypes.data_as(ctypes.c_void_p) for a in arrays],
+    harness.h_bjorhus_cp(n, int(physical), *[a.ctypes.data_as(ctypes.c_void_p) for a in arrays],
                          P(out_g), P(out_pi), P(out_phi))
-    scale = np.abs(z["out_corr_pi"]).max()
+    want_pi = z["out_phys_corr_pi"] if physical else z["out_corr_pi"]
+    want_phi = z["out_phys_corr_phi"] if physical else z["out_corr_phi"]
+    scale = np.abs(want_pi).max()
     assert np.max(np.abs(out_g - z["out_corr_g"])) < 1e-12 * scale
-    assert np.max(np.abs(out_pi - z["out_corr_pi"])) < 1e-12 * scale
-    assert np.max(np.abs(out_phi - z["out_corr_phi"])) < 1e-12 * scale
+    assert np.max(np.abs(out_pi - want_pi)) < 1e-12 * scale
+    assert np.max(np.abs(out_phi - want_phi)) < 1e-12 * scale
