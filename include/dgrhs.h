@@ -210,7 +210,7 @@ int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
  * computed from the volume time derivative, the volume partial derivatives, the
  * gauge source and the constraint fields on the face are added to dt(g, Pi,
  * Phi) on the face points.  Needs inertial coordinates (dgrhs_set_geometry) and
- * the Harmonic gauge or gauge fields; static mesh. */
+ * any of the gauges; static mesh. */
 #define DGRHS_NEIGHBOR_BJORHUS (-2147483647)
 #define DGRHS_NEIGHBOR_BJORHUS_PHYSICAL (-2147483646)
 int dgrhs_set_mortars(dgrhs_ctx* ctx, int n_mortars, const int32_t* mortars);

@@ -551,7 +551,14 @@ def bjorhus_corrections(N, u, invjac, static_fields, coords, nbr, gauge_params=G
                 d_pi = np.array([unpack(du[10:20, i, p]) for i in range(3)])
                 d_phi = np.array([[unpack(np.array([du[20 + m + 3 * s, i, p] for s in range(10)]))
                                    for m in range(3)] for i in range(3)])
-                if given:
+                if gauge_params[0] == 2.0:   # DampedHarmonic: evaluate it at the point
+                    H, dH = np.zeros(4), np.zeros((4, 4))
+                    P_ = lambda a_: np.ascontiguousarray(a_, dtype=np.float64)
+                    gg, pp, ff = P_(g), P_(pi), P_(phi)
+                    xx, gp_ = P_(coords[e][:, p]), P_(gauge_params)
+                    lib().orc_damped_harmonic(_p(gg), _p(pp), _p(ff), _p(xx), _p(gp_), _p(H),
+                                              _p(dH))
+                elif given:
                     H = static_fields[e][3:7, p]
                     dH = np.array([[static_fields[e][7 + aa + 4 * bb, p] for bb in range(4)]
                                    for aa in range(4)])

@@ -341,6 +341,7 @@ struct dgrhs_ctx {
   unsigned long long* violations = nullptr;  // DemandOutgoingCharSpeeds status (device)
   // ConstraintPreservingBjorhus faces (DGRHS_NEIGHBOR_BJORHUS in the neighbour table)
   int n_bjorhus_faces = 0;
+  int64_t aux_faces_eval = -1;       // RHS evaluation that already ran the Bjorhus/mortar kernels
   int32_t* bjorhus_faces = nullptr;  // [n][3] element, direction, physical
   // non-conforming mortars (dgrhs_set_mortars)
   int n_mortar_faces = 0;
@@ -428,21 +429,27 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
     dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
   ++g_launches;
   CU(cudaGetLastError());
-  // ConstraintPreservingBjorhus faces (all at once, with the boundary-element pass)
-  if (c->n_bjorhus_faces > 0 && pass != 1) {
-    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC)
-      return fail("ConstraintPreservingBjorhus with the DampedHarmonic gauge is not implemented");
+  // Bjorhus faces and non-conforming mortars need no halo data: all of them are
+  // evaluated once per right-hand side, with whichever pass comes first, so that
+  // their corrections are in place before ANY volume kernel of this evaluation
+  const bool aux_now = c->aux_faces_eval != c->rhs_evals;
+  c->aux_faces_eval = c->rhs_evals;
+  if (c->n_bjorhus_faces > 0 && aux_now) {
     dg::BjorhusArgs b{c->u, c->invjac, c->stat, c->gH, c->gdH, c->coords, c->D, c->corr,
-                      c->bjorhus_faces};
+                      c->bjorhus_faces, {}};
+    int gauge_mode = 1;
+    if (c->gauge == DGRHS_GAUGE_HARMONIC) gauge_mode = 0;
+    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+      const double* p = c->gauge_params;
+      b.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+      gauge_mode = 2;
+    }
     constexpr int bT = (N * N + 31) / 32 * 32;
-    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->stream>>>(
-        b, c->gauge == DGRHS_GAUGE_HARMONIC);
+    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->stream>>>(b, gauge_mode);
     ++g_launches;
     CU(cudaGetLastError());
   }
-  // non-conforming mortars: with the pass that covers the boundary elements (all
-  // mortars of a context are evaluated at once)
-  if (c->n_mortar_faces > 0 && pass != 1) {
+  if (c->n_mortar_faces > 0 && aux_now) {
     dg::MortarArgs m{c->u, c->invjac, c->stat, c->corr, c->mortar_faces, c->mortar_table,
                      c->mortar_P, c->mortar_R};
     constexpr int msmem = dg::mortar_smem_bytes<N>();
@@ -1534,6 +1541,7 @@ int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
       switch (c->N) {
 #define X(NN)                                                                     \
   case NN:                                                                        \
+    if (which == 0) c->aux_faces_eval = -1; /* time Bjorhus/mortar kernels too */ \
     if (which == 0) rc = launch_faces<NN>(c, 0, c->nelem);                        \
     if (which == 1) rc = launch_volume<NN>(c, c->dt_last, 0, c->nelem, true);     \
     if (which == 3) rc = launch_volume<NN>(c, scratch, 0, c->nelem, true, fused); \

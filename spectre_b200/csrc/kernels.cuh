@@ -1349,19 +1349,21 @@ struct BjorhusArgs {
   const double* D;
   double* corr;
   const int32_t* faces;  // [n][3] = element, direction, physical (0/1)
+  DampedHarmonicParams dh;
 };
 
 // Everything that does not depend on N: volume time derivative at the point,
 // the boundary condition's inputs, the condition itself.  One (not inlined) copy.
 // d = face direction, dlog[c][jhat] = logical derivatives, corr[50] in Variables
 // component order.
-static __device__ __noinline__ void gh_bjorhus_point(bool harmonic, bool physical, int d,
+static __device__ __noinline__ void gh_bjorhus_point(int gauge, const DampedHarmonicParams& dh,
+                                                     bool physical, int d,
                                                      const double (&g)[10],
                                                      const double (&pi)[10],
                                                      const double (&phi)[3][10],
                                                      const double (&J)[3][3], double gamma0,
                                                      double gamma1, double gamma2,
-                                                     const GaugeH& gh, const double (&x)[3],
+                                                     GaugeH& gh, const double (&x)[3],
                                                      const double (&dlog)[50][3],
                                                      double (&corr)[50]) {
   GhContext ctx;
@@ -1369,10 +1371,17 @@ static __device__ __noinline__ void gh_bjorhus_point(bool harmonic, bool physica
   {
     GaugeInput gin;
     gin.fields = &gh;
-    if (harmonic)
+    if (gauge == 0) {
       gh_prologue<0>(g, pi, phi, J, gamma0, gamma1, gamma2, gin, ctx, Q);
-    else
+    } else if (gauge == 1) {
       gh_prologue<1>(g, pi, phi, J, gamma0, gamma1, gamma2, gin, ctx, Q);
+    } else {
+      // DampedHarmonic: the prologue evaluates H_a and d_a H_b at the point; keep them
+      gin.dh = dh;
+      for (int xx = 0; xx < 3; ++xx) gin.x[xx] = x[xx];
+      gin.computed = &gh;
+      gh_prologue<2>(g, pi, phi, J, gamma0, gamma1, gamma2, gin, ctx, Q);
+    }
 #pragma unroll 1
     for (int s = 0; s < 10; ++s) {
       double ph[3], dph[3][3], oph[3];
@@ -1455,9 +1464,10 @@ static __device__ __noinline__ void gh_bjorhus_point(bool harmonic, bool physica
     }
 }
 
+// gauge: 0 Harmonic, 1 gauge fields from memory, 2 DampedHarmonic
 template <int N>
 __global__ void __launch_bounds__((N * N + 31) / 32 * 32)
-    gh_bjorhus_kernel(BjorhusArgs a, bool harmonic) {
+    gh_bjorhus_kernel(BjorhusArgs a, int gauge) {
   constexpr int npad = Cfg<N>::npad, f = N * N, T = (N * N + 31) / 32 * 32;
   __shared__ double sD[N * N];
   for (int idx = threadIdx.x; idx < N * N; idx += T) sD[idx] = a.D[idx];
@@ -1491,7 +1501,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32)
     gh.H[xx] = 0.0;
     for (int y = 0; y < 4; ++y) gh.dH[xx][y] = 0.0;
   }
-  if (!harmonic) {
+  if (gauge == 1) {
     const double* he = a.gH + (size_t)e * 4 * npad + p;
     const double* dhe = a.gdH + (size_t)e * 16 * npad + p;
     for (int xx = 0; xx < 4; ++xx) {
@@ -1516,7 +1526,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32)
     dlog[c][2] = d2;
   }
   double corr[50];
-  gh_bjorhus_point(harmonic, physical, d, g, pi, phi, J, gamma0, gamma1, gamma2, gh, x, dlog,
+  gh_bjorhus_point(gauge, a.dh, physical, d, g, pi, phi, J, gamma0, gamma1, gamma2, gh, x, dlog,
                    corr);
   double* cf = a.corr + (size_t)e * 10 * 30 * f + (size_t)d * 5 * f + tid;
 #pragma unroll 1

@@ -207,6 +207,7 @@ struct GaugeInput {
   const GaugeH* fields;          // kGauge == 1
   DampedHarmonicParams dh;       // kGauge == 2
   double x[3];                   // kGauge == 2: inertial coordinates
+  GaugeH* computed = nullptr;    // kGauge == 2: if set, receives H_a and d_a H_b
 };
 
 // Computes the context and Q[10], the part of the bracket of the dt Pi
@@ -333,6 +334,7 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
     damped_harmonic_gauge(gin.dh, gin.x, lapse, q.shift, sqrt(q.det), q.ig, dag,
                           ctx.half_pi_nn, ctx.half_phi_nn, g, gauge_local);
     gauge = &gauge_local;
+    if (gin.computed) *gin.computed = gauge_local;
   }
   // gauge constraint C_a = Gamma_a + H_a, Gamma_a = G^{bc} Gamma_a,bc
   double Ca[4];

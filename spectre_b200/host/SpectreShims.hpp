@@ -199,6 +199,29 @@ inline std::vector<double> quadrature_weights(size_t n) {
   check(dgrhs_collocation_points_and_weights(static_cast<int>(n), x.data(), w.data()));
   return w;
 }
+// Spectral::ChildSize / MortarSize and the projection matrices of non-conforming
+// mortars (NumericalAlgorithms/Spectral/Projection.hpp:28-36, Projection.cpp:57-362),
+// equal extents on both meshes; row-major [target point][source point]
+enum class ChildSize : uint8_t { Uninitialized = 0, Full = 1, UpperHalf = 2, LowerHalf = 3 };
+using MortarSize = ChildSize;
+inline int abi_size_code(ChildSize s) {
+  switch (s) {
+    case ChildSize::Full: return 0;
+    case ChildSize::LowerHalf: return 1;
+    case ChildSize::UpperHalf: return 2;
+    default: throw std::runtime_error("Received uninitialized child_size.");
+  }
+}
+inline std::vector<double> projection_matrix_parent_to_child(size_t n, ChildSize size) {
+  std::vector<double> M(n * n);
+  check(dgrhs_projection_matrix(static_cast<int>(n), 0, abi_size_code(size), M.data()));
+  return M;
+}
+inline std::vector<double> projection_matrix_child_to_parent(size_t n, ChildSize size) {
+  std::vector<double> M(n * n);
+  check(dgrhs_projection_matrix(static_cast<int>(n), 1, abi_size_code(size), M.data()));
+  return M;
+}
 }  // namespace Spectral
 
 template <size_t Dim>

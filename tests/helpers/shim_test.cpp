@@ -62,6 +62,18 @@ int main() {
     for (size_t j = 0; j < 5; ++j) s += D[i * 5 + j] * x[j] * x[j] * x[j];
     if (std::fabs(s - 3 * x[i] * x[i]) > 1e-13) { std::printf("D matrix wrong\n"); return 1; }
   }
+  {  // restriction of the prolongation of both halves is the identity
+    const auto Pl = Spectral::projection_matrix_parent_to_child(5, Spectral::ChildSize::LowerHalf);
+    const auto Pu = Spectral::projection_matrix_parent_to_child(5, Spectral::ChildSize::UpperHalf);
+    const auto Rl = Spectral::projection_matrix_child_to_parent(5, Spectral::ChildSize::LowerHalf);
+    const auto Ru = Spectral::projection_matrix_child_to_parent(5, Spectral::ChildSize::UpperHalf);
+    for (size_t i = 0; i < 5; ++i)
+      for (size_t j = 0; j < 5; ++j) {
+        double s = 0.0;
+        for (size_t k = 0; k < 5; ++k) s += Rl[i * 5 + k] * Pl[k * 5 + j] + Ru[i * 5 + k] * Pu[k * 5 + j];
+        if (std::fabs(s - (i == j ? 1.0 : 0.0)) > 1e-12) { std::printf("projection matrices wrong\n"); return 1; }
+      }
+  }
   const auto c = TimeSteppers::adams_coefficients::coefficients({0.0, 1.0, 2.0}, 2.0, 3.0);
   if (std::fabs(c[2] - 23.0 / 12.0) > 1e-15) { std::printf("AB3 coefficients wrong\n"); return 1; }
   // ---- error behaviour: bad arguments throw with the library's message ----

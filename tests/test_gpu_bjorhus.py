@@ -99,6 +99,35 @@ def test_bjorhus_on_kerr_schild_shell(kind):
     ctx.close()
 
 
+def test_bjorhus_with_damped_harmonic_gauge():
+    """The boundary conditions of the binary-black-hole input files:
+    ConstraintPreservingPhysical with the DampedHarmonic gauge (H_a and d_a H_b are
+    evaluated at the face points by the same code as in the volume kernel)."""
+    N = 5
+    rng = np.random.default_rng(77)
+    brick = domain.Brick([3.0, -0.5, -0.5], [4.0, 0.5, 0.5], [1, 1, 1], N,
+                         periodic=(False, True, True))
+    x, nbr = brick.coords(), brick.neighbors().copy()
+    nbr[nbr == -1] = lib.BJORHUS_PHYSICAL
+    J = brick.inverse_jacobian() + 0.05 * rng.uniform(-1, 1, (brick.n_elements, 9, N ** 3))
+    u = analytic.gauge_wave(x, 0.1) + 1e-2 * rng.uniform(-1, 1, (brick.n_elements, 50, N ** 3))
+    stat = rng.uniform(-1, 1, (brick.n_elements, 3, N ** 3))
+    params = [3.0, 1.2, 1.5, 1.7, 2, 4, 6]
+    ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+    ctx.set_geometry(J, x, nbr)
+    ctx.set_static_fields(stat)
+    ctx.set_gauge(lib.GAUGE_DAMPED_HARMONIC, params)
+    ctx.set_state(u)
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    gp = np.array([2.0] + params)
+    ref = orc.dg_rhs(1, N, u, J, stat, nbr, gauge_params=gp, coords=x)
+    assert _relerr(got, ref, GH_BLOCKS) < TOL
+    harmonic = orc.dg_rhs(1, N, u, J, stat, nbr, coords=x)
+    assert _relerr(harmonic, ref, GH_BLOCKS) > 1e-9   # the gauge source does enter
+    ctx.close()
+
+
 def test_bjorhus_misuse():
     N = 3
     brick = domain.Brick([3.0, 0, 0], [4.0, 1, 1], [0, 0, 0], N, periodic=(False,) * 3)

@@ -189,13 +189,15 @@ def test_demand_outgoing_char_speeds_on_excision_boundary():
     ev.ctx.close()
 
 
-def test_partitioned_shell_matches_single_context():
+@pytest.mark.parametrize("outer", ["DirichletAnalytic", "ConstraintPreservingPhysical"])
+def test_partitioned_shell_matches_single_context(outer):
     """The multi-GPU path on the multi-block shell (ghost faces with non-aligned
-    orientation + DirichletAnalytic slots), run as 3 contexts on one GPU with the
-    halo moved by device copies: bit-identical to the single-context evolution."""
+    orientation + DirichletAnalytic slots or Bjorhus faces, which also sit on
+    "interior" elements of a rank), run as 3 contexts on one GPU with the halo
+    moved by device copies: bit-identical to the single-context evolution."""
     import torch
     N, dt, world = 4, 1e-4, 3
-    problem = evolution.gh_kerr_schild_shell_problem((1, 0), N)
+    problem = evolution.gh_kerr_schild_shell_problem((1, 0), N, outer_boundary=outer)
     single = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, dt)
     single.take_steps(2)
     ref = single.gather_state(problem.brick.n_elements)
