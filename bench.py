@@ -205,8 +205,11 @@ def workload_config(args, world, cpu=False):
         ref = [args.refine, args.refine, lr]
     else:
         n_el = (2 ** args.refine) ** 3
+    extra = {}
+    if workload == "kerr-schild-shell":
+        extra = {"inner_boundary": args.inner_boundary, "outer_boundary": args.outer_boundary}
     return {
-        "workload": names[workload],
+        "workload": names[workload], **extra,
         "elements_per_gpu": n_el, "refinement": ref,
         "points_per_dim": args.points, "gauge": args.gauge, "stepper": "AdamsBashforth(3)",
         "parallelism": f"elements partitioned along the block Z-curve over {world} GPU(s), "
@@ -218,7 +221,10 @@ def workload_config(args, world, cpu=False):
 
 def shell_radial_level(args, world):
     """Radial refinement level of the shell workload: 2^(refine+1) radial elements
-    on one GPU, doubled with the GPU count (weak scaling)."""
+    on one GPU, doubled with the GPU count (weak scaling); strong scaling: fixed
+    2^(refine+1) * strong_factor radial elements."""
+    if getattr(args, "scaling", "weak") == "strong":
+        return args.refine + 1 + int(np.log2(args.strong_factor))
     lr, w = args.refine + 1, world
     while w > 1:
         lr += 1
@@ -243,6 +249,17 @@ def main():
     ap.add_argument("--cpu-sample-refine", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--outer-boundary", default="DirichletAnalytic",
+                    choices=["DirichletAnalytic", "ConstraintPreserving",
+                             "ConstraintPreservingPhysical"],
+                    help="kerr-schild-shell: boundary condition on the outer sphere")
+    ap.add_argument("--inner-boundary", default="DirichletAnalytic",
+                    choices=["DirichletAnalytic", "DemandOutgoingCharSpeeds"],
+                    help="kerr-schild-shell: boundary condition on the excision sphere")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="kerr-schild-shell: weak = 2^(refine+1) radial elements per GPU; "
+                         "strong = 2^(refine+1) * strong-factor radial elements in total")
+    ap.add_argument("--strong-factor", type=int, default=4)
     ap.add_argument("--volume-variant", type=int, default=0,
                     help="dgrhs_set_split_volume: 0 default, 1 split kernels, 2 pair-staged "
                          "kernel for N >= 10 (A/B comparisons)")
@@ -282,7 +299,8 @@ def main():
         q = 1.0 + 0.125 * np.pi / 2 ** args.refine
         problem = evolution.gh_kerr_schild_shell_problem(
             (args.refine, lr), N, inner_radius=1.9, outer_radius=1.9 * q ** (2 ** lr),
-            order="radial")
+            order="radial", inner_boundary=args.inner_boundary,
+            outer_boundary=args.outer_boundary)
     elif args.workload == "kerr-schild":
         # element size fixed (1/8 M per element edge), lattice grows with the GPU count
         ne = [2 ** r for r in refinement]
@@ -433,7 +451,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling if args.workload == "kerr-schild-shell" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "max_abs_error_vs_exact": err,

@@ -143,6 +143,19 @@ DG_HD_NOINLINE void bjorhus_constraint_preserving(const BjorhusInput& in, Bjorhu
     }
   }
 
+  // gg_phi[k][n][a] = g^{jk} g^{mn} Phi_jma
+  double gg_phi[3][3][4];
+  for (int k = 0; k < 3; ++k)
+    for (int n = 0; n < 3; ++n)
+      for (int a = 0; a < 4; ++a) {
+        double v = 0.0;
+        for (int j = 0; j < 3; ++j) {
+          double w = 0.0;
+          for (int m = 0; m < 3; ++m) w += ig[m][n] * in.phi[j][m + 1][a];
+          v += ig[j][k] * w;
+        }
+        gg_phi[k][n][a] = v;
+      }
   double c2[3][4];
   for (int i = 0; i < 3; ++i)
     for (int a = 0; a < 4; ++a) {
@@ -166,14 +179,9 @@ DG_HD_NOINLINE void bjorhus_constraint_preserving(const BjorhusInput& in, Bjorhu
       // 1/2 g^{jk} (psi^{cd} Phi_jcd) Phi_ike t^e t_a
       for (int j = 0; j < 3; ++j)
         for (int k = 0; k < 3; ++k) v += 0.5 * ig[j][k] * tr_phi[j] * phi_t[i][k + 1] * t_lo[a];
-      // - g^{jk} g^{mn} Phi_jma Phi_ikn
-      for (int j = 0; j < 3; ++j)
-        for (int k = 0; k < 3; ++k) {
-          double w = 0.0;
-          for (int m = 0; m < 3; ++m)
-            for (int n = 0; n < 3; ++n) w += ig[m][n] * in.phi[j][m + 1][a] * in.phi[i][k + 1][n + 1];
-          v -= ig[j][k] * w;
-        }
+      // - g^{jk} g^{mn} Phi_jma Phi_ikn = - X[k][n][a] Y[i][k][n]
+      for (int k = 0; k < 3; ++k)
+        for (int n = 0; n < 3; ++n) v -= gg_phi[k][n][a] * in.phi[i][k + 1][n + 1];
       // 1/2 Phi_icd Pi_be t_a (psi^{cb} psi^{de} + 1/2 psi^{be} t^c t^d)
       {
         double w = 0.0;
@@ -206,17 +214,32 @@ DG_HD_NOINLINE void bjorhus_constraint_preserving(const BjorhusInput& in, Bjorhu
         div_H += ig[i][j] * in.dH[i + 1][j + 1];         // g^{ij} d_i H_j
       }
     s_ta += 0.5 * tr_dphi_sp + div_H;
-    // -1/2 g^{ij} g^{mn} Phi_imc Phi_njd psi^{cd}
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j)
-        for (int m = 0; m < 3; ++m)
-          for (int n = 0; n < 3; ++n) {
-            double w = 0.0;
-            for (int c = 0; c < 4; ++c)
-              for (int d = 0; d < 4; ++d)
-                w += in.phi[i][m + 1][c] * in.phi[n][j + 1][d] * in.ipsi[c][d];
-            s_ta -= 0.5 * ig[i][j] * ig[m][n] * w;
+    // -1/2 g^{ij} g^{mn} Phi_imc Phi_njd psi^{cd}, with U[i][n][c] = g^{mn} Phi_imc and
+    // W[n][i][c] = psi^{cd} g^{ij} Phi_njd
+    {
+      double U[3][3][4], W[3][3][4];
+      for (int i = 0; i < 3; ++i)
+        for (int n = 0; n < 3; ++n)
+          for (int c = 0; c < 4; ++c) {
+            double u = 0.0, r = 0.0;
+            for (int m = 0; m < 3; ++m) {
+              u += ig[m][n] * in.phi[i][m + 1][c];
+              r += ig[n][m] * in.phi[i][m + 1][c];   // g^{nj} Phi_{i j c} (row n of g^{..})
+            }
+            U[i][n][c] = u;
+            W[i][n][c] = r;                          // raised with psi below
           }
+      double w = 0.0;
+      for (int i = 0; i < 3; ++i)
+        for (int n = 0; n < 3; ++n)
+          for (int c = 0; c < 4; ++c) {
+            // psi^{cd} g^{ij} Phi_{n j d}: W[n][i][d] contracted with psi
+            double r = 0.0;
+            for (int d = 0; d < 4; ++d) r += in.ipsi[c][d] * W[n][i][d];
+            w += U[i][n][c] * r;
+          }
+      s_ta -= 0.5 * w;
+    }
     // -1/4 g^{ij} Phi_icd Phi_j^{cd}
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) {
@@ -345,22 +368,22 @@ DG_HD_NOINLINE void bjorhus_constraint_preserving(const BjorhusInput& in, Bjorhu
       bc_psi[a][b] = speed[0] * v;                     // BjorhusImpl.cpp:26-47
       bc_plus[a][b] = -rhs_plus[a][b];                 // Bjorhus.cpp:317-325
     }
-  for (int i = 0; i < 3; ++i)                          // BjorhusImpl.cpp:49-103
-    for (int a = 0; a < 4; ++a)
-      for (int b = 0; b < 4; ++b) {
-        double v = 0.0;
-        for (int j = 0; j < 3; ++j)
-          for (int k = 0; k < 3; ++k) {
-            const double e = levi_civita(i, j, k);
-            if (e == 0.0) continue;
-            // four-index constraint C_jab = eps_{j l m} d_l Phi_mab
-            double c4 = 0.0;
-            for (int l = 0; l < 3; ++l)
-              for (int m = 0; m < 3; ++m) c4 += levi_civita(j, l, m) * in.d_phi[l][m][a][b];
-            v += e * n_up[k] * c4;
-          }
-        bc_zero[i][a][b] = speed[1] * v;
-      }
+  {
+    // four-index constraint C_jab = eps_{j l m} d_l Phi_mab (Constraints.cpp:1070-1100)
+    double c4[3][4][4];
+    for (int j = 0; j < 3; ++j) {
+      const int l = (j + 1) % 3, m = (j + 2) % 3;
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) c4[j][a][b] = in.d_phi[l][m][a][b] - in.d_phi[m][l][a][b];
+    }
+    // dt v_zero_iab = lambda_0 eps_{i j k} n^k C_jab (BjorhusImpl.cpp:49-103)
+    for (int i = 0; i < 3; ++i) {
+      const int j = (i + 1) % 3, k = (i + 2) % 3;
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b)
+          bc_zero[i][a][b] = speed[1] * (n_up[k] * c4[j][a][b] - n_up[j] * c4[k][a][b]);
+    }
+  }
   {
     // constraint-dependent terms (BjorhusImpl.cpp:153-221, mu = 0) and gauge
     // Sommerfeld terms (:105-151)

@@ -1,0 +1,312 @@
+"""Front end for the reference's YAML input files (the subset of options the
+accelerated path understands): tests/InputFiles/ScalarWave/PlaneWave3D.yaml,
+GeneralizedHarmonic/GaugeWave3D.yaml and GeneralizedHarmonic/KerrSchild.yaml of
+the reference run unchanged.
+
+    python -m spectre_b200.input_file --input-file KerrSchild.yaml [--steps N]
+
+The reference parses these with its Options system (src/Options/) into the
+GlobalCache / DataBox of the executable named in the metadata block
+(EvolveScalarWave3D, EvolveGhNoBlackHole3D, EvolveGhSingleBlackHole:
+src/Evolution/Executables/); here the same option names build a
+spectre_b200.evolution.Problem and drive the C-ABI.  Options outside the path
+(observers' file names, AMR, phase changes, resource info) are accepted and
+ignored; options that would change the numerics and are not implemented raise
+InputFileError, like the reference's PARSE_ERROR.
+"""
+from __future__ import annotations
+
+import argparse
+
+import numpy as np
+import yaml
+
+from . import analytic, domain, evolution, lib
+
+
+class InputFileError(ValueError):
+    pass
+
+
+def _one(options, what):
+    """A YAML map with exactly one key (the reference's factory-creatable idiom)."""
+    if isinstance(options, str):
+        return options, {}
+    if not isinstance(options, dict) or len(options) != 1:
+        raise InputFileError(f"{what}: expected exactly one option group, got {options!r}")
+    (name, body), = options.items()
+    return name, (body or {})
+
+
+def _gaussian_plus_constant(opts, what):
+    name, o = _one(opts, what)
+    if name == "Constant":
+        value = float(o["Value"])
+        return value
+    if name != "GaussianPlusConstant":
+        raise InputFileError(f"{what}: damping function {name} is not implemented")
+    c, a, w = float(o["Constant"]), float(o["Amplitude"]), float(o["Width"])
+    center = tuple(float(v) for v in o["Center"])
+    if a == 0.0:
+        return c
+    return lambda x: analytic.gaussian_plus_constant(x, c, a, w, center)
+
+
+STEPPERS = {
+    "AdamsBashforth": lib.STEPPER_ADAMS_BASHFORTH, "Rk3HesthavenSsp": lib.STEPPER_RK3_HESTHAVEN,
+    "Rk3Owren": lib.STEPPER_RK3_OWREN, "Rk3Kennedy": lib.STEPPER_RK3_KENNEDY,
+    "ClassicalRungeKutta4": lib.STEPPER_RK4, "DormandPrince5": lib.STEPPER_DORMAND_PRINCE5,
+}
+
+
+class Run:
+    """Everything an input file determines for the path."""
+
+    def __init__(self, metadata, options):
+        self.metadata, self.options = metadata or {}, options
+        exe = str(self.metadata.get("Executable", ""))
+        self.system = lib.SYSTEM_SCALAR_WAVE if "ScalarWave" in exe else lib.SYSTEM_GH
+        ev = options["Evolution"]
+        self.t0, self.dt = float(ev["InitialTime"]), float(ev["InitialTimeStep"])
+        # a slab is InitialSlabSize long (default: one step); triggers count slabs
+        self.steps_per_slab = int(round(float(ev.get("InitialSlabSize", self.dt)) / self.dt))
+        name, o = _one(ev["TimeStepper"], "TimeStepper")
+        if name not in STEPPERS:
+            raise InputFileError(f"TimeStepper {name} is not implemented")
+        self.stepper, self.order = STEPPERS[name], int(o.get("Order", 0))
+        self.step_choosers_ignored = []
+        if "StepChoosers" in ev and ev["StepChoosers"]:
+            # global time stepping with a fixed step is what the path implements; the
+            # choosers of KerrSchild.yaml only act at slab boundaries
+            self.step_choosers_ignored = [list(c)[0] for c in ev["StepChoosers"]]
+        sd = options["SpatialDiscretization"]
+        bc_name, _ = _one(sd["BoundaryCorrection"], "BoundaryCorrection")
+        if bc_name != "UpwindPenalty":
+            raise InputFileError(f"BoundaryCorrection {bc_name} is not implemented")
+        dgo = sd["DiscontinuousGalerkin"]
+        if dgo.get("Formulation", "StrongInertial") != "StrongInertial" or \
+                dgo.get("Quadrature", "GaussLobatto") != "GaussLobatto":
+            raise InputFileError("only StrongInertial on GaussLobatto points is implemented")
+        self.filter = None
+        flt = (options.get("Filtering") or {}).get("ExpFilter0")
+        if flt and flt.get("Enable", True):
+            self.filter = (float(flt["Alpha"]), int(flt["HalfPower"]))
+        self._initial_data()
+        self._domain()
+        self._system()
+        self._events()
+
+    # -- InitialData ---------------------------------------------------------
+    def _initial_data(self):
+        name, o = _one(self.options["InitialData"], "InitialData")
+        self.initial_data_name = name
+        if name == "PlaneWave":
+            pname, prof = _one(o["Profile"], "PlaneWave.Profile")
+            if pname != "Sinusoid":
+                raise InputFileError(f"PlaneWave profile {pname} is not implemented")
+            k, c = tuple(map(float, o["WaveVector"])), tuple(map(float, o["Center"]))
+            A, wn, ph = float(prof["Amplitude"]), float(prof["Wavenumber"]), float(prof["Phase"])
+            self.u0 = lambda x, t: analytic.plane_wave(x, t, k, c, A, wn, ph)
+            self.time_dependent = True
+        elif name == "GeneralizedHarmonic(GaugeWave)":
+            A, wl = float(o["Amplitude"]), float(o["Wavelength"])
+            self.gauge_wave = (A, wl)
+            self.u0 = lambda x, t: analytic.gauge_wave(x, t, A, wl)
+            self.time_dependent = True
+        elif name == "GeneralizedHarmonic(KerrSchild)":
+            if any(float(v) != 0.0 for v in list(o["Spin"]) + list(o["Velocity"])):
+                raise InputFileError("KerrSchild with spin or boost is not implemented")
+            M, c = float(o["Mass"]), tuple(map(float, o["Center"]))
+            self.u0 = lambda x, t: analytic.kerr_schild(x, M, c)
+            self.time_dependent = False
+        else:
+            raise InputFileError(f"InitialData {name} is not implemented")
+
+    # -- DomainCreator -------------------------------------------------------
+    def _boundary_condition(self, opts, what):
+        name, o = _one(opts, what)
+        if name == "DirichletAnalytic":
+            return "DirichletAnalytic"
+        if name == "DemandOutgoingCharSpeeds":
+            return "DemandOutgoingCharSpeeds"
+        if name == "ConstraintPreservingBjorhus":
+            return str(o["Type"])
+        if name == "Periodic":
+            return "Periodic"
+        raise InputFileError(f"{what}: boundary condition {name} is not implemented")
+
+    def _domain(self):
+        name, o = _one(self.options["DomainCreator"], "DomainCreator")
+        if o.get("TimeDependence", None) not in (None, "None") or \
+                o.get("TimeDependentMaps", None) not in (None, "None"):
+            raise InputFileError("time-dependent maps are not implemented")
+        self.ghost, self.outgoing, self.bjorhus = False, False, None
+        if name == "Brick":
+            pts = o["InitialGridPoints"]
+            if len(set(pts)) != 1:
+                raise InputFileError("anisotropic InitialGridPoints are not implemented")
+            bcs = o["BoundaryConditions"]
+            kinds = []
+            for b in bcs:
+                if isinstance(b, dict) and set(b) == {"Lower", "Upper"}:
+                    kinds.append((self._boundary_condition(b["Lower"], "Brick.Lower"),
+                                  self._boundary_condition(b["Upper"], "Brick.Upper")))
+                else:
+                    k = self._boundary_condition(b, "Brick.BoundaryConditions")
+                    kinds.append((k, k))
+            periodic = tuple(k == ("Periodic", "Periodic") for k in kinds)
+            self.domain = domain.Brick(o["LowerBound"], o["UpperBound"], o["InitialRefinement"],
+                                       int(pts[0]), periodic=periodic)
+            face_bc = {2 * dim + side: kinds[dim][side] for dim in range(3) for side in range(2)
+                       if not periodic[dim]}
+        elif name == "Sphere":
+            iname, io = _one(o["Interior"], "Sphere.Interior")
+            if iname != "ExciseWithBoundaryCondition":
+                raise InputFileError("Sphere with a filled interior is not implemented")
+            if o.get("WhichWedges", "All") != "All" or \
+                    o.get("EquatorialCompression", None) not in (None, "None"):
+                raise InputFileError("Sphere: WhichWedges / EquatorialCompression not implemented")
+            ref, pts = o["InitialRefinement"], o["InitialGridPoints"]
+            if isinstance(pts, (list, tuple)):
+                if len(set(pts)) != 1:
+                    raise InputFileError("anisotropic InitialGridPoints are not implemented")
+                pts = pts[0]
+            if isinstance(ref, (list, tuple)):
+                if ref[0] != ref[1]:
+                    raise InputFileError("different angular refinement levels not implemented")
+                ref = (int(ref[0]), int(ref[2]))
+            self.domain = domain.SphericalShell(
+                float(o["InnerRadius"]), float(o["OuterRadius"]), ref, int(pts),
+                tuple(map(float, o.get("RadialPartitioning", []))),
+                list(o.get("RadialDistribution", ["Linear"])),
+                bool(o.get("UseEquiangularMap", True)))
+            face_bc = {4: self._boundary_condition(io, "Sphere.Interior"),
+                       5: self._boundary_condition(o["OuterBoundaryCondition"],
+                                                   "Sphere.OuterBoundaryCondition")}
+        else:
+            raise InputFileError(f"DomainCreator {name} is not implemented")
+        self.face_bc = face_bc
+        ghost_dirs = {d for d, k in face_bc.items() if k == "DirichletAnalytic"}
+        if ghost_dirs:
+            self.ghost = lambda g, d: d in ghost_dirs
+        self.outgoing = any(k == "DemandOutgoingCharSpeeds" for k in face_bc.values())
+        bj = {d: k for d, k in face_bc.items() if k.startswith("ConstraintPreserving")}
+        if bj:
+            self.bjorhus = lambda g, d: bj.get(d)
+
+    # -- EvolutionSystem -----------------------------------------------------
+    def _system(self):
+        self.gauge, self.gauge_params, self.analytic_christoffel = lib.GAUGE_HARMONIC, (), False
+        if self.system == lib.SYSTEM_SCALAR_WAVE:
+            self.static = (0.0,)     # gamma2 = 0 in the executable (ScalarWave/Initialize.hpp:48-49)
+            return
+        gh = self.options["EvolutionSystem"]["GeneralizedHarmonic"]
+        gname, go = _one(gh["GaugeCondition"], "GaugeCondition")
+        if gname == "Harmonic":
+            pass
+        elif gname == "AnalyticChristoffel":
+            if self.initial_data_name == "GeneralizedHarmonic(GaugeWave)":
+                self.gauge = lib.GAUGE_ANALYTIC_GAUGE_WAVE
+                self.gauge_params = self.gauge_wave
+            else:
+                self.analytic_christoffel = True
+        elif gname == "DampedHarmonic":
+            self.gauge = lib.GAUGE_DAMPED_HARMONIC
+            self.gauge_params = (float(go["SpatialDecayWidth"]), *map(float, go["Amplitudes"]),
+                                 *map(int, go["Exponents"]))
+        else:
+            raise InputFileError(f"GaugeCondition {gname} is not implemented")
+        self.static = tuple(_gaussian_plus_constant(gh[f"DampingFunctionGamma{i}"],
+                                                    f"DampingFunctionGamma{i}") for i in range(3))
+
+    # -- EventsAndTriggers ---------------------------------------------------
+    def _events(self):
+        self.n_steps, self.observe_interval = None, None
+        for et in self.options.get("EventsAndTriggers") or []:
+            trig = et.get("Trigger")
+            events = [list(e)[0] if isinstance(e, dict) else e for e in et.get("Events", [])]
+            if "Completion" in events and isinstance(trig, dict):
+                tname, to = _one(trig, "Trigger")
+                spec = (to or {}).get("Specified", {}).get("Values")
+                if tname == "Slabs" and spec:
+                    self.n_steps = int(spec[0]) * self.steps_per_slab
+                elif tname == "Times" and spec:
+                    self.n_steps = int(round((float(spec[0]) - self.t0) / self.dt))
+            if "ObserveNorms" in events and isinstance(trig, dict):
+                tname, to = _one(trig, "Trigger")
+                if tname == "Slabs" and "EvenlySpaced" in (to or {}):
+                    self.observe_interval = int(to["EvenlySpaced"]["Interval"]) * \
+                        self.steps_per_slab
+
+    # -- build + run ---------------------------------------------------------
+    def problem(self):
+        p = evolution.Problem(self.system, self.domain, self.u0, self.static,
+                              dirichlet_analytic=self.ghost,
+                              analytic_christoffel_gauge=self.analytic_christoffel,
+                              demand_outgoing=self.outgoing, bjorhus=self.bjorhus)
+        p.boundary_time_dependent = bool(self.ghost) and self.time_dependent
+        return p
+
+    def evolution(self, device=0, world=1, rank=0, process_group=None):
+        ev = evolution.Evolution(self.problem(), self.stepper, self.order, self.dt, self.t0,
+                                 self.gauge, self.gauge_params, device, world, rank,
+                                 process_group)
+        if self.filter:
+            ev.ctx.set_exponential_filter(True, *self.filter)
+        return ev
+
+    def run(self, n_steps=None, device=0, observe=None):
+        """Evolve and return [(step, time, {name: L2 error norm})] -- ObserveNorms of
+        Error(...) with NormType L2Norm, Components Sum
+        (ParallelAlgorithms/Events/ObserveNorms.hpp:60-80)."""
+        n_steps = self.n_steps if n_steps is None else n_steps
+        if n_steps is None:
+            raise InputFileError("no Completion trigger with a specified slab or time")
+        observe = observe or self.observe_interval or n_steps
+        ev = self.evolution(device)
+        names = ("Psi", "Pi", "Phi") if self.system == lib.SYSTEM_SCALAR_WAVE else \
+            ("SpacetimeMetric", "Pi", "Phi")
+        blocks = ((0, 1), (1, 2), (2, 5)) if self.system == lib.SYSTEM_SCALAR_WAVE else \
+            ((0, 10), (10, 20), (20, 50))
+        out, done = [], 0
+        ids = ev.part.global_ids
+
+        def observe_now():
+            state = ev.ctx.get_state()
+            exact = ev.problem.u0(ids, ev.ctx.time)
+            npts = state.shape[0] * state.shape[2]
+            norms = {f"Error({nm})": float(np.sqrt(np.sum((state[:, a:b] - exact[:, a:b]) ** 2)
+                                                   / npts)) for nm, (a, b) in zip(names, blocks)}
+            out.append((done, ev.ctx.time, norms))
+        observe_now()
+        while done < n_steps:
+            k = min(observe - done % observe, n_steps - done)
+            ev.take_steps(k)
+            done += k
+            observe_now()
+        if self.outgoing:
+            ev.ctx.check_outgoing_char_speeds()
+        ev.ctx.close()
+        return out
+
+
+def load(path):
+    with open(path) as f:
+        docs = list(yaml.safe_load_all(f))
+    if len(docs) == 1:
+        return Run({}, docs[0])
+    return Run(docs[0], docs[1])
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("--input-file", required=True)
+    ap.add_argument("--steps", type=int, default=None)
+    args = ap.parse_args()
+    run = load(args.input_file)
+    for step, t, norms in run.run(args.steps):
+        print(f"step {step:6d}  t = {t:.6f}  " + "  ".join(f"{k} = {v:.6e}" for k, v in norms.items()))
+
+
+if __name__ == "__main__":
+    main()
