@@ -125,16 +125,22 @@ MORTAR_FULL, MORTAR_LOWER_HALF, MORTAR_UPPER_HALF = 0, 1, 2
 
 class RefinedBrick:
     """A Brick whose coarse cells (2^L per dimension) are individually h-refined
-    once (split into 2 x 2 x 2 children), as AMR or per-block `InitialRefinement`
-    differences produce: element faces between a coarse element and a refined
-    cell are non-conforming 2:1 mortars (dg::mortar_size, NumericalAlgorithms/
-    DiscontinuousGalerkin/MortarHelpers.cpp:51-77; Element<3>::neighbors() then
-    holds four neighbour ids for that direction, Domain/Structure/Neighbors.hpp).
+    once, isotropically (2 x 2 x 2 children) or only in some dimensions (the
+    reference's AMR is anisotropic: `Amr: Policies: Isotropy: Anisotropic`), as AMR
+    or per-block `InitialRefinement` differences produce: element faces between a
+    coarser and a finer element are non-conforming 2:1 mortars (dg::mortar_size,
+    NumericalAlgorithms/DiscontinuousGalerkin/MortarHelpers.cpp:51-77;
+    Element<3>::neighbors() then holds several neighbour ids for that direction,
+    Domain/Structure/Neighbors.hpp).
 
+    refined_cells: cells split in all three dimensions, or a dict cell -> (bool,
+    bool, bool) saying which dimensions are split.
     neighbors(): [n_elements, 6] with HANGING on both sides of such faces;
     mortars(): rows (coarse element, its direction, fine element, its direction,
     size_a, size_b), the MortarSize of the fine face inside the coarse face per
-    face dimension (first remaining dimension first)."""
+    face dimension (first remaining dimension first; Full where both sides have
+    the same extent).  An interface where each side is the finer one in one face
+    dimension (the mortar would be smaller than both faces) is not supported."""
 
     def __init__(self, lower, upper, refinement, N, refined_cells, periodic=(True, True, True)):
         self.lower = np.asarray(lower, float)
@@ -144,31 +150,41 @@ class RefinedBrick:
         self.N = int(N)
         self.n = self.N ** 3
         self.periodic = tuple(periodic) if not isinstance(periodic, bool) else (periodic,) * 3
-        self.refined = {tuple(c) for c in refined_cells}
+        if isinstance(refined_cells, dict):
+            self.split = {tuple(c): tuple(bool(x) for x in m) for c, m in refined_cells.items()}
+        else:
+            self.split = {tuple(c): (True, True, True) for c in refined_cells}
+        self.refined = set(self.split)
         nx, ny, nz = self.ne
         cells = [(ix, iy, iz) for iz in range(nz) for iy in range(ny) for ix in range(nx)]
         cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], self.levels))
-        # element = (coarse cell, child or None); children in Z order
+        # element = (coarse cell, child or None); children in Z order, child
+        # coordinate 0 in a dimension that is not split
         self.elements = []
         for c in cells:
-            if c in self.refined:
-                for k in range(8):
-                    self.elements.append((c, (k & 1, (k >> 1) & 1, (k >> 2) & 1)))
-            else:
+            m = self.split.get(c)
+            if m is None:
                 self.elements.append((c, None))
+                continue
+            for k in range(8):
+                ch = (k & 1, (k >> 1) & 1, (k >> 2) & 1)
+                if all(ch[d] == 0 or m[d] for d in range(3)):
+                    self.elements.append((c, ch))
         self.index_of = {el: i for i, el in enumerate(self.elements)}
         self.n_elements = len(self.elements)
         self.xi, self.weights = lib.collocation_points_and_weights(self.N)
         self._tables = None
 
+    def _mask(self, c):
+        return self.split.get(c, (False, False, False))
+
     def element_ids(self):
         out = []
         for c, ch in self.elements:
-            if ch is None:
-                out.append(element_id(0, c, self.levels))
-            else:
-                out.append(element_id(0, [2 * c[d] + ch[d] for d in range(3)],
-                                      [l + 1 for l in self.levels]))
+            m = self._mask(c)
+            chh = ch or (0, 0, 0)
+            out.append(element_id(0, [2 * c[d] + chh[d] if m[d] else c[d] for d in range(3)],
+                                  [self.levels[d] + (1 if m[d] else 0) for d in range(3)]))
         return out
 
     def _bounds(self, el):
@@ -176,8 +192,9 @@ class RefinedBrick:
         h = (self.upper - self.lower) / np.asarray(self.ne)
         lo = self.lower + h * np.asarray(c)
         if ch is not None:
-            h = 0.5 * h
-            lo = lo + h * np.asarray(ch)
+            m = np.asarray(self._mask(c), float)
+            h = h * (1.0 - 0.5 * m)
+            lo = lo + h * np.asarray(ch) * m
         return lo, lo + h
 
     def coords(self, ids=None):
@@ -205,11 +222,12 @@ class RefinedBrick:
         nb = np.full((self.n_elements, 6), -1, dtype=np.int64)
         mortars = []
         for e, (c, ch) in enumerate(self.elements):
+            m = self._mask(c)
+            chh = ch or (0, 0, 0)
             for d in range(6):
                 dim, side = d // 2, d % 2
-                if ch is not None and ch[dim] != side:
-                    # sibling inside the same refined cell
-                    sib = list(ch)
+                if m[dim] and chh[dim] != side:
+                    sib = list(chh)          # sibling inside the same refined cell
                     sib[dim] = side
                     nb[e, d] = self.index_of[(c, tuple(sib))]
                     continue
@@ -220,25 +238,38 @@ class RefinedBrick:
                         continue
                     nc[dim] %= self.ne[dim]
                 nc = tuple(nc)
-                if ch is None and nc not in self.refined:
-                    nb[e, d] = self.index_of[(nc, None)]
-                elif ch is not None and nc in self.refined:
-                    other = list(ch)
-                    other[dim] = 1 - side
-                    nb[e, d] = self.index_of[(nc, tuple(other))]
-                elif ch is not None:
-                    nb[e, d] = HANGING          # the coarse side lists the mortar
-                else:
-                    nb[e, d] = HANGING
-                    fd = [x for x in range(3) if x != dim]
-                    for kb in range(2):
-                        for ka in range(2):
-                            child = [0, 0, 0]
-                            child[dim] = 1 - side
-                            child[fd[0]], child[fd[1]] = ka, kb
-                            mortars.append((e, d, self.index_of[(nc, tuple(child))], d ^ 1,
-                                            MORTAR_UPPER_HALF if ka else MORTAR_LOWER_HALF,
-                                            MORTAR_UPPER_HALF if kb else MORTAR_LOWER_HALF))
+                mn = self._mask(nc)
+                fd = [x for x in range(3) if x != dim]
+                # per face dimension: +1 the neighbour is finer, -1 we are finer, 0 equal
+                rel = [int(mn[x]) - int(m[x]) for x in fd]
+                if 1 in rel and -1 in rel:
+                    raise NotImplementedError("mortar smaller than both faces")
+                base = [0, 0, 0]
+                if mn[dim]:
+                    base[dim] = 1 - side
+                if all(r <= 0 for r in rel):
+                    # one neighbour: the same size or coarser
+                    for x in fd:
+                        base[x] = chh[x] if mn[x] else 0
+                    other = (nc, tuple(base)) if nc in self.split else (nc, None)
+                    if any(r < 0 for r in rel):
+                        nb[e, d] = HANGING   # the coarser side lists the mortar
+                    else:
+                        nb[e, d] = self.index_of[other]
+                    continue
+                # we are the coarse side: one mortar per finer neighbour
+                nb[e, d] = HANGING
+                ra = range(2) if rel[0] == 1 else [None]
+                rb = range(2) if rel[1] == 1 else [None]
+                for kb in rb:
+                    for ka in ra:
+                        child = list(base)
+                        child[fd[0]] = ka if ka is not None else (chh[fd[0]] if mn[fd[0]] else 0)
+                        child[fd[1]] = kb if kb is not None else (chh[fd[1]] if mn[fd[1]] else 0)
+                        size = lambda k: MORTAR_FULL if k is None else (
+                            MORTAR_UPPER_HALF if k else MORTAR_LOWER_HALF)
+                        mortars.append((e, d, self.index_of[(nc, tuple(child))], d ^ 1,
+                                        size(ka), size(kb)))
         self._tables = (nb.astype(np.int32), np.asarray(mortars, dtype=np.int32).reshape(-1, 6))
 
     def neighbors(self):

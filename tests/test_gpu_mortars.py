@@ -61,6 +61,21 @@ def test_rhs_with_mortars_matches_oracle(system, N):
     ctx.close()
 
 
+@pytest.mark.parametrize("system,N", [("sw", 5), ("gh", 4)])
+def test_anisotropic_refinement_matches_oracle(system, N):
+    """Cells split in one or two dimensions: mortars with MortarSize Full in one
+    face dimension (identity projection in that dimension)."""
+    split = {(0, 0, 0): (True, False, False), (1, 1, 1): (True, True, False),
+             (1, 0, 0): (False, False, True)}
+    rb, ctx, u, J, stat, nb, mt = _setup(system, N, split, seed=20 + N)
+    assert {(int(m[4]), int(m[5])) for m in mt} >= {(1, 0), (0, 1), (1, 1)}
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    ref = orc.dg_rhs(1 if system == "gh" else 0, N, u, J, stat, nb, mortars=mt)
+    assert _relerr(got, ref, GH_BLOCKS if system == "gh" else SW_BLOCKS) < TOL
+    ctx.close()
+
+
 @pytest.mark.parametrize("system", ["sw", "gh"])
 def test_evolution_with_mortars(system):
     N, dt = 4, 2e-4

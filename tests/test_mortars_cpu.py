@@ -134,3 +134,36 @@ def test_oracle_mortars_consistency(N):
             np.testing.assert_allclose(r_ref[e], r_base[eb], atol=1e-11)
             checked += 1
     assert checked == 3
+
+
+def test_anisotropic_refinement_mortars():
+    """Cells split in one or two dimensions only: mortars that are Full in one face
+    dimension and a half in the other; continuous polynomial data still give no
+    boundary correction, and the sizes describe the geometry."""
+    N = 4
+    split = {(0, 0, 0): (True, False, False), (1, 1, 1): (True, True, False),
+             (1, 0, 0): (False, False, True)}
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N, split, periodic=(False,) * 3)
+    nb, mt = rb.neighbors(), rb.mortars()
+    assert rb.n_elements == 5 + 2 + 4 + 2 and len(set(rb.element_ids())) == rb.n_elements
+    sizes = Counter((int(m[4]), int(m[5])) for m in mt)
+    assert sizes[(1, 0)] and sizes[(0, 1)] and sizes[(1, 1)] and (0, 0) not in sizes
+    x, J = rb.coords(), rb.inverse_jacobian()
+    for ec, dc, ef, df, sa, sb in mt:
+        fc = x[ec][:, domain._face_point_indices(N, dc)]
+        ff = x[ef][:, domain._face_point_indices(N, df)]
+        fd = [d for d in range(3) if d != dc // 2]
+        for dim, size in zip(fd, (sa, sb)):
+            lo, hi = fc[dim].min(), fc[dim].max()
+            mid = 0.5 * (lo + hi)
+            want = {0: (lo, hi), 1: (lo, mid), 2: (mid, hi)}[size]
+            assert ff[dim].min() == pytest.approx(want[0]) and ff[dim].max() == pytest.approx(want[1])
+    stat = np.full((rb.n_elements, 1, N ** 3), 0.3)
+    u = _poly(x)
+    full = orc.dg_rhs(0, N, u, J, stat, nb, mortars=mt)
+    vol = orc.dg_rhs(0, N, u, J, stat, nb, volume_only=True)
+    assert np.max(np.abs(full - vol)) < 1e-12
+    with pytest.raises(NotImplementedError, match="smaller than both faces"):
+        domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N,
+                            {(0, 0, 0): (False, True, False), (1, 0, 0): (False, False, True)},
+                            periodic=(False,) * 3).neighbors()
