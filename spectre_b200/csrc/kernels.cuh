@@ -1510,20 +1510,31 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32)
     }
   }
   // logical derivatives of all 50 components at the point (K1)
+  // (five components per trip: their 15 N loads are independent, so one trip costs
+  // about one L2 latency instead of five)
   double dlog[50][3];
 #pragma unroll 1
-  for (int c = 0; c < 50; ++c) {
-    const double* tc = ue + (size_t)c * npad;
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+  for (int c0 = 0; c0 < 50; c0 += 5) {
+    double acc[5][3];
+#pragma unroll
+    for (int cc = 0; cc < 5; ++cc) acc[cc][0] = acc[cc][1] = acc[cc][2] = 0.0;
 #pragma unroll
     for (int m = 0; m < N; ++m) {
-      d0 = fma(sD[i * N + m], __ldg(tc + m + N * (j + N * k)), d0);
-      d1 = fma(sD[j * N + m], __ldg(tc + i + N * (m + N * k)), d1);
-      d2 = fma(sD[k * N + m], __ldg(tc + i + N * (j + N * m)), d2);
+      const double di = sD[i * N + m], dj = sD[j * N + m], dk = sD[k * N + m];
+#pragma unroll
+      for (int cc = 0; cc < 5; ++cc) {
+        const double* tc = ue + (size_t)(c0 + cc) * npad;
+        acc[cc][0] = fma(di, __ldg(tc + m + N * (j + N * k)), acc[cc][0]);
+        acc[cc][1] = fma(dj, __ldg(tc + i + N * (m + N * k)), acc[cc][1]);
+        acc[cc][2] = fma(dk, __ldg(tc + i + N * (j + N * m)), acc[cc][2]);
+      }
     }
-    dlog[c][0] = d0;
-    dlog[c][1] = d1;
-    dlog[c][2] = d2;
+#pragma unroll
+    for (int cc = 0; cc < 5; ++cc) {
+      dlog[c0 + cc][0] = acc[cc][0];
+      dlog[c0 + cc][1] = acc[cc][1];
+      dlog[c0 + cc][2] = acc[cc][2];
+    }
   }
   double corr[50];
   gh_bjorhus_point(gauge, a.dh, physical, d, g, pi, phi, J, gamma0, gamma1, gamma2, gh, x, dlog,
