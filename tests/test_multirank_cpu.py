@@ -117,3 +117,61 @@ def test_z_curve_order_matches_reference_bit_interleave():
     # unequal refinement: dimensions with level 0 are skipped
     assert domain.z_curve_index(1, 0, 1, (1, 0, 1)) == 0b11
     assert domain.z_curve_index(2, 0, 1, (2, 0, 1)) == 0b101
+
+
+def _shell_worker(rank, world, port, order, results):
+    """The same exchange on the six-wedge shell: neighbours across wedge
+    boundaries are not aligned, so a ghost slot holds the SENDER's face in the
+    sender's ordering and the receiver's orientation table (neighbour direction
+    + face permutation) finds the matching point -- what the face kernel does."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = domain.SphericalShell(1.9, 4.0, (1, 1), N, order=order)
+    nb, (nd, perm) = sh.neighbors(), sh.neighbor_orientations()
+    x = sh.coords()
+    part = domain.Partition(nb, world, rank, boundary_slots=True, neighbor_direction=nd,
+                            face_permutation=perm)
+    assert part.oriented
+    ln = part.local_neighbors
+    # "pack_halo": the face coordinates of the sender's face, in its own ordering
+    send = torch.zeros(max(part.n_ghost, 1) * 3 * F, dtype=torch.float64)
+    sv = send.numpy().reshape(-1, 3, F)
+    for slot, (le, d) in enumerate(part.send_map):
+        sv[slot] = x[part.global_ids[le]][:, _face_points(d)]
+    recv = torch.full((max(part.n_ghost, 1) * 3 * F,), np.nan, dtype=torch.float64)
+    halo = HaloExchange(part, 3 * F, dist)
+    for w in halo.start(send, recv):
+        w.wait()
+    rv = recv.numpy().reshape(-1, 3, F)
+    q = np.arange(F)
+    qa, qb = q % N, q // N
+    checked = 0
+    for le in range(part.n_local):
+        for d in range(6):
+            v = ln[le, d]
+            if v > -2 or -(v + 2) >= part.n_recv:
+                continue  # local neighbour, or a boundary-condition slot
+            code = part.local_face_permutation[le, d]
+            na, nbb = np.where(code & 1, qb, qa), np.where(code & 1, qa, qb)
+            if code & 2:
+                na = N - 1 - na
+            if code & 4:
+                nbb = N - 1 - nbb
+            mine = x[part.global_ids[le]][:, _face_points(d)]
+            theirs = rv[-(v + 2)][:, na + N * nbb]
+            np.testing.assert_allclose(theirs, mine, atol=1e-13)   # the same physical points
+            checked += 1
+    assert checked == part.n_recv
+    counts = [None] * world
+    dist.all_gather_object(counts, (part.n_local, part.n_recv))
+    if rank == 0 and order == "radial":
+        # cutting at constant radius: at most two spheres of faces per rank
+        assert max(c[1] for c in counts) <= 2 * 6 * 4
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,order", [(2, "block"), (2, "radial"), (3, "block")])
+def test_shell_partition_and_oriented_halo_exchange_gloo(world, order):
+    mp.spawn(_shell_worker, args=(world, _free_port(), order, None), nprocs=world, join=True)
