@@ -200,7 +200,10 @@ int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
  * 797-1045 (dg_boundary_terms on the mortar, dg::project_from_mortar,
  * MortarHelpers.hpp:100-129, lift_flux with the face normal magnitude,
  * add_slice_to_data; the mortars of one coarse face are summed in table order).
- * A context with mortars must hold both sides of every mortar (single rank). */
+ * A side that lives on another rank is written element = -(slot + 2): its face
+ * (packed by the owner with dgrhs_pack_halo like every cut face) arrives in ghost
+ * slot `slot`; the rank of the coarse side projects and sums the coarse
+ * correction, the rank of the fine side lifts the fine one. */
 #define DGRHS_NEIGHBOR_HANGING (-2147483647 - 1)
 /* Neighbor-table entry of an EXTERNAL face with gh::BoundaryConditions::
  * ConstraintPreservingBjorhus, Type ConstraintPreserving (DGRHS_NEIGHBOR_BJORHUS)

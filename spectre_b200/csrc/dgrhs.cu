@@ -345,6 +345,7 @@ struct dgrhs_ctx {
   int32_t* bjorhus_faces = nullptr;  // [n][3] element, direction, physical
   // non-conforming mortars (dgrhs_set_mortars)
   int n_mortar_faces = 0;
+  int n_mortar_faces_local = 0;      // groups without a remote side come first
   int32_t* mortar_faces = nullptr;   // [n_mortar_faces][4]
   int32_t* mortar_table = nullptr;   // [n_mortars][4]
   double* mortar_P = nullptr;        // [3][N*N]
@@ -449,23 +450,31 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
     ++g_launches;
     CU(cudaGetLastError());
   }
-  if (c->n_mortar_faces > 0 && aux_now) {
+  // mortar groups whose sides are all local run with the first pass; groups with a
+  // remote side need the halo: with the boundary pass (or the single full pass)
+  auto launch_mortars = [&](int first, int count) -> int {
+    if (count <= 0) return 0;
     dg::MortarArgs m{c->u, c->invjac, c->stat, c->corr, c->mortar_faces, c->mortar_table,
-                     c->mortar_P, c->mortar_R};
+                     c->mortar_P, c->mortar_R, c->halo_recv, first};
     constexpr int msmem = dg::mortar_smem_bytes<N>();
     constexpr int mT = (N * N + 31) / 32 * 32;
     if (c->system == DGRHS_SYSTEM_GH) {
       auto k = dg::mortar_kernel<N, 1>;
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
-      k<<<c->n_mortar_faces, mT, msmem, c->stream>>>(m);
+      k<<<count, mT, msmem, c->stream>>>(m);
     } else {
       auto k = dg::mortar_kernel<N, 0>;
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
-      k<<<c->n_mortar_faces, mT, msmem, c->stream>>>(m);
+      k<<<count, mT, msmem, c->stream>>>(m);
     }
     ++g_launches;
     CU(cudaGetLastError());
-  }
+    return 0;
+  };
+  if (aux_now && launch_mortars(0, c->n_mortar_faces_local)) return 1;
+  if (pass != 1 &&
+      launch_mortars(c->n_mortar_faces_local, c->n_mortar_faces - c->n_mortar_faces_local))
+    return 1;
   return 0;
 }
 
@@ -1018,35 +1027,83 @@ int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
   CU(cudaSetDevice(c->device));
   if (c->nbr_host.empty()) return fail("call dgrhs_set_geometry first");
   if (n_mortars < 0 || (n_mortars > 0 && !mortars)) return fail("bad mortar table");
-  // group the mortars by coarse face, keeping the caller's order inside a face
+  // a side may live on another rank: element = -(slot + 2) names the ghost slot
+  // that receives its face.  Groups (the mortars of one coarse face) keep the
+  // caller's order inside; groups without any remote side come first (they run
+  // before the halo arrives), the others after them.
+  auto is_ghost = [](int e) { return e <= -2; };
   std::vector<int> order(n_mortars);
   for (int m = 0; m < n_mortars; ++m) order[m] = m;
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-    const int32_t* a = mortars + 6 * (size_t)x;
-    const int32_t* b = mortars + 6 * (size_t)y;
-    return a[0] != b[0] ? a[0] < b[0] : a[1] < b[1];
-  });
+  // group key: a local coarse face (element, direction); a remote coarse side is
+  // its own group (one ghost slot per mortar)
+  auto key = [&](int m) {
+    const int32_t* r = mortars + 6 * (size_t)m;
+    return is_ghost(r[0]) ? std::pair<long long, int>((long long)c->nelem + (-(r[0] + 2)), r[1])
+                          : std::pair<long long, int>(r[0], r[1]);
+  };
+  std::vector<char> coarse_remote(n_mortars, 0);
+  {
+    std::vector<std::pair<std::pair<long long, int>, int>> keyed;
+    for (int m = 0; m < n_mortars; ++m) keyed.push_back({key(m), m});
+    std::stable_sort(keyed.begin(), keyed.end(),
+                     [](const auto& x, const auto& y) { return x.first < y.first; });
+    // a group is "remote" if any of its sides is a ghost
+    size_t i = 0;
+    std::vector<std::pair<int, std::vector<int>>> groups;  // (remote flag, members)
+    while (i < keyed.size()) {
+      size_t j = i;
+      int remote = 0;
+      std::vector<int> members;
+      while (j < keyed.size() && keyed[j].first == keyed[i].first) {
+        const int32_t* r = mortars + 6 * (size_t)keyed[j].second;
+        remote |= is_ghost(r[0]) || is_ghost(r[2]);
+        members.push_back(keyed[j].second);
+        ++j;
+      }
+      groups.push_back({remote, members});
+      i = j;
+    }
+    std::stable_sort(groups.begin(), groups.end(),
+                     [](const auto& x, const auto& y) { return x.first < y.first; });
+    order.clear();
+    c->n_mortar_faces_local = 0;
+    for (const auto& g : groups) {
+      if (!g.first) ++c->n_mortar_faces_local;
+      for (int m : g.second) order.push_back(m);
+    }
+  }
   std::vector<int32_t> faces, table;
   std::vector<char> fine_seen((size_t)c->nelem * 6, 0);
+  size_t local_coarse = 0, local_fine = 0;
+  std::pair<long long, int> last_key{-1, -1};
   for (int k = 0; k < n_mortars; ++k) {
     const int32_t* m = mortars + 6 * (size_t)order[k];
     const int ec = m[0], dc = m[1], ef = m[2], df = m[3], sa = m[4], sb = m[5];
-    if (ec < 0 || ec >= c->nelem || ef < 0 || ef >= c->nelem || dc < 0 || dc > 5 || df < 0 ||
+    if (ec >= c->nelem || ef >= c->nelem || ec == -1 || ef == -1 || dc < 0 || dc > 5 || df < 0 ||
         df > 5)
       return fail("mortar %d: element or direction out of range", order[k]);
+    if ((is_ghost(ec) && -(ec + 2) >= c->nghost) || (is_ghost(ef) && -(ef + 2) >= c->nghost))
+      return fail("mortar %d: ghost face index out of range", order[k]);
+    if (is_ghost(ec) && is_ghost(ef)) return fail("mortar %d: both sides are remote", order[k]);
     if (df != (dc ^ 1))
       return fail("mortar %d: only aligned blocks are supported (fine direction must be the "
                   "opposite of the coarse direction)", order[k]);
     if (sa < 0 || sa > 2 || sb < 0 || sb > 2 || (sa == 0 && sb == 0))
       return fail("mortar %d: bad mortar size (%d, %d)", order[k], sa, sb);
-    if (c->nbr_host[(size_t)ec * 6 + dc] != DGRHS_NEIGHBOR_HANGING ||
-        c->nbr_host[(size_t)ef * 6 + df] != DGRHS_NEIGHBOR_HANGING)
+    if ((ec >= 0 && c->nbr_host[(size_t)ec * 6 + dc] != DGRHS_NEIGHBOR_HANGING) ||
+        (ef >= 0 && c->nbr_host[(size_t)ef * 6 + df] != DGRHS_NEIGHBOR_HANGING))
       return fail("mortar %d: both faces must be marked DGRHS_NEIGHBOR_HANGING in the "
                   "neighbor table", order[k]);
-    if (fine_seen[(size_t)ef * 6 + df]++)
-      return fail("mortar %d: fine face listed twice", order[k]);
-    if (faces.empty() || faces[faces.size() - 4] != ec || faces[faces.size() - 3] != dc) {
+    if (ef >= 0) {
+      if (fine_seen[(size_t)ef * 6 + df]++)
+        return fail("mortar %d: fine face listed twice", order[k]);
+      ++local_fine;
+    }
+    const auto kk = key(order[k]);
+    if (kk != last_key) {
       faces.insert(faces.end(), {ec, dc, k, 0});
+      last_key = kk;
+      if (ec >= 0) ++local_coarse;
     }
     ++faces[faces.size() - 1];
     table.insert(table.end(), {ef, df, sa, sb});
@@ -1054,9 +1111,9 @@ int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
   // every hanging face must be covered, or the volume kernel would add stale data
   size_t hanging = 0;
   for (int v : c->nbr_host) hanging += v == DGRHS_NEIGHBOR_HANGING;
-  if (hanging != faces.size() / 4 + (size_t)n_mortars)
+  if (hanging != local_coarse + local_fine)
     return fail("%zu faces are marked hanging but the mortar table covers %zu", hanging,
-                faces.size() / 4 + (size_t)n_mortars);
+                local_coarse + local_fine);
   if (c->mortar_faces) cudaFree(c->mortar_faces);
   if (c->mortar_table) cudaFree(c->mortar_table);
   c->mortar_faces = c->mortar_table = nullptr;

@@ -1111,6 +1111,10 @@ struct MortarArgs {
   const int32_t* mortars;  // [n_mortars][4]      = fine element, direction, size_a, size_b
   const double* P;         // [3][N*N] parent->child, row-major [child point][parent point]
   const double* R;         // [3][N*N] child->parent, row-major [parent point][child point]
+  // a side that lives on another rank: element = -(slot + 2), its face arrived in
+  // ghost slot `slot` [HC][f] (u | J row | gammas, like every cut face)
+  const double* ghost;
+  int face_begin;          // first coarse-face group of this launch
 };
 
 // dg_boundary_terms of one pair from PACKAGED values (the n_i v^+- fields are
@@ -1154,28 +1158,45 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
   const int tid = threadIdx.x;
   const bool active = tid < f;
   const int qa = tid % N, qb = active ? tid / N : 0;
-  const int32_t* fc = a.faces + 4 * blockIdx.x;
+  const int32_t* fc = a.faces + 4 * (a.face_begin + blockIdx.x);
   const int ec = fc[0], dc = fc[1], m0 = fc[2], nm = fc[3];
+  constexpr int HC = C + 3 + (kSystem == 1 ? 2 : 1);
   for (int i = tid; i < 3 * N * N; i += T) {
     (&sP[0][0])[i] = a.P[i];
     (&sR[0][0])[i] = a.R[i];
   }
 
   // one side of the interface at this thread's point of face d of element e
-  auto make_side = [&](int e, int d, int p, GhFaceSide& sd) {
+  // (p = volume index of the point, q = its index on the face)
+  auto make_side = [&](int e, int d, int p, int q, GhFaceSide& sd) {
     const double sign = (d & 1) ? 1.0 : -1.0;
     const int dim = d >> 1;
-    double unn[3];
-    const double* jo = a.invjac + (size_t)e * 9 * npad + p;
+    double unn[3], g1, g2, g[10];
+    if (e >= 0) {
+      const double* jo = a.invjac + (size_t)e * 9 * npad + p;
 #pragma unroll
-    for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
-    const double* so = a.stat + (size_t)e * S * npad + p;
+      for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
+      const double* so = a.stat + (size_t)e * S * npad + p;
+      g1 = kSystem == 1 ? __ldg(so + npad) : 0.0;
+      g2 = kSystem == 1 ? __ldg(so + 2 * npad) : __ldg(so);
+      if constexpr (kSystem == 1) {
+        const double* uo = a.u + (size_t)e * C * npad + p;
+#pragma unroll
+        for (int s = 0; s < 10; ++s) g[s] = __ldg(uo + (size_t)s * npad);
+      }
+    } else {
+      const double* gs = a.ghost + (size_t)(-(e + 2)) * HC * f + q;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(gs + (size_t)(C + x) * f);
+      g1 = kSystem == 1 ? __ldg(gs + (size_t)(C + 3) * f) : 0.0;
+      g2 = kSystem == 1 ? __ldg(gs + (size_t)(C + 4) * f) : __ldg(gs + (size_t)(C + 3) * f);
+      if constexpr (kSystem == 1) {
+#pragma unroll
+        for (int s = 0; s < 10; ++s) g[s] = __ldg(gs + (size_t)s * f);
+      }
+    }
     if constexpr (kSystem == 1) {
-      double g[10];
-      const double* uo = a.u + (size_t)e * C * npad + p;
-#pragma unroll
-      for (int s = 0; s < 10; ++s) g[s] = __ldg(uo + (size_t)s * npad);
-      gh_face_side(g, unn, __ldg(so + npad), __ldg(so + 2 * npad), sd);
+      gh_face_side(g, unn, g1, g2, sd);
     } else {
       // flat-space normalisation (NormalCovectorAndMagnitude.hpp:78-90), speeds
       // lambda_psi = lambda_0 = 0, lambda_+- = +-1 (UpwindPenalty.cpp:60-75)
@@ -1183,7 +1204,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
       const double inv = 1.0 / sd.mag;
 #pragma unroll
       for (int x = 0; x < 3; ++x) sd.n_lo[x] = sd.n_up[x] = unn[x] * inv;
-      sd.gamma2 = __ldg(so);
+      sd.gamma2 = g2;
       sd.speed[0] = 0.0;
       sd.speed[1] = 0.0;
       sd.speed[2] = 1.0;
@@ -1191,19 +1212,21 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
     }
   };
   // packaged values of pair s on one side
-  auto package = [&](const GhFaceSide& sd, int e, int p, int s, double (&pk)[13]) {
-    const double* uo = a.u + (size_t)e * C * npad + p;
+  auto package = [&](const GhFaceSide& sd, int e, int p, int q, int s, double (&pk)[13]) {
+    const double* uo = e >= 0 ? a.u + (size_t)e * C * npad + p
+                              : a.ghost + (size_t)(-(e + 2)) * HC * f + q;
+    const size_t cs = e >= 0 ? (size_t)npad : (size_t)f;   // component stride
     double g, pi, ph[3];
     if constexpr (kSystem == 1) {
-      g = __ldg(uo + (size_t)s * npad);
-      pi = __ldg(uo + (size_t)(10 + s) * npad);
+      g = __ldg(uo + (size_t)s * cs);
+      pi = __ldg(uo + (size_t)(10 + s) * cs);
 #pragma unroll
-      for (int m = 0; m < 3; ++m) ph[m] = __ldg(uo + (size_t)(20 + m + 3 * s) * npad);
+      for (int m = 0; m < 3; ++m) ph[m] = __ldg(uo + (size_t)(20 + m + 3 * s) * cs);
     } else {
       g = __ldg(uo);
-      pi = __ldg(uo + npad);
+      pi = __ldg(uo + cs);
 #pragma unroll
-      for (int m = 0; m < 3; ++m) ph[m] = __ldg(uo + (size_t)(2 + m) * npad);
+      for (int m = 0; m < 3; ++m) ph[m] = __ldg(uo + (size_t)(2 + m) * cs);
     }
     GhPairPackaged k;
     gh_pair_package(sd, g, pi, ph, k);
@@ -1226,7 +1249,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
   GhFaceSide sC;
   const int pC = active ? face_point<N>(dc, qa, qb) : 0;
   if (active) {
-    make_side(ec, dc, pC, sC);
+    make_side(ec, dc, pC, tid, sC);
 #pragma unroll
     for (int x = 0; x < 4; ++x) sA[13 + x][tid] = sC.speed[x];
   }
@@ -1243,7 +1266,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
     const double* Rb = sR[sb];
     GhFaceSide sFn;
     const int pF = active ? face_point<N>(df, qa, qb) : 0;
-    if (active) make_side(ef, df, pF, sFn);
+    if (active) make_side(ef, df, pF, tid, sFn);
     const double liftF = active ? -0.5 * (double)(N * (N - 1)) * sFn.mag : 0.0;
     double spC[4] = {0.0, 0.0, 0.0, 0.0};  // coarse characteristic speeds on the mortar
 #pragma unroll 1
@@ -1251,7 +1274,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
       const int c_lo = 0, c_hi = s == 0 ? 17 : 13;
       if (active) {
         double pk[13];
-        package(sC, ec, pC, s, pk);
+        package(sC, ec, pC, tid, s, pk);
 #pragma unroll
         for (int c = 0; c < 13; ++c) sA[c][tid] = pk[c];
       }
@@ -1287,17 +1310,18 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
           }
         }
         double pkF[13];
-        package(sFn, ef, pF, s, pkF);
+        package(sFn, ef, pF, tid, s, pkF);
         pair_boundary_terms_packaged(sFn.speed, pkF, spC, pkC, cF);
         pair_boundary_terms_packaged(spC, pkC, sFn.speed, pkF, cC);
-        double* cf = corr_ptr(ef, s, df) + tid;
+        double* cf = corr_ptr(ef >= 0 ? ef : 0, s, df) + tid;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-          cf[(size_t)c * f] = cF[c] * liftF;
+          if (ef >= 0) cf[(size_t)c * f] = cF[c] * liftF;   // (a remote fine side: its rank does it)
           sE[c][tid] = cC[c];
         }
       }
       __syncthreads();
+      if (ec < 0) continue;   // remote coarse side: its rank projects and lifts (uniform branch)
       // project_from_mortar, first face dimension: thread = (a, b')
       if (active) {
 #pragma unroll

@@ -606,14 +606,21 @@ class Partition:
     """
 
     def __init__(self, neighbors: np.ndarray, world: int, rank: int,
-                 boundary_slots=False, neighbor_direction=None, face_permutation=None):
+                 boundary_slots=False, neighbor_direction=None, face_permutation=None,
+                 mortars=None):
         """boundary_slots: give external faces (neighbour -1) of local elements a
         ghost slot after the exchanged ones, to be filled with the exterior state
         of a ghost boundary condition (DirichletAnalytic); True = every external
         face, or a predicate (global element, direction) -> bool.
         neighbor_direction / face_permutation [n_elements, 6]: orientation of
-        non-aligned neighbours (default: aligned, neighbour direction d ^ 1)."""
+        non-aligned neighbours (default: aligned, neighbour direction d ^ 1).
+        mortars [n, 6]: global table of the non-conforming mortars (coarse element,
+        direction, fine element, direction, size_a, size_b).  local_mortars is the
+        same table in local numbering, rows in the global order; a side that lives
+        on another rank is a ghost slot, written -(slot + 2), which receives the
+        remote face like any cut face (one slot per mortar)."""
         ne = neighbors.shape[0]
+        mortars = np.zeros((0, 6), dtype=np.int64) if mortars is None else np.asarray(mortars)
         if neighbor_direction is None:
             neighbor_direction = np.tile((np.arange(6) ^ 1).astype(np.int32), (ne, 1))
             face_permutation = np.zeros((ne, 6), dtype=np.int32)
@@ -624,11 +631,22 @@ class Partition:
         for r in range(world):
             owner[bounds[r]:bounds[r + 1]] = r
         mine = np.arange(bounds[rank], bounds[rank + 1])
-        if world > 1 and (neighbors == HANGING).any():
-            raise NotImplementedError("non-conforming mortars across ranks")
+        if len(mortars) == 0 and (neighbors == HANGING).any():
+            raise ValueError("hanging faces without a mortar table")
         nb_mine = neighbors[mine]
         remote = (nb_mine >= 0) & (owner[np.clip(nb_mine, 0, ne - 1)] != rank)
         is_boundary = remote.any(axis=1)
+        # a mortar group (all mortars of one coarse face) with a member on another
+        # rank needs halo data: every local participant is a boundary element
+        group_remote = {}
+        for ec, dc, ef, df, _, _ in mortars.tolist():
+            key = (ec, dc)
+            group_remote[key] = group_remote.get(key, False) or owner[ec] != owner[ef]
+        for ec, dc, ef, df, _, _ in mortars.tolist():
+            if group_remote[(ec, dc)]:
+                for g in (ec, ef):
+                    if owner[g] == rank:
+                        is_boundary[g - bounds[rank]] = True
         order = np.concatenate([mine[~is_boundary], mine[is_boundary]])
         self.world, self.rank = world, rank
         self.global_ids = order                      # local -> global
@@ -653,15 +671,34 @@ class Partition:
                 if owner[v] == rank:
                     local_nb[le, d] = g2l[v]
                 else:
-                    recv.append((int(owner[v]), v, int(neighbor_direction[g, d]), le, d))
+                    recv.append((int(owner[v]), v, int(neighbor_direction[g, d]), int(g), d,
+                                 None))
+        # faces of remote mortar partners: one ghost slot per mortar
+        for m, (ec, dc, ef, df, _, _) in enumerate(mortars.tolist()):
+            if owner[ec] == rank and owner[ef] != rank:
+                recv.append((int(owner[ef]), ef, df, ec, dc, m))
+            elif owner[ef] == rank and owner[ec] != rank:
+                recv.append((int(owner[ec]), ec, dc, ef, df, m))
         # canonical order shared by both sides: by (peer, global element of the
-        # SENDER, sender direction)
-        recv.sort(key=lambda t: (t[0], t[1], t[2]))
+        # SENDER, sender direction, global element of the receiver, its direction)
+        recv.sort(key=lambda t: t[:5])
         self.recv_counts = [0] * world
-        for slot, (peer, v, dn, le, d) in enumerate(recv):
-            local_nb[le, d] = -(slot + 2)
+        mortar_slot = {}
+        for slot, (peer, v, dn, g, d, m) in enumerate(recv):
+            if m is None:
+                local_nb[g2l[g], d] = -(slot + 2)
+            else:
+                mortar_slot[m] = slot
             self.recv_counts[peer] += 1
         self.n_recv = len(recv)
+        rows = []
+        for m, (ec, dc, ef, df, sa, sb) in enumerate(mortars.tolist()):
+            if owner[ec] != rank and owner[ef] != rank:
+                continue
+            lc = g2l[ec] if owner[ec] == rank else -(mortar_slot[m] + 2)
+            lf = g2l[ef] if owner[ef] == rank else -(mortar_slot[m] + 2)
+            rows.append((lc, dc, lf, df, sa, sb))
+        self.local_mortars = np.asarray(rows, dtype=np.int32).reshape(-1, 6)
         self.external_faces = []  # (local element, direction, slot)
         if boundary_slots:
             wanted = boundary_slots if callable(boundary_slots) else (lambda g, d: True)
@@ -680,11 +717,17 @@ class Partition:
             for d in range(6):
                 v = int(neighbors[g, d])
                 if v >= 0 and owner[v] != rank:
-                    send.append((int(owner[v]), int(g), d, le))
-        send.sort(key=lambda t: (t[0], t[1], t[2]))
+                    # the receiver is the neighbour, seeing us through its direction
+                    send.append((int(owner[v]), int(g), d, v, int(neighbor_direction[g, d]), le))
+        for ec, dc, ef, df, _, _ in mortars.tolist():
+            if owner[ec] == rank and owner[ef] != rank:
+                send.append((int(owner[ef]), ec, dc, ef, df, g2l[ec]))
+            elif owner[ef] == rank and owner[ec] != rank:
+                send.append((int(owner[ec]), ef, df, ec, dc, g2l[ef]))
+        send.sort(key=lambda t: t[:5])
         self.send_counts = [0] * world
         self.send_map = np.zeros((len(send), 2), dtype=np.int32)
-        for slot, (peer, g, d, le) in enumerate(send):
+        for slot, (peer, g, d, gr, dr, le) in enumerate(send):
             self.send_map[slot] = (le, d)
             self.send_counts[peer] += 1
         assert len(send) == len(recv) or world > 1  # symmetric on periodic bricks

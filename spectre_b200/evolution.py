@@ -210,7 +210,8 @@ class Evolution:
         self.part = domain.Partition(problem.neighbors, world, rank,
                                      boundary_slots=problem.dirichlet_analytic,
                                      neighbor_direction=problem.orientations[0],
-                                     face_permutation=problem.orientations[1])
+                                     face_permutation=problem.orientations[1],
+                                     mortars=problem.mortars)
         ids = self.part.global_ids
         self.ctx = lib.Context(problem.system, problem.N, self.part.n_local,
                                self.part.n_ghost, device)
@@ -228,14 +229,10 @@ class Evolution:
         if self.part.oriented:
             ctx.set_neighbor_orientations(self.part.local_neighbor_direction,
                                           self.part.local_face_permutation)
-        if len(problem.mortars):
-            if world > 1:
-                raise NotImplementedError("non-conforming mortars across ranks")
-            g2l = {int(g): i for i, g in enumerate(ids)}
-            local = np.array([[g2l[m[0]], m[1], g2l[m[2]], m[3], m[4], m[5]]
-                              for m in problem.mortars.tolist()], dtype=np.int32)
-            self.local_mortars = local
-            ctx.set_mortars(local)
+        if len(self.part.local_mortars):
+            # (sides on other ranks are ghost slots, Partition.local_mortars)
+            self.local_mortars = self.part.local_mortars
+            ctx.set_mortars(self.local_mortars)
         if problem.demand_outgoing:
             ctx.set_demand_outgoing_char_speeds(True)
         ctx.set_static_fields(problem.static(ids))
