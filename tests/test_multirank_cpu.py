@@ -175,3 +175,52 @@ def _shell_worker(rank, world, port, order, results):
 @pytest.mark.parametrize("world,order", [(2, "block"), (2, "radial"), (3, "block")])
 def test_shell_partition_and_oriented_halo_exchange_gloo(world, order):
     mp.spawn(_shell_worker, args=(world, _free_port(), order, None), nprocs=world, join=True)
+
+
+def _mortar_worker(rank, world, port, results):
+    """Mortars whose sides live on different ranks: the remote side's face arrives
+    in the ghost slot named in Partition.local_mortars."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N,
+                             {(0, 0, 0): (True, True, True), (1, 1, 0): (True, False, True)})
+    nb, mt = rb.neighbors(), rb.mortars()
+    part = domain.Partition(nb, world, rank, mortars=mt)
+    send = torch.zeros(max(part.n_ghost, 1) * HC * F, dtype=torch.float64)
+    sv = send.numpy().reshape(-1, HC, F)
+    for slot, (le, d) in enumerate(part.send_map):
+        sv[slot] = _field(part.global_ids[le], rb.n_elements)[:, _face_points(d)]
+    recv = torch.full((max(part.n_ghost, 1) * HC * F,), -1.0, dtype=torch.float64)
+    halo = HaloExchange(part, HC * F, dist)
+    for w in halo.start(send, recv):
+        w.wait()
+    rv = recv.numpy().reshape(-1, HC, F)
+    # global rows of my mortars, in the same order as local_mortars
+    bounds = [(rb.n_elements * r) // world for r in range(world + 1)]
+    owner = lambda g: max(r for r in range(world) if bounds[r] <= g)
+    mine = [m for m in mt.tolist() if owner(m[0]) == rank or owner(m[2]) == rank]
+    assert len(mine) == len(part.local_mortars)
+    remote = 0
+    for (ec, dc, ef, df, sa, sb), (lc, dc2, lf, df2, sa2, sb2) in zip(mine, part.local_mortars):
+        assert (dc, df, sa, sb) == (dc2, df2, sa2, sb2)
+        for g, d, l in ((ec, dc, lc), (ef, df, lf)):
+            if l >= 0:
+                assert part.global_ids[l] == g
+                assert part.local_neighbors[l, d] == domain.HANGING
+                assert l >= part.n_interior or owner(ec) == owner(ef)
+            else:
+                expect = _field(g, rb.n_elements)[:, _face_points(d)]
+                np.testing.assert_array_equal(rv[-(l + 2)], expect)
+                remote += 1
+    counts = [None] * world
+    dist.all_gather_object(counts, remote)
+    if rank == 0:
+        assert sum(counts) > 0 and sum(counts) % 2 == 0   # every cut mortar is seen from both sides
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_mortars_across_ranks_gloo(world):
+    mp.spawn(_mortar_worker, args=(world, _free_port(), None), nprocs=world, join=True)
