@@ -137,7 +137,10 @@ __device__ __forceinline__ void logical_derivs(const double* __restrict__ tc,
   // N = 12: two partial sums per direction (even and odd m) halve the length of
   // the dependent DFMA chains; measured 6.61 -> 6.38 ms per fused launch on the
   // Kerr-Schild workload (4096 elements), but slower for N = 10 (3.24 -> 3.36 ms)
-  if constexpr (N >= 12 && N % 2 == 0) {
+#ifndef DG_SPLIT_ACC_MIN_N
+#define DG_SPLIT_ACC_MIN_N 12
+#endif
+  if constexpr (N >= DG_SPLIT_ACC_MIN_N && N % 2 == 0) {
     double e0 = 0.0, e1 = 0.0, e2 = 0.0, o0 = 0.0, o1 = 0.0, o2 = 0.0;
     const double2* row2 = reinterpret_cast<const double2*>(row);
 #pragma unroll
