@@ -306,6 +306,24 @@ int dgrhs_gh_time_derivative(int n, const double* u, const double* du,
                              const double* gamma2, int harmonic,
                              const double* gauge_h, const double* d4_gauge_h,
                              double* dt_u);
+/* gh::BoundaryConditions::ConstraintPreservingBjorhus<3>::dg_time_derivative
+ * (GeneralizedHarmonic/BoundaryConditions/Bjorhus.hpp, Bjorhus.cpp:104-391) on n
+ * face points of a static mesh (face_mesh_velocity == nullopt), arguments in the
+ * reference's order and Tensor storage order ([independent component][n]:
+ * tnsr::i 3, tnsr::aa / AA 10, tnsr::iaa 30 at i + 3 sym, tnsr::ijaa 90 at
+ * i + 3 (j + 3 sym), tnsr::ab 16 at a + 4 b); physical = 0 Type
+ * ConstraintPreserving, 1 ConstraintPreservingPhysical.  The unused
+ * normal_vector and d_spacetime_metric arguments of the reference are omitted. */
+int dgrhs_gh_bjorhus_dg_time_derivative(
+    int n, int physical, const double* normal_covector, const double* spacetime_metric,
+    const double* pi, const double* phi, const double* coords, const double* gamma1,
+    const double* gamma2, const double* lapse, const double* shift,
+    const double* inverse_spacetime_metric, const double* spacetime_unit_normal_vector,
+    const double* three_index_constraint, const double* gauge_source,
+    const double* spacetime_deriv_gauge_source, const double* dt_spacetime_metric,
+    const double* dt_pi, const double* dt_phi, const double* d_pi, const double* d_phi,
+    double* dt_spacetime_metric_correction, double* dt_pi_correction,
+    double* dt_phi_correction);
 /* ScalarWave::TimeDerivative<3>::apply (ScalarWave/TimeDerivative.hpp:26-50,
  * TimeDerivative.cpp:14-45): u [5][n], du [15][n], gamma2 [n] -> dt_u [5][n] */
 int dgrhs_sw_time_derivative(int n, const double* u, const double* du,

@@ -14,6 +14,7 @@
 
 #include "../../include/dgrhs.h"
 #include "pointwise.cuh"
+#include "bjorhus.cuh"
 
 extern "C" void dgrhs_internal_set_error(const char* msg);
 extern "C" void dgrhs_internal_count_launch(void);
@@ -271,7 +272,110 @@ int grid(int n) { return (n + 127) / 128; }
 
 }  // namespace
 
+// gh::BoundaryConditions::ConstraintPreservingBjorhus<3>::dg_time_derivative
+// (Bjorhus.cpp:104-391) on n face points, every tensor in the reference's storage
+// order (first index fastest, symmetric pairs 00 01 02 03 11 12 13 22 23 33)
+struct BjorhusOpArgs {
+  const double *n_lo, *g, *pi, *phi, *x, *gamma1, *gamma2, *lapse, *shift, *ipsi, *t_up, *c3, *H,
+      *dH, *dt_g, *dt_pi, *dt_phi, *d_pi, *d_phi;
+  double *out_g, *out_pi, *out_phi;
+};
+
+__global__ void gh_bjorhus_op_kernel(int n, int physical, BjorhusOpArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  dg::BjorhusInput in;
+  in.physical = physical != 0;
+  in.gamma1 = a.gamma1[p];
+  in.gamma2 = a.gamma2[p];
+  in.lapse = a.lapse[p];
+  for (int i = 0; i < 3; ++i) {
+    in.n_lo[i] = a.n_lo[(size_t)i * n + p];
+    in.x[i] = a.x[(size_t)i * n + p];
+    in.shift[i] = a.shift[(size_t)i * n + p];
+  }
+  for (int aa = 0; aa < 4; ++aa) {
+    in.t_up[aa] = a.t_up[(size_t)aa * n + p];
+    in.H[aa] = a.H[(size_t)aa * n + p];
+    for (int bb = 0; bb < 4; ++bb) {
+      const size_t s = dg::sym4(aa, bb);
+      in.dH[aa][bb] = a.dH[(size_t)(aa + 4 * bb) * n + p];
+      in.g[aa][bb] = a.g[s * n + p];
+      in.pi[aa][bb] = a.pi[s * n + p];
+      in.ipsi[aa][bb] = a.ipsi[s * n + p];
+      in.dt_g[aa][bb] = a.dt_g[s * n + p];
+      in.dt_pi[aa][bb] = a.dt_pi[s * n + p];
+      for (int i = 0; i < 3; ++i) {
+        in.phi[i][aa][bb] = a.phi[(i + 3 * s) * n + p];
+        in.c3[i][aa][bb] = a.c3[(i + 3 * s) * n + p];
+        in.dt_phi[i][aa][bb] = a.dt_phi[(i + 3 * s) * n + p];
+        in.d_pi[i][aa][bb] = a.d_pi[(i + 3 * s) * n + p];
+        for (int j = 0; j < 3; ++j) in.d_phi[i][j][aa][bb] = a.d_phi[(i + 3 * (j + 3 * s)) * n + p];
+      }
+    }
+  }
+  dg::BjorhusOutput out;
+  dg::bjorhus_constraint_preserving(in, out);
+  for (int aa = 0; aa < 4; ++aa)
+    for (int bb = aa; bb < 4; ++bb) {
+      const size_t s = dg::sym4(aa, bb);
+      a.out_g[s * n + p] = out.g[aa][bb];
+      a.out_pi[s * n + p] = out.pi[aa][bb];
+      for (int i = 0; i < 3; ++i) a.out_phi[(i + 3 * s) * n + p] = out.phi[i][aa][bb];
+    }
+}
+
 extern "C" {
+
+int dgrhs_gh_bjorhus_dg_time_derivative(
+    int n, int physical, const double* normal_covector, const double* spacetime_metric,
+    const double* pi, const double* phi, const double* coords, const double* gamma1,
+    const double* gamma2, const double* lapse, const double* shift,
+    const double* inverse_spacetime_metric, const double* spacetime_unit_normal_vector,
+    const double* three_index_constraint, const double* gauge_source,
+    const double* spacetime_deriv_gauge_source, const double* dt_spacetime_metric,
+    const double* dt_pi, const double* dt_phi, const double* d_pi, const double* d_phi,
+    double* dt_spacetime_metric_correction, double* dt_pi_correction,
+    double* dt_phi_correction) {
+  if (need_gpu()) return 1;
+  if (n < 1) return fail("n must be positive");
+  Staged st;
+  BjorhusOpArgs a;
+  a.n_lo = st.in(normal_covector, (size_t)3 * n);
+  a.g = st.in(spacetime_metric, (size_t)10 * n);
+  a.pi = st.in(pi, (size_t)10 * n);
+  a.phi = st.in(phi, (size_t)30 * n);
+  a.x = st.in(coords, (size_t)3 * n);
+  a.gamma1 = st.in(gamma1, n);
+  a.gamma2 = st.in(gamma2, n);
+  a.lapse = st.in(lapse, n);
+  a.shift = st.in(shift, (size_t)3 * n);
+  a.ipsi = st.in(inverse_spacetime_metric, (size_t)10 * n);
+  a.t_up = st.in(spacetime_unit_normal_vector, (size_t)4 * n);
+  a.c3 = st.in(three_index_constraint, (size_t)30 * n);
+  a.H = st.in(gauge_source, (size_t)4 * n);
+  a.dH = st.in(spacetime_deriv_gauge_source, (size_t)16 * n);
+  a.dt_g = st.in(dt_spacetime_metric, (size_t)10 * n);
+  a.dt_pi = st.in(dt_pi, (size_t)10 * n);
+  a.dt_phi = st.in(dt_phi, (size_t)30 * n);
+  a.d_pi = st.in(d_pi, (size_t)30 * n);
+  a.d_phi = st.in(d_phi, (size_t)90 * n);
+  a.out_g = st.in(nullptr, (size_t)10 * n);
+  a.out_pi = st.in(nullptr, (size_t)10 * n);
+  a.out_phi = st.in(nullptr, (size_t)30 * n);
+  if (!a.n_lo || !a.g || !a.pi || !a.phi || !a.x || !a.gamma1 || !a.gamma2 || !a.lapse ||
+      !a.shift || !a.ipsi || !a.t_up || !a.c3 || !a.H || !a.dH || !a.dt_g || !a.dt_pi ||
+      !a.dt_phi || !a.d_pi || !a.d_phi || !a.out_g || !a.out_pi || !a.out_phi)
+    return fail("device staging failed");
+  gh_bjorhus_op_kernel<<<grid(n), 128>>>(n, physical, a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(dt_spacetime_metric_correction, a.out_g, (size_t)10 * n * 8,
+                cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(dt_pi_correction, a.out_pi, (size_t)10 * n * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(dt_phi_correction, a.out_phi, (size_t)30 * n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 int dgrhs_gh_time_derivative(int n, const double* u, const double* du,
                              const double* gamma0, const double* gamma1,

@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <optional>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "../../include/dgrhs.h"
@@ -462,6 +463,54 @@ class UpwindPenalty {
   }
 };
 }  // namespace BoundaryCorrections
+
+namespace BoundaryConditions {
+namespace detail {
+enum class ConstraintPreservingBjorhusType { ConstraintPreserving, ConstraintPreservingPhysical };
+}
+// gh::BoundaryConditions::ConstraintPreservingBjorhus<3> (GeneralizedHarmonic/
+// BoundaryConditions/Bjorhus.hpp): dg_time_derivative with the reference's argument
+// list; returns the reference's optional error message (none on a static mesh)
+template <size_t Dim>
+class ConstraintPreservingBjorhus {
+ public:
+  static_assert(Dim == 3);
+  explicit ConstraintPreservingBjorhus(detail::ConstraintPreservingBjorhusType type) : type_(type) {}
+  std::optional<std::string> dg_time_derivative(
+      tnsr::aa10* dt_spacetime_metric_correction, tnsr::aa10* dt_pi_correction,
+      tnsr::iaa30* dt_phi_correction, const std::optional<tnsr::i3>& face_mesh_velocity,
+      const tnsr::i3& normal_covector, const tnsr::i3& /*normal_vector*/,
+      const tnsr::aa10& spacetime_metric, const tnsr::aa10& pi, const tnsr::iaa30& phi,
+      const tnsr::i3& coords, const ScalarDV& gamma1, const ScalarDV& gamma2, const ScalarDV& lapse,
+      const tnsr::i3& shift, const tnsr::aa10& inverse_spacetime_metric,
+      const tnsr::a4& spacetime_unit_normal_vector, const tnsr::iaa30& three_index_constraint,
+      const tnsr::a4& gauge_source, const tnsr::ab16& spacetime_deriv_gauge_source,
+      const tnsr::aa10& logical_dt_spacetime_metric, const tnsr::aa10& logical_dt_pi,
+      const tnsr::iaa30& logical_dt_phi, const tnsr::iaa30& /*d_spacetime_metric*/,
+      const tnsr::iaa30& d_pi, const tnsr::ijaa90& d_phi) const {
+    if (face_mesh_velocity.has_value()) throw std::runtime_error("moving meshes are out of scope of this path");
+    const size_t n = lapse.get().size();
+    std::vector<double> og(10 * n), op(10 * n), oph(30 * n);
+    check(dgrhs_gh_bjorhus_dg_time_derivative(
+        static_cast<int>(n), type_ == detail::ConstraintPreservingBjorhusType::ConstraintPreservingPhysical,
+        normal_covector.flat().data(), spacetime_metric.flat().data(), pi.flat().data(), phi.flat().data(),
+        coords.flat().data(), gamma1.get().data(), gamma2.get().data(), lapse.get().data(),
+        shift.flat().data(), inverse_spacetime_metric.flat().data(),
+        spacetime_unit_normal_vector.flat().data(), three_index_constraint.flat().data(),
+        gauge_source.flat().data(), spacetime_deriv_gauge_source.flat().data(),
+        logical_dt_spacetime_metric.flat().data(), logical_dt_pi.flat().data(),
+        logical_dt_phi.flat().data(), d_pi.flat().data(), d_phi.flat().data(), og.data(), op.data(),
+        oph.data()));
+    dt_spacetime_metric_correction->from_flat(og.data(), n);
+    dt_pi_correction->from_flat(op.data(), n);
+    dt_phi_correction->from_flat(oph.data(), n);
+    return std::nullopt;
+  }
+
+ private:
+  detail::ConstraintPreservingBjorhusType type_;
+};
+}  // namespace BoundaryConditions
 }  // namespace gh
 
 // ---- TimeSteppers ------------------------------------------------------------------

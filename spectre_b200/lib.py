@@ -35,7 +35,7 @@ EXPORTS = [
     "dgrhs_synchronize", "dgrhs_stream", "dgrhs_state_device_ptr",
     "dgrhs_padded_points", "dgrhs_partial_derivatives", "dgrhs_differentiation_matrix",
     "dgrhs_collocation_points_and_weights", "dgrhs_adams_bashforth_coefficients",
-    "dgrhs_gh_time_derivative", "dgrhs_sw_time_derivative", "dgrhs_gh_package_data",
+    "dgrhs_gh_time_derivative", "dgrhs_gh_bjorhus_dg_time_derivative", "dgrhs_sw_time_derivative", "dgrhs_gh_package_data",
     "dgrhs_gh_boundary_terms", "dgrhs_sw_package_data", "dgrhs_sw_boundary_terms",
     "dgrhs_lift_flux",
 ]

@@ -54,6 +54,32 @@ int main() {
   gh::TimeDerivative<3>::apply(&dtg, &dtPi, &dtPhi, &t1, &t2, dg, dPi, dPhi, g, Pi, Phi, g0, g1, g2, harmonic);
   for (size_t p = 0; p < n; ++p) err = std::fmax(err, std::fabs(dtg.get(2, 1)[p] + Pi.get(1, 2)[p]));
   if (err > 1e-16) { std::printf("GH dt g != -lapse Pi: %g\n", err); return 1; }
+  // ---- ConstraintPreservingBjorhus::dg_time_derivative: flat space with no time
+  //      derivative and satisfied constraints needs no boundary correction ----
+  {
+    using Type = gh::BoundaryConditions::detail::ConstraintPreservingBjorhusType;
+    const gh::BoundaryConditions::ConstraintPreservingBjorhus<3> bc(Type::ConstraintPreservingPhysical);
+    tnsr::aa10 flat(n), zero_aa(n), cg(n), cPi(n);
+    tnsr::iaa30 zero_iaa(n), cPhi(n);
+    tnsr::ijaa90 zero_ijaa(n);
+    tnsr::i3 normal(n), coords(n), shift(n);
+    tnsr::a4 t_up(n), H(n);
+    tnsr::ab16 dH(n);
+    ScalarDV lapse(n, 1.0), gam1(n, -1.0), gam2(n, 1.0);
+    for (size_t p = 0; p < n; ++p) {
+      flat.get(0, 0)[p] = -1.0; flat.get(1, 1)[p] = flat.get(2, 2)[p] = flat.get(3, 3)[p] = 1.0;
+      normal.get(0)[p] = 1.0; coords.get(0)[p] = 10.0; t_up.get(0)[p] = 1.0;
+    }
+    fill(cg); fill(cPi); fill(cPhi);
+    const auto msg = bc.dg_time_derivative(&cg, &cPi, &cPhi, std::nullopt, normal, normal, flat, zero_aa, zero_iaa,
+                                           coords, gam1, gam2, lapse, shift, flat, t_up, zero_iaa, H, dH, zero_aa,
+                                           zero_aa, zero_iaa, zero_iaa, zero_iaa, zero_ijaa);
+    err = 0.0;
+    for (auto& c : cg) for (size_t p = 0; p < n; ++p) err = std::fmax(err, std::fabs(c[p]));
+    for (auto& c : cPi) for (size_t p = 0; p < n; ++p) err = std::fmax(err, std::fabs(c[p]));
+    for (auto& c : cPhi) for (size_t p = 0; p < n; ++p) err = std::fmax(err, std::fabs(c[p]));
+    if (msg.has_value() || err != 0.0) { std::printf("Bjorhus flat-space correction not zero: %g\n", err); return 1; }
+  }
   // ---- spectral + stepper helpers ----
   const auto D = Spectral::differentiation_matrix(5);
   const auto x = Spectral::collocation_points(5);

@@ -148,3 +148,57 @@ def test_cpp_level2_example_matches_oracle():
     for name, (a, b) in zip(("Psi", "Pi", "Phi"), ((0, 1), (1, 2), (2, 5))):
         want = np.sqrt(np.sum((ev.u[:, a:b] - exact[:, a:b]) ** 2) / npts)
         assert got[f"Error({name})"] == pytest.approx(want, rel=1e-8)
+
+
+@pytest.mark.parametrize("physical", [False, True])
+def test_bjorhus_dg_time_derivative_vs_reference_numpy_fixtures(golden_dir, physical):
+    """ConstraintPreservingBjorhus::dg_time_derivative through the operator-level
+    C-ABI entry point, fed like Test_Bjorhus.cpp feeds the C++ (an independent random
+    tensor for every argument), against the outputs of the reference's Bjorhus.py."""
+    import ctypes
+    z = np.load(os.path.join(golden_dir, "bjorhus.npz"))
+    n = len(z["in_lapse"])
+    pairs = [(a, b) for a in range(4) for b in range(a, 4)]
+
+    def aa(t):      # [n,4,4] -> [10][n]
+        return np.ascontiguousarray(np.stack([t[:, a, b] for a, b in pairs]))
+
+    def iaa(t):     # [n,3,4,4] -> [30][n] at i + 3 sym
+        out = np.zeros((30, n))
+        for s, (a, b) in enumerate(pairs):
+            for i in range(3):
+                out[i + 3 * s] = t[:, i, a, b]
+        return out
+
+    def ijaa(t):    # [n,3,3,4,4] -> [90][n] at i + 3 (j + 3 sym)
+        out = np.zeros((90, n))
+        for s, (a, b) in enumerate(pairs):
+            for j in range(3):
+                for i in range(3):
+                    out[i + 3 * (j + 3 * s)] = t[:, i, j, a, b]
+        return out
+
+    def vec(t):     # [n,k] -> [k][n]
+        return np.ascontiguousarray(t.T)
+    I = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+    dH = np.zeros((16, n))
+    for a in range(4):
+        for b in range(4):
+            dH[a + 4 * b] = I["spacetime_deriv_gauge_source"][:, a, b]
+    args = [vec(I["normal_covector"]), aa(I["spacetime_metric"]), aa(I["pi"]), iaa(I["phi"]),
+            vec(I["coords"]), I["gamma1"].copy(), I["gamma2"].copy(), I["lapse"].copy(),
+            vec(I["shift"]), aa(I["inverse_spacetime_metric"]),
+            vec(I["spacetime_unit_normal_vector"]), iaa(I["three_index_constraint"]),
+            vec(I["gauge_source"]), dH, aa(I["dt_spacetime_metric"]), aa(I["dt_pi"]),
+            iaa(I["dt_phi"]), iaa(I["d_pi"]), ijaa(I["d_phi"])]
+    args = [np.ascontiguousarray(a, dtype=np.float64) for a in args]
+    og, op, oph = np.zeros((10, n)), np.zeros((10, n)), np.zeros((30, n))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib._check(lib.load().dgrhs_gh_bjorhus_dg_time_derivative(
+        n, int(physical), *[P(a) for a in args], P(og), P(op), P(oph)))
+    want_pi = z["out_phys_corr_pi"] if physical else z["out_corr_pi"]
+    want_phi = z["out_phys_corr_phi"] if physical else z["out_corr_phi"]
+    scale = np.abs(want_pi).max()
+    assert np.max(np.abs(og - aa(z["out_corr_g"]))) < 1e-12 * scale
+    assert np.max(np.abs(op - aa(want_pi))) < 1e-12 * scale
+    assert np.max(np.abs(oph - iaa(want_phi))) < 1e-12 * scale
