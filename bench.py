@@ -249,6 +249,8 @@ def main():
     ap.add_argument("--cpu-sample-refine", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-pipeline", action="store_true",
+                    help="measure e2e with blocking calls on one context only")
     ap.add_argument("--outer-boundary", default="DirichletAnalytic",
                     choices=["DirichletAnalytic", "ConstraintPreserving",
                              "ConstraintPreservingPhysical"],
@@ -441,6 +443,41 @@ def main():
                "h2d_bytes_per_step": int(nbytes) * world, "d2h_bytes_per_step": int(nbytes) * world,
                "steps": k_e2e,
                "what": "dgrhs_set_state(pinned host) + one AB3 step + dgrhs_get_state per step"}
+        if world == 1 and not args.no_e2e_pipeline:
+            # the same three calls per batch in their stream-ordered form on two contexts:
+            # batch i+1 uploads while batch i steps and downloads (PCIe is full duplex);
+            # every batch still crosses the bus both ways inside the timed region
+            serial = e2e["value"]
+            ev_b = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, args.dt, 0.0, gauge,
+                                       (0.1, 1.0) if args.gauge == "analytic" else (), local_rank,
+                                       world, rank, pg)
+            ev_b.take_steps(args.warmup)          # self-start outside the timed region
+            host_b = torch.empty(state.size, dtype=torch.float64, pin_memory=True)
+            host_b_np = host_b.numpy().reshape(state.shape)
+            host_b_np[...] = state
+            lanes = [(ev, host_np), (ev_b, host_b_np)]
+            k_pipe = 2 * k_e2e
+            for e, _ in lanes:
+                e.ctx.synchronize()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(k_pipe):
+                e, h = lanes[i % 2]
+                e.ctx.synchronize()               # this lane's previous batch is back on the host
+                e.ctx.set_state_async(h)
+                e.take_steps(1)
+                e.ctx.get_state_async(h)
+            for e, _ in lanes:
+                e.ctx.synchronize()
+            el = time.perf_counter() - t0
+            assert np.isfinite(host_np).all() and np.isfinite(host_b_np).all()
+            e2e.update({"value": total_points * k_pipe / el, "steps": k_pipe,
+                        "serial_value": serial,
+                        "what": "per batch: dgrhs_set_state_async(pinned host) + one AB3 step + "
+                                "dgrhs_get_state_async, two contexts double-buffered so one "
+                                "batch uploads while the other steps and downloads; "
+                                "serial_value = one context, blocking calls"})
+            del ev_b
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -125,6 +125,14 @@ int dgrhs_set_gauge_analytic_christoffel(dgrhs_ctx* ctx, const double* u_analyti
 /* Evolved variables, host [n_elements][n_vars][n] (Variables layout). */
 int dgrhs_set_state(dgrhs_ctx* ctx, const double* u);
 int dgrhs_get_state(dgrhs_ctx* ctx, double* u);
+/* Stream-ordered forms of the two calls above: the copy is queued behind the
+ * context's earlier work (steps included) and the call returns immediately;
+ * `u` must stay valid, and for a copy that really overlaps other contexts'
+ * work be page-locked, until dgrhs_synchronize(ctx) returns.  Two contexts
+ * driven this way double-buffer independent batches: one uploads while the
+ * other steps and downloads (PCIe is full duplex). */
+int dgrhs_set_state_async(dgrhs_ctx* ctx, const double* u);
+int dgrhs_get_state_async(dgrhs_ctx* ctx, double* u);
 /* Last computed time derivative (after boundary corrections), same layout. */
 int dgrhs_get_time_derivative(dgrhs_ctx* ctx, double* dt_u);
 

@@ -387,11 +387,10 @@ DG_HD_NOINLINE void bjorhus_constraint_preserving(const BjorhusInput& in, Bjorhu
   {
     // constraint-dependent terms (BjorhusImpl.cpp:153-221, mu = 0) and gauge
     // Sommerfeld terms (:105-151)
-    double nc2[4], common[4];
+    double common[4];
     for (int a = 0; a < 4; ++a) {
       double v = 0.0;
       for (int i = 0; i < 3; ++i) v += n_up[i] * c2[i][a];
-      nc2[a] = v;
       common[a] = r2 * speed[3] * (fc[a] + v);          // c^{0-}_a = F_a + n^k C_ka
     }
     double uAu = 0.0, trA = 0.0, in_A[4], A_in[4];
@@ -442,7 +441,6 @@ DG_HD_NOINLINE void bjorhus_constraint_preserving(const BjorhusInput& in, Bjorhu
                        uBv * out_lo[a] * in_lo[b] - vBv * in_lo[a] * in_lo[b]);
         bc_minus[a][b] = v - rhs_minus[a][b];
       }
-    (void)nc2;
   }
   if (in.physical) {
     // add_physical_terms_to_dt_v_minus (BjorhusImpl.cpp:223-494; mu_phys = 0,

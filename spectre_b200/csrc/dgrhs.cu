@@ -1212,6 +1212,22 @@ int dgrhs_get_state(dgrhs_ctx* c, double* u) {
   CU(cudaSetDevice(c->device));
   return download(c, u, c->u, c->C);
 }
+// stream-ordered forms: the copy is queued behind the context's earlier work and the
+// call returns at once (page-locked host memory needed for a truly asynchronous copy)
+int dgrhs_set_state_async(dgrhs_ctx* c, const double* u) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy2DAsync(c->u, (size_t)c->npad * 8, u, (size_t)c->n * 8, (size_t)c->n * 8,
+                       (size_t)c->nelem * c->C, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+int dgrhs_get_state_async(dgrhs_ctx* c, double* u) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy2DAsync(u, (size_t)c->n * 8, c->u, (size_t)c->npad * 8, (size_t)c->n * 8,
+                       (size_t)c->nelem * c->C, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
 int dgrhs_get_time_derivative(dgrhs_ctx* c, double* dt_u) {
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));

@@ -24,6 +24,7 @@ EXPORTS = [
     "dgrhs_set_geometry", "dgrhs_set_neighbor_orientations", "dgrhs_set_static_fields", "dgrhs_set_gauge",
     "dgrhs_set_gauge_fields", "dgrhs_set_gauge_analytic_christoffel",
     "dgrhs_set_boundary_ghost_data", "dgrhs_set_state", "dgrhs_get_state",
+    "dgrhs_set_state_async", "dgrhs_get_state_async",
     "dgrhs_get_time_derivative", "dgrhs_compute_time_derivative", "dgrhs_set_interior_count",
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
@@ -256,6 +257,18 @@ class Context:
         u = np.zeros((self.n_elements, self.n_vars, self.n))
         _check(self._lib.dgrhs_get_state(self._h, _ptr(u)))
         return u
+
+    def set_state_async(self, u):
+        """Stream-ordered upload; `u` ([E][vars][n] float64, C-contiguous, ideally
+        page-locked) must stay alive until `synchronize()`."""
+        assert u.dtype == np.float64 and u.flags.c_contiguous
+        assert u.shape == (self.n_elements, self.n_vars, self.n), u.shape
+        _check(self._lib.dgrhs_set_state_async(self._h, _ptr(u)))
+
+    def get_state_async(self, out):
+        assert out.dtype == np.float64 and out.flags.c_contiguous
+        assert out.shape == (self.n_elements, self.n_vars, self.n), out.shape
+        _check(self._lib.dgrhs_get_state_async(self._h, _ptr(out)))
 
     def get_time_derivative(self):
         u = np.zeros((self.n_elements, self.n_vars, self.n))

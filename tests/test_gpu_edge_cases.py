@@ -141,3 +141,50 @@ def test_demand_outgoing_check_needs_enabling():
     assert rc != 0 and n.value == 6 * N * N and mn.value == pytest.approx(-1.0, abs=1e-14)
     ctx.set_demand_outgoing_char_speeds(False)
     ctx.close()
+
+
+def test_stream_ordered_state_transfers_double_buffered():
+    """dgrhs_set_state_async / dgrhs_get_state_async: two contexts that alternate
+    batches (one uploads while the other steps and downloads) return exactly what
+    the blocking calls return for the same batches."""
+    import torch
+    N = 4
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    E = brick.n_elements
+    x, J, nbr = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    stat = np.zeros((E, 1, N ** 3))
+    rng = np.random.default_rng(11)
+    batches = [rng.uniform(-1, 1, (E, 5, N ** 3)) for _ in range(6)]
+
+    def make():
+        c = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, E, 0)
+        c.set_geometry(J, x, nbr)
+        c.set_static_fields(stat)
+        c.set_stepper(lib.STEPPER_RK3_HESTHAVEN, 3, 0.0, 1e-3)
+        return c
+    ref_ctx = make()
+    want = []
+    for b in batches:
+        ref_ctx.set_state(b)
+        ref_ctx.take_steps(1)
+        want.append(ref_ctx.get_state())
+    ref_ctx.close()
+    lanes = [make(), make()]
+    pinned = [[torch.empty(b.size, dtype=torch.float64, pin_memory=True) for b in batches]
+              for _ in range(2)]
+    outs = []
+    for i, b in enumerate(batches):
+        c = lanes[i % 2]
+        src = pinned[0][i].numpy().reshape(b.shape)
+        dst = pinned[1][i].numpy().reshape(b.shape)
+        src[...] = b
+        c.set_state_async(src)
+        c.take_steps(1)
+        c.get_state_async(dst)
+        outs.append(dst)
+    for c in lanes:
+        c.synchronize()
+    for got, ref in zip(outs, want):
+        np.testing.assert_array_equal(got, ref)
+    for c in lanes:
+        c.close()
