@@ -194,7 +194,7 @@ int64_t dgrhs_rhs_evaluations(dgrhs_ctx* ctx);
  * *time the time at which the RHS must be evaluated; end_substep records the
  * derivative and updates u. is_step_done is set when a full step completed. */
 int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
-/* Non-conforming (h-refined, 2:1) mortars, aligned blocks, equal N on both sides.
+/* Non-conforming (h-refined, 2:1) mortars, equal N on both sides.
  * Faces on either side of such an interface carry DGRHS_NEIGHBOR_HANGING in the
  * neighbor table of dgrhs_set_geometry (Element<3>::neighbors() holds several
  * ids for that direction); the mortar table lists, per mortar (= fine face), the
@@ -202,7 +202,15 @@ int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
  * size_b}: Spectral::MortarSize of the fine face inside the coarse face per face
  * dimension (first remaining dimension first; 0 Full, 1 LowerHalf, 2 UpperHalf),
  * i.e. dg::mortar_size(coarse, fine, dimension, orientation)
- * (NumericalAlgorithms/DiscontinuousGalerkin/MortarHelpers.cpp:51-77).
+ * (NumericalAlgorithms/DiscontinuousGalerkin/MortarHelpers.cpp:51-77), given in
+ * the COARSE element's logical frame.  Blocks that are not aligned
+ * (OrientationMap::is_aligned() false): the fine direction is whichever face of
+ * the fine element touches the coarse face, and the entry is written
+ * direction | (perm << 3) with the face permutation bits of
+ * dgrhs_set_neighbor_orientations, taking a mortar point (a, b) in the coarse
+ * element's face frame to the fine element's face point it coincides with
+ * (the orient_variables_on_slice applied to exchanged mortar data,
+ * ComputeTimeDerivative.hpp:712-721).  Aligned blocks: perm = 0.
  * Semantics: InternalMortarDataImpl.hpp:230-320 (package on the face, then
  * dg::project_to_mortar, MortarHelpers.hpp:74-98) and ApplyBoundaryCorrections.hpp:
  * 797-1045 (dg_boundary_terms on the mortar, dg::project_from_mortar,

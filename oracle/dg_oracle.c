@@ -1056,8 +1056,13 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
   }
   /* non-conforming mortars (serial: several mortars add to one coarse face) */
   for (int m = 0; m < n_mortars; ++m) {
+    /* row[3] = fine direction | (perm << 3): perm takes a mortar point (a, b) in the
+     * coarse element's face frame to the fine element's face point, with the bits of
+     * nbr_face (orient_variables_on_slice of the received mortar data,
+     * ApplyBoundaryCorrections.hpp:236-262 / OrientationMapHelpers.cpp:25-120) */
     const int ec = mortars[6 * m], dc = mortars[6 * m + 1], ef = mortars[6 * m + 2],
-              df = mortars[6 * m + 3], sa = mortars[6 * m + 4], sb = mortars[6 * m + 5];
+              df = mortars[6 * m + 3] & 7, permF = mortars[6 * m + 3] >> 3,
+              sa = mortars[6 * m + 4], sb = mortars[6 * m + 5];
     const double* Pa = P + (size_t)sa * N * N;
     const double* Pb = P + (size_t)sb * N * N;
     const double* Ra = R + (size_t)sa * N * N;
@@ -1089,18 +1094,22 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
     for (int b = 0; b < N; ++b)
       for (int a = 0; a < N; ++a) {
         const int q = a + N * b;
+        int fa = (permF & 1) ? b : a, fb = (permF & 1) ? a : b;
+        if (permF & 2) fa = N - 1 - fa;
+        if (permF & 4) fb = N - 1 - fb;
+        const int qF = fa + N * fb;
         double pc[134], pf[134], corr[50];
         for (int c = 0; c < PK; ++c) {
           pc[c] = pkCm[(size_t)c * f + q];
-          pf[c] = pkF[(size_t)c * f + q];
+          pf[c] = pkF[(size_t)c * f + qF];
         }
         /* the fine element: its face is the mortar */
         if (system == 0)
           sw_boundary_terms_point(pf, pc, corr);
         else
           gh_boundary_terms_point(pf, pc, corr);
-        const int p = face_index(N, df, a, b);
-        const double lift = -0.5 * (double)(N * (N - 1)) * magF[q];
+        const int p = face_index(N, df, fa, fb);
+        const double lift = -0.5 * (double)(N * (N - 1)) * magF[qF];
         for (int c = 0; c < C; ++c) dtF[(size_t)c * n + p] += corr[c] * lift;
         /* the coarse element's correction on the mortar */
         if (system == 0)

@@ -328,6 +328,10 @@ struct dgrhs_ctx {
   int n_send = 0;  // faces packed for other ranks (0: no exchange needed)
   bool aligned_table_ok = true;
   cudaStream_t stream = nullptr;
+  // side stream for the few-CTA, latency-bound Bjorhus kernel: it runs next to the
+  // face kernel (disjoint corr slots) and joins before the volume kernel
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   double *u = nullptr, *invjac = nullptr, *coords = nullptr, *stat = nullptr;
   double *corr = nullptr, *D = nullptr, *gH = nullptr, *gdH = nullptr;
   double *halo_send = nullptr, *halo_recv = nullptr;
@@ -422,20 +426,15 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   }
   dg::FaceArgs a{c->u,    c->invjac, c->stat, c->nbr, c->nbr_face, c->halo_recv,
                  c->corr, c->nelem,  n_int,   pass,   c->violations};
-  const long long total = (long long)c->nelem * 6 * N * N;
-  const int blocks = (int)((total + 127) / 128);
-  if (c->system == DGRHS_SYSTEM_GH)
-    dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
-  else
-    dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
-  ++g_launches;
-  CU(cudaGetLastError());
   // Bjorhus faces and non-conforming mortars need no halo data: all of them are
   // evaluated once per right-hand side, with whichever pass comes first, so that
   // their corrections are in place before ANY volume kernel of this evaluation
   const bool aux_now = c->aux_faces_eval != c->rhs_evals;
   c->aux_faces_eval = c->rhs_evals;
-  if (c->n_bjorhus_faces > 0 && aux_now) {
+  const bool bjorhus_now = c->n_bjorhus_faces > 0 && aux_now;
+  if (bjorhus_now) {
+    CU(cudaEventRecord(c->aux_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
     dg::BjorhusArgs b{c->u, c->invjac, c->stat, c->gH, c->gdH, c->coords, c->D, c->corr,
                       c->bjorhus_faces, {}};
     int gauge_mode = 1;
@@ -446,10 +445,20 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
       gauge_mode = 2;
     }
     constexpr int bT = (N * N + 31) / 32 * 32;
-    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->stream>>>(b, gauge_mode);
+    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->aux_stream>>>(b, gauge_mode);
     ++g_launches;
     CU(cudaGetLastError());
+    CU(cudaEventRecord(c->aux_join, c->aux_stream));
   }
+  const long long total = (long long)c->nelem * 6 * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  else
+    dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  ++g_launches;
+  CU(cudaGetLastError());
+  if (bjorhus_now) CU(cudaStreamWaitEvent(c->stream, c->aux_join, 0));
   // mortar groups whose sides are all local run with the first pass; groups with a
   // remote side need the halo: with the boundary pass (or the single full pass)
   auto launch_mortars = [&](int first, int count) -> int {
@@ -753,6 +762,13 @@ int dgrhs_create(dgrhs_ctx** out, int system, int N, int nelem, int nghost, int 
   c->f = N * N;
   c->npad = dg::padded_points(N);
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming));
+  }
   if (dev_alloc(&c->u, c->state_len())) return 1;
   if (dev_alloc(&c->invjac, (size_t)nelem * 9 * c->npad)) return 1;
   if (dev_alloc(&c->stat, (size_t)nelem * c->S * c->npad)) return 1;
@@ -792,6 +808,9 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   if (c->mortar_P) cudaFree(c->mortar_P);
   if (c->mortar_R) cudaFree(c->mortar_R);
   if (c->halo_map) cudaFree(c->halo_map);
+  if (c->aux_join) cudaEventDestroy(c->aux_join);
+  if (c->aux_fork) cudaEventDestroy(c->aux_fork);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -1078,16 +1097,17 @@ int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
   std::pair<long long, int> last_key{-1, -1};
   for (int k = 0; k < n_mortars; ++k) {
     const int32_t* m = mortars + 6 * (size_t)order[k];
-    const int ec = m[0], dc = m[1], ef = m[2], df = m[3], sa = m[4], sb = m[5];
-    if (ec >= c->nelem || ef >= c->nelem || ec == -1 || ef == -1 || dc < 0 || dc > 5 || df < 0 ||
-        df > 5)
-      return fail("mortar %d: element or direction out of range", order[k]);
+    // m[3] = fine direction | perm << 3 (perm: the face permutation of non-aligned
+    // blocks, bits as in dgrhs_set_neighbor_orientations, taking a mortar point in the
+    // coarse element's face frame to the fine element's face point)
+    const int ec = m[0], dc = m[1], ef = m[2], df = m[3] & 7, permf = m[3] >> 3, sa = m[4],
+              sb = m[5];
+    if (ec >= c->nelem || ef >= c->nelem || ec == -1 || ef == -1 || dc < 0 || dc > 5 ||
+        m[3] < 0 || df > 5 || permf > 7)
+      return fail("mortar %d: element, direction or face permutation out of range", order[k]);
     if ((is_ghost(ec) && -(ec + 2) >= c->nghost) || (is_ghost(ef) && -(ef + 2) >= c->nghost))
       return fail("mortar %d: ghost face index out of range", order[k]);
     if (is_ghost(ec) && is_ghost(ef)) return fail("mortar %d: both sides are remote", order[k]);
-    if (df != (dc ^ 1))
-      return fail("mortar %d: only aligned blocks are supported (fine direction must be the "
-                  "opposite of the coarse direction)", order[k]);
     if (sa < 0 || sa > 2 || sb < 0 || sb > 2 || (sa == 0 && sb == 0))
       return fail("mortar %d: bad mortar size (%d, %d)", order[k], sa, sb);
     if ((ec >= 0 && c->nbr_host[(size_t)ec * 6 + dc] != DGRHS_NEIGHBOR_HANGING) ||
@@ -1106,7 +1126,7 @@ int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
       if (ec >= 0) ++local_coarse;
     }
     ++faces[faces.size() - 1];
-    table.insert(table.end(), {ef, df, sa, sb});
+    table.insert(table.end(), {ef, m[3], sa, sb});
   }
   // every hanging face must be covered, or the volume kernel would add stale data
   size_t hanging = 0;

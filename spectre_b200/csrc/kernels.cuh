@@ -1111,7 +1111,7 @@ struct MortarArgs {
   const double* stat;
   double* corr;
   const int32_t* faces;    // [n_coarse_faces][4] = coarse element, direction, first mortar, count
-  const int32_t* mortars;  // [n_mortars][4]      = fine element, direction, size_a, size_b
+  const int32_t* mortars;  // [n_mortars][4]      = fine element, direction | perm << 3, size_a, size_b
   const double* P;         // [3][N*N] parent->child, row-major [child point][parent point]
   const double* R;         // [3][N*N] child->parent, row-major [parent point][child point]
   // a side that lives on another rank: element = -(slot + 2), its face arrived in
@@ -1262,14 +1262,20 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
 #pragma unroll 1
   for (int mi = 0; mi < nm; ++mi) {
     const int32_t* mt = a.mortars + 4 * (m0 + mi);
-    const int ef = mt[0], df = mt[1], sa = mt[2], sb = mt[3];
+    // mt[1] = fine direction | perm << 3: perm takes this thread's mortar point, given
+    // in the coarse element's face frame, to the fine element's face point (blocks that
+    // are not aligned; orient_variables_on_slice of the exchanged mortar data)
+    const int ef = mt[0], df = mt[1] & 7, sa = mt[2], sb = mt[3];
+    int fa = qa, fb = qb;
+    if (mt[1] >> 3) orient_face_point<N>(mt[1] >> 3, qa, qb, fa, fb);
+    const int qF = active ? fa + N * fb : 0;
     const double* Pa = sP[sa];
     const double* Pb = sP[sb];
     const double* Ra = sR[sa];
     const double* Rb = sR[sb];
     GhFaceSide sFn;
-    const int pF = active ? face_point<N>(df, qa, qb) : 0;
-    if (active) make_side(ef, df, pF, tid, sFn);
+    const int pF = active ? face_point<N>(df, fa, fb) : 0;
+    if (active) make_side(ef, df, pF, qF, sFn);
     const double liftF = active ? -0.5 * (double)(N * (N - 1)) * sFn.mag : 0.0;
     double spC[4] = {0.0, 0.0, 0.0, 0.0};  // coarse characteristic speeds on the mortar
 #pragma unroll 1
@@ -1313,10 +1319,10 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
           }
         }
         double pkF[13];
-        package(sFn, ef, pF, tid, s, pkF);
+        package(sFn, ef, pF, qF, s, pkF);
         pair_boundary_terms_packaged(sFn.speed, pkF, spC, pkC, cF);
         pair_boundary_terms_packaged(spC, pkC, sFn.speed, pkF, cC);
-        double* cf = corr_ptr(ef >= 0 ? ef : 0, s, df) + tid;
+        double* cf = corr_ptr(ef >= 0 ? ef : 0, s, df) + qF;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
           if (ef >= 0) cf[(size_t)c * f] = cF[c] * liftF;   // (a remote fine side: its rank does it)

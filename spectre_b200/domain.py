@@ -440,9 +440,17 @@ class SphericalShell:
         if not isinstance(refinement[0], (tuple, list)):
             refinement = [tuple(refinement)] * self.n_layers
         assert len(refinement) == self.n_layers
-        self.refinement = [(int(r[0]), int(r[1])) for r in refinement]
-        self.layer_levels = [(r[0], r[0], r[1]) for r in self.refinement]
-        self.levels = self.layer_levels[0]
+        # a layer entry is (angular, radial) for its six wedges or six such pairs, one
+        # per wedge (the creator's per-block InitialRefinement)
+        self.refinement = [
+            [(int(w[0]), int(w[1])) for w in r] if isinstance(r[0], (tuple, list))
+            else (int(r[0]), int(r[1])) for r in refinement]
+        self.block_levels = []
+        for r in self.refinement:
+            per_wedge = r if isinstance(r, list) else [r] * 6
+            assert len(per_wedge) == 6
+            self.block_levels += [(w[0], w[0], w[1]) for w in per_wedge]
+        self.levels = self.block_levels[0]
         self.ne = tuple(2 ** r for r in self.levels)
         if isinstance(radial_distribution, str):
             radial_distribution = [radial_distribution] * self.n_layers
@@ -451,20 +459,23 @@ class SphericalShell:
         self.n_blocks = 6 * self.n_layers
         self.cells = []  # element index -> (block, cell)
         radial_offset, off = [], 0
-        for layer, lev in enumerate(self.layer_levels):
-            nx, ny, nz = (2 ** l for l in lev)
-            cells = [(ix, iy, iz) for iz in range(nz) for iy in range(ny) for ix in range(nx)]
-            cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], lev))
+        for layer in range(self.n_layers):
             for w in range(6):
+                lev = self.block_levels[6 * layer + w]
+                nx, ny, nz = (2 ** l for l in lev)
+                cells = [(ix, iy, iz) for iz in range(nz) for iy in range(ny) for ix in range(nx)]
+                cells.sort(key=lambda c: z_curve_index(c[0], c[1], c[2], lev))
                 self.cells += [(6 * layer + w, c) for c in cells]
             radial_offset.append(off)
-            off += nz
+            off += max(2 ** self.block_levels[6 * layer + w][2] for w in range(6))
         if order == "radial":
+            if any(len(set(self.block_levels[6 * l:6 * l + 6])) > 1 for l in range(self.n_layers)):
+                raise ValueError('order="radial" needs the same refinement in the six wedges '
+                                 'of a layer')
             self.cells.sort(key=lambda bc: (
                 radial_offset[bc[0] // 6] + bc[1][2], bc[0] % 6,
                 z_curve_index(bc[1][0], bc[1][1], 0,
-                              (self.layer_levels[bc[0] // 6][0], self.layer_levels[bc[0] // 6][1],
-                               0))))
+                              (self.block_levels[bc[0]][0], self.block_levels[bc[0]][1], 0))))
         elif order != "block":
             raise ValueError(order)
         self.order = order
@@ -473,7 +484,7 @@ class SphericalShell:
         self._conn = None
 
     def element_ids(self):
-        return [element_id(b, c, self.layer_levels[b // 6]) for b, c in self.cells]
+        return [element_id(b, c, self.block_levels[b]) for b, c in self.cells]
 
     def map_points(self, e, xi):
         """Element-logical points xi [3, m] of element e -> (x [3, m], jacobian
@@ -482,7 +493,7 @@ class SphericalShell:
         layer, wedge = b // 6, b % 6
         blk, half = [], []
         for d in range(3):
-            h = 2.0 / 2 ** self.layer_levels[layer][d]
+            h = 2.0 / 2 ** self.block_levels[b][d]
             blk.append(-1.0 + h * cell[d] + 0.5 * h * (np.asarray(xi[d], float) + 1.0))
             half.append(0.5 * h)
         x, jac = wedge_map(blk[0], blk[1], blk[2], self.radii[layer], self.radii[layer + 1],
@@ -550,10 +561,14 @@ class SphericalShell:
 
 def find_hanging_faces(dom, nbr, tol=1e-9):
     """2:1 non-conforming faces of a multi-block domain with `map_points`: a face
-    without a conforming partner whose four logical quarter centres are the
-    centres of four (likewise unmatched) faces is a coarse face with four
-    mortars.  Marks both sides HANGING in nbr (in place) and returns the mortar
-    table.  Only aligned faces are supported (as between the layers of a shell)."""
+    without a conforming partner whose logical halves / quarters (split in one or
+    both face dimensions) have the centres of (likewise unmatched) faces at their
+    centres is a coarse face with two or four mortars.  Marks both sides HANGING in
+    nbr (in place) and returns the mortar table: rows (coarse element, direction,
+    fine element, fine direction | perm << 3, size_a, size_b) with the mortar sizes
+    in the coarse element's frame and perm the face permutation that takes a mortar
+    point (a, b) of the coarse frame to the fine element's face point (0 between
+    aligned blocks; bits as in connectivity_from_geometry)."""
     from scipy.spatial import cKDTree
     free = [(e, d) for e in range(nbr.shape[0]) for d in range(6) if nbr[e, d] == -1]
     if not free:
@@ -565,33 +580,55 @@ def find_hanging_faces(dom, nbr, tol=1e-9):
         fd = [x for x in range(3) if x != d // 2]
         xi[fd[0]], xi[fd[1]] = a, b
         return xi
-    centers = np.array([dom.map_points(e, face_point(d, 0.0, 0.0)[:, None])[0][:, 0]
-                        for e, d in free])
+
+    def phys(e, d, a, b):
+        return dom.map_points(e, face_point(d, a, b)[:, None])[0][:, 0]
+
+    def close(p, q):
+        return np.linalg.norm(p - q) <= tol * max(np.linalg.norm(q), 1e-300)
+    centers = np.array([phys(e, d, 0.0, 0.0) for e, d in free])
     tree = cKDTree(centers)
+    # sub-face = (size code, centre, half width) per face dimension
+    pieces = {0: [(MORTAR_FULL, 0.0, 1.0)],
+              1: [(MORTAR_LOWER_HALF, -0.5, 0.5), (MORTAR_UPPER_HALF, 0.5, 0.5)]}
     mortars = []
     for k, (e, d) in enumerate(free):
-        found = []
-        for kb in range(2):
-            for ka in range(2):
-                q = dom.map_points(e, face_point(d, ka - 0.5, kb - 0.5)[:, None])[0][:, 0]
-                dist, j = tree.query(q)
-                if dist < tol * max(np.linalg.norm(q), 1e-300) and j != k:
-                    found.append((ka, kb, free[j]))
-        if len(found) != 4:
-            continue
-        for ka, kb, (e2, d2) in found:
-            if d2 != d ^ 1:
-                raise NotImplementedError("non-aligned non-conforming faces")
-            # the fine face must run parallel to the coarse one (no permutation)
-            fine = dom.map_points(e2, face_point(d2, -1.0, 1.0)[:, None])[0][:, 0]
-            mine = dom.map_points(e, face_point(d, ka - 1.0, kb * 1.0)[:, None])[0][:, 0]
-            if np.linalg.norm(fine - mine) > tol * max(np.linalg.norm(mine), 1e-300):
-                raise NotImplementedError("non-aligned non-conforming faces")
-            mortars.append((e, d, e2, d2, MORTAR_UPPER_HALF if ka else MORTAR_LOWER_HALF,
-                            MORTAR_UPPER_HALF if kb else MORTAR_LOWER_HALF))
+        for split in ((1, 1), (1, 0), (0, 1)):
+            found = []
+            for sa, ca, ha in pieces[split[0]]:
+                for sb, cb, hb in pieces[split[1]]:
+                    q = phys(e, d, ca, cb)
+                    dist, j = tree.query(q)
+                    if dist < tol * max(np.linalg.norm(q), 1e-300) and j != k:
+                        found.append((sa, ca, ha, sb, cb, hb, free[j]))
+            if len(found) != len(pieces[split[0]]) * len(pieces[split[1]]):
+                continue
+            for sa, ca, ha, sb, cb, hb, (e2, d2) in found:
+                # three corners of the mortar, in the coarse frame, tell the eight face
+                # permutations apart
+                code = None
+                for perm in range(8):
+                    ok = True
+                    for a, b in ((-1.0, -1.0), (1.0, -1.0), (-1.0, 1.0)):
+                        fa, fb = (b, a) if perm & 1 else (a, b)
+                        if perm & 2:
+                            fa = -fa
+                        if perm & 4:
+                            fb = -fb
+                        if not close(phys(e2, d2, fa, fb), phys(e, d, ca + ha * a, cb + hb * b)):
+                            ok = False
+                            break
+                    if ok:
+                        code = perm
+                        break
+                if code is None:
+                    raise ValueError(f"faces ({e},{d}) and ({e2},{d2}) share a centre but not "
+                                     "their corners")
+                mortars.append((e, d, e2, d2 | (code << 3), sa, sb))
+            break
     for e, d, e2, d2, _, _ in mortars:
         nbr[e, d] = HANGING
-        nbr[e2, d2] = HANGING
+        nbr[e2, d2 & 7] = HANGING
     return np.asarray(mortars, dtype=np.int32).reshape(-1, 6)
 
 
@@ -674,7 +711,10 @@ class Partition:
                     recv.append((int(owner[v]), v, int(neighbor_direction[g, d]), int(g), d,
                                  None))
         # faces of remote mortar partners: one ghost slot per mortar
+        # (fine direction may carry the face permutation of non-aligned blocks in its
+        # upper bits: every face travels in its owner's frame, so only the row keeps it)
         for m, (ec, dc, ef, df, _, _) in enumerate(mortars.tolist()):
+            df &= 7
             if owner[ec] == rank and owner[ef] != rank:
                 recv.append((int(owner[ef]), ef, df, ec, dc, m))
             elif owner[ef] == rank and owner[ec] != rank:
@@ -720,6 +760,7 @@ class Partition:
                     # the receiver is the neighbour, seeing us through its direction
                     send.append((int(owner[v]), int(g), d, v, int(neighbor_direction[g, d]), le))
         for ec, dc, ef, df, _, _ in mortars.tolist():
+            df &= 7
             if owner[ec] == rank and owner[ef] != rank:
                 send.append((int(owner[ef]), ec, dc, ef, df, g2l[ec]))
             elif owner[ef] == rank and owner[ec] != rank:

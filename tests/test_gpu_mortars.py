@@ -130,8 +130,12 @@ def test_mortar_table_validation():
     with pytest.raises(lib.DgrhsError, match="marked hanging but the mortar table covers"):
         ctx.set_mortars(mt[:-1])
     bad = mt.copy()
-    bad[0, 3] = bad[0, 1]
-    with pytest.raises(lib.DgrhsError, match="only aligned blocks"):
+    bad[0, 3] = bad[0, 1]   # that face of the fine element is not a hanging one
+    with pytest.raises(lib.DgrhsError, match="must be marked DGRHS_NEIGHBOR_HANGING"):
+        ctx.set_mortars(bad)
+    bad = mt.copy()
+    bad[0, 3] |= 8 << 3
+    with pytest.raises(lib.DgrhsError, match="face permutation out of range"):
         ctx.set_mortars(bad)
     bad = mt.copy()
     bad[0, 4] = 3
@@ -193,7 +197,8 @@ def _emulate_ranks(problem, world, steps, dt):
     return out
 
 
-@pytest.mark.parametrize("kind,world", [("brick", 2), ("brick", 3), ("shell", 2)])
+@pytest.mark.parametrize("kind,world", [("brick", 2), ("brick", 3), ("shell", 2),
+                                        ("wedge-refined shell", 2)])
 def test_mortars_across_ranks_match_single_context(kind, world):
     """Mortars whose two sides live on different ranks: the remote side's face
     arrives in a ghost slot, the coarse side's rank projects and sums, the fine
@@ -205,10 +210,15 @@ def test_mortars_across_ranks_match_single_context(kind, world):
                                  {(0, 0, 0): (True, True, True), (1, 1, 0): (True, False, True)})
         problem = evolution.Problem(lib.SYSTEM_GH, rb, lambda x, t: analytic.gauge_wave(x, t),
                                     (1.0, -1.0, 1.0))
-    else:
+    elif kind == "shell":
         N, dt = 3, 1e-4
         problem = evolution.gh_kerr_schild_shell_problem([(2, 0), (1, 1)], N,
                                                          radial_partitioning=(2.1,))
+    else:   # mortars between blocks that are not aligned (rows with face permutations)
+        N, dt = 3, 1e-4
+        problem = evolution.gh_kerr_schild_shell_problem(
+            [[(1, 1), (0, 0), (0, 0), (0, 0), (1, 0), (0, 0)]], N)
+        assert ((np.asarray(problem.mortars)[:, 3] >> 3) != 0).any()
     assert len(problem.mortars) > 0
     single = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 2, dt)
     single.take_steps(2)
@@ -219,3 +229,47 @@ def test_mortars_across_ranks_match_single_context(kind, world):
     assert any((p.local_mortars[:, [0, 2]] < 0).any() for p in parts)   # really across ranks
     got = _emulate_ranks(problem, world, 2, dt)
     np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("system,N", [("sw", 4), ("gh", 4), ("gh", 7)])
+def test_mortars_between_non_aligned_blocks(system, N):
+    """Every element of an h-refined Brick in its own rotated / reflected logical frame
+    (tests/rotation.py): oriented conforming faces, oriented mortar rows and mortar
+    sizes in the rotated coarse frames.  The GPU runs the rotated mesh, the oracle the
+    aligned one (tests/test_mortars_cpu.py shows the oracle agrees with itself)."""
+    from tests import rotation
+    rng = np.random.default_rng(N)
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N,
+                             {(0, 0, 0): (1, 1, 1), (1, 1, 0): (1, 0, 1), (0, 1, 1): (0, 0, 1)})
+    x, nb, mt = rb.coords(), rb.neighbors(), rb.mortars()
+    E = rb.n_elements
+    J = rb.inverse_jacobian() + 0.05 * rng.uniform(-1, 1, (E, 9, N ** 3))
+    if system == "gh":
+        sysid, sid, blocks = lib.SYSTEM_GH, 1, GH_BLOCKS
+        u = analytic.gauge_wave(x, 0.1) + 1e-2 * rng.uniform(-1, 1, (E, 50, N ** 3))
+        stat = rng.uniform(-1, 1, (E, 3, N ** 3))
+    else:
+        sysid, sid, blocks = lib.SYSTEM_SCALAR_WAVE, 0, SW_BLOCKS
+        u = analytic.plane_wave(x, 0.3) + 0.1 * rng.uniform(-1, 1, (E, 5, N ** 3))
+        stat = rng.uniform(0, 1, (E, 1, N ** 3))
+    all48 = rotation.signed_perms()
+    frames = [all48[k] for k in rng.choice(48, E)]
+    u_r, J_r, s_r, nbr_r, nd_r, perm_r, pm, mt_r = rotation.rotate_problem(
+        N, u, J, stat, nb, frames, mortars=mt)
+    assert ((mt_r[:, 3] >> 3) != 0).any()
+    ctx = lib.Context(sysid, N, E)
+    ctx.set_geometry(J_r, None, nbr_r)
+    ctx.set_neighbor_orientations(nd_r, perm_r)
+    ctx.set_mortars(mt_r)
+    ctx.set_static_fields(s_r)
+    ctx.set_state(u_r)
+    ctx.compute_time_derivative(0.0)
+    got_r = ctx.get_time_derivative()
+    got = np.empty_like(got_r)
+    for e in range(E):
+        got[e] = got_r[e][:, pm[e]]
+    ref = orc.dg_rhs(sid, N, u, J, stat, nb, mortars=mt)
+    assert _relerr(got, ref, blocks) < TOL
+    ref_r = orc.dg_rhs(sid, N, u_r, J_r, s_r, nbr_r, nbr_dir=nd_r, face_perm=perm_r, mortars=mt_r)
+    assert _relerr(got_r, ref_r, blocks) < TOL
+    ctx.close()

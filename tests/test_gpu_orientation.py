@@ -4,104 +4,17 @@ same physics.  The GPU runs the rotated mesh (with neighbour directions and
 face permutations), the oracle runs the aligned mesh; results are compared after
 mapping back.  Reference: orient_variables_on_slice, Domain/Structure/
 OrientationMapHelpers.cpp:25-120; call site ComputeTimeDerivative.hpp:712-721."""
-import itertools
-
 import numpy as np
 import pytest
 
 from oracle import oracle as orc
 from spectre_b200 import analytic, domain, lib
+from tests import rotation
 
 pytestmark = pytest.mark.gpu
 
 
-def _signed_perms():
-    out = []
-    for perm in itertools.permutations(range(3)):
-        for signs in itertools.product((1, -1), repeat=3):
-            out.append((perm, signs))
-    return out  # the 48 orientations of a cube
-
-
-def _point_map(N, perm, signs):
-    """new_index[p_old] for the frame xi'_a = signs[a] * xi_{perm[a]}."""
-    p = np.arange(N ** 3)
-    old = (p % N, (p // N) % N, p // (N * N))
-    new = []
-    for a in range(3):
-        i = old[perm[a]]
-        new.append(i if signs[a] > 0 else N - 1 - i)
-    return new[0] + N * (new[1] + N * new[2])
-
-
-def _dir_map(perm, signs):
-    """old direction -> new direction."""
-    m = {}
-    for a in range(3):
-        for side in range(2):
-            old_d = 2 * perm[a] + (side if signs[a] > 0 else 1 - side)
-            m[old_d] = 2 * a + side
-    return m
-
-
-def _face_points(N, d):
-    dim, fixed = d // 2, (N - 1 if d % 2 else 0)
-    q = np.arange(N * N)
-    a, b = q % N, q // N
-    return [fixed + N * (a + N * b), a + N * (fixed + N * b), a + N * (b + N * fixed)][dim]
-
-
-def _rotate_problem(N, u, J, stat, nbr, frames):
-    ne = u.shape[0]
-    pm = [_point_map(N, *frames[e]) for e in range(ne)]
-    dm = [_dir_map(*frames[e]) for e in range(ne)]
-    u_r, J_r, s_r = np.empty_like(u), np.empty_like(J), np.empty_like(stat)
-    nbr_r = np.full_like(nbr, -1)
-    nd_r = np.zeros_like(nbr)
-    perm_r = np.zeros_like(nbr)
-    for e in range(ne):
-        perm, signs = frames[e]
-        u_r[e][:, pm[e]] = u[e]
-        s_r[e][:, pm[e]] = stat[e]
-        for a in range(3):
-            for i in range(3):
-                J_r[e][a + 3 * i][pm[e]] = signs[a] * J[e][perm[a] + 3 * i]
-    inv_pm = [np.argsort(m) for m in pm]  # new index -> old index
-    for e in range(ne):
-        for d_old in range(6):
-            nb = nbr[e, d_old]
-            d_new = dm[e][d_old]
-            nd_new = dm[nb][d_old ^ 1]
-            nbr_r[e, d_new] = nb
-            nd_r[e, d_new] = nd_new
-            # match face points: our new face ordering -> old volume index -> the
-            # aligned neighbour point (same tangential indices on the opposite face)
-            fp_new = _face_points(N, d_new)
-            p_old = inv_pm[e][fp_new]
-            i = [p_old % N, (p_old // N) % N, p_old // (N * N)]
-            dim = d_old // 2
-            i[dim] = np.where(i[dim] == 0, N - 1, 0)
-            p_nb_old = i[0] + N * (i[1] + N * i[2])
-            p_nb_new = pm[nb][p_nb_old]
-            fp_nb = _face_points(N, nd_new)
-            pos = {int(v): k for k, v in enumerate(fp_nb)}
-            target = np.array([pos[int(v)] for v in p_nb_new])
-            q = np.arange(N * N)
-            qa, qb = q % N, q // N
-            found = None
-            for code in range(8):
-                na = np.where(code & 1, qb, qa)
-                nbb = np.where(code & 1, qa, qb)
-                if code & 2:
-                    na = N - 1 - na
-                if code & 4:
-                    nbb = N - 1 - nbb
-                if np.array_equal(na + N * nbb, target):
-                    found = code
-                    break
-            assert found is not None
-            perm_r[e, d_new] = found
-    return u_r, J_r, s_r, nbr_r, nd_r, perm_r, pm
+_signed_perms, _rotate_problem = rotation.signed_perms, rotation.rotate_problem
 
 
 @pytest.mark.parametrize("system", ["gh", "sw"])

@@ -284,3 +284,42 @@ def test_shell_with_layers_of_different_refinement():
     ev.take_steps(3)
     assert np.max(np.abs(ctx.get_state() - u0)) < 1e-4
     ctx.close()
+
+
+@pytest.mark.parametrize("fine", [{0: (1, 1)}, {5: (1, 1), 4: (1, 0)}, {2: (1, 0), 3: (1, 0)}])
+def test_shell_with_wedges_of_different_refinement(fine):
+    """Sphere with per-block InitialRefinement: refined wedges next to coarse ones, so
+    the wedge-to-wedge interfaces are 2:1 mortars (four quarters, or two halves when
+    only the angular level differs) between blocks that are NOT aligned -- mortar rows
+    with face permutations, next to oriented conforming faces and ghost boundaries."""
+    N = 5
+    ref = [fine.get(w, (0, 0)) for w in range(6)]
+    problem = evolution.gh_kerr_schild_shell_problem([ref], N)
+    mt = np.asarray(problem.mortars)
+    assert len(mt) > 0 and ((mt[:, 3] >> 3) != 0).any()
+    ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, 1e-4)
+    ctx, part = ev.ctx, ev.part
+    ids = part.global_ids
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    u0 = problem.u0(ids, 0.0)
+    u = u0 + 1e-3 * np.random.default_rng(4).uniform(-1, 1, u0.shape)
+    ctx.set_state(u)
+    ctx.compute_time_derivative(0.0)
+    got = ctx.get_time_derivative()
+    H, dH = _gauge_fields(N, x, J, u0)
+    ext = ev.boundary_ghost_data(problem, 0.0)[:, :50]
+    sf = np.concatenate([stat, H, dH], axis=1)
+    kw = dict(gauge_params=orc.GAUGE_GIVEN, ext_u=ext, nbr_dir=part.local_neighbor_direction,
+              face_perm=part.local_face_permutation)
+    ref_rhs = orc.dg_rhs(1, N, u, J, sf, part.local_neighbors, mortars=ev.local_mortars, **kw)
+    assert _relerr(got, ref_rhs, GH_BLOCKS) < TOL
+    stripped = np.array(ev.local_mortars).copy()
+    stripped[:, 3] &= 7
+    wrong = orc.dg_rhs(1, N, u, J, sf, part.local_neighbors, mortars=stripped, **kw)
+    assert _relerr(wrong, ref_rhs, GH_BLOCKS) > 1e-3
+    # the static solution stays put
+    ctx.set_state(u0)
+    ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 3, 0.0, 1e-4)
+    ev.take_steps(3)
+    assert np.max(np.abs(ctx.get_state() - u0)) < 1e-3
+    ctx.close()

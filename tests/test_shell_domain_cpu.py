@@ -217,3 +217,81 @@ def test_shell_layers_of_different_refinement_have_mortars():
         interp = np.einsum("Bb,Aa,xba->xBA", P[sb], P[sa], fc)
         assert np.max(np.abs(interp - ff)) < 2e-2
         np.testing.assert_allclose(np.linalg.norm(ff, axis=0), 2.3, rtol=1e-13)
+
+
+@pytest.mark.parametrize("fine_wedge_refinement,n_split", [((1, 1), 4), ((1, 0), 2)])
+def test_shell_wedges_of_different_refinement_have_oriented_mortars(fine_wedge_refinement,
+                                                                    n_split):
+    """Per-block InitialRefinement: one wedge finer than its four neighbours -> the
+    wedge-to-wedge interfaces are 2:1 mortars between blocks that are NOT aligned
+    (four quarter mortars, or two half mortars when only the angular level
+    differs).  The mortar rows carry the fine face's permutation; the coarse face's
+    coordinates, interpolated to the mortar in the coarse frame, land on the fine
+    face's points after that permutation."""
+    N = 5
+    perms_seen, not_opposite = set(), False
+    for fine_wedge in range(6):
+        ref = [(0, 0)] * 6
+        ref[fine_wedge] = fine_wedge_refinement
+        sh = domain.SphericalShell(1.9, 2.9, [ref], N)
+        nb, mt = sh.neighbors(), sh.mortars()
+        n_fine = 4 * 2 ** fine_wedge_refinement[1]
+        assert sh.n_elements == 5 + n_fine
+        assert len(mt) == 4 * n_split and (nb == domain.HANGING).sum() == 4 + 4 * n_split
+        not_opposite |= bool(((mt[:, 3] & 7) != (mt[:, 1] ^ 1)).any())
+        perms_seen |= set((mt[:, 3] >> 3).tolist())
+        x = sh.coords()
+        P = [np.eye(N), orc.projection_matrix_parent_to_child(N, N, 1),
+             orc.projection_matrix_parent_to_child(N, N, 2)]
+        q = np.arange(N * N)
+        a, b = q % N, q // N
+        for ec, dc, ef, dfp, sa, sb in mt:
+            df, perm = dfp & 7, dfp >> 3
+            assert sh.cells[ec][0] != fine_wedge and sh.cells[ef][0] == fine_wedge
+            fc = x[ec][:, domain._face_point_indices(N, dc)].reshape(3, N, N)   # [xyz, b, a]
+            interp = np.einsum("Bb,Aa,xba->xBA", P[sb], P[sa], fc).reshape(3, N * N)
+            fa, fb = (b, a) if perm & 1 else (a, b)
+            if perm & 2:
+                fa = N - 1 - fa
+            if perm & 4:
+                fb = N - 1 - fb
+            ff = x[ef][:, domain._face_point_indices(N, df)][:, fa + N * fb]
+            assert np.max(np.abs(interp - ff)) < 2e-3
+            # a wrong permutation would be off by the size of the face
+            wrong = x[ef][:, domain._face_point_indices(N, df)][:, (N - 1 - fa) + N * fb]
+            assert np.max(np.abs(interp - wrong)) > 0.1
+    # rotated and reflected interfaces occur (the +z wedge alone is aligned with its neighbours)
+    assert len(perms_seen) >= 2 and not_opposite, perms_seen
+
+
+def test_oracle_static_black_hole_on_wedge_refined_shell():
+    """Exact Kerr-Schild data on a shell with one wedge refined: with the oriented
+    mortar rows the right-hand side stays at the truncation level of the coarse
+    wedges; with the permutation bits stripped the mortar data are mismatched and
+    it is tens of times larger."""
+    from spectre_b200 import evolution
+    N = 5
+
+    def max_rhs(refinement, strip=False):
+        pr = evolution.gh_kerr_schild_shell_problem(refinement, N)
+        ids = np.arange(pr.brick.n_elements)
+        x, J, stat = pr.coords(ids), pr.inverse_jacobian(ids), pr.static(ids)
+        u0 = pr.u0(ids, 0.0)
+        H = np.zeros((len(x), 4, N ** 3))
+        dH = np.zeros((len(x), 16, N ** 3))
+        for e in range(len(x)):
+            H[e], dH[e] = orc.analytic_christoffel_gauge(N, u0[e], J[e])
+        nd, perm = pr.orientations
+        mt = np.array(pr.mortars).copy()
+        if strip:
+            mt[:, 3] &= 7
+        r = orc.dg_rhs(1, N, u0, J, np.concatenate([stat, H, dH], axis=1), pr.neighbors,
+                       gauge_params=orc.GAUGE_GIVEN, nbr_dir=nd, face_perm=perm,
+                       mortars=mt if len(mt) else None)
+        return float(np.max(np.abs(r)))
+    coarse = max_rhs((0, 0))
+    for w in (0, 5):
+        ref = [(0, 0)] * 6
+        ref[w] = (1, 1)
+        assert max_rhs([ref]) < 1.5 * coarse
+        assert max_rhs([ref], strip=True) > 20 * coarse
