@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -330,6 +331,9 @@ struct dgrhs_ctx {
   cudaStream_t stream = nullptr;
   // side stream for the few-CTA, latency-bound Bjorhus kernel: it runs next to the
   // face kernel (disjoint corr slots) and joins before the volume kernel
+  // set by launch_faces when the face kernel is the last thing queued: the volume
+  // kernel that follows may be launched as its programmatic dependent
+  bool pdl_volume = false;
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   double *u = nullptr, *invjac = nullptr, *coords = nullptr, *stat = nullptr;
@@ -398,6 +402,30 @@ int download(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
                        (size_t)c->nelem * ncomp, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// DGRHS_NO_PDL=1 in the environment turns programmatic dependent launch off
+static const bool g_pdl = [] {
+  const char* v = std::getenv("DGRHS_NO_PDL");
+  return !(v && v[0] == '1');
+}();
+
+// kernel<<<blocks, threads, smem, stream>>>(args), optionally as the programmatic
+// dependent of the kernel queued before it
+template <typename Kernel, typename Args>
+cudaError_t launch_dependent(Kernel k, int blocks, int threads, size_t smem, cudaStream_t stream,
+                             bool pdl, const Args& args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, args);
 }
 
 #ifndef DG_FOR_EACH_N  // (a build with -D'DG_FOR_EACH_N(X)=X(12)' compiles faster for experiments)
@@ -484,6 +512,7 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   if (pass != 1 &&
       launch_mortars(c->n_mortar_faces_local, c->n_mortar_faces - c->n_mortar_faces_local))
     return 1;
+  c->pdl_volume = g_pdl && !bjorhus_now && c->n_mortar_faces == 0;
   return 0;
 }
 
@@ -527,6 +556,8 @@ int launch_gh_split(dgrhs_ctx* c, const dg::GhVolArgs& a, int eb, int ee) {
 template <int N>
 int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
                   const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
+  const bool pdl = c->pdl_volume;
+  c->pdl_volume = false;
   if (ee <= eb) return 0;
   const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
   if (c->system == DGRHS_SYSTEM_GH) {
@@ -553,18 +584,18 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
     if (c->gauge == DGRHS_GAUGE_HARMONIC) {
       auto k = dg::gh_volume_kernel<N, 0>;
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
     } else if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
       if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
       const double* p = c->gauge_params;
       a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
       auto k = dg::gh_volume_kernel<N, 2>;
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
     } else {
       auto k = dg::gh_volume_kernel<N, 1>;
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
     }
   } else {
     dg::SwVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr, c->D, eb,
@@ -596,6 +627,7 @@ int launch_pack(dgrhs_ctx* c) {
 
 int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume_only,
               bool do_gauge, const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
+  c->pdl_volume = false;
   switch (c->N) {
 #define X(NN)                                                        \
   case NN:                                                           \

@@ -75,6 +75,20 @@ __device__ __forceinline__ int face_point(int d, int qa, int qb) {
 }
 
 // --------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol): the face kernel lets the volume
+// kernel that follows it in the stream start while its last wave drains; the
+// volume kernel runs its prologue (which needs nothing the face kernel writes)
+// and waits only before it fetches the face corrections.  Without the launch
+// attribute both instructions do nothing.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_for_primary() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// --------------------------------------------------------------------------
 // mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP)
 // --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -345,27 +359,39 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
 
   // stage the 5 components of pair s = (g_s, Pi_s, Phi_0s, Phi_1s, Phi_2s)
   // and the pair's face corrections
-  auto issue = [&](int s, int stage) {
+  // (which = 1: the state tiles, 2: the corrections, 3: both; the barrier expects
+  // the bytes of both from the first call on)
+  auto issue = [&](int s, int stage, int which) {
     double* t = ring + stage * SD;
-    mbar_expect_tx(&bars[stage], (5 * npad + (with_corr ? 30 * f : 0)) * 8);
-    tma_bulk_g2s(t, ue + (size_t)s * npad, npad * 8, &bars[stage]);
-    tma_bulk_g2s(t + npad, ue + (size_t)(10 + s) * npad, npad * 8, &bars[stage]);
-    tma_bulk_g2s(t + 2 * npad, ue + (size_t)(20 + 3 * s) * npad, 3 * npad * 8,
-                 &bars[stage]);
-    if (with_corr) tma_bulk_g2s(t + 5 * npad, ce + (size_t)s * 30 * f, 30 * f * 8, &bars[stage]);
+    if (which & 1) {
+      mbar_expect_tx(&bars[stage], (5 * npad + (with_corr ? 30 * f : 0)) * 8);
+      tma_bulk_g2s(t, ue + (size_t)s * npad, npad * 8, &bars[stage]);
+      tma_bulk_g2s(t + npad, ue + (size_t)(10 + s) * npad, npad * 8, &bars[stage]);
+      tma_bulk_g2s(t + 2 * npad, ue + (size_t)(20 + 3 * s) * npad, 3 * npad * 8,
+                   &bars[stage]);
+    }
+    if ((which & 2) && with_corr)
+      tma_bulk_g2s(t + 5 * npad, ce + (size_t)s * 30 * f, 30 * f * 8, &bars[stage]);
   };
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < NS; ++st) mbar_init(&bars[st], 1);
     mbar_fence_init();
 #pragma unroll
-    for (int st = 0; st < NS; ++st) issue(st, st);
+    for (int st = 0; st < NS; ++st) issue(st, st, 1);
   }
   for (int idx = tid; idx < N * N; idx += T) sD[idx] = a.D[idx];
 
   // ---- prologue: everything that needs all 50 components at the point ----
   GhContext ctx;
   if (active) gh_point_prologue<N, kGauge>(a, e, pt, sQ + tid, T, ctx);
+  // the face corrections are the only input the preceding face kernel writes: under
+  // programmatic dependent launch everything above overlaps that kernel's last wave
+  if (tid == 0 && with_corr) {
+    pdl_wait_for_primary();
+#pragma unroll
+    for (int st = 0; st < NS; ++st) issue(st, st, 2);
+  }
   __syncthreads();  // sD visible, barrier init visible to all waiters
 
   const int i = pt % N, j = (pt / N) % N, k = pt / (N * N);
@@ -435,7 +461,7 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
       }
     }
     __syncthreads();  // every reader is done with this stage
-    if (tid == 0 && s + NS < 10) issue(s + NS, stage);
+    if (tid == 0 && s + NS < 10) issue(s + NS, stage, 3);
   }
 }
 
@@ -882,6 +908,7 @@ __device__ __forceinline__ bool face_task(const FaceArgs& a, int e, int d, int n
 template <int N>
 __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   constexpr int npad = Cfg<N>::npad, f = N * N, HC = 55;
+  pdl_launch_dependents();  // the volume kernel may start its prologue (see pdl_wait_for_primary)
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)a.nelem * 6 * f;
   if (idx >= total) return;
