@@ -177,16 +177,26 @@ def test_shell_partition_and_oriented_halo_exchange_gloo(world, order):
     mp.spawn(_shell_worker, args=(world, _free_port(), order, None), nprocs=world, join=True)
 
 
-def _mortar_worker(rank, world, port, results):
+def _mortar_worker(rank, world, port, kind, results):
     """Mortars whose sides live on different ranks: the remote side's face arrives
-    in the ghost slot named in Partition.local_mortars."""
+    in the ghost slot named in Partition.local_mortars.  kind "shell": a shell with
+    two wedges refined, i.e. mortar rows between blocks that are not aligned (fine
+    direction | perm << 3) next to oriented conforming faces."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N,
-                             {(0, 0, 0): (True, True, True), (1, 1, 0): (True, False, True)})
-    nb, mt = rb.neighbors(), rb.mortars()
-    part = domain.Partition(nb, world, rank, mortars=mt)
+    if kind == "brick":
+        rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N,
+                                 {(0, 0, 0): (True, True, True), (1, 1, 0): (True, False, True)})
+        nb, mt = rb.neighbors(), rb.mortars()
+        part = domain.Partition(nb, world, rank, mortars=mt)
+    else:
+        rb = domain.SphericalShell(1.9, 2.9, [[(1, 1), (0, 0), (0, 0), (0, 0), (1, 0), (0, 0)]], N)
+        nb, mt = rb.neighbors(), rb.mortars()
+        assert ((mt[:, 3] >> 3) != 0).any()
+        nd, perm = rb.neighbor_orientations()
+        part = domain.Partition(nb, world, rank, neighbor_direction=nd, face_permutation=perm,
+                                mortars=mt)
     send = torch.zeros(max(part.n_ghost, 1) * HC * F, dtype=torch.float64)
     sv = send.numpy().reshape(-1, HC, F)
     for slot, (le, d) in enumerate(part.send_map):
@@ -204,7 +214,7 @@ def _mortar_worker(rank, world, port, results):
     remote = 0
     for (ec, dc, ef, df, sa, sb), (lc, dc2, lf, df2, sa2, sb2) in zip(mine, part.local_mortars):
         assert (dc, df, sa, sb) == (dc2, df2, sa2, sb2)
-        for g, d, l in ((ec, dc, lc), (ef, df, lf)):
+        for g, d, l in ((ec, dc, lc), (ef, df & 7, lf)):
             if l >= 0:
                 assert part.global_ids[l] == g
                 assert part.local_neighbors[l, d] == domain.HANGING
@@ -221,6 +231,6 @@ def _mortar_worker(rank, world, port, results):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_mortars_across_ranks_gloo(world):
-    mp.spawn(_mortar_worker, args=(world, _free_port(), None), nprocs=world, join=True)
+@pytest.mark.parametrize("world,kind", [(2, "brick"), (3, "brick"), (2, "shell")])
+def test_mortars_across_ranks_gloo(world, kind):
+    mp.spawn(_mortar_worker, args=(world, _free_port(), kind, None), nprocs=world, join=True)
