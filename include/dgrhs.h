@@ -384,6 +384,14 @@ int dgrhs_adams_bashforth_coefficients(int order, const double* history_times,
                                        double step_start, double step_end,
                                        double* coefficients);
 
+/* TimeStepper::order(), number_of_substeps(), number_of_past_steps(),
+ * stable_step() (Time/TimeSteppers/TimeStepper.hpp:47-246; AdamsBashforth.cpp:60-95,
+ * Rk3HesthavenSsp.cpp:21-26, Rk3Owren.cpp:8-15, Rk3Kennedy.cpp:8-10,
+ * ClassicalRungeKutta4.cpp:10-22, DormandPrince5.cpp:8-19).  `order` is read for
+ * AdamsBashforth only; any output pointer may be NULL.  Host-only. */
+int dgrhs_stepper_properties(int stepper, int order, int* order_out, int* number_of_substeps,
+                             int* number_of_past_steps, double* stable_step);
+
 #ifdef __cplusplus
 }
 #endif

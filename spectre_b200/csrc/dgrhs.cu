@@ -1780,6 +1780,74 @@ int dgrhs_adams_bashforth_coefficients(int order, const double* times, double st
   return 0;
 }
 
+// TimeStepper::order / number_of_substeps / number_of_past_steps / stable_step.
+// The stable step (largest dt for which y' = -2 y / ... decays, normalised so that
+// forward Euler gives 1) is computed from first principles: Adams-Bashforth from the
+// root zeta = -1 of the characteristic polynomial, Runge-Kutta from the first
+// crossing |R(-2 x)| = 1 of the stability polynomial R(z) = 1 + sum_k z^k b.A^(k-1).1
+// of the tableau -- the CPU tests compare with the constants of the reference
+// (AdamsBashforth.cpp:72-90, Rk3HesthavenSsp.cpp:23-26, Rk3Owren.cpp:15,
+// Rk3Kennedy.cpp:10, ClassicalRungeKutta4.cpp:22, DormandPrince5.cpp:19).
+int dgrhs_stepper_properties(int stepper, int order, int* order_out, int* number_of_substeps,
+                             int* number_of_past_steps, double* stable_step) {
+  int ord = 0, substeps = 0, past = 0;
+  double stable = 0.0;
+  if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
+    if (order < 1 || order > 6) return fail("AdamsBashforth order must be in [1, 6]");
+    ord = order;
+    substeps = 1;
+    past = order - 1;
+    double alternating = 0.0;  // sum_j beta_j (-1)^j, j = 0 the newest derivative
+    for (int j = 0; j < order; ++j)
+      alternating += kAbConst[order][order - 1 - j] * ((j & 1) ? -1.0 : 1.0);
+    stable = 1.0 / alternating;
+  } else {
+    std::vector<double> poly{1.0};  // R(z) coefficients, lowest degree first
+    if (stepper == DGRHS_STEPPER_RK3_HESTHAVEN) {
+      ord = 3;
+      substeps = 3;
+      poly = {1.0, 1.0, 0.5, 1.0 / 6.0};  // any 3-stage method of order 3
+    } else if (is_tableau_stepper(stepper)) {
+      const ButcherTableau& tab = butcher_tableau(stepper);
+      const int s = (int)tab.result_coefficients.size();
+      substeps = s;
+      ord = stepper == DGRHS_STEPPER_RK4 ? 4 : stepper == DGRHS_STEPPER_DORMAND_PRINCE5 ? 5 : 3;
+      std::vector<double> v(s, 1.0);  // A^(k-1) 1
+      for (int k = 1; k <= s; ++k) {
+        double bk = 0.0;
+        for (int i = 0; i < s; ++i) bk += tab.result_coefficients[i] * v[i];
+        poly.push_back(bk);
+        std::vector<double> w(s, 0.0);
+        for (int i = 1; i < s; ++i)
+          for (int j = 0; j < i; ++j) w[i] += tab.substep_coefficients[i - 1][j] * v[j];
+        v = w;
+      }
+    } else {
+      return fail("unknown time stepper %d", stepper);
+    }
+    auto growth = [&](double x) {
+      double r = 0.0;
+      for (size_t k = poly.size(); k-- > 0;) r = r * (-2.0 * x) + poly[k];
+      return std::abs(r) - 1.0;
+    };
+    double lo = 1e-6, hi = lo;
+    while (growth(hi) < 0.0 && hi < 100.0) {
+      lo = hi;
+      hi += 1e-3;
+    }
+    for (int it = 0; it < 200; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      (growth(mid) < 0.0 ? lo : hi) = mid;
+    }
+    stable = 0.5 * (lo + hi);
+  }
+  if (order_out) *order_out = ord;
+  if (number_of_substeps) *number_of_substeps = substeps;
+  if (number_of_past_steps) *number_of_past_steps = past;
+  if (stable_step) *stable_step = stable;
+  return 0;
+}
+
 int dgrhs_partial_derivatives(int N, int C, const double* u, const double* invjac,
                               double* du) {
   if (N < 2 || N > 12) return fail("n_points_1d must be in [2, 12]");

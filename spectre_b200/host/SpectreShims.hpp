@@ -526,6 +526,53 @@ inline std::vector<double> coefficients(const std::vector<double>& history_times
   return c;
 }
 }  // namespace adams_coefficients
+
+// The property queries of TimeStepper (TimeStepper.hpp:47-246) for the steppers the
+// path runs; stepping itself happens inside the batched context (DgEvolution below,
+// set_time_stepper(stepper.id(), stepper.order(), ...)).
+class TimeStepper {
+ public:
+  virtual ~TimeStepper() = default;
+  virtual int id() const = 0;
+  size_t order() const { return static_cast<size_t>(props().order); }
+  uint64_t number_of_substeps() const { return static_cast<uint64_t>(props().substeps); }
+  size_t number_of_past_steps() const { return static_cast<size_t>(props().past_steps); }
+  double stable_step() const { return props().stable_step; }
+
+ protected:
+  struct Props {
+    int order, substeps, past_steps;
+    double stable_step;
+  };
+  virtual size_t requested_order() const { return 0; }
+  Props props() const {
+    Props p{};
+    check(dgrhs_stepper_properties(id(), static_cast<int>(requested_order()), &p.order, &p.substeps,
+                                   &p.past_steps, &p.stable_step));
+    return p;
+  }
+};
+class AdamsBashforth : public TimeStepper {
+ public:
+  static constexpr size_t maximum_order = 6;  // of this path (the reference allows 8)
+  explicit AdamsBashforth(size_t order) : order_(order) { (void)props(); }  // throws on a bad order
+  int id() const override { return DGRHS_STEPPER_ADAMS_BASHFORTH; }
+
+ private:
+  size_t requested_order() const override { return order_; }
+  size_t order_;
+};
+#define SPECTRE_B200_RK_STEPPER(NAME, ID)              \
+  class NAME : public TimeStepper {                    \
+   public:                                             \
+    int id() const override { return ID; }             \
+  }
+SPECTRE_B200_RK_STEPPER(Rk3HesthavenSsp, DGRHS_STEPPER_RK3_HESTHAVEN);
+SPECTRE_B200_RK_STEPPER(Rk3Owren, DGRHS_STEPPER_RK3_OWREN);
+SPECTRE_B200_RK_STEPPER(Rk3Kennedy, DGRHS_STEPPER_RK3_KENNEDY);
+SPECTRE_B200_RK_STEPPER(ClassicalRungeKutta4, DGRHS_STEPPER_RK4);
+SPECTRE_B200_RK_STEPPER(DormandPrince5, DGRHS_STEPPER_DORMAND_PRINCE5);
+#undef SPECTRE_B200_RK_STEPPER
 }  // namespace TimeSteppers
 
 // ---- batched evolution: the replacement of DgElementArray + step_actions ------------
@@ -545,6 +592,9 @@ class DgEvolution {
   void get_variables(double* u) { check(dgrhs_get_state(ctx_, u)); }
   void set_time_stepper(int stepper, int order, double t0, double dt) {
     check(dgrhs_set_stepper(ctx_, stepper, order, t0, dt));
+  }
+  void set_time_stepper(const TimeSteppers::TimeStepper& stepper, double t0, double dt) {
+    set_time_stepper(stepper.id(), static_cast<int>(stepper.order()), t0, dt);
   }
   void take_steps(int n) { check(dgrhs_take_steps(ctx_, n)); }
   double time() const { return dgrhs_time(ctx_); }

@@ -24,7 +24,7 @@ EXPORTS = [
     "dgrhs_set_geometry", "dgrhs_set_neighbor_orientations", "dgrhs_set_static_fields", "dgrhs_set_gauge",
     "dgrhs_set_gauge_fields", "dgrhs_set_gauge_analytic_christoffel",
     "dgrhs_set_boundary_ghost_data", "dgrhs_set_state", "dgrhs_get_state",
-    "dgrhs_set_state_async", "dgrhs_get_state_async",
+    "dgrhs_set_state_async", "dgrhs_get_state_async", "dgrhs_stepper_properties",
     "dgrhs_get_time_derivative", "dgrhs_compute_time_derivative", "dgrhs_set_interior_count",
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
@@ -47,6 +47,16 @@ _lib = None
 HANGING = -2 ** 31   # DGRHS_NEIGHBOR_HANGING
 BJORHUS = -2 ** 31 + 1   # DGRHS_NEIGHBOR_BJORHUS (Type ConstraintPreserving)
 BJORHUS_PHYSICAL = -2 ** 31 + 2   # DGRHS_NEIGHBOR_BJORHUS_PHYSICAL
+
+
+def stepper_properties(stepper, order=0):
+    """(order, number_of_substeps, number_of_past_steps, stable_step) of a time stepper
+    (TimeStepper.hpp:47-246); host-only."""
+    o, s, p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    st = ctypes.c_double()
+    _check(load().dgrhs_stepper_properties(int(stepper), int(order), ctypes.byref(o),
+                                           ctypes.byref(s), ctypes.byref(p), ctypes.byref(st)))
+    return o.value, s.value, p.value, st.value
 
 
 def projection_matrix(N, child_to_parent, size):

@@ -78,3 +78,62 @@ def test_exponential_filter_matrix(N):
         np.testing.assert_allclose(F @ x ** p, x ** p, atol=1e-11)
     top = np.polynomial.legendre.legval(x, [0] * (N - 1) + [1])
     assert np.max(np.abs(F @ top)) < 1e-14
+
+
+# TimeStepper::order / number_of_substeps / number_of_past_steps / stable_step of the
+# reference: AdamsBashforth.cpp:60-95 (stable steps 1, 1/2, 3/11, 3/20, 45/551, 5/114
+# follow from its alternating coefficient sum), Rk3HesthavenSsp.cpp:21-26,
+# Rk3Owren.cpp:8-15, Rk3Kennedy.cpp:8-10, ClassicalRungeKutta4.cpp:10-22,
+# DormandPrince5.cpp:8-19
+_RK3_STABLE = 0.5 * (1.0 + np.cbrt(4.0 + np.sqrt(17.0)) - 1.0 / np.cbrt(4.0 + np.sqrt(17.0)))
+STEPPER_PROPERTIES = {
+    "AdamsBashforth1": (lib.STEPPER_ADAMS_BASHFORTH, 1, (1, 1, 0, 1.0)),
+    "AdamsBashforth2": (lib.STEPPER_ADAMS_BASHFORTH, 2, (2, 1, 1, 1.0 / 2.0)),
+    "AdamsBashforth3": (lib.STEPPER_ADAMS_BASHFORTH, 3, (3, 1, 2, 3.0 / 11.0)),
+    "AdamsBashforth4": (lib.STEPPER_ADAMS_BASHFORTH, 4, (4, 1, 3, 3.0 / 20.0)),
+    "AdamsBashforth5": (lib.STEPPER_ADAMS_BASHFORTH, 5, (5, 1, 4, 45.0 / 551.0)),
+    "AdamsBashforth6": (lib.STEPPER_ADAMS_BASHFORTH, 6, (6, 1, 5, 5.0 / 114.0)),
+    "Rk3HesthavenSsp": (lib.STEPPER_RK3_HESTHAVEN, 0, (3, 3, 0, _RK3_STABLE)),
+    "Rk3Owren": (lib.STEPPER_RK3_OWREN, 0, (3, 3, 0, 1.2563726633091645)),
+    "Rk3Kennedy": (lib.STEPPER_RK3_KENNEDY, 0, (3, 4, 0, 1.832102281377816)),
+    "ClassicalRungeKutta4": (lib.STEPPER_RK4, 0, (4, 4, 0, 1.3926467817026411)),
+    "DormandPrince5": (lib.STEPPER_DORMAND_PRINCE5, 0, (5, 6, 0, 1.6532839463174733)),
+}
+
+
+def test_stepper_properties_match_reference_constants():
+    """The library derives the stable step from the stability polynomial of its own
+    tableaus / the Adams-Bashforth characteristic polynomial; the reference states
+    the numbers.  Agreement pins the tableaus' stability polynomials too."""
+    for name, (stepper, order, want) in STEPPER_PROPERTIES.items():
+        got = lib.stepper_properties(stepper, order)
+        assert got[:3] == want[:3], name
+        assert abs(got[3] - want[3]) < 1e-13 * want[3], (name, got[3], want[3])
+        # the oracle's tableaus have the same number of substeps
+        if name in orc.RK_TABLEAUS:
+            assert len(orc.RK_TABLEAUS[name][2]) == want[1]
+    with pytest.raises(lib.DgrhsError, match="order must be in"):
+        lib.stepper_properties(lib.STEPPER_ADAMS_BASHFORTH, 7)
+    with pytest.raises(lib.DgrhsError, match="unknown time stepper"):
+        lib.stepper_properties(17)
+
+
+def test_cpp_time_stepper_shims_host_only():
+    """TimeSteppers::AdamsBashforth / Rk3HesthavenSsp / ... of SpectreShims.hpp: the
+    property queries need no GPU."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_build", "stepper_properties")
+    src = os.path.join(ROOT, "tests", "helpers", "stepper_properties.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-o", exe, src, "-L",
+                           os.path.join(ROOT, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(ROOT, "spectre_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = {ln.split()[0]: ln.split()[1:] for ln in out.stdout.strip().splitlines()}
+    assert rows.pop("bad_order_throws") == ["1"]
+    assert set(rows) == set(STEPPER_PROPERTIES)
+    for name, (_, _, want) in STEPPER_PROPERTIES.items():
+        o, s, p, st = rows[name]
+        assert (int(o), int(s), int(p)) == want[:3]
+        assert abs(float(st) - want[3]) < 1e-13 * want[3]
