@@ -238,6 +238,15 @@ int dgrhs_set_mortars(dgrhs_ctx* ctx, int n_mortars, const int32_t* mortars);
  * for Legendre-Gauss-Lobatto meshes with n_points_1d points on both sides,
  * row-major [target point][source point]. */
 int dgrhs_projection_matrix(int n_points_1d, int child_to_parent, int size, double* matrix);
+/* The same for meshes with different numbers of points (p-refinement:
+ * Spectral::projection_matrix_parent_to_child(parent_mesh, child_mesh, size) /
+ * projection_matrix_child_to_parent(parent_mesh, child_mesh, size), Projection.cpp:
+ * 57-362; the child (mortar) mesh is the finer one, 2 <= n_parent <= n_child <= 12):
+ * parent -> child [n_child][n_parent], child -> parent [n_parent][n_child],
+ * row-major [target point][source point].  Host-only; the batched path itself
+ * runs one N per context (no p-mortars yet). */
+int dgrhs_projection_matrix_meshes(int n_parent, int n_child, int child_to_parent, int size,
+                                   double* matrix);
 /* gh::BoundaryConditions::DemandOutgoingCharSpeeds on every external face
  * without a ghost state (neighbor -1), GeneralizedHarmonic/BoundaryConditions/
  * DemandOutgoingCharSpeeds.cpp:37-76 (applied by BoundaryConditionsImpl.hpp:

@@ -999,6 +999,80 @@ void invert(std::vector<double> A, int N, std::vector<double>& inv) {
   }
 }
 
+// size: 0 Full, 1 LowerHalf, 2 UpperHalf; Np points on the parent (element face) mesh,
+// Nc >= Np on the child (mortar) mesh.  Parent -> child [Nc][Np]: barycentric
+// interpolation to the child's points mapped into the parent interval.  Child ->
+// parent [Np][Nc]: the L2 projection, parent mode k = (2k+1)/2 * integral over the
+// child's interval of (child function) * P_k, integrated exactly by Gauss-Lobatto
+// quadrature with enough points for degree (Nc - 1) + (Np - 1).
+void projection_matrix_meshes(int Np, int Nc, bool child_to_parent, int size,
+                              std::vector<double>& M) {
+  M.assign((size_t)Np * Nc, 0.0);
+  if (size == 0 && Np == Nc) {
+    for (int i = 0; i < Np; ++i) M[(size_t)i * Np + i] = 1.0;
+    return;
+  }
+  std::vector<double> xp, wp, xc, wc;
+  lgl(Np, xp, wp);
+  lgl(Nc, xc, wc);
+  // a child coordinate x sits at scale * x + shift in the parent interval
+  const double scale = size == 0 ? 1.0 : 0.5;
+  const double shift = size == 0 ? 0.0 : (size == 2 ? 0.5 : -0.5);
+  if (!child_to_parent) {
+    std::vector<double> bw(Np, 1.0);
+    for (int j = 1; j < Np; ++j)
+      for (int k = 0; k < j; ++k) {
+        bw[k] *= xp[k] - xp[j];
+        bw[j] *= xp[j] - xp[k];
+      }
+    for (int j = 0; j < Np; ++j) bw[j] = 1.0 / bw[j];
+    for (int k = 0; k < Nc; ++k) {
+      const double t = scale * xc[k] + shift;
+      int match = -1;
+      for (int j = 0; j < Np; ++j)
+        if (std::abs(t - xp[j]) < 1e-14) match = j;
+      if (match >= 0) {
+        M[(size_t)k * Np + match] = 1.0;
+        continue;
+      }
+      double sum = 0.0;
+      for (int j = 0; j < Np; ++j) {
+        M[(size_t)k * Np + j] = bw[j] / (t - xp[j]);
+        sum += M[(size_t)k * Np + j];
+      }
+      for (int j = 0; j < Np; ++j) M[(size_t)k * Np + j] /= sum;
+    }
+    return;
+  }
+  // nodal (child) -> modal (child) -> modal (parent) -> nodal (parent)
+  std::vector<double> Vc((size_t)Nc * Nc), Vci, xq, wq;
+  for (int i = 0; i < Nc; ++i)
+    for (int j = 0; j < Nc; ++j) Vc[(size_t)i * Nc + j] = legendre_p(j, xc[i]);
+  invert(Vc, Nc, Vci);
+  const int nq = (Np + Nc + 1) / 2 + 1;
+  lgl(nq, xq, wq);
+  std::vector<double> T((size_t)Np * Nc, 0.0);  // parent mode k from child mode j
+  for (int k = 0; k < Np; ++k)
+    for (int j = 0; j < Nc; ++j) {
+      double sum = 0.0;
+      for (int q = 0; q < nq; ++q)
+        sum += scale * wq[q] * legendre_p(j, xq[q]) * legendre_p(k, scale * xq[q] + shift);
+      T[(size_t)k * Nc + j] = 0.5 * (2.0 * k + 1.0) * sum;
+    }
+  std::vector<double> TV((size_t)Np * Nc, 0.0);  // parent modes from child nodal values
+  for (int k = 0; k < Np; ++k)
+    for (int j = 0; j < Nc; ++j) {
+      double sum = 0.0;
+      for (int m = 0; m < Nc; ++m) sum += T[(size_t)k * Nc + m] * Vci[(size_t)m * Nc + j];
+      TV[(size_t)k * Nc + j] = sum;
+    }
+  for (int i = 0; i < Np; ++i)
+    for (int j = 0; j < Nc; ++j) {
+      double sum = 0.0;
+      for (int k = 0; k < Np; ++k) sum += legendre_p(k, xp[i]) * TV[(size_t)k * Nc + j];
+      M[(size_t)i * Nc + j] = sum;
+    }
+}
 // size: 0 Full, 1 LowerHalf, 2 UpperHalf; same number of points on both meshes
 void projection_matrix(int N, bool child_to_parent, int size, std::vector<double>& M) {
   M.assign((size_t)N * N, 0.0);
@@ -1069,6 +1143,20 @@ int dgrhs_projection_matrix(int N, int child_to_parent, int size, double* matrix
   if (size < 0 || size > 2) return fail("mortar size must be 0 (Full), 1 (LowerHalf) or 2 (UpperHalf)");
   std::vector<double> M;
   projection_matrix(N, child_to_parent != 0, size, M);
+  std::memcpy(matrix, M.data(), M.size() * 8);
+  return 0;
+}
+
+int dgrhs_projection_matrix_meshes(int n_parent, int n_child, int child_to_parent, int size,
+                                   double* matrix) {
+  if (n_parent < 2 || n_child > 12 || n_child < n_parent)
+    return fail("need 2 <= n_parent <= n_child <= 12 (the mortar mesh is the finer one)");
+  if (size < 0 || size > 2) return fail("mortar size must be 0 (Full), 1 (LowerHalf) or 2 (UpperHalf)");
+  std::vector<double> M;
+  if (n_parent == n_child)  // the matrices the mortar kernel uses
+    projection_matrix(n_parent, child_to_parent != 0, size, M);
+  else
+    projection_matrix_meshes(n_parent, n_child, child_to_parent != 0, size, M);
   std::memcpy(matrix, M.data(), M.size() * 8);
   return 0;
 }

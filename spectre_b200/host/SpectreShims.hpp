@@ -202,7 +202,7 @@ inline std::vector<double> quadrature_weights(size_t n) {
 }
 // Spectral::ChildSize / MortarSize and the projection matrices of non-conforming
 // mortars (NumericalAlgorithms/Spectral/Projection.hpp:28-36, Projection.cpp:57-362),
-// equal extents on both meshes; row-major [target point][source point]
+// row-major [target point][source point]
 enum class ChildSize : uint8_t { Uninitialized = 0, Full = 1, UpperHalf = 2, LowerHalf = 3 };
 using MortarSize = ChildSize;
 inline int abi_size_code(ChildSize s) {
@@ -221,6 +221,20 @@ inline std::vector<double> projection_matrix_parent_to_child(size_t n, ChildSize
 inline std::vector<double> projection_matrix_child_to_parent(size_t n, ChildSize size) {
   std::vector<double> M(n * n);
   check(dgrhs_projection_matrix(static_cast<int>(n), 1, abi_size_code(size), M.data()));
+  return M;
+}
+// meshes with different extents (the reference's (parent_mesh, child_mesh, size)
+// arguments reduced to the two point counts): [n_child][n_parent] and [n_parent][n_child]
+inline std::vector<double> projection_matrix_parent_to_child(size_t n_parent, size_t n_child, ChildSize size) {
+  std::vector<double> M(n_parent * n_child);
+  check(dgrhs_projection_matrix_meshes(static_cast<int>(n_parent), static_cast<int>(n_child), 0,
+                                       abi_size_code(size), M.data()));
+  return M;
+}
+inline std::vector<double> projection_matrix_child_to_parent(size_t n_parent, size_t n_child, ChildSize size) {
+  std::vector<double> M(n_parent * n_child);
+  check(dgrhs_projection_matrix_meshes(static_cast<int>(n_parent), static_cast<int>(n_child), 1,
+                                       abi_size_code(size), M.data()));
   return M;
 }
 }  // namespace Spectral

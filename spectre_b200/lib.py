@@ -25,6 +25,7 @@ EXPORTS = [
     "dgrhs_set_gauge_fields", "dgrhs_set_gauge_analytic_christoffel",
     "dgrhs_set_boundary_ghost_data", "dgrhs_set_state", "dgrhs_get_state",
     "dgrhs_set_state_async", "dgrhs_get_state_async", "dgrhs_stepper_properties",
+    "dgrhs_projection_matrix_meshes",
     "dgrhs_get_time_derivative", "dgrhs_compute_time_derivative", "dgrhs_set_interior_count",
     "dgrhs_pack_halo", "dgrhs_compute_time_derivative_range", "dgrhs_set_halo_map",
     "dgrhs_halo_send_ptr", "dgrhs_halo_recv_ptr", "dgrhs_halo_comps", "dgrhs_set_stepper",
@@ -64,6 +65,15 @@ def projection_matrix(N, child_to_parent, size):
     1 LowerHalf, 2 UpperHalf (host function, no GPU needed)."""
     M = np.zeros((N, N))
     _check(load().dgrhs_projection_matrix(N, int(child_to_parent), size, _ptr(M)))
+    return M
+
+
+def projection_matrix_meshes(n_parent, n_child, child_to_parent, size):
+    """The same between meshes with different numbers of points (the child / mortar
+    mesh is the finer one): [n_child, n_parent] or, child to parent, [n_parent, n_child]."""
+    M = np.zeros((n_parent, n_child) if child_to_parent else (n_child, n_parent))
+    _check(load().dgrhs_projection_matrix_meshes(n_parent, n_child, int(child_to_parent), size,
+                                                 _ptr(M)))
     return M
 
 

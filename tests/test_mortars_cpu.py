@@ -208,3 +208,33 @@ def test_oracle_mortars_between_non_aligned_blocks(system):
         got[e] = got_r[e][:, pm[e]]
     err = max(np.max(np.abs(got[:, b] - ref[:, b])) / np.max(np.abs(ref[:, b])) for b in blocks)
     assert err < 1e-12, err
+
+
+@pytest.mark.parametrize("n_parent,n_child", [(2, 3), (3, 5), (4, 4), (5, 8), (7, 12), (11, 12)])
+def test_projection_matrices_between_different_meshes(n_parent, n_child):
+    """p-refinement (the mortar mesh has more points than the element face):
+    dgrhs_projection_matrix_meshes (barycentric interpolation; exact quadrature of the
+    L2 projection) against the oracle's restatement of the closed forms of
+    Projection.cpp:57-362, plus the properties Test_Projection.cpp checks."""
+    xp, _ = orc.lgl_points_and_weights(n_parent)
+    xc, _ = orc.lgl_points_and_weights(n_child)
+    total = np.zeros((n_parent, n_parent))
+    for size in (orc.MORTAR_FULL,) + SIZES:
+        P = lib.projection_matrix_meshes(n_parent, n_child, False, size)
+        R = lib.projection_matrix_meshes(n_parent, n_child, True, size)
+        assert P.shape == (n_child, n_parent) and R.shape == (n_parent, n_child)
+        np.testing.assert_allclose(P, orc.projection_matrix_parent_to_child(n_parent, n_child, size),
+                                   atol=1e-13)
+        np.testing.assert_allclose(R, orc.projection_matrix_child_to_parent(n_child, n_parent, size),
+                                   atol=5e-13)
+        t = {orc.MORTAR_FULL: xc, orc.MORTAR_UPPER_HALF: 0.5 * (xc + 1.0),
+             orc.MORTAR_LOWER_HALF: 0.5 * (xc - 1.0)}[size]
+        for k in range(n_parent):      # exact for the parent's polynomials
+            np.testing.assert_allclose(P @ xp ** k, t ** k, atol=1e-13)
+        if size == orc.MORTAR_FULL:    # projecting the interpolant gives the function back
+            np.testing.assert_allclose(R @ P, np.eye(n_parent), atol=1e-12)
+        else:
+            total += R @ P
+    np.testing.assert_allclose(total, np.eye(n_parent), atol=1e-12)
+    with pytest.raises(lib.DgrhsError, match="n_parent <= n_child"):
+        lib.projection_matrix_meshes(n_child + 1, n_child, False, 0)
