@@ -817,6 +817,15 @@ def l2_norm(v):
     return math.sqrt(float(np.sum(v * v)) / npts)
 
 
+def four_index_constraint(d_phi):
+    """C_i.. = eps_ijk d_j Phi_k.. (Constraints.cpp:1070-1100, python twin
+    TestFunctions.py:295-300).  d_phi [3 (j), 3 (k), ...] -> [3, ...]."""
+    eps = np.zeros((3, 3, 3))
+    eps[0, 1, 2] = eps[1, 2, 0] = eps[2, 0, 1] = 1.0
+    eps[0, 2, 1] = eps[2, 1, 0] = eps[1, 0, 2] = -1.0
+    return np.einsum("ijk,jk...->i...", eps, d_phi)
+
+
 def gh_constraint_norms(N, u, invjac, H=None):
     """L2 norms (ObserveNorms.hpp:60-80, Components: Sum) of the GH gauge
     constraint C_a = H_a + Gamma_a (Constraints.cpp:965-1000), the three-index
@@ -825,9 +834,6 @@ def gh_constraint_norms(N, u, invjac, H=None):
     u [nelem, 50, n], invjac [nelem, 9, n]."""
     nelem, _, n = u.shape
     sums = np.zeros(3)
-    eps = np.zeros((3, 3, 3))
-    eps[0, 1, 2] = eps[1, 2, 0] = eps[2, 0, 1] = 1.0
-    eps[0, 2, 1] = eps[2, 1, 0] = eps[1, 0, 2] = -1.0
     for e in range(nelem):
         Hg, _ = analytic_christoffel_gauge(N, u[e], invjac[e])  # = -Gamma_a
         gam = -Hg
@@ -842,7 +848,7 @@ def gh_constraint_norms(N, u, invjac, H=None):
             for j in range(3):
                 for k in range(3):
                     dphi[j, k] = du[3 * (20 + k + 3 * s) + j]
-            c4 = np.einsum("ijk,jk...->i...", eps, dphi)
+            c4 = four_index_constraint(dphi)
             sums[2] += np.sum(c4 * c4)
     return np.sqrt(sums / (nelem * n))
 

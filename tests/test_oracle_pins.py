@@ -366,3 +366,66 @@ def test_bjorhus_physical_vs_reference_numpy(golden_dir):
         np.testing.assert_allclose(cg, z["out_corr_g"][p], rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(cp, z["out_phys_corr_pi"][p], rtol=1e-12, atol=2e-12)
         np.testing.assert_allclose(cph, z["out_phys_corr_phi"][p], rtol=1e-12, atol=2e-12)
+
+
+def _pack_gh(g, pi, phi):
+    """[n,4,4], [n,4,4], [n,3,4,4] -> Variables layout [50, n]."""
+    n = len(g)
+    u = np.zeros((50, n))
+    for a in range(4):
+        for b in range(a, 4):
+            s = orc.sym4(a, b)
+            u[s], u[10 + s] = g[:, a, b], pi[:, a, b]
+            for i in range(3):
+                u[20 + i + 3 * s] = phi[:, i, a, b]
+    return u
+
+
+def test_gauge_wave_gh_variables_vs_reference_numpy(golden_dir):
+    """The analytic GaugeWave solution composed to GH variables (spacetime metric,
+    Pi, Phi as WrappedGr.tpp:100-120 does) against the reference's GaugeWave.py +
+    ComputeSpacetimeQuantities.py + ComputeGhQuantities.py (tests/golden/gen_gr_goldens.py)."""
+    z = np.load(os.path.join(golden_dir, "gr_pointwise.npz"))
+    for k in range(len(z["gw_t"])):
+        x = z["gw_x"][k][:, None]
+        u = orc.gh_vars_from_metric(*orc.gauge_wave_metric(
+            x, float(z["gw_t"][k]), float(z["gw_amplitude"][k]), float(z["gw_wavelength"][k])))
+        want = _pack_gh(z["gw_spacetime_metric"][k:k + 1], z["gw_pi"][k:k + 1], z["gw_phi"][k:k + 1])
+        np.testing.assert_allclose(u, want, rtol=1e-13, atol=1e-14)
+
+
+def test_spacetime_quantities_and_constraints_vs_reference_numpy(golden_dir):
+    """Lapse, shift, inverse spacetime metric, trace of the Christoffel symbols
+    (-H_a of the AnalyticChristoffel gauge), gauge constraint and four-index constraint
+    of random physical GH states against ComputeSpacetimeQuantities.py,
+    ComputeGhQuantities.py::trace_christoffel and GeneralizedHarmonic/TestFunctions.py
+    (gauge_constraint :9-52, four_index_constraint :295-300)."""
+    z = {k[3:]: v for k, v in np.load(os.path.join(golden_dir, "gr_pointwise.npz")).items()
+         if k.startswith("st_")}
+    n = len(z["lapse"])
+    u = _pack_gh(z["spacetime_metric"], z["pi"], z["phi"])
+    geo = orc.gh_geometry(u)
+    np.testing.assert_allclose(geo["lapse"], z["lapse"], rtol=1e-13)
+    np.testing.assert_allclose(geo["shift"], z["shift"].T, rtol=1e-12, atol=1e-14)
+    k = 0
+    for a in range(4):
+        for b in range(a, 4):
+            np.testing.assert_allclose(geo["inv_g"][k], z["inverse_spacetime_metric"][:, a, b],
+                                       rtol=1e-12, atol=1e-13)
+            k += 1
+    # H_a = -Gamma_a; the numerical derivative part needs a mesh: 8 points = one N = 2
+    # element per chunk with an identity Jacobian (only H is compared)
+    assert n % 8 == 0
+    eye = np.zeros((9, 8))
+    eye[0] = eye[4] = eye[8] = 1.0
+    for c in range(n // 8):
+        sl = slice(8 * c, 8 * c + 8)
+        Hg, _ = orc.analytic_christoffel_gauge(2, np.ascontiguousarray(u[:, sl]), eye)
+        np.testing.assert_allclose(-Hg, z["trace_christoffel"][sl].T, rtol=1e-12, atol=1e-12)
+        # gauge constraint C_a = H_a + Gamma_a for the fixture's random H_a
+        np.testing.assert_allclose(z["gauge_function"][sl].T - Hg, z["gauge_constraint"][sl].T,
+                                   rtol=1e-12, atol=1e-12)
+    # four-index constraint C_iab = eps_ijk d_j Phi_kab, the function gh_constraint_norms uses
+    c4 = orc.four_index_constraint(np.moveaxis(z["d_phi"], 0, -1))      # [j, k, a, b, n]
+    np.testing.assert_allclose(np.moveaxis(c4, -1, 0), z["four_index_constraint"],
+                               rtol=1e-13, atol=1e-14)
