@@ -278,10 +278,116 @@ class ElementId {
   }
   uint64_t bits() const { return bits_; }
   size_t block_id() const { return bits_ & 0xFF; }
+  size_t refinement_level(size_t d) const { return (bits_ >> (16 * (d + 1) + 12)) & 0xF; }
+  size_t index(size_t d) const { return (bits_ >> (16 * (d + 1))) & 0xFFF; }
 
  private:
   uint64_t bits_ = 0;
 };
+
+// ---- Direction<3>, SegmentId, OrientationMap<3>, dg::mortar_size ----------------------
+// What a caller needs to turn Element<3>::neighbors() (ids + OrientationMap per direction,
+// Domain/Structure/{Direction,SegmentId,OrientationMap}.hpp) into the tables of
+// dgrhs_set_geometry / dgrhs_set_neighbor_orientations / dgrhs_set_mortars.
+struct Direction3 {
+  size_t dimension = 0;
+  int sign = 1;  // +1 Side::Upper, -1 Side::Lower
+  Direction3 opposite() const { return {dimension, -sign}; }
+  int abi() const { return static_cast<int>(2 * dimension) + (sign > 0 ? 1 : 0); }  // the C-ABI's d
+  static Direction3 from_abi(int d) { return {static_cast<size_t>(d / 2), (d & 1) ? 1 : -1}; }
+  bool operator==(const Direction3& o) const { return dimension == o.dimension && sign == o.sign; }
+};
+struct SegmentId {
+  size_t refinement_level = 0, index = 0;
+  SegmentId id_if_flipped() const { return {refinement_level, (size_t{1} << refinement_level) - 1 - index}; }
+};
+template <size_t Dim>
+class OrientationMap;
+template <>
+class OrientationMap<3> {
+ public:
+  OrientationMap() : mapped_{Direction3{0, 1}, Direction3{1, 1}, Direction3{2, 1}} {}
+  // mapped_directions[d]: where the host block's upper-d direction points in the neighbour's frame
+  explicit OrientationMap(std::array<Direction3, 3> mapped_directions) : mapped_(mapped_directions) {
+    bool seen[3] = {false, false, false};
+    for (const auto& m : mapped_) {
+      if (m.dimension > 2 || seen[m.dimension]) throw std::runtime_error("This OrientationMap fails to map Directions one-to-one.");
+      seen[m.dimension] = true;
+    }
+  }
+  bool is_aligned() const {
+    for (size_t d = 0; d < 3; ++d)
+      if (mapped_[d].dimension != d || mapped_[d].sign < 0) return false;
+    return true;
+  }
+  Direction3 operator()(const Direction3& host) const {
+    return {mapped_[host.dimension].dimension, mapped_[host.dimension].sign * host.sign};
+  }
+  std::array<SegmentId, 3> operator()(const std::array<SegmentId, 3>& host_segments) const {
+    std::array<SegmentId, 3> out{};
+    for (size_t d = 0; d < 3; ++d)
+      out[mapped_[d].dimension] = mapped_[d].sign > 0 ? host_segments[d] : host_segments[d].id_if_flipped();
+    return out;
+  }
+  OrientationMap inverse_map() const {
+    std::array<Direction3, 3> inv{};
+    for (size_t d = 0; d < 3; ++d) inv[mapped_[d].dimension] = {d, mapped_[d].sign};
+    return OrientationMap(inv);
+  }
+
+ private:
+  std::array<Direction3, 3> mapped_;
+};
+
+// The per-face entries of dgrhs_set_neighbor_orientations for the neighbour reached through
+// `direction`: the neighbour's direction that points back, and the permutation of the two
+// face coordinates (bit 0: swapped; bit 1 / bit 2: first / second neighbour face coordinate
+// runs backwards) -- orient_variables_on_slice restricted to the face
+// (OrientationMapHelpers.cpp:25-120).  A mortar row between non-aligned blocks carries
+// neighbor_direction | permutation << 3 with the orientation seen from the coarse element.
+struct FaceOrientation {
+  int neighbor_direction;
+  int permutation;
+};
+inline FaceOrientation face_orientation(const OrientationMap<3>& orientation, const Direction3& direction) {
+  size_t tangential[2], k = 0;
+  for (size_t d = 0; d < 3; ++d)
+    if (d != direction.dimension) tangential[k++] = d;
+  const Direction3 ma = orientation(Direction3{tangential[0], 1});
+  const Direction3 mb = orientation(Direction3{tangential[1], 1});
+  const bool swapped = ma.dimension > mb.dimension;
+  const bool reverse_first = (swapped ? mb.sign : ma.sign) < 0;
+  const bool reverse_second = (swapped ? ma.sign : mb.sign) < 0;
+  return {orientation(direction).opposite().abi(),
+          (swapped ? 1 : 0) | (reverse_first ? 2 : 0) | (reverse_second ? 4 : 0)};
+}
+
+namespace dg {
+// dg::mortar_size (NumericalAlgorithms/DiscontinuousGalerkin/MortarHelpers.cpp:51-77): size of
+// the mortar to `neighbor` inside the face of `self` perpendicular to `dimension`, per face
+// dimension of `self` (the two size entries of a dgrhs_set_mortars row when `self` is the
+// coarse element; Full everywhere when `self` is the fine one)
+inline std::array<Spectral::MortarSize, 2> mortar_size(const ElementId<3>& self, const ElementId<3>& neighbor,
+                                                       size_t dimension, const OrientationMap<3>& orientation) {
+  std::array<SegmentId, 3> theirs{};
+  for (size_t d = 0; d < 3; ++d) theirs[d] = {neighbor.refinement_level(d), neighbor.index(d)};
+  const auto in_my_frame = orientation.inverse_map()(theirs);
+  std::array<Spectral::MortarSize, 2> out{};
+  size_t k = 0;
+  for (size_t d = 0; d < 3; ++d) {
+    if (d == dimension) continue;
+    const long diff = static_cast<long>(in_my_frame[d].refinement_level) - static_cast<long>(self.refinement_level(d));
+    if (diff <= 0) {
+      out[k++] = Spectral::MortarSize::Full;
+    } else if (diff == 1) {
+      out[k++] = in_my_frame[d].index % 2 == 0 ? Spectral::MortarSize::LowerHalf : Spectral::MortarSize::UpperHalf;
+    } else {
+      throw std::runtime_error("neighbours may differ by at most one refinement level (2:1 balance)");
+    }
+  }
+  return out;
+}
+}  // namespace dg
 
 // ---- partial_derivatives ---------------------------------------------------------
 // du[3 c + i] = d_i u_c for a block of n_comps components (Variables layout)

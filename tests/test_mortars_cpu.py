@@ -4,6 +4,7 @@ the library's independent computation), their defining properties as tested by
 tests/Unit/NumericalAlgorithms/Spectral/Test_Projection.cpp, and the oracle's
 mortar path (InternalMortarDataImpl.hpp:230-320, ApplyBoundaryCorrections.hpp:
 797-1045) on an h-refined Brick."""
+import os
 from collections import Counter
 
 import numpy as np
@@ -238,3 +239,77 @@ def test_projection_matrices_between_different_meshes(n_parent, n_child):
     np.testing.assert_allclose(total, np.eye(n_parent), atol=1e-12)
     with pytest.raises(lib.DgrhsError, match="n_parent <= n_child"):
         lib.projection_matrix_meshes(n_child + 1, n_child, False, 0)
+
+
+def test_cpp_orientation_map_and_mortar_size_shims():
+    """OrientationMap<3> -> (neighbour direction, face permutation) and dg::mortar_size of
+    SpectreShims.hpp (what a caller uses to turn Element<3>::neighbors() into the tables
+    of the C-ABI; host-only): on an h-refined Brick whose elements all carry random
+    rotated / reflected frames, the relative OrientationMap of two neighbours is known
+    from their frames; the shim must reproduce the direction / permutation tables found
+    by brute-force point matching and the oriented mortar rows (tests/rotation.py)."""
+    import subprocess
+    from tests import rotation
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "orientation_codes")
+    src = os.path.join(root, "tests", "helpers", "orientation_codes.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-o", exe, src, "-L",
+                           os.path.join(root, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(root, "spectre_b200")])
+    N = 3
+    rng = np.random.default_rng(17)
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N,
+                             {(0, 0, 0): (1, 1, 1), (1, 1, 0): (1, 0, 1), (0, 1, 1): (0, 0, 1)})
+    nb, mt = rb.neighbors(), rb.mortars()
+    E = rb.n_elements
+    all48 = rotation.signed_perms()
+    frames = [all48[k] for k in rng.choice(48, E)]
+    z = np.zeros((E, 1, N ** 3))
+    _, _, _, nbr_r, nd_r, perm_r, _, mt_r = rotation.rotate_problem(
+        N, z, np.zeros((E, 9, N ** 3)), z, nb, frames, mortars=mt)
+
+    def relative(e, o):
+        """host (e) upper-a direction -> (dimension, sign) in the frame of o"""
+        (pe, se), (po, so) = frames[e], frames[o]
+        out = []
+        for a in range(3):
+            a2 = po.index(pe[a])
+            out += [a2, se[a] * so[a2]]
+        return out
+
+    def segments(e):
+        """(level, index) per rotated dimension"""
+        c, ch = rb.elements[e]
+        m = rb._mask(c)
+        chh = ch or (0, 0, 0)
+        lev = [rb.levels[d] + (1 if m[d] else 0) for d in range(3)]
+        idx = [2 * c[d] + chh[d] if m[d] else c[d] for d in range(3)]
+        p, s = frames[e]
+        out = []
+        for a in range(3):
+            i = idx[p[a]] if s[a] > 0 else 2 ** lev[p[a]] - 1 - idx[p[a]]
+            out += [lev[p[a]], i]
+        return out
+    lines, want = [], []
+    for e in range(E):
+        for d in range(6):
+            o = nbr_r[e, d]
+            if o >= 0:
+                lines.append("F " + " ".join(map(str, relative(e, o) + [d])))
+                want.append((int(nd_r[e, d]), int(perm_r[e, d])))
+    for ec, dc, ef, dfp, sa, sb in mt_r.tolist():
+        lines.append("F " + " ".join(map(str, relative(ec, ef) + [dc])))
+        want.append((dfp & 7, dfp >> 3))
+        lines.append("M " + " ".join(map(str, relative(ec, ef) + [dc // 2] + segments(ec)
+                                         + segments(ef))))
+        want.append((sa, sb))
+        # seen from the fine element the mortar is its whole face
+        lines.append("M " + " ".join(map(str, relative(ef, ec) + [(dfp & 7) // 2] + segments(ef)
+                                         + segments(ec))))
+        want.append((0, 0))
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = [tuple(map(int, ln.split())) for ln in out.stdout.strip().splitlines()]
+    assert len(got) == len(want) > 100
+    assert got == want
