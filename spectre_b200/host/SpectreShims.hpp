@@ -695,6 +695,88 @@ SPECTRE_B200_RK_STEPPER(DormandPrince5, DGRHS_STEPPER_DORMAND_PRINCE5);
 #undef SPECTRE_B200_RK_STEPPER
 }  // namespace TimeSteppers
 
+// ---- connectivity tables from Element<3>-style neighbour lists ----------------------
+// Collects, per element and direction, what Element<3>::neighbors() holds (the ids of the
+// neighbours in that direction and the OrientationMap to their block) or an external-boundary
+// marker, and produces the flat tables of dgrhs_set_geometry (neighbors),
+// dgrhs_set_neighbor_orientations and dgrhs_set_mortars.  Elements are named by their index in
+// the context (the order of the Variables blocks).
+class DgConnectivity {
+ public:
+  explicit DgConnectivity(std::vector<ElementId<3>> element_ids)
+      : ids_(std::move(element_ids)),
+        neighbors_(6 * ids_.size(), -1),
+        directions_(6 * ids_.size()),
+        permutations_(6 * ids_.size(), 0) {
+    for (size_t e = 0; e < ids_.size(); ++e)
+      for (int d = 0; d < 6; ++d) directions_[6 * e + d] = d ^ 1;
+  }
+  // the neighbours of `element` in `direction`: one (conforming, or coarser than the element)
+  // or several (finer; 2:1), all in the block reached through `orientation` (finer neighbours
+  // may also be handed over in several calls)
+  void set_neighbors(size_t element, const Direction3& direction, const std::vector<size_t>& neighbor_elements,
+                     const OrientationMap<3>& orientation) {
+    if (element >= ids_.size() || neighbor_elements.empty()) throw std::runtime_error("bad neighbour list");
+    const size_t slot = 6 * element + static_cast<size_t>(direction.abi());
+    const auto fo = face_orientation(orientation, direction);
+    bool any_finer = false, any_coarser = false;
+    std::vector<std::array<Spectral::MortarSize, 2>> sizes;
+    for (size_t nb : neighbor_elements) {
+      if (nb >= ids_.size()) throw std::runtime_error("neighbour index out of range");
+      sizes.push_back(dg::mortar_size(ids_[element], ids_[nb], direction.dimension, orientation));
+      const auto back = dg::mortar_size(ids_[nb], ids_[element], static_cast<size_t>(fo.neighbor_direction / 2),
+                                        orientation.inverse_map());
+      for (int k = 0; k < 2; ++k) {
+        any_finer = any_finer || sizes.back()[k] != Spectral::MortarSize::Full;
+        any_coarser = any_coarser || back[k] != Spectral::MortarSize::Full;
+      }
+    }
+    if (any_finer && any_coarser)
+      throw std::runtime_error("a mortar smaller than both faces (finer in one face dimension, coarser in "
+                               "the other) is not supported");
+    if (!any_finer && !any_coarser) {
+      if (neighbor_elements.size() != 1) throw std::runtime_error("several conforming neighbours in one direction");
+      neighbors_[slot] = static_cast<int32_t>(neighbor_elements[0]);
+      directions_[slot] = fo.neighbor_direction;
+      permutations_[slot] = fo.permutation;
+      return;
+    }
+    neighbors_[slot] = DGRHS_NEIGHBOR_HANGING;
+    if (any_coarser) return;  // the fine side: the coarse element lists the mortar
+    for (size_t k = 0; k < neighbor_elements.size(); ++k) {
+      mortars_.insert(mortars_.end(),
+                      {static_cast<int32_t>(element), direction.abi(), static_cast<int32_t>(neighbor_elements[k]),
+                       fo.neighbor_direction | (fo.permutation << 3), Spectral::abi_size_code(sizes[k][0]),
+                       Spectral::abi_size_code(sizes[k][1])});
+    }
+  }
+  // an external face: -1 (no boundary correction), -(slot + 2) (ghost boundary condition),
+  // DGRHS_NEIGHBOR_BJORHUS / DGRHS_NEIGHBOR_BJORHUS_PHYSICAL
+  void set_external_boundary(size_t element, const Direction3& direction, int32_t code) {
+    if (element >= ids_.size() || code >= 0) throw std::runtime_error("bad external boundary code");
+    neighbors_[6 * element + static_cast<size_t>(direction.abi())] = code;
+  }
+  const std::vector<int32_t>& neighbors() const { return neighbors_; }                    // [E][6]
+  const std::vector<int32_t>& neighbor_directions() const { return directions_; }        // [E][6]
+  const std::vector<int32_t>& face_permutations() const { return permutations_; }        // [E][6]
+  const std::vector<int32_t>& mortars() const { return mortars_; }                       // [n][6]
+  bool aligned() const {
+    for (size_t k = 0; k < neighbors_.size(); ++k)
+      if (permutations_[k] != 0 || directions_[k] != static_cast<int32_t>((k % 6) ^ 1)) return false;
+    return true;
+  }
+  // geometry + connectivity of a context in one go
+  void apply(dgrhs_ctx* ctx, const double* inv_jacobian, const double* coords) const {
+    check(dgrhs_set_geometry(ctx, inv_jacobian, coords, neighbors_.data()));
+    if (!aligned()) check(dgrhs_set_neighbor_orientations(ctx, directions_.data(), permutations_.data()));
+    if (!mortars_.empty()) check(dgrhs_set_mortars(ctx, static_cast<int>(mortars_.size() / 6), mortars_.data()));
+  }
+
+ private:
+  std::vector<ElementId<3>> ids_;
+  std::vector<int32_t> neighbors_, directions_, permutations_, mortars_;
+};
+
 // ---- batched evolution: the replacement of DgElementArray + step_actions ------------
 class DgEvolution {
  public:

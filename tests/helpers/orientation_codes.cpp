@@ -5,14 +5,62 @@
 #include <cstdio>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "../../spectre_b200/host/SpectreShims.hpp"
 
 using namespace spectre_b200;
 
+// "C n" then n lines "(lev idx)x3", then records "N element direction count nb... d0 s0 d1 s1 d2 s2"
+// and "E element direction code", closed by "end": prints the four tables of DgConnectivity
+static void connectivity() {
+  size_t n;
+  std::cin >> n;
+  std::vector<ElementId<3>> ids;
+  for (size_t e = 0; e < n; ++e) {
+    std::array<std::pair<size_t, size_t>, 3> seg{};
+    for (auto& s : seg) std::cin >> s.first >> s.second;
+    ids.emplace_back(0, seg);
+  }
+  DgConnectivity conn(ids);
+  std::string rec;
+  while (std::cin >> rec && rec != "end") {
+    size_t element;
+    int direction;
+    std::cin >> element >> direction;
+    if (rec == "E") {
+      long code;
+      std::cin >> code;
+      conn.set_external_boundary(element, Direction3::from_abi(direction), static_cast<int32_t>(code));
+      continue;
+    }
+    size_t count;
+    std::cin >> count;
+    std::vector<size_t> nbs(count);
+    for (auto& v : nbs) std::cin >> v;
+    std::array<Direction3, 3> mapped{};
+    for (auto& m : mapped) std::cin >> m.dimension >> m.sign;
+    conn.set_neighbors(element, Direction3::from_abi(direction), nbs, OrientationMap<3>(mapped));
+  }
+  auto dump = [](const char* name, const std::vector<int32_t>& v) {
+    std::printf("%s", name);
+    for (auto x : v) std::printf(" %d", x);
+    std::printf("\n");
+  };
+  dump("neighbors", conn.neighbors());
+  dump("directions", conn.neighbor_directions());
+  dump("permutations", conn.face_permutations());
+  dump("mortars", conn.mortars());
+  std::printf("aligned %d\n", conn.aligned() ? 1 : 0);
+}
+
 int main() {
   std::string kind;
   while (std::cin >> kind) {
+    if (kind == "C") {
+      connectivity();
+      continue;
+    }
     std::array<Direction3, 3> mapped{};
     for (auto& m : mapped) std::cin >> m.dimension >> m.sign;
     const OrientationMap<3> orientation(mapped);

@@ -313,3 +313,91 @@ def test_cpp_orientation_map_and_mortar_size_shims():
     got = [tuple(map(int, ln.split())) for ln in out.stdout.strip().splitlines()]
     assert len(got) == len(want) > 100
     assert got == want
+
+
+@pytest.mark.parametrize("periodic,rotated", [(True, True), (False, True), (False, False)])
+def test_cpp_connectivity_builder(periodic, rotated):
+    """DgConnectivity of SpectreShims.hpp: fed Element<3>-style neighbour lists (ids of the
+    neighbours per direction + the OrientationMap to them) of an h-refined Brick whose
+    elements all sit in random rotated frames, it must produce the neighbour table, the
+    orientation tables and the oriented mortar rows of tests/rotation.py."""
+    import subprocess
+    from tests import rotation
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "orientation_codes")
+    src = os.path.join(root, "tests", "helpers", "orientation_codes.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-o", exe, src, "-L",
+                           os.path.join(root, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(root, "spectre_b200")])
+    N = 2
+    rng = np.random.default_rng(23 + periodic)
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], N,
+                             {(0, 0, 0): (1, 1, 1), (1, 1, 0): (1, 0, 1), (0, 1, 1): (0, 0, 1)},
+                             periodic=(periodic,) * 3)
+    nb, mt = rb.neighbors(), rb.mortars()
+    E = rb.n_elements
+    all48 = rotation.signed_perms()
+    frames = [all48[k] if rotated else ((0, 1, 2), (1, 1, 1)) for k in rng.choice(48, E)]
+    z = np.zeros((E, 1, N ** 3))
+    _, _, _, nbr_r, nd_r, perm_r, _, mt_r = rotation.rotate_problem(
+        N, z, np.zeros((E, 9, N ** 3)), z, nb, frames, mortars=mt)
+
+    def relative(e, o):
+        (pe, se), (po, so) = frames[e], frames[o]
+        out = []
+        for a in range(3):
+            a2 = po.index(pe[a])
+            out += [a2, se[a] * so[a2]]
+        return out
+
+    def segments(e):
+        c, ch = rb.elements[e]
+        m = rb._mask(c)
+        chh = ch or (0, 0, 0)
+        lev = [rb.levels[d] + (1 if m[d] else 0) for d in range(3)]
+        idx = [2 * c[d] + chh[d] if m[d] else c[d] for d in range(3)]
+        p, s = frames[e]
+        return [v for a in range(3)
+                for v in (lev[p[a]], idx[p[a]] if s[a] > 0 else 2 ** lev[p[a]] - 1 - idx[p[a]])]
+    lines = [f"C {E}"] + [" ".join(map(str, segments(e))) for e in range(E)]
+    fine_of = {}      # (coarse, direction) -> fine elements
+    coarse_of = {}    # (fine, direction) -> coarse element
+    for ec, dc, ef, dfp, _, _ in mt_r.tolist():
+        fine_of.setdefault((ec, dc), []).append(ef)
+        coarse_of[(ef, dfp & 7)] = ec
+    for e in range(E):
+        for d in range(6):
+            v = int(nbr_r[e, d])
+            if v >= 0:
+                others = [v]
+            elif v == domain.HANGING:
+                others = fine_of.get((e, d)) or [coarse_of[(e, d)]]
+            else:
+                lines.append(f"E {e} {d} {v}")
+                continue
+            # (every element of this mesh has its own frame, so the finer neighbours of a
+            # face are handed over one by one, each with its own OrientationMap)
+            if rotated:
+                for o in others:
+                    lines.append(" ".join(map(str, ["N", e, d, 1, o] + relative(e, o))))
+            else:   # one block: the whole list with the block's (aligned) OrientationMap
+                lines.append(" ".join(map(str, ["N", e, d, len(others)] + others
+                                          + relative(e, others[0]))))
+    lines.append("end")
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    tables = {ln.split()[0]: np.array(ln.split()[1:], dtype=np.int64)
+              for ln in out.stdout.strip().splitlines()}
+    np.testing.assert_array_equal(tables["neighbors"].reshape(E, 6), nbr_r)
+    conforming = nbr_r >= 0
+    np.testing.assert_array_equal(tables["directions"].reshape(E, 6)[conforming], nd_r[conforming])
+    np.testing.assert_array_equal(tables["permutations"].reshape(E, 6)[conforming],
+                                  perm_r[conforming])
+    got_rows = sorted(map(tuple, tables["mortars"].reshape(-1, 6).tolist()))
+    assert got_rows == sorted(map(tuple, mt_r.tolist())) and len(got_rows) > 0
+    assert tables["aligned"][0] == (0 if rotated else 1)
+    assert periodic or (nbr_r == -1).any()
+    if not rotated:
+        np.testing.assert_array_equal(nbr_r, nb)
+        assert sorted(map(tuple, mt_r.tolist())) == sorted(map(tuple, np.asarray(mt).tolist()))
