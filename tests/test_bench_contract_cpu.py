@@ -51,11 +51,18 @@ def test_reference_arm_prints_one_contract_line():
     _check(lines[0], 1, 2)
 
 
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                           "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
-                          "29547", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "1", "--cpu-sample-refine", "2"],
                          capture_output=True, text=True, cwd=ROOT, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
