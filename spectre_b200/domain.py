@@ -536,6 +536,15 @@ class SphericalShell:
                                      self.order)
             nbr, nd, perm = connectivity_from_geometry(corners.coords(), 2)
             mortars = find_hanging_faces(corners, nbr)
+            # what is still unmatched must be the two spheres; an angular face left over is
+            # an interface this path cannot represent (levels differing by more than one, or
+            # a mortar smaller than both faces: finer in one face dimension, coarser in the other)
+            bad = [(e, d) for e, d in zip(*np.nonzero(nbr == -1)) if d < 4]
+            if bad:
+                e, d = bad[0]
+                raise ValueError(f"unsupported non-conforming interface at block {self.cells[e][0]} "
+                                 f"direction {d}: neighbouring blocks may differ by one refinement "
+                                 "level, and not in opposite senses in the two face dimensions")
             self._conn = (nbr, nd, perm, mortars)
         return self._conn
 

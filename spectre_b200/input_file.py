@@ -24,6 +24,49 @@ import yaml
 from . import analytic, domain, evolution, lib
 
 
+SPHERE_WEDGE_NAMES = ("UpperZ", "LowerZ", "UpperY", "LowerY", "UpperX", "LowerX")
+
+
+def _expand_over_sphere_blocks(value, n_layers, what):
+    """The four forms of a per-block option of the Sphere creator (Sphere.hpp:222-245,
+    ExpandOverBlocks.tpp:37-120): one number, one [phi, theta, r] triple, a triple for every
+    block (shells inside-out, wedges UpperZ LowerZ UpperY LowerY UpperX LowerX in each,
+    Sphere.cpp:168-180), or a map from block names ("Shell0UpperZ") and block groups
+    ("Shell0", "Wedges") to triples.  Returns one triple per block."""
+    names = [f"Shell{l}{w}" for l in range(n_layers) for w in SPHERE_WEDGE_NAMES]
+
+    def triple(v):
+        if isinstance(v, int):
+            return (v, v, v)
+        if isinstance(v, (list, tuple)) and len(v) == 3 and all(isinstance(x, int) for x in v):
+            return tuple(v)
+        raise InputFileError(f"{what}: expected a number or a list of three numbers, got {v!r}")
+    if isinstance(value, dict):
+        groups = {"Wedges": names}
+        for l in range(n_layers):
+            groups[f"Shell{l}"] = names[6 * l:6 * l + 6]
+        per_block = {}
+        for key, v in value.items():
+            members = groups.get(key, [key])
+            for name in members:
+                if name not in names:
+                    raise InputFileError(f"{what}: unknown block or group '{key}'")
+                if name in per_block:
+                    raise InputFileError(f"{what}: duplicate block name '{name}' "
+                                         f"(expanded from '{key}')")
+                per_block[name] = triple(v)
+        missing = [n for n in names if n not in per_block]
+        if missing:
+            raise InputFileError(f"{what}: value for block '{missing[0]}' is missing")
+        return [per_block[n] for n in names]
+    if isinstance(value, (list, tuple)) and value and isinstance(value[0], (list, tuple)):
+        if len(value) != len(names):
+            raise InputFileError(f"{what}: you supplied {len(value)} values, but the domain "
+                                 f"creator has {len(names)} blocks")
+        return [triple(v) for v in value]
+    return [triple(value)] * len(names)
+
+
 class InputFileError(ValueError):
     pass
 
@@ -166,18 +209,24 @@ class Run:
             if o.get("WhichWedges", "All") != "All" or \
                     o.get("EquatorialCompression", None) not in (None, "None"):
                 raise InputFileError("Sphere: WhichWedges / EquatorialCompression not implemented")
-            ref, pts = o["InitialRefinement"], o["InitialGridPoints"]
-            if isinstance(pts, (list, tuple)):
-                if len(set(pts)) != 1:
-                    raise InputFileError("anisotropic InitialGridPoints are not implemented")
-                pts = pts[0]
-            if isinstance(ref, (list, tuple)):
-                if ref[0] != ref[1]:
-                    raise InputFileError("different angular refinement levels not implemented")
-                ref = (int(ref[0]), int(ref[2]))
+            partitioning = tuple(map(float, o.get("RadialPartitioning", [])))
+            n_layers = len(partitioning) + 1
+            pts_blocks = _expand_over_sphere_blocks(o["InitialGridPoints"], n_layers,
+                                                    "Sphere.InitialGridPoints")
+            if len({p for blk in pts_blocks for p in blk}) != 1:
+                raise InputFileError("InitialGridPoints that differ between blocks or dimensions "
+                                     "(p-refinement, anisotropic meshes) are not implemented")
+            pts = pts_blocks[0][0]
+            ref_blocks = _expand_over_sphere_blocks(o["InitialRefinement"], n_layers,
+                                                    "Sphere.InitialRefinement")
+            if any(r[0] != r[1] for r in ref_blocks):
+                raise InputFileError("different angular refinement levels in one block are not "
+                                     "implemented")
+            ref = [[(r[0], r[2]) for r in ref_blocks[6 * l:6 * l + 6]] for l in range(n_layers)]
+            ref = [layer[0] if len(set(layer)) == 1 else layer for layer in ref]
             self.domain = domain.SphericalShell(
                 float(o["InnerRadius"]), float(o["OuterRadius"]), ref, int(pts),
-                tuple(map(float, o.get("RadialPartitioning", []))),
+                partitioning,
                 list(o.get("RadialDistribution", ["Linear"])),
                 bool(o.get("UseEquiangularMap", True)))
             face_bc = {4: self._boundary_condition(io, "Sphere.Interior"),

@@ -107,3 +107,48 @@ def test_run_reference_input_files():
     ks = input_file.load(f"{REF}/GeneralizedHarmonic/KerrSchild.yaml")
     obs = ks.run()
     assert obs[-1][0] == 15 and all(np.isfinite(v) and v < 0.2 for v in obs[-1][2].values())
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_sphere_per_block_refinement_options(tmp_path):
+    """The four forms of Sphere.InitialRefinement (Sphere.hpp:222-233, ExpandOverBlocks):
+    number, [phi, theta, r], one triple per block, map over block / group names.  Per-block
+    values give oriented 2:1 mortars between the wedges."""
+    import yaml
+    with open(f"{REF}/GeneralizedHarmonic/KerrSchild.yaml") as f:
+        meta, opts = list(yaml.safe_load_all(f))
+
+    def load_with(**sphere_options):
+        o = yaml.safe_load(yaml.safe_dump(opts))
+        o["DomainCreator"]["Sphere"].update(sphere_options)
+        path = tmp_path / "input.yaml"
+        with open(path, "w") as f:
+            yaml.safe_dump_all([meta, o], f)
+        return input_file.load(str(path))
+    r = load_with(InitialRefinement=[1, 1, 2])
+    assert r.domain.n_elements == 6 * 4 * 4 and len(r.domain.mortars()) == 0
+    per_block = [[1, 1, 1]] + [[0, 0, 0]] * 5
+    r = load_with(InitialRefinement=per_block)
+    assert r.domain.n_elements == 8 + 5 and len(r.domain.mortars()) == 16
+    by_name = load_with(InitialRefinement={"Shell0UpperZ": [1, 1, 1], "Shell0LowerZ": [0, 0, 0],
+                                           "Shell0UpperY": 0, "Shell0LowerY": 0,
+                                           "Shell0UpperX": 0, "Shell0LowerX": 0})
+    np.testing.assert_array_equal(by_name.domain.mortars(), r.domain.mortars())
+    assert ((r.domain.mortars()[:, 3] >> 3) != 0).any()
+    two = load_with(RadialPartitioning=[2.1], RadialDistribution=["Logarithmic", "Linear"],
+                    InitialRefinement={"Shell0": [1, 1, 0], "Shell1": [0, 0, 1]})
+    assert two.domain.n_layers == 2 and two.domain.n_elements == 6 * 4 + 6 * 2
+    assert len(two.domain.mortars()) == 6 * 4
+    for bad, msg in (({"Shell0": 0, "Shell0UpperZ": 1}, "duplicate block name"),
+                     ({"Shell0UpperZ": 1}, "is missing"),
+                     ({"Shell7": 1}, "unknown block or group"),
+                     ([[0, 0, 0]] * 5, "you supplied 5 values"),
+                     ([1, 0, 0], "different angular refinement levels")):
+        with pytest.raises(input_file.InputFileError, match=msg):
+            load_with(InitialRefinement=bad)
+    with pytest.raises(input_file.InputFileError, match="p-refinement"):
+        load_with(InitialGridPoints={"Shell0UpperZ": 6, "Shell0LowerZ": 5, "Shell0UpperY": 5,
+                                     "Shell0LowerY": 5, "Shell0UpperX": 5, "Shell0LowerX": 5})
+    # finer in the angle on one side, finer in radius on the other: no such mortar here
+    with pytest.raises(ValueError, match="unsupported non-conforming interface"):
+        load_with(InitialRefinement=[[1, 1, 0]] + [[0, 0, 1]] * 5).domain.mortars()
