@@ -21,9 +21,11 @@
 // INTEGRATION.md.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cstddef>
 #include <cstdint>
+#include <map>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -775,6 +777,162 @@ class DgConnectivity {
  private:
   std::vector<ElementId<3>> ids_;
   std::vector<int32_t> neighbors_, directions_, permutations_, mortars_;
+};
+
+// ---- one rank's share of the element list and its halo bookkeeping -------------------
+// The C++ twin of spectre_b200/domain.py::Partition.  The global element list (ordered by
+// block and Z-curve like BlockZCurveProcDistribution, ElementDistribution.hpp:33-47) is cut
+// into `world` contiguous chunks; this rank's elements are ordered interior first (all
+// neighbours local), then boundary, so that the interior range can run while the halo is in
+// flight.  Ghost slots: first the faces received from other ranks, sorted by (peer, sender's
+// global element, sender's direction, receiver's global element, receiver's direction) -- the
+// sender packs in the same order, so the per-peer pieces are contiguous in both buffers --
+// then, if requested, one slot per external face for a ghost boundary condition.
+// Tables are global on input ([n_elements][6] neighbours / directions / permutations as
+// DgConnectivity produces them, mortar rows [n][6]) and local on output.
+class DgPartition {
+ public:
+  DgPartition(const std::vector<int32_t>& neighbors, int world, int rank,
+              const std::vector<int32_t>* neighbor_directions = nullptr,
+              const std::vector<int32_t>* face_permutations = nullptr,
+              const std::vector<int32_t>& mortars = {}, bool boundary_slots = false) {
+    const long ne = static_cast<long>(neighbors.size() / 6);
+    if (world < 1 || rank < 0 || rank >= world || neighbors.size() % 6 != 0 || mortars.size() % 6 != 0)
+      throw std::runtime_error("bad partition arguments");
+    auto bound = [&](int r) { return ne * r / world; };
+    auto owner = [&](long g) {
+      int r = static_cast<int>((g * world) / std::max<long>(ne, 1));
+      while (r + 1 <= world - 1 && bound(r + 1) <= g) ++r;
+      while (r > 0 && bound(r) > g) --r;
+      return r;
+    };
+    auto dir_of = [&](long g, int d) {
+      return neighbor_directions ? (*neighbor_directions)[6 * g + d] : (d ^ 1);
+    };
+    const long lo = bound(rank), hi = bound(rank + 1);
+    const size_t nm = mortars.size() / 6;
+    std::vector<char> is_boundary(static_cast<size_t>(hi - lo), 0);
+    for (long g = lo; g < hi; ++g)
+      for (int d = 0; d < 6; ++d) {
+        const int32_t v = neighbors[6 * g + d];
+        if (v >= 0 && owner(v) != rank) is_boundary[g - lo] = 1;
+        if (v == DGRHS_NEIGHBOR_HANGING && nm == 0) throw std::runtime_error("hanging faces without a mortar table");
+      }
+    // a mortar group (the mortars of one coarse face) with a side on another rank needs
+    // halo data: every local participant is a boundary element
+    std::map<std::pair<int32_t, int32_t>, bool> group_remote;
+    for (size_t m = 0; m < nm; ++m) {
+      const int32_t* r = &mortars[6 * m];
+      bool& flag = group_remote[{r[0], r[1]}];
+      flag = flag || owner(r[0]) != owner(r[2]);
+    }
+    for (size_t m = 0; m < nm; ++m) {
+      const int32_t* r = &mortars[6 * m];
+      if (!group_remote[{r[0], r[1]}]) continue;
+      for (int32_t g : {r[0], r[2]})
+        if (owner(g) == rank) is_boundary[g - lo] = 1;
+    }
+    for (long g = lo; g < hi; ++g)
+      if (!is_boundary[g - lo]) global_ids_.push_back(static_cast<int32_t>(g));
+    n_interior_ = static_cast<int>(global_ids_.size());
+    for (long g = lo; g < hi; ++g)
+      if (is_boundary[g - lo]) global_ids_.push_back(static_cast<int32_t>(g));
+    const size_t nl = global_ids_.size();
+    std::map<int32_t, int32_t> g2l;
+    for (size_t l = 0; l < nl; ++l) g2l[global_ids_[l]] = static_cast<int32_t>(l);
+    local_neighbors_.assign(6 * nl, -1);
+    local_directions_.resize(6 * nl);
+    local_permutations_.assign(6 * nl, 0);
+    using Key = std::array<long, 5>;  // peer, sender element, sender direction, receiver element, its direction
+    struct Entry {
+      Key key;
+      long mortar;   // -1: a conforming face
+      int32_t local; // receiver: unused; sender: local element
+    };
+    std::vector<Entry> recv, send;
+    for (size_t l = 0; l < nl; ++l) {
+      const long g = global_ids_[l];
+      for (int d = 0; d < 6; ++d) {
+        local_directions_[6 * l + d] = d ^ 1;
+        const int32_t v = neighbors[6 * g + d];
+        if (v == DGRHS_NEIGHBOR_HANGING) local_neighbors_[6 * l + d] = DGRHS_NEIGHBOR_HANGING;
+        if (v < 0) continue;
+        local_directions_[6 * l + d] = dir_of(g, d);
+        local_permutations_[6 * l + d] = face_permutations ? (*face_permutations)[6 * g + d] : 0;
+        if (owner(v) == rank) {
+          local_neighbors_[6 * l + d] = g2l[v];
+        } else {
+          recv.push_back({{owner(v), v, dir_of(g, d), g, d}, -1, 0});
+          send.push_back({{owner(v), g, d, v, dir_of(g, d)}, -1, static_cast<int32_t>(l)});
+        }
+      }
+    }
+    for (size_t m = 0; m < nm; ++m) {
+      const int32_t* r = &mortars[6 * m];
+      const long ec = r[0], dc = r[1], ef = r[2], df = r[3] & 7;
+      if (owner(ec) == rank && owner(ef) != rank) {
+        recv.push_back({{owner(ef), ef, df, ec, dc}, static_cast<long>(m), 0});
+        send.push_back({{owner(ef), ec, dc, ef, df}, static_cast<long>(m), g2l[static_cast<int32_t>(ec)]});
+      } else if (owner(ef) == rank && owner(ec) != rank) {
+        recv.push_back({{owner(ec), ec, dc, ef, df}, static_cast<long>(m), 0});
+        send.push_back({{owner(ec), ef, df, ec, dc}, static_cast<long>(m), g2l[static_cast<int32_t>(ef)]});
+      }
+    }
+    auto by_key = [](const Entry& a, const Entry& b) { return a.key < b.key; };
+    std::stable_sort(recv.begin(), recv.end(), by_key);
+    std::stable_sort(send.begin(), send.end(), by_key);
+    recv_counts_.assign(world, 0);
+    send_counts_.assign(world, 0);
+    std::map<long, int32_t> mortar_slot;
+    for (size_t slot = 0; slot < recv.size(); ++slot) {
+      const Entry& e = recv[slot];
+      if (e.mortar < 0)
+        local_neighbors_[6 * g2l[static_cast<int32_t>(e.key[3])] + e.key[4]] = -(static_cast<int32_t>(slot) + 2);
+      else
+        mortar_slot[e.mortar] = static_cast<int32_t>(slot);
+      ++recv_counts_[e.key[0]];
+    }
+    n_recv_ = static_cast<int>(recv.size());
+    for (size_t m = 0; m < nm; ++m) {
+      const int32_t* r = &mortars[6 * m];
+      const bool coarse_here = owner(r[0]) == rank, fine_here = owner(r[2]) == rank;
+      if (!coarse_here && !fine_here) continue;
+      const int32_t lc = coarse_here ? g2l[r[0]] : -(mortar_slot[static_cast<long>(m)] + 2);
+      const int32_t lf = fine_here ? g2l[r[2]] : -(mortar_slot[static_cast<long>(m)] + 2);
+      local_mortars_.insert(local_mortars_.end(), {lc, r[1], lf, r[3], r[4], r[5]});
+    }
+    if (boundary_slots)
+      for (size_t l = 0; l < nl; ++l)
+        for (int d = 0; d < 6; ++d)
+          if (neighbors[6 * static_cast<long>(global_ids_[l]) + d] == -1) {
+            const int32_t slot = n_recv_ + static_cast<int32_t>(external_faces_.size() / 3);
+            external_faces_.insert(external_faces_.end(), {static_cast<int32_t>(l), d, slot});
+            local_neighbors_[6 * l + d] = -(slot + 2);
+          }
+    for (const Entry& e : send) {
+      send_map_.insert(send_map_.end(), {e.local, static_cast<int32_t>(e.key[2])});
+      ++send_counts_[e.key[0]];
+    }
+  }
+  int n_local() const { return static_cast<int>(global_ids_.size()); }
+  int n_interior() const { return n_interior_; }                                   // dgrhs_set_interior_count
+  int n_recv() const { return n_recv_; }
+  int n_ghost() const { return n_recv_ + static_cast<int>(external_faces_.size() / 3); }  // dgrhs_create
+  const std::vector<int32_t>& global_ids() const { return global_ids_; }          // local -> global element
+  const std::vector<int32_t>& local_neighbors() const { return local_neighbors_; }        // dgrhs_set_geometry
+  const std::vector<int32_t>& local_neighbor_directions() const { return local_directions_; }
+  const std::vector<int32_t>& local_face_permutations() const { return local_permutations_; }
+  const std::vector<int32_t>& local_mortars() const { return local_mortars_; }    // dgrhs_set_mortars
+  const std::vector<int32_t>& send_map() const { return send_map_; }              // dgrhs_set_halo_map: (element, direction)
+  const std::vector<int>& send_counts() const { return send_counts_; }            // faces per peer, ncclSend
+  const std::vector<int>& recv_counts() const { return recv_counts_; }            // faces per peer, ncclRecv
+  const std::vector<int32_t>& external_faces() const { return external_faces_; }  // (element, direction, slot)
+
+ private:
+  int n_interior_ = 0, n_recv_ = 0;
+  std::vector<int32_t> global_ids_, local_neighbors_, local_directions_, local_permutations_, local_mortars_,
+      send_map_, external_faces_;
+  std::vector<int> send_counts_, recv_counts_;
 };
 
 // ---- batched evolution: the replacement of DgElementArray + step_actions ------------

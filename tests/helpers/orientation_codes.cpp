@@ -54,11 +54,56 @@ static void connectivity() {
   std::printf("aligned %d\n", conn.aligned() ? 1 : 0);
 }
 
+// "P n_elements world rank oriented boundary_slots n_mortars", then the global tables
+// (neighbors [n][6]; if oriented: directions, permutations; mortar rows): prints DgPartition
+static void partition() {
+  long ne, nm;
+  int world, rank, oriented, slots;
+  std::cin >> ne >> world >> rank >> oriented >> slots >> nm;
+  auto read = [](size_t count) {
+    std::vector<int32_t> v(count);
+    for (auto& x : v) {
+      long long t;
+      std::cin >> t;
+      x = static_cast<int32_t>(t);
+    }
+    return v;
+  };
+  const auto nbr = read(6 * ne);
+  std::vector<int32_t> dirs, perms;
+  if (oriented) {
+    dirs = read(6 * ne);
+    perms = read(6 * ne);
+  }
+  const auto mortars = read(6 * nm);
+  const DgPartition part(nbr, world, rank, oriented ? &dirs : nullptr, oriented ? &perms : nullptr, mortars,
+                         slots != 0);
+  auto dump = [](const char* name, const auto& v) {
+    std::printf("%s", name);
+    for (auto x : v) std::printf(" %d", static_cast<int>(x));
+    std::printf("\n");
+  };
+  std::printf("counts %d %d %d %d\n", part.n_local(), part.n_interior(), part.n_recv(), part.n_ghost());
+  dump("global_ids", part.global_ids());
+  dump("neighbors", part.local_neighbors());
+  dump("directions", part.local_neighbor_directions());
+  dump("permutations", part.local_face_permutations());
+  dump("mortars", part.local_mortars());
+  dump("send_map", part.send_map());
+  dump("send_counts", part.send_counts());
+  dump("recv_counts", part.recv_counts());
+  dump("external_faces", part.external_faces());
+}
+
 int main() {
   std::string kind;
   while (std::cin >> kind) {
     if (kind == "C") {
       connectivity();
+      continue;
+    }
+    if (kind == "P") {
+      partition();
       continue;
     }
     std::array<Direction3, 3> mapped{};

@@ -234,3 +234,73 @@ def _mortar_worker(rank, world, port, kind, results):
 @pytest.mark.parametrize("world,kind", [(2, "brick"), (3, "brick"), (2, "shell")])
 def test_mortars_across_ranks_gloo(world, kind):
     mp.spawn(_mortar_worker, args=(world, _free_port(), kind, None), nprocs=world, join=True)
+
+
+def _partition_cases():
+    brick = domain.Brick([0, 0, 0], [1, 1, 1], [2, 1, 2], 2)
+    yield "periodic brick", brick.neighbors(), None, None, None, False
+    open_brick = domain.Brick([0, 0, 0], [1, 1, 1], [1, 2, 1], 2, periodic=(False, True, False))
+    yield "open brick with ghost boundary slots", open_brick.neighbors(), None, None, None, True
+    shell = domain.SphericalShell(1.9, 2.9, [(1, 1), (1, 0)], 2, radial_partitioning=(2.3,))
+    nd, perm = shell.neighbor_orientations()
+    yield "shell", shell.neighbors(), nd, perm, None, True
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], 2,
+                             {(0, 0, 0): (True, True, True), (1, 1, 0): (True, False, True)})
+    yield "refined brick", rb.neighbors(), None, None, rb.mortars(), False
+    ws = domain.SphericalShell(1.9, 2.9, [[(1, 1), (0, 0), (0, 0), (0, 0), (1, 0), (0, 0)]], 2)
+    nd, perm = ws.neighbor_orientations()
+    yield "wedge-refined shell", ws.neighbors(), nd, perm, ws.mortars(), True
+
+
+def test_cpp_partition_matches_python_partition():
+    """DgPartition of SpectreShims.hpp (the C++ host side of the multi-GPU schedule) gives
+    the same local order, local tables, ghost slots, send map and per-peer counts as
+    spectre_b200.domain.Partition, for bricks, shells with non-aligned blocks, and
+    aligned / oriented mortars cut across ranks."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "orientation_codes")
+    src = os.path.join(root, "tests", "helpers", "orientation_codes.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-o", exe, src, "-L",
+                           os.path.join(root, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(root, "spectre_b200")])
+    checked = 0
+    for name, nbr, nd, perm, mt, slots in _partition_cases():
+        ne = nbr.shape[0]
+        mt_arr = np.zeros((0, 6), dtype=np.int64) if mt is None else np.asarray(mt)
+        for world in (1, 2, 3):
+            for rank in range(world):
+                want = domain.Partition(nbr, world, rank, boundary_slots=slots, neighbor_direction=nd,
+                                        face_permutation=perm, mortars=mt)
+                text = [f"P {ne} {world} {rank} {int(nd is not None)} {int(slots)} {len(mt_arr)}",
+                        " ".join(map(str, nbr.reshape(-1).tolist()))]
+                if nd is not None:
+                    text += [" ".join(map(str, np.asarray(nd).reshape(-1).tolist())),
+                             " ".join(map(str, np.asarray(perm).reshape(-1).tolist()))]
+                text.append(" ".join(map(str, mt_arr.reshape(-1).tolist())))
+                out = subprocess.run([exe], input="\n".join(text) + "\n", capture_output=True,
+                                     text=True)
+                assert out.returncode == 0, (name, out.stderr)
+                got = {ln.split()[0]: np.array(ln.split()[1:], dtype=np.int64)
+                       for ln in out.stdout.strip().splitlines()}
+                tag = (name, world, rank)
+                assert got["counts"].tolist() == [want.n_local, want.n_interior, want.n_recv,
+                                                  want.n_ghost], tag
+                np.testing.assert_array_equal(got["global_ids"], want.global_ids, err_msg=str(tag))
+                np.testing.assert_array_equal(got["neighbors"].reshape(-1, 6), want.local_neighbors,
+                                              err_msg=str(tag))
+                np.testing.assert_array_equal(got["directions"].reshape(-1, 6),
+                                              want.local_neighbor_direction, err_msg=str(tag))
+                np.testing.assert_array_equal(got["permutations"].reshape(-1, 6),
+                                              want.local_face_permutation, err_msg=str(tag))
+                np.testing.assert_array_equal(got["mortars"].reshape(-1, 6), want.local_mortars,
+                                              err_msg=str(tag))
+                np.testing.assert_array_equal(got["send_map"].reshape(-1, 2), want.send_map,
+                                              err_msg=str(tag))
+                assert got["send_counts"].tolist() == list(want.send_counts), tag
+                assert got["recv_counts"].tolist() == list(want.recv_counts), tag
+                assert got["external_faces"].reshape(-1, 3).tolist() == \
+                    [list(t) for t in want.external_faces], tag
+                checked += 1
+    assert checked == 5 * 6
