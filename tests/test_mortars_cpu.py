@@ -308,6 +308,17 @@ def test_cpp_orientation_map_and_mortar_size_shims():
         lines.append("M " + " ".join(map(str, relative(ef, ec) + [(dfp & 7) // 2] + segments(ef)
                                          + segments(ec))))
         want.append((0, 0))
+    # the known answers of Test_MortarHelpers.cpp:57-68 (2-d cases embedded in 3-d) and
+    # :129-135 (non-aligned blocks: xi -> +eta, eta -> +zeta, zeta -> -xi)
+    aligned = [0, 1, 1, 1, 2, 1]
+    lines.append("M " + " ".join(map(str, aligned + [1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])))
+    want.append((0, 0))
+    lines.append("M " + " ".join(map(str, aligned + [1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])))
+    want.append((0, 0))
+    lines.append("M " + " ".join(map(str, aligned + [1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0])))
+    want.append((1, 0))
+    lines.append("M 1 1 2 1 0 -1 0  0 0 3 2 7 5  6 61 3 0 4 5")
+    want.append((2, 0))
     out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     got = [tuple(map(int, ln.split())) for ln in out.stdout.strip().splitlines()]
