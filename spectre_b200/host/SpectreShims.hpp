@@ -287,6 +287,30 @@ class ElementId {
   uint64_t bits_ = 0;
 };
 
+namespace domain {
+// domain::z_curve_index (Domain/Structure/ZCurve.cpp:17-80): position of the element on the
+// Morton curve of its block; dimensions are interleaved from the least refined one up, bits of
+// a dimension stop once its refinement level is used up.  Elements are handed to a context, and
+// cut into per-rank chunks by DgPartition, in (block, z_curve_index) order.
+inline size_t z_curve_index(const ElementId<3>& id) {
+  std::array<std::pair<size_t, size_t>, 3> dims{};   // (refinement level, dimension), ascending
+  for (size_t d = 0; d < 3; ++d) dims[d] = {id.refinement_level(d), d};
+  std::sort(dims.begin(), dims.end());
+  size_t out = 0, leading_gap = 0;
+  for (size_t i = 0; i < 3; ++i) {
+    const auto [level, dim] = dims[i];
+    size_t total_gap = leading_gap;
+    if (level > 0) ++leading_gap;
+    for (size_t bit = 0; bit < level; ++bit) {
+      out |= (id.index(dim) & (size_t{1} << bit)) << total_gap;
+      for (size_t j = 0; j < 3; ++j)
+        if (i != j && bit + 1 < dims[j].first) ++total_gap;
+    }
+  }
+  return out;
+}
+}  // namespace domain
+
 // ---- Direction<3>, SegmentId, OrientationMap<3>, dg::mortar_size ----------------------
 // What a caller needs to turn Element<3>::neighbors() (ids + OrientationMap per direction,
 // Domain/Structure/{Direction,SegmentId,OrientationMap}.hpp) into the tables of

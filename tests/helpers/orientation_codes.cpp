@@ -106,6 +106,12 @@ int main() {
       partition();
       continue;
     }
+    if (kind == "Z") {  // "Z (lev idx)x3" -> domain::z_curve_index
+      std::array<std::pair<size_t, size_t>, 3> seg{};
+      for (auto& sg : seg) std::cin >> sg.first >> sg.second;
+      std::printf("%zu\n", domain::z_curve_index(ElementId<3>(0, seg)));
+      continue;
+    }
     std::array<Direction3, 3> mapped{};
     for (auto& m : mapped) std::cin >> m.dimension >> m.sign;
     const OrientationMap<3> orientation(mapped);

@@ -117,6 +117,43 @@ def test_z_curve_order_matches_reference_bit_interleave():
     # unequal refinement: dimensions with level 0 are skipped
     assert domain.z_curve_index(1, 0, 1, (1, 0, 1)) == 0b11
     assert domain.z_curve_index(2, 0, 1, (2, 0, 1)) == 0b101
+    for (ix, iz), want in ZCURVE_KNOWN_ANSWERS.items():
+        assert domain.z_curve_index(ix, 0, iz, (2, 0, 3)) == want
+
+
+# tests/Unit/Domain/Structure/Test_ZCurve.cpp:236-291: refinement levels (2, 0, 3),
+# (x index, z index) -> Z-curve index
+ZCURVE_KNOWN_ANSWERS = {
+    (0, 0): 0, (1, 0): 1, (2, 0): 4, (3, 0): 5, (0, 1): 2, (1, 1): 3, (2, 1): 6, (3, 1): 7,
+    (0, 2): 8, (1, 2): 9, (2, 2): 12, (3, 2): 13, (0, 3): 10, (1, 3): 11, (2, 3): 14, (3, 3): 15,
+    (0, 4): 16, (1, 4): 17, (2, 4): 20, (3, 4): 21, (0, 5): 18, (1, 5): 19, (2, 5): 22,
+    (3, 5): 23, (0, 6): 24}
+
+
+def test_cpp_z_curve_index_shim():
+    """domain::z_curve_index of SpectreShims.hpp against the reference's known answers and
+    against spectre_b200.domain.z_curve_index on random unequal refinements."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "orientation_codes")
+    src = os.path.join(root, "tests", "helpers", "orientation_codes.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-o", exe, src, "-L",
+                           os.path.join(root, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(root, "spectre_b200")])
+    lines, want = [], []
+    for (ix, iz), v in ZCURVE_KNOWN_ANSWERS.items():
+        lines.append(f"Z 2 {ix} 0 0 3 {iz}")
+        want.append(v)
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        lev = rng.integers(0, 5, 3)
+        idx = [int(rng.integers(0, 2 ** l)) for l in lev]
+        lines.append("Z " + " ".join(f"{l} {i}" for l, i in zip(lev, idx)))
+        want.append(domain.z_curve_index(*idx, tuple(int(l) for l in lev)))
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert [int(v) for v in out.stdout.split()] == want
 
 
 def _shell_worker(rank, world, port, order, results):
