@@ -106,6 +106,21 @@ int main() {
       partition();
       continue;
     }
+    if (kind == "I") {  // "I d0 s0 d1 s1 d2 s2 (lev idx)x3" -> inverse map, mapped segment ids, is_aligned
+      std::array<Direction3, 3> mapped{};
+      for (auto& m : mapped) std::cin >> m.dimension >> m.sign;
+      std::array<SegmentId, 3> seg{};
+      for (auto& sg : seg) std::cin >> sg.refinement_level >> sg.index;
+      const OrientationMap<3> o(mapped);
+      const auto inv = o.inverse_map();
+      for (size_t d = 0; d < 3; ++d) {
+        const auto m = inv(Direction3{d, 1});
+        std::printf("%zu %d ", m.dimension, m.sign);
+      }
+      for (const auto& sg : o(seg)) std::printf("%zu %zu ", sg.refinement_level, sg.index);
+      std::printf("%d\n", o.is_aligned() ? 1 : 0);
+      continue;
+    }
     if (kind == "Z") {  // "Z (lev idx)x3" -> domain::z_curve_index
       std::array<std::pair<size_t, size_t>, 3> seg{};
       for (auto& sg : seg) std::cin >> sg.first >> sg.second;

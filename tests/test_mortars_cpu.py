@@ -319,6 +319,15 @@ def test_cpp_orientation_map_and_mortar_size_shims():
     want.append((1, 0))
     lines.append("M 1 1 2 1 0 -1 0  0 0 3 2 7 5  6 61 3 0 4 5")
     want.append((2, 0))
+    # OrientationMap known answers of Test_OrientationMap.cpp: :308-314 the inverse of
+    # (-eta, -zeta, +xi) is (+zeta, -xi, -eta); :268-285 the all-flipped map takes the segments
+    # (2,1) (3,1) (3,3) to (2,2) (3,6) (3,4) and is not aligned
+    lines.append("I 1 -1 2 -1 0 1  0 0 0 0 0 0")
+    want.append((2, 1, 0, -1, 1, -1, 0, 0, 0, 0, 0, 0, 0))
+    lines.append("I 0 -1 1 -1 2 -1  2 1 3 1 3 3")
+    want.append((0, -1, 1, -1, 2, -1, 2, 2, 3, 6, 3, 4, 0))
+    lines.append("I 0 1 1 1 2 1  2 1 3 1 3 3")
+    want.append((0, 1, 1, 1, 2, 1, 2, 1, 3, 1, 3, 3, 1))
     out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     got = [tuple(map(int, ln.split())) for ln in out.stdout.strip().splitlines()]
