@@ -49,6 +49,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py's CPU arm sets the thread count itself (torchrun exports
+ * OMP_NUM_THREADS=1 to its workers) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------
  * logical + inertial partial derivatives
  * NumericalAlgorithms/LinearOperators/PartialDerivatives.tpp:316-363 (three
@@ -1184,6 +1194,46 @@ void orc_lincomb(long long len, double a, double* u, int nterms,
     double v = a * u[p];
     for (int j = 0; j < nterms; ++j) v += coefs[j] * vs[j][p];
     u[p] = v;
+  }
+}
+
+/* Exponential filter applied to every component block: apply_matrices(u, {F, F, F})
+ * (NumericalAlgorithms/LinearOperators/ExponentialFilter.cpp:45-76 ->
+ * ApplyMatrices.hpp), F row-major [N][N]; u holds `nblocks` blocks of N^3
+ * doubles (xi fastest), filtered in place, one dimension after the other. */
+void orc_apply_filter(int N, long long nblocks, const double* F, double* u) {
+  const int n = N * N * N;
+#pragma omp parallel
+  {
+    double* a = (double*)malloc(sizeof(double) * (size_t)n);
+    double* b = (double*)malloc(sizeof(double) * (size_t)n);
+#pragma omp for schedule(static)
+    for (long long blk = 0; blk < nblocks; ++blk) {
+      double* v = u + blk * n;
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+            for (int m = 0; m < N; ++m) s += F[i * N + m] * v[m + N * (j + N * k)];
+            a[i + N * (j + N * k)] = s;
+          }
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+            for (int m = 0; m < N; ++m) s += F[j * N + m] * a[i + N * (m + N * k)];
+            b[i + N * (j + N * k)] = s;
+          }
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+            for (int m = 0; m < N; ++m) s += F[k * N + m] * b[i + N * (j + N * m)];
+            v[i + N * (j + N * k)] = s;
+          }
+    }
+    free(a);
+    free(b);
   }
 }
 

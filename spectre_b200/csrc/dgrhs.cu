@@ -14,34 +14,12 @@
 #include <string>
 #include <vector>
 
-#include "../../include/dgrhs.h"
-#include "kernels.cuh"
+#include "ctx.cuh"
 
 namespace {
 
 thread_local std::string g_error;
 int64_t g_launches = 0;
-
-int fail(const char* fmt, ...) {
-  char buf[1024];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_error = buf;
-  return 1;
-}
-
-#define CU(call)                                                            \
-  do {                                                                      \
-    cudaError_t err__ = (call);                                             \
-    if (err__ != cudaSuccess)                                               \
-      return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
-                  __FILE__, __LINE__);                                      \
-  } while (0)
-
-#define CHECK_CTX(ctx) \
-  if (!(ctx)) return fail("null context")
 
 // ---------------------------------------------------------------------------
 // Spectral quantities: Legendre-Gauss-Lobatto nodes/weights (Kopriva Alg. 25,
@@ -310,85 +288,7 @@ std::vector<double> ab_coefficients_ticks(const std::vector<long long>& ticks,
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
-struct HistoryEntry {
-  long long tick;
-  int slot;
-};
-
-struct SubstepOp {
-  enum Kind { kAbStep, kAbEvalOnly, kRestoreU0 } kind;
-  int order;
-  long long tick, tick_end;
-  bool regular = false;  // a step of the evolution proper (not self-start)
-};
-
-struct dgrhs_ctx {
-  int system = 0, N = 0, nelem = 0, nghost = 0, device = 0;
-  int C = 0, S = 0, HC = 0, n = 0, npad = 0, f = 0;
-  int n_interior = -1;
-  int n_send = 0;  // faces packed for other ranks (0: no exchange needed)
-  bool aligned_table_ok = true;
-  cudaStream_t stream = nullptr;
-  // side stream for the few-CTA, latency-bound Bjorhus kernel: it runs next to the
-  // face kernel (disjoint corr slots) and joins before the volume kernel
-  // set by launch_faces when the face kernel is the last thing queued: the volume
-  // kernel that follows may be launched as its programmatic dependent
-  bool pdl_volume = false;
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
-  double *u = nullptr, *invjac = nullptr, *coords = nullptr, *stat = nullptr;
-  double *corr = nullptr, *D = nullptr, *gH = nullptr, *gdH = nullptr;
-  double *halo_send = nullptr, *halo_recv = nullptr;
-  int32_t *nbr = nullptr, *halo_map = nullptr, *nbr_face = nullptr;
-  std::vector<int32_t> nbr_host;
-  std::vector<double*> dt_slots;  // derivative buffers (history ring)
-  double* u0 = nullptr;           // saved value (self-start / RK step start)
-  double* u_alt = nullptr;        // second state buffer for the fused update
-  double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
-  double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
-  unsigned long long* violations = nullptr;  // DemandOutgoingCharSpeeds status (device)
-  // ConstraintPreservingBjorhus faces (DGRHS_NEIGHBOR_BJORHUS in the neighbour table)
-  int n_bjorhus_faces = 0;
-  int64_t aux_faces_eval = -1;       // RHS evaluation that already ran the Bjorhus/mortar kernels
-  int32_t* bjorhus_faces = nullptr;  // [n][3] element, direction, physical
-  // non-conforming mortars (dgrhs_set_mortars)
-  int n_mortar_faces = 0;
-  int n_mortar_faces_local = 0;      // groups without a remote side come first
-  int32_t* mortar_faces = nullptr;   // [n_mortar_faces][4]
-  int32_t* mortar_table = nullptr;   // [n_mortars][4]
-  double* mortar_P = nullptr;        // [3][N*N]
-  double* mortar_R = nullptr;        // [3][N*N]
-  int volume_variant = 0;         // 0 default, 1 context + streaming kernels (N <= 10),
-                                  // 2 DFMA pair-staged kernel also for N = 12
-  bool fuse_update = true;        // fuse UpdateU into the volume kernel
-  dg::UpdateArgs pending_upd{};   // filled by begin_substep when fusing
-  bool upd_active = false;
-  double* dt_last = nullptr;
-  int gauge = DGRHS_GAUGE_HARMONIC;
-  double gauge_params[8] = {0};
-  // stepping
-  int stepper = DGRHS_STEPPER_ADAMS_BASHFORTH, order = 1;
-  double t0 = 0.0, dt = 0.0;
-  long long tick_den = 1, step_index = 0;
-  std::deque<HistoryEntry> history;
-  std::deque<SubstepOp> pending;  // self-start program
-  std::vector<int> free_slots;
-  int rk_substep = 0;
-  int cur_slot = -1;
-  SubstepOp cur_op{};
-  bool in_substep = false;
-  int64_t rhs_evals = 0;
-  size_t state_len() const { return (size_t)nelem * C * npad; }
-};
-
 namespace {
-
-template <typename T>
-int dev_alloc(T** p, size_t count) {
-  CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
-  CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
-  return 0;
-}
 
 // host [E][ncomp][n] <-> device [E][ncomp][npad]
 int upload(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
@@ -404,241 +304,14 @@ int download(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
   return 0;
 }
 
-// DGRHS_NO_PDL=1 in the environment turns programmatic dependent launch off
-static const bool g_pdl = [] {
-  const char* v = std::getenv("DGRHS_NO_PDL");
-  return !(v && v[0] == '1');
-}();
-
-// kernel<<<blocks, threads, smem, stream>>>(args), optionally as the programmatic
-// dependent of the kernel queued before it
-template <typename Kernel, typename Args>
-cudaError_t launch_dependent(Kernel k, int blocks, int threads, size_t smem, cudaStream_t stream,
-                             bool pdl, const Args& args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)blocks);
-  cfg.blockDim = dim3((unsigned)threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k, args);
-}
-
-#ifndef DG_FOR_EACH_N  // (a build with -D'DG_FOR_EACH_N(X)=X(12)' compiles faster for experiments)
-#define DG_FOR_EACH_N(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
-#endif
-
-template <int N>
-int launch_faces(dgrhs_ctx* c, int eb, int ee) {
-  if (ee <= eb) return 0;
-  if (!c->nbr_face && !c->aligned_table_ok)
-    return fail("neighbor table is not that of aligned blocks: call "
-                "dgrhs_set_neighbor_orientations");
-  // whole batch: every interface once; element ranges: the interior / boundary
-  // split of the multi-GPU schedule (see FaceArgs::pass)
-  int pass = 0, n_int = c->nelem;
-  if (!(eb == 0 && ee == c->nelem)) {
-    if (c->n_interior < 0)
-      return fail("element ranges need dgrhs_set_interior_count (interior elements first)");
-    n_int = c->n_interior;
-    if (eb == 0 && ee == n_int)
-      pass = 1;
-    else if (eb == n_int && ee == c->nelem)
-      pass = 2;
-    else
-      return fail("element range must be [0, n_interior) or [n_interior, n_elements)");
-  }
-  dg::FaceArgs a{c->u,    c->invjac, c->stat, c->nbr, c->nbr_face, c->halo_recv,
-                 c->corr, c->nelem,  n_int,   pass,   c->violations};
-  // Bjorhus faces and non-conforming mortars need no halo data: all of them are
-  // evaluated once per right-hand side, with whichever pass comes first, so that
-  // their corrections are in place before ANY volume kernel of this evaluation
-  const bool aux_now = c->aux_faces_eval != c->rhs_evals;
-  c->aux_faces_eval = c->rhs_evals;
-  const bool bjorhus_now = c->n_bjorhus_faces > 0 && aux_now;
-  if (bjorhus_now) {
-    CU(cudaEventRecord(c->aux_fork, c->stream));
-    CU(cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
-    dg::BjorhusArgs b{c->u, c->invjac, c->stat, c->gH, c->gdH, c->coords, c->D, c->corr,
-                      c->bjorhus_faces, {}};
-    int gauge_mode = 1;
-    if (c->gauge == DGRHS_GAUGE_HARMONIC) gauge_mode = 0;
-    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
-      const double* p = c->gauge_params;
-      b.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
-      gauge_mode = 2;
-    }
-    constexpr int bT = (N * N + 31) / 32 * 32;
-    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->aux_stream>>>(b, gauge_mode);
-    ++g_launches;
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(c->aux_join, c->aux_stream));
-  }
-  const long long total = (long long)c->nelem * 6 * N * N;
-  const int blocks = (int)((total + 127) / 128);
-  if (c->system == DGRHS_SYSTEM_GH)
-    dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
-  else
-    dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
-  ++g_launches;
-  CU(cudaGetLastError());
-  if (bjorhus_now) CU(cudaStreamWaitEvent(c->stream, c->aux_join, 0));
-  // mortar groups whose sides are all local run with the first pass; groups with a
-  // remote side need the halo: with the boundary pass (or the single full pass)
-  auto launch_mortars = [&](int first, int count) -> int {
-    if (count <= 0) return 0;
-    dg::MortarArgs m{c->u, c->invjac, c->stat, c->corr, c->mortar_faces, c->mortar_table,
-                     c->mortar_P, c->mortar_R, c->halo_recv, first};
-    constexpr int msmem = dg::mortar_smem_bytes<N>();
-    constexpr int mT = (N * N + 31) / 32 * 32;
-    if (c->system == DGRHS_SYSTEM_GH) {
-      auto k = dg::mortar_kernel<N, 1>;
-      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
-      k<<<count, mT, msmem, c->stream>>>(m);
-    } else {
-      auto k = dg::mortar_kernel<N, 0>;
-      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
-      k<<<count, mT, msmem, c->stream>>>(m);
-    }
-    ++g_launches;
-    CU(cudaGetLastError());
-    return 0;
-  };
-  if (aux_now && launch_mortars(0, c->n_mortar_faces_local)) return 1;
-  if (pass != 1 &&
-      launch_mortars(c->n_mortar_faces_local, c->n_mortar_faces - c->n_mortar_faces_local))
-    return 1;
-  c->pdl_volume = g_pdl && !bjorhus_now && c->n_mortar_faces == 0;
-  return 0;
-}
-
-template <int N>
-int launch_gauge(dgrhs_ctx* c, double time) {
-  if (c->gauge != DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE) return 0;
-  if (!c->coords) return fail("AnalyticChristoffel(GaugeWave) gauge needs coordinates");
-  dg::GaugeWaveArgs g{c->coords, c->gH, c->gauge_params[0], c->gauge_params[1], time,
-                      c->nelem};
-  const long long total = (long long)c->nelem * c->n;
-  dg::gauge_wave_h_kernel<N><<<(int)((total + 255) / 256), 256, 0, c->stream>>>(g);
-  ++g_launches;
-  CU(cudaGetLastError());
-  // spatial derivative d_i H_b -> gdH component (i+1) + 4 b; d_0 H_b stays 0
-  dg::DerivArgs d{c->gH, c->invjac, c->gdH, c->D, 4, 16, 1, 4};
-  dg::partial_derivatives_kernel<N><<<c->nelem * 4, 256, 0, c->stream>>>(d);
-  ++g_launches;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-template <int N, int kGauge>
-int launch_gh_split(dgrhs_ctx* c, const dg::GhVolArgs& a, int eb, int ee) {
-  if (!c->ctxbuf &&
-      dev_alloc(&c->ctxbuf, (size_t)c->nelem * dg::kGhCtxComps * c->npad))
-    return 1;
-  dg::GhCtxArgs ca{c->u, c->stat, c->gH, c->gdH, c->coords, c->ctxbuf, a.dh, eb, ee};
-  const long long pts = (long long)(ee - eb) * c->n;
-  dg::gh_context_kernel<N, kGauge><<<(int)((pts + 255) / 256), 256, 0, c->stream>>>(ca);
-  ++g_launches;
-  CU(cudaGetLastError());
-  constexpr int smem = dg::SCfg<N>::smem_bytes;
-  auto k = dg::gh_stream_kernel<N>;
-  CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k<<<(ee - eb) * dg::Cfg<N>::nchunk, dg::Cfg<N>::T, smem, c->stream>>>(a, c->ctxbuf);
-  ++g_launches;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-template <int N>
-int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
-                  const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
-  const bool pdl = c->pdl_volume;
-  c->pdl_volume = false;
-  if (ee <= eb) return 0;
-  const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
-  if (c->system == DGRHS_SYSTEM_GH) {
-    dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
-                    c->gH, c->gdH, c->D, c->coords, {}, eb, upd};
-    if constexpr (dg::SCfg<N>::fits && N <= 10) {
-      if (c->volume_variant == 1) {
-        if (c->gauge == DGRHS_GAUGE_HARMONIC) return launch_gh_split<N, 0>(c, a, eb, ee);
-        if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
-          if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
-          const double* p = c->gauge_params;
-          a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
-          return launch_gh_split<N, 2>(c, a, eb, ee);
-        }
-        return launch_gh_split<N, 1>(c, a, eb, ee);
-      }
-    }
-    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
-      if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
-      const double* p = c->gauge_params;
-      a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
-    }
-    constexpr int smem = dg::gh_volume_smem_bytes<N>();
-    if (c->gauge == DGRHS_GAUGE_HARMONIC) {
-      auto k = dg::gh_volume_kernel<N, 0>;
-      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
-    } else if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
-      if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
-      const double* p = c->gauge_params;
-      a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
-      auto k = dg::gh_volume_kernel<N, 2>;
-      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
-    } else {
-      auto k = dg::gh_volume_kernel<N, 1>;
-      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
-    }
-  } else {
-    dg::SwVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr, c->D, eb,
-                    upd};
-    constexpr int smem = dg::sw_volume_smem_bytes<N>();
-    auto k = dg::sw_volume_kernel<N>;
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
-  }
-  ++g_launches;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-template <int N>
-int launch_pack(dgrhs_ctx* c) {
-  if (c->n_send == 0) return 0;
-  dg::PackArgs a{c->u, c->invjac, c->stat, c->halo_map, c->halo_send, c->n_send};
-  const long long total = (long long)c->n_send * N * N;
-  const int blocks = (int)((total + 127) / 128);
-  if (c->system == DGRHS_SYSTEM_GH)
-    dg::pack_halo_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(a);
-  else
-    dg::pack_halo_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(a);
-  ++g_launches;
-  CU(cudaGetLastError());
-  return 0;
-}
-
 int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume_only,
               bool do_gauge, const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
   c->pdl_volume = false;
-  switch (c->N) {
-#define X(NN)                                                        \
-  case NN:                                                           \
-    if (do_gauge && launch_gauge<NN>(c, time)) return 1;             \
-    if (!volume_only && launch_faces<NN>(c, eb, ee)) return 1;       \
-    return launch_volume<NN>(c, dt, eb, ee, !volume_only, upd);
-    DG_FOR_EACH_N(X)
-#undef X
-    default:
-      return fail("unsupported number of grid points per dimension: %d", c->N);
-  }
+  const DgNOps* ops = dgrhs_nops(c->N);
+  if (!ops) return fail("unsupported number of grid points per dimension: %d", c->N);
+  if (do_gauge && ops->gauge(c, time)) return 1;
+  if (!volume_only && ops->faces(c, eb, ee)) return 1;
+  return ops->volume(c, dt, eb, ee, !volume_only, &upd);
 }
 
 int lincomb(dgrhs_ctx* c, double* u, double a, const std::vector<double>& coef,
@@ -662,18 +335,7 @@ int lincomb(dgrhs_ctx* c, double* u, double a, const std::vector<double>& coef,
 
 int apply_filter(dgrhs_ctx* c) {
   if (!c->filterF) return 0;
-  dg::FilterArgs a{c->u, c->filterF, c->C};
-  switch (c->N) {
-#define X(NN)                                                                              \
-  case NN:                                                                                 \
-    dg::exponential_filter_kernel<NN><<<c->nelem * c->C, 256, 0, c->stream>>>(a);          \
-    break;
-    DG_FOR_EACH_N(X)
-#undef X
-  }
-  ++g_launches;
-  CU(cudaGetLastError());
-  return 0;
+  return dgrhs_nops(c->N)->filter(c);
 }
 
 int ensure_slots(dgrhs_ctx* c, int count) {
@@ -758,6 +420,24 @@ int prepare_fused_update(dgrhs_ctx* c) {
 }
 
 }  // namespace
+
+
+#define DG_FOR_EACH_N(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+extern "C" {
+#define X(NN) const DgNOps* dgrhs_internal_nops_##NN(void);
+DG_FOR_EACH_N(X)
+#undef X
+}
+const DgNOps* dgrhs_nops(int N) {
+  switch (N) {
+#define X(NN) \
+  case NN:    \
+    return dgrhs_internal_nops_##NN();
+    DG_FOR_EACH_N(X)
+#undef X
+  }
+  return nullptr;
+}
 
 // ---------------------------------------------------------------------------
 // C-ABI
@@ -1312,26 +992,10 @@ int dgrhs_set_gauge_analytic_christoffel(dgrhs_ctx* c, const double* u_analytic)
   double* tmp = nullptr;
   if (dev_alloc(&tmp, c->state_len())) return 1;
   if (upload(c, tmp, u_analytic, c->C)) return 1;
-  dg::GaugeFromStateArgs g{tmp, c->gH, c->nelem};
-  const long long total = (long long)c->nelem * c->n;
-  int rc = 0;
-  switch (c->N) {
-#define X(NN)                                                                             \
-  case NN: {                                                                              \
-    dg::gauge_h_from_state_kernel<NN><<<(int)((total + 255) / 256), 256, 0, c->stream>>>(g); \
-    dg::DerivArgs d{c->gH, c->invjac, c->gdH, c->D, 4, 16, 1, 4};                         \
-    dg::partial_derivatives_kernel<NN><<<c->nelem * 4, 256, 0, c->stream>>>(d);           \
-  } break;
-    DG_FOR_EACH_N(X)
-#undef X
-    default:
-      rc = 1;
-  }
-  g_launches += 2;
-  CU(cudaGetLastError());
+  const int rc = dgrhs_nops(c->N)->gauge_from_state(c, tmp);
   CU(cudaStreamSynchronize(c->stream));
   cudaFree(tmp);
-  return rc ? fail("unsupported N") : 0;
+  return rc;
 }
 
 int dgrhs_set_gauge_fields(dgrhs_ctx* c, const double* H, const double* dH) {
@@ -1422,14 +1086,7 @@ int dgrhs_set_boundary_ghost_data(dgrhs_ctx* c, int slot_begin, int n_slots,
 int dgrhs_pack_halo(dgrhs_ctx* c) {
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));
-  switch (c->N) {
-#define X(NN) \
-  case NN:    \
-    return launch_pack<NN>(c);
-    DG_FOR_EACH_N(X)
-#undef X
-  }
-  return fail("unsupported N");
+  return dgrhs_nops(c->N)->pack(c);
 }
 
 int dgrhs_compute_time_derivative_range(dgrhs_ctx* c, double time, int eb, int ee) {
@@ -1751,17 +1408,13 @@ int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
     for (int r = -1; r < reps; ++r) {  // r = -1: warm-up
       CU(cudaEventRecord(e0, c->stream));
       int rc = 0;
-      switch (c->N) {
-#define X(NN)                                                                     \
-  case NN:                                                                        \
-    if (which == 0) c->aux_faces_eval = -1; /* time Bjorhus/mortar kernels too */ \
-    if (which == 0) rc = launch_faces<NN>(c, 0, c->nelem);                        \
-    if (which == 1) rc = launch_volume<NN>(c, c->dt_last, 0, c->nelem, true);     \
-    if (which == 3) rc = launch_volume<NN>(c, scratch, 0, c->nelem, true, fused); \
-    break;
-        DG_FOR_EACH_N(X)
-#undef X
+      const DgNOps* ops = dgrhs_nops(c->N);
+      if (which == 0) {
+        c->aux_faces_eval = -1;  // time the Bjorhus/mortar kernels too
+        rc = ops->faces(c, 0, c->nelem);
       }
+      if (which == 1) rc = ops->volume(c, c->dt_last, 0, c->nelem, true, nullptr);
+      if (which == 3) rc = ops->volume(c, scratch, 0, c->nelem, true, &fused);
       if (which == 2) {
         std::vector<double> coef(update_terms, 0.0);
         std::vector<const double*> v;
@@ -1790,21 +1443,7 @@ int dgrhs_gh_constraint_norms(dgrhs_ctx* c, double* norms) {
   CU(cudaSetDevice(c->device));
   double* sums = nullptr;
   if (dev_alloc(&sums, 3)) return 1;
-  dg::ConstraintArgs a{c->u, c->invjac, c->gauge == DGRHS_GAUGE_HARMONIC ? nullptr : c->gH,
-                       c->D, sums};
-  switch (c->N) {
-#define X(NN)                                                                       \
-  case NN: {                                                                        \
-    constexpr int smem = (4 * dg::Cfg<NN>::npad + NN * NN) * 8;                     \
-    auto k = dg::gh_constraints_kernel<NN>;                                         \
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    k<<<c->nelem, 256, smem, c->stream>>>(a);                                       \
-  } break;
-    DG_FOR_EACH_N(X)
-#undef X
-  }
-  ++g_launches;
-  CU(cudaGetLastError());
+  if (dgrhs_nops(c->N)->constraints(c, sums)) return 1;
   double h[3];
   CU(cudaMemcpyAsync(h, sums, 24, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1955,16 +1594,7 @@ int dgrhs_partial_derivatives(int N, int C, const double* u, const double* invja
   CU(cudaMemcpy2D(j_d, (size_t)npad * 8, invjac, (size_t)n * 8, (size_t)n * 8, 9,
                   cudaMemcpyHostToDevice));
   dg::DerivArgs a{u_d, j_d, du_d, D_d, C, 3 * C, 0, 3};
-  switch (N) {
-#define X(NN)                                                      \
-  case NN:                                                         \
-    dg::partial_derivatives_kernel<NN><<<C, 256>>>(a);             \
-    break;
-    DG_FOR_EACH_N(X)
-#undef X
-  }
-  ++g_launches;
-  CU(cudaGetLastError());
+  if (dgrhs_nops(N)->partial_derivatives(&a, C, nullptr)) return 1;
   CU(cudaMemcpy2D(du, (size_t)n * 8, du_d, (size_t)npad * 8, (size_t)n * 8, 3 * C,
                   cudaMemcpyDeviceToHost));
   cudaFree(u_d);

@@ -1661,7 +1661,7 @@ struct LincombArgs {
   long long len2;  // number of double2
 };
 
-__global__ void __launch_bounds__(256) lincomb_kernel(LincombArgs p) {
+static __global__ void __launch_bounds__(256) lincomb_kernel(LincombArgs p) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   double2* __restrict__ u2 = reinterpret_cast<double2*>(p.u);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.len2;

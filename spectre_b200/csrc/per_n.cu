@@ -1,0 +1,270 @@
+// Every kernel instantiation of ONE number of grid points per dimension
+// (compile with -DDG_N=<2..12>; __graft_entry__.build() compiles the eleven
+// copies in parallel) and the launchers that queue them, exported to dgrhs.cu as
+// a table (DgNOps, ctx.cuh).
+#ifndef DG_N
+#error "compile with -DDG_N=<points per dimension>"
+#endif
+
+#include "ctx.cuh"
+
+namespace {
+
+template <int N>
+int launch_faces(dgrhs_ctx* c, int eb, int ee) {
+  if (ee <= eb) return 0;
+  if (!c->nbr_face && !c->aligned_table_ok)
+    return fail("neighbor table is not that of aligned blocks: call "
+                "dgrhs_set_neighbor_orientations");
+  // whole batch: every interface once; element ranges: the interior / boundary
+  // split of the multi-GPU schedule (see FaceArgs::pass)
+  int pass = 0, n_int = c->nelem;
+  if (!(eb == 0 && ee == c->nelem)) {
+    if (c->n_interior < 0)
+      return fail("element ranges need dgrhs_set_interior_count (interior elements first)");
+    n_int = c->n_interior;
+    if (eb == 0 && ee == n_int)
+      pass = 1;
+    else if (eb == n_int && ee == c->nelem)
+      pass = 2;
+    else
+      return fail("element range must be [0, n_interior) or [n_interior, n_elements)");
+  }
+  dg::FaceArgs a{c->u,    c->invjac, c->stat, c->nbr, c->nbr_face, c->halo_recv,
+                 c->corr, c->nelem,  n_int,   pass,   c->violations};
+  // Bjorhus faces and non-conforming mortars need no halo data: all of them are
+  // evaluated once per right-hand side, with whichever pass comes first, so that
+  // their corrections are in place before ANY volume kernel of this evaluation
+  const bool aux_now = c->aux_faces_eval != c->rhs_evals;
+  c->aux_faces_eval = c->rhs_evals;
+  const bool bjorhus_now = c->n_bjorhus_faces > 0 && aux_now;
+  if (bjorhus_now) {
+    CU(cudaEventRecord(c->aux_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
+    dg::BjorhusArgs b{c->u, c->invjac, c->stat, c->gH, c->gdH, c->coords, c->D, c->corr,
+                      c->bjorhus_faces, {}};
+    int gauge_mode = 1;
+    if (c->gauge == DGRHS_GAUGE_HARMONIC) gauge_mode = 0;
+    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+      const double* p = c->gauge_params;
+      b.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+      gauge_mode = 2;
+    }
+    constexpr int bT = (N * N + 31) / 32 * 32;
+    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->aux_stream>>>(b, gauge_mode);
+    dgrhs_internal_count_launch();
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->aux_join, c->aux_stream));
+  }
+  const long long total = (long long)c->nelem * 6 * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  else
+    dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  if (bjorhus_now) CU(cudaStreamWaitEvent(c->stream, c->aux_join, 0));
+  // mortar groups whose sides are all local run with the first pass; groups with a
+  // remote side need the halo: with the boundary pass (or the single full pass)
+  auto launch_mortars = [&](int first, int count) -> int {
+    if (count <= 0) return 0;
+    dg::MortarArgs m{c->u, c->invjac, c->stat, c->corr, c->mortar_faces, c->mortar_table,
+                     c->mortar_P, c->mortar_R, c->halo_recv, first};
+    constexpr int msmem = dg::mortar_smem_bytes<N>();
+    constexpr int mT = (N * N + 31) / 32 * 32;
+    if (c->system == DGRHS_SYSTEM_GH) {
+      auto k = dg::mortar_kernel<N, 1>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+      k<<<count, mT, msmem, c->stream>>>(m);
+    } else {
+      auto k = dg::mortar_kernel<N, 0>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+      k<<<count, mT, msmem, c->stream>>>(m);
+    }
+    dgrhs_internal_count_launch();
+    CU(cudaGetLastError());
+    return 0;
+  };
+  if (aux_now && launch_mortars(0, c->n_mortar_faces_local)) return 1;
+  if (pass != 1 &&
+      launch_mortars(c->n_mortar_faces_local, c->n_mortar_faces - c->n_mortar_faces_local))
+    return 1;
+  c->pdl_volume = g_pdl && !bjorhus_now && c->n_mortar_faces == 0;
+  return 0;
+}
+
+template <int N>
+int launch_gauge(dgrhs_ctx* c, double time) {
+  if (c->gauge != DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE) return 0;
+  if (!c->coords) return fail("AnalyticChristoffel(GaugeWave) gauge needs coordinates");
+  dg::GaugeWaveArgs g{c->coords, c->gH, c->gauge_params[0], c->gauge_params[1], time,
+                      c->nelem};
+  const long long total = (long long)c->nelem * c->n;
+  dg::gauge_wave_h_kernel<N><<<(int)((total + 255) / 256), 256, 0, c->stream>>>(g);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  // spatial derivative d_i H_b -> gdH component (i+1) + 4 b; d_0 H_b stays 0
+  dg::DerivArgs d{c->gH, c->invjac, c->gdH, c->D, 4, 16, 1, 4};
+  dg::partial_derivatives_kernel<N><<<c->nelem * 4, 256, 0, c->stream>>>(d);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N, int kGauge>
+int launch_gh_split(dgrhs_ctx* c, const dg::GhVolArgs& a, int eb, int ee) {
+  if (!c->ctxbuf &&
+      dev_alloc(&c->ctxbuf, (size_t)c->nelem * dg::kGhCtxComps * c->npad))
+    return 1;
+  dg::GhCtxArgs ca{c->u, c->stat, c->gH, c->gdH, c->coords, c->ctxbuf, a.dh, eb, ee};
+  const long long pts = (long long)(ee - eb) * c->n;
+  dg::gh_context_kernel<N, kGauge><<<(int)((pts + 255) / 256), 256, 0, c->stream>>>(ca);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  constexpr int smem = dg::SCfg<N>::smem_bytes;
+  auto k = dg::gh_stream_kernel<N>;
+  CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k<<<(ee - eb) * dg::Cfg<N>::nchunk, dg::Cfg<N>::T, smem, c->stream>>>(a, c->ctxbuf);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
+                  const dg::UpdateArgs& upd = dg::UpdateArgs{}) {
+  const bool pdl = c->pdl_volume;
+  c->pdl_volume = false;
+  if (ee <= eb) return 0;
+  const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
+  if (c->system == DGRHS_SYSTEM_GH) {
+    dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
+                    c->gH, c->gdH, c->D, c->coords, {}, eb, upd};
+    if constexpr (dg::SCfg<N>::fits && N <= 10) {
+      if (c->volume_variant == 1) {
+        if (c->gauge == DGRHS_GAUGE_HARMONIC) return launch_gh_split<N, 0>(c, a, eb, ee);
+        if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+          if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
+          const double* p = c->gauge_params;
+          a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+          return launch_gh_split<N, 2>(c, a, eb, ee);
+        }
+        return launch_gh_split<N, 1>(c, a, eb, ee);
+      }
+    }
+    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+      if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
+      const double* p = c->gauge_params;
+      a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+    }
+    constexpr int smem = dg::gh_volume_smem_bytes<N>();
+    if (c->gauge == DGRHS_GAUGE_HARMONIC) {
+      auto k = dg::gh_volume_kernel<N, 0>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
+    } else if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+      if (!c->coords) return fail("DampedHarmonic gauge needs inertial coordinates");
+      const double* p = c->gauge_params;
+      a.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+      auto k = dg::gh_volume_kernel<N, 2>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
+    } else {
+      auto k = dg::gh_volume_kernel<N, 1>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CU(launch_dependent(k, blocks, dg::Cfg<N>::T, smem, c->stream, pdl, a));
+    }
+  } else {
+    dg::SwVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr, c->D, eb,
+                    upd};
+    constexpr int smem = dg::sw_volume_smem_bytes<N>();
+    auto k = dg::sw_volume_kernel<N>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<blocks, dg::Cfg<N>::T, smem, c->stream>>>(a);
+  }
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_pack(dgrhs_ctx* c) {
+  if (c->n_send == 0) return 0;
+  dg::PackArgs a{c->u, c->invjac, c->stat, c->halo_map, c->halo_send, c->n_send};
+  const long long total = (long long)c->n_send * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::pack_halo_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(a);
+  else
+    dg::pack_halo_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_volume_p(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
+                    const dg::UpdateArgs* upd) {
+  return launch_volume<N>(c, dt, eb, ee, with_corr, upd ? *upd : dg::UpdateArgs{});
+}
+
+template <int N>
+int launch_filter(dgrhs_ctx* c) {
+  dg::FilterArgs a{c->u, c->filterF, c->C};
+  dg::exponential_filter_kernel<N><<<c->nelem * c->C, 256, 0, c->stream>>>(a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// H_a = -Gamma_a of a given state and its spatial derivatives (AnalyticChristoffel
+// gauge of a static solution, AnalyticChristoffel.cpp:76-147)
+template <int N>
+int launch_gauge_from_state(dgrhs_ctx* c, const double* state_dev) {
+  dg::GaugeFromStateArgs g{state_dev, c->gH, c->nelem};
+  const long long total = (long long)c->nelem * c->n;
+  dg::gauge_h_from_state_kernel<N><<<(int)((total + 255) / 256), 256, 0, c->stream>>>(g);
+  dgrhs_internal_count_launch();
+  dg::DerivArgs d{c->gH, c->invjac, c->gdH, c->D, 4, 16, 1, 4};
+  dg::partial_derivatives_kernel<N><<<c->nelem * 4, 256, 0, c->stream>>>(d);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_constraints(dgrhs_ctx* c, double* sums_dev) {
+  dg::ConstraintArgs a{c->u, c->invjac, c->gauge == DGRHS_GAUGE_HARMONIC ? nullptr : c->gH,
+                       c->D, sums_dev};
+  constexpr int smem = (4 * dg::Cfg<N>::npad + N * N) * 8;
+  auto k = dg::gh_constraints_kernel<N>;
+  CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k<<<c->nelem, 256, smem, c->stream>>>(a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_partial_derivatives(const dg::DerivArgs* a, int blocks, cudaStream_t stream) {
+  dg::partial_derivatives_kernel<N><<<blocks, 256, 0, stream>>>(*a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static const DgNOps kOps = {launch_faces<DG_N>,
+                     launch_gauge<DG_N>,
+                     launch_volume_p<DG_N>,
+                     launch_pack<DG_N>,
+                     launch_filter<DG_N>,
+                     launch_gauge_from_state<DG_N>,
+                     launch_constraints<DG_N>,
+                     launch_partial_derivatives<DG_N>};
+
+}  // namespace
+
+#define DG_CAT2(a, b) a##b
+#define DG_CAT(a, b) DG_CAT2(a, b)
+extern "C" const DgNOps* DG_CAT(dgrhs_internal_nops_, DG_N)(void) { return &kOps; }

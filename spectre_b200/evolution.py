@@ -199,6 +199,34 @@ def scalar_wave_problem(refinement, N):
                    (0.0,))
 
 
+def boundary_ghost_data(problem, part, t, halo_comps):
+    """[n_external][halo_comps][N^2]: exterior state = analytic solution on the
+    face, then the interior element's inverse-Jacobian row and gammas."""
+    N, f = problem.N, problem.N ** 2
+    C = 50 if problem.system == lib.SYSTEM_GH else 5
+    hc = halo_comps
+    ids = part.global_ids
+    out = np.zeros((len(part.external_faces), hc, f))
+    q = np.arange(f)
+    a, b = q % N, q // N
+    elems = sorted({le for le, _, _ in part.external_faces})
+    x = dict(zip(elems, problem.coords(ids[elems])))
+    J = dict(zip(elems, problem.inverse_jacobian(ids[elems])))
+    S = dict(zip(elems, problem.static(ids[elems])))
+    for k, (le, d, slot) in enumerate(part.external_faces):
+        dim, fixed = d // 2, (N - 1 if d % 2 else 0)
+        p = [fixed + N * (a + N * b), a + N * (fixed + N * b), a + N * (b + N * fixed)][dim]
+        out[k, :C] = problem._initial_data(x[le][:, p], t)
+        for i in range(3):
+            out[k, C + i] = J[le][dim + 3 * i, p]
+        if problem.system == lib.SYSTEM_GH:
+            out[k, C + 3] = S[le][1, p]
+            out[k, C + 4] = S[le][2, p]
+        else:
+            out[k, C + 3] = S[le][0, p]
+    return out
+
+
 class Evolution:
     """GTS evolution of one rank's share of a problem."""
 
@@ -264,31 +292,7 @@ class Evolution:
             self._halo = HaloExchange(self.part, per_face, dist, process_group)
 
     def boundary_ghost_data(self, problem, t):
-        """[n_external][halo_comps][N^2]: exterior state = analytic solution on the
-        face, then the interior element's inverse-Jacobian row and gammas."""
-        N, f = problem.N, problem.N ** 2
-        C = 50 if problem.system == lib.SYSTEM_GH else 5
-        hc = self.ctx.halo_comps
-        ids = self.part.global_ids
-        out = np.zeros((len(self.part.external_faces), hc, f))
-        q = np.arange(f)
-        a, b = q % N, q // N
-        elems = sorted({le for le, _, _ in self.part.external_faces})
-        x = dict(zip(elems, problem.coords(ids[elems])))
-        J = dict(zip(elems, problem.inverse_jacobian(ids[elems])))
-        S = dict(zip(elems, problem.static(ids[elems])))
-        for k, (le, d, slot) in enumerate(self.part.external_faces):
-            dim, fixed = d // 2, (N - 1 if d % 2 else 0)
-            p = [fixed + N * (a + N * b), a + N * (fixed + N * b), a + N * (b + N * fixed)][dim]
-            out[k, :C] = problem._initial_data(x[le][:, p], t)
-            for i in range(3):
-                out[k, C + i] = J[le][dim + 3 * i, p]
-            if problem.system == lib.SYSTEM_GH:
-                out[k, C + 3] = S[le][1, p]
-                out[k, C + 4] = S[le][2, p]
-            else:
-                out[k, C + 3] = S[le][0, p]
-        return out
+        return boundary_ghost_data(problem, self.part, t, self.ctx.halo_comps)
 
     # -- one RHS + update ------------------------------------------------
     def _substep(self) -> bool:

@@ -111,10 +111,13 @@ def test_gh_rhs_random_physical_state():
     ctx.close()
 
 
-def test_gh_rhs_gauge_fields():
-    N = 6
-    rng = np.random.default_rng(9)
-    brick, x, u, J, stat = _gh_problem(rng, N, 1)
+@pytest.mark.parametrize("N,refine", [(6, 1), (8, 1), (9, 0), (10, 1), (11, 0), (12, 1)])
+def test_gh_rhs_gauge_fields(N, refine):
+    """The gauge-fields instantiation of the volume kernel (H_a, d_a H_b from memory:
+    the AnalyticChristoffel gauge of the Kerr-Schild configs) at every N the
+    Kerr-Schild configs use; N >= 10 runs 256-point chunks, one CTA per SM."""
+    rng = np.random.default_rng(9 + N)
+    brick, x, u, J, stat = _gh_problem(rng, N, refine)
     nb = brick.neighbors()
     H = rng.uniform(-1, 1, (brick.n_elements, 4, brick.n))
     dH = rng.uniform(-1, 1, (brick.n_elements, 16, brick.n))
@@ -124,11 +127,12 @@ def test_gh_rhs_gauge_fields():
     ctx.set_gauge(lib.GAUGE_FIELDS)
     ctx.set_gauge_fields(H, dH)
     ctx.set_state(u)
-    ctx.compute_time_derivative(0.0)
-    got = ctx.get_time_derivative()
-    ref = orc.dg_rhs(1, N, u, J, np.concatenate([stat, H, dH], axis=1), nb,
-                     gauge_params=orc.GAUGE_GIVEN)
-    assert _relerr(got, ref, GH_BLOCKS) < TOL
+    for volume_only in (True, False):
+        ctx.compute_time_derivative(0.0, volume_only=volume_only)
+        got = ctx.get_time_derivative()
+        ref = orc.dg_rhs(1, N, u, J, np.concatenate([stat, H, dH], axis=1), nb,
+                         gauge_params=orc.GAUGE_GIVEN, volume_only=volume_only)
+        assert _relerr(got, ref, GH_BLOCKS) < TOL
     ctx.close()
 
 

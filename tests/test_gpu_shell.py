@@ -34,7 +34,8 @@ def _gauge_fields(N, x, J, u0):
 
 
 @pytest.mark.parametrize("N,refinement,layers", [(5, (0, 0), ()), (4, (1, 1), (2.1,)),
-                                                 (8, (1, 0), ())])
+                                                 (8, (1, 0), ()), (10, (0, 1), ()),
+                                                 (12, (0, 0), ()), (12, (1, 0), ())])
 def test_gh_rhs_on_shell_matches_oracle(N, refinement, layers):
     problem = evolution.gh_kerr_schild_shell_problem(refinement, N, radial_partitioning=layers)
     ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, 1e-4)
@@ -134,6 +135,46 @@ def test_kerr_schild_yaml_configuration():
     cg = ctx.gh_constraint_norms()
     co = orc.gh_constraint_norms(N, got, J, H)
     np.testing.assert_allclose(cg, co, rtol=1e-9, atol=1e-14)
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,order", [(10, 3), (12, 3)])
+def test_kerr_schild_shell_evolution_north_star_points(N, order):
+    """BASELINE configs[2]/[3] at their own numbers of grid points (P = 9 / P = 11):
+    Kerr-Schild shell, DirichletAnalytic on both spheres, AnalyticChristoffel gauge
+    (the gauge-fields kernel), AB3 with the exponential filter of KerrSchild.yaml
+    :127-132; self-start + 5 steps against the oracle, evolved tensors and the
+    three constraint norms."""
+    dt = 1e-4
+    problem = evolution.gh_kerr_schild_shell_problem((0, 0), N)
+    ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, order, dt)
+    ctx, part = ev.ctx, ev.part
+    ctx.set_exponential_filter(True, 36.0, 64)
+    ids = part.global_ids
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    u0 = problem.u0(ids, 0.0)
+    H, dH = _gauge_fields(N, x, J, u0)
+    ext = ev.boundary_ghost_data(problem, 0.0)[:, :50]
+    sf = np.concatenate([stat, H, dH], axis=1)
+    F = orc.exponential_filter_matrix(N, 36.0, 64)
+
+    def rhs(v, t):
+        return orc.dg_rhs(1, N, v, J, sf, part.local_neighbors, gauge_params=orc.GAUGE_GIVEN,
+                          ext_u=ext, nbr_dir=part.local_neighbor_direction,
+                          face_perm=part.local_face_permutation)
+    ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, order, 0.0, dt)
+    ev.take_steps(5)
+    oev = orc.Evolution(rhs, u0, 0.0, dt, f"AB{order}",
+                        post_update=lambda v: orc.apply_filter(N, v, F))
+    for _ in range(5):
+        oev.step()
+    got = ctx.get_state()
+    assert ctx.rhs_evaluations == oev.rhs_evals
+    assert _relerr(got, oev.u, GH_BLOCKS) < TOL
+    assert np.max(np.abs(got - u0)) < 1e-6      # exact static solution, spectral accuracy
+    cg = ctx.gh_constraint_norms()
+    co = orc.gh_constraint_norms(N, got, J, H)
+    np.testing.assert_allclose(cg, co, rtol=1e-8, atol=1e-13)
     ctx.close()
 
 
