@@ -5,17 +5,25 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...     # CPU arm (the oracle port)
 
-Workload (config.workload): BASELINE.json configs[1] -- GeneralizedHarmonic
-gauge wave on the periodic Brick [0,1]^3, 16^3 elements per GPU, N = P+1 = 8
-Legendre-Gauss-Lobatto points per dimension, Adams-Bashforth 3, dt = 2e-4,
-gamma0/1/2 = 1/-1/1, UpwindPenalty.  A "step" is one full AB3 time step of all
-elements = one RHS evaluation per grid point + the stepper update.  Multi-GPU
-runs are weak scaling (16^3 elements per rank, halo exchange over NCCL).
+Workload (config.workload), default = the north-star configuration, BASELINE.json
+configs[3]: GeneralizedHarmonic Kerr-Schild black hole (M = 1, a = 0) on the
+Sphere domain with excision, six equiangular wedges x 4^3 angular x 2^4 radial
+= 6144 elements per GPU, N = P+1 = 12 Legendre-Gauss-Lobatto points per
+dimension (10.6 M grid points, 4.25 GB per state copy per GPU),
+DirichletAnalytic boundaries, AnalyticChristoffel gauge, GaussianPlusConstant
+damping, exponential filter, Adams-Bashforth 3 -- tests/InputFiles/
+GeneralizedHarmonic/KerrSchild.yaml:73-132 at the resolution of configs[3].
+A "step" is one full AB3 time step of all elements = one RHS evaluation per
+grid point + the stepper update + the filter.  Multi-GPU runs are weak scaling:
+the shell grows outwards by radial layers and is cut at constant radius, the
+cut mortar faces are exchanged over NCCL.  `--workload gauge-wave` is
+BASELINE.json configs[1] (GH gauge wave, 16^3 elements, N = 8), also measured
+in every default run and reported as `secondary` in the same JSON line.
 
 The JSON line carries: value (state resident in HBM), e2e (state copied
 host->device and back every step through the C-ABI), roofline of the dominant
 kernel (CUDA-event timed inside this run), cpu_baseline (oracle port on the
-host cores, bounded sample), clocks, gpu_launches.
+host cores, bounded sample of the same workload), clocks, gpu_launches.
 """
 from __future__ import annotations
 
@@ -35,6 +43,13 @@ sys.path.insert(0, ROOT)
 METRIC = "fp64 DG grid-point RHS updates/sec"
 UNIT = "grid-point-updates/s"
 
+WORKLOAD_DEFAULTS = {            # refine, points per dimension, CPU-sample refine
+    "kerr-schild-shell": (3, 12, 1),
+    "gauge-wave": (4, 8, 3),
+    "kerr-schild": (4, 12, 2),
+}
+FILTER = (36.0, 64)              # KerrSchild.yaml:127-132 (Alpha, HalfPower)
+
 
 def b_alg(N, n_u=50, G=3, T_f=6, k=3):
     """Algorithmic bytes per grid-point update, SURVEY.md 8(d)."""
@@ -45,11 +60,11 @@ def kernel_alg_bytes(N, n_u=50, n_static=3, k=3):
     """Compulsory bytes per grid point of each of OUR kernels:
     face: both sides' face values + 5 face statics in, lifted corrections out;
     volume: u, J^-1, statics, corrections in, dt_u out; update: u, k derivs in,
-    u out."""
+    u out; filter: u in, u out."""
     face = 8.0 * (6.0 / N) * (2 * (n_u + 5) + n_u)
     volume = 8.0 * (2 * n_u + 9 + n_static + (6.0 / N) * n_u)
     update = 8.0 * (k + 2) * n_u
-    return {"face": face, "volume": volume, "update": update}
+    return {"face": face, "volume": volume, "update": update, "filter": 8.0 * 2 * n_u}
 
 
 def peaks():
@@ -76,9 +91,11 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                 "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.3)     # let the sampler come up before the timed region
+            self.lines.clear()
         except Exception:
             self.proc = None
 
@@ -89,7 +106,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        lines = list(self.lines)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -97,7 +114,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -125,100 +142,6 @@ def weak_refinement(world, base):
     return ref
 
 
-# ---------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores (bounded sample of the workload)
-# ---------------------------------------------------------------------------
-def cpu_oracle_run(N, sample_refine, steps, warmup, dt, budget_s=25.0):
-    from oracle import oracle as orc
-    orc.use_optimized_build()   # -O3 -march=native timing build (never used for parity)
-    b = orc.Brick([0, 0, 0], [1, 1, 1], [sample_refine] * 3, N)
-    x, J, nb = b.coords(), b.inverse_jacobian(), b.neighbors()
-    u = np.stack([orc.gh_vars_from_metric(*orc.gauge_wave_metric(x[e], 0.0))
-                  for e in range(b.nelem)])
-    stat = np.zeros((b.nelem, 3, b.n))
-    stat[:, 0], stat[:, 1], stat[:, 2] = 1.0, -1.0, 1.0
-    ev = orc.Evolution(lambda v, t: orc.dg_rhs(1, N, v, J, stat, nb), u, 0.0, dt, "AB3")
-    for _ in range(warmup):
-        ev.step()
-    t0 = time.perf_counter()
-    done = 0
-    for _ in range(steps):
-        ev.step()
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    el = time.perf_counter() - t0
-    pts = b.nelem * b.n
-    return {"value": pts * done / el, "unit": UNIT, "cores": int(orc.lib().orc_num_threads()),
-            "kind": "port",
-            "sample": f"{b.nelem} elements (refinement {sample_refine}), N={N}, {done} AB3 steps "
-                      f"in {el:.1f} s, oracle/dg_oracle.c (gcc -O3 -march=native) + numpy update, "
-                      f"OpenMP over elements",
-            "steps": done, "ms_per_step": 1e3 * el / done}
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    r = cpu_oracle_run(args.points, args.cpu_sample_refine, args.steps, min(args.warmup, 1),
-                       args.dt, budget_s=60.0)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
-        "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 1),
-        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1, cpu=True),
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
-        "note": "reference Charm++ executable cannot be built here (no Charm++/Blaze/...): "
-                "this arm times the CPU restatement (oracle) of the same path",
-    }
-    print(json.dumps(line))
-
-
-def workload_config(args, world, cpu=False):
-    ref = weak_refinement(world, args.refine)
-    names = {
-        "gauge-wave": "BASELINE.json configs[1]: GeneralizedHarmonic gauge wave (A=0.1, "
-                      "lambda=1), periodic Brick [0,1]^3 per GPU (the domain grows by whole "
-                      "wavelengths with the GPU count), AB3, dt=2e-4, UpwindPenalty, "
-                      "gamma0/1/2=1/-1/1",
-        "kerr-schild": "BASELINE.json configs[2]/[3] stand-in: GeneralizedHarmonic Kerr-Schild "
-                       "(M=1, a=0) on a Brick lattice (elements of edge M/8 from x=2M), "
-                       "DirichletAnalytic boundaries, AnalyticChristoffel gauge, "
-                       "GaussianPlusConstant damping (KerrSchild.yaml), AB3, dt=2e-4",
-        "kerr-schild-shell": "BASELINE.json configs[2]/[3]: GeneralizedHarmonic Kerr-Schild "
-                             "(M=1, a=0) on the Sphere domain with excision (six equiangular "
-                             "wedges per layer, Logarithmic radial distribution, inner radius "
-                             "1.9 M, h-refined: 4^L angular x 2^Lr radial elements per wedge, "
-                             "the shell grows outwards with the GPU count and is cut at constant radius), "
-                             "DirichletAnalytic "
-                             "boundaries, AnalyticChristoffel gauge, GaussianPlusConstant "
-                             "damping (KerrSchild.yaml), AB3, dt=2e-4",
-    }
-    workload = getattr(args, "workload", "gauge-wave")
-    if workload == "kerr-schild-shell":
-        lr = shell_radial_level(args, world)
-        n_el = 6 * 4 ** args.refine * 2 ** lr // world
-        ref = [args.refine, args.refine, lr]
-    else:
-        n_el = (2 ** args.refine) ** 3
-    extra = {}
-    if workload == "kerr-schild-shell":
-        extra = {"inner_boundary": args.inner_boundary, "outer_boundary": args.outer_boundary}
-    return {
-        "workload": names[workload], **extra,
-        "elements_per_gpu": n_el, "refinement": ref,
-        "points_per_dim": args.points, "gauge": args.gauge, "stepper": "AdamsBashforth(3)",
-        "parallelism": f"elements partitioned along the block Z-curve over {world} GPU(s), "
-                       "mortar-face halo exchange (NCCL send/recv)",
-        "cache": "inputs larger than L2 (state 0.84 GB + 3 history slots per GPU; no flush "
-                 "needed)" if not cpu else "n/a (CPU arm)",
-    }
-
-
 def shell_radial_level(args, world):
     """Radial refinement level of the shell workload: 2^(refine+1) radial elements
     on one GPU, doubled with the GPU count (weak scaling); strong scaling: fixed
@@ -232,211 +155,351 @@ def shell_radial_level(args, world):
     return lr
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--refine", type=int, default=4, help="2^refine elements per dim per GPU")
-    ap.add_argument("--points", type=int, default=8, help="LGL points per dimension (N = P+1)")
-    ap.add_argument("--dt", type=float, default=2e-4)
-    ap.add_argument("--gauge", default="harmonic", choices=["harmonic", "analytic"])
-    ap.add_argument("--workload", default="gauge-wave", choices=["gauge-wave", "kerr-schild", "kerr-schild-shell"],
-                    help="gauge-wave: BASELINE configs[1] (default, the headline); kerr-schild: "
-                         "configs[2]/[3] stand-in (Kerr-Schild on a Brick lattice with "
-                         "DirichletAnalytic boundaries, AnalyticChristoffel gauge)")
-    ap.add_argument("--cpu-sample-refine", type=int, default=3)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-e2e-pipeline", action="store_true",
-                    help="measure e2e with blocking calls on one context only")
-    ap.add_argument("--outer-boundary", default="DirichletAnalytic",
-                    choices=["DirichletAnalytic", "ConstraintPreserving",
-                             "ConstraintPreservingPhysical"],
-                    help="kerr-schild-shell: boundary condition on the outer sphere")
-    ap.add_argument("--inner-boundary", default="DirichletAnalytic",
-                    choices=["DirichletAnalytic", "DemandOutgoingCharSpeeds"],
-                    help="kerr-schild-shell: boundary condition on the excision sphere")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="kerr-schild-shell: weak = 2^(refine+1) radial elements per GPU; "
-                         "strong = 2^(refine+1) * strong-factor radial elements in total")
-    ap.add_argument("--strong-factor", type=int, default=4)
-    ap.add_argument("--volume-variant", type=int, default=0,
-                    help="dgrhs_set_split_volume: 0 default, 1 split kernels, 2 pair-staged "
-                         "kernel for N >= 10 (A/B comparisons)")
-    ap.add_argument("--verify", action="store_true",
-                    help="multi-GPU: compare the gathered state bit-for-bit with a single-GPU "
-                         "evolution of the same global problem on rank 0 (small configs)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+def shell_problem(evolution, refine, lr, N, inner_boundary="DirichletAnalytic",
+                  outer_boundary="DirichletAnalytic"):
+    # radial element ratio q such that elements are a quarter as deep as they are
+    # wide at every radius; the outer radius grows with the number of radial elements
+    q = 1.0 + 0.125 * np.pi / 2 ** refine
+    return evolution.gh_kerr_schild_shell_problem(
+        (refine, lr), N, inner_radius=1.9, outer_radius=1.9 * q ** (2 ** lr),
+        order="radial", inner_boundary=inner_boundary, outer_boundary=outer_boundary)
 
-    if args.impl == "reference":
-        run_reference(args)
-        return
 
-    import torch
-    from spectre_b200 import evolution, lib
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (bounded sample of the workload).
+# The Charm++ executables of the reference cannot be built here,
+# so this arm times the CPU restatement of the same path: oracle/dg_oracle.c
+# built -O3 -march=native, OpenMP over elements for the RHS, the AB3 update
+# (orc_lincomb) and the filter (orc_apply_filter), with every host thread.
+# ---------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+class CpuArm:
+    def __init__(self, workload, N, sample_refine, dt, use_filter):
+        import ctypes
+        from oracle import oracle as orc
+        self.orc, self.ct = orc, ctypes
+        self.L = orc.use_optimized_build()   # timing build (never used for parity)
+        # torchrun exports OMP_NUM_THREADS=1 to its workers: set the count ourselves
+        self.L.orc_set_num_threads(host_threads())
+        self.threads = int(self.L.orc_num_threads())
+        self.N, self.dt = N, dt
+        if workload == "kerr-schild-shell":
+            from spectre_b200 import domain, evolution
+            problem = shell_problem(evolution, sample_refine, sample_refine + 1, N)
+            part = domain.Partition(problem.neighbors, 1, 0,
+                                    boundary_slots=problem.dirichlet_analytic,
+                                    neighbor_direction=problem.orientations[0],
+                                    face_permutation=problem.orientations[1],
+                                    mortars=problem.mortars)
+            ids = part.global_ids
+            x, J = problem.coords(ids), problem.inverse_jacobian(ids)
+            u0 = problem.u0(ids, 0.0)
+            H = np.zeros((len(ids), 4, N ** 3))
+            dH = np.zeros((len(ids), 16, N ** 3))
+            for e in range(len(ids)):
+                H[e], dH[e] = orc.analytic_christoffel_gauge(N, u0[e], J[e])
+            sf = np.concatenate([problem.static(ids), H, dH], axis=1)
+            ext = evolution.boundary_ghost_data(problem, part, 0.0, 55)[:, :50]
+            nbr, nd, perm = (part.local_neighbors, part.local_neighbor_direction,
+                             part.local_face_permutation)
+            self.rhs = lambda v: orc.dg_rhs(1, N, v, J, sf, nbr, gauge_params=orc.GAUGE_GIVEN,
+                                            ext_u=ext, nbr_dir=nd, face_perm=perm)
+            self.u = np.ascontiguousarray(u0)
+            self.desc = (f"Kerr-Schild shell, refinement ({sample_refine}, {sample_refine + 1}): "
+                         f"{len(ids)} elements")
+        else:
+            b = orc.Brick([0, 0, 0], [1, 1, 1], [sample_refine] * 3, N)
+            x, J, nb = b.coords(), b.inverse_jacobian(), b.neighbors()
+            u0 = np.stack([orc.gh_vars_from_metric(*orc.gauge_wave_metric(x[e], 0.0))
+                           for e in range(b.nelem)])
+            stat = np.zeros((b.nelem, 3, b.n))
+            stat[:, 0], stat[:, 1], stat[:, 2] = 1.0, -1.0, 1.0
+            self.rhs = lambda v: orc.dg_rhs(1, N, v, J, stat, nb)
+            self.u = np.ascontiguousarray(u0)
+            self.desc = f"gauge wave, refinement {sample_refine}: {b.nelem} elements"
+        self.F = (np.ascontiguousarray(orc.exponential_filter_matrix(N, *FILTER))
+                  if use_filter else None)
+        self.points = self.u.shape[0] * N ** 3
+        self.hist = [self.rhs(self.u) for _ in range(2)]   # AB3 history (static start)
+
+    def step(self):
+        ct, orc = self.ct, self.orc
+        self.hist.append(self.rhs(self.u))
+        dt = self.dt
+        coefs = np.array([5.0 / 12.0 * dt, -4.0 / 3.0 * dt, 23.0 / 12.0 * dt])
+        ptrs = (ct.c_void_p * 3)(*[h.ctypes.data for h in self.hist])
+        self.L.orc_lincomb(ct.c_longlong(self.u.size), ct.c_double(1.0), orc._p(self.u), 3,
+                           orc._p(coefs), ptrs)
+        if self.F is not None:
+            self.L.orc_apply_filter(self.N, ct.c_longlong(self.u.shape[0] * self.u.shape[1]),
+                                    orc._p(self.F), orc._p(self.u))
+        self.hist.pop(0)
+
+    def run(self, steps, warmup, budget_s):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            self.step()
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        el = time.perf_counter() - t0
+        assert np.isfinite(self.u).all()
+        v = self.points * done / el
+        return {"value": v, "unit": UNIT, "cores": self.threads, "kind": "port",
+                "value_per_core": v / self.threads,
+                "sample": f"{self.desc}, N={self.N}, {done} AB3 steps"
+                          f"{' + filter' if self.F is not None else ''} in {el:.1f} s; "
+                          "oracle/dg_oracle.c (gcc -O3 -march=native), OpenMP over elements "
+                          f"for RHS, update and filter, {self.threads} threads",
+                "steps": done, "ms_per_step": 1e3 * el / done}
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference "
-                         "for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    pg = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-        pg = dist.group.WORLD
-    N = args.points
-    refinement = weak_refinement(world, args.refine)
-    if args.workload == "kerr-schild-shell":
-        # radial element ratio q such that elements are a quarter as deep as they are
-        # wide at every radius; the outer radius grows with the number of radial
-        # elements (4.1 M on one GPU, 868 M on eight for --refine 3)
+    if rank != 0:
+        return
+    arm = CpuArm(args.workload, args.points, args.cpu_sample_refine, args.dt,
+                 args.workload == "kerr-schild-shell" and not args.no_filter)
+    r = arm.run(args.steps, min(args.warmup, 1), budget_s=60.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 1),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1, cpu=True),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                           "value_per_core")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "reference Charm++ executable cannot be built here (no Charm++/Blaze/...): "
+                "this arm times the CPU restatement (oracle) of the same path on a bounded "
+                "sample of the workload (config.cpu_sample)",
+    }
+    print(json.dumps(line))
+
+
+WORKLOAD_NAMES = {
+    "gauge-wave": "BASELINE.json configs[1]: GeneralizedHarmonic gauge wave (A=0.1, "
+                  "lambda=1), periodic Brick [0,1]^3 per GPU (the domain grows by whole "
+                  "wavelengths with the GPU count), AB3, dt=2e-4, UpwindPenalty, "
+                  "gamma0/1/2=1/-1/1",
+    "kerr-schild": "BASELINE.json configs[2]/[3] stand-in: GeneralizedHarmonic Kerr-Schild "
+                   "(M=1, a=0) on a Brick lattice (elements of edge M/8 from x=2M), "
+                   "DirichletAnalytic boundaries, AnalyticChristoffel gauge, "
+                   "GaussianPlusConstant damping (KerrSchild.yaml), AB3, dt=2e-4",
+    "kerr-schild-shell": "BASELINE.json configs[3] (configs[2] geometry at P=11): "
+                         "GeneralizedHarmonic Kerr-Schild (M=1, a=0) on the Sphere domain with "
+                         "excision (six equiangular wedges per layer, Logarithmic radial "
+                         "distribution, inner radius 1.9 M, h-refined: 4^L angular x 2^Lr radial "
+                         "elements per wedge; weak scaling adds radial layers outwards and cuts "
+                         "the shell at constant radius), DirichletAnalytic boundaries, "
+                         "AnalyticChristoffel gauge, GaussianPlusConstant damping, exponential "
+                         "filter (KerrSchild.yaml:73-132), AB3, dt=2e-4",
+}
+
+
+def workload_config(args, world, cpu=False):
+    workload = args.workload
+    ref = weak_refinement(world, args.refine)
+    extra = {}
+    if workload == "kerr-schild-shell":
         lr = shell_radial_level(args, world)
-        q = 1.0 + 0.125 * np.pi / 2 ** args.refine
-        problem = evolution.gh_kerr_schild_shell_problem(
-            (args.refine, lr), N, inner_radius=1.9, outer_radius=1.9 * q ** (2 ** lr),
-            order="radial", inner_boundary=args.inner_boundary,
-            outer_boundary=args.outer_boundary)
-    elif args.workload == "kerr-schild":
+        n_el = 6 * 4 ** args.refine * 2 ** lr // world
+        ref = [args.refine, args.refine, lr]
+        extra = {"inner_boundary": args.inner_boundary, "outer_boundary": args.outer_boundary,
+                 "filter": None if args.no_filter else
+                 {"Alpha": FILTER[0], "HalfPower": FILTER[1]}}
+    else:
+        n_el = (2 ** args.refine) ** 3
+    gauge = "AnalyticChristoffel" if workload.startswith("kerr-schild") else args.gauge
+    state_gb = n_el * 50 * args.points ** 3 * 8 / 1e9
+    cfg = {
+        "workload": WORKLOAD_NAMES[workload], **extra,
+        "elements_per_gpu": n_el, "refinement": ref,
+        "points_per_dim": args.points, "gauge": gauge, "stepper": "AdamsBashforth(3)",
+        "parallelism": f"elements partitioned along the block Z-curve / by radius over {world} "
+                       "GPU(s), mortar-face halo exchange (NCCL send/recv)",
+        "cache": f"inputs larger than L2 (state {state_gb:.2f} GB + 3 history slots per GPU; no "
+                 "flush needed)" if not cpu else "n/a (CPU arm)",
+    }
+    if cpu:
+        sr = args.cpu_sample_refine
+        cfg["cpu_sample"] = (f"bounded sample of this workload: refinement "
+                             f"{(sr, sr + 1) if workload == 'kerr-schild-shell' else sr} "
+                             "instead of the full element count (same N, physics, stepper, filter)")
+    return cfg
+
+
+def make_problem(evolution, args, world):
+    N = args.points
+    if args.workload == "kerr-schild-shell":
+        return shell_problem(evolution, args.refine, shell_radial_level(args, world), N,
+                             args.inner_boundary, args.outer_boundary)
+    refinement = weak_refinement(world, args.refine)
+    if args.workload == "kerr-schild":
         # element size fixed (1/8 M per element edge), lattice grows with the GPU count
         ne = [2 ** r for r in refinement]
-        problem = evolution.gh_kerr_schild_problem(
+        return evolution.gh_kerr_schild_problem(
             refinement, N, lower=(2.0, 2.0, 2.0), upper=tuple(2.0 + 0.125 * n for n in ne))
-    else:
-        # weak scaling keeps the element size of the single-GPU run (1/2^refine): the
-        # periodic domain grows by whole wavelengths, so dt stays inside the AB3 limit
-        upper = tuple(float(2 ** (r - args.refine)) for r in refinement)
-        problem = evolution.gh_gauge_wave_problem(refinement, N, upper=upper)
-    gauge = lib.GAUGE_HARMONIC if args.gauge == "harmonic" else lib.GAUGE_ANALYTIC_GAUGE_WAVE
-    ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, args.dt, 0.0, gauge,
-                             (0.1, 1.0) if args.gauge == "analytic" else (), local_rank, world,
-                             rank, pg)
-    ctx = ev.ctx
-    if args.volume_variant:
-        ctx.set_split_volume(args.volume_variant)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{local_rank}")
+    # weak scaling keeps the element size of the single-GPU run (1/2^refine): the
+    # periodic domain grows by whole wavelengths, so dt stays inside the AB3 limit
+    upper = tuple(float(2 ** (r - args.refine)) for r in refinement)
+    return evolution.gh_gauge_wave_problem(refinement, N, upper=upper)
 
-    def barrier():
-        ctx.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
+
+class GpuRun:
+    """One workload on this rank's GPU: set-up, timed steps, per-kernel roofline."""
+
+    def __init__(self, args, world, rank, local_rank, pg):
+        import torch
+        from spectre_b200 import evolution, lib
+        self.torch, self.lib, self.evolution = torch, lib, evolution
+        self.args, self.world, self.rank, self.local_rank, self.pg = args, world, rank, local_rank, pg
+        self.problem = make_problem(evolution, args, world)
+        self.gauge = (lib.GAUGE_HARMONIC if args.gauge == "harmonic"
+                      else lib.GAUGE_ANALYTIC_GAUGE_WAVE)
+        self.gauge_params = (0.1, 1.0) if args.gauge == "analytic" else ()
+        self.use_filter = args.workload == "kerr-schild-shell" and not args.no_filter
+        self.ev = self.new_evolution()
+        self.ctx = self.ev.ctx
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=f"cuda:{local_rank}")
+
+    def new_evolution(self):
+        lib = self.lib
+        ev = self.evolution.Evolution(self.problem, lib.STEPPER_ADAMS_BASHFORTH, 3, self.args.dt,
+                                      0.0, self.gauge, self.gauge_params, self.local_rank,
+                                      self.world, self.rank, self.pg)
+        if self.use_filter:
+            ev.ctx.set_exponential_filter(True, *FILTER)
+        if self.args.volume_variant:
+            ev.ctx.set_split_volume(self.args.volume_variant)
+        return ev
+
+    def barrier(self):
+        self.ctx.synchronize()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
-            torch.cuda.synchronize()
+            self.torch.cuda.synchronize()
 
-    # self-start (not timed: SURVEY 8d "exclude init, self-start") + warm-up
-    ev.take_steps(args.warmup)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = lib.kernel_launch_count()
-    evals0 = ctx.rhs_evaluations
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    ev.take_steps(args.steps)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = lib.kernel_launch_count() - launches0
-    rhs_evals = ctx.rhs_evaluations - evals0
-    assert rhs_evals == args.steps
-    if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    total_points = ev.n_points * world
-    value = total_points * args.steps / (ms * 1e-3)
+    def timed_steps(self, steps, warmup, sample_clocks):
+        torch, lib, ev = self.torch, self.lib, self.ev
+        # self-start (not timed: SURVEY 8d "exclude init, self-start") + warm-up
+        ev.take_steps(warmup)
+        self.barrier()
+        sampler = ClockSampler(self.local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        launches0 = lib.kernel_launch_count()
+        evals0 = self.ctx.rhs_evaluations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        ev.take_steps(steps)
+        e1.record(self.stream)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        launches = lib.kernel_launch_count() - launches0
+        assert self.ctx.rhs_evaluations - evals0 == steps
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=f"cuda:{self.local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
 
-    # sanity: the state must still be finite and close to the exact solution
-    state = ctx.get_state()
-    assert np.isfinite(state).all(), "state is not finite after the timed run"
-    exact = problem.u0(ev.part.global_ids[:8], ctx.time)
-    err = float(np.max(np.abs(state[:8] - exact)))
-    assert err < 1e-3, f"solution drifted from the exact solution: {err}"
+    def check_state(self):
+        """The state must still be finite and close to the exact solution."""
+        state = self.ctx.get_state()
+        assert np.isfinite(state).all(), "state is not finite after the timed run"
+        ids = self.ev.part.global_ids
+        sel = np.unique(np.linspace(0, len(ids) - 1, 16).astype(int))
+        exact = self.problem.u0(ids[sel], self.ctx.time)
+        err = float(np.max(np.abs(state[sel] - exact)))
+        assert err < 1e-3, f"solution drifted from the exact solution: {err}"
+        return state, err
 
-    if args.verify and world > 1:
-        n_global = problem.brick.n_elements
-        steps_total = args.warmup + args.steps
-        gathered = ev.gather_state(n_global)
-        if rank == 0:
-            ref_ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, args.dt, 0.0,
-                                         gauge, (0.1, 1.0) if args.gauge == "analytic" else (),
-                                         local_rank)
-            ref_ev.take_steps(steps_total)
-            same = np.array_equal(ref_ev.gather_state(n_global), gathered)
-            print(f"[verify] {world}-rank state bit-identical to single-GPU state: {same}",
-                  file=sys.stderr)
-            assert same, "multi-GPU evolution differs from the single-GPU evolution"
-            ref_ev.ctx.close()
-
-    # per-kernel roofline (CUDA events inside the library, same stream)
-    kms = ctx.time_kernels(reps=5, update_terms=3)
-    peak, peak_src = peaks()
-    # static per-point fields read by the volume kernel: 3 damping fields, +20
-    # when the gauge source function comes from memory (G = 23)
-    G = 23 if (args.workload.startswith("kerr-schild") or args.gauge == "analytic") else 3
-    kb = kernel_alg_bytes(N, n_static=G)
-    kb["volume_update_fused"] = kb["volume"] + kb["update"]
-    names = ["face", "volume", "update", "volume_update_fused"]
-    # the step launches the face kernel and the fused volume+update kernel; the
-    # separate volume / update timings are reported for comparison only
-    in_step = ["face", "volume_update_fused"]
-    kms_d = {n: float(m) for n, m in zip(names, kms)}
-    dom_name = max(in_step, key=lambda n: kms_d[n])
-    pts_local = ev.n_points
-    achieved = kb[dom_name] * pts_local / (kms_d[dom_name] * 1e-3) / 1e9
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        kname = {"face": "gh_face_kernel",
-                 "volume_update_fused": "gh_volume_kernel (stepper update fused)"}[dom_name]
-        traffic = tj.get(f"{kname}|{N}|{ev.part.n_local}")
-    except Exception:
+    def roofline(self, value):
+        args, N = self.args, self.args.points
+        kms = self.ctx.time_kernels(reps=5, update_terms=3)
+        peak, peak_src = peaks()
+        # static per-point fields read by the volume kernel: 3 damping fields, +20
+        # when the gauge source function comes from memory (SURVEY 8d: G = 23)
+        G = 23 if (args.workload.startswith("kerr-schild") or args.gauge == "analytic") else 3
+        kb = kernel_alg_bytes(N, n_static=G)
+        kb["volume_update_fused"] = kb["volume"] + kb["update"]
+        names = ["face", "volume", "update", "volume_update_fused", "filter"]
+        # the step launches the face kernel, the fused volume+update kernel and (if
+        # enabled) the filter; the separate volume / update timings are for comparison
+        in_step = ["face", "volume_update_fused"] + (["filter"] if self.use_filter else [])
+        kms_d = {n: float(m) for n, m in zip(names, kms)}
+        dom = max(in_step, key=lambda n: kms_d[n])
+        pts = self.ev.n_points
+        achieved = kb[dom] * pts / (kms_d[dom] * 1e-3) / 1e9
+        kname = {"face": "gh_face_kernel", "filter": "exponential_filter_kernel",
+                 "volume_update_fused": "gh_volume_kernel (stepper update fused)"}[dom]
         traffic = None
-    roofline = {
-        "bound": "hbm",
-        "kernel": {"face": "gh_face_kernel",
-                   "volume_update_fused": "gh_volume_kernel (stepper update fused)"}[dom_name],
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "alg_bytes_per_launch": kb[dom_name] * pts_local,
-        "alg_bytes_note": "SURVEY 8(d) accounting: volume group + update group (the fused "
-                          "kernel actually moves less: u and dt_u are not re-read)",
-        "kernels_ms": kms_d,
-        "kernels_frac": {n: kb[n] * pts_local / (kms_d[n] * 1e-3) / 1e9 / peak for n in names},
-        "step": {"b_alg_bytes_per_update": b_alg(N, G=G),
-                 "achieved": value / world * b_alg(N, G=G) / 1e9,
-                 "frac": value / world * b_alg(N, G=G) / 1e9 / peak,
-                 "note": "whole step per GPU against SURVEY.md 8(d) B_alg"},
-    }
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(f"{kname}|{N}|{self.ev.part.n_local}")
+        except Exception:
+            traffic = None
+        step_time = sum(kms_d[n] for n in in_step)
+        b = b_alg(N, G=G)
+        step = {"b_alg_bytes_per_update": b, "achieved": value / self.world * b / 1e9,
+                "frac": value / self.world * b / 1e9 / peak,
+                "note": "whole step per GPU against SURVEY.md 8(d) B_alg"}
+        if self.use_filter:
+            bf = b + kb["filter"]
+            step["note"] += ("; the step also runs the exponential filter pass (read u, write "
+                             "u = 800 B/update) that B_alg does not count: frac_incl_filter_bytes "
+                             "adds those bytes")
+            step["frac_incl_filter_bytes"] = value / self.world * bf / 1e9 / peak
+        return {
+            "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "alg_bytes_per_launch": kb[dom] * pts,
+            "alg_bytes_note": "SURVEY 8(d) accounting: volume group + update group (the fused "
+                              "kernel actually moves less: u and dt_u are not re-read)",
+            "kernels_ms": kms_d,
+            "kernels_share_of_step": {n: kms_d[n] / step_time for n in in_step},
+            "kernels_frac": {n: (kb[n] * pts / (kms_d[n] * 1e-3) / 1e9 / peak
+                                 if kms_d[n] > 0 else None) for n in names},
+            "step": step,
+        }
 
-    # end to end through the C-ABI with host buffers: state H2D + one step + D2H
-    e2e = None
-    if not args.no_e2e:
+    def e2e(self, state, total_points):
+        """End to end through the C-ABI with host buffers: state H2D + one step + D2H."""
+        import ctypes
+        torch, lib, args, ev, ctx = self.torch, self.lib, self.args, self.ev, self.ctx
+        world = self.world
         nbytes = state.nbytes
         host = torch.empty(state.size, dtype=torch.float64, pin_memory=True)
         host_np = host.numpy().reshape(state.shape)
         host_np[...] = state
-        import ctypes
         L = lib.load()
         k_e2e = max(3, min(args.steps, 5))
-        barrier()
+        self.barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
             lib._check(L.dgrhs_set_state(ctx._h, ctypes.c_void_p(host.data_ptr())))
             ev.take_steps(1)
             lib._check(L.dgrhs_get_state(ctx._h, ctypes.c_void_p(host.data_ptr())))
-        barrier()
+        self.barrier()
         el = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([el], device=f"cuda:{local_rank}", dtype=torch.float64)
+            import torch.distributed as dist
+            t = torch.tensor([el], device=f"cuda:{self.local_rank}", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
         e2e = {"value": total_points * k_e2e / el, "unit": UNIT,
@@ -448,9 +511,7 @@ def main():
             # batch i+1 uploads while batch i steps and downloads (PCIe is full duplex);
             # every batch still crosses the bus both ways inside the timed region
             serial = e2e["value"]
-            ev_b = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, args.dt, 0.0, gauge,
-                                       (0.1, 1.0) if args.gauge == "analytic" else (), local_rank,
-                                       world, rank, pg)
+            ev_b = self.new_evolution()
             ev_b.take_steps(args.warmup)          # self-start outside the timed region
             host_b = torch.empty(state.size, dtype=torch.float64, pin_memory=True)
             host_b_np = host_b.numpy().reshape(state.shape)
@@ -477,12 +538,142 @@ def main():
                                 "dgrhs_get_state_async, two contexts double-buffered so one "
                                 "batch uploads while the other steps and downloads; "
                                 "serial_value = one context, blocking calls"})
-            del ev_b
+            ev_b.ctx.close()
+        return e2e
+
+    def verify(self, steps_total):
+        """Multi-GPU: gathered state bit-for-bit against a single-GPU evolution."""
+        lib = self.lib
+        n_global = self.problem.brick.n_elements
+        gathered = self.ev.gather_state(n_global)
+        if self.rank == 0:
+            ref_ev = self.evolution.Evolution(self.problem, lib.STEPPER_ADAMS_BASHFORTH, 3,
+                                              self.args.dt, 0.0, self.gauge, self.gauge_params,
+                                              self.local_rank)
+            if self.use_filter:
+                ref_ev.ctx.set_exponential_filter(True, *FILTER)
+            ref_ev.take_steps(steps_total)
+            same = np.array_equal(ref_ev.gather_state(n_global), gathered)
+            print(f"[verify] {self.world}-rank state bit-identical to single-GPU state: {same}",
+                  file=sys.stderr)
+            assert same, "multi-GPU evolution differs from the single-GPU evolution"
+            ref_ev.ctx.close()
+
+
+def secondary_line(args, world, rank, local_rank, pg):
+    """BASELINE.json configs[1] in the same run (short): value, step time, roofline."""
+    sub = argparse.Namespace(**vars(args))
+    sub.workload = "gauge-wave"
+    sub.refine, sub.points, sub.cpu_sample_refine = WORKLOAD_DEFAULTS["gauge-wave"]
+    sub.gauge, sub.scaling = "harmonic", "weak"
+    run = GpuRun(sub, world, rank, local_rank, pg)
+    steps = 50
+    ms, launches, _ = run.timed_steps(steps, 3, sample_clocks=False)
+    total_points = run.ev.n_points * world
+    value = total_points * steps / (ms * 1e-3)
+    _, err = run.check_state()
+    roof = run.roofline(value)
+    run.ctx.close()
+    return {"config": workload_config(sub, world), "value": value, "unit": UNIT, "steps": steps,
+            "ms_per_step": ms / steps, "gpu_launches": int(launches),
+            "roofline": {k: roof[k] for k in ("kernel", "achieved", "peak", "frac", "kernels_ms",
+                                              "step")},
+            "max_abs_error_vs_exact": err}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kerr-schild-shell",
+                    choices=["gauge-wave", "kerr-schild", "kerr-schild-shell"],
+                    help="kerr-schild-shell: BASELINE configs[3], the north-star configuration "
+                         "(default); gauge-wave: configs[1]; kerr-schild: Brick-lattice stand-in")
+    ap.add_argument("--refine", type=int, default=None,
+                    help="shell: 4^refine angular x 2^(refine+1) radial elements per wedge and "
+                         "GPU (default 3: 6144 elements); bricks: 2^refine elements per dim "
+                         "per GPU (default 4)")
+    ap.add_argument("--points", type=int, default=None,
+                    help="LGL points per dimension N = P+1 (default: 12 shell, 8 gauge wave)")
+    ap.add_argument("--dt", type=float, default=2e-4)
+    ap.add_argument("--gauge", default="harmonic", choices=["harmonic", "analytic"],
+                    help="gauge-wave workload only (the Kerr-Schild workloads use "
+                         "AnalyticChristoffel)")
+    ap.add_argument("--no-filter", action="store_true",
+                    help="kerr-schild-shell: switch the exponential filter off")
+    ap.add_argument("--cpu-sample-refine", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the configs[1] measurement reported as `secondary`")
+    ap.add_argument("--no-e2e-pipeline", action="store_true",
+                    help="measure e2e with blocking calls on one context only")
+    ap.add_argument("--outer-boundary", default="DirichletAnalytic",
+                    choices=["DirichletAnalytic", "ConstraintPreserving",
+                             "ConstraintPreservingPhysical"],
+                    help="kerr-schild-shell: boundary condition on the outer sphere")
+    ap.add_argument("--inner-boundary", default="DirichletAnalytic",
+                    choices=["DirichletAnalytic", "DemandOutgoingCharSpeeds"],
+                    help="kerr-schild-shell: boundary condition on the excision sphere")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="kerr-schild-shell: weak = 2^(refine+1) radial elements per GPU; "
+                         "strong = 2^(refine+1) * strong-factor radial elements in total")
+    ap.add_argument("--strong-factor", type=int, default=4)
+    ap.add_argument("--volume-variant", type=int, default=0,
+                    help="dgrhs_set_split_volume: 0 default, 1 split kernels (A/B comparisons)")
+    ap.add_argument("--verify", action="store_true",
+                    help="multi-GPU: compare the gathered state bit-for-bit with a single-GPU "
+                         "evolution of the same global problem on rank 0 (small configs)")
+    args = ap.parse_args()
+    d_refine, d_points, d_sample = WORKLOAD_DEFAULTS[args.workload]
+    args.refine = d_refine if args.refine is None else args.refine
+    args.points = d_points if args.points is None else args.points
+    args.cpu_sample_refine = d_sample if args.cpu_sample_refine is None else args.cpu_sample_refine
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference "
+                         "for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        pg = dist.group.WORLD
+
+    run = GpuRun(args, world, rank, local_rank, pg)
+    ms, launches, clocks = run.timed_steps(args.steps, args.warmup, sample_clocks=rank == 0)
+    total_points = run.ev.n_points * world
+    value = total_points * args.steps / (ms * 1e-3)
+    state, err = run.check_state()
+    if args.verify and world > 1:
+        run.verify(args.warmup + args.steps)
+    roofline = run.roofline(value)
+    e2e = None if args.no_e2e else run.e2e(state, total_points)
+    del state
+    run.ctx.close()
+
+    secondary = None
+    if args.workload == "kerr-schild-shell" and not args.no_secondary:
+        secondary = secondary_line(args, world, rank, local_rank, pg)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_oracle_run(N, args.cpu_sample_refine, 40, 1, args.dt, budget_s=20.0)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        arm = CpuArm(args.workload, args.points, args.cpu_sample_refine, args.dt, run.use_filter)
+        cpu = arm.run(40, 1, budget_s=20.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "value_per_core")}
 
     if rank == 0:
         line = {
@@ -492,10 +683,11 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "max_abs_error_vs_exact": err,
+            "max_abs_error_vs_exact": err, "secondary": secondary,
         }
         print(json.dumps(line))
     if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 

@@ -148,7 +148,9 @@ int dgrhs_compute_time_derivative(dgrhs_ctx* ctx, double time, int volume_only);
 
 /* Multi-GPU split of the same call: elements [0, n_interior)
  * have no ghost faces.  Sequence per RHS: pack_halo -> exchange (caller, NCCL)
- * -> compute(interior) may overlap -> compute(boundary) after the exchange. */
+ * -> compute(interior) may overlap -> compute(boundary) after the exchange.
+ * An empty range is a no-op; the first non-empty range of an evaluation counts it
+ * (dgrhs_rhs_evaluations) and runs the once-per-RHS kernels. */
 int dgrhs_set_interior_count(dgrhs_ctx* ctx, int n_interior);
 int dgrhs_pack_halo(dgrhs_ctx* ctx);
 int dgrhs_compute_time_derivative_range(dgrhs_ctx* ctx, double time,
@@ -175,6 +177,30 @@ int dgrhs_set_boundary_ghost_data(dgrhs_ctx* ctx, int slot_begin, int n_slots,
 void* dgrhs_halo_send_ptr(dgrhs_ctx* ctx);
 void* dgrhs_halo_recv_ptr(dgrhs_ctx* ctx);
 int dgrhs_halo_comps(dgrhs_ctx* ctx);
+
+/* The exchange itself inside the library (one process per GPU, NCCL over NVLink):
+ * replaces send_data_for_fluxes (ComputeTimeDerivative.hpp:652-774: every element
+ * sends its mortar data to the neighbour's inbox) and
+ * receive_boundary_data_global_time_stepping (ApplyBoundaryCorrections.hpp:205-380)
+ * at batch granularity: ONE ncclSend/ncclRecv pair per peer rank and RHS carries
+ * every cut mortar face, on the context's communication stream, overlapped with the
+ * kernels of the elements that need no halo.
+ *   dgrhs_comm_unique_id  rank 0 creates the 128-byte ncclUniqueId and hands it to
+ *                         the other ranks by any means (file, MPI, torch.distributed)
+ *   dgrhs_comm_init       every rank, once (collective: ncclCommInitRank)
+ *   dgrhs_set_halo_peers  faces sent to / received from each rank [world]; the send
+ *                         buffer (order of dgrhs_set_halo_map) and the ghost slots are
+ *                         segmented by peer in rank order
+ *   dgrhs_exchange_halo   pack + exchange, the context's stream waits for the halo
+ *                         (callers that drive the substeps themselves)
+ * After dgrhs_comm_init, dgrhs_take_steps runs the whole multi-GPU schedule itself:
+ * pack -> NCCL exchange (comm stream) | interior faces + interior volume (main
+ * stream) | remaining faces (comm stream, after the halo) -> boundary volume. */
+int dgrhs_comm_unique_id(void* unique_id_128_bytes);
+int dgrhs_comm_init(dgrhs_ctx* ctx, const void* unique_id_128_bytes, int rank, int world);
+int dgrhs_set_halo_peers(dgrhs_ctx* ctx, const int32_t* send_counts,
+                         const int32_t* recv_counts);
+int dgrhs_exchange_halo(dgrhs_ctx* ctx);
 
 /* ---- time stepping (Time/TimeSteppers, Time/Actions) ------------------- */
 
@@ -290,8 +316,10 @@ int dgrhs_end_substep(dgrhs_ctx* ctx, int* is_step_done);
  * face kernel, the volume kernel and a k-term stepper update `reps` times
  * each on the context's stream, bracketed by CUDA events, and returns the mean
  * milliseconds per launch in ms[0..2]; ms[3] is the volume kernel with the
- * stepper update fused in (the kernel the steppers actually use).  Does not
- * change u (updates go to scratch buffers). */
+ * stepper update fused in (the kernel the steppers actually use); ms[4] is the
+ * exponential filter pass over a scratch copy of the state (0 if the filter is
+ * not enabled).  ms must hold 5 doubles.  Does not change u (updates and the
+ * filter go to scratch buffers). */
 int dgrhs_time_kernels(dgrhs_ctx* ctx, int reps, int update_terms, double* ms);
 
 /* GH constraint diagnostics of the current state, as the

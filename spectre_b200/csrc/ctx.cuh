@@ -116,6 +116,14 @@ struct dgrhs_ctx {
   SubstepOp cur_op{};
   bool in_substep = false;
   int64_t rhs_evals = 0;
+  int range_covered = 0;  // elements already evaluated in the current RHS (range calls)
+  // halo exchange inside the library (dgrhs_comm_init): NCCL communicator of the
+  // ranks that share the domain, one send/recv pair per peer and RHS on its own stream
+  void* nccl_comm = nullptr;  // ncclComm_t
+  int comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_faces2 = nullptr;
+  std::vector<int> send_counts, recv_counts;  // faces per peer (rank order)
   size_t state_len() const { return (size_t)nelem * C * npad; }
 };
 

@@ -447,6 +447,7 @@ extern "C" {
 // shared with operators.cu (not part of the public header)
 void dgrhs_internal_set_error(const char* msg) { g_error = msg; }
 void dgrhs_internal_count_launch(void) { ++g_launches; }
+void dgrhs_internal_comm_destroy(void* comm);
 
 const char* dgrhs_last_error(void) { return g_error.c_str(); }
 int64_t dgrhs_kernel_launch_count(void) { return g_launches; }
@@ -507,6 +508,14 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->nccl_comm) {
+    cudaStreamSynchronize(c->comm_stream);
+    dgrhs_internal_comm_destroy(c->nccl_comm);
+    cudaStreamDestroy(c->comm_stream);
+    cudaEventDestroy(c->ev_packed);
+    cudaEventDestroy(c->ev_halo);
+    cudaEventDestroy(c->ev_faces2);
+  }
   for (double* p : {c->u, c->invjac, c->coords, c->stat, c->corr, c->D, c->gH, c->gdH,
                     c->halo_send, c->halo_recv, c->u0, c->u_alt, c->ctxbuf, c->filterF})
     if (p) cudaFree(p);
@@ -1093,8 +1102,14 @@ int dgrhs_compute_time_derivative_range(dgrhs_ctx* c, double time, int eb, int e
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));
   if (eb < 0 || ee > c->nelem || eb > ee) return fail("bad element range");
-  if (eb == 0) ++c->rhs_evals;
-  return rhs_range(c, time, c->dt_last, eb, ee, false, eb == 0,
+  if (eb == ee) return 0;  // an empty range (e.g. no interior elements) is a no-op
+  // the first non-empty range of an RHS evaluation counts it and runs the gauge
+  // kernels; the evaluation is complete once every element has been covered
+  const bool first = c->range_covered == 0;
+  if (first) ++c->rhs_evals;
+  c->range_covered += ee - eb;
+  if (c->range_covered >= c->nelem) c->range_covered = 0;
+  return rhs_range(c, time, c->dt_last, eb, ee, false, first,
                    (c->in_substep && c->upd_active) ? c->pending_upd : dg::UpdateArgs{});
 }
 
@@ -1162,6 +1177,7 @@ int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
   CU(cudaSetDevice(c->device));
   if (c->in_substep) return fail("begin_substep called twice");
   if (c->dt == 0.0) return fail("set_stepper has not been called");
+  c->range_covered = 0;
   if (c->stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
     while (!c->pending.empty() && c->pending.front().kind == SubstepOp::kRestoreU0) {
       CU(cudaMemcpyAsync(c->u, c->u0, c->state_len() * 8, cudaMemcpyDeviceToDevice,
@@ -1363,18 +1379,215 @@ int dgrhs_end_substep(dgrhs_ctx* c, int* is_step_done) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Halo exchange inside the library: NCCL send/recv of the cut mortar faces
+// (reference: send_data_for_fluxes / receive_boundary_data_global_time_stepping,
+// ComputeTimeDerivative.hpp:652-774, ApplyBoundaryCorrections.hpp:205-380).
+// libnccl is resolved at run time (dlopen) so that single-GPU callers need no
+// NCCL and a process that already loaded a libnccl.so.2 (e.g. PyTorch's) shares it.
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.handle) return &api;
+  void* h = nullptr;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    fail("cannot load libnccl.so.2: %s", dlerror());
+    return nullptr;
+  }
+#define DG_NCCL_SYM(field, sym)                                   \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, sym)); \
+  if (!api.field) {                                               \
+    fail("libnccl lacks %s", sym);                                \
+    return nullptr;                                               \
+  }
+  DG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  DG_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  DG_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  DG_NCCL_SYM(Send, "ncclSend")
+  DG_NCCL_SYM(Recv, "ncclRecv")
+  DG_NCCL_SYM(GroupStart, "ncclGroupStart")
+  DG_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  DG_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef DG_NCCL_SYM
+  api.handle = h;
+  return &api;
+}
+
+#define NC(call)                                                                       \
+  do {                                                                                 \
+    ncclResult_t r__ = (call);                                                         \
+    if (r__ != ncclSuccess)                                                            \
+      return fail("%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r__), __FILE__, \
+                  __LINE__);                                                           \
+  } while (0)
+
+// queue the exchange of the packed faces on the communication stream
+int start_halo_exchange(dgrhs_ctx* c) {
+  NcclApi* nc = nccl_api();
+  if (!nc) return 1;
+  CU(cudaEventRecord(c->ev_packed, c->stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
+  const size_t per_face = (size_t)c->HC * c->f;
+  ncclComm_t comm = static_cast<ncclComm_t>(c->nccl_comm);
+  size_t so = 0, ro = 0;
+  NC(nc->GroupStart());
+  for (int peer = 0; peer < c->comm_world; ++peer) {
+    const size_t ns = (size_t)c->send_counts[peer], nr = (size_t)c->recv_counts[peer];
+    if (nr)
+      NC(nc->Recv(c->halo_recv + ro * per_face, nr * per_face, ncclDouble, peer, comm,
+                  c->comm_stream));
+    if (ns)
+      NC(nc->Send(c->halo_send + so * per_face, ns * per_face, ncclDouble, peer, comm,
+                  c->comm_stream));
+    so += ns;
+    ro += nr;
+  }
+  NC(nc->GroupEnd());
+  CU(cudaEventRecord(c->ev_halo, c->comm_stream));
+  return 0;
+}
+
+// One RHS evaluation of a rank that exchanges faces.  Streams:
+//   main: pack | faces of interior interfaces, volume of interior elements | (join) volume of
+//         boundary elements
+//   comm: (packed) NCCL send/recv | faces of the remaining interfaces (they need the halo
+//         and write corrections of boundary elements only, so they run NEXT TO the interior
+//         volume kernel instead of after it)
+int rhs_with_exchange(dgrhs_ctx* c, double t) {
+  const dg::UpdateArgs upd = c->upd_active ? c->pending_upd : dg::UpdateArgs{};
+  const DgNOps* ops = dgrhs_nops(c->N);
+  if (ops->pack(c)) return 1;
+  if (start_halo_exchange(c)) return 1;
+  ++c->rhs_evals;
+  const int ni = c->n_interior;
+  if (ni > 0 && rhs_range(c, t, c->dt_last, 0, ni, false, true, upd)) return 1;
+  if (ni == 0 && ops->gauge(c, t)) return 1;
+  {
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->comm_stream;  // the launcher queues on c->stream
+    const int rc = ops->faces(c, ni, c->nelem);
+    c->stream = main_stream;
+    c->pdl_volume = false;       // other work sits between these faces and the volume kernel
+    if (rc) return 1;
+  }
+  CU(cudaEventRecord(c->ev_faces2, c->comm_stream));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_faces2, 0));
+  return ops->volume(c, c->dt_last, ni, c->nelem, true, &upd);
+}
+
+}  // namespace
+
+extern "C" {
+
+void dgrhs_internal_comm_destroy(void* comm) {
+  if (NcclApi* nc = nccl_api()) nc->CommDestroy(static_cast<ncclComm_t>(comm));
+}
+
+int dgrhs_comm_unique_id(void* unique_id_128_bytes) {
+  NcclApi* nc = nccl_api();
+  if (!nc) return 1;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NC(nc->GetUniqueId(static_cast<ncclUniqueId*>(unique_id_128_bytes)));
+  return 0;
+}
+
+int dgrhs_comm_init(dgrhs_ctx* c, const void* unique_id_128_bytes, int rank, int world) {
+  CHECK_CTX(c);
+  if (world < 1 || rank < 0 || rank >= world) return fail("bad rank %d of %d", rank, world);
+  if (c->nccl_comm) return fail("communicator already initialised");
+  NcclApi* nc = nccl_api();
+  if (!nc) return 1;
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id_128_bytes, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NC(nc->CommInitRank(&comm, world, id, rank));
+  c->nccl_comm = comm;
+  c->comm_rank = rank;
+  c->comm_world = world;
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+  CU(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_faces2, cudaEventDisableTiming));
+  c->send_counts.assign(world, 0);
+  c->recv_counts.assign(world, 0);
+  return 0;
+}
+
+int dgrhs_set_halo_peers(dgrhs_ctx* c, const int32_t* send_counts, const int32_t* recv_counts) {
+  CHECK_CTX(c);
+  if (!c->nccl_comm) return fail("dgrhs_comm_init has not been called");
+  long long ns = 0, nr = 0;
+  for (int p = 0; p < c->comm_world; ++p) {
+    if (send_counts[p] < 0 || recv_counts[p] < 0) return fail("negative face count");
+    if (p == c->comm_rank && (send_counts[p] || recv_counts[p]))
+      return fail("a rank does not exchange faces with itself");
+    ns += send_counts[p];
+    nr += recv_counts[p];
+  }
+  if (ns != c->n_send) return fail("send counts sum to %lld, the halo map has %d faces", ns, c->n_send);
+  if (nr > c->nghost) return fail("recv counts sum to %lld, the context has %d ghost slots", nr, c->nghost);
+  c->send_counts.assign(send_counts, send_counts + c->comm_world);
+  c->recv_counts.assign(recv_counts, recv_counts + c->comm_world);
+  return 0;
+}
+
+int dgrhs_exchange_halo(dgrhs_ctx* c) {
+  CHECK_CTX(c);
+  if (!c->nccl_comm) return fail("dgrhs_comm_init has not been called");
+  CU(cudaSetDevice(c->device));
+  if (dgrhs_nops(c->N)->pack(c)) return 1;
+  if (start_halo_exchange(c)) return 1;
+  CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  return 0;
+}
+
 int dgrhs_take_steps(dgrhs_ctx* c, int n_steps) {
   CHECK_CTX(c);
-  if (c->n_send > 0)
-    return fail("context exchanges faces with other ranks: drive substeps from the caller");
+  const bool exchange = c->n_send > 0 || (c->nccl_comm && c->comm_world > 1);
+  if (exchange) {
+    if (!c->nccl_comm)
+      return fail("context exchanges faces with other ranks: call dgrhs_comm_init + "
+                  "dgrhs_set_halo_peers, or drive the substeps from the caller");
+    if (c->n_interior < 0) return fail("dgrhs_set_interior_count has not been called");
+  }
   for (int s = 0; s < n_steps;) {
     double t;
     int done = 0;
     if (dgrhs_begin_substep(c, &t)) return 1;
-    ++c->rhs_evals;
-    if (rhs_range(c, t, c->dt_last, 0, c->nelem, false, true,
-                  c->upd_active ? c->pending_upd : dg::UpdateArgs{}))
-      return 1;
+    if (exchange) {
+      if (rhs_with_exchange(c, t)) return 1;
+    } else {
+      ++c->rhs_evals;
+      if (rhs_range(c, t, c->dt_last, 0, c->nelem, false, true,
+                    c->upd_active ? c->pending_upd : dg::UpdateArgs{}))
+        return 1;
+    }
     if (dgrhs_end_substep(c, &done)) return 1;
     if (done) ++s;
   }
@@ -1429,6 +1642,27 @@ int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
       if (r >= 0) total += t;
     }
     ms[which] = total / reps;
+  }
+  // the filter pass (apply_matrices with three N x N matrices per component), on the
+  // scratch state so that u stays untouched
+  ms[4] = 0.0;
+  if (c->filterF) {
+    double* keep = c->u;
+    c->u = c->u_alt;
+    float total = 0.f;
+    int rc = 0;
+    for (int r = -1; r < reps && !rc; ++r) {
+      cudaEventRecord(e0, c->stream);
+      rc = apply_filter(c);
+      cudaEventRecord(e1, c->stream);
+      cudaEventSynchronize(e1);
+      float t;
+      cudaEventElapsedTime(&t, e0, e1);
+      if (r >= 0) total += t;
+    }
+    c->u = keep;
+    if (rc) return 1;
+    ms[4] = total / reps;
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

@@ -34,6 +34,16 @@ namespace dg {
 // --------------------------------------------------------------------------
 // configuration
 // --------------------------------------------------------------------------
+// Measured on B200 (profiles/README.md, round 2; ms per fused launch, base -> variant):
+// rows of the differentiation matrix from shared memory: N = 12 3.22 -> 3.07, N = 10 2.43 -> 2.59;
+// per-warp stage release: N = 12 3.19 -> 3.14 (2.93 with both), N = 10 2.44 -> 2.38, N = 8 1.20 -> 1.21
+#ifndef DG_SHARED_D_MIN_N
+#define DG_SHARED_D_MIN_N 12
+#endif
+#ifndef DG_WARP_RELEASE_MIN_N
+#define DG_WARP_RELEASE_MIN_N 10
+#endif
+
 template <int N>
 struct Cfg {
   static constexpr int n = N * N * N;
@@ -54,7 +64,16 @@ struct Cfg {
   static constexpr int nchunk = (n + chunk_max - 1) / chunk_max;
   static constexpr int T = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
   static constexpr int min_blocks = two_cta ? 2 : 1;
-  static constexpr int fixed_bytes = (10 * T + (N * N + 1) / 2 * 2) * 8 + 64;
+  // N >= DG_SHARED_D_MIN_N: the rows of the differentiation matrix are read from
+  // shared memory inside the pair loop (a transposed copy serves the xi direction
+  // without bank conflicts) instead of living in 6N registers per thread
+  static constexpr bool shared_D = N >= DG_SHARED_D_MIN_N;
+  // a ring stage is released per warp (counter in shared memory; the last warp to
+  // finish a pair issues the next TMA copies into its stage) instead of by a
+  // CTA-wide barrier per pair
+  static constexpr bool warp_release = N >= DG_WARP_RELEASE_MIN_N;
+  static constexpr int fixed_bytes =
+      (10 * T + (shared_D ? 2 : 1) * ((N * N + 1) / 2 * 2)) * 8 + 64;
   static constexpr int max_stages =
       (232448 / min_blocks - 1024 - fixed_bytes) / (stage_doubles * 8);
   static constexpr int nstage = max_stages >= 4 ? 4 : max_stages;
@@ -346,7 +365,11 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
   double* ring = reinterpret_cast<double*>(smem_raw);
   double* sQ = ring + NS * SD;
   double* sD = sQ + 10 * T;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (N * N + 1) / 2 * 2);
+  constexpr bool kSharedD = Cfg<N>::shared_D;
+  double* sDT = sD + (N * N + 1) / 2 * 2;  // transposed copy (kSharedD only)
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(sD + (kSharedD ? 2 : 1) * ((N * N + 1) / 2 * 2));
+  unsigned int* released = reinterpret_cast<unsigned int*>(bars + 4);  // [NS] warps done
 
   const int e = a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
   const int chunk = blockIdx.x % Cfg<N>::nchunk;
@@ -375,12 +398,18 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
   };
   if (tid == 0) {
 #pragma unroll
-    for (int st = 0; st < NS; ++st) mbar_init(&bars[st], 1);
+    for (int st = 0; st < NS; ++st) {
+      mbar_init(&bars[st], 1);
+      released[st] = 0u;
+    }
     mbar_fence_init();
 #pragma unroll
     for (int st = 0; st < NS; ++st) issue(st, st, 1);
   }
-  for (int idx = tid; idx < N * N; idx += T) sD[idx] = a.D[idx];
+  for (int idx = tid; idx < N * N; idx += T) {
+    sD[idx] = a.D[idx];
+    if constexpr (kSharedD) sDT[(idx % N) * N + idx / N] = a.D[idx];
+  }
 
   // ---- prologue: everything that needs all 50 components at the point ----
   GhContext ctx;
@@ -395,13 +424,15 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
   __syncthreads();  // sD visible, barrier init visible to all waiters
 
   const int i = pt % N, j = (pt / N) % N, k = pt / (N * N);
-  double Di[N], Dj[N], Dk[N];
-  if (active) {
+  double Di[kSharedD ? 1 : N], Dj[kSharedD ? 1 : N], Dk[kSharedD ? 1 : N];
+  if constexpr (!kSharedD) {
+    if (active) {
 #pragma unroll
-    for (int m = 0; m < N; ++m) {
-      Di[m] = sD[i * N + m];
-      Dj[m] = sD[j * N + m];
-      Dk[m] = sD[k * N + m];
+      for (int m = 0; m < N; ++m) {
+        Di[m] = sD[i * N + m];
+        Dj[m] = sD[j * N + m];
+        Dk[m] = sD[k * N + m];
+      }
     }
   }
   double* __restrict__ dte = a.dt + (size_t)e * 50 * npad;
@@ -426,12 +457,42 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
     const double* t = ring + stage * SD;
     if (active) {
       double dg[3], dpi[3], dph[3][3], ph[3];
-      logical_derivs<N>(t, i, j, k, Di, Dj, Dk, dg);
-      logical_derivs<N>(t + npad, i, j, k, Di, Dj, Dk, dpi);
+      if constexpr (kSharedD) {
+        // m outer, the five components inner: 15 independent FMA chains, the three
+        // matrix entries of this m are fetched once for all components
+        double acc[5][3];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        logical_derivs<N>(t + (2 + m) * npad, i, j, k, Di, Dj, Dk, dph[m]);
-        ph[m] = t[(2 + m) * npad + pt];
+        for (int c = 0; c < 5; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
+        const double* row = t + N * (j + N * k);
+        const double* col = t + i + N * N * k;
+        const double* pil = t + i + N * j;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          const double di = sDT[m * N + i], dj = sD[j * N + m], dk = sD[k * N + m];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            acc[c][0] = fma(di, row[c * npad + m], acc[c][0]);
+            acc[c][1] = fma(dj, col[c * npad + N * m], acc[c][1]);
+            acc[c][2] = fma(dk, pil[c * npad + N * N * m], acc[c][2]);
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          dg[x] = acc[0][x];
+          dpi[x] = acc[1][x];
+#pragma unroll
+          for (int m = 0; m < 3; ++m) dph[m][x] = acc[2 + m][x];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) ph[m] = t[(2 + m) * npad + pt];
+      } else {
+        logical_derivs<N>(t, i, j, k, Di, Dj, Dk, dg);
+        logical_derivs<N>(t + npad, i, j, k, Di, Dj, Dk, dpi);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          logical_derivs<N>(t + (2 + m) * npad, i, j, k, Di, Dj, Dk, dph[m]);
+          ph[m] = t[(2 + m) * npad + pt];
+        }
       }
       double o[5];
       {
@@ -460,8 +521,20 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
                        o[2 + m]);
       }
     }
-    __syncthreads();  // every reader is done with this stage
-    if (tid == 0 && s + NS < 10) issue(s + NS, stage, 3);
+    if constexpr (Cfg<N>::warp_release) {
+      // every lane's reads of the stage feed values it has already stored, so after
+      // the warp converges the stage is free as far as this warp is concerned; the
+      // last of the T/32 warps to get here refills it
+      __syncwarp();
+      if ((tid & 31) == 0 && s + NS < 10) {
+        __threadfence_block();
+        const unsigned int done = atomicAdd(&released[stage], 1u) + 1u;
+        if (done == (unsigned int)((T / 32) * (s / NS + 1))) issue(s + NS, stage, 3);
+      }
+    } else {
+      __syncthreads();  // every reader is done with this stage
+      if (tid == 0 && s + NS < 10) issue(s + NS, stage, 3);
+    }
   }
 }
 
@@ -1841,41 +1914,96 @@ __global__ void __launch_bounds__(256) gh_constraints_kernel(ConstraintArgs a) {
 struct FilterArgs {
   double* u;        // [E][C][npad]
   const double* F;  // [N*N] row-major filter matrix
-  int C;
+  int per_cta;      // component blocks per CTA (divides E*C)
+};
+
+// Register-blocked line form: a task is (grid line, group of R output rows); the
+// thread keeps its R x N block of the filter matrix in registers for the whole
+// kernel, loads the line's N values (the NG threads of a line read the same
+// addresses: broadcast) and produces R filtered values with R*N FMAs -- N
+// shared-memory loads per R*N FMAs instead of 2N loads per N FMAs (round 1: one
+// thread per point, N-term dot products with both operands from shared memory:
+// 8.4 ms for 6144 elements at N = 12; matrix rows as broadcast shared-memory
+// operands: 4.7 ms, bound by the LSU).  Passes ping-pong between two padded tiles
+// (odd row stride: no bank conflicts in any of the three directions).
+template <int N>
+struct FilterCfg {
+  static constexpr int R0 = 40 / N > 0 ? (40 / N < N ? 40 / N : N) : 1;
+  static constexpr int NG = (N + R0 - 1) / R0;  // row groups per line
+  static constexpr int R = (N + NG - 1) / NG;   // output rows per task
+  static constexpr int T = 192;                 // multiple of 32 and of every NG (1..4)
+  static constexpr int RS = N | 1;              // odd row stride: point (i, l) at i + RS * l
+  static_assert(T % NG == 0, "a thread keeps one row group");
 };
 
 template <int N>
-__global__ void __launch_bounds__(256) exponential_filter_kernel(FilterArgs a) {
-  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
-  __shared__ __align__(16) double t0[npad];
-  __shared__ __align__(16) double t1[npad];
+__global__ void __launch_bounds__(FilterCfg<N>::T) exponential_filter_kernel(FilterArgs a) {
+  using F = FilterCfg<N>;
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, f = N * N, T = F::T, RS = F::RS;
+  constexpr int NG = F::NG, R = F::R;
+  constexpr int kIters = (n + T - 1) / T;
+  __shared__ double t0[f * RS];
+  __shared__ double t1[f * RS];
   __shared__ double sF[N * N];
-  double* uc = a.u + (size_t)blockIdx.x * npad;
-  for (int p = threadIdx.x; p < n; p += blockDim.x) t0[p] = uc[p];
-  for (int p = threadIdx.x; p < N * N; p += blockDim.x) sF[p] = a.F[p];
-  __syncthreads();
-  for (int p = threadIdx.x; p < n; p += blockDim.x) {
-    const int i = p % N, rest = p / N;
-    double v = 0.0;
+  // a CTA filters a.per_cta consecutive component blocks; the next block is fetched
+  // into registers while the current one is filtered
+  double* ub = a.u + (size_t)blockIdx.x * a.per_cta * npad;
+  const int tid = threadIdx.x;
+  for (int p = tid; p < N * N; p += T) sF[p] = a.F[p];
+  double v[kIters];
+  // all loads of the thread in flight at once (a rolled loop would wait for each)
 #pragma unroll
-    for (int m = 0; m < N; ++m) v = fma(sF[i * N + m], t0[m + N * rest], v);
-    t1[p] = v;
+  for (int it = 0; it < kIters; ++it) {
+    const int p = tid + it * T;
+    v[it] = p < n ? ub[p] : 0.0;
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < n; p += blockDim.x) {
-    const int i = p % N, j = (p / N) % N, k = p / (N * N);
-    double v = 0.0;
+  const int g = tid % NG, r0 = g * R;
+  double Fb[R][N];
 #pragma unroll
-    for (int m = 0; m < N; ++m) v = fma(sF[j * N + m], t1[i + N * (m + N * k)], v);
-    t0[p] = v;
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < n; p += blockDim.x) {
-    const int ij = p % (N * N), k = p / (N * N);
-    double v = 0.0;
+  for (int q = 0; q < R; ++q)
 #pragma unroll
-    for (int m = 0; m < N; ++m) v = fma(sF[k * N + m], t0[ij + N * N * m], v);
-    uc[p] = v;
+    for (int m = 0; m < N; ++m) Fb[q][m] = sF[(r0 + q < N ? r0 + q : N - 1) * N + m];
+#pragma unroll 1
+  for (int blk = 0; blk < a.per_cta; ++blk) {
+    double* uc = ub + (size_t)blk * npad;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int p = tid + it * T;
+      if (p < n) t0[p % N + RS * (p / N)] = v[it];
+    }
+    __syncthreads();  // also: the stores of the previous block have read t1
+    if (blk + 1 < a.per_cta) {
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int p = tid + it * T;
+        v[it] = p < n ? uc[npad + p] : 0.0;
+      }
+    }
+    // xi, eta, zeta in that order like ApplyMatrices.cpp: t0 -> t1 -> t0 -> t1
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const double* __restrict__ src = (pass == 1) ? t1 : t0;
+      double* __restrict__ dst = (pass == 1) ? t0 : t1;
+      for (int task = tid; task < NG * f; task += T) {
+        const int l = task / NG;  // line; task % NG == g
+        const int base =
+            pass == 0 ? RS * l : (pass == 1 ? l % N + RS * N * (l / N) : l % N + RS * (l / N));
+        const int stride = pass == 0 ? 1 : (pass == 1 ? RS : RS * N);
+        double x[N];
+#pragma unroll
+        for (int m = 0; m < N; ++m) x[m] = src[base + m * stride];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          double w = 0.0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) w = fma(Fb[q][m], x[m], w);
+          if (r0 + q < N) dst[base + (r0 + q) * stride] = w;
+        }
+      }
+      __syncthreads();
+    }
+    for (int p = tid; p < n; p += T) uc[p] = t1[p % N + RS * (p / N)];
   }
 }
 

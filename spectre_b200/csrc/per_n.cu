@@ -211,8 +211,11 @@ int launch_volume_p(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
 
 template <int N>
 int launch_filter(dgrhs_ctx* c) {
-  dg::FilterArgs a{c->u, c->filterF, c->C};
-  dg::exponential_filter_kernel<N><<<c->nelem * c->C, 256, 0, c->stream>>>(a);
+  // GH: 25 component blocks per CTA (two CTAs per element); ScalarWave: one element
+  const int per_cta = c->C % 25 == 0 ? 25 : c->C;
+  dg::FilterArgs a{c->u, c->filterF, per_cta};
+  const int blocks = c->nelem * (c->C / per_cta);
+  dg::exponential_filter_kernel<N><<<blocks, dg::FilterCfg<N>::T, 0, c->stream>>>(a);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   return 0;

@@ -9,12 +9,16 @@ the reference's send_data_for_fluxes / receive_boundary_data_global_time_steppin
 except that raw face values (55 components) travel instead of the 134-component
 packaged data.  Schedule per substep:
 
-    pack_halo (ctx stream) -> NCCL send/recv (torch.distributed, async)
-    RHS of interior elements (overlaps the exchange)
-    wait -> RHS of boundary elements -> stepper update
+    pack_halo (ctx stream) -> NCCL send/recv (comm stream)
+    faces + volume of interior elements (overlap the exchange)
+    remaining faces (comm stream, after the halo) -> volume of boundary elements
+    -> stepper update
 
-torch is used only for the process group and for wrapping the library's halo
-buffers as tensors.
+The exchange and the whole schedule live inside libdgrhs.so (dgrhs_comm_init,
+dgrhs_take_steps): torch.distributed only hands the 128-byte ncclUniqueId to the
+other ranks.  The Python-driven schedule over torch.distributed (HaloExchange) is
+kept for the gloo CPU tests, for time-dependent boundary data and as an A/B
+reference (Evolution(..., native_exchange=False)).
 """
 from __future__ import annotations
 
@@ -232,8 +236,9 @@ class Evolution:
 
     def __init__(self, problem, stepper=lib.STEPPER_ADAMS_BASHFORTH, order=3, dt=2e-4,
                  t0=0.0, gauge=lib.GAUGE_HARMONIC, gauge_params=(), device=0, world=1, rank=0,
-                 process_group=None):
+                 process_group=None, native_exchange=True):
         self.world, self.rank = world, rank
+        self.native_exchange = False
         self.problem = problem
         self.part = domain.Partition(problem.neighbors, world, rank,
                                      boundary_slots=problem.dirichlet_analytic,
@@ -290,6 +295,15 @@ class Evolution:
                 device=f"cuda:{device}")
             self._stream = torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{device}")
             self._halo = HaloExchange(self.part, per_face, dist, process_group)
+            if (native_exchange and dist.is_available() and dist.is_initialized()
+                    and dist.get_backend(process_group) == "nccl"
+                    and not problem.boundary_time_dependent):
+                # the library's own communicator: rank 0 makes the ncclUniqueId
+                uid = [lib.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0, group=process_group)
+                ctx.comm_init(uid[0], rank, world)
+                ctx.set_halo_peers(self.part.send_counts, self.part.recv_counts)
+                self.native_exchange = True
 
     def boundary_ghost_data(self, problem, t):
         return boundary_ghost_data(problem, self.part, t, self.ctx.halo_comps)
@@ -318,6 +332,10 @@ class Evolution:
         return ctx.end_substep()
 
     def take_steps(self, n: int):
+        if self.world == 1 or self.native_exchange:
+            if not (self.part.external_faces and self.problem.boundary_time_dependent):
+                self.ctx.take_steps(n)     # the whole schedule runs inside the library
+                return
         done = 0
         while done < n:
             if self._substep():

@@ -40,6 +40,7 @@ EXPORTS = [
     "dgrhs_gh_time_derivative", "dgrhs_gh_bjorhus_dg_time_derivative", "dgrhs_sw_time_derivative", "dgrhs_gh_package_data",
     "dgrhs_gh_boundary_terms", "dgrhs_sw_package_data", "dgrhs_sw_boundary_terms",
     "dgrhs_lift_flux",
+    "dgrhs_comm_unique_id", "dgrhs_comm_init", "dgrhs_set_halo_peers", "dgrhs_exchange_halo",
 ]
 
 _lib = None
@@ -112,6 +113,13 @@ def _f64(a):
 
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def comm_unique_id() -> bytes:
+    """ncclUniqueId (128 bytes) for dgrhs_comm_init: rank 0 makes it, every rank gets it."""
+    buf = ctypes.create_string_buffer(128)
+    _check(load().dgrhs_comm_unique_id(buf))
+    return buf.raw
 
 
 def kernel_launch_count() -> int:
@@ -333,6 +341,21 @@ class Context:
     def halo_recv_ptr(self):
         return self._lib.dgrhs_halo_recv_ptr(self._h)
 
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Join the NCCL communicator of the ranks that share the domain (collective)."""
+        assert len(unique_id) == 128
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        _check(self._lib.dgrhs_comm_init(self._h, buf, int(rank), int(world)))
+
+    def set_halo_peers(self, send_counts, recv_counts):
+        sc = np.ascontiguousarray(send_counts, dtype=np.int32)
+        rc = np.ascontiguousarray(recv_counts, dtype=np.int32)
+        _check(self._lib.dgrhs_set_halo_peers(self._h, sc.ctypes.data_as(ctypes.c_void_p),
+                                              rc.ctypes.data_as(ctypes.c_void_p)))
+
+    def exchange_halo(self):
+        _check(self._lib.dgrhs_exchange_halo(self._h))
+
     def set_stepper(self, stepper, order, t0, dt):
         _check(self._lib.dgrhs_set_stepper(self._h, stepper, order, ctypes.c_double(t0),
                                            ctypes.c_double(dt)))
@@ -389,8 +412,8 @@ class Context:
 
     def time_kernels(self, reps=5, update_terms=3):
         """Mean ms per launch of (face kernel, volume kernel, stepper update,
-        volume kernel with the update fused in)."""
-        ms = np.zeros(4)
+        volume kernel with the update fused in, exponential filter pass or 0)."""
+        ms = np.zeros(5)
         _check(self._lib.dgrhs_time_kernels(self._h, reps, update_terms, _ptr(ms)))
         return ms
 

@@ -171,7 +171,9 @@ def test_kerr_schild_shell_evolution_north_star_points(N, order):
     got = ctx.get_state()
     assert ctx.rhs_evaluations == oev.rhs_evals
     assert _relerr(got, oev.u, GH_BLOCKS) < TOL
-    assert np.max(np.abs(got - u0)) < 1e-6      # exact static solution, spectral accuracy
+    # the exact static solution is kept up to the top Legendre mode the filter removes
+    top_mode = np.max(np.abs(orc.apply_filter(N, u0, F) - u0))
+    assert np.max(np.abs(got - u0)) < max(1.5 * top_mode, 1e-9)
     cg = ctx.gh_constraint_norms()
     co = orc.gh_constraint_norms(N, got, J, H)
     np.testing.assert_allclose(cg, co, rtol=1e-8, atol=1e-13)
