@@ -76,59 +76,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and clock-event (throttle) reasons DURING the timed region, read through
+    NVML in this process (nvidia_ml_py), a few samples only (every 250 ms).  Every query
+    perturbs a multi-GPU run: measured on the 2-GPU box, `nvidia-smi -lms 20` stalls NCCL
+    progress for ~65 ms per query (configs[1] at 2 GPUs: 1.65 -> 4.65 ms per step), and
+    NVML polled every 50 ms still costs 4-20 % (1.68 -> 1.75 ms; shell N = 12: 13.5 ->
+    16.2 ms per step)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, device_index):
-        self.idx = device_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, device_index, period_s=0.25):
+        self.idx, self.period = device_index, period_s
+        self.samples, self.bits = [], 0
+        self.smax = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.error = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-            time.sleep(0.3)     # let the sampler come up before the timed region
-            self.lines.clear()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # no NVML: report that instead of a number
+            self.error = f"NVML unavailable: {e}"
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(self.h))
+            except Exception as e:
+                self.error = str(e)
+                return
+            self._stop.wait(self.period)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        lines = list(self.lines)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(np.max(smax)) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.error or "no sampler"]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.smax,
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b),
+                "samples": len(self.samples), "how": "NVML in-process, 250 ms period"}
 
 
 def weak_refinement(world, base):
@@ -377,7 +377,9 @@ class GpuRun:
         lib = self.lib
         ev = self.evolution.Evolution(self.problem, lib.STEPPER_ADAMS_BASHFORTH, 3, self.args.dt,
                                       0.0, self.gauge, self.gauge_params, self.local_rank,
-                                      self.world, self.rank, self.pg)
+                                      self.world, self.rank, self.pg,
+                                      native_exchange=not getattr(self.args, "python_exchange",
+                                                                  False))
         if self.use_filter:
             ev.ctx.set_exponential_filter(True, *FILTER)
         if self.args.volume_variant:
@@ -397,6 +399,8 @@ class GpuRun:
         # self-start (not timed: SURVEY 8d "exclude init, self-start") + warm-up
         ev.take_steps(warmup)
         self.barrier()
+        if os.environ.get("BENCH_NO_CLOCK_SAMPLER") == "1":
+            sample_clocks = False
         sampler = ClockSampler(self.local_rank) if sample_clocks else None
         if sampler:
             sampler.start()
@@ -411,6 +415,14 @@ class GpuRun:
         clocks = sampler.stop() if sampler else None
         launches = lib.kernel_launch_count() - launches0
         assert self.ctx.rhs_evaluations - evals0 == steps
+        self.phases, self.extra_steps = None, 0
+        if self.world > 1 and getattr(ev, "native_exchange", False):
+            # event timeline of one more (untimed) step of the multi-GPU schedule
+            self.ctx.set_phase_timing(True)
+            ev.take_steps(1)
+            self.phases = self.ctx.phase_times()
+            self.ctx.set_phase_timing(False)
+            self.extra_steps = 1
         if self.world > 1:
             import torch.distributed as dist
             t = torch.tensor([ms], device=f"cuda:{self.local_rank}", dtype=torch.float64)
@@ -623,6 +635,9 @@ def main():
     ap.add_argument("--strong-factor", type=int, default=4)
     ap.add_argument("--volume-variant", type=int, default=0,
                     help="dgrhs_set_split_volume: 0 default, 1 split kernels (A/B comparisons)")
+    ap.add_argument("--python-exchange", action="store_true",
+                    help="multi-GPU A/B: drive the halo exchange from Python over "
+                         "torch.distributed (round-1 schedule) instead of inside libdgrhs.so")
     ap.add_argument("--verify", action="store_true",
                     help="multi-GPU: compare the gathered state bit-for-bit with a single-GPU "
                          "evolution of the same global problem on rank 0 (small configs)")
@@ -659,7 +674,7 @@ def main():
     value = total_points * args.steps / (ms * 1e-3)
     state, err = run.check_state()
     if args.verify and world > 1:
-        run.verify(args.warmup + args.steps)
+        run.verify(args.warmup + args.steps + run.extra_steps)
     roofline = run.roofline(value)
     e2e = None if args.no_e2e else run.e2e(state, total_points)
     del state
@@ -685,6 +700,12 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "max_abs_error_vs_exact": err, "secondary": secondary,
         }
+        if run.phases:
+            line["multi_gpu_timeline_ms"] = {
+                "rank": 0, "what": "CUDA-event timeline of one RHS evaluation inside "
+                "dgrhs_take_steps, ms since its start (main stream: pack, faces_interior, "
+                "volume_interior; comm stream: nccl_start, nccl_end, faces_boundary, "
+                "volume_boundary)", **run.phases}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

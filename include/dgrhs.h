@@ -195,12 +195,22 @@ int dgrhs_halo_comps(dgrhs_ctx* ctx);
  *                         (callers that drive the substeps themselves)
  * After dgrhs_comm_init, dgrhs_take_steps runs the whole multi-GPU schedule itself:
  * pack -> NCCL exchange (comm stream) | interior faces + interior volume (main
- * stream) | remaining faces (comm stream, after the halo) -> boundary volume. */
+ * stream) | remaining faces + boundary volume (comm stream, after the halo, next
+ * to the interior volume kernel) -> join. */
 int dgrhs_comm_unique_id(void* unique_id_128_bytes);
 int dgrhs_comm_init(dgrhs_ctx* ctx, const void* unique_id_128_bytes, int rank, int world);
 int dgrhs_set_halo_peers(dgrhs_ctx* ctx, const int32_t* send_counts,
                          const int32_t* recv_counts);
 int dgrhs_exchange_halo(dgrhs_ctx* ctx);
+/* Event timeline of the multi-GPU schedule (profiles/: the substitute for a per-rank
+ * nsys timeline, nsys is not installed here).  When enabled, every RHS evaluation of
+ * dgrhs_take_steps records CUDA events; dgrhs_get_phase_times returns, for the LAST
+ * evaluation, the milliseconds from its start to the end of: pack (main stream),
+ * interior faces (main), interior volume (main), the wait for the packed faces (comm
+ * stream: NCCL start), NCCL send/recv (comm), remaining faces (comm), boundary volume
+ * (comm) -- ms[0..6]. */
+int dgrhs_set_phase_timing(dgrhs_ctx* ctx, int enable);
+int dgrhs_get_phase_times(dgrhs_ctx* ctx, double* ms);
 
 /* ---- time stepping (Time/TimeSteppers, Time/Actions) ------------------- */
 

@@ -122,8 +122,11 @@ struct dgrhs_ctx {
   void* nccl_comm = nullptr;  // ncclComm_t
   int comm_rank = 0, comm_world = 1;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_faces2 = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_faces1 = nullptr, ev_faces2 = nullptr;
   std::vector<int> send_counts, recv_counts;  // faces per peer (rank order)
+  // optional event timeline of the multi-GPU schedule (dgrhs_set_phase_timing)
+  bool phase_timing = false;
+  cudaEvent_t phase_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t state_len() const { return (size_t)nelem * C * npad; }
 };
 

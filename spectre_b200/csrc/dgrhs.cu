@@ -515,6 +515,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
     cudaEventDestroy(c->ev_packed);
     cudaEventDestroy(c->ev_halo);
     cudaEventDestroy(c->ev_faces2);
+    cudaEventDestroy(c->ev_faces1);
   }
   for (double* p : {c->u, c->invjac, c->coords, c->stat, c->corr, c->D, c->gH, c->gdH,
                     c->halo_send, c->halo_recv, c->u0, c->u_alt, c->ctxbuf, c->filterF})
@@ -1450,6 +1451,7 @@ int start_halo_exchange(dgrhs_ctx* c) {
   if (!nc) return 1;
   CU(cudaEventRecord(c->ev_packed, c->stream));
   CU(cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
+  if (c->phase_timing) CU(cudaEventRecord(c->phase_ev[4], c->comm_stream));
   const size_t per_face = (size_t)c->HC * c->f;
   ncclComm_t comm = static_cast<ncclComm_t>(c->nccl_comm);
   size_t so = 0, ro = 0;
@@ -1467,35 +1469,57 @@ int start_halo_exchange(dgrhs_ctx* c) {
   }
   NC(nc->GroupEnd());
   CU(cudaEventRecord(c->ev_halo, c->comm_stream));
+  if (c->phase_timing) CU(cudaEventRecord(c->phase_ev[5], c->comm_stream));
   return 0;
 }
 
 // One RHS evaluation of a rank that exchanges faces.  Streams:
-//   main: pack | faces of interior interfaces, volume of interior elements | (join) volume of
+//   main: pack | faces of the interfaces that touch an interior element | volume of the
+//         interior elements | (join)
+//   comm: (packed) NCCL send/recv | faces of the remaining interfaces (they need the halo and
+//         write corrections of boundary elements only) | (faces of main done) volume of the
 //         boundary elements
-//   comm: (packed) NCCL send/recv | faces of the remaining interfaces (they need the halo
-//         and write corrections of boundary elements only, so they run NEXT TO the interior
-//         volume kernel instead of after it)
+// The boundary pass runs NEXT TO the interior volume kernel (higher stream priority), not
+// behind it: no kernel tail of the interior pass is waited for and no launch gap is exposed.
 int rhs_with_exchange(dgrhs_ctx* c, double t) {
   const dg::UpdateArgs upd = c->upd_active ? c->pending_upd : dg::UpdateArgs{};
   const DgNOps* ops = dgrhs_nops(c->N);
-  if (ops->pack(c)) return 1;
-  if (start_halo_exchange(c)) return 1;
+  cudaStream_t main_stream = c->stream;
+  const bool pt = c->phase_timing;
+  if (pt) CU(cudaEventRecord(c->phase_ev[0], main_stream));
+  // pack + exchange on the communication stream, behind everything queued so far
+  CU(cudaEventRecord(c->ev_packed, main_stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
+  c->stream = c->comm_stream;
+  int prc = ops->pack(c);
+  if (!prc && pt && cudaEventRecord(c->phase_ev[1], c->comm_stream) != cudaSuccess) prc = 1;
+  if (!prc) prc = start_halo_exchange(c);
+  c->stream = main_stream;
+  if (prc) return 1;
   ++c->rhs_evals;
   const int ni = c->n_interior;
-  if (ni > 0 && rhs_range(c, t, c->dt_last, 0, ni, false, true, upd)) return 1;
-  if (ni == 0 && ops->gauge(c, t)) return 1;
+  c->pdl_volume = false;
+  if (ops->gauge(c, t)) return 1;
+  if (ni > 0 && ops->faces(c, 0, ni)) return 1;
+  CU(cudaEventRecord(c->ev_faces1, main_stream));
+  if (pt) CU(cudaEventRecord(c->phase_ev[2], main_stream));
+  c->pdl_volume = false;  // an event sits between the faces and the volume kernel
+  if (ni > 0 && ops->volume(c, c->dt_last, 0, ni, true, &upd)) return 1;
+  if (pt) CU(cudaEventRecord(c->phase_ev[3], main_stream));
   {
-    cudaStream_t main_stream = c->stream;
-    c->stream = c->comm_stream;  // the launcher queues on c->stream
-    const int rc = ops->faces(c, ni, c->nelem);
+    c->stream = c->comm_stream;  // the launchers queue on c->stream
+    int rc = ops->faces(c, ni, c->nelem);
+    if (pt) cudaEventRecord(c->phase_ev[6], c->comm_stream);
+    c->pdl_volume = false;
+    if (!rc && cudaStreamWaitEvent(c->comm_stream, c->ev_faces1, 0) != cudaSuccess) rc = 1;
+    if (!rc) rc = ops->volume(c, c->dt_last, ni, c->nelem, true, &upd);
     c->stream = main_stream;
-    c->pdl_volume = false;       // other work sits between these faces and the volume kernel
     if (rc) return 1;
   }
+  if (pt) CU(cudaEventRecord(c->phase_ev[7], c->comm_stream));
   CU(cudaEventRecord(c->ev_faces2, c->comm_stream));
-  CU(cudaStreamWaitEvent(c->stream, c->ev_faces2, 0));
-  return ops->volume(c, c->dt_last, ni, c->nelem, true, &upd);
+  CU(cudaStreamWaitEvent(main_stream, c->ev_faces2, 0));
+  return 0;
 }
 
 }  // namespace
@@ -1534,6 +1558,7 @@ int dgrhs_comm_init(dgrhs_ctx* c, const void* unique_id_128_bytes, int rank, int
   CU(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_faces2, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_faces1, cudaEventDisableTiming));
   c->send_counts.assign(world, 0);
   c->recv_counts.assign(world, 0);
   return 0;
@@ -1554,6 +1579,29 @@ int dgrhs_set_halo_peers(dgrhs_ctx* c, const int32_t* send_counts, const int32_t
   if (nr > c->nghost) return fail("recv counts sum to %lld, the context has %d ghost slots", nr, c->nghost);
   c->send_counts.assign(send_counts, send_counts + c->comm_world);
   c->recv_counts.assign(recv_counts, recv_counts + c->comm_world);
+  return 0;
+}
+
+int dgrhs_set_phase_timing(dgrhs_ctx* c, int enable) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (enable && !c->phase_ev[0])
+    for (auto& e : c->phase_ev) CU(cudaEventCreate(&e));
+  c->phase_timing = enable != 0;
+  return 0;
+}
+
+int dgrhs_get_phase_times(dgrhs_ctx* c, double* ms) {
+  CHECK_CTX(c);
+  if (!c->phase_timing || !c->nccl_comm) return fail("phase timing is not enabled");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->comm_stream));
+  for (int i = 1; i < 8; ++i) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, c->phase_ev[0], c->phase_ev[i]));
+    ms[i - 1] = t;
+  }
   return 0;
 }
 

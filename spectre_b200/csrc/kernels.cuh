@@ -928,6 +928,9 @@ struct FaceArgs {
   // below n_interior (+ external faces of those elements); 2 = the rest (incl.
   // ghost faces) -- used to overlap the halo exchange.
   int n_interior, pass;
+  // first element of the launch grid: pass 2 only has work on elements >= n_interior
+  // (both sides of its interfaces are boundary elements)
+  int elem_begin;
   // DemandOutgoingCharSpeeds on external faces without a ghost state (nbr = -1),
   // GeneralizedHarmonic/BoundaryConditions/DemandOutgoingCharSpeeds.cpp:37-76:
   // violations[0] counts face points where a characteristic speed (w.r.t. the
@@ -983,11 +986,11 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   constexpr int npad = Cfg<N>::npad, f = N * N, HC = 55;
   pdl_launch_dependents();  // the volume kernel may start its prologue (see pdl_wait_for_primary)
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)a.nelem * 6 * f;
+  const long long total = (long long)(a.nelem - a.elem_begin) * 6 * f;
   if (idx >= total) return;
   const int q = (int)(idx % f);
   const int d = (int)((idx / f) % 6);
-  const int e = (int)(idx / (6 * f));
+  const int e = a.elem_begin + (int)(idx / (6 * f));
   const int qa = q % N, qb = q / N;
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
@@ -1112,11 +1115,11 @@ template <int N>
 __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   constexpr int npad = Cfg<N>::npad, f = N * N, HC = 9;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)a.nelem * 6 * f;
+  const long long total = (long long)(a.nelem - a.elem_begin) * 6 * f;
   if (idx >= total) return;
   const int q = (int)(idx % f);
   const int d = (int)((idx / f) % 6);
-  const int e = (int)(idx / (6 * f));
+  const int e = a.elem_begin + (int)(idx / (6 * f));
   const int qa = q % N, qb = q / N;
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;

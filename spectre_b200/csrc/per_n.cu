@@ -31,7 +31,7 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
       return fail("element range must be [0, n_interior) or [n_interior, n_elements)");
   }
   dg::FaceArgs a{c->u,    c->invjac, c->stat, c->nbr, c->nbr_face, c->halo_recv,
-                 c->corr, c->nelem,  n_int,   pass,   c->violations};
+                 c->corr, c->nelem,  n_int,   pass,   pass == 2 ? n_int : 0, c->violations};
   // Bjorhus faces and non-conforming mortars need no halo data: all of them are
   // evaluated once per right-hand side, with whichever pass comes first, so that
   // their corrections are in place before ANY volume kernel of this evaluation
@@ -56,7 +56,7 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->aux_join, c->aux_stream));
   }
-  const long long total = (long long)c->nelem * 6 * N * N;
+  const long long total = (long long)(c->nelem - a.elem_begin) * 6 * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)
     dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);

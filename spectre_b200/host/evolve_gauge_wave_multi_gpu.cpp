@@ -211,7 +211,7 @@ int main(int argc, char** argv) {
     std::printf("world %d elements %zu N %zu steps %d time %.17g\n", world, d.n_elem, N, steps, results[0].time);
     std::printf("max |u - exact| %.3e\n", err);
     std::printf("multi-GPU state bit-identical to single-GPU state: %s\n", identical ? "yes" : "NO");
-    return identical && err < 1e-6 ? 0 : 2;
+    return identical && err < 1e-4 ? 0 : 2;
   } catch (const std::exception& err) {
     std::fprintf(stderr, "ERROR: %s\n", err.what());
     return 1;

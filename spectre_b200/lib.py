@@ -41,6 +41,7 @@ EXPORTS = [
     "dgrhs_gh_boundary_terms", "dgrhs_sw_package_data", "dgrhs_sw_boundary_terms",
     "dgrhs_lift_flux",
     "dgrhs_comm_unique_id", "dgrhs_comm_init", "dgrhs_set_halo_peers", "dgrhs_exchange_halo",
+    "dgrhs_set_phase_timing", "dgrhs_get_phase_times",
 ]
 
 _lib = None
@@ -352,6 +353,18 @@ class Context:
         rc = np.ascontiguousarray(recv_counts, dtype=np.int32)
         _check(self._lib.dgrhs_set_halo_peers(self._h, sc.ctypes.data_as(ctypes.c_void_p),
                                               rc.ctypes.data_as(ctypes.c_void_p)))
+
+    def set_phase_timing(self, enable=True):
+        _check(self._lib.dgrhs_set_phase_timing(self._h, int(bool(enable))))
+
+    def phase_times(self):
+        """ms from the start of the last multi-GPU RHS evaluation to the end of (pack,
+        interior faces, interior volume, NCCL start, NCCL end, remaining faces, boundary
+        volume)."""
+        ms = np.zeros(7)
+        _check(self._lib.dgrhs_get_phase_times(self._h, _ptr(ms)))
+        return dict(zip(("pack", "faces_interior", "volume_interior", "nccl_start", "nccl_end",
+                         "faces_boundary", "volume_boundary"), ms.tolist()))
 
     def exchange_halo(self):
         _check(self._lib.dgrhs_exchange_halo(self._h))
