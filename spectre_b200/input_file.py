@@ -13,6 +13,15 @@ spectre_b200.evolution.Problem and drive the C-ABI.  Options outside the path
 (observers' file names, AMR, phase changes, resource info) are accepted and
 ignored; options that would change the numerics and are not implemented raise
 InputFileError, like the reference's PARSE_ERROR.
+
+Global time stepping with a FIXED step is what the path implements.  An input
+file whose executable uses local time stepping (EvolveGhSingleBlackHole,
+EvolveGhBinaryBlackHole: USE_LTS in Evolution/Executables/GeneralizedHarmonic/
+CMakeLists.txt) or that lists StepChoosers (they adjust the step on every LTS
+step / at every slab boundary) is therefore NOT numerically equivalent to the
+reference run: it is rejected unless the caller passes
+allow_gts_fixed_step=True (command line: --allow-gts-fixed-step), in which case
+the ignored choosers are printed with the results.
 """
 from __future__ import annotations
 
@@ -105,7 +114,9 @@ STEPPERS = {
 class Run:
     """Everything an input file determines for the path."""
 
-    def __init__(self, metadata, options):
+    LTS_EXECUTABLES = ("EvolveGhSingleBlackHole", "EvolveGhBinaryBlackHole")
+
+    def __init__(self, metadata, options, allow_gts_fixed_step=False):
         self.metadata, self.options = metadata or {}, options
         exe = str(self.metadata.get("Executable", ""))
         self.system = lib.SYSTEM_SCALAR_WAVE if "ScalarWave" in exe else lib.SYSTEM_GH
@@ -119,9 +130,20 @@ class Run:
         self.stepper, self.order = STEPPERS[name], int(o.get("Order", 0))
         self.step_choosers_ignored = []
         if "StepChoosers" in ev and ev["StepChoosers"]:
-            # global time stepping with a fixed step is what the path implements; the
-            # choosers of KerrSchild.yaml only act at slab boundaries
-            self.step_choosers_ignored = [list(c)[0] for c in ev["StepChoosers"]]
+            self.step_choosers_ignored = [list(c)[0] if isinstance(c, dict) else str(c)
+                                          for c in ev["StepChoosers"]]
+        self.lts_executable = any(exe.startswith(name) for name in self.LTS_EXECUTABLES)
+        if (self.lts_executable or self.step_choosers_ignored) and not allow_gts_fixed_step:
+            why = []
+            if self.lts_executable:
+                why.append(f"executable {exe} uses local time stepping")
+            if self.step_choosers_ignored:
+                why.append("StepChoosers " + ", ".join(self.step_choosers_ignored)
+                           + " would change the step size")
+            raise InputFileError(
+                "; ".join(why) + ": the path takes fixed global time steps, so the run would not "
+                "be numerically equivalent to the reference executable (pass "
+                "allow_gts_fixed_step=True / --allow-gts-fixed-step to run it anyway)")
         sd = options["SpatialDiscretization"]
         bc_name, _ = _one(sd["BoundaryCorrection"], "BoundaryCorrection")
         if bc_name != "UpwindPenalty":
@@ -197,6 +219,11 @@ class Run:
                 else:
                     k = self._boundary_condition(b, "Brick.BoundaryConditions")
                     kinds.append((k, k))
+            for dim, k in enumerate(kinds):
+                if (k[0] == "Periodic") != (k[1] == "Periodic"):
+                    raise InputFileError(
+                        f"Brick: periodic boundary condition on only one side of dimension {dim} "
+                        "(both or neither must be Periodic)")
             periodic = tuple(k == ("Periodic", "Periodic") for k in kinds)
             self.domain = domain.Brick(o["LowerBound"], o["UpperBound"], o["InitialRefinement"],
                                        int(pts[0]), periodic=periodic)
@@ -241,6 +268,14 @@ class Run:
         self.outgoing = any(k == "DemandOutgoingCharSpeeds" for k in face_bc.values())
         bj = {d: k for d, k in face_bc.items() if k.startswith("ConstraintPreserving")}
         if bj:
+            if len({d // 2 for d in bj}) > 1:
+                # the reference applies the external faces of an element one after the other,
+                # each seeing the dt corrected by the previous ones on shared edge points
+                # (BoundaryConditionsImpl.hpp:277-278, 636-660); the path evaluates every
+                # Bjorhus face from the uncorrected volume dt
+                raise InputFileError(
+                    "ConstraintPreservingBjorhus in more than one dimension (elements with two "
+                    "or more Bjorhus faces) is not implemented")
             self.bjorhus = lambda g, d: bj.get(d)
 
     # -- EvolutionSystem -----------------------------------------------------
@@ -339,20 +374,27 @@ class Run:
         return out
 
 
-def load(path):
+def load(path, allow_gts_fixed_step=False):
     with open(path) as f:
         docs = list(yaml.safe_load_all(f))
     if len(docs) == 1:
-        return Run({}, docs[0])
-    return Run(docs[0], docs[1])
+        return Run({}, docs[0], allow_gts_fixed_step)
+    return Run(docs[0], docs[1], allow_gts_fixed_step)
 
 
 def main():
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--input-file", required=True)
     ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--allow-gts-fixed-step", action="store_true",
+                    help="run an LTS / step-chooser input file with fixed global steps (NOT "
+                         "numerically equivalent to the reference executable)")
     args = ap.parse_args()
-    run = load(args.input_file)
+    run = load(args.input_file, args.allow_gts_fixed_step)
+    if run.lts_executable or run.step_choosers_ignored:
+        print("WARNING: fixed global time steps; ignored StepChoosers: "
+              f"{run.step_choosers_ignored or 'none'}; LTS executable: {run.lts_executable} "
+              "-- not numerically equivalent to the reference run")
     for step, t, norms in run.run(args.steps):
         print(f"step {step:6d}  t = {t:.6f}  " + "  ".join(f"{k} = {v:.6e}" for k, v in norms.items()))
 

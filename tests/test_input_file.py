@@ -13,6 +13,24 @@ from spectre_b200 import domain, input_file, lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/tests/InputFiles"
+# byte-for-byte copies of the reference's input files (tests/golden/gen_input_files.py): the
+# GPU box has no /root/reference
+GOLDEN = os.path.join(HERE, "golden", "inputs")
+
+
+def _reference_input(rel):
+    """The reference's own file when the checkout is present, else the committed copy."""
+    path = os.path.join(REF, rel)
+    return path if os.path.exists(path) else os.path.join(GOLDEN, os.path.basename(rel))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_committed_input_files_are_the_reference_files():
+    for rel in ("ScalarWave/PlaneWave3D.yaml", "GeneralizedHarmonic/GaugeWave3D.yaml",
+                "GeneralizedHarmonic/KerrSchild.yaml"):
+        with open(os.path.join(REF, rel), "rb") as a, \
+                open(os.path.join(GOLDEN, os.path.basename(rel)), "rb") as b:
+            assert a.read() == b.read(), rel
 
 
 def test_parse_own_fixtures():
@@ -31,15 +49,21 @@ def test_parse_own_fixtures():
     assert s.n_steps == 10 and s.t0 == 0.1 and s.domain.N == 7 and s.static == (0.0,)
 
 
-@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
 def test_parse_reference_input_files():
-    sw = input_file.load(f"{REF}/ScalarWave/PlaneWave3D.yaml")
+    sw = input_file.load(_reference_input("ScalarWave/PlaneWave3D.yaml"))
     assert (sw.system, sw.stepper, sw.order, sw.dt, sw.n_steps) == \
         (lib.SYSTEM_SCALAR_WAVE, lib.STEPPER_ADAMS_BASHFORTH, 3, 1e-3, 50)
-    gw = input_file.load(f"{REF}/GeneralizedHarmonic/GaugeWave3D.yaml")
+    gw = input_file.load(_reference_input("GeneralizedHarmonic/GaugeWave3D.yaml"))
     assert gw.gauge == lib.GAUGE_ANALYTIC_GAUGE_WAVE and gw.gauge_params == (0.1, 1.0)
     assert gw.static == (1.0, -1.0, 1.0) and gw.filter is None and gw.n_steps == 2
-    ks = input_file.load(f"{REF}/GeneralizedHarmonic/KerrSchild.yaml")
+    assert not gw.lts_executable and not gw.step_choosers_ignored
+    # EvolveGhSingleBlackHole is an LTS executable and the file lists step choosers: a run
+    # with fixed global steps is not the reference's run and must be asked for explicitly
+    with pytest.raises(input_file.InputFileError, match="local time stepping"):
+        input_file.load(_reference_input("GeneralizedHarmonic/KerrSchild.yaml"))
+    ks = input_file.load(_reference_input("GeneralizedHarmonic/KerrSchild.yaml"),
+                         allow_gts_fixed_step=True)
+    assert ks.lts_executable
     assert isinstance(ks.domain, domain.SphericalShell) and ks.domain.n_elements == 6
     assert ks.domain.radii == [1.9, 2.3] and ks.domain.distributions == ["Logarithmic"]
     assert (ks.stepper, ks.order, ks.dt) == (lib.STEPPER_ADAMS_BASHFORTH, 4, 2e-4)
@@ -97,25 +121,83 @@ def test_run_own_fixtures():
     assert all(v < 2e-2 for v in obs[-1][2].values()) and obs[-1][2]["Error(Pi)"] > 0.0
 
 
+def _oracle_error_norms(run, n_steps):
+    """The same input file evolved by the CPU oracle: Error(...) L2 norms as ObserveNorms
+    reports them (NormType L2Norm, Components Sum, ObserveNorms.hpp:60-80)."""
+    from oracle import oracle as orc
+    from spectre_b200 import evolution
+    problem = run.problem()
+    part = domain.Partition(problem.neighbors, 1, 0, boundary_slots=problem.dirichlet_analytic,
+                            neighbor_direction=problem.orientations[0],
+                            face_permutation=problem.orientations[1], mortars=problem.mortars)
+    ids, N = part.global_ids, problem.N
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    u0 = problem.u0(ids, run.t0)
+    kw = {}
+    if part.oriented:
+        kw = dict(nbr_dir=part.local_neighbor_direction, face_perm=part.local_face_permutation)
+
+    def gauge_fields(t):
+        H = np.zeros((len(ids), 4, N ** 3))
+        dH = np.zeros((len(ids), 16, N ** 3))
+        for e in range(len(ids)):
+            H[e], dH[e] = orc.analytic_christoffel_gauge(N, run.u0(x[e], t), J[e])
+        return np.concatenate([stat, H, dH], axis=1)
+    static_sf = gauge_fields(run.t0) if run.analytic_christoffel else None
+
+    def rhs(v, t):
+        ext = (evolution.boundary_ghost_data(problem, part, t, 55)[:, :50]
+               if part.external_faces else None)
+        if run.gauge == lib.GAUGE_ANALYTIC_GAUGE_WAVE:
+            sf = gauge_fields(t)      # AnalyticChristoffel of the time-dependent solution
+        elif run.analytic_christoffel:
+            sf = static_sf
+        else:
+            return orc.dg_rhs(1, N, v, J, stat, part.local_neighbors, ext_u=ext, **kw)
+        return orc.dg_rhs(1, N, v, J, sf, part.local_neighbors, gauge_params=orc.GAUGE_GIVEN,
+                          ext_u=ext, **kw)
+    post = None
+    if run.filter:
+        F = orc.exponential_filter_matrix(N, *run.filter)
+        post = lambda v: orc.apply_filter(N, v, F)
+    oev = orc.Evolution(rhs, u0, run.t0, run.dt, f"AB{run.order}", post_update=post)
+    for _ in range(n_steps):
+        oev.step()
+    exact = problem.u0(ids, oev.time)
+    npts = exact.shape[0] * exact.shape[2]
+    return {f"Error({nm})": float(np.sqrt(np.sum((oev.u[:, a:b] - exact[:, a:b]) ** 2) / npts))
+            for nm, (a, b) in zip(("SpacetimeMetric", "Pi", "Phi"), ((0, 10), (10, 20), (20, 50)))}
+
+
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
 def test_run_reference_input_files():
-    gw = input_file.load(f"{REF}/GeneralizedHarmonic/GaugeWave3D.yaml")
+    """GaugeWave3D.yaml and KerrSchild.yaml of the reference, unchanged (the committed
+    byte-for-byte copies when /root/reference is absent): the printed Error(...) norms equal
+    the CPU oracle's for the same file to 1e-12 relative (plus 1e-15 absolute: the norms
+    themselves are differences of nearly equal numbers)."""
+    gw = input_file.load(_reference_input("GeneralizedHarmonic/GaugeWave3D.yaml"))
     obs = gw.run()
     assert [o[0] for o in obs] == [0, 2]
-    assert all(v < 1e-5 for v in obs[-1][2].values())
-    ks = input_file.load(f"{REF}/GeneralizedHarmonic/KerrSchild.yaml")
+    assert all(v < 1e-3 for v in obs[-1][2].values())
+    want = _oracle_error_norms(gw, gw.n_steps)
+    for k, v in want.items():
+        assert obs[-1][2][k] == pytest.approx(v, rel=1e-12, abs=1e-15), k
+    # EvolveGhSingleBlackHole is LTS with step choosers: only on request, fixed global steps
+    ks = input_file.load(_reference_input("GeneralizedHarmonic/KerrSchild.yaml"),
+                         allow_gts_fixed_step=True)
     obs = ks.run()
     assert obs[-1][0] == 15 and all(np.isfinite(v) and v < 0.2 for v in obs[-1][2].values())
+    want = _oracle_error_norms(ks, ks.n_steps)
+    for k, v in want.items():
+        assert obs[-1][2][k] == pytest.approx(v, rel=1e-12, abs=1e-15), k
 
 
-@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
 def test_sphere_per_block_refinement_options(tmp_path):
     """The four forms of Sphere.InitialRefinement (Sphere.hpp:222-233, ExpandOverBlocks):
     number, [phi, theta, r], one triple per block, map over block / group names.  Per-block
     values give oriented 2:1 mortars between the wedges."""
     import yaml
-    with open(f"{REF}/GeneralizedHarmonic/KerrSchild.yaml") as f:
+    with open(_reference_input("GeneralizedHarmonic/KerrSchild.yaml")) as f:
         meta, opts = list(yaml.safe_load_all(f))
 
     def load_with(**sphere_options):
@@ -124,7 +206,7 @@ def test_sphere_per_block_refinement_options(tmp_path):
         path = tmp_path / "input.yaml"
         with open(path, "w") as f:
             yaml.safe_dump_all([meta, o], f)
-        return input_file.load(str(path))
+        return input_file.load(str(path), allow_gts_fixed_step=True)
     r = load_with(InitialRefinement=[1, 1, 2])
     assert r.domain.n_elements == 6 * 4 * 4 and len(r.domain.mortars()) == 0
     per_block = [[1, 1, 1]] + [[0, 0, 0]] * 5
@@ -152,3 +234,22 @@ def test_sphere_per_block_refinement_options(tmp_path):
     # finer in the angle on one side, finer in radius on the other: no such mortar here
     with pytest.raises(ValueError, match="unsupported non-conforming interface"):
         load_with(InitialRefinement=[[1, 1, 0]] + [[0, 0, 1]] * 5).domain.mortars()
+
+
+def test_one_sided_periodic_and_multi_dimension_bjorhus_are_errors():
+    import copy
+    import yaml
+    with open(os.path.join(HERE, "inputs", "GaugeWaveBjorhus.yaml")) as f:
+        meta, opts = list(yaml.safe_load_all(f))
+    bcs = opts["DomainCreator"]["Brick"]["BoundaryConditions"]
+    o = copy.deepcopy(opts)
+    o["DomainCreator"]["Brick"]["BoundaryConditions"][1] = {
+        "Lower": "Periodic", "Upper": {"DirichletAnalytic": None}}
+    with pytest.raises(input_file.InputFileError, match="only one side"):
+        input_file.Run(meta, o)
+    o = copy.deepcopy(opts)
+    bj = {"ConstraintPreservingBjorhus": {"Type": "ConstraintPreserving"}}
+    o["DomainCreator"]["Brick"]["BoundaryConditions"] = [{"Lower": bj, "Upper": bj},
+                                                         {"Lower": bj, "Upper": bj}, bcs[2]]
+    with pytest.raises(input_file.InputFileError, match="more than one dimension"):
+        input_file.Run(meta, o)
