@@ -50,7 +50,7 @@ enum {
 
 /* TimeSteppers (Time/TimeSteppers/) */
 enum {
-  DGRHS_STEPPER_ADAMS_BASHFORTH = 0, /* AdamsBashforth.cpp:120-201, order 1..6 */
+  DGRHS_STEPPER_ADAMS_BASHFORTH = 0, /* AdamsBashforth.cpp:120-201, order 1..8 */
   DGRHS_STEPPER_RK3_HESTHAVEN = 1,   /* Rk3HesthavenSsp.cpp:55-81 */
   /* RungeKutta::update_u_impl with a Butcher tableau (RungeKutta.cpp:69-122) */
   DGRHS_STEPPER_RK3_OWREN = 2,       /* Rk3Owren.cpp:17-34 */
@@ -230,6 +230,18 @@ int64_t dgrhs_rhs_evaluations(dgrhs_ctx* ctx);
  * *time the time at which the RHS must be evaluated; end_substep records the
  * derivative and updates u. is_step_done is set when a full step completed. */
 int dgrhs_begin_substep(dgrhs_ctx* ctx, double* time);
+/* Exact time bookkeeping of the reference (Time/Slab.hpp, Time/Time.hpp:114-117,
+ * TimeStepId.cpp:66-82): after dgrhs_set_stepper, declare the first slab and the number
+ * of (equal) steps per slab.  Step and substep times are then formed as the reference
+ * forms them -- slab k+1 = [end_k, end_k + (end_k - start_k)], time = (1 - f) start +
+ * f end with the exact rational slab fraction f, substep time = (1 - c) t_step +
+ * c t_next_step, step size = (end - start) * (1 / steps_per_slab) -- instead of
+ * t0 + k dt.  host/SpectreTime.hpp holds the matching Slab/Time/TimeDelta/TimeStepId
+ * value types; DgTimeLoop checks every substep time against the TimeStepId's. */
+int dgrhs_set_slab(dgrhs_ctx* ctx, double slab_start, double slab_end, int steps_per_slab);
+/* number of self-start RHS evaluations (SelfStartActions.hpp) still to come before the
+ * first regular step; 0 for substep methods */
+int dgrhs_self_start_substeps_left(dgrhs_ctx* ctx, int* n);
 /* Non-conforming (h-refined, 2:1) mortars, equal N on both sides.
  * Faces on either side of such an interface carry DGRHS_NEIGHBOR_HANGING in the
  * neighbor table of dgrhs_set_geometry (Element<3>::neighbors() holds several
@@ -438,6 +450,11 @@ int dgrhs_adams_bashforth_coefficients(int order, const double* history_times,
  * AdamsBashforth only; any output pointer may be NULL.  Host-only. */
 int dgrhs_stepper_properties(int stepper, int order, int* order_out, int* number_of_substeps,
                              int* number_of_past_steps, double* stable_step);
+
+/* Fraction of the step at which substep k = 1 .. number_of_substeps-1 is evaluated
+ * (TimeStepper::next_time_id: RungeKutta.cpp:34-58 butcher_tableau().substep_times,
+ * Rk3HesthavenSsp.cpp:36-48 {1, 1/2}; AdamsBashforth has no substeps).  Host-only. */
+int dgrhs_stepper_substep_fractions(int stepper, double* fractions);
 
 #ifdef __cplusplus
 }

@@ -199,6 +199,10 @@ _AB_CONST = {
     5: [251.0 / 720.0, -637.0 / 360.0, 109.0 / 30.0, -1387.0 / 360.0, 1901.0 / 720.0],
     6: [-95.0 / 288.0, 959.0 / 480.0, -3649.0 / 720.0, 4991.0 / 720.0, -2641.0 / 480.0,
         4277.0 / 1440.0],
+    7: [19087.0 / 60480.0, -5603.0 / 2520.0, 135713.0 / 20160.0, -10754.0 / 945.0,
+        235183.0 / 20160.0, -18637.0 / 2520.0, 198721.0 / 60480.0],
+    8: [-5257.0 / 17280.0, 32863.0 / 13440.0, -115747.0 / 13440.0, 2102243.0 / 120960.0,
+        -296053.0 / 13440.0, 242653.0 / 13440.0, -1152169.0 / 120960.0, 16083.0 / 4480.0],
 }
 
 
@@ -686,12 +690,19 @@ RK_TABLEAUS = {
 
 
 class Evolution:
-    def __init__(self, rhs, u0, t0, dt, stepper="AB3", post_update=None):
+    def __init__(self, rhs, u0, t0, dt, stepper="AB3", post_update=None, slab=None):
         """rhs(u, t) -> dt_u.  stepper: 'AB<k>' or 'RK3' (Rk3HesthavenSsp).
-        post_update(u) -> u: action after UpdateU in step_actions (the filter)."""
+        post_update(u) -> u: action after UpdateU in step_actions (the filter).
+        slab = (start, end, steps_per_slab): times and step size formed as the reference's
+        Slab / Time / TimeDelta / TimeStepId form them (Slab.hpp advance, Time.cpp:114-117,
+        :127-129, TimeStepId.cpp:72-82) instead of t0 + k dt; t0 and dt are then ignored."""
         self.post = post_update if post_update is not None else (lambda v: v)
         self.rhs = rhs
         self.u = u0.copy()
+        self.slab = slab
+        if slab is not None:
+            t0 = slab[0]
+            dt = (slab[1] - slab[0]) * (1.0 / slab[2])
         self.t0 = t0
         self.dt = dt
         self.stepper = stepper
@@ -703,7 +714,24 @@ class Evolution:
             self._self_start()
 
     def _time(self, frac):
-        return self.t0 + float(frac) * self.dt
+        if self.slab is None:
+            return self.t0 + float(frac) * self.dt
+        a, b, per_slab = self.slab
+        f = Fraction(frac) / per_slab          # in slabs
+        k = f.numerator // f.denominator
+        f -= k
+        for _ in range(k):                      # Slab::advance
+            a, b = b, b + (b - a)
+        g = 1 - f
+        return (g.numerator / g.denominator) * a + (f.numerator / f.denominator) * b
+
+    def _substep_time(self, n, c):
+        """time of a substep at the fraction c (a double) of the step that starts at step n"""
+        if c == 0.0:
+            return self._time(n)
+        if self.slab is None:
+            return self.t0 + (float(n) + c) * self.dt
+        return (1.0 - c) * self._time(n) + c * self._time(n + 1)
 
     def _eval(self, frac):
         self.rhs_evals += 1
@@ -758,10 +786,12 @@ class Evolution:
             u0 = self.u.copy()
             f0 = self._eval(n)
             self.u = self.post(u0 + dt * f0)
-            f1 = self._eval(n + 1)
+            self.rhs_evals += 1
+            f1 = self.rhs(self.u, self._substep_time(n, 1.0))
             u1 = self.u.copy()
             self.u = self.post(0.25 * (3.0 * u0 + u1 + dt * f1))
-            f2 = self._eval(n + Fraction(1, 2))
+            self.rhs_evals += 1
+            f2 = self.rhs(self.u, self._substep_time(n, 0.5))
             u2 = self.u.copy()
             self.u = self.post((1.0 / 3.0) * (u0 + 2.0 * u2 + 2.0 * dt * f2))
         elif self.stepper in RK_TABLEAUS:
@@ -772,9 +802,8 @@ class Evolution:
             u_start = self.u.copy()
             fs = []
             for k in range(nsub):
-                tk = float(n) + (0.0 if k == 0 else c[k - 1])
                 self.rhs_evals += 1
-                fs.append(self.rhs(self.u, self.t0 + tk * self.dt))
+                fs.append(self.rhs(self.u, self._substep_time(n, 0.0 if k == 0 else c[k - 1])))
                 row = b if k == nsub - 1 else A[k]
                 u = u_start.copy()
                 for coef, f in zip(row, fs):

@@ -107,6 +107,9 @@ struct dgrhs_ctx {
   // stepping
   int stepper = DGRHS_STEPPER_ADAMS_BASHFORTH, order = 1;
   double t0 = 0.0, dt = 0.0;
+  // exact slab bookkeeping (dgrhs_set_slab): first slab and steps per slab; 0 = t0 + k dt
+  double slab_start = 0.0, slab_end = 0.0;
+  int steps_per_slab = 0;
   long long tick_den = 1, step_index = 0;
   std::deque<HistoryEntry> history;
   std::deque<SubstepOp> pending;  // self-start program

@@ -177,7 +177,9 @@ void exponential_filter_matrix(int N, double alpha, unsigned half_power,
 // ---------------------------------------------------------------------------
 // Adams-Bashforth coefficients (AdamsCoefficients.cpp:13-42, :75-117)
 // ---------------------------------------------------------------------------
-const double kAbConst[7][6] = {
+// orders 7 and 8: integrals over one step of the Lagrange basis through the k previous
+// equally spaced times (the maximum order of the reference, AdamsBashforth.hpp:199)
+const double kAbConst[9][8] = {
     {},
     {1.0},
     {-0.5, 1.5},
@@ -185,7 +187,11 @@ const double kAbConst[7][6] = {
     {-3.0 / 8.0, 37.0 / 24.0, -59.0 / 24.0, 55.0 / 24.0},
     {251.0 / 720.0, -637.0 / 360.0, 109.0 / 30.0, -1387.0 / 360.0, 1901.0 / 720.0},
     {-95.0 / 288.0, 959.0 / 480.0, -3649.0 / 720.0, 4991.0 / 720.0, -2641.0 / 480.0,
-     4277.0 / 1440.0}};
+     4277.0 / 1440.0},
+    {19087.0 / 60480.0, -5603.0 / 2520.0, 135713.0 / 20160.0, -10754.0 / 945.0,
+     235183.0 / 20160.0, -18637.0 / 2520.0, 198721.0 / 60480.0},
+    {-5257.0 / 17280.0, 32863.0 / 13440.0, -115747.0 / 13440.0, 2102243.0 / 120960.0,
+     -296053.0 / 13440.0, 242653.0 / 13440.0, -1152169.0 / 120960.0, 16083.0 / 4480.0}};
 
 std::vector<double> variable_coefficients(std::vector<double> ct, double step_start,
                                           double step_end) {
@@ -580,12 +586,24 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   c->n_mortar_faces = 0;
   // external faces with the Bjorhus boundary condition
   std::vector<int32_t> bj;
-  for (int e = 0; e < c->nelem; ++e)
+  for (int e = 0; e < c->nelem; ++e) {
+    int dims_with_bjorhus = 0;
     for (int d = 0; d < 6; ++d)
       if (neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS ||
-          neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS_PHYSICAL)
+          neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS_PHYSICAL) {
         bj.insert(bj.end(),
                   {e, d, neighbors[(size_t)e * 6 + d] == DGRHS_NEIGHBOR_BJORHUS_PHYSICAL});
+        dims_with_bjorhus |= 1 << (d >> 1);
+      }
+    // The reference applies the external faces of an element one after the other: a later
+    // face projects the time derivative that earlier faces have already corrected on the
+    // shared edge / corner points (BoundaryConditionsImpl.hpp:277-278, 636-660).  The
+    // Bjorhus kernel evaluates every face from the uncorrected volume time derivative,
+    // which is the same thing only if the faces share no points (opposite faces).
+    if (dims_with_bjorhus & (dims_with_bjorhus - 1))
+      return fail("element %d has ConstraintPreservingBjorhus faces in more than one dimension "
+                  "(faces that share edge points): not supported", e);
+  }
   if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
   c->bjorhus_faces = nullptr;
   c->n_bjorhus_faces = (int)(bj.size() / 3);
@@ -1124,7 +1142,7 @@ int dgrhs_set_stepper(dgrhs_ctx* c, int stepper, int order, double t0, double dt
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));
   if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
-    if (order < 1 || order > 6) return fail("Adams-Bashforth order must be in [1, 6]");
+    if (order < 1 || order > 8) return fail("Adams-Bashforth order must be in [1, 8]");
   } else if (stepper == DGRHS_STEPPER_RK3_HESTHAVEN) {
     order = 3;
   } else if (is_tableau_stepper(stepper)) {
@@ -1137,6 +1155,7 @@ int dgrhs_set_stepper(dgrhs_ctx* c, int stepper, int order, double t0, double dt
   c->t0 = t0;
   c->dt = dt;
   c->step_index = 0;
+  c->steps_per_slab = 0;
   c->rk_substep = 0;
   c->in_substep = false;
   c->history.clear();
@@ -1173,6 +1192,45 @@ int dgrhs_set_stepper(dgrhs_ctx* c, int stepper, int order, double t0, double dt
   return 0;
 }
 
+// Time of step boundary `tick` (in units of dt / tick_den) the way the reference forms it:
+// a Time is a slab plus an exact rational fraction f of it, value (1 - f) start + f end
+// (Time.cpp:114-117); the slab that follows [a, b] is [b, b + (b - a)] (Slab.hpp advance).
+// Without dgrhs_set_slab: t0 + (tick / tick_den) dt.
+static double time_at_tick(const dgrhs_ctx* c, long long tick) {
+  if (c->steps_per_slab == 0) return c->t0 + ((double)tick / (double)c->tick_den) * c->dt;
+  const long long den = (long long)c->steps_per_slab * c->tick_den;
+  long long slab = tick / den, num = tick % den;
+  double a = c->slab_start, b = c->slab_end;
+  for (long long s = 0; s < slab; ++s) {
+    const double next = b + (b - a);
+    a = b;
+    b = next;
+  }
+  return ((double)(den - num) / (double)den) * a + ((double)num / (double)den) * b;
+}
+
+int dgrhs_set_slab(dgrhs_ctx* c, double slab_start, double slab_end, int steps_per_slab) {
+  CHECK_CTX(c);
+  if (c->dt == 0.0) return fail("set_stepper has not been called");
+  if (c->in_substep || c->step_index != 0) return fail("set_slab must follow set_stepper directly");
+  if (!(slab_start < slab_end) || steps_per_slab < 1) return fail("bad slab");
+  c->slab_start = slab_start;
+  c->slab_end = slab_end;
+  c->steps_per_slab = steps_per_slab;
+  c->t0 = slab_start;
+  // TimeDelta::value (Time.cpp:127-129): slab duration times the fraction's double value
+  c->dt = (slab_end - slab_start) * (1.0 / (double)steps_per_slab);
+  return 0;
+}
+
+int dgrhs_self_start_substeps_left(dgrhs_ctx* c, int* n) {
+  CHECK_CTX(c);
+  int k = 0;
+  for (const SubstepOp& op : c->pending) k += op.kind != SubstepOp::kRestoreU0;
+  *n = k;
+  return 0;
+}
+
 int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
   CHECK_CTX(c);
   CU(cudaSetDevice(c->device));
@@ -1196,7 +1254,7 @@ int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
     c->cur_slot = c->free_slots.back();
     c->free_slots.pop_back();
     c->dt_last = c->dt_slots[c->cur_slot];
-    *time = c->t0 + ((double)c->cur_op.tick / (double)c->tick_den) * c->dt;
+    *time = time_at_tick(c, c->cur_op.tick);
   } else if (is_tableau_stepper(c->stepper)) {
     // RungeKutta::next_time_id (RungeKutta.cpp:37-59): substep k > 0 is at
     // t + dt * substep_times[k-1]
@@ -1204,13 +1262,26 @@ int dgrhs_begin_substep(dgrhs_ctx* c, double* time) {
     const double frac = c->rk_substep == 0 ? 0.0 : tab.substep_times[c->rk_substep - 1];
     c->cur_slot = c->rk_substep;
     c->dt_last = c->dt_slots[c->cur_slot];
-    *time = c->t0 + ((double)c->step_index + frac) * c->dt;
+    // TimeStepId::next_substep: (1 - frac) t_step + frac t_next_step
+    if (c->steps_per_slab == 0)
+      *time = c->t0 + ((double)c->step_index + frac) * c->dt;
+    else if (c->rk_substep == 0)
+      *time = time_at_tick(c, c->step_index);
+    else
+      *time = (1.0 - frac) * time_at_tick(c, c->step_index) +
+              frac * time_at_tick(c, c->step_index + 1);
   } else {
     const long long base = c->step_index * 2;
     const long long off[3] = {0, 2, 1};  // substep times t, t+dt, t+dt/2
     c->cur_slot = 0;
     c->dt_last = c->dt_slots[0];
-    *time = c->t0 + ((double)(base + off[c->rk_substep]) / 2.0) * c->dt;
+    if (c->steps_per_slab == 0) {
+      *time = c->t0 + ((double)(base + off[c->rk_substep]) / 2.0) * c->dt;
+    } else {
+      const double frac = 0.5 * (double)off[c->rk_substep];
+      const double ts = time_at_tick(c, base), te = time_at_tick(c, base + 2);
+      *time = c->rk_substep == 0 ? ts : (1.0 - frac) * ts + frac * te;
+    }
   }
   c->in_substep = true;
   return prepare_fused_update(c);
@@ -1642,7 +1713,7 @@ int dgrhs_take_steps(dgrhs_ctx* c, int n_steps) {
   return 0;
 }
 
-double dgrhs_time(dgrhs_ctx* c) { return c ? c->t0 + (double)c->step_index * c->dt : 0.0; }
+double dgrhs_time(dgrhs_ctx* c) { return c ? time_at_tick(c, c->step_index * c->tick_den) : 0.0; }
 int64_t dgrhs_rhs_evaluations(dgrhs_ctx* c) { return c ? c->rhs_evals : 0; }
 
 int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
@@ -1766,7 +1837,7 @@ int dgrhs_collocation_points_and_weights(int N, double* points, double* weights)
 
 int dgrhs_adams_bashforth_coefficients(int order, const double* times, double step_start,
                                        double step_end, double* coefficients) {
-  if (order < 1 || order > 6) return fail("order must be in [1, 6]");
+  if (order < 1 || order > 8) return fail("order must be in [1, 8]");
   const double step = step_end - step_start;
   bool constant = true;
   std::vector<double> control{0.0};
@@ -1797,12 +1868,26 @@ int dgrhs_adams_bashforth_coefficients(int order, const double* times, double st
 // of the tableau -- the CPU tests compare with the constants of the reference
 // (AdamsBashforth.cpp:72-90, Rk3HesthavenSsp.cpp:23-26, Rk3Owren.cpp:15,
 // Rk3Kennedy.cpp:10, ClassicalRungeKutta4.cpp:22, DormandPrince5.cpp:19).
+int dgrhs_stepper_substep_fractions(int stepper, double* fractions) {
+  if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) return 0;
+  if (stepper == DGRHS_STEPPER_RK3_HESTHAVEN) {
+    fractions[0] = 1.0;
+    fractions[1] = 0.5;
+    return 0;
+  }
+  if (!is_tableau_stepper(stepper)) return fail("unknown time stepper %d", stepper);
+  const ButcherTableau& tab = butcher_tableau(stepper);
+  const size_t nsub = tab.result_coefficients.size();
+  for (size_t k = 0; k + 1 < nsub; ++k) fractions[k] = tab.substep_times[k];
+  return 0;
+}
+
 int dgrhs_stepper_properties(int stepper, int order, int* order_out, int* number_of_substeps,
                              int* number_of_past_steps, double* stable_step) {
   int ord = 0, substeps = 0, past = 0;
   double stable = 0.0;
   if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
-    if (order < 1 || order > 6) return fail("AdamsBashforth order must be in [1, 6]");
+    if (order < 1 || order > 8) return fail("AdamsBashforth order must be in [1, 8]");
     ord = order;
     substeps = 1;
     past = order - 1;

@@ -700,7 +700,7 @@ class TimeStepper {
 };
 class AdamsBashforth : public TimeStepper {
  public:
-  static constexpr size_t maximum_order = 6;  // of this path (the reference allows 8)
+  static constexpr size_t maximum_order = 8;  // AdamsBashforth.hpp:199
   explicit AdamsBashforth(size_t order) : order_(order) { (void)props(); }  // throws on a bad order
   int id() const override { return DGRHS_STEPPER_ADAMS_BASHFORTH; }
 

@@ -42,6 +42,7 @@ EXPORTS = [
     "dgrhs_lift_flux",
     "dgrhs_comm_unique_id", "dgrhs_comm_init", "dgrhs_set_halo_peers", "dgrhs_exchange_halo",
     "dgrhs_set_phase_timing", "dgrhs_get_phase_times",
+    "dgrhs_set_slab", "dgrhs_self_start_substeps_left", "dgrhs_stepper_substep_fractions",
 ]
 
 _lib = None
@@ -372,6 +373,16 @@ class Context:
     def set_stepper(self, stepper, order, t0, dt):
         _check(self._lib.dgrhs_set_stepper(self._h, stepper, order, ctypes.c_double(t0),
                                            ctypes.c_double(dt)))
+
+    def set_slab(self, slab_start, slab_end, steps_per_slab=1):
+        """Exact slab bookkeeping of the reference (Time/Slab.hpp, Time.cpp:114-117)."""
+        _check(self._lib.dgrhs_set_slab(self._h, ctypes.c_double(slab_start),
+                                        ctypes.c_double(slab_end), int(steps_per_slab)))
+
+    def self_start_substeps_left(self):
+        n = ctypes.c_int(0)
+        _check(self._lib.dgrhs_self_start_substeps_left(self._h, ctypes.byref(n)))
+        return n.value
 
     def set_exponential_filter(self, enable: bool, alpha: float = 36.0, half_power: int = 64):
         _check(self._lib.dgrhs_set_exponential_filter(self._h, int(enable),

@@ -23,7 +23,7 @@ int main() {
   show("ClassicalRungeKutta4", TimeSteppers::ClassicalRungeKutta4{});
   show("DormandPrince5", TimeSteppers::DormandPrince5{});
   bool threw = false;
-  try { TimeSteppers::AdamsBashforth bad(7); } catch (const std::runtime_error&) { threw = true; }
+  try { TimeSteppers::AdamsBashforth bad(9); } catch (const std::runtime_error&) { threw = true; }
   std::printf("bad_order_throws %d\n", threw ? 1 : 0);
   return 0;
 }

@@ -82,7 +82,7 @@ def test_exponential_filter_matrix(N):
 
 # TimeStepper::order / number_of_substeps / number_of_past_steps / stable_step of the
 # reference: AdamsBashforth.cpp:60-95 (stable steps 1, 1/2, 3/11, 3/20, 45/551, 5/114
-# follow from its alternating coefficient sum), Rk3HesthavenSsp.cpp:21-26,
+# follow from its alternating coefficient sum; orders 7 and 8: 945/40633, 945/77432), Rk3HesthavenSsp.cpp:21-26,
 # Rk3Owren.cpp:8-15, Rk3Kennedy.cpp:8-10, ClassicalRungeKutta4.cpp:10-22,
 # DormandPrince5.cpp:8-19
 _RK3_STABLE = 0.5 * (1.0 + np.cbrt(4.0 + np.sqrt(17.0)) - 1.0 / np.cbrt(4.0 + np.sqrt(17.0)))
@@ -93,6 +93,8 @@ STEPPER_PROPERTIES = {
     "AdamsBashforth4": (lib.STEPPER_ADAMS_BASHFORTH, 4, (4, 1, 3, 3.0 / 20.0)),
     "AdamsBashforth5": (lib.STEPPER_ADAMS_BASHFORTH, 5, (5, 1, 4, 45.0 / 551.0)),
     "AdamsBashforth6": (lib.STEPPER_ADAMS_BASHFORTH, 6, (6, 1, 5, 5.0 / 114.0)),
+    "AdamsBashforth7": (lib.STEPPER_ADAMS_BASHFORTH, 7, (7, 1, 6, 945.0 / 40633.0)),
+    "AdamsBashforth8": (lib.STEPPER_ADAMS_BASHFORTH, 8, (8, 1, 7, 945.0 / 77432.0)),
     "Rk3HesthavenSsp": (lib.STEPPER_RK3_HESTHAVEN, 0, (3, 3, 0, _RK3_STABLE)),
     "Rk3Owren": (lib.STEPPER_RK3_OWREN, 0, (3, 3, 0, 1.2563726633091645)),
     "Rk3Kennedy": (lib.STEPPER_RK3_KENNEDY, 0, (3, 4, 0, 1.832102281377816)),
@@ -113,7 +115,7 @@ def test_stepper_properties_match_reference_constants():
         if name in orc.RK_TABLEAUS:
             assert len(orc.RK_TABLEAUS[name][2]) == want[1]
     with pytest.raises(lib.DgrhsError, match="order must be in"):
-        lib.stepper_properties(lib.STEPPER_ADAMS_BASHFORTH, 7)
+        lib.stepper_properties(lib.STEPPER_ADAMS_BASHFORTH, 9)
     with pytest.raises(lib.DgrhsError, match="unknown time stepper"):
         lib.stepper_properties(17)
 
@@ -137,3 +139,36 @@ def test_cpp_time_stepper_shims_host_only():
         o, s, p, st = rows[name]
         assert (int(o), int(s), int(p)) == want[:3]
         assert abs(float(st) - want[3]) < 1e-13 * want[3]
+
+
+def _build_time_types_test():
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_build", "time_types_test")
+    src = os.path.join(ROOT, "tests", "helpers", "time_types_test.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "spectre_b200", "host"),
+                           "-o", exe, src, "-L", os.path.join(ROOT, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(ROOT, "spectre_b200")])
+    return exe
+
+
+def test_time_value_types_reference_known_answers():
+    """Rational / Slab / Time / TimeDelta / TimeStepId of host/SpectreTime.hpp against the
+    known answers of the reference's Test_Slab.cpp, Test_Time.cpp, Test_TimeStepId.cpp
+    (round-off-prone slab ends included) and the id sequences of next_time_id for every
+    stepper; host only."""
+    import subprocess
+    out = subprocess.run([_build_time_types_test()], capture_output=True, text=True)
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
+
+
+def test_substep_fractions():
+    import ctypes
+    h = lib.load()
+    for stepper, want in ((lib.STEPPER_RK3_HESTHAVEN, [1.0, 0.5]),
+                          (lib.STEPPER_RK3_OWREN, [12.0 / 23.0, 4.0 / 5.0]),
+                          (lib.STEPPER_RK4, [0.5, 0.5, 1.0]),
+                          (lib.STEPPER_DORMAND_PRINCE5, [0.2, 0.3, 0.8, 8.0 / 9.0, 1.0])):
+        buf = (ctypes.c_double * 8)()
+        assert h.dgrhs_stepper_substep_fractions(stepper, buf) == 0
+        assert list(buf[:len(want)]) == want

@@ -139,4 +139,10 @@ def test_bjorhus_misuse():
     gh = lib.Context(lib.SYSTEM_GH, N, 1)
     with pytest.raises(lib.DgrhsError, match="needs inertial coordinates"):
         gh.set_geometry(brick.inverse_jacobian(), None, nbr)
+    # faces that share edge points would have to be applied one after the other
+    # (BoundaryConditionsImpl.hpp:277-278, 636-660): rejected, opposite faces are fine
+    with pytest.raises(lib.DgrhsError, match="more than one dimension"):
+        gh.set_geometry(brick.inverse_jacobian(), brick.coords(), nbr)
+    opposite = np.array([[lib.BJORHUS, lib.BJORHUS, -1, -1, -1, -1]], dtype=np.int32)
+    gh.set_geometry(brick.inverse_jacobian(), brick.coords(), opposite)
     gh.close()

@@ -105,8 +105,8 @@ def test_misuse_errors():
         ctx.set_demand_outgoing_char_speeds(True)
     with pytest.raises(lib.DgrhsError, match="set_stepper has not been called"):
         ctx.begin_substep()
-    with pytest.raises(lib.DgrhsError, match=r"order must be in \[1, 6\]"):
-        ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 7, 0.0, 1e-3)
+    with pytest.raises(lib.DgrhsError, match=r"order must be in \[1, 8\]"):
+        ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 9, 0.0, 1e-3)
     with pytest.raises(lib.DgrhsError, match="unknown stepper"):
         ctx.set_stepper(17, 3, 0.0, 1e-3)
     ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 2, 0.0, 1e-3)

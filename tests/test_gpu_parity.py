@@ -551,9 +551,9 @@ def test_time_dependent_dirichlet_analytic_gauge_wave():
     ev.ctx.close()
 
 
-@pytest.mark.parametrize("order", [5, 6])
+@pytest.mark.parametrize("order", [5, 6, 7, 8])
 def test_high_order_adams_bashforth(order):
-    """AB5/AB6 (more old terms than the fused update carries: separate update
+    """AB5..AB8, the reference's maximum order (more old terms than the fused update carries: separate update
     kernel) incl. the self-start, vs the oracle."""
     N, dt = 4, 1e-3
     brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
