@@ -48,6 +48,9 @@ enum {
                                       time of every RHS call */
 };
 
+/* Spectral::MortarSize (Spectral/SegmentSize.hpp) */
+enum { DGRHS_MORTAR_FULL = 0, DGRHS_MORTAR_LOWER_HALF = 1, DGRHS_MORTAR_UPPER_HALF = 2 };
+
 /* TimeSteppers (Time/TimeSteppers/) */
 enum {
   DGRHS_STEPPER_ADAMS_BASHFORTH = 0, /* AdamsBashforth.cpp:120-201, order 1..8 */
@@ -321,6 +324,11 @@ int dgrhs_set_fused_update(dgrhs_ctx* ctx, int enable);
  * 64): every evolved component of every element is multiplied by the filter
  * matrix along xi, eta, zeta after each substep update.  Disabled by default. */
 int dgrhs_set_exponential_filter(dgrhs_ctx* ctx, int enable, double alpha, int half_power);
+/* Filters::Exponential applied once to the resident state, outside a substep:
+ * apply_matrices(u, {F, F, F}) on every evolved component (LinearOperators/
+ * ExponentialFilter.cpp:45-76; the action dg::Actions::Filter, Filtering.hpp:120-165,
+ * runs it after every substep update -- dgrhs_end_substep does that itself). */
+int dgrhs_apply_exponential_filter(dgrhs_ctx* ctx);
 /* Spectral::filtering::exponential_filter(Mesh<1>{N, Legendre, GaussLobatto},
  * alpha, half_power) (Spectral/Filtering.cpp:20-32), row-major [N*N]. */
 int dgrhs_exponential_filter_matrix(int n_points_1d, double alpha, int half_power,
@@ -450,6 +458,44 @@ int dgrhs_adams_bashforth_coefficients(int order, const double* history_times,
  * AdamsBashforth only; any output pointer may be NULL.  Host-only. */
 int dgrhs_stepper_properties(int stepper, int order, int* order_out, int* number_of_substeps,
                              int* number_of_past_steps, double* stable_step);
+
+/* Row `substep` of the Butcher tableau as RungeKutta::update_u_impl uses it
+ * (RungeKutta.cpp:69-122): the coefficients of f_0 .. f_substep for the update that
+ * follows substep `substep`; the last substep returns the result coefficients. */
+int dgrhs_butcher_row(int stepper, int substep, double* coefficients);
+
+/* TimeStepper::update_u(u, history, time_step) (TimeStepper.hpp:96-102) on a flat span of
+ * `size` doubles (host pointers, one round trip).  history_derivatives [n_history][size],
+ * oldest first.  AdamsBashforth (AdamsBashforth.cpp:120-135): n_history = order entries at
+ * history_times (arbitrary spacing, AdamsCoefficients.hpp:64-104), u holds the value at the
+ * newest time and becomes the value one time_step later.  Substep methods: the history holds
+ * the derivatives of the substeps done so far in this step, step_start_value the value at
+ * the start of the step; u holds the current substep value and becomes the next one
+ * (Rk3HesthavenSsp.cpp:63-81, RungeKutta.cpp:69-122). */
+int dgrhs_update_u(int stepper, int order, long long size, double* u, int n_history,
+                   const double* history_times, const double* history_derivatives,
+                   const double* step_start_value, double time_step);
+
+/* dg::project_to_mortar / dg::project_from_mortar (NumericalAlgorithms/DiscontinuousGalerkin/
+ * MortarHelpers.hpp:74-129) for variables on a face: [n_comps][extent_b][extent_a], a fastest.
+ * face_extents / mortar_extents: points per face dimension (mortar >= face,
+ * MortarHelpers.cpp:22-49); mortar_size: DGRHS_MORTAR_* per dimension.  To the mortar:
+ * interpolation (Projection.cpp:279-362); from the mortar: L2 projection
+ * (Projection.cpp:57-262).  Dimensions that need no projection are skipped like
+ * apply_matrices does. */
+int dgrhs_project_to_mortar(int n_comps, const int* face_extents, const int* mortar_extents,
+                            const int* mortar_size, const double* face_vars, double* mortar_vars);
+int dgrhs_project_from_mortar(int n_comps, const int* face_extents, const int* mortar_extents,
+                              const int* mortar_size, const double* mortar_vars,
+                              double* face_vars);
+
+/* orient_variables_on_slice (Domain/Structure/OrientationMapHelpers.cpp:25-120) for the face
+ * of a 3-D element: vars [n_comps][extent_b][extent_a] in this element's frame ->
+ * the neighbour's frame.  permutation as in dgrhs_set_neighbor_orientations: bit 0 swaps the
+ * two face coordinates, bits 1 / 2 flip the neighbour's first / second face coordinate
+ * (host/SpectreShims.hpp face_orientation() derives it from an OrientationMap<3>). */
+int dgrhs_orient_variables_on_slice(int n_comps, const int* slice_extents, int permutation,
+                                    const double* vars, double* oriented);
 
 /* Fraction of the step at which substep k = 1 .. number_of_substeps-1 is evaluated
  * (TimeStepper::next_time_id: RungeKutta.cpp:34-58 butcher_tableau().substep_times,

@@ -84,6 +84,8 @@ struct dgrhs_ctx {
   double* u_alt = nullptr;        // second state buffer for the fused update
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
+  double filterF_host[144] = {};  // the same on the host (kernel parameter of the filter pass)
+  int num_sms = 148;
   unsigned long long* violations = nullptr;  // DemandOutgoingCharSpeeds status (device)
   // ConstraintPreservingBjorhus faces (DGRHS_NEIGHBOR_BJORHUS in the neighbour table)
   int n_bjorhus_faces = 0;

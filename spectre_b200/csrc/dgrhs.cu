@@ -474,6 +474,7 @@ int dgrhs_create(dgrhs_ctx** out, int system, int N, int nelem, int nghost, int 
   c->nelem = nelem;
   c->nghost = nghost;
   c->device = device;
+  CU(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   c->C = system == DGRHS_SYSTEM_GH ? 50 : 5;
   c->S = system == DGRHS_SYSTEM_GH ? 3 : 1;
   c->HC = c->C + 3 + (system == DGRHS_SYSTEM_GH ? 2 : 1);
@@ -1073,7 +1074,12 @@ int dgrhs_compute_time_derivative(dgrhs_ctx* c, double time, int volume_only) {
     return fail("context exchanges faces with other ranks: use pack_halo + "
                 "compute_time_derivative_range");
   ++c->rhs_evals;
-  return rhs_range(c, time, c->dt_last, 0, c->nelem, volume_only != 0, true);
+  // inside a substep (begin_substep ... end_substep) the stepper update may be fused into
+  // the volume kernel; a volume-only evaluation is a diagnostic and never is
+  if (c->in_substep && c->upd_active && volume_only)
+    return fail("volume_only evaluation inside a substep with the fused update");
+  return rhs_range(c, time, c->dt_last, 0, c->nelem, volume_only != 0, true,
+                   (c->in_substep && c->upd_active) ? c->pending_upd : dg::UpdateArgs{});
 }
 
 int dgrhs_set_interior_count(dgrhs_ctx* c, int n_interior) {
@@ -1300,7 +1306,16 @@ int dgrhs_set_exponential_filter(dgrhs_ctx* c, int enable, double alpha, int hal
   exponential_filter_matrix(c->N, alpha, (unsigned)half_power, F);
   if (!c->filterF && dev_alloc(&c->filterF, F.size())) return 1;
   CU(cudaMemcpy(c->filterF, F.data(), F.size() * 8, cudaMemcpyHostToDevice));
+  std::memcpy(c->filterF_host, F.data(), F.size() * 8);
   return 0;
+}
+
+int dgrhs_apply_exponential_filter(dgrhs_ctx* c) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (!c->filterF) return fail("no exponential filter set");
+  if (c->in_substep) return fail("apply_exponential_filter inside a substep");
+  return apply_filter(c);
 }
 
 int dgrhs_exponential_filter_matrix(int N, double alpha, int half_power, double* matrix) {
@@ -1868,6 +1883,17 @@ int dgrhs_adams_bashforth_coefficients(int order, const double* times, double st
 // of the tableau -- the CPU tests compare with the constants of the reference
 // (AdamsBashforth.cpp:72-90, Rk3HesthavenSsp.cpp:23-26, Rk3Owren.cpp:15,
 // Rk3Kennedy.cpp:10, ClassicalRungeKutta4.cpp:22, DormandPrince5.cpp:19).
+int dgrhs_butcher_row(int stepper, int substep, double* coefficients) {
+  if (!is_tableau_stepper(stepper)) return fail("stepper %d has no Butcher tableau", stepper);
+  const ButcherTableau& tab = butcher_tableau(stepper);
+  const int nsub = (int)tab.result_coefficients.size();
+  if (substep < 0 || substep >= nsub) return fail("substep out of range");
+  const std::vector<double>& row =
+      substep == nsub - 1 ? tab.result_coefficients : tab.substep_coefficients[substep];
+  for (int i = 0; i <= substep; ++i) coefficients[i] = i < (int)row.size() ? row[i] : 0.0;
+  return 0;
+}
+
 int dgrhs_stepper_substep_fractions(int stepper, double* fractions) {
   if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) return 0;
   if (stepper == DGRHS_STEPPER_RK3_HESTHAVEN) {

@@ -293,6 +293,7 @@ struct GhVolArgs {
   DampedHarmonicParams dh;
   int elem_begin;
   UpdateArgs upd;
+  int prefetch_dist;  // CTAs ahead whose prologue inputs are pulled into L2 (0: off)
 };
 
 template <int N>
@@ -452,6 +453,37 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
 #pragma unroll
       for (int m = 0; m < 3; ++m)
         fused_prefetch(a.upd, ubase + (size_t)(20 + m + 3 * s) * npad, hv[2 + m]);
+    }
+    if (a.prefetch_dist > 0) {
+      // The CTA that will run on some SM when this one retires starts with a prologue that
+      // waits on ~80 global loads per thread (12 % of the kernel's stall samples at N = 12,
+      // one CTA per SM, nothing to overlap with): request its inputs into L2 now, a few
+      // component rows per pair.
+      const unsigned int bt = blockIdx.x + (unsigned int)a.prefetch_dist;
+      if (bt < gridDim.x) {
+        const int et = a.elem_begin + (int)(bt / Cfg<N>::nchunk);
+        const int ptt = (int)(bt % Cfg<N>::nchunk) * T + tid;
+        if (ptt < n) {
+          const double* ut = a.u + (size_t)et * 50 * npad + ptt;
+          prefetch_l2(ut + (size_t)s * npad);
+          prefetch_l2(ut + (size_t)(10 + s) * npad);
+#pragma unroll
+          for (int m = 0; m < 3; ++m) prefetch_l2(ut + (size_t)(20 + m + 3 * s) * npad);
+          if (s < 9)
+            prefetch_l2(a.invjac + ((size_t)et * 9 + s) * npad + ptt);
+          else
+#pragma unroll
+            for (int m = 0; m < 3; ++m) prefetch_l2(a.stat + ((size_t)et * 3 + m) * npad + ptt);
+          if constexpr (kGauge == 1) {
+            if (s < 4) prefetch_l2(a.gH + ((size_t)et * 4 + s) * npad + ptt);
+            prefetch_l2(a.gdH + ((size_t)et * 16 + s) * npad + ptt);
+            if (s < 6) prefetch_l2(a.gdH + ((size_t)et * 16 + 10 + s) * npad + ptt);
+          }
+          if constexpr (kGauge == 2) {
+            if (s < 3) prefetch_l2(a.coords + ((size_t)et * 3 + s) * npad + ptt);
+          }
+        }
+      }
     }
     mbar_wait(&bars[stage], (s / NS) & 1);
     const double* t = ring + stage * SD;
@@ -1911,102 +1943,88 @@ __global__ void __launch_bounds__(256) gh_constraints_kernel(ConstraintArgs a) {
 // Exponential filter after the substep: dg::Actions::Filter<
 // Filters::Exponential<0>> = apply_matrices(u, {F, F, F}) on every evolved
 // component (LinearOperators/ExponentialFilter.cpp:45-76, Spectral/Filtering.cpp
-// :20-32).  One CTA per (element, component); xi, eta, zeta in that order like
-// ApplyMatrices.cpp.
+// :20-32).
 // --------------------------------------------------------------------------
 struct FilterArgs {
   double* u;        // [E][C][npad]
-  const double* F;  // [N*N] row-major filter matrix
-  int per_cta;      // component blocks per CTA (divides E*C)
+  int ntiles;       // E * C component blocks
+  double Fm[144];   // [N][N] row-major filter matrix (kernel parameter = constant bank:
+                    // with the loops unrolled every entry is an immediate operand of its DFMA)
 };
 
-// Register-blocked line form: a task is (grid line, group of R output rows); the
-// thread keeps its R x N block of the filter matrix in registers for the whole
-// kernel, loads the line's N values (the NG threads of a line read the same
-// addresses: broadcast) and produces R filtered values with R*N FMAs -- N
-// shared-memory loads per R*N FMAs instead of 2N loads per N FMAs (round 1: one
-// thread per point, N-term dot products with both operands from shared memory:
-// 8.4 ms for 6144 elements at N = 12; matrix rows as broadcast shared-memory
-// operands: 4.7 ms, bound by the LSU).  Passes ping-pong between two padded tiles
-// (odd row stride: no bank conflicts in any of the three directions).
+// Line form: a thread filters one whole grid line in registers -- N loads, N*N FMAs whose
+// matrix operand comes from the constant bank, N stores -- so a pass costs one shared-memory
+// load and one store per point (round 1: one thread per point, both operands of every FMA
+// from shared memory, 8.4 ms for 6144 elements at N = 12; round 2a: R x N register blocks of
+// the matrix, 4 loads per point and pass, 2.85 ms, shared-memory wavefronts at 71 %).
+// A CTA works on G component blocks at once, N*N threads each.  The thread (a, b) of a block
+//   loads the zeta line (i, j) = (a, b) from global memory (coalesced) into the padded tile,
+//   filters the xi line (j, k) = (a, b), then the eta line (i, k) = (a, b) in place,
+//   filters the zeta line (i, j) = (a, b) and stores it to global memory (coalesced);
+// xi, eta, zeta in that order like ApplyMatrices.cpp.  Tile index i + RS j + PS k with an odd
+// row stride RS and a plane stride PS = N mod 16: no bank conflicts along xi and eta.
 template <int N>
 struct FilterCfg {
-  static constexpr int R0 = 40 / N > 0 ? (40 / N < N ? 40 / N : N) : 1;
-  static constexpr int NG = (N + R0 - 1) / R0;  // row groups per line
-  static constexpr int R = (N + NG - 1) / NG;   // output rows per task
-  static constexpr int T = 192;                 // multiple of 32 and of every NG (1..4)
-  static constexpr int RS = N | 1;              // odd row stride: point (i, l) at i + RS * l
-  static_assert(T % NG == 0, "a thread keeps one row group");
+  static constexpr int f = N * N;
+  static constexpr int G = 320 / f > 0 ? 320 / f : 1;  // component blocks per CTA pass
+  static constexpr int T = (G * f + 31) / 32 * 32;
+  static constexpr int RS = N | 1;
+  static constexpr int PS = RS * N + ((N - RS * N) % 16 + 16) % 16;
+  static constexpr int tile = PS * N;
+  static constexpr int smem_bytes = G * tile * 8;
 };
 
+// dst[stride * q] = sum_m F[q][m] x[m]
 template <int N>
-__global__ void __launch_bounds__(FilterCfg<N>::T) exponential_filter_kernel(FilterArgs a) {
-  using F = FilterCfg<N>;
-  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, f = N * N, T = F::T, RS = F::RS;
-  constexpr int NG = F::NG, R = F::R;
-  constexpr int kIters = (n + T - 1) / T;
-  __shared__ double t0[f * RS];
-  __shared__ double t1[f * RS];
-  __shared__ double sF[N * N];
-  // a CTA filters a.per_cta consecutive component blocks; the next block is fetched
-  // into registers while the current one is filtered
-  double* ub = a.u + (size_t)blockIdx.x * a.per_cta * npad;
-  const int tid = threadIdx.x;
-  for (int p = tid; p < N * N; p += T) sF[p] = a.F[p];
-  double v[kIters];
-  // all loads of the thread in flight at once (a rolled loop would wait for each)
+__device__ __forceinline__ void filter_line(const FilterArgs& a, const double (&x)[N],
+                                            double* __restrict__ dst, int stride) {
 #pragma unroll
-  for (int it = 0; it < kIters; ++it) {
-    const int p = tid + it * T;
-    v[it] = p < n ? ub[p] : 0.0;
+  for (int q = 0; q < N; ++q) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) s = fma(a.Fm[q * N + m], x[m], s);
+    dst[stride * q] = s;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(FilterCfg<N>::T) exponential_filter_kernel(
+    const __grid_constant__ FilterArgs a) {
+  using F = FilterCfg<N>;
+  constexpr int npad = Cfg<N>::npad, f = N * N, RS = F::RS, PS = F::PS, G = F::G;
+  extern __shared__ __align__(16) unsigned char filter_smem[];
+  const int tid = threadIdx.x;
+  const int g = tid / f, l = tid % f, la = l % N, lb = l / N;
+  double* t = reinterpret_cast<double*>(filter_smem) + g * F::tile;
+  const bool mine = tid < G * f && blockIdx.x * G + g < a.ntiles;
+  double* ug = a.u + (size_t)(blockIdx.x * G + (mine ? g : 0)) * npad + l;
+  double x[N];
+  if (mine) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) x[q] = ug[f * q];
+#pragma unroll
+    for (int q = 0; q < N; ++q) t[la + RS * lb + PS * q] = x[q];
   }
   __syncthreads();
-  const int g = tid % NG, r0 = g * R;
-  double Fb[R][N];
+  if (mine) {  // xi: the line (j, k) = (la, lb)
+    double* line = t + RS * la + PS * lb;
 #pragma unroll
-  for (int q = 0; q < R; ++q)
+    for (int m = 0; m < N; ++m) x[m] = line[m];
+    filter_line<N>(a, x, line, 1);
+  }
+  __syncthreads();
+  if (mine) {  // eta: the line (i, k) = (la, lb)
+    double* line = t + la + PS * lb;
 #pragma unroll
-    for (int m = 0; m < N; ++m) Fb[q][m] = sF[(r0 + q < N ? r0 + q : N - 1) * N + m];
-#pragma unroll 1
-  for (int blk = 0; blk < a.per_cta; ++blk) {
-    double* uc = ub + (size_t)blk * npad;
+    for (int m = 0; m < N; ++m) x[m] = line[RS * m];
+    filter_line<N>(a, x, line, RS);
+  }
+  __syncthreads();
+  if (mine) {  // zeta: the line (i, j) = (la, lb), straight to global memory
+    const double* line = t + la + RS * lb;
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int p = tid + it * T;
-      if (p < n) t0[p % N + RS * (p / N)] = v[it];
-    }
-    __syncthreads();  // also: the stores of the previous block have read t1
-    if (blk + 1 < a.per_cta) {
-#pragma unroll
-      for (int it = 0; it < kIters; ++it) {
-        const int p = tid + it * T;
-        v[it] = p < n ? uc[npad + p] : 0.0;
-      }
-    }
-    // xi, eta, zeta in that order like ApplyMatrices.cpp: t0 -> t1 -> t0 -> t1
-#pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-      const double* __restrict__ src = (pass == 1) ? t1 : t0;
-      double* __restrict__ dst = (pass == 1) ? t0 : t1;
-      for (int task = tid; task < NG * f; task += T) {
-        const int l = task / NG;  // line; task % NG == g
-        const int base =
-            pass == 0 ? RS * l : (pass == 1 ? l % N + RS * N * (l / N) : l % N + RS * (l / N));
-        const int stride = pass == 0 ? 1 : (pass == 1 ? RS : RS * N);
-        double x[N];
-#pragma unroll
-        for (int m = 0; m < N; ++m) x[m] = src[base + m * stride];
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-          double w = 0.0;
-#pragma unroll
-          for (int m = 0; m < N; ++m) w = fma(Fb[q][m], x[m], w);
-          if (r0 + q < N) dst[base + (r0 + q) * stride] = w;
-        }
-      }
-      __syncthreads();
-    }
-    for (int p = tid; p < n; p += T) uc[p] = t1[p % N + RS * (p / N)];
+    for (int m = 0; m < N; ++m) x[m] = line[PS * m];
+    filter_line<N>(a, x, ug, f);
   }
 }
 

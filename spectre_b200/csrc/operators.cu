@@ -519,3 +519,206 @@ int dgrhs_lift_flux(int f, int n_comps, double* boundary_correction,
 }
 
 }  // extern "C"
+
+// ---- dg::project_to_mortar / project_from_mortar, orient_variables_on_slice,
+// ---- TimeStepper::update_u at operator granularity ---------------------------------
+
+namespace {
+// one pass of apply_matrices along one face dimension: out[c][..] = sum_s M[t][s] in[c][..]
+// dims: in [n_comps][nb][na] (a fastest); along = 0: a, 1: b; M row-major [n_out][n_in]
+__global__ void apply_matrix_2d_kernel(int n_comps, int na, int nb, int along, int n_out,
+                                       const double* __restrict__ M,
+                                       const double* __restrict__ in, double* __restrict__ out) {
+  const int na_out = along == 0 ? n_out : na, nb_out = along == 1 ? n_out : nb;
+  const int per = na_out * nb_out;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_comps * per) return;
+  const int c = idx / per, p = idx % per, a = p % na_out, b = p / na_out;
+  const double* src = in + (size_t)c * na * nb;
+  double s = 0.0;
+  if (along == 0) {
+    for (int m = 0; m < na; ++m) s = fma(M[a * na + m], src[m + na * b], s);
+  } else {
+    for (int m = 0; m < nb; ++m) s = fma(M[b * nb + m], src[a + na * m], s);
+  }
+  out[idx] = s;
+}
+
+__global__ void orient_slice_kernel(int n_comps, int na, int nb, int perm,
+                                    const double* __restrict__ in, double* __restrict__ out) {
+  const int per = na * nb;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_comps * per) return;
+  const int c = idx / per, p = idx % per, qa = p % na, qb = p / na;
+  // the neighbour's extents and the point (qa, qb) in the neighbour's frame
+  const int ma = (perm & 1) ? nb : na;
+  int ta = (perm & 1) ? qb : qa, tb = (perm & 1) ? qa : qb;
+  const int mb = (perm & 1) ? na : nb;
+  if (perm & 2) ta = ma - 1 - ta;
+  if (perm & 4) tb = mb - 1 - tb;
+  out[(size_t)c * per + ta + ma * tb] = in[idx];
+}
+
+struct UpdateTerms {
+  int n;
+  double a;          // factor of u itself
+  double c[9];
+  const double* v[9];
+};
+__global__ void update_u_kernel(long long size, double* __restrict__ u, UpdateTerms t) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= size) return;
+  double r = u[idx] * t.a;
+  for (int j = 0; j < t.n; ++j) r = fma(t.c[j], t.v[j][idx], r);
+  u[idx] = r;
+}
+
+// project along both face dimensions; to_mortar: face -> mortar (interpolation),
+// else mortar -> face (L2 projection)
+int project_face(bool to_mortar, int n_comps, const int* face_extents, const int* mortar_extents,
+                 const int* mortar_size, const double* in, double* out) {
+  if (need_gpu()) return 1;
+  if (n_comps < 1) return fail("n_comps must be positive");
+  for (int d = 0; d < 2; ++d) {
+    if (face_extents[d] < 2 || mortar_extents[d] > 12 || mortar_extents[d] < face_extents[d])
+      return fail("need 2 <= face extent <= mortar extent <= 12 (MortarHelpers.cpp:22-49: the "
+                  "mortar mesh has the larger extents)");
+    if (mortar_size[d] < 0 || mortar_size[d] > 2) return fail("bad mortar size");
+  }
+  Staged st;
+  int ext[2] = {to_mortar ? face_extents[0] : mortar_extents[0],
+                to_mortar ? face_extents[1] : mortar_extents[1]};
+  const size_t n_in = (size_t)n_comps * ext[0] * ext[1];
+  double* cur = st.in(in, n_in);
+  if (!cur) return fail("device staging failed");
+  for (int d = 0; d < 2; ++d) {
+    const int n_face = face_extents[d], n_mortar = mortar_extents[d];
+    // apply_matrices skips a dimension whose matrix is the identity (MortarHelpers.hpp:74-129)
+    if (n_face == n_mortar && mortar_size[d] == 0) continue;
+    const int n_out = to_mortar ? n_mortar : n_face, n_src = to_mortar ? n_face : n_mortar;
+    std::vector<double> M((size_t)n_out * n_src);
+    if (dgrhs_projection_matrix_meshes(n_face, n_mortar, to_mortar ? 0 : 1, mortar_size[d], M.data()))
+      return 1;
+    double* dM = st.in(M.data(), M.size());
+    int nxt[2] = {ext[0], ext[1]};
+    nxt[d] = n_out;
+    double* dst = st.in(nullptr, (size_t)n_comps * nxt[0] * nxt[1]);
+    if (!dM || !dst) return fail("device staging failed");
+    const int total = n_comps * nxt[0] * nxt[1];
+    apply_matrix_2d_kernel<<<(total + 127) / 128, 128>>>(n_comps, ext[0], ext[1], d, n_out, dM, cur, dst);
+    dgrhs_internal_count_launch();
+    CU(cudaGetLastError());
+    cur = dst;
+    ext[0] = nxt[0];
+    ext[1] = nxt[1];
+  }
+  CU(cudaMemcpy(out, cur, (size_t)n_comps * ext[0] * ext[1] * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int dgrhs_project_to_mortar(int n_comps, const int* face_extents, const int* mortar_extents,
+                            const int* mortar_size, const double* face_vars, double* mortar_vars) {
+  return project_face(true, n_comps, face_extents, mortar_extents, mortar_size, face_vars,
+                      mortar_vars);
+}
+
+int dgrhs_project_from_mortar(int n_comps, const int* face_extents, const int* mortar_extents,
+                              const int* mortar_size, const double* mortar_vars,
+                              double* face_vars) {
+  if (face_extents[0] == mortar_extents[0] && face_extents[1] == mortar_extents[1] &&
+      mortar_size[0] == 0 && mortar_size[1] == 0)
+    return fail("no projection is needed for a mortar that matches the face "
+                "(MortarHelpers.hpp: needs_projection)");
+  return project_face(false, n_comps, face_extents, mortar_extents, mortar_size, mortar_vars,
+                      face_vars);
+}
+
+int dgrhs_orient_variables_on_slice(int n_comps, const int* slice_extents, int permutation,
+                                    const double* vars, double* oriented) {
+  if (need_gpu()) return 1;
+  if (n_comps < 1 || slice_extents[0] < 1 || slice_extents[1] < 1 || permutation < 0 ||
+      permutation > 7)
+    return fail("bad arguments");
+  Staged st;
+  const size_t total = (size_t)n_comps * slice_extents[0] * slice_extents[1];
+  double* d_in = st.in(vars, total);
+  double* d_out = st.in(nullptr, total);
+  if (!d_in || !d_out) return fail("device staging failed");
+  orient_slice_kernel<<<(int)((total + 127) / 128), 128>>>(n_comps, slice_extents[0],
+                                                            slice_extents[1], permutation, d_in,
+                                                            d_out);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(oriented, d_out, total * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dgrhs_update_u(int stepper, int order, long long size, double* u, int n_history,
+                   const double* history_times, const double* history_derivatives,
+                   const double* step_start_value, double time_step) {
+  if (need_gpu()) return 1;
+  if (size < 1 || n_history < 1 || n_history > 8) return fail("bad size / history length");
+  UpdateTerms t{};
+  t.a = 1.0;
+  Staged st;
+  double* d_u = st.in(u, (size_t)size);
+  double* d_h = st.in(history_derivatives, (size_t)size * n_history);
+  if (!d_u || !d_h) return fail("device staging failed");
+  auto add = [&](double c, const double* v) {
+    t.c[t.n] = c;
+    t.v[t.n] = v;
+    ++t.n;
+  };
+  if (stepper == DGRHS_STEPPER_ADAMS_BASHFORTH) {
+    // AdamsBashforth::update_u_impl (AdamsBashforth.cpp:120-135): u += sum_j c_j f_j with the
+    // coefficients of the history times (AdamsCoefficients.hpp:64-104), oldest term first
+    if (order != n_history) return fail("Adams-Bashforth of order k needs k history entries");
+    std::vector<double> coef(n_history);
+    const double start = history_times[n_history - 1];
+    if (dgrhs_adams_bashforth_coefficients(order, history_times, start, start + time_step,
+                                           coef.data()))
+      return 1;
+    for (int j = 0; j < n_history; ++j) add(coef[j], d_h + (size_t)j * size);
+  } else {
+    int nsub = 0;
+    if (dgrhs_stepper_properties(stepper, 0, nullptr, &nsub, nullptr, nullptr)) return 1;
+    if (n_history > nsub) return fail("more history entries than substeps");
+    if (!step_start_value) return fail("substep methods need the value at the start of the step");
+    double* d_0 = st.in(step_start_value, (size_t)size);
+    if (!d_0) return fail("device staging failed");
+    const double* f_last = d_h + (size_t)(n_history - 1) * size;
+    if (stepper == DGRHS_STEPPER_RK3_HESTHAVEN) {
+      // Rk3HesthavenSsp.cpp:63-81; u holds the value of the current substep
+      if (n_history == 1) {
+        add(time_step, f_last);
+      } else if (n_history == 2) {
+        t.a = 0.25;
+        add(0.75, d_0);
+        add(0.25 * time_step, f_last);
+      } else {
+        t.a = 2.0 / 3.0;
+        add(1.0 / 3.0, d_0);
+        add((2.0 / 3.0) * time_step, f_last);
+      }
+    } else {
+      // RungeKutta.cpp:69-122: u = u_start + dt sum_i coef_i f_i, the last substep with the
+      // result coefficients
+      std::vector<double> row(n_history);
+      if (dgrhs_butcher_row(stepper, n_history - 1, row.data())) return 1;
+      t.a = 0.0;
+      add(1.0, d_0);
+      for (int i = 0; i < n_history; ++i)
+        if (row[i] != 0.0) add(row[i] * time_step, d_h + (size_t)i * size);
+    }
+  }
+  update_u_kernel<<<(int)((size + 255) / 256), 256>>>(size, d_u, t);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(u, d_u, (size_t)size * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

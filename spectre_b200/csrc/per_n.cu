@@ -140,7 +140,13 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
   const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
   if (c->system == DGRHS_SYSTEM_GH) {
     dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
-                    c->gH, c->gdH, c->D, c->coords, {}, eb, upd};
+                    c->gH, c->gdH, c->D, c->coords, {}, eb, upd, 0};
+    {
+      // one CTA per SM (N >= 10): pull the inputs of the CTA one wave ahead into L2
+      static const char* env = std::getenv("DGRHS_PREFETCH_DIST");
+      a.prefetch_dist = env ? std::atoi(env)
+                            : (dg::Cfg<N>::two_cta ? 0 : c->num_sms * dg::Cfg<N>::min_blocks);
+    }
     if constexpr (dg::SCfg<N>::fits && N <= 10) {
       if (c->volume_variant == 1) {
         if (c->gauge == DGRHS_GAUGE_HARMONIC) return launch_gh_split<N, 0>(c, a, eb, ee);
@@ -211,11 +217,16 @@ int launch_volume_p(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
 
 template <int N>
 int launch_filter(dgrhs_ctx* c) {
-  // GH: 25 component blocks per CTA (two CTAs per element); ScalarWave: one element
-  const int per_cta = c->C % 25 == 0 ? 25 : c->C;
-  dg::FilterArgs a{c->u, c->filterF, per_cta};
-  const int blocks = c->nelem * (c->C / per_cta);
-  dg::exponential_filter_kernel<N><<<blocks, dg::FilterCfg<N>::T, 0, c->stream>>>(a);
+  dg::FilterArgs a;
+  a.u = c->u;
+  a.ntiles = c->nelem * c->C;
+  for (int k = 0; k < N * N; ++k) a.Fm[k] = c->filterF_host[k];
+  using F = dg::FilterCfg<N>;
+  const int ngroups = (a.ntiles + F::G - 1) / F::G;
+  CU(cudaFuncSetAttribute(dg::exponential_filter_kernel<N>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, F::smem_bytes));
+  const int blocks = ngroups;
+  dg::exponential_filter_kernel<N><<<blocks, F::T, F::smem_bytes, c->stream>>>(a);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   return 0;

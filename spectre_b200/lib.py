@@ -42,6 +42,8 @@ EXPORTS = [
     "dgrhs_lift_flux",
     "dgrhs_comm_unique_id", "dgrhs_comm_init", "dgrhs_set_halo_peers", "dgrhs_exchange_halo",
     "dgrhs_set_phase_timing", "dgrhs_get_phase_times",
+    "dgrhs_apply_exponential_filter", "dgrhs_butcher_row", "dgrhs_update_u",
+    "dgrhs_project_to_mortar", "dgrhs_project_from_mortar", "dgrhs_orient_variables_on_slice",
     "dgrhs_set_slab", "dgrhs_self_start_substeps_left", "dgrhs_stepper_substep_fractions",
 ]
 
@@ -387,6 +389,9 @@ class Context:
     def set_exponential_filter(self, enable: bool, alpha: float = 36.0, half_power: int = 64):
         _check(self._lib.dgrhs_set_exponential_filter(self._h, int(enable),
                                                       ctypes.c_double(alpha), half_power))
+
+    def apply_exponential_filter(self):
+        _check(self._lib.dgrhs_apply_exponential_filter(self._h))
 
     def set_mortars(self, mortars):
         """[n, 6] rows (coarse element, direction, fine element, direction, size_a,

@@ -202,3 +202,168 @@ def test_bjorhus_dg_time_derivative_vs_reference_numpy_fixtures(golden_dir, phys
     assert np.max(np.abs(og - aa(z["out_corr_g"]))) < 1e-12 * scale
     assert np.max(np.abs(op - aa(want_pi))) < 1e-12 * scale
     assert np.max(np.abs(oph - iaa(want_phi))) < 1e-12 * scale
+
+
+@pytest.mark.parametrize("N", range(2, 13))
+@pytest.mark.parametrize("system", [lib.SYSTEM_SCALAR_WAVE, lib.SYSTEM_GH])
+def test_apply_exponential_filter(system, N):
+    """Filters::Exponential applied once (ExponentialFilter.cpp:45-76): the line kernel
+    (one thread per grid line, matrix entries from the constant bank) vs apply_matrices of
+    the oracle, every N, with an element count that leaves the last CTA partly filled."""
+    C = 5 if system == lib.SYSTEM_SCALAR_WAVE else 50
+    E = 3
+    rng = np.random.default_rng(100 * N + C)
+    u = rng.uniform(-1, 1, (E, C, N ** 3))
+    ctx = lib.Context(system, N, E)
+    with pytest.raises(lib.DgrhsError, match="no exponential filter set"):
+        ctx.apply_exponential_filter()
+    for alpha, half_power in ((36.0, 64), (4.0, 2)):
+        ctx.set_exponential_filter(True, alpha, half_power)
+        ctx.set_state(u)
+        ctx.apply_exponential_filter()
+        got = ctx.get_state()
+        F = orc.exponential_filter_matrix(N, alpha, half_power)
+        want = orc.apply_filter(N, u, F)
+        assert np.max(np.abs(got - want)) < 1e-13 * max(1.0, np.max(np.abs(want)))
+    ctx.close()
+
+
+def _call(name, *args):
+    h = lib.load()
+    rc = getattr(h, name)(*args)
+    if rc:
+        raise lib.DgrhsError(h.dgrhs_last_error().decode())
+
+
+def _ints(v):
+    import ctypes
+    return (ctypes.c_int * len(v))(*v)
+
+
+def _dptr(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+@pytest.mark.parametrize("face,mortar,sizes", [
+    ((5, 5), (5, 5), (orc.MORTAR_UPPER_HALF, orc.MORTAR_FULL)),      # h-mortar in a
+    ((4, 6), (4, 6), (orc.MORTAR_LOWER_HALF, orc.MORTAR_UPPER_HALF)),
+    ((4, 5), (6, 5), (orc.MORTAR_FULL, orc.MORTAR_FULL)),            # p-mortar in a
+    ((3, 4), (5, 7), (orc.MORTAR_FULL, orc.MORTAR_LOWER_HALF)),      # hp
+    ((12, 2), (12, 12), (orc.MORTAR_UPPER_HALF, orc.MORTAR_UPPER_HALF))])
+def test_project_to_and_from_mortar(face, mortar, sizes):
+    """dg::project_to_mortar / project_from_mortar (MortarHelpers.hpp:74-129) through the
+    C-ABI vs apply_matrices with the oracle's projection matrices (pinned to the closed
+    forms of Test_Projection.cpp in tests/test_oracle_pins.py); projecting a polynomial of
+    the face degree to the mortar and back gives it back when the mortar covers the face."""
+    C = 3
+    rng = np.random.default_rng(sum(face) + 7 * sum(mortar))
+    v = rng.uniform(-1, 1, (C, face[1], face[0]))
+
+    def mats(to_mortar):
+        out = []
+        for d in range(2):
+            if face[d] == mortar[d] and sizes[d] == orc.MORTAR_FULL:
+                out.append(None)
+            elif to_mortar:
+                out.append(orc.projection_matrix_parent_to_child(face[d], mortar[d], sizes[d]))
+            else:
+                out.append(orc.projection_matrix_child_to_parent(mortar[d], face[d], sizes[d]))
+        return out
+
+    def apply(x, ms):          # x [C][b][a]
+        if ms[0] is not None:
+            x = np.einsum("ta,cba->cbt", ms[0], x)
+        if ms[1] is not None:
+            x = np.einsum("tb,cba->cta", ms[1], x)
+        return x
+
+    want = apply(v, mats(True))
+    got = np.zeros((C, mortar[1], mortar[0]))
+    _call("dgrhs_project_to_mortar", C, _ints(face), _ints(mortar), _ints(sizes), _dptr(v), _dptr(got))
+    assert np.max(np.abs(got - want)) < 1e-13
+    back_want = apply(want, mats(False))
+    back = np.zeros((C, face[1], face[0]))
+    _call("dgrhs_project_from_mortar", C, _ints(face), _ints(mortar), _ints(sizes), _dptr(got), _dptr(back))
+    assert np.max(np.abs(back - back_want)) < 1e-12
+    if sizes == (orc.MORTAR_FULL, orc.MORTAR_FULL):
+        assert np.max(np.abs(back - v)) < 1e-12     # p-mortar: the L2 projection inverts the interpolation
+    with pytest.raises(lib.DgrhsError, match="mortar extent"):
+        _call("dgrhs_project_to_mortar", C, _ints((6, 6)), _ints((5, 6)), _ints(sizes), _dptr(v), _dptr(got))
+    with pytest.raises(lib.DgrhsError, match="no projection is needed"):
+        _call("dgrhs_project_from_mortar", C, _ints((4, 4)), _ints((4, 4)), _ints((0, 0)), _dptr(v), _dptr(got))
+
+
+@pytest.mark.parametrize("perm", range(8))
+def test_orient_variables_on_slice(perm):
+    """orient_variables_on_slice (OrientationMapHelpers.cpp:25-120) on a face with different
+    extents in its two dimensions: a point (qa, qb) of this element's face lands where the
+    neighbour's frame has it (the same rule the face kernels gather with)."""
+    C, na, nb = 2, 3, 5
+    rng = np.random.default_rng(perm)
+    v = rng.uniform(-1, 1, (C, nb, na))
+    got = np.zeros(C * na * nb)
+    _call("dgrhs_orient_variables_on_slice", C, _ints((na, nb)), perm, _dptr(v), _dptr(got))
+    ma, mb = (nb, na) if perm & 1 else (na, nb)
+    want = np.zeros((C, mb, ma))
+    for qb in range(nb):
+        for qa in range(na):
+            ta, tb = (qb, qa) if perm & 1 else (qa, qb)
+            if perm & 2:
+                ta = ma - 1 - ta
+            if perm & 4:
+                tb = mb - 1 - tb
+            want[:, tb, ta] = v[:, qb, qa]
+    assert np.array_equal(got.reshape(C, mb, ma), want)
+
+
+def test_update_u_operator():
+    """TimeStepper::update_u on a flat span (TimeStepper.hpp:96-102): Adams-Bashforth with
+    unequal history spacing against the oracle's coefficients, Rk3HesthavenSsp and a Butcher
+    tableau method against the oracle's substep formulas."""
+    import ctypes
+    from fractions import Fraction
+    size = 1000
+    rng = np.random.default_rng(3)
+    u = rng.uniform(-1, 1, size)
+    # AB3, history at t = 0, 0.3, 0.5 (dt units), step 0.5 -> 0.9
+    times = np.array([0.0, 0.3, 0.5])
+    f = rng.uniform(-1, 1, (3, size))
+    coef = orc.ab_coefficients_frac([Fraction(0), Fraction(3, 10), Fraction(1, 2)], Fraction(1, 2),
+                                    Fraction(9, 10), 1.0)
+    want = u.copy()
+    for c, d in zip(coef, f):
+        want += c * d
+    got = u.copy()
+    _call("dgrhs_update_u", lib.STEPPER_ADAMS_BASHFORTH, 3, ctypes.c_longlong(size), _dptr(got), 3,
+          _dptr(times), _dptr(f), None, ctypes.c_double(0.4))
+    assert np.max(np.abs(got - want)) < 1e-13
+    # Rk3HesthavenSsp: three substeps
+    dt = 0.01
+    u0 = u.copy()
+    cur = u.copy()
+    fs = rng.uniform(-1, 1, (3, size))
+    wants = [u0 + dt * fs[0]]
+    wants.append(0.25 * (3.0 * u0 + wants[0] + dt * fs[1]))
+    wants.append((1.0 / 3.0) * (u0 + 2.0 * wants[1] + 2.0 * dt * fs[2]))
+    for k in range(3):
+        _call("dgrhs_update_u", lib.STEPPER_RK3_HESTHAVEN, 0, ctypes.c_longlong(size), _dptr(cur), k + 1,
+              None, _dptr(np.ascontiguousarray(fs[:k + 1])), _dptr(u0), ctypes.c_double(dt))
+        assert np.max(np.abs(cur - wants[k])) < 1e-14
+    # DormandPrince5 through the tableau rows
+    c_, A, b = orc.RK_TABLEAUS["DP5"]
+    nsub = len(b)
+    fs = rng.uniform(-1, 1, (nsub, size))
+    cur = u.copy()
+    for k in range(nsub):
+        row = b if k == nsub - 1 else A[k]
+        want = u0.copy()
+        for cf, d in zip(row, fs):
+            if cf != 0.0:
+                want += cf * dt * d
+        _call("dgrhs_update_u", lib.STEPPER_DORMAND_PRINCE5, 0, ctypes.c_longlong(size), _dptr(cur), k + 1,
+              None, _dptr(np.ascontiguousarray(fs[:k + 1])), _dptr(u0), ctypes.c_double(dt))
+        assert np.max(np.abs(cur - want)) < 1e-14
+    with pytest.raises(lib.DgrhsError, match="needs k history entries"):
+        _call("dgrhs_update_u", lib.STEPPER_ADAMS_BASHFORTH, 4, ctypes.c_longlong(size), _dptr(got), 3,
+              _dptr(times), _dptr(f), None, ctypes.c_double(0.4))
