@@ -284,6 +284,22 @@ int dgrhs_self_start_substeps_left(dgrhs_ctx* ctx, int* n);
 #define DGRHS_NEIGHBOR_BJORHUS (-2147483647)
 #define DGRHS_NEIGHBOR_BJORHUS_PHYSICAL (-2147483646)
 int dgrhs_set_mortars(dgrhs_ctx* ctx, int n_mortars, const int32_t* mortars);
+/* p-refinement (elements with different numbers of grid points):
+ * one context per N; a face whose neighbour lives in a context with another N is marked
+ * DGRHS_NEIGHBOR_P_MORTAR in the neighbour table and listed here: table [n_faces][4] =
+ * {element, direction, NB = the neighbour's points per dimension, the neighbour's direction
+ * | permutation << 3 (as dgrhs_set_neighbor_orientations)}.  The mortar mesh has the larger
+ * extents (dg::mortar_mesh, MortarHelpers.cpp:22-49); both sides package on their own face
+ * mesh and project to the mortar, the correction is projected back and lifted
+ * (MortarHelpers.hpp:74-129, Projection.cpp:57-362, ApplyBoundaryCorrections.hpp:286-380).
+ * Before every right-hand side the neighbour's face must be in place:
+ *   dgrhs_set_halo_map + dgrhs_pack_halo on the neighbour's context (its faces in halo slots),
+ *   dgrhs_p_mortar_transfer(neighbour ctx, this ctx, n, halo slots, face indices of this table)
+ * (stream-ordered device copies, same device), then dgrhs_compute_time_derivative_range. */
+#define DGRHS_NEIGHBOR_P_MORTAR (-2147483645)
+int dgrhs_set_p_mortars(dgrhs_ctx* ctx, int n_faces, const int32_t* table);
+int dgrhs_p_mortar_transfer(dgrhs_ctx* src, dgrhs_ctx* dst, int n, const int32_t* src_slots,
+                            const int32_t* dst_faces);
 /* Spectral::projection_matrix_parent_to_child (child_to_parent = 0; Projection.cpp:
  * 279-362) / projection_matrix_child_to_parent (= 1; :57-262, operand not massive)
  * for Legendre-Gauss-Lobatto meshes with n_points_1d points on both sides,

@@ -963,3 +963,123 @@ def projection_matrix_child_to_parent(n_child, n_parent, size):
         return temp @ Vinv_mortar[:n_parent, :]
     upper = projection_matrix_child_to_parent(n_child, n_parent, MORTAR_UPPER_HALF)
     return upper[::-1, ::-1].copy()
+
+
+# ---------------------------------------------------------------------------
+# p-refinement: mortars between elements with different numbers of grid points
+# (dg::mortar_mesh = the larger extents, MortarHelpers.cpp:22-49; project_to_mortar /
+# project_from_mortar, MortarHelpers.hpp:74-129; ApplyBoundaryCorrections.hpp:286-380)
+# ---------------------------------------------------------------------------
+P_MORTAR = -2 ** 31 + 3
+
+
+def face_point_indices(N, d):
+    """volume indices of the points of face d, face index q = a + N b (a the first
+    remaining dimension)"""
+    dim, fixed = d // 2, (N - 1 if d % 2 else 0)
+    a, b = np.meshgrid(np.arange(N), np.arange(N), indexing="xy")
+    a, b = a.ravel(), b.ravel()
+    if dim == 0:
+        return fixed + N * (a + N * b)
+    if dim == 1:
+        return a + N * (fixed + N * b)
+    return a + N * (b + N * fixed)
+
+
+def face_packaged_data(system, N, u_e, invjac_e, static_e, d):
+    """InternalMortarDataImpl.hpp:180-320 for one face: slice, unit normal
+    (NormalCovectorAndMagnitude.hpp:47-92), dg_package_data.  Returns (packaged [PK, f],
+    magnitude of the unnormalised normal [f])."""
+    p = face_point_indices(N, d)
+    f = N * N
+    sign = 1.0 if d % 2 else -1.0
+    unn = np.stack([sign * invjac_e[d // 2 + 3 * i][p] for i in range(3)])
+    uf = _c(u_e[:, p])
+    L = lib()
+    if system == 0:
+        mag = np.sqrt(unn[0] * unn[0] + unn[1] * unn[1] + unn[2] * unn[2])
+        n_lo = _c(unn / mag)
+        out = np.zeros((16, f))
+        L.orc_sw_package_data(f, _p(uf), _p(_c(static_e[0][p])), _p(n_lo), _p(out))
+        return out, mag
+    geo = gh_geometry(uf)
+    ig = geo["inv_gamma"]          # 00 01 02 11 12 22
+    idx = [[0, 1, 2], [1, 3, 4], [2, 4, 5]]
+    n_up = np.stack([ig[idx[i][0]] * unn[0] + ig[idx[i][1]] * unn[1] + ig[idx[i][2]] * unn[2]
+                     for i in range(3)])
+    mag = np.sqrt(n_up[0] * unn[0] + n_up[1] * unn[1] + n_up[2] * unn[2])
+    n_lo, n_up = _c(unn / mag), _c(n_up / mag)
+    out = np.zeros((134, f))
+    L.orc_gh_package_data(f, _p(uf), _p(_c(static_e[1][p])), _p(_c(static_e[2][p])),
+                          _p(_c(geo["lapse"])), _p(_c(geo["shift"])), _p(n_lo), _p(n_up), _p(out))
+    return out, mag
+
+
+def orient_face_map(n, perm):
+    """index map q -> q' of orient_variables_on_slice on an n x n face: bit 0 swaps the face
+    coordinates, bits 1 / 2 flip the first / second coordinate of the target frame"""
+    a, b = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    a, b = a.ravel(), b.ravel()
+    ta, tb = (b, a) if perm & 1 else (a, b)
+    if perm & 2:
+        ta = n - 1 - ta
+    if perm & 4:
+        tb = n - 1 - tb
+    return ta + n * tb
+
+
+def _apply_face_matrices(x, Ma, Mb):
+    """apply_matrices on [C, nb, na] data: first face dimension, then the second"""
+    if Ma is not None:
+        x = np.einsum("ta,cba->cbt", Ma, x)
+    if Mb is not None:
+        x = np.einsum("tb,cba->cta", Mb, x)
+    return x
+
+
+def dg_rhs_p_refined(system, classes, links, gauge_params=GAUGE_HARMONIC):
+    """Right-hand side of a domain whose elements come in classes with different N.
+    classes: list of dicts N, u [E, C, n], invjac, static, nbr (faces to another class marked
+    P_MORTAR).  links: (class_a, element_a, direction_a, class_b, element_b, direction_b,
+    perm) -- perm takes a face point of a to the same point in b's frame.
+    Returns the list of dt_u per class."""
+    L = lib()
+    out = []
+    for cl in classes:
+        nbr = np.where(cl["nbr"] == P_MORTAR, -1, cl["nbr"]).astype(np.int32)
+        out.append(dg_rhs(system, cl["N"], cl["u"], cl["invjac"], cl["static"], nbr,
+                          gauge_params=gauge_params))
+    C, PK = (5, 16) if system == 0 else (50, 134)
+    for (ca, ea, da, cb, eb, db, perm) in links:
+        A, B = classes[ca], classes[cb]
+        NA, NB = A["N"], B["N"]
+        NM = max(NA, NB)
+        side = []
+        for cl, e, d in ((A, ea, da), (B, eb, db)):
+            pk, mag = face_packaged_data(system, cl["N"], cl["u"][e], cl["invjac"][e],
+                                         cl["static"][e], d)
+            n = cl["N"]
+            pk = pk.reshape(PK, n, n)
+            if n < NM:   # project_to_mortar: interpolation in both face dimensions
+                Pm = projection_matrix_parent_to_child(n, NM, MORTAR_FULL)
+                pk = _apply_face_matrices(pk, Pm, Pm)
+            side.append((pk.reshape(PK, NM * NM), mag))
+        a2b = orient_face_map(NM, perm)
+        b2a = np.argsort(a2b)
+        for own, other, cl, e, d, omap, dt in ((0, 1, A, ea, da, a2b, out[ca]),
+                                               (1, 0, B, eb, db, b2a, out[cb])):
+            n = cl["N"]
+            pk_own = _c(side[own][0])
+            pk_ext = _c(side[other][0][:, omap])
+            corr = np.zeros((C, NM * NM))
+            if system == 0:
+                L.orc_sw_boundary_terms(NM * NM, _p(pk_own), _p(pk_ext), _p(corr))
+            else:
+                L.orc_gh_boundary_terms(NM * NM, _p(pk_own), _p(pk_ext), _p(corr))
+            corr = corr.reshape(C, NM, NM)
+            if n < NM:   # project_from_mortar: L2 projection
+                Rm = projection_matrix_child_to_parent(NM, n, MORTAR_FULL)
+                corr = _apply_face_matrices(corr, Rm, Rm)
+            lift = -0.5 * n * (n - 1) * side[own][1]      # LiftFlux.hpp:57-61
+            dt[e][:, face_point_indices(n, d)] += corr.reshape(C, n * n) * lift
+    return out

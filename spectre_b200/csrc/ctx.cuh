@@ -98,6 +98,13 @@ struct dgrhs_ctx {
   int32_t* mortar_table = nullptr;   // [n_mortars][4]
   double* mortar_P = nullptr;        // [3][N*N]
   double* mortar_R = nullptr;        // [3][N*N]
+  // faces to a neighbour with a different N (another context): dgrhs_set_p_mortars
+  int n_pmortar_faces = 0;
+  int32_t* pm_faces = nullptr;       // [n][4] = element, direction, NB, neighbour direction | perm << 3
+  double* pm_ghost = nullptr;        // [n][HC][144] the neighbours' faces
+  double* pm_P = nullptr;            // [13][144]
+  double* pm_R = nullptr;            // [13][144]
+  cudaEvent_t pm_event = nullptr;
   int volume_variant = 0;         // 0 default, 1 context + streaming kernels (N <= 10),
                                   // 2 DFMA pair-staged kernel also for N = 12
   bool fuse_update = true;        // fuse UpdateU into the volume kernel

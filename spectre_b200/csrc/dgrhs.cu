@@ -535,6 +535,9 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   if (c->mortar_faces) cudaFree(c->mortar_faces);
   if (c->mortar_table) cudaFree(c->mortar_table);
   if (c->mortar_P) cudaFree(c->mortar_P);
+  for (void* q : {(void*)c->pm_faces, (void*)c->pm_ghost, (void*)c->pm_P, (void*)c->pm_R})
+    if (q) cudaFree(q);
+  if (c->pm_event) cudaEventDestroy(c->pm_event);
   if (c->mortar_R) cudaFree(c->mortar_R);
   if (c->halo_map) cudaFree(c->halo_map);
   if (c->aux_join) cudaEventDestroy(c->aux_join);
@@ -553,6 +556,7 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   for (size_t i = 0; i < (size_t)c->nelem * 6; ++i) {
     const int v = neighbors[i];
     if (v == DGRHS_NEIGHBOR_HANGING) continue;  // non-conforming face: dgrhs_set_mortars
+    if (v == DGRHS_NEIGHBOR_P_MORTAR) continue;  // neighbour with another N: dgrhs_set_p_mortars
     if (v == DGRHS_NEIGHBOR_BJORHUS || v == DGRHS_NEIGHBOR_BJORHUS_PHYSICAL) {
       if (c->system != DGRHS_SYSTEM_GH)
         return fail("ConstraintPreservingBjorhus is a GeneralizedHarmonic boundary condition");
@@ -585,6 +589,7 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   if (c->nbr_face) cudaFree(c->nbr_face);
   c->nbr_face = nullptr;
   c->n_mortar_faces = 0;
+  c->n_pmortar_faces = 0;
   // external faces with the Bjorhus boundary condition
   std::vector<int32_t> bj;
   for (int e = 0; e < c->nelem; ++e) {
@@ -867,6 +872,84 @@ int dgrhs_projection_matrix_meshes(int n_parent, int n_child, int child_to_paren
   else
     projection_matrix_meshes(n_parent, n_child, child_to_parent != 0, size, M);
   std::memcpy(matrix, M.data(), M.size() * 8);
+  return 0;
+}
+
+// ---- p-refinement: faces between contexts with different N ------------------------
+int dgrhs_set_p_mortars(dgrhs_ctx* c, int n_faces, const int32_t* table) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (c->nbr_host.empty()) return fail("call dgrhs_set_geometry first");
+  if (n_faces < 0 || (n_faces > 0 && !table)) return fail("bad p-mortar table");
+  size_t marked = 0;
+  for (int v : c->nbr_host) marked += v == DGRHS_NEIGHBOR_P_MORTAR;
+  if (marked != (size_t)n_faces)
+    return fail("%zu faces are marked DGRHS_NEIGHBOR_P_MORTAR but the table lists %d", marked,
+                n_faces);
+  std::vector<char> seen((size_t)c->nelem * 6, 0);
+  for (int i = 0; i < n_faces; ++i) {
+    const int32_t* r = table + 4 * (size_t)i;
+    if (r[0] < 0 || r[0] >= c->nelem || r[1] < 0 || r[1] > 5) return fail("p-mortar %d: bad face", i);
+    if (c->nbr_host[(size_t)r[0] * 6 + r[1]] != DGRHS_NEIGHBOR_P_MORTAR || seen[(size_t)r[0] * 6 + r[1]]++)
+      return fail("p-mortar %d: the face must be marked DGRHS_NEIGHBOR_P_MORTAR (once)", i);
+    if (r[2] < 2 || r[2] > 12 || r[2] == c->N)
+      return fail("p-mortar %d: the neighbour needs 2..12 grid points per dimension, not %d "
+                  "(equal N: a conforming face of one context)", i, r[2]);
+    if ((r[3] & 7) > 5 || (r[3] >> 3) < 0 || (r[3] >> 3) > 7) return fail("p-mortar %d: bad orientation", i);
+  }
+  for (void** q : {(void**)&c->pm_faces, (void**)&c->pm_ghost})
+    if (*q) {
+      cudaFree(*q);
+      *q = nullptr;
+    }
+  c->n_pmortar_faces = n_faces;
+  if (n_faces == 0) return 0;
+  CU(cudaMalloc(&c->pm_faces, (size_t)n_faces * 16));
+  CU(cudaMemcpy(c->pm_faces, table, (size_t)n_faces * 16, cudaMemcpyHostToDevice));
+  if (dev_alloc(&c->pm_ghost, (size_t)n_faces * c->HC * 144)) return 1;
+  // mortar mesh = the larger extents (MortarHelpers.cpp:22-49): interpolation of the side
+  // with fewer points up to it, L2 projection back (Projection.cpp:57-362)
+  std::vector<double> P(13 * 144, 0.0), R(13 * 144, 0.0), M;
+  for (int nb = 2; nb <= 12; ++nb) {
+    if (nb == c->N) continue;
+    const int lo = std::min(nb, c->N), hi = std::max(nb, c->N);
+    projection_matrix_meshes(lo, hi, false, 0, M);
+    std::copy(M.begin(), M.end(), P.begin() + (size_t)nb * 144);
+    projection_matrix_meshes(lo, hi, true, 0, M);
+    std::copy(M.begin(), M.end(), R.begin() + (size_t)nb * 144);
+  }
+  if (!c->pm_P && dev_alloc(&c->pm_P, P.size())) return 1;
+  if (!c->pm_R && dev_alloc(&c->pm_R, R.size())) return 1;
+  CU(cudaMemcpy(c->pm_P, P.data(), P.size() * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->pm_R, R.data(), R.size() * 8, cudaMemcpyHostToDevice));
+  if (!c->pm_event) CU(cudaEventCreateWithFlags(&c->pm_event, cudaEventDisableTiming));
+  return 0;
+}
+
+int dgrhs_p_mortar_transfer(dgrhs_ctx* src, dgrhs_ctx* dst, int n, const int32_t* src_slots,
+                            const int32_t* dst_faces) {
+  CHECK_CTX(src);
+  CHECK_CTX(dst);
+  if (src->device != dst->device) return fail("p-mortar transfer: contexts on different devices");
+  if (src->system != dst->system) return fail("p-mortar transfer: different evolution systems");
+  if (n < 0 || (n > 0 && (!src_slots || !dst_faces))) return fail("bad arguments");
+  if (n == 0) return 0;
+  if (!src->pm_event) CU(cudaEventCreateWithFlags(&src->pm_event, cudaEventDisableTiming));
+  CU(cudaSetDevice(dst->device));
+  // after the source's dgrhs_pack_halo, before the destination's next right-hand side
+  CU(cudaEventRecord(src->pm_event, src->stream));
+  CU(cudaStreamWaitEvent(dst->stream, src->pm_event, 0));
+  const size_t per_src = (size_t)src->HC * src->f;
+  for (int i = 0; i < n; ++i) {
+    if (src_slots[i] < 0 || src_slots[i] >= src->n_send) return fail("p-mortar transfer: bad halo slot");
+    if (dst_faces[i] < 0 || dst_faces[i] >= dst->n_pmortar_faces) return fail("p-mortar transfer: bad face");
+    CU(cudaMemcpyAsync(dst->pm_ghost + (size_t)dst_faces[i] * dst->HC * 144,
+                       src->halo_send + (size_t)src_slots[i] * per_src, per_src * 8,
+                       cudaMemcpyDeviceToDevice, dst->stream));
+  }
+  // the source must not pack again before the copies have read its send buffer
+  CU(cudaEventRecord(dst->pm_event, dst->stream));
+  CU(cudaStreamWaitEvent(src->stream, dst->pm_event, 0));
   return 0;
 }
 

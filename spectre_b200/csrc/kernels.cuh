@@ -984,6 +984,7 @@ constexpr int32_t kHangingFace = INT32_MIN;
 // by the face kernels, gh_bjorhus_kernel writes its (unlifted) dt corrections
 constexpr int32_t kBjorhusFace = INT32_MIN + 1;          // Type ConstraintPreserving
 constexpr int32_t kBjorhusPhysicalFace = INT32_MIN + 2;  // Type ConstraintPreservingPhysical
+constexpr int32_t kPMortarFace = INT32_MIN + 3;  // neighbour with a different N (pmortar_kernel)
 
 // neighbour-side face coordinates of our face point (qa, qb)
 template <int N>
@@ -1027,7 +1028,8 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
-  if (nb == kHangingFace || nb == kBjorhusFace || nb == kBjorhusPhysicalFace)
+  if (nb == kHangingFace || nb == kBjorhusFace || nb == kBjorhusPhysicalFace ||
+      nb == kPMortarFace)
     return;  // written by the mortar / Bjorhus kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
@@ -1156,7 +1158,8 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   const int dim = d >> 1;
   const double sign = (d & 1) ? 1.0 : -1.0;
   const int nb = a.nbr[e * 6 + d];
-  if (nb == kHangingFace || nb == kBjorhusFace || nb == kBjorhusPhysicalFace)
+  if (nb == kHangingFace || nb == kBjorhusFace || nb == kBjorhusPhysicalFace ||
+      nb == kPMortarFace)
     return;  // written by the mortar / Bjorhus kernel
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
@@ -1492,6 +1495,241 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
         }
       }
     }
+  }
+}
+
+// --------------------------------------------------------------------------
+// p-nonconforming faces: the neighbour has a different number of grid
+// points NB per dimension and lives in another context (one context per N; its face arrives
+// as the usual 55-/9-component halo on ITS NB x NB face points).  The mortar mesh has the
+// larger extents NM = max(N, NB) (dg::mortar_mesh, MortarHelpers.cpp:22-49).  Both sides
+// package on their own face mesh and project to the mortar (project_to_mortar: the
+// interpolation of Projection.cpp:279-362, identity for the side that already has NM
+// points); the boundary correction is evaluated on the mortar points, projected back to
+// this element's face mesh (project_from_mortar: the L2 projection of Projection.cpp:57-262,
+// identity if N == NM), lifted with this face's normal magnitude and written to the face's
+// correction slots (ApplyBoundaryCorrections.hpp:286-380).  One CTA per face.
+// --------------------------------------------------------------------------
+struct PMortarArgs {
+  const double* u;
+  const double* invjac;
+  const double* stat;
+  double* corr;
+  const int32_t* faces;  // [n][4] = element, direction, NB, neighbour direction | perm << 3
+  const double* ghost;   // [n][HC][144]: the neighbour's face on its own NB x NB points
+  const double* P;       // [13][144]: row NB = interpolation min(N, NB) -> NM points, [NM][lo]
+  const double* R;       // [13][144]: row NB = projection NM -> min(N, NB) points, [lo][NM]
+};
+
+constexpr int kPMortarThreads = 160;
+constexpr int pmortar_smem_bytes() { return (4 * 17 + 2 * 5 + 2) * 144 * 8; }
+
+template <int N, int kSystem>
+__global__ void __launch_bounds__(kPMortarThreads) pmortar_kernel(PMortarArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, T = kPMortarThreads;
+  constexpr int C = kSystem == 1 ? 50 : 5, NP = kSystem == 1 ? 10 : 1;
+  constexpr int S = kSystem == 1 ? 3 : 1;
+  constexpr int HC = C + 3 + (kSystem == 1 ? 2 : 1);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using Row = double[144];
+  Row* sO = reinterpret_cast<Row*>(smem_raw);  // [17] own packaged values (+ 4 speeds), own face points
+  Row* sN = sO + 17;                           // [17] the neighbour's, on its face points
+  Row* sB = sN + 17;                           // [17] after the first interpolation pass
+  Row* sM = sB + 17;                           // [17] the interpolated side on the mortar
+  Row* sE = sM + 17;                           // [5]  this element's correction on the mortar
+  Row* sF = sE + 5;                            // [5]  after the first projection pass
+  double* sP = &sF[5][0];
+  double* sR = sP + 144;
+  const int tid = threadIdx.x;
+  const int32_t* fc = a.faces + 4 * blockIdx.x;
+  const int e = fc[0], d = fc[1], NB = fc[2], dn = fc[3] & 7, perm = fc[3] >> 3;
+  const int NM = NB > N ? NB : N, fB = NB * NB, fM = NM * NM;
+  const int lo = NB > N ? N : NB;   // the side that is interpolated has lo points
+  for (int i = tid; i < 144; i += T) {
+    sP[i] = a.P[NB * 144 + i];
+    sR[i] = a.R[NB * 144 + i];
+  }
+  const double* gs = a.ghost + (size_t)blockIdx.x * HC * 144;
+
+  // ---- the two sides at their own face points -------------------------------------
+  GhFaceSide sdO, sdN;
+  const bool own_pt = tid < f, nbr_pt = tid < fB;
+  const int pO = own_pt ? face_point<N>(d, tid % N, tid / N) : 0;
+  auto finish_side = [&](const double (&unn)[3], double g1, double g2, const double (&g)[10],
+                         GhFaceSide& sd) {
+    if constexpr (kSystem == 1) {
+      gh_face_side(g, unn, g1, g2, sd);
+    } else {
+      sd.mag = sqrt(unn[0] * unn[0] + unn[1] * unn[1] + unn[2] * unn[2]);
+      const double inv = 1.0 / sd.mag;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) sd.n_lo[x] = sd.n_up[x] = unn[x] * inv;
+      sd.gamma2 = g2;
+      sd.speed[0] = 0.0;
+      sd.speed[1] = 0.0;
+      sd.speed[2] = 1.0;
+      sd.speed[3] = -1.0;
+    }
+  };
+  if (own_pt) {
+    const double sign = (d & 1) ? 1.0 : -1.0;
+    double unn[3], g[10] = {};
+    const double* jo = a.invjac + (size_t)e * 9 * npad + pO;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(jo + (size_t)((d >> 1) + 3 * x) * npad);
+    const double* so = a.stat + (size_t)e * S * npad + pO;
+    const double g1 = kSystem == 1 ? __ldg(so + npad) : 0.0;
+    const double g2 = kSystem == 1 ? __ldg(so + 2 * npad) : __ldg(so);
+    if constexpr (kSystem == 1) {
+      const double* uo = a.u + (size_t)e * C * npad + pO;
+#pragma unroll
+      for (int s = 0; s < 10; ++s) g[s] = __ldg(uo + (size_t)s * npad);
+    }
+    finish_side(unn, g1, g2, g, sdO);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) sO[13 + x][tid] = sdO.speed[x];
+  }
+  if (nbr_pt) {
+    const double sign = (dn & 1) ? 1.0 : -1.0;
+    double unn[3], g[10] = {};
+#pragma unroll
+    for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(gs + (size_t)(C + x) * fB + tid);
+    const double g1 = kSystem == 1 ? __ldg(gs + (size_t)(C + 3) * fB + tid) : 0.0;
+    const double g2 = kSystem == 1 ? __ldg(gs + (size_t)(C + 4) * fB + tid)
+                                   : __ldg(gs + (size_t)(C + 3) * fB + tid);
+    if constexpr (kSystem == 1) {
+#pragma unroll
+      for (int s = 0; s < 10; ++s) g[s] = __ldg(gs + (size_t)s * fB + tid);
+    }
+    finish_side(unn, g1, g2, g, sdN);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) sN[13 + x][tid] = sdN.speed[x];
+  }
+  const double liftO = own_pt ? -0.5 * (double)(N * (N - 1)) * sdO.mag : 0.0;
+  auto package = [&](const GhFaceSide& sd, const double* base, size_t cs, int s, Row* dst) {
+    double g, pi, ph[3];
+    if constexpr (kSystem == 1) {
+      g = __ldg(base + (size_t)s * cs);
+      pi = __ldg(base + (size_t)(10 + s) * cs);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) ph[m] = __ldg(base + (size_t)(20 + m + 3 * s) * cs);
+    } else {
+      g = __ldg(base);
+      pi = __ldg(base + cs);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) ph[m] = __ldg(base + (size_t)(2 + m) * cs);
+    }
+    GhPairPackaged k;
+    gh_pair_package(sd, g, pi, ph, k);
+    dst[0][tid] = k.v_g;
+    dst[1][tid] = k.g2_v_g;
+    dst[2][tid] = k.v_plus;
+    dst[3][tid] = k.v_minus;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      dst[4 + m][tid] = k.v_zero[m];
+      dst[7 + m][tid] = k.v_plus * sd.n_lo[m];
+      dst[10 + m][tid] = k.v_minus * sd.n_lo[m];
+    }
+  };
+  // this thread's mortar point (a, b) in this element's face frame and the same point in
+  // the neighbour's frame (orient_variables_on_slice of the received data)
+  const bool mortar_pt = tid < fM;
+  const int ma = tid % NM, mb = mortar_pt ? tid / NM : 0;
+  int na = (perm & 1) ? mb : ma, nb = (perm & 1) ? ma : mb;
+  if (perm & 2) na = NM - 1 - na;
+  if (perm & 4) nb = NM - 1 - nb;
+  const int qN = na + NM * nb;
+  const bool own_is_low = N < NB;
+  double spM[4] = {0.0, 0.0, 0.0, 0.0};  // speeds of the interpolated side on the mortar
+  __syncthreads();
+
+#pragma unroll 1
+  for (int s = 0; s < NP; ++s) {
+    const int c_hi = s == 0 ? 17 : 13;
+    if (own_pt) package(sdO, a.u + (size_t)e * C * npad + pO, (size_t)npad, s, sO);
+    if (nbr_pt) package(sdN, gs + tid, (size_t)fB, s, sN);
+    __syncthreads();
+    // project_to_mortar of the side with fewer points, in that side's own frame:
+    // first face dimension (thread = (a', b), a' < NM, b < lo), then the second
+    const Row* src = own_is_low ? sO : sN;
+    if (tid < NM * lo) {
+      const int a2 = tid % NM, b = tid / NM;
+      for (int c = 0; c < c_hi; ++c) {
+        double v = 0.0;
+        for (int m = 0; m < lo; ++m) v += sP[a2 * lo + m] * src[c][m + lo * b];
+        sB[c][tid] = v;
+      }
+    }
+    __syncthreads();
+    if (mortar_pt) {
+      const int a2 = tid % NM, b2 = tid / NM;
+      for (int c = 0; c < 13; ++c) {
+        double v = 0.0;
+        for (int m = 0; m < lo; ++m) v += sP[b2 * lo + m] * sB[c][a2 + NM * m];
+        sM[c][tid] = v;
+      }
+      if (s == 0)
+        for (int x = 0; x < 4; ++x) {
+          double v = 0.0;
+          for (int m = 0; m < lo; ++m) v += sP[b2 * lo + m] * sB[13 + x][a2 + NM * m];
+          sM[13 + x][tid] = v;
+        }
+    }
+    __syncthreads();
+    if (mortar_pt) {
+      double pkO[13], pkN[13], spO[4], spN[4], cO[5];
+      const Row* own = own_is_low ? sM : sO;   // on the mortar, this element's frame
+      const Row* nbr = own_is_low ? sN : sM;   // on the mortar, the neighbour's frame
+#pragma unroll
+      for (int c = 0; c < 13; ++c) {
+        pkO[c] = own[c][tid];
+        pkN[c] = nbr[c][qN];
+      }
+      if (s == 0) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) spM[x] = sM[13 + x][own_is_low ? tid : qN];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        spO[x] = own_is_low ? spM[x] : sO[13 + x][tid];
+        spN[x] = own_is_low ? sN[13 + x][qN] : spM[x];
+      }
+      pair_boundary_terms_packaged(spO, pkO, spN, pkN, cO);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) sE[c][tid] = cO[c];
+    }
+    __syncthreads();
+    double* cc = (kSystem == 1 ? a.corr + (size_t)e * 10 * 30 * f + (size_t)s * 30 * f + (size_t)d * 5 * f
+                               : a.corr + ((size_t)e * 6 + d) * 5 * f) + tid;
+    if (!own_is_low) {
+      // this face is the mortar: lift (LiftFlux.hpp:57-61)
+      if (own_pt)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) cc[(size_t)c * f] = sE[c][tid] * liftO;
+    } else {
+      // project_from_mortar: first face dimension (thread = (a, b'), a < N, b' < NM)
+      if (tid < N * NM) {
+        const int qa = tid % N, b2 = tid / N;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          double v = 0.0;
+          for (int m = 0; m < NM; ++m) v += sR[qa * NM + m] * sE[c][m + NM * b2];
+          sF[c][tid] = v;
+        }
+      }
+      __syncthreads();
+      if (own_pt) {
+        const int qa = tid % N, qb = tid / N;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          double v = 0.0;
+          for (int m = 0; m < NM; ++m) v += sR[qb * NM + m] * sF[c][qa + N * m];
+          cc[(size_t)c * f] = v * liftO;
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 

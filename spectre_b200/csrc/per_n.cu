@@ -90,7 +90,24 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   if (pass != 1 &&
       launch_mortars(c->n_mortar_faces_local, c->n_mortar_faces - c->n_mortar_faces_local))
     return 1;
-  c->pdl_volume = g_pdl && !bjorhus_now && c->n_mortar_faces == 0;
+  // faces to neighbours with another N: the neighbour's face was transferred before this
+  // right-hand side (dgrhs_p_mortar_transfer); with the pass that has the halo
+  if (pass != 1 && c->n_pmortar_faces > 0) {
+    dg::PMortarArgs m{c->u, c->invjac, c->stat, c->corr, c->pm_faces, c->pm_ghost, c->pm_P, c->pm_R};
+    constexpr int psmem = dg::pmortar_smem_bytes();
+    if (c->system == DGRHS_SYSTEM_GH) {
+      auto k = dg::pmortar_kernel<N, 1>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
+      k<<<c->n_pmortar_faces, dg::kPMortarThreads, psmem, c->stream>>>(m);
+    } else {
+      auto k = dg::pmortar_kernel<N, 0>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
+      k<<<c->n_pmortar_faces, dg::kPMortarThreads, psmem, c->stream>>>(m);
+    }
+    dgrhs_internal_count_launch();
+    CU(cudaGetLastError());
+  }
+  c->pdl_volume = g_pdl && !bjorhus_now && c->n_mortar_faces == 0 && c->n_pmortar_faces == 0;
   return 0;
 }
 

@@ -44,7 +44,7 @@ EXPORTS = [
     "dgrhs_set_phase_timing", "dgrhs_get_phase_times",
     "dgrhs_apply_exponential_filter", "dgrhs_butcher_row", "dgrhs_update_u",
     "dgrhs_project_to_mortar", "dgrhs_project_from_mortar", "dgrhs_orient_variables_on_slice",
-    "dgrhs_set_slab", "dgrhs_self_start_substeps_left", "dgrhs_stepper_substep_fractions",
+    "dgrhs_set_p_mortars", "dgrhs_p_mortar_transfer", "dgrhs_set_slab", "dgrhs_self_start_substeps_left", "dgrhs_stepper_substep_fractions",
 ]
 
 _lib = None
@@ -53,6 +53,7 @@ _lib = None
 HANGING = -2 ** 31   # DGRHS_NEIGHBOR_HANGING
 BJORHUS = -2 ** 31 + 1   # DGRHS_NEIGHBOR_BJORHUS (Type ConstraintPreserving)
 BJORHUS_PHYSICAL = -2 ** 31 + 2   # DGRHS_NEIGHBOR_BJORHUS_PHYSICAL
+P_MORTAR = -2 ** 31 + 3   # DGRHS_NEIGHBOR_P_MORTAR (neighbour with a different N)
 
 
 def stepper_properties(stepper, order=0):
@@ -389,6 +390,18 @@ class Context:
     def set_exponential_filter(self, enable: bool, alpha: float = 36.0, half_power: int = 64):
         _check(self._lib.dgrhs_set_exponential_filter(self._h, int(enable),
                                                       ctypes.c_double(alpha), half_power))
+
+    def set_p_mortars(self, table):
+        """[n, 4] rows (element, direction, neighbour's N, neighbour direction | perm << 3);
+        the faces carry P_MORTAR in the neighbour table."""
+        t = np.ascontiguousarray(table, dtype=np.int32).reshape(-1, 4)
+        _check(self._lib.dgrhs_set_p_mortars(self._h, len(t), _ptr(t)))
+
+    def p_mortar_transfer_from(self, src, src_slots, dst_faces):
+        """the faces `src` packed into its halo slots -> this context's p-mortar faces"""
+        a = np.ascontiguousarray(src_slots, dtype=np.int32)
+        b = np.ascontiguousarray(dst_faces, dtype=np.int32)
+        _check(self._lib.dgrhs_p_mortar_transfer(src._h, self._h, len(a), _ptr(a), _ptr(b)))
 
     def apply_exponential_filter(self):
         _check(self._lib.dgrhs_apply_exponential_filter(self._h))

@@ -421,3 +421,45 @@ def test_cpp_connectivity_builder(periodic, rotated):
     if not rotated:
         np.testing.assert_array_equal(nbr_r, nb)
         assert sorted(map(tuple, mt_r.tolist())) == sorted(map(tuple, np.asarray(mt).tolist()))
+
+
+def test_oracle_p_mortar_path_reduces_to_conforming():
+    """dg_rhs_p_refined (numpy: packaged data per face, projection to the mortar mesh,
+    boundary terms, projection back, lift) with two classes of EQUAL N is the conforming
+    right-hand side of the C oracle: pins the face normal, packaging, link and lift
+    conventions of the p-mortar oracle path (the projections are pinned to
+    Test_Projection.cpp's closed forms in test_oracle_pins.py)."""
+    from spectre_b200 import analytic, domain
+    for system in (0, 1):
+        N = 4
+        brick = domain.Brick([0, 0, 0], [1.0, 0.5, 0.5], [1, 0, 0], N)
+        x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+        rng = np.random.default_rng(system)
+        if system == 0:
+            u = analytic.plane_wave(x * 2 * np.pi, 0.1) + 1e-2 * rng.uniform(-1, 1, (2, 5, N ** 3))
+            stat = rng.uniform(0.5, 1.5, (2, 1, N ** 3))
+        else:
+            u = analytic.gauge_wave(x, 0.05) + 1e-3 * rng.uniform(-1, 1, (2, 50, N ** 3))
+            stat = np.zeros((2, 3, N ** 3))
+            stat[:, 0], stat[:, 1], stat[:, 2] = 1.0, -1.0, rng.uniform(0.5, 1.5, (2, N ** 3))
+        ref = orc.dg_rhs(system, N, u, J, stat, nb)
+        classes = [{"N": N, "u": u[k:k + 1], "invjac": J[k:k + 1], "static": stat[k:k + 1],
+                    "nbr": np.array([[orc.P_MORTAR, orc.P_MORTAR, 0, 0, 0, 0]], dtype=np.int32)}
+                   for k in range(2)]
+        links = [(0, 0, 1, 1, 0, 0, 0), (0, 0, 0, 1, 0, 1, 0)]
+        got = orc.dg_rhs_p_refined(system, classes, links)
+        for k in range(2):
+            assert np.max(np.abs(got[k] - ref[k:k + 1])) < 1e-14 * np.max(np.abs(ref))
+
+
+def test_oracle_p_mortar_projection_properties():
+    """A p-mortar between N = 4 and N = 6: data of the coarse side's polynomial degree are
+    reproduced exactly by project_to_mortar followed by project_from_mortar, and the face
+    orientation maps are permutations whose inverse is again one of the eight codes."""
+    P = orc.projection_matrix_parent_to_child(4, 6, orc.MORTAR_FULL)
+    R = orc.projection_matrix_child_to_parent(6, 4, orc.MORTAR_FULL)
+    assert np.max(np.abs(R @ P - np.eye(4))) < 1e-13
+    for perm in range(8):
+        m = orc.orient_face_map(5, perm)
+        assert sorted(m.tolist()) == list(range(25))
+        assert any(np.array_equal(orc.orient_face_map(5, q)[m], np.arange(25)) for q in range(8))
