@@ -91,6 +91,33 @@ def kerr_schild(x, mass=1.0, center=(0.0, 0.0, 0.0)):
     return gh_variables(g, {}, d_g)
 
 
+def superposed_kerr_schild(x, masses=(0.5, 0.5), centers=((8.0, 0.0, 0.0), (-8.0, 0.0, 0.0))):
+    """Synthetic binary-black-hole-like data for BASELINE configs[4]: the Kerr-Schild
+    perturbations of two non-spinning holes at rest added on the flat background,
+    g = eta + sum_k 2 H_k l_k l_k, with d_t g = 0 (the reference has no GH analytic data of
+    this kind; its closest relative is the superposed-Kerr-Schild free data of
+    PointwiseFunctions/AnalyticData/Xcts/Binary.hpp).  Not a solution: used as initial and
+    boundary data of the throughput / parity workload only."""
+    eta = np.diag([-1.0, 1.0, 1.0, 1.0])
+    shape = x.shape[:-2] + (x.shape[-1],)
+    g = {ab: np.full(shape, eta[ab]) for ab in _SYM}
+    d_g = {(i,) + ab: np.zeros(shape) for ab in _SYM for i in range(3)}
+    for mass, center in zip(masses, centers):
+        xc = [x[..., i, :] - center[i] for i in range(3)]
+        r = np.sqrt(xc[0] ** 2 + xc[1] ** 2 + xc[2] ** 2)
+        H = mass / r
+        l = [np.ones_like(r)] + [xc[i] / r for i in range(3)]
+        dH = [-mass * xc[i] / r ** 3 for i in range(3)]
+        dl = [[np.zeros_like(r)] + [((1.0 if i == j else 0.0) - xc[i] * xc[j] / r ** 2) / r
+                                     for j in range(3)] for i in range(3)]
+        for (a, b) in _SYM:
+            g[(a, b)] = g[(a, b)] + 2.0 * H * l[a] * l[b]
+            for i in range(3):
+                d_g[(i, a, b)] = d_g[(i, a, b)] + 2.0 * dH[i] * l[a] * l[b] + 2.0 * H * (
+                    dl[i][a] * l[b] + l[a] * dl[i][b])
+    return gh_variables(g, {}, d_g)
+
+
 def gaussian_plus_constant(x, constant, amplitude, width, center=(0.0, 0.0, 0.0)):
     r2 = sum((x[..., i, :] - center[i]) ** 2 for i in range(3))
     return constant + amplitude * np.exp(-r2 / width ** 2)

@@ -182,6 +182,26 @@ def gh_kerr_schild_shell_problem(refinement, N, inner_radius=1.9, outer_radius=2
                    demand_outgoing=outgoing, bjorhus=bjorhus)
 
 
+def gh_binary_problem(refinement, N, separation=16.0, excision_radius=0.8, object_outer_radius=4.0,
+                      envelope_radius=60.0, outer_radius=300.0, opening_angle_degrees=120.0,
+                      masses=(0.5, 0.5)):
+    """BASELINE.json configs[4]: superposed Kerr-Schild data (synthetic) on the
+    BinaryCompactObject domain (44 blocks, both objects excised; block layout of
+    support/Pipelines/Bbh/Inspiral.yaml:54-101 with CubeScale 1, one N and one refinement
+    level for all blocks, static maps), DirichletAnalytic with the initial data on the two
+    excision spheres and the outer sphere, AnalyticChristoffel gauge of the initial data,
+    constant damping parameters."""
+    from . import bco
+    xa, xb = 0.5 * separation, -0.5 * separation
+    dom = bco.BinaryCompactObject(xa, xb, excision_radius, object_outer_radius, excision_radius,
+                                  object_outer_radius, envelope_radius, outer_radius, refinement,
+                                  N, opening_angle_degrees)
+    centers = ((xa, 0.0, 0.0), (xb, 0.0, 0.0))
+    return Problem(lib.SYSTEM_GH, dom,
+                   lambda x, t: analytic.superposed_kerr_schild(x, masses, centers),
+                   (1.0, -1.0, 1.0), dirichlet_analytic=True, analytic_christoffel_gauge=True)
+
+
 def gh_gauge_wave_dirichlet_problem(refinement, N, amplitude=0.1, wavelength=1.0,
                                     gammas=(1.0, -1.0, 1.0)):
     """Gauge wave on the Brick [0,1]^3 that is periodic in y and z only; the x
