@@ -47,6 +47,7 @@ WORKLOAD_DEFAULTS = {            # refine, points per dimension, CPU-sample refi
     "kerr-schild-shell": (3, 12, 1),
     "gauge-wave": (4, 8, 3),
     "kerr-schild": (4, 12, 2),
+    "bbh": (2, 12, 0),
 }
 FILTER = (36.0, 64)              # KerrSchild.yaml:127-132 (Alpha, HalfPower)
 
@@ -189,9 +190,11 @@ class CpuArm:
         self.L.orc_set_num_threads(host_threads())
         self.threads = int(self.L.orc_num_threads())
         self.N, self.dt = N, dt
-        if workload == "kerr-schild-shell":
+        if workload in ("kerr-schild-shell", "bbh"):
             from spectre_b200 import domain, evolution
-            problem = shell_problem(evolution, sample_refine, sample_refine + 1, N)
+            problem = (shell_problem(evolution, sample_refine, sample_refine + 1, N)
+                       if workload == "kerr-schild-shell"
+                       else evolution.gh_binary_problem(sample_refine, N))
             part = domain.Partition(problem.neighbors, 1, 0,
                                     boundary_slots=problem.dirichlet_analytic,
                                     neighbor_direction=problem.orientations[0],
@@ -212,6 +215,8 @@ class CpuArm:
                                             ext_u=ext, nbr_dir=nd, face_perm=perm)
             self.u = np.ascontiguousarray(u0)
             self.desc = (f"Kerr-Schild shell, refinement ({sample_refine}, {sample_refine + 1}): "
+                         f"{len(ids)} elements" if workload == "kerr-schild-shell" else
+                         f"BinaryCompactObject domain, refinement {sample_refine}: "
                          f"{len(ids)} elements")
         else:
             b = orc.Brick([0, 0, 0], [1, 1, 1], [sample_refine] * 3, N)
@@ -223,8 +228,8 @@ class CpuArm:
             self.rhs = lambda v: orc.dg_rhs(1, N, v, J, stat, nb)
             self.u = np.ascontiguousarray(u0)
             self.desc = f"gauge wave, refinement {sample_refine}: {b.nelem} elements"
-        self.F = (np.ascontiguousarray(orc.exponential_filter_matrix(N, *FILTER))
-                  if use_filter else None)
+        self.F = (np.ascontiguousarray(orc.exponential_filter_matrix(
+            N, *((36.0, 420) if workload == "bbh" else FILTER))) if use_filter else None)
         self.points = self.u.shape[0] * N ** 3
         self.hist = [self.rhs(self.u) for _ in range(2)]   # AB3 history (static start)
 
@@ -268,7 +273,7 @@ def run_reference(args):
     if rank != 0:
         return
     arm = CpuArm(args.workload, args.points, args.cpu_sample_refine, args.dt,
-                 args.workload == "kerr-schild-shell" and not args.no_filter)
+                 args.workload in ("kerr-schild-shell", "bbh") and not args.no_filter)
     r = arm.run(args.steps, min(args.warmup, 1), budget_s=60.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
@@ -304,6 +309,14 @@ WORKLOAD_NAMES = {
                          "the shell at constant radius), DirichletAnalytic boundaries, "
                          "AnalyticChristoffel gauge, GaussianPlusConstant damping, exponential "
                          "filter (KerrSchild.yaml:73-132), AB3, dt=2e-4",
+    "bbh": "BASELINE.json configs[4]: GeneralizedHarmonic, synthetic superposed Kerr-Schild data "
+           "of two holes (m = 0.5 each, separation 16) on the BinaryCompactObject domain (44 "
+           "blocks: per object six spherical and six cube wedges, ten bulged frustums, ten outer "
+           "(half-)wedges, opening angle 120 degrees, both objects excised; block layout of "
+           "Inspiral.yaml:54-101 with CubeScale 1, one N and 8^L elements per block, static "
+           "maps), DirichletAnalytic boundaries, AnalyticChristoffel gauge, exponential filter "
+           "(Alpha 36, HalfPower 420, Inspiral.yaml:219-224), AB3, dt=2e-4; strong scaling: the "
+           "domain is fixed, elements are cut in block / Z-curve order",
 }
 
 
@@ -318,9 +331,15 @@ def workload_config(args, world, cpu=False):
         extra = {"inner_boundary": args.inner_boundary, "outer_boundary": args.outer_boundary,
                  "filter": None if args.no_filter else
                  {"Alpha": FILTER[0], "HalfPower": FILTER[1]}}
+    elif workload == "bbh":
+        n_el = -(-44 * 8 ** args.refine // world)
+        ref = [args.refine] * 3
+        extra = {"blocks": 44, "elements_total": 44 * 8 ** args.refine,
+                 "filter": None if args.no_filter else {"Alpha": 36.0, "HalfPower": 420}}
     else:
         n_el = (2 ** args.refine) ** 3
-    gauge = "AnalyticChristoffel" if workload.startswith("kerr-schild") else args.gauge
+    gauge = ("AnalyticChristoffel" if workload.startswith("kerr-schild") or workload == "bbh"
+             else args.gauge)
     state_gb = n_el * 50 * args.points ** 3 * 8 / 1e9
     cfg = {
         "workload": WORKLOAD_NAMES[workload], **extra,
@@ -344,6 +363,8 @@ def make_problem(evolution, args, world):
     if args.workload == "kerr-schild-shell":
         return shell_problem(evolution, args.refine, shell_radial_level(args, world), N,
                              args.inner_boundary, args.outer_boundary)
+    if args.workload == "bbh":
+        return evolution.gh_binary_problem(args.refine, N)
     refinement = weak_refinement(world, args.refine)
     if args.workload == "kerr-schild":
         # element size fixed (1/8 M per element edge), lattice grows with the GPU count
@@ -368,7 +389,8 @@ class GpuRun:
         self.gauge = (lib.GAUGE_HARMONIC if args.gauge == "harmonic"
                       else lib.GAUGE_ANALYTIC_GAUGE_WAVE)
         self.gauge_params = (0.1, 1.0) if args.gauge == "analytic" else ()
-        self.use_filter = args.workload == "kerr-schild-shell" and not args.no_filter
+        self.use_filter = args.workload in ("kerr-schild-shell", "bbh") and not args.no_filter
+        self.filter = (36.0, 420) if args.workload == "bbh" else FILTER
         self.ev = self.new_evolution()
         self.ctx = self.ev.ctx
         self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=f"cuda:{local_rank}")
@@ -381,7 +403,7 @@ class GpuRun:
                                       native_exchange=not getattr(self.args, "python_exchange",
                                                                   False))
         if self.use_filter:
-            ev.ctx.set_exponential_filter(True, *FILTER)
+            ev.ctx.set_exponential_filter(True, *self.filter)
         if self.args.volume_variant:
             ev.ctx.set_split_volume(self.args.volume_variant)
         return ev
@@ -447,7 +469,8 @@ class GpuRun:
         peak, peak_src = peaks()
         # static per-point fields read by the volume kernel: 3 damping fields, +20
         # when the gauge source function comes from memory (G = 23)
-        G = 23 if (args.workload.startswith("kerr-schild") or args.gauge == "analytic") else 3
+        G = 23 if (args.workload.startswith("kerr-schild") or args.workload == "bbh"
+                   or args.gauge == "analytic") else 3
         kb = kernel_alg_bytes(N, n_static=G)
         kb["volume_update_fused"] = kb["volume"] + kb["update"]
         names = ["face", "volume", "update", "volume_update_fused", "filter"]
@@ -563,7 +586,7 @@ class GpuRun:
                                               self.args.dt, 0.0, self.gauge, self.gauge_params,
                                               self.local_rank)
             if self.use_filter:
-                ref_ev.ctx.set_exponential_filter(True, *FILTER)
+                ref_ev.ctx.set_exponential_filter(True, *self.filter)
             ref_ev.take_steps(steps_total)
             same = np.array_equal(ref_ev.gather_state(n_global), gathered)
             print(f"[verify] {self.world}-rank state bit-identical to single-GPU state: {same}",
@@ -600,7 +623,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="kerr-schild-shell",
-                    choices=["gauge-wave", "kerr-schild", "kerr-schild-shell"],
+                    choices=["gauge-wave", "kerr-schild", "kerr-schild-shell", "bbh"],
                     help="kerr-schild-shell: BASELINE configs[3], the north-star configuration "
                          "(default); gauge-wave: configs[1]; kerr-schild: Brick-lattice stand-in")
     ap.add_argument("--refine", type=int, default=None,
@@ -694,7 +717,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": args.scaling if args.workload == "kerr-schild-shell" else "weak",
+            "scaling": ("strong" if args.workload == "bbh" else
+                        args.scaling if args.workload == "kerr-schild-shell" else "weak"),
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
