@@ -91,6 +91,13 @@ struct dgrhs_ctx {
   int n_bjorhus_faces = 0;
   int64_t aux_faces_eval = -1;       // RHS evaluation that already ran the Bjorhus/mortar kernels
   int32_t* bjorhus_faces = nullptr;  // [n][3] element, direction, physical
+  // elements without / with a Bjorhus face: the volume kernel of the first list runs next to
+  // the Bjorhus kernel, only the second list waits for it
+  int32_t* vol_list = nullptr;       // [nelem] plain elements first
+  int n_vol_plain = 0;
+  bool bjorhus_join_pending = false; // set by the face launcher, consumed by rhs_range
+  const int32_t* vol_list_cur = nullptr;  // element list of the next volume launch (or null)
+  int vol_list_count = 0;
   // non-conforming mortars (dgrhs_set_mortars)
   int n_mortar_faces = 0;
   int n_mortar_faces_local = 0;      // groups without a remote side come first

@@ -316,7 +316,24 @@ int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume
   const DgNOps* ops = dgrhs_nops(c->N);
   if (!ops) return fail("unsupported number of grid points per dimension: %d", c->N);
   if (do_gauge && ops->gauge(c, time)) return 1;
+  c->bjorhus_join_pending = false;
   if (!volume_only && ops->faces(c, eb, ee)) return 1;
+  if (c->bjorhus_join_pending) {
+    // The Bjorhus kernel (few long, latency-bound CTAs on the side stream) only feeds the
+    // elements that own a Bjorhus face: all other elements go first, next to it
+    c->bjorhus_join_pending = false;
+    c->vol_list_cur = c->vol_list;
+    c->vol_list_count = c->n_vol_plain;
+    int rc = c->n_vol_plain > 0 ? ops->volume(c, dt, eb, ee, true, &upd) : 0;
+    if (!rc && cudaStreamWaitEvent(c->stream, c->aux_join, 0) != cudaSuccess) rc = 1;
+    c->pdl_volume = false;
+    c->vol_list_cur = c->vol_list + c->n_vol_plain;
+    c->vol_list_count = c->nelem - c->n_vol_plain;
+    if (!rc) rc = ops->volume(c, dt, eb, ee, true, &upd);
+    c->vol_list_cur = nullptr;
+    c->vol_list_count = 0;
+    return rc;
+  }
   return ops->volume(c, dt, eb, ee, !volume_only, &upd);
 }
 
@@ -532,6 +549,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   if (c->nbr_face) cudaFree(c->nbr_face);
   if (c->violations) cudaFree(c->violations);
   if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
+  if (c->vol_list) cudaFree(c->vol_list);
   if (c->mortar_faces) cudaFree(c->mortar_faces);
   if (c->mortar_table) cudaFree(c->mortar_table);
   if (c->mortar_P) cudaFree(c->mortar_P);
@@ -612,7 +630,21 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   }
   if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
   c->bjorhus_faces = nullptr;
+  if (c->vol_list) cudaFree(c->vol_list);
+  c->vol_list = nullptr;
   c->n_bjorhus_faces = (int)(bj.size() / 3);
+  if (!bj.empty()) {
+    std::vector<char> has(c->nelem, 0);
+    for (size_t k = 0; k < bj.size(); k += 3) has[bj[k]] = 1;
+    std::vector<int32_t> order;
+    for (int e = 0; e < c->nelem; ++e)
+      if (!has[e]) order.push_back(e);
+    c->n_vol_plain = (int)order.size();
+    for (int e = 0; e < c->nelem; ++e)
+      if (has[e]) order.push_back(e);
+    CU(cudaMalloc(&c->vol_list, order.size() * 4));
+    CU(cudaMemcpy(c->vol_list, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
+  }
   if (!bj.empty()) {
     CU(cudaMalloc(&c->bjorhus_faces, bj.size() * 4));
     CU(cudaMemcpy(c->bjorhus_faces, bj.data(), bj.size() * 4, cudaMemcpyHostToDevice));
@@ -1670,6 +1702,10 @@ int rhs_with_exchange(dgrhs_ctx* c, double t) {
   c->pdl_volume = false;
   if (ops->gauge(c, t)) return 1;
   if (ni > 0 && ops->faces(c, 0, ni)) return 1;
+  if (c->bjorhus_join_pending) {  // (every element is interior: whole-batch pass)
+    c->bjorhus_join_pending = false;
+    CU(cudaStreamWaitEvent(main_stream, c->aux_join, 0));
+  }
   CU(cudaEventRecord(c->ev_faces1, main_stream));
   if (pt) CU(cudaEventRecord(c->phase_ev[2], main_stream));
   c->pdl_volume = false;  // an event sits between the faces and the volume kernel
@@ -1842,6 +1878,10 @@ int dgrhs_time_kernels(dgrhs_ctx* c, int reps, int update_terms, double* ms) {
       if (which == 0) {
         c->aux_faces_eval = -1;  // time the Bjorhus/mortar kernels too
         rc = ops->faces(c, 0, c->nelem);
+        if (c->bjorhus_join_pending) {  // no volume launch follows here: join now
+          c->bjorhus_join_pending = false;
+          CU(cudaStreamWaitEvent(c->stream, c->aux_join, 0));
+        }
       }
       if (which == 1) rc = ops->volume(c, c->dt_last, 0, c->nelem, true, nullptr);
       if (which == 3) rc = ops->volume(c, scratch, 0, c->nelem, true, &fused);

@@ -294,6 +294,7 @@ struct GhVolArgs {
   int elem_begin;
   UpdateArgs upd;
   int prefetch_dist;  // CTAs ahead whose prologue inputs are pulled into L2 (0: off)
+  const int32_t* elem_list;  // nullptr: elements elem_begin, elem_begin + 1, ...; else the list
 };
 
 template <int N>
@@ -372,7 +373,8 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
       reinterpret_cast<uint64_t*>(sD + (kSharedD ? 2 : 1) * ((N * N + 1) / 2 * 2));
   unsigned int* released = reinterpret_cast<unsigned int*>(bars + 4);  // [NS] warps done
 
-  const int e = a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
+  const int e = a.elem_list ? a.elem_list[blockIdx.x / Cfg<N>::nchunk]
+                            : a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
   const int chunk = blockIdx.x % Cfg<N>::nchunk;
   const int tid = threadIdx.x;
   const int pt = chunk * T + tid;
@@ -461,7 +463,8 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
       // component rows per pair.
       const unsigned int bt = blockIdx.x + (unsigned int)a.prefetch_dist;
       if (bt < gridDim.x) {
-        const int et = a.elem_begin + (int)(bt / Cfg<N>::nchunk);
+        const int et = a.elem_list ? a.elem_list[bt / Cfg<N>::nchunk]
+                                   : a.elem_begin + (int)(bt / Cfg<N>::nchunk);
         const int ptt = (int)(bt % Cfg<N>::nchunk) * T + tid;
         if (ptt < n) {
           const double* ut = a.u + (size_t)et * 50 * npad + ptt;

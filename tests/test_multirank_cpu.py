@@ -164,7 +164,13 @@ def _shell_worker(rank, world, port, order, results):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    sh = domain.SphericalShell(1.9, 4.0, (1, 1), N, order=order)
+    if order == "bco":
+        # BASELINE configs[4]: the 44-block BinaryCompactObject domain cut in block order
+        from spectre_b200 import bco
+        sh = bco.BinaryCompactObject(8.0, -8.0, 0.8, 4.0, 0.8, 4.0, 60.0, 300.0, 0, N,
+                                     opening_angle_degrees=120.0)
+    else:
+        sh = domain.SphericalShell(1.9, 4.0, (1, 1), N, order=order)
     nb, (nd, perm) = sh.neighbors(), sh.neighbor_orientations()
     x = sh.coords()
     part = domain.Partition(nb, world, rank, boundary_slots=True, neighbor_direction=nd,
@@ -197,7 +203,7 @@ def _shell_worker(rank, world, port, order, results):
                 nbb = N - 1 - nbb
             mine = x[part.global_ids[le]][:, _face_points(d)]
             theirs = rv[-(v + 2)][:, na + N * nbb]
-            np.testing.assert_allclose(theirs, mine, atol=1e-13)   # the same physical points
+            np.testing.assert_allclose(theirs, mine, atol=1e-13 * max(1.0, np.abs(mine).max()))   # the same physical points
             checked += 1
     assert checked == part.n_recv
     counts = [None] * world
@@ -209,7 +215,8 @@ def _shell_worker(rank, world, port, order, results):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,order", [(2, "block"), (2, "radial"), (3, "block")])
+@pytest.mark.parametrize("world,order", [(2, "block"), (2, "radial"), (3, "block"), (2, "bco"),
+                                         (4, "bco")])
 def test_shell_partition_and_oriented_halo_exchange_gloo(world, order):
     mp.spawn(_shell_worker, args=(world, _free_port(), order, None), nprocs=world, join=True)
 
