@@ -259,6 +259,9 @@ class Run:
             face_bc = {4: self._boundary_condition(io, "Sphere.Interior"),
                        5: self._boundary_condition(o["OuterBoundaryCondition"],
                                                    "Sphere.OuterBoundaryCondition")}
+        elif name == "BinaryCompactObject":
+            self._binary_compact_object(o)
+            return
         else:
             raise InputFileError(f"DomainCreator {name} is not implemented")
         self.face_bc = face_bc
@@ -277,6 +280,75 @@ class Run:
                     "ConstraintPreservingBjorhus in more than one dimension (elements with two "
                     "or more Bjorhus faces) is not implemented")
             self.bjorhus = lambda g, d: bj.get(d)
+
+    def _binary_compact_object(self, o):
+        """domain::creators::BinaryCompactObject (BinaryCompactObject.hpp option list): the
+        subset spectre_b200.bco builds -- both objects excised, CubeScale 1, no centre-of-mass
+        offset, static maps, one number of grid points for all blocks and dimensions."""
+        from . import bco
+        if float(o.get("CubeScale", 1.0)) != 1.0:
+            raise InputFileError("BinaryCompactObject: CubeScale != 1 (focally offset wedges) is "
+                                 "not implemented")
+        if any(float(v) != 0.0 for v in o.get("CenterOfMassOffset", [0.0, 0.0])):
+            raise InputFileError("BinaryCompactObject: CenterOfMassOffset is not implemented")
+        objects = {}
+        for tag in ("ObjectA", "ObjectB"):
+            ob = o[tag]
+            if "InnerRadius" not in ob:
+                raise InputFileError(f"BinaryCompactObject: {tag} without an excised sphere "
+                                     "(CartesianCubeAtXCoord) is not implemented")
+            iname, io = _one(ob["Interior"], f"{tag}.Interior")
+            if iname != "ExciseWithBoundaryCondition":
+                raise InputFileError(f"BinaryCompactObject: {tag} with a filled interior is not "
+                                     "implemented")
+            objects[tag] = (float(ob["XCoord"]), float(ob["InnerRadius"]),
+                            float(ob["OuterRadius"]), bool(ob.get("UseLogarithmicMap", False)),
+                            self._boundary_condition(io, f"{tag}.Interior"))
+        if objects["ObjectA"][3] != objects["ObjectB"][3]:
+            raise InputFileError("BinaryCompactObject: different UseLogarithmicMap for the two "
+                                 "objects is not implemented")
+        groups = bco.BinaryCompactObject.GROUPS
+
+        def per_group(value, what, length):
+            if isinstance(value, dict):
+                missing = [g for g in groups if g not in value]
+                if missing:
+                    raise InputFileError(f"{what}: no entry for {missing}")
+                out = {g: value[g] for g in groups}
+            else:
+                out = {g: value for g in groups}
+            return {g: (tuple(int(x) for x in v) if isinstance(v, (list, tuple))
+                        else (int(v),) * length) for g, v in out.items()}
+        pts = per_group(o["InitialGridPoints"], "BinaryCompactObject.InitialGridPoints", 3)
+        if len({p for v in pts.values() for p in v}) != 1:
+            raise InputFileError("InitialGridPoints that differ between blocks or dimensions "
+                                 "(p-refinement, anisotropic meshes) are not implemented")
+        ref = per_group(o["InitialRefinement"], "BinaryCompactObject.InitialRefinement", 3)
+        env, shell = o["Envelope"], o["OuterShell"]
+        (xa, ra_in, ra_out, log_a, bc_a), (xb, rb_in, rb_out, _, bc_b) = (objects["ObjectA"],
+                                                                          objects["ObjectB"])
+        try:
+            self.domain = bco.BinaryCompactObject(
+                xa, xb, ra_in, ra_out, rb_in, rb_out, float(env["Radius"]), float(shell["Radius"]),
+                ref, pts["Envelope"][0], float(shell.get("OpeningAngle", 90.0)),
+                bool(o.get("UseEquiangularMap", True)), log_a,
+                str(env.get("RadialDistribution", "Linear")),
+                str(shell.get("RadialDistribution", "Linear")))
+        except ValueError as err:
+            raise InputFileError(f"BinaryCompactObject: {err}") from None
+        kinds = {"excision_a": bc_a, "excision_b": bc_b,
+                 "outer": self._boundary_condition(shell["BoundaryCondition"],
+                                                   "OuterShell.BoundaryCondition")}
+        dom = self.domain
+        kind_of = lambda g, d: kinds[dom.external_boundary(g, d)]   # noqa: E731
+        self.face_bc = kinds
+        if "DirichletAnalytic" in kinds.values():
+            self.ghost = lambda g, d: kind_of(g, d) == "DirichletAnalytic"
+        self.outgoing = "DemandOutgoingCharSpeeds" in kinds.values()
+        if any(k.startswith("ConstraintPreserving") for k in kinds.values()):
+            self.bjorhus = lambda g, d: (kind_of(g, d)
+                                         if kind_of(g, d).startswith("ConstraintPreserving")
+                                         else None)
 
     # -- EvolutionSystem -----------------------------------------------------
     def _system(self):

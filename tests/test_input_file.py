@@ -253,3 +253,65 @@ def test_one_sided_periodic_and_multi_dimension_bjorhus_are_errors():
                                                          {"Lower": bj, "Upper": bj}, bcs[2]]
     with pytest.raises(input_file.InputFileError, match="more than one dimension"):
         input_file.Run(meta, o)
+
+
+def _binary_domain_options():
+    """DomainCreator block in the schema of support/Pipelines/Bbh/Inspiral.yaml:54-112
+    (static maps, CubeScale 1)."""
+    excise = {"ExciseWithBoundaryCondition": {"DemandOutgoingCharSpeeds": None}}
+    groups = ("ObjectAShell", "ObjectACube", "ObjectBShell", "ObjectBCube", "Envelope",
+              "OuterShell")
+    return {"BinaryCompactObject": {
+        "ObjectA": {"InnerRadius": 0.8, "OuterRadius": 4.0, "XCoord": 8.0, "Interior": excise,
+                    "UseLogarithmicMap": True},
+        "ObjectB": {"InnerRadius": 0.8, "OuterRadius": 4.0, "XCoord": -8.0, "Interior": excise,
+                    "UseLogarithmicMap": True},
+        "CenterOfMassOffset": [0.0, 0.0],
+        "Envelope": {"Radius": 60.0, "RadialDistribution": "Logarithmic"},
+        "OuterShell": {"Radius": 300.0, "RadialDistribution": "Linear", "OpeningAngle": 120.0,
+                       "BoundaryCondition": {"ConstraintPreservingBjorhus":
+                                             {"Type": "ConstraintPreservingPhysical"}}},
+        "UseEquiangularMap": True, "CubeScale": 1.0,
+        "InitialRefinement": {g: ([1, 1, 0] if g.endswith("Cube") else [0, 0, 0])
+                              for g in groups},
+        "InitialGridPoints": 4, "TimeDependentMaps": None}}
+
+
+def test_binary_compact_object_creator_options(tmp_path):
+    """DomainCreator: BinaryCompactObject in the option schema of Inspiral.yaml:54-112 (with
+    the KerrSchild.yaml evolution options around it): the 44-block domain with per-group
+    refinement, the three boundary conditions on their spheres, and explicit errors for what
+    the path cannot represent."""
+    import yaml
+    with open(_reference_input("GeneralizedHarmonic/KerrSchild.yaml")) as f:
+        meta, opts = list(yaml.safe_load_all(f))
+
+    def load_with(**changes):
+        o = yaml.safe_load(yaml.safe_dump(opts))
+        o["DomainCreator"] = _binary_domain_options()
+        o["DomainCreator"]["BinaryCompactObject"].update(changes)
+        path = tmp_path / "bbh.yaml"
+        with open(path, "w") as f:
+            yaml.safe_dump_all([meta, o], f)
+        return input_file.load(str(path), allow_gts_fixed_step=True)
+    r = load_with()
+    assert r.domain.n_blocks == 44 and r.domain.n_elements == 32 + 12 * 4
+    assert len(r.domain.mortars()) == 88
+    assert r.outgoing and not r.ghost
+    nbr = r.domain.neighbors()
+    ext = [(e, d) for e in range(r.domain.n_elements) for d in range(6) if nbr[e, d] == -1]
+    kinds = [r.bjorhus(e, d) for e, d in ext]
+    assert kinds.count("ConstraintPreservingPhysical") == 10 and kinds.count(None) == 12
+    p = r.problem()
+    assert p.neighbors.shape == (80, 6)
+    for changes, msg in (({"CubeScale": 1.2}, "CubeScale"),
+                         ({"CenterOfMassOffset": [0.1, 0.0]}, "CenterOfMassOffset"),
+                         ({"InitialGridPoints": {g: ([7, 7, 5] if g == "Envelope" else 5) for g in
+                                                 ("ObjectAShell", "ObjectACube", "ObjectBShell",
+                                                  "ObjectBCube", "Envelope", "OuterShell")}},
+                          "p-refinement"),
+                         ({"TimeDependentMaps": {"InitialTime": 0.0}}, "time-dependent maps"),
+                         ({"Envelope": {"Radius": 20.0, "RadialDistribution": "Linear"}},
+                          "envelope radius is too small")):
+        with pytest.raises(input_file.InputFileError, match=msg):
+            load_with(**changes)
