@@ -460,7 +460,12 @@ class GpuRun:
         sel = np.unique(np.linspace(0, len(ids) - 1, 16).astype(int))
         exact = self.problem.u0(ids[sel], self.ctx.time)
         err = float(np.max(np.abs(state[sel] - exact)))
-        assert err < 1e-3, f"solution drifted from the exact solution: {err}"
+        if self.args.workload == "bbh":
+            # superposed Kerr-Schild data are not a solution: the evolution moves away from
+            # them (by design); only a gross failure is an error here
+            assert err < 0.1, f"state moved implausibly far from the initial data: {err}"
+        else:
+            assert err < 1e-3, f"solution drifted from the exact solution: {err}"
         return state, err
 
     def roofline(self, value):

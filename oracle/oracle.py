@@ -1040,7 +1040,7 @@ def _apply_face_matrices(x, Ma, Mb):
 def dg_rhs_p_refined(system, classes, links, gauge_params=GAUGE_HARMONIC):
     """Right-hand side of a domain whose elements come in classes with different N.
     classes: list of dicts N, u [E, C, n], invjac, static, nbr (faces to another class marked
-    P_MORTAR).  links: (class_a, element_a, direction_a, class_b, element_b, direction_b,
+    P_MORTAR; optional ext_u, nbr_dir, face_perm as in dg_rhs for the faces inside a class).  links: (class_a, element_a, direction_a, class_b, element_b, direction_b,
     perm) -- perm takes a face point of a to the same point in b's frame.
     Returns the list of dt_u per class."""
     L = lib()
@@ -1048,7 +1048,8 @@ def dg_rhs_p_refined(system, classes, links, gauge_params=GAUGE_HARMONIC):
     for cl in classes:
         nbr = np.where(cl["nbr"] == P_MORTAR, -1, cl["nbr"]).astype(np.int32)
         out.append(dg_rhs(system, cl["N"], cl["u"], cl["invjac"], cl["static"], nbr,
-                          gauge_params=gauge_params))
+                          gauge_params=gauge_params, ext_u=cl.get("ext_u"),
+                          nbr_dir=cl.get("nbr_dir"), face_perm=cl.get("face_perm")))
     C, PK = (5, 16) if system == 0 else (50, 134)
     for (ca, ea, da, cb, eb, db, perm) in links:
         A, B = classes[ca], classes[cb]

@@ -132,3 +132,70 @@ def test_p_mortar_evolution_and_misuse():
         ctxs[0].set_p_mortars([[0, 1, NA, 0], [0, 0, NB, 1]])
     for ctx in ctxs:
         ctx.close()
+
+
+def test_p_refined_binary_domain_matches_oracle():
+    """Block groups of the BinaryCompactObject domain with different N (the isotropic part of
+    Inspiral.yaml:102-108's InitialGridPoints): p-mortars between non-aligned curved blocks
+    (wedge <-> cube wedge <-> frustum <-> half wedge), DirichletAnalytic on the three spheres,
+    AnalyticChristoffel gauge.  RHS and two self-started AB3 steps vs the oracle."""
+    from spectre_b200 import analytic, bco, p_refinement
+    dom = bco.BinaryCompactObject(8.0, -8.0, 0.8, 4.0, 0.8, 4.0, 60.0, 300.0, 0, 4,
+                                  opening_angle_degrees=120.0)
+    points = {"ObjectAShell": 6, "ObjectACube": 4, "ObjectBShell": 6, "ObjectBCube": 5,
+              "Envelope": 6, "OuterShell": 5}
+    pts = [points[name] for name in dom.block_names]
+    centers = ((8.0, 0.0, 0.0), (-8.0, 0.0, 0.0))
+    data = lambda x, t: analytic.superposed_kerr_schild(x, (0.5, 0.5), centers)   # noqa: E731
+    dt = 1e-3
+    ev = p_refinement.PRefinedEvolution(lib.SYSTEM_GH, dom, pts, data, (1.0, -1.0, 1.0), dt=dt)
+    assert ev.Ns == [4, 5, 6] and sum(len(i) for i in ev.ids) == 44
+    rng = np.random.default_rng(5)
+    classes = []
+    for k, N in enumerate(ev.Ns):
+        u = ev.u0[k] + 1e-3 * rng.uniform(-1, 1, ev.u0[k].shape)
+        ev.ctxs[k].set_state(u)
+        ev.ctxs[k].set_stepper(lib.STEPPER_ADAMS_BASHFORTH, 3, 0.0, dt)
+        H = np.zeros((len(u), 4, N ** 3))
+        dH = np.zeros((len(u), 16, N ** 3))
+        for e in range(len(u)):
+            H[e], dH[e] = orc.analytic_christoffel_gauge(N, ev.u0[k][e], ev.J[k][e])
+        t = ev.tables[k]
+        ext = ev.boundary_ghost_data(k, ev.x[k], ev.J[k], ev.stat[k], ev.u0[k])[:, :50]
+        classes.append({"N": N, "u": u, "invjac": ev.J[k],
+                        "static": np.concatenate([ev.stat[k], H, dH], axis=1),
+                        "nbr": t["nbr"], "nbr_dir": t["nbr_dir"], "face_perm": t["face_perm"],
+                        "ext_u": ext})
+    # links from the tables: every interface once, seen from the class that lists it first
+    links, seen = [], set()
+    cls_of = {N: k for k, N in enumerate(ev.Ns)}
+    local = {int(g): (k, le) for k, ids in enumerate(ev.ids) for le, g in enumerate(ids)}
+    for a, t in enumerate(ev.tables):
+        for (le, d, nb_points, code, g2) in t["pm"]:
+            b, le2 = local[g2]
+            key = tuple(sorted([(a, le, d), (b, le2, code & 7)]))
+            if key in seen:
+                continue
+            seen.add(key)
+            links.append((a, le, d, b, le2, code & 7, code >> 3))
+    assert len(links) == sum(len(t["pm"]) for t in ev.tables) // 2 > 20
+    ev.compute_time_derivative(0.0)
+    got = [ctx.get_time_derivative() for ctx in ev.ctxs]
+    want = orc.dg_rhs_p_refined(1, classes, links, gauge_params=orc.GAUGE_GIVEN)
+    scale = max(np.max(np.abs(w)) for w in want)
+    for g, w in zip(got, want):
+        assert np.max(np.abs(g - w)) < TOL * scale
+    ev.take_steps(2)
+    sizes = np.cumsum([c["u"].size for c in classes])[:-1]
+
+    def rhs(v, t):
+        for c, part in zip(classes, np.split(v, sizes)):
+            c["u"] = part.reshape(c["u"].shape)
+        return np.concatenate([r.ravel() for r in orc.dg_rhs_p_refined(
+            1, classes, links, gauge_params=orc.GAUGE_GIVEN)])
+    o = orc.Evolution(rhs, np.concatenate([c["u"].ravel() for c in classes]), 0.0, dt, "AB3")
+    o.step()
+    o.step()
+    state = np.concatenate([ctx.get_state().ravel() for ctx in ev.ctxs])
+    assert np.max(np.abs(state - o.u)) < TOL * np.max(np.abs(o.u))
+    ev.close()
