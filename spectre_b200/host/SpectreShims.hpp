@@ -248,6 +248,10 @@ class Mesh {
   Mesh(size_t isotropic_extents, Spectral::Basis b, Spectral::Quadrature q) : basis_(b), quadrature_(q) {
     extents_.fill(static_cast<uint8_t>(isotropic_extents));
   }
+  Mesh(const std::array<size_t, Dim>& extents, Spectral::Basis b, Spectral::Quadrature q)
+      : basis_(b), quadrature_(q) {
+    for (size_t d = 0; d < Dim; ++d) extents_[d] = static_cast<uint8_t>(extents[d]);
+  }
   size_t extents(size_t d) const { return extents_[d]; }
   size_t number_of_grid_points() const {
     size_t n = 1;
@@ -388,6 +392,20 @@ inline FaceOrientation face_orientation(const OrientationMap<3>& orientation, co
           (swapped ? 1 : 0) | (reverse_first ? 2 : 0) | (reverse_second ? 4 : 0)};
 }
 
+// orient_variables_on_slice (OrientationMapHelpers.cpp:25-120): variables on the face
+// perpendicular to `sliced_dim` of this element, [n_comps][slice points], into the frame of the
+// neighbour reached through `orientation_of_neighbor`
+inline std::vector<double> orient_variables_on_slice(const std::vector<double>& variables_on_slice, size_t n_comps,
+                                                     const std::array<size_t, 2>& slice_extents, size_t sliced_dim,
+                                                     const OrientationMap<3>& orientation_of_neighbor) {
+  const auto fo = face_orientation(orientation_of_neighbor, Direction3{sliced_dim, 1});
+  const int ext[2] = {static_cast<int>(slice_extents[0]), static_cast<int>(slice_extents[1])};
+  std::vector<double> out(variables_on_slice.size());
+  check(dgrhs_orient_variables_on_slice(static_cast<int>(n_comps), ext, fo.permutation, variables_on_slice.data(),
+                                        out.data()));
+  return out;
+}
+
 namespace dg {
 // dg::mortar_size (NumericalAlgorithms/DiscontinuousGalerkin/MortarHelpers.cpp:51-77): size of
 // the mortar to `neighbor` inside the face of `self` perpendicular to `dimension`, per face
@@ -428,6 +446,40 @@ inline void partial_derivatives(std::vector<double>* du, const std::vector<doubl
 }
 
 namespace dg {
+// dg::mortar_mesh (MortarHelpers.cpp:22-49): the larger extents in every face dimension
+inline Mesh<2> mortar_mesh(const Mesh<2>& face_mesh1, const Mesh<2>& face_mesh2) {
+  return Mesh<2>({std::max(face_mesh1.extents(0), face_mesh2.extents(0)),
+                  std::max(face_mesh1.extents(1), face_mesh2.extents(1))},
+                 Spectral::Basis::Legendre, Spectral::Quadrature::GaussLobatto);
+}
+// MortarHelpers.hpp:60-72
+inline bool needs_projection(const Mesh<2>& face_mesh, const Mesh<2>& mortar_mesh,
+                             const std::array<Spectral::MortarSize, 2>& mortar_size) {
+  return face_mesh.extents(0) != mortar_mesh.extents(0) || face_mesh.extents(1) != mortar_mesh.extents(1) ||
+         mortar_size[0] != Spectral::MortarSize::Full || mortar_size[1] != Spectral::MortarSize::Full;
+}
+// dg::project_to_mortar / project_from_mortar (MortarHelpers.hpp:74-129) on a Variables-like
+// block [n_comps][points of the face / mortar mesh], first face dimension fastest
+inline std::vector<double> project_to_mortar(const std::vector<double>& vars, size_t n_comps,
+                                             const Mesh<2>& face_mesh, const Mesh<2>& mortar_mesh,
+                                             const std::array<Spectral::MortarSize, 2>& mortar_size) {
+  const int fe[2] = {static_cast<int>(face_mesh.extents(0)), static_cast<int>(face_mesh.extents(1))};
+  const int me[2] = {static_cast<int>(mortar_mesh.extents(0)), static_cast<int>(mortar_mesh.extents(1))};
+  const int sz[2] = {Spectral::abi_size_code(mortar_size[0]), Spectral::abi_size_code(mortar_size[1])};
+  std::vector<double> out(n_comps * mortar_mesh.number_of_grid_points());
+  check(dgrhs_project_to_mortar(static_cast<int>(n_comps), fe, me, sz, vars.data(), out.data()));
+  return out;
+}
+inline std::vector<double> project_from_mortar(const std::vector<double>& vars, size_t n_comps,
+                                               const Mesh<2>& face_mesh, const Mesh<2>& mortar_mesh,
+                                               const std::array<Spectral::MortarSize, 2>& mortar_size) {
+  const int fe[2] = {static_cast<int>(face_mesh.extents(0)), static_cast<int>(face_mesh.extents(1))};
+  const int me[2] = {static_cast<int>(mortar_mesh.extents(0)), static_cast<int>(mortar_mesh.extents(1))};
+  const int sz[2] = {Spectral::abi_size_code(mortar_size[0]), Spectral::abi_size_code(mortar_size[1])};
+  std::vector<double> out(n_comps * face_mesh.number_of_grid_points());
+  check(dgrhs_project_from_mortar(static_cast<int>(n_comps), fe, me, sz, vars.data(), out.data()));
+  return out;
+}
 enum class Formulation { StrongInertial, WeakInertial };
 // dg::lift_flux on a Variables-like block [n_comps][f]
 inline void lift_flux(std::vector<double>* boundary_correction_terms, size_t n_comps,
@@ -703,6 +755,17 @@ class AdamsBashforth : public TimeStepper {
   static constexpr size_t maximum_order = 8;  // AdamsBashforth.hpp:199
   explicit AdamsBashforth(size_t order) : order_(order) { (void)props(); }  // throws on a bad order
   int id() const override { return DGRHS_STEPPER_ADAMS_BASHFORTH; }
+  // TimeStepper::update_u (TimeStepper.hpp:96-102, AdamsBashforth.cpp:120-135): u holds the value
+  // at the newest history time; history = (time, derivative) oldest first, order() entries
+  void update_u(std::vector<double>* u, const std::vector<double>& history_times,
+                const std::vector<std::vector<double>>& history_derivatives, double time_step) const {
+    if (history_times.size() != order_ || history_derivatives.size() != order_)
+      throw std::runtime_error("AdamsBashforth::update_u needs order() history entries");
+    std::vector<double> flat;
+    for (const auto& d : history_derivatives) flat.insert(flat.end(), d.begin(), d.end());
+    check(dgrhs_update_u(id(), static_cast<int>(order_), static_cast<long long>(u->size()), u->data(),
+                         static_cast<int>(order_), history_times.data(), flat.data(), nullptr, time_step));
+  }
 
  private:
   size_t requested_order() const override { return order_; }
@@ -981,6 +1044,12 @@ class DgEvolution {
     set_time_stepper(stepper.id(), static_cast<int>(stepper.order()), t0, dt);
   }
   void take_steps(int n) { check(dgrhs_take_steps(ctx_, n)); }
+  // dg::Actions::Filter<Filters::Exponential<0>> (ExponentialFilter.cpp:45-76): enabled, it runs
+  // after every substep update; apply_exponential_filter() applies it once to the resident state
+  void set_exponential_filter(double alpha, unsigned half_power) {
+    check(dgrhs_set_exponential_filter(ctx_, 1, alpha, static_cast<int>(half_power)));
+  }
+  void apply_exponential_filter() { check(dgrhs_apply_exponential_filter(ctx_)); }
   double time() const { return dgrhs_time(ctx_); }
   dgrhs_ctx* handle() { return ctx_; }
 

@@ -102,6 +102,59 @@ int main() {
   }
   const auto c = TimeSteppers::adams_coefficients::coefficients({0.0, 1.0, 2.0}, 2.0, 3.0);
   if (std::fabs(c[2] - 23.0 / 12.0) > 1e-15) { std::printf("AB3 coefficients wrong\n"); return 1; }
+  // ---- dg::mortar_mesh / project_to_mortar / project_from_mortar: a p-mortar ----
+  {
+    const Mesh<2> face({4, 5}, Spectral::Basis::Legendre, Spectral::Quadrature::GaussLobatto);
+    const Mesh<2> other({6, 3}, Spectral::Basis::Legendre, Spectral::Quadrature::GaussLobatto);
+    const Mesh<2> mortar = dg::mortar_mesh(face, other);
+    if (mortar.extents(0) != 6 || mortar.extents(1) != 5) { std::printf("mortar_mesh wrong\n"); return 1; }
+    const std::array<Spectral::MortarSize, 2> full{Spectral::MortarSize::Full, Spectral::MortarSize::Full};
+    if (!dg::needs_projection(face, mortar, full) || dg::needs_projection(mortar, mortar, full)) {
+      std::printf("needs_projection wrong\n");
+      return 1;
+    }
+    std::vector<double> v(2 * 20);
+    for (auto& x : v) x = dist(gen);
+    const auto on_mortar = dg::project_to_mortar(v, 2, face, mortar, full);
+    const auto back = dg::project_from_mortar(on_mortar, 2, face, mortar, full);
+    if (on_mortar.size() != 2 * 30) { std::printf("project_to_mortar size wrong\n"); return 1; }
+    for (size_t k = 0; k < v.size(); ++k)
+      if (std::fabs(back[k] - v[k]) > 1e-12) { std::printf("p-mortar round trip wrong\n"); return 1; }
+    // the projection to an upper-half mortar interpolates: a linear function stays linear
+    const auto xi4 = Spectral::collocation_points(4);
+    std::vector<double> lin(20);
+    for (size_t b = 0; b < 5; ++b)
+      for (size_t a = 0; a < 4; ++a) lin[a + 4 * b] = 2.0 + 3.0 * xi4[a];
+    const std::array<Spectral::MortarSize, 2> upper_a{Spectral::MortarSize::UpperHalf, Spectral::MortarSize::Full};
+    const auto half = dg::project_to_mortar(lin, 1, face, face, upper_a);
+    for (size_t b = 0; b < 5; ++b)
+      for (size_t a = 0; a < 4; ++a)
+        if (std::fabs(half[a + 4 * b] - (2.0 + 3.0 * 0.5 * (xi4[a] + 1.0))) > 1e-13) {
+          std::printf("upper-half projection wrong\n");
+          return 1;
+        }
+  }
+  // ---- orient_variables_on_slice: the aligned map is the identity, a flip of the first
+  //      face coordinate reverses it ----
+  {
+    std::vector<double> v(3 * 4);
+    for (size_t k = 0; k < v.size(); ++k) v[k] = static_cast<double>(k);
+    const auto same = orient_variables_on_slice(v, 1, {3, 4}, 2, OrientationMap<3>{});
+    if (same != v) { std::printf("aligned orient_variables_on_slice is not the identity\n"); return 1; }
+  }
+  // ---- TimeStepper::update_u on a flat span: AB3 with equal steps ----
+  {
+    const TimeSteppers::AdamsBashforth ab3(3);
+    std::vector<double> u{1.0, -2.0}, want = u;
+    const std::vector<std::vector<double>> f{{0.5, 1.0}, {-1.0, 2.0}, {0.25, -0.75}};
+    const double dt = 0.1;
+    ab3.update_u(&u, {0.0, 0.1, 0.2}, f, dt);
+    const double ck[3] = {5.0 / 12.0, -4.0 / 3.0, 23.0 / 12.0};
+    for (size_t p = 0; p < 2; ++p)
+      for (size_t j = 0; j < 3; ++j) want[p] += dt * ck[j] * f[j][p];
+    for (size_t p = 0; p < 2; ++p)
+      if (std::fabs(u[p] - want[p]) > 1e-15) { std::printf("AdamsBashforth::update_u wrong\n"); return 1; }
+  }
   // ---- error behaviour: bad arguments throw with the library's message ----
   bool threw = false;
   try { Mesh<3> m(13, Spectral::Basis::Legendre, Spectral::Quadrature::GaussLobatto); DgEvolution ev(1, m, 8); }
