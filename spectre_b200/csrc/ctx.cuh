@@ -91,13 +91,13 @@ struct dgrhs_ctx {
   int n_bjorhus_faces = 0;
   int64_t aux_faces_eval = -1;       // RHS evaluation that already ran the Bjorhus/mortar kernels
   int32_t* bjorhus_faces = nullptr;  // [n][3] element, direction, physical
-  // elements without / with a Bjorhus face: the volume kernel of the first list runs next to
-  // the Bjorhus kernel, only the second list waits for it
-  int32_t* vol_list = nullptr;       // [nelem] plain elements first
-  int n_vol_plain = 0;
+  // The elements that own a Bjorhus face form the tail [bjorhus_tail_begin, nelem) of the
+  // element order (-1: they do not): the volume kernel of the other elements then runs next to
+  // the Bjorhus kernel and only the tail waits for it.  (An element list in the kernel
+  // arguments instead of a range cost 170 B more spills per thread and 18 % of the fused
+  // volume kernel's time at N = 12, profiles/README.md.)
+  int bjorhus_tail_begin = -1;
   bool bjorhus_join_pending = false; // set by the face launcher, consumed by rhs_range
-  const int32_t* vol_list_cur = nullptr;  // element list of the next volume launch (or null)
-  int vol_list_count = 0;
   // non-conforming mortars (dgrhs_set_mortars)
   int n_mortar_faces = 0;
   int n_mortar_faces_local = 0;      // groups without a remote side come first
@@ -153,8 +153,19 @@ namespace {
 
 template <typename T>
 int dev_alloc(T** p, size_t count) {
-  CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
-  CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  // experiment (profiles/README.md, round 2): DGRHS_ALLOC_SKEW=<bytes> staggers the start
+  // addresses of the large arrays by k * skew (the arrays are then never freed)
+  static const long skew = std::getenv("DGRHS_ALLOC_SKEW") ? std::atol(std::getenv("DGRHS_ALLOC_SKEW")) : 0;
+  static int counter = 0;
+  if (skew > 0 && bytes > (size_t(64) << 20)) {
+    char* base = nullptr;
+    CU(cudaMalloc((void**)&base, bytes + 16 * (size_t)skew));
+    *p = reinterpret_cast<T*>(base + (size_t)(counter++ % 16) * (size_t)skew);
+  } else {
+    CU(cudaMalloc((void**)p, bytes));
+  }
+  CU(cudaMemset(*p, 0, bytes));
   return 0;
 }
 

@@ -320,18 +320,13 @@ int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume
   if (!volume_only && ops->faces(c, eb, ee)) return 1;
   if (c->bjorhus_join_pending) {
     // The Bjorhus kernel (few long, latency-bound CTAs on the side stream) only feeds the
-    // elements that own a Bjorhus face: all other elements go first, next to it
+    // elements that own a Bjorhus face (the tail of the element order): the others go first
     c->bjorhus_join_pending = false;
-    c->vol_list_cur = c->vol_list;
-    c->vol_list_count = c->n_vol_plain;
-    int rc = c->n_vol_plain > 0 ? ops->volume(c, dt, eb, ee, true, &upd) : 0;
+    const int tb = c->bjorhus_tail_begin;
+    int rc = ops->volume(c, dt, eb, tb, true, &upd);
     if (!rc && cudaStreamWaitEvent(c->stream, c->aux_join, 0) != cudaSuccess) rc = 1;
     c->pdl_volume = false;
-    c->vol_list_cur = c->vol_list + c->n_vol_plain;
-    c->vol_list_count = c->nelem - c->n_vol_plain;
-    if (!rc) rc = ops->volume(c, dt, eb, ee, true, &upd);
-    c->vol_list_cur = nullptr;
-    c->vol_list_count = 0;
+    if (!rc) rc = ops->volume(c, dt, tb, ee, true, &upd);
     return rc;
   }
   return ops->volume(c, dt, eb, ee, !volume_only, &upd);
@@ -549,7 +544,6 @@ int dgrhs_destroy(dgrhs_ctx* c) {
   if (c->nbr_face) cudaFree(c->nbr_face);
   if (c->violations) cudaFree(c->violations);
   if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
-  if (c->vol_list) cudaFree(c->vol_list);
   if (c->mortar_faces) cudaFree(c->mortar_faces);
   if (c->mortar_table) cudaFree(c->mortar_table);
   if (c->mortar_P) cudaFree(c->mortar_P);
@@ -630,20 +624,18 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   }
   if (c->bjorhus_faces) cudaFree(c->bjorhus_faces);
   c->bjorhus_faces = nullptr;
-  if (c->vol_list) cudaFree(c->vol_list);
-  c->vol_list = nullptr;
   c->n_bjorhus_faces = (int)(bj.size() / 3);
+  c->bjorhus_tail_begin = -1;
   if (!bj.empty()) {
+    int first = c->nelem;
     std::vector<char> has(c->nelem, 0);
-    for (size_t k = 0; k < bj.size(); k += 3) has[bj[k]] = 1;
-    std::vector<int32_t> order;
-    for (int e = 0; e < c->nelem; ++e)
-      if (!has[e]) order.push_back(e);
-    c->n_vol_plain = (int)order.size();
-    for (int e = 0; e < c->nelem; ++e)
-      if (has[e]) order.push_back(e);
-    CU(cudaMalloc(&c->vol_list, order.size() * 4));
-    CU(cudaMemcpy(c->vol_list, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
+    for (size_t k = 0; k < bj.size(); k += 3) {
+      has[bj[k]] = 1;
+      first = std::min(first, (int)bj[k]);
+    }
+    bool tail = first > 0;
+    for (int e = first; e < c->nelem && tail; ++e) tail = has[e] != 0;
+    if (tail) c->bjorhus_tail_begin = first;
   }
   if (!bj.empty()) {
     CU(cudaMalloc(&c->bjorhus_faces, bj.size() * 4));

@@ -40,6 +40,15 @@ namespace dg {
 #ifndef DG_SHARED_D_MIN_N
 #define DG_SHARED_D_MIN_N 12
 #endif
+#ifndef DG_LAZY_DH
+#define DG_LAZY_DH 0   // measured: more spills (488 B instead of 264 B per thread at N = 12)
+#endif
+#ifndef DG_STREAMING_HINTS
+#define DG_STREAMING_HINTS 1
+#endif
+#ifndef DG_Q_IN_SMEM
+#define DG_Q_IN_SMEM 1
+#endif
 #ifndef DG_WARP_RELEASE_MIN_N
 #define DG_WARP_RELEASE_MIN_N 10
 #endif
@@ -265,7 +274,13 @@ struct UpdateArgs {
 __device__ __forceinline__ void fused_prefetch(const UpdateArgs& up, size_t idx,
                                                double (&hv)[3]) {
 #pragma unroll
+#if DG_STREAMING_HINTS
+  // read once, never again: evict-first in L2, so that the lines that ARE reused (the element
+  // tiles the seven chunk CTAs of an element stage, the spill slots) stay
+  for (int j = 0; j < 3; ++j) hv[j] = (j < up.nterms) ? __ldcs(up.v[j] + idx) : 0.0;
+#else
   for (int j = 0; j < 3; ++j) hv[j] = (j < up.nterms) ? __ldg(up.v[j] + idx) : 0.0;
+#endif
 }
 __device__ __forceinline__ void fused_update(const UpdateArgs& up, size_t idx, double u,
                                              const double (&hv)[3], double dt_new) {
@@ -274,7 +289,11 @@ __device__ __forceinline__ void fused_update(const UpdateArgs& up, size_t idx, d
   for (int j = 0; j < 3; ++j)
     if (j < up.nterms) r = fma(up.c[j], hv[j], r);
   r = fma(up.c_new, dt_new, r);
+#if DG_STREAMING_HINTS
+  __stcs(up.u_new + idx, r);
+#else
   up.u_new[idx] = r;
+#endif
 }
 
 // --------------------------------------------------------------------------
@@ -294,7 +313,6 @@ struct GhVolArgs {
   int elem_begin;
   UpdateArgs upd;
   int prefetch_dist;  // CTAs ahead whose prologue inputs are pulled into L2 (0: off)
-  const int32_t* elem_list;  // nullptr: elements elem_begin, elem_begin + 1, ...; else the list
 };
 
 template <int N>
@@ -337,15 +355,26 @@ __device__ __forceinline__ void gh_point_prologue(const GhVolArgs& a, int e, int
     const double* he = a.gH + (size_t)e * 4 * npad + pt;
     const double* dhe = a.gdH + (size_t)e * 16 * npad + pt;
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-      gh.H[x] = __ldg(he + (size_t)x * npad);
+    for (int x = 0; x < 4; ++x) gh.H[x] = __ldg(he + (size_t)x * npad);
+#if DG_LAZY_DH
+    gin.dH_global = dhe;
+    gin.dH_stride = npad;
+#else
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
 #pragma unroll
       for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
-    }
+#endif
   }
+#if DG_Q_IN_SMEM
+  (void)Q;
+  gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx,
+                           QStrided{sQ_pt, q_stride}, ig);
+#else
   gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig);
 #pragma unroll
   for (int s = 0; s < 10; ++s) sQ_pt[s * q_stride] = Q[s];
+#endif
   // the inverse Jacobian is fetched only now: keeping its 9 values out of
   // the register-critical part of the prologue avoids spills
   asm volatile("" ::: "memory");
@@ -373,8 +402,7 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
       reinterpret_cast<uint64_t*>(sD + (kSharedD ? 2 : 1) * ((N * N + 1) / 2 * 2));
   unsigned int* released = reinterpret_cast<unsigned int*>(bars + 4);  // [NS] warps done
 
-  const int e = a.elem_list ? a.elem_list[blockIdx.x / Cfg<N>::nchunk]
-                            : a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
+  const int e = a.elem_begin + blockIdx.x / Cfg<N>::nchunk;
   const int chunk = blockIdx.x % Cfg<N>::nchunk;
   const int tid = threadIdx.x;
   const int pt = chunk * T + tid;
@@ -463,8 +491,7 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
       // component rows per pair.
       const unsigned int bt = blockIdx.x + (unsigned int)a.prefetch_dist;
       if (bt < gridDim.x) {
-        const int et = a.elem_list ? a.elem_list[bt / Cfg<N>::nchunk]
-                                   : a.elem_begin + (int)(bt / Cfg<N>::nchunk);
+        const int et = a.elem_begin + (int)(bt / Cfg<N>::nchunk);
         const int ptt = (int)(bt % Cfg<N>::nchunk) * T + tid;
         if (ptt < n) {
           const double* ut = a.u + (size_t)et * 50 * npad + ptt;
@@ -543,10 +570,17 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
 #pragma unroll
         for (int c = 0; c < 5; ++c) o[c] = slots.add(o[c], cs, c);
       }
+#if DG_STREAMING_HINTS
+      __stcs(dte + (size_t)s * npad + pt, o[0]);
+      __stcs(dte + (size_t)(10 + s) * npad + pt, o[1]);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) __stcs(dte + (size_t)(20 + m + 3 * s) * npad + pt, o[2 + m]);
+#else
       dte[(size_t)s * npad + pt] = o[0];
       dte[(size_t)(10 + s) * npad + pt] = o[1];
 #pragma unroll
       for (int m = 0; m < 3; ++m) dte[(size_t)(20 + m + 3 * s) * npad + pt] = o[2 + m];
+#endif
       if (do_upd) {
         fused_update(a.upd, ubase + (size_t)s * npad, t[pt], hv[0], o[0]);
         fused_update(a.upd, ubase + (size_t)(10 + s) * npad, t[npad + pt], hv[1], o[1]);

@@ -66,7 +66,8 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   CU(cudaGetLastError());
   // whole-batch pass of the fused GH kernel: the join is deferred to the volume launch of the
   // elements that own a Bjorhus face (rhs_range); otherwise join here
-  const bool defer_join = bjorhus_now && pass == 0 && c->vol_list && c->volume_variant == 0 &&
+  const bool defer_join = bjorhus_now && pass == 0 && c->bjorhus_tail_begin > 0 &&
+                          c->volume_variant == 0 &&
                           std::getenv("DGRHS_NO_BJORHUS_OVERLAP") == nullptr;
   if (bjorhus_now && !defer_join) CU(cudaStreamWaitEvent(c->stream, c->aux_join, 0));
   c->bjorhus_join_pending = defer_join;
@@ -160,10 +161,10 @@ int launch_volume(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
   const bool pdl = c->pdl_volume;
   c->pdl_volume = false;
   if (ee <= eb) return 0;
-  const int blocks = (c->vol_list_cur ? c->vol_list_count : ee - eb) * dg::Cfg<N>::nchunk;
+  const int blocks = (ee - eb) * dg::Cfg<N>::nchunk;
   if (c->system == DGRHS_SYSTEM_GH) {
     dg::GhVolArgs a{c->u, dt, c->invjac, c->stat, with_corr ? c->corr : nullptr,
-                    c->gH, c->gdH, c->D, c->coords, {}, eb, upd, 0, c->vol_list_cur};
+                    c->gH, c->gdH, c->D, c->coords, {}, eb, upd, 0};
     {
       // one CTA per SM (N >= 10): pull the inputs of the CTA one wave ahead into L2
       static const char* env = std::getenv("DGRHS_PREFETCH_DIST");

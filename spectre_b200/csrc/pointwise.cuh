@@ -208,6 +208,11 @@ struct GaugeInput {
   DampedHarmonicParams dh;       // kGauge == 2
   double x[3];                   // kGauge == 2: inertial coordinates
   GaugeH* computed = nullptr;    // kGauge == 2: if set, receives H_a and d_a H_b
+  // kGauge == 1, device only: d_a H_b read from global memory where it is used
+  // (component a + 4 b at dH_global[(a + 4 b) * dH_stride]) instead of from fields->dH:
+  // sixteen fewer values live through the first half of the prologue
+  const double* dH_global = nullptr;
+  size_t dH_stride = 0;
 };
 
 // Computes the context and Q[10], the part of the bracket of the dt Pi
@@ -238,11 +243,19 @@ DG_HD void gh_context_set_jacobian(GhContext& ctx, const double (&J)[3][3],
   }
 }
 
-template <int kGauge>
+// Q may be an array of 10 doubles or any object with operator[] that returns a reference
+// (QStrided: straight into shared memory, so that the ten accumulators do not hold registers
+// through the register-critical middle of the prologue)
+struct QStrided {
+  double* p;
+  int stride;
+  DG_HD double& operator[](int s) const { return p[s * stride]; }
+};
+template <int kGauge, typename QRef>
 DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
                             const double (&phi)[3][10], double gamma0, double gamma1,
                             double gamma2, const GaugeInput& gin, GhContext& ctx,
-                            double (&Q)[10], double (&ig_out)[6]);
+                            QRef&& Q, double (&ig_out)[6]);
 
 template <int kGauge>
 DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
@@ -254,11 +267,11 @@ DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
   gh_context_set_jacobian(ctx, J, ig);
 }
 
-template <int kGauge>
+template <int kGauge, typename QRef>
 DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
                             const double (&phi)[3][10], double gamma0, double gamma1,
                             double gamma2, const GaugeInput& gin, GhContext& ctx,
-                            double (&Q)[10], double (&ig_out)[6]) {
+                            QRef&& Q, double (&ig_out)[6]) {
   constexpr bool kHarmonic = kGauge == 0;
   Geom3p1 q;
   geom_from_metric(g, q);
@@ -376,7 +389,14 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
     for (int mu = 0; mu < 4; ++mu)
 #pragma unroll
       for (int nu = mu; nu < 4; ++nu) {
+#ifdef __CUDA_ARCH__
+        double v = gin.dH_global
+                       ? -(__ldg(gin.dH_global + (size_t)(mu + 4 * nu) * gin.dH_stride) +
+                           __ldg(gin.dH_global + (size_t)(nu + 4 * mu) * gin.dH_stride))
+                       : -(gauge->dH[mu][nu] + gauge->dH[nu][mu]);
+#else
         double v = -(gauge->dH[mu][nu] + gauge->dH[nu][mu]);
+#endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) v += 2.0 * Hup[e] * DG_CHR(e, mu, nu);
         Q[sym4(mu, nu)] += v;
