@@ -40,8 +40,14 @@ namespace dg {
 #ifndef DG_SHARED_D_MIN_N
 #define DG_SHARED_D_MIN_N 12
 #endif
-#ifndef DG_LAZY_DH
-#define DG_LAZY_DH 0   // measured: more spills (488 B instead of 264 B per thread at N = 12)
+#ifndef DG_LATE_GAUGE_LOAD
+#define DG_LATE_GAUGE_LOAD 0   // measured: more spills (312 B instead of 264 B per thread)
+#endif
+#ifndef DG_PARK_IN_RING
+#define DG_PARK_IN_RING 1
+#endif
+#ifndef DG_STAGED_LOADS
+#define DG_STAGED_LOADS 0   // measured: same spill count, one more L2 round trip per CTA
 #endif
 #ifndef DG_STREAMING_HINTS
 #define DG_STREAMING_HINTS 1
@@ -327,10 +333,31 @@ constexpr int gh_volume_smem_bytes() {
 template <int N, int kGauge>
 __device__ __forceinline__ void gh_point_prologue(const GhVolArgs& a, int e, int pt,
                                                   double* __restrict__ sQ_pt, int q_stride,
-                                                  GhContext& ctx) {
+                                                  GhContext& ctx,
+                                                  double* __restrict__ park_pt = nullptr) {
   constexpr int npad = Cfg<N>::npad;
   const double* __restrict__ ue = a.u + (size_t)e * 50 * npad;
   double g[10], pi[10], phi[3][10], Q[10], ig[6];
+#if DG_STAGED_LOADS
+  // The metric first: the 3+1 split is formed while only these ten values (and nothing that
+  // is needed later) occupy registers; the other 40 + 20 loads are issued behind it.  Costs one
+  // more L2 round trip per CTA (the inputs were prefetched into L2 by the previous wave),
+  // saves the spills the single 76-load burst caused.
+#pragma unroll
+  for (int s = 0; s < 10; ++s) g[s] = __ldg(ue + (size_t)s * npad + pt);
+  {
+    Geom3p1 q0;
+    geom_from_metric(g, q0);
+    asm volatile("" ::"d"(q0.lapse), "d"(q0.ig[0]), "d"(q0.ig[3]), "d"(q0.ig[5]) : "memory");
+  }
+#pragma unroll
+  for (int s = 0; s < 10; ++s) {
+    pi[s] = __ldg(ue + (size_t)(10 + s) * npad + pt);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad + pt);
+  }
+#else
 #pragma unroll
   for (int s = 0; s < 10; ++s) {
     g[s] = __ldg(ue + (size_t)s * npad + pt);
@@ -339,6 +366,7 @@ __device__ __forceinline__ void gh_point_prologue(const GhVolArgs& a, int e, int
     for (int m = 0; m < 3; ++m)
       phi[m][s] = __ldg(ue + (size_t)(20 + m + 3 * s) * npad + pt);
   }
+#endif
   const double* se = a.stat + (size_t)e * 3 * npad + pt;
   const double gamma0 = __ldg(se), gamma1 = __ldg(se + npad),
                gamma2 = __ldg(se + 2 * npad);
@@ -354,22 +382,27 @@ __device__ __forceinline__ void gh_point_prologue(const GhVolArgs& a, int e, int
   if constexpr (kGauge == 1) {
     const double* he = a.gH + (size_t)e * 4 * npad + pt;
     const double* dhe = a.gdH + (size_t)e * 16 * npad + pt;
-#pragma unroll
-    for (int x = 0; x < 4; ++x) gh.H[x] = __ldg(he + (size_t)x * npad);
-#if DG_LAZY_DH
+#if DG_LATE_GAUGE_LOAD
+    gin.H_global = he;
     gin.dH_global = dhe;
-    gin.dH_stride = npad;
+    gin.stride = npad;
 #else
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < 4; ++x) {
+      gh.H[x] = __ldg(he + (size_t)x * npad);
 #pragma unroll
       for (int y = 0; y < 4; ++y) gh.dH[x][y] = __ldg(dhe + (size_t)(x + 4 * y) * npad);
+    }
 #endif
   }
 #if DG_Q_IN_SMEM
   (void)Q;
-  gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx,
-                           QStrided{sQ_pt, q_stride}, ig);
+  if (park_pt != nullptr)
+    gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx,
+                             QStrided{sQ_pt, q_stride}, ig, QStrided{park_pt, q_stride});
+  else
+    gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx,
+                             QStrided{sQ_pt, q_stride}, ig);
 #else
   gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig);
 #pragma unroll
@@ -443,16 +476,25 @@ __global__ void __launch_bounds__(Cfg<N>::T, Cfg<N>::min_blocks) gh_volume_kerne
   }
 
   // ---- prologue: everything that needs all 50 components at the point ----
+  // N = 12: the correction block of the second ring stage is idle until the prologue is over
+  // (its copy is issued behind the barrier below): sixteen doubles per thread of it park the
+  // early results of the prologue (see LocalPark) instead of registers / spill slots
+  constexpr bool kPark = DG_PARK_IN_RING && NS == 2 && 30 * f >= 16 * T;
   GhContext ctx;
-  if (active) gh_point_prologue<N, kGauge>(a, e, pt, sQ + tid, T, ctx);
+  if (active)
+    gh_point_prologue<N, kGauge>(a, e, pt, sQ + tid, T, ctx,
+                                 kPark ? ring + SD + 5 * npad + tid : nullptr);
   // the face corrections are the only input the preceding face kernel writes: under
   // programmatic dependent launch everything above overlaps that kernel's last wave
   if (tid == 0 && with_corr) {
     pdl_wait_for_primary();
 #pragma unroll
-    for (int st = 0; st < NS; ++st) issue(st, st, 2);
+    for (int st = 0; st < (kPark ? 1 : NS); ++st) issue(st, st, 2);
   }
   __syncthreads();  // sD visible, barrier init visible to all waiters
+  if constexpr (kPark) {
+    if (tid == 0 && with_corr) issue(1, 1, 2);
+  }
 
   const int i = pt % N, j = (pt / N) % N, k = pt / (N * N);
   double Di[kSharedD ? 1 : N], Dj[kSharedD ? 1 : N], Dk[kSharedD ? 1 : N];

@@ -208,11 +208,13 @@ struct GaugeInput {
   DampedHarmonicParams dh;       // kGauge == 2
   double x[3];                   // kGauge == 2: inertial coordinates
   GaugeH* computed = nullptr;    // kGauge == 2: if set, receives H_a and d_a H_b
-  // kGauge == 1, device only: d_a H_b read from global memory where it is used
-  // (component a + 4 b at dH_global[(a + 4 b) * dH_stride]) instead of from fields->dH:
-  // sixteen fewer values live through the first half of the prologue
+  // kGauge == 1, device only: if set, H_a (component a at H_global[a * stride]) and d_a H_b
+  // (component a + 4 b at dH_global[(a + 4 b) * stride]) are fetched inside the prologue just
+  // before their first use instead of being handed over in `fields`: twenty values fewer in
+  // registers while the 50 evolved components arrive and the normal contractions are formed
+  const double* H_global = nullptr;
   const double* dH_global = nullptr;
-  size_t dH_stride = 0;
+  size_t stride = 0;
 };
 
 // Computes the context and Q[10], the part of the bracket of the dt Pi
@@ -246,16 +248,40 @@ DG_HD void gh_context_set_jacobian(GhContext& ctx, const double (&J)[3][3],
 // Q may be an array of 10 doubles or any object with operator[] that returns a reference
 // (QStrided: straight into shared memory, so that the ten accumulators do not hold registers
 // through the register-critical middle of the prologue)
+// Orders the shared-memory updates of Q (and with them the arithmetic that feeds them): keeps
+// the compiler from interleaving the unrolled iterations of the quadratic terms, whose
+// temporaries would otherwise all be live at once.  No instruction is emitted.
+#if defined(__CUDA_ARCH__) && !defined(DG_NO_SCHED_BARRIER)
+#define DG_SCHED_BARRIER() asm volatile("" ::: "memory")
+#else
+#define DG_SCHED_BARRIER() ((void)0)
+#endif
 struct QStrided {
   double* p;
   int stride;
   DG_HD double& operator[](int s) const { return p[s * stride]; }
 };
+// Sixteen values that are formed early and needed only by the streaming phase (w, V,
+// half_pi_nn, half_phi_nn) are handed to a "park" object between the two: LocalPark keeps them
+// in registers (host code, the small kernels), the fused volume kernel passes shared memory
+// that is idle during the prologue, so that they do not occupy registers through the
+// quadratic terms.
+struct LocalPark {
+  double v[16];
+  DG_HD double& operator[](int k) { return v[k]; }
+};
+template <int kGauge, typename QRef, typename Park>
+DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
+                            const double (&phi)[3][10], double gamma0, double gamma1,
+                            double gamma2, const GaugeInput& gin, GhContext& ctx,
+                            QRef&& Q, double (&ig_out)[6], Park&& park);
 template <int kGauge, typename QRef>
 DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
                             const double (&phi)[3][10], double gamma0, double gamma1,
                             double gamma2, const GaugeInput& gin, GhContext& ctx,
-                            QRef&& Q, double (&ig_out)[6]);
+                            QRef&& Q, double (&ig_out)[6]) {
+  gh_prologue_core<kGauge>(g, pi, phi, gamma0, gamma1, gamma2, gin, ctx, Q, ig_out, LocalPark{});
+}
 
 template <int kGauge>
 DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
@@ -267,11 +293,11 @@ DG_HD void gh_prologue(const double (&g)[10], const double (&pi)[10],
   gh_context_set_jacobian(ctx, J, ig);
 }
 
-template <int kGauge, typename QRef>
+template <int kGauge, typename QRef, typename Park>
 DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
                             const double (&phi)[3][10], double gamma0, double gamma1,
                             double gamma2, const GaugeInput& gin, GhContext& ctx,
-                            QRef&& Q, double (&ig_out)[6]) {
+                            QRef&& Q, double (&ig_out)[6], Park&& park) {
   constexpr bool kHarmonic = kGauge == 0;
   Geom3p1 q;
   geom_from_metric(g, q);
@@ -320,7 +346,7 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
     double v = nv[0] * pon[0];
 #pragma unroll
     for (int a = 1; a < 4; ++a) v += nv[a] * pon[a];
-    ctx.half_pi_nn = 0.5 * v;
+    if constexpr (kGauge == 2) ctx.half_pi_nn = 0.5 * v; else park[12] = 0.5 * v;
   }
   double pho[3][4];
 #pragma unroll
@@ -335,14 +361,47 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
     double v = nv[0] * pho[n][0];
 #pragma unroll
     for (int a = 1; a < 4; ++a) v += nv[a] * pho[n][a];
-    ctx.half_phi_nn[n] = 0.5 * v;
+    if constexpr (kGauge == 2) ctx.half_phi_nn[n] = 0.5 * v; else park[13 + n] = 0.5 * v;
   }
+  // w and V of the linear-coefficient context need only these contractions and gamma^{ij}:
+  // formed now and parked (see LocalPark)
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    double v = pon[1] * q.ig[sym3(0, m)];
+    v += pon[2] * q.ig[sym3(1, m)];
+    v += pon[3] * q.ig[sym3(2, m)];
+    park[m] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      double v = pho[i][1] * q.ig[sym3(0, m)];
+      v += pho[i][2] * q.ig[sym3(1, m)];
+      v += pho[i][3] * q.ig[sym3(2, m)];
+      park[3 + 3 * i + m] = v;
+    }
   // Christoffel symbols of the first kind Gamma_k,ij (Christoffel.cpp:16-31)
   // are formed on the fly: chr(k,i,j) = 1/2 (d_i g_jk + d_j g_ik - d_k g_ij)
 #define DG_CHR(k, i, j) \
   (0.5 * (dag[i][sym4(j, k)] + dag[j][sym4(i, k)] - dag[k][sym4(i, j)]))
   GaugeH gauge_local;
   const GaugeH* gauge = gin.fields;
+#ifdef __CUDA_ARCH__
+  if constexpr (kGauge == 1) {
+    if (gin.H_global != nullptr) {
+      asm volatile("" ::: "memory");   // not before the work above
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        gauge_local.H[a] = __ldg(gin.H_global + (size_t)a * gin.stride);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          gauge_local.dH[a][b] = __ldg(gin.dH_global + (size_t)(a + 4 * b) * gin.stride);
+      }
+      gauge = &gauge_local;
+    }
+  }
+#endif
   if constexpr (kGauge == 2) {
     damped_harmonic_gauge(gin.dh, gin.x, lapse, q.shift, sqrt(q.det), q.ig, dag,
                           ctx.half_pi_nn, ctx.half_phi_nn, g, gauge_local);
@@ -389,14 +448,7 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
     for (int mu = 0; mu < 4; ++mu)
 #pragma unroll
       for (int nu = mu; nu < 4; ++nu) {
-#ifdef __CUDA_ARCH__
-        double v = gin.dH_global
-                       ? -(__ldg(gin.dH_global + (size_t)(mu + 4 * nu) * gin.dH_stride) +
-                           __ldg(gin.dH_global + (size_t)(nu + 4 * mu) * gin.dH_stride))
-                       : -(gauge->dH[mu][nu] + gauge->dH[nu][mu]);
-#else
         double v = -(gauge->dH[mu][nu] + gauge->dH[nu][mu]);
-#endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) v += 2.0 * Hup[e] * DG_CHR(e, mu, nu);
         Q[sym4(mu, nu)] += v;
@@ -423,6 +475,7 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
         for (int d = 0; d < 4; ++d) v += pi[sym4(mu, d)] * X[nu][d];
         Q[sym4(mu, nu)] -= 2.0 * v;
       }
+    DG_SCHED_BARRIER();
   }
   // T2 = sum_n (gamma^{nm} Phi_m) G Phi_n  (:355-358)
 #pragma unroll
@@ -454,6 +507,7 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
         for (int d = 0; d < 4; ++d) v += Y[sym4(mu, d)] * X[nu][d];
         Q[sym4(mu, nu)] += 2.0 * v;
       }
+    DG_SCHED_BARRIER();
   }
   // T3_{mu nu} = tr(Gamma_mu G Gamma_nu G) = Gamma_nu,ab C_mu^{ab},
   // C_mu = G Gamma_mu G (symmetric)  (:360-364).  One C_mu is live at a time.
@@ -490,26 +544,24 @@ DG_HD void gh_prologue_core(const double (&g)[10], const double (&pi)[10],
         for (int b = a; b < 4; ++b) v += DG_CHR(nu, a, b) * C[sym4(a, b)];
       Q[sym4(mu, nu)] -= 2.0 * v;
     }
+    DG_SCHED_BARRIER();
   }
 #undef DG_CHR
   // linear-coefficient context
 #pragma unroll
   for (int m = 0; m < 3; ++m) {
     ctx.shift[m] = q.shift[m];
-    double v = pon[1] * q.ig[sym3(0, m)];
-    v += pon[2] * q.ig[sym3(1, m)];
-    v += pon[3] * q.ig[sym3(2, m)];
-    ctx.w[m] = v;
+    ctx.w[m] = park[m];
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      double v = pho[i][1] * q.ig[sym3(0, m)];
-      v += pho[i][2] * q.ig[sym3(1, m)];
-      v += pho[i][3] * q.ig[sym3(2, m)];
-      ctx.V[i][m] = v;
-    }
+    for (int m = 0; m < 3; ++m) ctx.V[i][m] = park[3 + 3 * i + m];
+  if constexpr (kGauge != 2) {
+    ctx.half_pi_nn = park[12];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) ctx.half_phi_nn[n] = park[13 + n];
+  }
 #pragma unroll
   for (int x = 0; x < 6; ++x) ig_out[x] = q.ig[x];
 }
