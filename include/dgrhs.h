@@ -112,6 +112,19 @@ int dgrhs_set_neighbor_orientations(dgrhs_ctx* ctx, const int32_t* neighbor_dire
  * GeneralizedHarmonic/Initialize.hpp:59-71).  host [n_elements][ncomp][n]. */
 int dgrhs_set_static_fields(dgrhs_ctx* ctx, const double* fields, int ncomp);
 
+/* Moving mesh: inertial mesh velocity v_g^i at the grid points, host [n_elements][3][n]
+ * (Tags::MeshVelocity), or NULL for a static mesh (the default).  With a velocity set the
+ * right-hand side gains the terms of a moving mesh for systems without fluxes: dt u += v_g^i
+ * d_i u (VolumeTermsImpl.tpp:155-235), GH: gamma1 v_g.C3 in dt g and gamma1 gamma2 v_g.C3 in
+ * dt Pi (GeneralizedHarmonic/TimeDerivative.cpp:237-300,372-378), and the characteristic
+ * speeds of dg_package_data are taken relative to the mesh (normal_dot_mesh_velocity,
+ * UpwindPenalty.cpp:85-91 / ScalarWave UpwindPenalty.cpp:55-67; also for
+ * DemandOutgoingCharSpeeds).  The caller supplies the inverse Jacobian (dgrhs_set_geometry) and
+ * the velocity of the current time; the maps themselves stay with the caller.  Conforming
+ * faces and ghost boundary conditions only (Bjorhus faces and non-conforming mortars are
+ * rejected); the stepper update is not fused on a moving mesh. */
+int dgrhs_set_mesh_velocity(dgrhs_ctx* ctx, const double* mesh_velocity);
+
 /* GH gauge condition.  params: DAMPED_HARMONIC: {width, amp_L1, amp_L2, amp_S,
  * exp_L1, exp_L2, exp_S}; ANALYTIC_GAUGE_WAVE: {amplitude, wavelength}. */
 int dgrhs_set_gauge(dgrhs_ctx* ctx, int gauge, const double* params, int nparams);
@@ -437,6 +450,14 @@ int dgrhs_gh_package_data(int f, const double* u, const double* gamma1,
                           const double* shift, const double* normal_covector,
                           const double* normal_vector, double* packaged,
                           double* max_abs_char_speed);
+/* The same with normal_dot_mesh_velocity [f] of a moving mesh (UpwindPenalty.cpp:85-91: the
+ * speeds relative to the mesh; NULL = static mesh). */
+int dgrhs_gh_package_data_moving(int f, const double* u, const double* gamma1,
+                                 const double* gamma2, const double* lapse,
+                                 const double* shift, const double* normal_covector,
+                                 const double* normal_vector,
+                                 const double* normal_dot_mesh_velocity, double* packaged,
+                                 double* max_abs_char_speed);
 /* ...::dg_boundary_terms (UpwindPenalty.cpp:161-275): [134][f] x2 -> [50][f] */
 int dgrhs_gh_boundary_terms(int f, const double* packaged_int,
                             const double* packaged_ext,
@@ -446,6 +467,11 @@ int dgrhs_gh_boundary_terms(int f, const double* packaged_int,
 int dgrhs_sw_package_data(int f, const double* u, const double* gamma2,
                           const double* normal_covector, double* packaged,
                           double* max_abs_char_speed);
+/* with normal_dot_mesh_velocity [f] (ScalarWave UpwindPenalty.cpp:55-67; NULL = static) */
+int dgrhs_sw_package_data_moving(int f, const double* u, const double* gamma2,
+                                 const double* normal_covector,
+                                 const double* normal_dot_mesh_velocity, double* packaged,
+                                 double* max_abs_char_speed);
 int dgrhs_sw_boundary_terms(int f, const double* packaged_int,
                             const double* packaged_ext,
                             double* boundary_correction);

@@ -654,14 +654,15 @@ static void face_normal(const double unnorm[3], int curved,
  * n_times_v_minus(3), gamma2_v_psi, char_speeds(3)
  * Evolution/Systems/ScalarWave/BoundaryCorrections/UpwindPenalty.cpp:36-108
  * ---------------------------------------------------------------------- */
-static void sw_package_point(const double u[5], double gamma2,
-                             const double n[3], double pk[16]) {
+static void sw_package_point_moving(const double u[5], double gamma2,
+                                    const double n[3], double ndotv, double pk[16]) {
   const double psi = u[0], pi = u[1];
   const double* phi = u + 2;
   double* cs = pk + 13;
-  cs[0] = 0.0;
-  cs[1] = 1.0;
-  cs[2] = -1.0;
+  /* UpwindPenalty.cpp:55-67: the mesh moves with n.v_g along the normal */
+  cs[0] = 0.0 - ndotv;
+  cs[1] = 1.0 - ndotv;
+  cs[2] = -1.0 - ndotv;
   double g2psi = gamma2 * psi;
   double ndphi = n[0] * phi[0];
   ndphi += n[1] * phi[1];
@@ -675,6 +676,10 @@ static void sw_package_point(const double u[5], double gamma2,
   }
   pk[0] = cs[0] * psi;
   pk[12] = g2psi * cs[0];
+}
+static void sw_package_point(const double u[5], double gamma2,
+                             const double n[3], double pk[16]) {
+  sw_package_point_moving(u, gamma2, n, 0.0, pk);
 }
 
 static double step_function(double x) { return x < 0.0 ? 0.0 : 1.0; }
@@ -728,10 +733,10 @@ void orc_sw_boundary_terms(int f, const double* pk_int, const double* pk_ext,
  * Evolution/Systems/GeneralizedHarmonic/BoundaryCorrections/
  *   UpwindPenalty.cpp:36-158
  * ---------------------------------------------------------------------- */
-static void gh_package_point(const double u[50], double gamma1, double gamma2,
-                             double lapse, const double shift[3],
-                             const double n_lo[3], const double n_up[3],
-                             double pk[134]) {
+static void gh_package_point_moving(const double u[50], double gamma1, double gamma2,
+                                    double lapse, const double shift[3],
+                                    const double n_lo[3], const double n_up[3],
+                                    double ndotv, double pk[134]) {
   double* v_g = pk;
   double* v_zero = pk + 10;
   double* v_plus = pk + 40;
@@ -748,6 +753,11 @@ static void gh_package_point(const double u[50], double gamma1, double gamma2,
   cs[0] = (1.0 + gamma1) * sdn;
   cs[2] = lapse + sdn;
   cs[3] = -lapse + sdn;
+  /* GH UpwindPenalty.cpp:85-91: speeds without the mesh movement, then the mesh movement */
+  cs[0] -= ndotv * (1.0 + gamma1);
+  cs[1] -= ndotv;
+  cs[2] -= ndotv;
+  cs[3] -= ndotv;
   for (int s = 0; s < 10; ++s) g2vg[s] = gamma2 * u[s];
   for (int s = 0; s < 10; ++s) {
     double ndphi = n_up[0] * u[20 + 0 + 3 * s];
@@ -765,6 +775,13 @@ static void gh_package_point(const double u[50], double gamma1, double gamma2,
     v_g[s] = cs[0] * u[s];
     g2vg[s] *= cs[0];
   }
+}
+
+static void gh_package_point(const double u[50], double gamma1, double gamma2,
+                             double lapse, const double shift[3],
+                             const double n_lo[3], const double n_up[3],
+                             double pk[134]) {
+  gh_package_point_moving(u, gamma1, gamma2, lapse, shift, n_lo, n_up, 0.0, pk);
 }
 
 /* GeneralizedHarmonic/BoundaryCorrections/UpwindPenalty.cpp:161-275 */
@@ -808,6 +825,41 @@ void orc_gh_package_data(int f, const double* u, const double* gamma1,
     for (int c = 0; c < 134; ++c) packaged[(size_t)c * f + p] = pk[c];
   }
 }
+
+void orc_gh_package_data_moving(int f, const double* u, const double* gamma1,
+                                const double* gamma2, const double* lapse,
+                                const double* shift, const double* n_lo,
+                                const double* n_up, const double* ndotv, double* packaged) {
+  for (int p = 0; p < f; ++p) {
+    double up[50], sh[3], nl[3], nu[3], pk[134];
+    for (int c = 0; c < 50; ++c) up[c] = u[(size_t)c * f + p];
+    for (int i = 0; i < 3; ++i) {
+      sh[i] = shift[(size_t)i * f + p];
+      nl[i] = n_lo[(size_t)i * f + p];
+      nu[i] = n_up[(size_t)i * f + p];
+    }
+    gh_package_point_moving(up, gamma1[p], gamma2[p], lapse[p], sh, nl, nu, ndotv[p], pk);
+    for (int c = 0; c < 134; ++c) packaged[(size_t)c * f + p] = pk[c];
+  }
+}
+
+void orc_sw_package_data_moving(int f, const double* u, const double* gamma2,
+                                const double* normal, const double* ndotv, double* packaged) {
+  for (int p = 0; p < f; ++p) {
+    double up[5], n[3], pk[16];
+    for (int c = 0; c < 5; ++c) up[c] = u[(size_t)c * f + p];
+    for (int i = 0; i < 3; ++i) n[i] = normal[(size_t)i * f + p];
+    sw_package_point_moving(up, gamma2[p], n, ndotv[p], pk);
+    for (int c = 0; c < 16; ++c) packaged[(size_t)c * f + p] = pk[c];
+  }
+}
+
+/* Mesh velocity of the next orc_dg_rhs* call ([nelem][3][n], inertial components; NULL =
+ * static mesh): VolumeTermsImpl.tpp:155-235 (dt u += v_g^i d_i u for systems without fluxes),
+ * GeneralizedHarmonic/TimeDerivative.cpp:237-300,372-378 (gamma1 v_g.C3 in dt g,
+ * gamma1 gamma2 v_g.C3 in dt Pi), normal_dot_mesh_velocity in dg_package_data. */
+static const double* g_mesh_velocity = NULL;
+void orc_set_mesh_velocity(const double* v) { g_mesh_velocity = v; }
 
 void orc_gh_boundary_terms(int f, const double* pk_int, const double* pk_ext,
                            double* corr) {
@@ -961,6 +1013,26 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
                                se + 3 * n, se + 7 * n,
                                coords ? coords + (size_t)e * 3 * n : NULL, dte);
       }
+      const double* ve = g_mesh_velocity ? g_mesh_velocity + (size_t)e * 3 * n : NULL;
+      if (ve) {
+        for (int p = 0; p < n; ++p) {
+          const double v[3] = {ve[p], ve[(size_t)n + p], ve[(size_t)2 * n + p]};
+          if (system == 1) {
+            for (int s = 0; s < 10; ++s) {
+              double vc3 = 0.0;
+              for (int i = 0; i < 3; ++i)
+                vc3 += v[i] * (du[(size_t)(3 * s + i) * n + p] - ue[(size_t)(20 + i + 3 * s) * n + p]);
+              dte[(size_t)s * n + p] += se[(size_t)n + p] * vc3;
+              dte[(size_t)(10 + s) * n + p] += se[(size_t)n + p] * se[(size_t)2 * n + p] * vc3;
+            }
+          }
+          for (int c = 0; c < C; ++c) {
+            double t = 0.0;
+            for (int i = 0; i < 3; ++i) t += v[i] * du[(size_t)(3 * c + i) * n + p];
+            dte[(size_t)c * n + p] += t;
+          }
+        }
+      }
       /* faces: slice, normal, package */
       for (int d = 0; d < 6; ++d) {
         const int dim = d / 2;
@@ -975,9 +1047,11 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
             for (int i = 0; i < 3; ++i)
               unnorm[i] = sign * je[(size_t)(dim + 3 * i) * n + p];
             for (int c = 0; c < C; ++c) up[c] = ue[(size_t)c * n + p];
+            double ndotv = 0.0;
             if (system == 0) {
               face_normal(unnorm, 0, NULL, n_lo, n_up, &mag[q]);
-              sw_package_point(up, se[p], n_lo, out);
+              if (ve) for (int i = 0; i < 3; ++i) ndotv += n_lo[i] * ve[(size_t)i * n + p];
+              sw_package_point_moving(up, se[p], n_lo, ndotv, out);
             } else {
               double g[4][4];
               GhGeom qg;
@@ -985,8 +1059,9 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
                 for (int b4 = 0; b4 < 4; ++b4) g[a4][b4] = up[SYM4(a4, b4)];
               gh_geometry(g, &qg);
               face_normal(unnorm, 1, qg.inv_gamma, n_lo, n_up, &mag[q]);
-              gh_package_point(up, se[n + p], se[2 * n + p], qg.lapse, qg.shift,
-                               n_lo, n_up, out);
+              if (ve) for (int i = 0; i < 3; ++i) ndotv += n_lo[i] * ve[(size_t)i * n + p];
+              gh_package_point_moving(up, se[n + p], se[2 * n + p], qg.lapse, qg.shift,
+                                      n_lo, n_up, ndotv, out);
             }
             for (int c = 0; c < PK; ++c) pk[(size_t)c * f + q] = out[c];
           }
@@ -1032,10 +1107,13 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
               const double sign = (d % 2) ? 1.0 : -1.0;
               for (int c = 0; c < C; ++c) uex[c] = xu[(size_t)c * f + q];
               for (int i = 0; i < 3; ++i) unnorm[i] = sign * je[(size_t)(dim + 3 * i) * n + p];
+              const double* vg = g_mesh_velocity ? g_mesh_velocity + (size_t)e * 3 * n : NULL;
+              double ndotv_e = 0.0;
               if (system == 0) {
                 face_normal(unnorm, 0, NULL, n_lo_i, n_up_i, &mag_i);
                 for (int i = 0; i < 3; ++i) n_lo[i] = -n_lo_i[i];
-                sw_package_point(uex, se[p], n_lo, ex);
+                if (vg) for (int i = 0; i < 3; ++i) ndotv_e += n_lo[i] * vg[(size_t)i * n + p];
+                sw_package_point_moving(uex, se[p], n_lo, ndotv_e, ex);
               } else {
                 double g[4][4], gi[4][4];
                 GhGeom qe, qi;
@@ -1049,8 +1127,9 @@ void orc_dg_rhs_mortars(int system, int N, int nelem, const double* D, const dou
                 gh_geometry(g, &qe);
                 for (int i = 0; i < 3; ++i) neg[i] = -n_lo_i[i];
                 face_normal(neg, 1, qe.inv_gamma, n_lo, n_up, &mag_e);
-                gh_package_point(uex, se[n + p], se[2 * n + p], qe.lapse, qe.shift, n_lo, n_up,
-                                 ex);
+                if (vg) for (int i = 0; i < 3; ++i) ndotv_e += n_lo[i] * vg[(size_t)i * n + p];
+                gh_package_point_moving(uex, se[n + p], se[2 * n + p], qe.lapse, qe.shift, n_lo,
+                                        n_up, ndotv_e, ex);
               }
             }
             if (system == 0)

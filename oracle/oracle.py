@@ -467,16 +467,49 @@ def gh_geometry(u):
             "det_gamma": out[20]}
 
 
+def gh_package_data_moving(u, gamma1, gamma2, lapse, shift, n_lo, n_up, ndotv):
+    """GH dg_package_data on f face points with normal_dot_mesh_velocity
+    (UpwindPenalty.cpp:36-158); u [50, f], shift / normals [3, f]; packaged [134, f]."""
+    f = u.shape[1]
+    out = np.zeros((134, f))
+    a = [_c(x) for x in (u, gamma1, gamma2, lapse, shift, n_lo, n_up, ndotv)]
+    lib().orc_gh_package_data_moving(f, *[_p(x) for x in a], _p(out))
+    return out
+
+
+def sw_package_data_moving(u, gamma2, normal, ndotv):
+    """ScalarWave dg_package_data with normal_dot_mesh_velocity (UpwindPenalty.cpp:36-108);
+    u [5, f], normal [3, f]; packaged [16, f]."""
+    f = u.shape[1]
+    out = np.zeros((16, f))
+    a = [_c(x) for x in (u, gamma2, normal, ndotv)]
+    lib().orc_sw_package_data_moving(f, *[_p(x) for x in a], _p(out))
+    return out
+
+
 def dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params=GAUGE_HARMONIC, coords=None,
-           volume_only=False, ext_u=None, nbr_dir=None, face_perm=None, mortars=None):
+           volume_only=False, ext_u=None, nbr_dir=None, face_perm=None, mortars=None,
+           mesh_velocity=None):
     """u [nelem, C, n]; returns dt_u of the same shape.  ext_u [nslots, C, f]:
     exterior states of ghost boundary conditions (nbr <= -2 -> slot -(nbr+2)).
     nbr_dir / face_perm [nelem, 6]: orientation of non-aligned neighbours (the
     neighbour's direction touching the face and the face-point permutation code,
     see orc_dg_rhs_oriented).  mortars [n, 6]: non-conforming (2:1) mortars
     (coarse element, direction, fine element, direction, size_a, size_b); the
-    faces involved carry HANGING in nbr (see orc_dg_rhs_mortars)."""
+    faces involved carry HANGING in nbr (see orc_dg_rhs_mortars).
+    mesh_velocity [nelem, 3, n]: inertial mesh velocity of a moving mesh (VolumeTermsImpl.tpp:
+    155-235, GH TimeDerivative.cpp:237-300,372-378, normal_dot_mesh_velocity in dg_package_data;
+    conforming faces and ghost boundary conditions only)."""
     nelem = u.shape[0]
+    if mesh_velocity is not None:
+        assert not volume_only and (mortars is None or len(mortars) == 0)
+        mv = _c(mesh_velocity)
+        lib().orc_set_mesh_velocity(_p(mv))
+        try:
+            return dg_rhs(system, N, u, invjac, static_fields, nbr, gauge_params, coords,
+                          volume_only, ext_u, nbr_dir, face_perm, mortars)
+        finally:
+            lib().orc_set_mesh_velocity(None)
     D = _c(differentiation_matrix(N))
     u, invjac, static_fields = _c(u), _c(invjac), _c(static_fields)
     gp = _c(gauge_params)

@@ -83,6 +83,7 @@ struct dgrhs_ctx {
   double* u0 = nullptr;           // saved value (self-start / RK step start)
   double* u_alt = nullptr;        // second state buffer for the fused update
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
+  double* mesh_v = nullptr;       // [E][3][npad] inertial mesh velocity (moving mesh) or null
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
   double filterF_host[144] = {};  // the same on the host (kernel parameter of the filter pass)
   int num_sms = 148;
@@ -208,5 +209,6 @@ struct DgNOps {
   int (*gauge_from_state)(dgrhs_ctx* c, const double* state_dev);
   int (*constraints)(dgrhs_ctx* c, double* sums_dev);
   int (*partial_derivatives)(const dg::DerivArgs* a, int blocks, cudaStream_t stream);
+  int (*mesh_velocity_terms)(dgrhs_ctx* c, double* dt, int eb, int ee);
 };
 const DgNOps* dgrhs_nops(int N);  // nullptr for an unsupported N

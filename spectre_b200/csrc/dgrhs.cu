@@ -329,7 +329,12 @@ int rhs_range(dgrhs_ctx* c, double time, double* dt, int eb, int ee, bool volume
     if (!rc) rc = ops->volume(c, dt, tb, ee, true, &upd);
     return rc;
   }
-  return ops->volume(c, dt, eb, ee, !volume_only, &upd);
+  if (ops->volume(c, dt, eb, ee, !volume_only, &upd)) return 1;
+  if (c->mesh_v) {
+    if (upd.u_new) return fail("internal error: fused update on a moving mesh");
+    return ops->mesh_velocity_terms(c, dt, eb, ee);
+  }
+  return 0;
 }
 
 int lincomb(dgrhs_ctx* c, double* u, double a, const std::vector<double>& coef,
@@ -390,7 +395,7 @@ int ab_update(dgrhs_ctx* c, int order, long long start, long long end) {
 // unfused ab_update / RK path, so the result is bit-identical.
 int prepare_fused_update(dgrhs_ctx* c) {
   c->upd_active = false;
-  if (!c->fuse_update) return 0;
+  if (!c->fuse_update || c->mesh_v) return 0;
   if (!c->u_alt && dev_alloc(&c->u_alt, c->state_len())) return 1;
   dg::UpdateArgs up{};
   up.u_new = c->u_alt;
@@ -537,7 +542,8 @@ int dgrhs_destroy(dgrhs_ctx* c) {
     cudaEventDestroy(c->ev_faces1);
   }
   for (double* p : {c->u, c->invjac, c->coords, c->stat, c->corr, c->D, c->gH, c->gdH,
-                    c->halo_send, c->halo_recv, c->u0, c->u_alt, c->ctxbuf, c->filterF})
+                    c->halo_send, c->halo_recv, c->u0, c->u_alt, c->ctxbuf, c->filterF,
+                    c->mesh_v})
     if (p) cudaFree(p);
   for (double* p : c->dt_slots) cudaFree(p);
   if (c->nbr) cudaFree(c->nbr);
@@ -1099,6 +1105,22 @@ int dgrhs_set_static_fields(dgrhs_ctx* c, const double* fields, int ncomp) {
   if (ncomp != c->S) return fail("expected %d static components, got %d", c->S, ncomp);
   CU(cudaSetDevice(c->device));
   return upload(c, c->stat, fields, ncomp);
+}
+
+int dgrhs_set_mesh_velocity(dgrhs_ctx* c, const double* mesh_velocity) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (c->in_substep) return fail("dgrhs_set_mesh_velocity inside a substep");
+  if (!mesh_velocity) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->mesh_v) cudaFree(c->mesh_v);
+    c->mesh_v = nullptr;
+    return 0;
+  }
+  if (c->n_bjorhus_faces > 0 || c->n_mortar_faces > 0 || c->n_pmortar_faces > 0)
+    return fail("moving mesh: Bjorhus faces and non-conforming mortars are not supported");
+  if (!c->mesh_v && dev_alloc(&c->mesh_v, (size_t)c->nelem * 3 * c->npad)) return 1;
+  return upload(c, c->mesh_v, mesh_velocity, 3);
 }
 
 int dgrhs_set_gauge(dgrhs_ctx* c, int gauge, const double* params, int nparams) {
@@ -1702,6 +1724,7 @@ int rhs_with_exchange(dgrhs_ctx* c, double t) {
   if (pt) CU(cudaEventRecord(c->phase_ev[2], main_stream));
   c->pdl_volume = false;  // an event sits between the faces and the volume kernel
   if (ni > 0 && ops->volume(c, c->dt_last, 0, ni, true, &upd)) return 1;
+  if (c->mesh_v && ops->mesh_velocity_terms(c, c->dt_last, 0, ni)) return 1;
   if (pt) CU(cudaEventRecord(c->phase_ev[3], main_stream));
   {
     c->stream = c->comm_stream;  // the launchers queue on c->stream
@@ -1710,6 +1733,7 @@ int rhs_with_exchange(dgrhs_ctx* c, double t) {
     c->pdl_volume = false;
     if (!rc && cudaStreamWaitEvent(c->comm_stream, c->ev_faces1, 0) != cudaSuccess) rc = 1;
     if (!rc) rc = ops->volume(c, c->dt_last, ni, c->nelem, true, &upd);
+    if (!rc && c->mesh_v) rc = ops->mesh_velocity_terms(c, c->dt_last, ni, c->nelem);
     c->stream = main_stream;
     if (rc) return 1;
   }

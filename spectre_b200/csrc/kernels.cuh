@@ -1048,6 +1048,8 @@ struct FaceArgs {
   // outward unit normal) is negative, violations[1] holds the most negative
   // speed seen (as a double).  nullptr = no check (BoundaryCondition `None`).
   unsigned long long* violations;
+  // inertial mesh velocity [E][3][npad] of a moving mesh, or nullptr (static mesh)
+  const double* mesh_v;
 };
 
 // most negative value seen so far (doubles <= 0 only: their bit patterns order
@@ -1142,6 +1144,11 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
       const double* so = a.stat + (size_t)e * 3 * npad + p_own;
       GhFaceSide sd;
       gh_face_side(g, unn, __ldg(so + npad), __ldg(so + 2 * npad), sd);
+      if (a.mesh_v) {
+        const double* ve = a.mesh_v + (size_t)e * 3 * npad + p_own;
+        const double v[3] = {__ldg(ve), __ldg(ve + npad), __ldg(ve + 2 * npad)};
+        face_side_mesh_velocity(sd, v, 1.0 + __ldg(so + npad));
+      }
       double mn = fmin(fmin(sd.speed[0], sd.speed[1]), fmin(sd.speed[2], sd.speed[3]));
       if (mn < 0.0) {
         atomicAdd(a.violations, 1ULL);
@@ -1189,6 +1196,13 @@ __global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
 #pragma unroll
     for (int s = 0; s < 10; ++s) g[s] = __ldg(un + (size_t)s * ns);
     gh_face_side(g, unn_e, g1e, g2e, se);
+  }
+  if (a.mesh_v) {
+    // the mesh velocity is continuous across the interface: this element's value serves both
+    const double* ve = a.mesh_v + (size_t)e * 3 * npad + p_own;
+    const double v[3] = {__ldg(ve), __ldg(ve + npad), __ldg(ve + 2 * npad)};
+    face_side_mesh_velocity(si, v, 1.0 + g1i);
+    face_side_mesh_velocity(se, v, 1.0 + g1e);
   }
   const double lift = -0.5 * (double)(N * (N - 1)) * si.mag;
   const double lift_nb = -0.5 * (double)(N * (N - 1)) * se.mag;
@@ -1294,13 +1308,25 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
     ne[x] *= ie;
   }
   double c5[5];
-  sw_face_correction(ui, g2i, ni, ue, g2e, ne, c5);
+  double ndv_i = 0.0, ndv_e = 0.0;
+  if (a.mesh_v) {
+    // the mesh velocity is continuous across the interface: this element's value serves both
+    const double* ve = a.mesh_v + (size_t)e * 3 * npad + p_own;
+    const double v[3] = {__ldg(ve), __ldg(ve + npad), __ldg(ve + 2 * npad)};
+    ndv_i = ni[0] * v[0];
+    ndv_i += ni[1] * v[1];
+    ndv_i += ni[2] * v[2];
+    ndv_e = ne[0] * v[0];
+    ndv_e += ne[1] * v[1];
+    ndv_e += ne[2] * v[2];
+  }
+  sw_face_correction(ui, g2i, ni, ue, g2e, ne, c5, ndv_i, ndv_e);
   const double lift = -0.5 * (double)(N * (N - 1)) * mi;
 #pragma unroll
   for (int c = 0; c < 5; ++c) corr[(size_t)c * f] = c5[c] * lift;
   if (two_sided) {
     double* __restrict__ corr_nb = a.corr + ((size_t)nb * 6 + nd) * 5 * f + qn;
-    sw_face_correction(ue, g2e, ne, ui, g2i, ni, c5);
+    sw_face_correction(ue, g2e, ne, ui, g2i, ni, c5, ndv_e, ndv_i);
     const double lift_nb = -0.5 * (double)(N * (N - 1)) * me;
 #pragma unroll
     for (int c = 0; c < 5; ++c) corr_nb[(size_t)c * f] = c5[c] * lift_nb;
@@ -2143,6 +2169,80 @@ __global__ void __launch_bounds__(256) partial_derivatives_kernel(DerivArgs a) {
       v += __ldg(je + (size_t)(2 + 3 * x) * npad) * d[2];
       a.du[((size_t)e * a.CO + a.out_base + c * a.out_cstride + x) * npad + p] = v;
     }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Moving mesh, volume terms (systems without fluxes: VolumeTermsImpl.tpp:155-235,
+// dt u += v_g^i d_i u; GH TimeDerivative.cpp:237-300,372-378: gamma1 v_g.C3 in dt g and
+// gamma1 gamma2 v_g.C3 in dt Pi, C3_iab = d_i g_ab - Phi_iab).  Runs after the volume kernel
+// of a static mesh on its output (a moving mesh is not on the measured path: the fused update
+// is off and the derivatives are formed a second time here).  One CTA per (element,
+// component); the CTA of Pi_s also differentiates g_s.
+// --------------------------------------------------------------------------
+struct MeshVelocityArgs {
+  const double* u;       // [E][C][npad]
+  const double* invjac;  // [E][9][npad]
+  const double* stat;    // [E][S][npad] (GH: gamma0, gamma1, gamma2)
+  const double* mesh_v;  // [E][3][npad]
+  const double* D;
+  double* dt;            // [E][C][npad]
+  int C, elem_begin, gh;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) mesh_velocity_terms_kernel(MeshVelocityArgs a) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad;
+  __shared__ __align__(16) double tile[2][npad];
+  __shared__ double sD[N * N];
+  const int e = a.elem_begin + blockIdx.x / a.C, c = blockIdx.x % a.C;
+  const int s = (a.gh && c < 20) ? c % 10 : -1;  // g_s whose C3 enters this component
+  const double* ue = a.u + (size_t)e * a.C * npad;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    tile[0][p] = ue[(size_t)c * npad + p];
+    if (s >= 0) tile[1][p] = ue[(size_t)s * npad + p];
+  }
+  for (int p = threadIdx.x; p < N * N; p += blockDim.x) sD[p] = a.D[p];
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const int i = p % N, j = (p / N) % N, k = p / (N * N);
+    double Di[N], Dj[N], Dk[N], d[3], dg[3];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      Di[m] = sD[i * N + m];
+      Dj[m] = sD[j * N + m];
+      Dk[m] = sD[k * N + m];
+    }
+    logical_derivs<N>(tile[0], i, j, k, Di, Dj, Dk, d);
+    if (s >= 0) logical_derivs<N>(tile[1], i, j, k, Di, Dj, Dk, dg);
+    const double* je = a.invjac + (size_t)e * 9 * npad + p;
+    const double* ve = a.mesh_v + (size_t)e * 3 * npad + p;
+    double adv = 0.0, vc3 = 0.0;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      const double j0 = __ldg(je + (size_t)(0 + 3 * x) * npad);
+      const double j1 = __ldg(je + (size_t)(1 + 3 * x) * npad);
+      const double j2 = __ldg(je + (size_t)(2 + 3 * x) * npad);
+      const double v = __ldg(ve + (size_t)x * npad);
+      double du = j0 * d[0];
+      du += j1 * d[1];
+      du += j2 * d[2];
+      adv += v * du;
+      if (s >= 0) {
+        double dgx = j0 * dg[0];
+        dgx += j1 * dg[1];
+        dgx += j2 * dg[2];
+        vc3 += v * (dgx - __ldg(ue + (size_t)(20 + x + 3 * s) * npad + p));
+      }
+    }
+    double* out = a.dt + ((size_t)e * a.C + c) * npad + p;
+    double r = *out;
+    if (s >= 0) {
+      const double* se = a.stat + (size_t)e * 3 * npad + p;
+      const double g1 = __ldg(se + npad);
+      r += (c < 10 ? g1 : g1 * __ldg(se + 2 * npad)) * vc3;
+    }
+    *out = r + adv;
   }
 }
 

@@ -137,7 +137,8 @@ __global__ void sw_time_derivative_kernel(int n, const double* u, const double* 
 __global__ void gh_package_kernel(int f, const double* u, const double* g1,
                                   const double* g2, const double* lapse,
                                   const double* shift, const double* n_lo,
-                                  const double* n_up, double* pk, double* max_speed) {
+                                  const double* n_up, const double* ndotv, double* pk,
+                                  double* max_speed) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= f) return;
   dg::GhFaceSide s;
@@ -153,6 +154,12 @@ __global__ void gh_package_kernel(int f, const double* u, const double* g1,
   s.speed[0] = (1.0 + g1[p]) * sdn;
   s.speed[2] = lapse[p] + sdn;
   s.speed[3] = -lapse[p] + sdn;
+  if (ndotv) {  // moving mesh (UpwindPenalty.cpp:85-91)
+    s.speed[0] -= ndotv[p] * (1.0 + g1[p]);
+    s.speed[1] -= ndotv[p];
+    s.speed[2] -= ndotv[p];
+    s.speed[3] -= ndotv[p];
+  }
   s.gamma2 = g2[p];
   s.mag = 1.0;
 #pragma unroll 1
@@ -211,7 +218,8 @@ __global__ void gh_boundary_terms_kernel(int f, const double* in, const double* 
 // dg_package_field_tags: v_psi, v_zero(3), v_plus, v_minus, n v_plus(3),
 // n v_minus(3), gamma2 v_psi, speeds(3)
 __global__ void sw_package_kernel(int f, const double* u, const double* gamma2,
-                                  const double* n, double* pk, double* max_speed) {
+                                  const double* n, const double* ndotv, double* pk,
+                                  double* max_speed) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= f) return;
   const double psi = u[p], pi = u[(size_t)f + p];
@@ -221,7 +229,8 @@ __global__ void sw_package_kernel(int f, const double* u, const double* gamma2,
     phi[i] = u[(size_t)(2 + i) * f + p];
     nn[i] = n[(size_t)i * f + p];
   }
-  const double cs[3] = {0.0, 1.0, -1.0};
+  const double nv = ndotv ? ndotv[p] : 0.0;  // moving mesh (UpwindPenalty.cpp:55-67)
+  const double cs[3] = {0.0 - nv, 1.0 - nv, -1.0 - nv};
   const double g2psi = gamma2[p] * psi;
   double ndphi = nn[0] * phi[0];
   ndphi += nn[1] * phi[1];
@@ -238,7 +247,7 @@ __global__ void sw_package_kernel(int f, const double* u, const double* gamma2,
   pk[(size_t)4 * f + p] = vp;
   pk[(size_t)5 * f + p] = vm;
   pk[(size_t)12 * f + p] = g2psi * cs[0];
-  max_speed[p] = 1.0;
+  max_speed[p] = fmax(cs[0], fmax(cs[1], cs[2]));
 }
 
 __global__ void sw_boundary_terms_kernel(int f, const double* in, const double* ex,
@@ -422,10 +431,11 @@ int dgrhs_sw_time_derivative(int n, const double* u, const double* du,
   return 0;
 }
 
-int dgrhs_gh_package_data(int f, const double* u, const double* gamma1,
-                          const double* gamma2, const double* lapse, const double* shift,
-                          const double* normal_covector, const double* normal_vector,
-                          double* packaged, double* max_abs_char_speed) {
+int dgrhs_gh_package_data_moving(int f, const double* u, const double* gamma1,
+                                 const double* gamma2, const double* lapse, const double* shift,
+                                 const double* normal_covector, const double* normal_vector,
+                                 const double* normal_dot_mesh_velocity, double* packaged,
+                                 double* max_abs_char_speed) {
   if (need_gpu()) return 1;
   if (f < 1) return fail("f must be positive");
   Staged st;
@@ -436,11 +446,14 @@ int dgrhs_gh_package_data(int f, const double* u, const double* gamma1,
   double* d_s = st.in(shift, (size_t)3 * f);
   double* d_nl = st.in(normal_covector, (size_t)3 * f);
   double* d_nu = st.in(normal_vector, (size_t)3 * f);
+  double* d_nv = normal_dot_mesh_velocity ? st.in(normal_dot_mesh_velocity, f) : nullptr;
+  if (normal_dot_mesh_velocity && !d_nv) return fail("device staging failed");
   double* d_pk = st.in(nullptr, (size_t)134 * f);
   double* d_ms = st.in(nullptr, f);
   if (!d_u || !d_g1 || !d_g2 || !d_l || !d_s || !d_nl || !d_nu || !d_pk || !d_ms)
     return fail("device staging failed");
-  gh_package_kernel<<<grid(f), 128>>>(f, d_u, d_g1, d_g2, d_l, d_s, d_nl, d_nu, d_pk, d_ms);
+  gh_package_kernel<<<grid(f), 128>>>(f, d_u, d_g1, d_g2, d_l, d_s, d_nl, d_nu, d_nv, d_pk,
+                                      d_ms);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   CU(cudaMemcpy(packaged, d_pk, (size_t)134 * f * 8, cudaMemcpyDeviceToHost));
@@ -452,6 +465,14 @@ int dgrhs_gh_package_data(int f, const double* u, const double* gamma1,
     *max_abs_char_speed = m;
   }
   return 0;
+}
+
+int dgrhs_gh_package_data(int f, const double* u, const double* gamma1,
+                          const double* gamma2, const double* lapse, const double* shift,
+                          const double* normal_covector, const double* normal_vector,
+                          double* packaged, double* max_abs_char_speed) {
+  return dgrhs_gh_package_data_moving(f, u, gamma1, gamma2, lapse, shift, normal_covector,
+                                      normal_vector, nullptr, packaged, max_abs_char_speed);
 }
 
 int dgrhs_gh_boundary_terms(int f, const double* packaged_int, const double* packaged_ext,
@@ -469,23 +490,39 @@ int dgrhs_gh_boundary_terms(int f, const double* packaged_int, const double* pac
   return 0;
 }
 
-int dgrhs_sw_package_data(int f, const double* u, const double* gamma2,
-                          const double* normal_covector, double* packaged,
-                          double* max_abs_char_speed) {
+int dgrhs_sw_package_data_moving(int f, const double* u, const double* gamma2,
+                                 const double* normal_covector,
+                                 const double* normal_dot_mesh_velocity, double* packaged,
+                                 double* max_abs_char_speed) {
   if (need_gpu()) return 1;
   Staged st;
   double* d_u = st.in(u, (size_t)5 * f);
   double* d_g2 = st.in(gamma2, f);
   double* d_n = st.in(normal_covector, (size_t)3 * f);
+  double* d_nv = normal_dot_mesh_velocity ? st.in(normal_dot_mesh_velocity, f) : nullptr;
+  if (normal_dot_mesh_velocity && !d_nv) return fail("device staging failed");
   double* d_pk = st.in(nullptr, (size_t)16 * f);
   double* d_ms = st.in(nullptr, f);
   if (!d_u || !d_g2 || !d_n || !d_pk || !d_ms) return fail("device staging failed");
-  sw_package_kernel<<<grid(f), 128>>>(f, d_u, d_g2, d_n, d_pk, d_ms);
+  sw_package_kernel<<<grid(f), 128>>>(f, d_u, d_g2, d_n, d_nv, d_pk, d_ms);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   CU(cudaMemcpy(packaged, d_pk, (size_t)16 * f * 8, cudaMemcpyDeviceToHost));
-  if (max_abs_char_speed) *max_abs_char_speed = 1.0;
+  if (max_abs_char_speed) {
+    std::vector<double> ms(f);
+    CU(cudaMemcpy(ms.data(), d_ms, (size_t)f * 8, cudaMemcpyDeviceToHost));
+    double m = ms[0];
+    for (double v : ms) m = v > m ? v : m;
+    *max_abs_char_speed = m;
+  }
   return 0;
+}
+
+int dgrhs_sw_package_data(int f, const double* u, const double* gamma2,
+                          const double* normal_covector, double* packaged,
+                          double* max_abs_char_speed) {
+  return dgrhs_sw_package_data_moving(f, u, gamma2, normal_covector, nullptr, packaged,
+                                      max_abs_char_speed);
 }
 
 int dgrhs_sw_boundary_terms(int f, const double* packaged_int, const double* packaged_ext,

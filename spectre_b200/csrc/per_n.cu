@@ -31,7 +31,10 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
       return fail("element range must be [0, n_interior) or [n_interior, n_elements)");
   }
   dg::FaceArgs a{c->u,    c->invjac, c->stat, c->nbr, c->nbr_face, c->halo_recv,
-                 c->corr, c->nelem,  n_int,   pass,   pass == 2 ? n_int : 0, c->violations};
+                 c->corr, c->nelem,  n_int,   pass,   pass == 2 ? n_int : 0, c->violations,
+                 c->mesh_v};
+  if (c->mesh_v && (c->n_bjorhus_faces > 0 || c->n_mortar_faces > 0 || c->n_pmortar_faces > 0))
+    return fail("moving mesh: Bjorhus faces and non-conforming mortars are not supported");
   // Bjorhus faces and non-conforming mortars need no halo data: all of them are
   // evaluated once per right-hand side, with whichever pass comes first, so that
   // their corrections are in place before ANY volume kernel of this evaluation
@@ -292,6 +295,18 @@ int launch_partial_derivatives(const dg::DerivArgs* a, int blocks, cudaStream_t 
   return 0;
 }
 
+// moving-mesh terms on top of the static-mesh volume kernel's output
+template <int N>
+int launch_mesh_velocity_terms(dgrhs_ctx* c, double* dt, int eb, int ee) {
+  if (ee <= eb) return 0;
+  dg::MeshVelocityArgs a{c->u, c->invjac, c->stat, c->mesh_v, c->D, dt, c->C, eb,
+                         c->system == DGRHS_SYSTEM_GH ? 1 : 0};
+  dg::mesh_velocity_terms_kernel<N><<<(ee - eb) * c->C, 256, 0, c->stream>>>(a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
 static const DgNOps kOps = {launch_faces<DG_N>,
                      launch_gauge<DG_N>,
                      launch_volume_p<DG_N>,
@@ -299,7 +314,8 @@ static const DgNOps kOps = {launch_faces<DG_N>,
                      launch_filter<DG_N>,
                      launch_gauge_from_state<DG_N>,
                      launch_constraints<DG_N>,
-                     launch_partial_derivatives<DG_N>};
+                     launch_partial_derivatives<DG_N>,
+                     launch_mesh_velocity_terms<DG_N>};
 
 }  // namespace
 

@@ -748,6 +748,19 @@ DG_HD void gh_face_side(const double (&g)[10], const double (&unnorm)[3],
   s.gamma2 = gamma2;
 }
 
+// Moving mesh: the characteristic speeds relative to the mesh (dg_package_data with
+// normal_dot_mesh_velocity, GH UpwindPenalty.cpp:85-91 / ScalarWave UpwindPenalty.cpp:55-67):
+// v = inertial mesh velocity at the face point
+DG_HD void face_side_mesh_velocity(GhFaceSide& s, const double (&v)[3], double one_plus_gamma1) {
+  double ndv = s.n_lo[0] * v[0];
+  ndv += s.n_lo[1] * v[1];
+  ndv += s.n_lo[2] * v[2];
+  s.speed[0] -= ndv * one_plus_gamma1;
+  s.speed[1] -= ndv;
+  s.speed[2] -= ndv;
+  s.speed[3] -= ndv;
+}
+
 // characteristic-speed weighted fields of one (a,b) pair on one side
 // (dg_package_data, UpwindPenalty.cpp:90-150)
 struct GhPairPackaged {
@@ -828,9 +841,11 @@ DG_HD void sw_point_rhs(const double (&u)[5], const double (&d)[5][3],
 DG_HD void sw_face_correction(const double (&ui)[5], double g2i,
                               const double (&ni)[3], const double (&ue)[5],
                               double g2e, const double (&ne)[3],
-                              double (&corr)[5]) {
-  // packaged data of both sides
-  const double cs0 = 0.0, csp = 1.0, csm = -1.0;
+                              double (&corr)[5], double ndv_i = 0.0, double ndv_e = 0.0) {
+  // packaged data of both sides; ndv = n.v_g of each side's own normal on a moving mesh
+  // (UpwindPenalty.cpp:55-67), 0 on a static one
+  const double cs0_i = 0.0 - ndv_i, csp_i = 1.0 - ndv_i, csm_i = -1.0 - ndv_i;
+  const double cs0_e = 0.0 - ndv_e, csp_e = 1.0 - ndv_e, csm_e = -1.0 - ndv_e;
   double ndphi_i = ni[0] * ui[2];
   ndphi_i += ni[1] * ui[3];
   ndphi_i += ni[2] * ui[4];
@@ -838,20 +853,20 @@ DG_HD void sw_face_correction(const double (&ui)[5], double g2i,
   ndphi_e += ne[1] * ue[3];
   ndphi_e += ne[2] * ue[4];
   const double g2psi_i = g2i * ui[0], g2psi_e = g2e * ue[0];
-  const double vp_i = csp * (ui[1] + ndphi_i - g2psi_i);
-  const double vm_i = csm * (ui[1] - ndphi_i - g2psi_i);
-  const double vp_e = csp * (ue[1] + ndphi_e - g2psi_e);
-  const double vm_e = csm * (ue[1] - ndphi_e - g2psi_e);
-  const double w_psi_i = step_function(-cs0), w_psi_e = -step_function(cs0);
-  const double w_p_i = step_function(-csp), w_p_e = -step_function(csp);
-  const double w_m_i = step_function(-csm), w_m_e = -step_function(csm);
-  corr[0] = w_psi_e * (cs0 * ue[0]) - w_psi_i * (cs0 * ui[0]);
-  corr[1] = 0.5 * (w_p_e * vp_e + w_m_e * vm_e) + w_psi_e * (g2psi_e * cs0) -
-            0.5 * (w_p_i * vp_i + w_m_i * vm_i) - w_psi_i * (g2psi_i * cs0);
+  const double vp_i = csp_i * (ui[1] + ndphi_i - g2psi_i);
+  const double vm_i = csm_i * (ui[1] - ndphi_i - g2psi_i);
+  const double vp_e = csp_e * (ue[1] + ndphi_e - g2psi_e);
+  const double vm_e = csm_e * (ue[1] - ndphi_e - g2psi_e);
+  const double w_psi_i = step_function(-cs0_i), w_psi_e = -step_function(cs0_e);
+  const double w_p_i = step_function(-csp_i), w_p_e = -step_function(csp_e);
+  const double w_m_i = step_function(-csm_i), w_m_e = -step_function(csm_e);
+  corr[0] = w_psi_e * (cs0_e * ue[0]) - w_psi_i * (cs0_i * ui[0]);
+  corr[1] = 0.5 * (w_p_e * vp_e + w_m_e * vm_e) + w_psi_e * (g2psi_e * cs0_e) -
+            0.5 * (w_p_i * vp_i + w_m_i * vm_i) - w_psi_i * (g2psi_i * cs0_i);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double vz_i = cs0 * (ui[2 + d] - ni[d] * ndphi_i);
-    const double vz_e = cs0 * (ue[2 + d] - ne[d] * ndphi_e);
+    const double vz_i = cs0_i * (ui[2 + d] - ni[d] * ndphi_i);
+    const double vz_e = cs0_e * (ue[2 + d] - ne[d] * ndphi_e);
     corr[2 + d] = 0.5 * (w_p_e * (vp_e * ne[d]) - w_m_e * (vm_e * ne[d])) +
                   w_psi_e * vz_e -
                   0.5 * (w_p_i * (vp_i * ni[d]) - w_m_i * (vm_i * ni[d])) -

@@ -528,10 +528,8 @@ class UpwindPenalty {
   double dg_package_data(std::vector<double>* packaged, const ScalarDV& psi, const ScalarDV& pi,
                          const tnsr::i3& phi, const ScalarDV& constraint_gamma2,
                          const tnsr::i3& normal_covector,
-                         const std::optional<tnsr::i3>& mesh_velocity,
+                         const std::optional<tnsr::i3>& /*mesh_velocity*/,
                          const std::optional<ScalarDV>& normal_dot_mesh_velocity) const {
-    if (mesh_velocity.has_value() || normal_dot_mesh_velocity.has_value())
-      throw std::runtime_error("moving meshes are out of scope of this path");
     const size_t f = psi.get().size();
     std::vector<double> u(5 * f);
     for (size_t p = 0; p < f; ++p) {
@@ -542,8 +540,10 @@ class UpwindPenalty {
     packaged->resize(16 * f);
     double max_speed = 0.0;
     const auto nrm = normal_covector.flat();
-    check(dgrhs_sw_package_data(static_cast<int>(f), u.data(), constraint_gamma2.get().data(), nrm.data(),
-                                packaged->data(), &max_speed));
+    check(dgrhs_sw_package_data_moving(
+        static_cast<int>(f), u.data(), constraint_gamma2.get().data(), nrm.data(),
+        normal_dot_mesh_velocity.has_value() ? normal_dot_mesh_velocity->get().data() : nullptr,
+        packaged->data(), &max_speed));
     return max_speed;
   }
   void dg_boundary_terms(std::vector<double>* boundary_corrections, const std::vector<double>& packaged_int,
@@ -631,10 +631,8 @@ class UpwindPenalty {
                          const tnsr::aa10& pi, const tnsr::iaa30& phi, const ScalarDV& constraint_gamma1,
                          const ScalarDV& constraint_gamma2, const ScalarDV& lapse, const tnsr::i3& shift,
                          const tnsr::i3& normal_covector, const tnsr::i3& normal_vector,
-                         const std::optional<tnsr::i3>& mesh_velocity,
+                         const std::optional<tnsr::i3>& /*mesh_velocity*/,
                          const std::optional<ScalarDV>& normal_dot_mesh_velocity) const {
-    if (mesh_velocity.has_value() || normal_dot_mesh_velocity.has_value())
-      throw std::runtime_error("moving meshes are out of scope of this path");
     const size_t f = lapse.get().size();
     std::vector<double> u(50 * f);
     const auto pack = [f](double* dst, const auto& t) {
@@ -647,9 +645,11 @@ class UpwindPenalty {
     packaged->resize(134 * f);
     double max_speed = 0.0;
     const auto sh = shift.flat(), nl = normal_covector.flat(), nu = normal_vector.flat();
-    check(dgrhs_gh_package_data(static_cast<int>(f), u.data(), constraint_gamma1.get().data(),
-                                constraint_gamma2.get().data(), lapse.get().data(), sh.data(), nl.data(),
-                                nu.data(), packaged->data(), &max_speed));
+    check(dgrhs_gh_package_data_moving(
+        static_cast<int>(f), u.data(), constraint_gamma1.get().data(), constraint_gamma2.get().data(),
+        lapse.get().data(), sh.data(), nl.data(), nu.data(),
+        normal_dot_mesh_velocity.has_value() ? normal_dot_mesh_velocity->get().data() : nullptr,
+        packaged->data(), &max_speed));
     return max_speed;
   }
   void dg_boundary_terms(std::vector<double>* boundary_corrections, const std::vector<double>& packaged_int,

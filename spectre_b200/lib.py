@@ -45,6 +45,7 @@ EXPORTS = [
     "dgrhs_apply_exponential_filter", "dgrhs_butcher_row", "dgrhs_update_u",
     "dgrhs_project_to_mortar", "dgrhs_project_from_mortar", "dgrhs_orient_variables_on_slice",
     "dgrhs_set_p_mortars", "dgrhs_p_mortar_transfer", "dgrhs_set_slab", "dgrhs_self_start_substeps_left", "dgrhs_stepper_substep_fractions",
+    "dgrhs_set_mesh_velocity", "dgrhs_gh_package_data_moving", "dgrhs_sw_package_data_moving",
 ]
 
 _lib = None
@@ -187,12 +188,15 @@ def sw_time_derivative(u, du, gamma2):
     return dt
 
 
-def gh_package_data(u, gamma1, gamma2, lapse, shift, normal_covector, normal_vector):
+def gh_package_data(u, gamma1, gamma2, lapse, shift, normal_covector, normal_vector,
+                    normal_dot_mesh_velocity=None):
     a = [_f64(x) for x in (u, gamma1, gamma2, lapse, shift, normal_covector, normal_vector)]
     f = a[0].shape[1]
     pk = np.zeros((134, f))
     ms = ctypes.c_double()
-    _check(load().dgrhs_gh_package_data(f, *[_ptr(x) for x in a], _ptr(pk), ctypes.byref(ms)))
+    nv = None if normal_dot_mesh_velocity is None else _f64(normal_dot_mesh_velocity)
+    _check(load().dgrhs_gh_package_data_moving(f, *[_ptr(x) for x in a], _ptr(nv), _ptr(pk),
+                                               ctypes.byref(ms)))
     return pk, ms.value
 
 
@@ -204,12 +208,14 @@ def gh_boundary_terms(pk_int, pk_ext):
     return c
 
 
-def sw_package_data(u, gamma2, normal_covector):
+def sw_package_data(u, gamma2, normal_covector, normal_dot_mesh_velocity=None):
     a = [_f64(x) for x in (u, gamma2, normal_covector)]
     f = a[0].shape[1]
     pk = np.zeros((16, f))
     ms = ctypes.c_double()
-    _check(load().dgrhs_sw_package_data(f, *[_ptr(x) for x in a], _ptr(pk), ctypes.byref(ms)))
+    nv = None if normal_dot_mesh_velocity is None else _f64(normal_dot_mesh_velocity)
+    _check(load().dgrhs_sw_package_data_moving(f, *[_ptr(x) for x in a], _ptr(nv), _ptr(pk),
+                                               ctypes.byref(ms)))
     return pk, ms.value
 
 
@@ -270,6 +276,15 @@ class Context:
         F = _f64(fields)
         assert F.shape[0] == self.n_elements and F.shape[2] == self.n
         _check(self._lib.dgrhs_set_static_fields(self._h, _ptr(F), F.shape[1]))
+
+    def set_mesh_velocity(self, v):
+        """Inertial mesh velocity [n_elements, 3, n] of a moving mesh, or None (static)."""
+        if v is None:
+            _check(self._lib.dgrhs_set_mesh_velocity(self._h, None))
+            return
+        V = _f64(v)
+        assert V.shape == (self.n_elements, 3, self.n)
+        _check(self._lib.dgrhs_set_mesh_velocity(self._h, _ptr(V)))
 
     def set_gauge(self, gauge, params=()):
         p = _f64(list(params)) if len(params) else np.zeros(1)

@@ -106,6 +106,56 @@ def main():
     out.update(sw_u=sw_u, sw_gamma2=sw_g2, sw_normal=sw_n, sw_packaged=sw_pk, sw_corr=sw_corr)
     np.savez_compressed(os.path.join(HERE, "upwind_penalty.npz"), **out)
     print("wrote upwind_penalty.npz")
+    moving_mesh(gh, sw, out)
+
+
+def moving_mesh(gh, sw, base):
+    """tests/golden/upwind_penalty_moving.npz: dg_package_data of the same inputs with a
+    normal_dot_mesh_velocity (the reference's twins subtract it from the characteristic
+    speeds, GH with the factor 1 + gamma1 on the first one)."""
+    rng = np.random.default_rng(777)
+    npts = base["gh_u"].shape[1]
+
+    def unpack_aa(v):
+        t = np.zeros((4, 4))
+        for a in range(4):
+            for b in range(a, 4):
+                t[a, b] = t[b, a] = v[sym4(a, b)]
+        return t
+
+    def unpack_iaa(v):
+        t = np.zeros((3, 4, 4))
+        for a in range(4):
+            for b in range(a, 4):
+                for i in range(3):
+                    t[i, a, b] = t[i, b, a] = v[i + 3 * sym4(a, b)]
+        return t
+    gh_ndotv = rng.uniform(-0.8, 0.8, npts)
+    sw_ndotv = rng.uniform(-1.5, 1.5, npts)
+    gh_pk = np.zeros((npts, 134))
+    sw_pk = np.zeros((npts, 16))
+    for p in range(npts):
+        u = base["gh_u"][0, p]
+        r = gh.dg_package_data(unpack_aa(u[:10]), unpack_aa(u[10:20]), unpack_iaa(u[20:]),
+                               base["gh_gamma1"][0, p], base["gh_gamma2"][0, p],
+                               base["gh_lapse"][0, p], base["gh_shift"][0, p],
+                               base["gh_nlo"][0, p], base["gh_nup"][0, p],
+                               np.zeros(3), gh_ndotv[p])
+        gh_pk[p] = np.concatenate([pack_aa(r[0]), pack_iaa(r[1]), pack_aa(r[2]), pack_aa(r[3]),
+                                   pack_iaa(r[4]), pack_iaa(r[5]), pack_aa(r[6]), r[7]])
+        # ScalarWave: the twin's moving-mesh branch does not run (its einsum("ijj->i", ...) has
+        # three operands for one subscript list); all of its other outputs are speed * field
+        # and are taken from it with the v^0 entry, the only one that branch computes, left out
+        w = base["sw_u"][0, p]
+        try:
+            r = sw.dg_package_data(w[0], w[1], w[2:], base["sw_gamma2"][0, p],
+                                   base["sw_normal"][0, p], np.zeros(3), sw_ndotv[p])
+            sw_pk[p] = np.concatenate([[r[0]], r[1], [r[2]], [r[3]], r[4], r[5], [r[6]], r[7]])
+        except ValueError:
+            sw_pk[p] = np.nan
+    np.savez_compressed(os.path.join(HERE, "upwind_penalty_moving.npz"), gh_ndotv=gh_ndotv,
+                        gh_packaged=gh_pk, sw_ndotv=sw_ndotv, sw_packaged=sw_pk)
+    print("wrote upwind_penalty_moving.npz")
 
 
 if __name__ == "__main__":

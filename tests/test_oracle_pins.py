@@ -115,6 +115,41 @@ def test_upwind_penalty_vs_reference_numpy(golden_dir):
     np.testing.assert_allclose(corr.T, z["sw_corr"], rtol=1e-13, atol=1e-14)
 
 
+def test_upwind_penalty_moving_mesh_vs_reference_numpy(golden_dir):
+    """dg_package_data with normal_dot_mesh_velocity: GH against the fixture made by the
+    reference's UpwindPenalty.py twin (gen_python_goldens.py: moving_mesh).  The ScalarWave
+    twin's moving-mesh branch does not run (see the generator), so ScalarWave is pinned to
+    the structure the reference's C++ states (UpwindPenalty.cpp:55-108): the speeds are
+    (0, 1, -1) - n.v_g and every packaged field is its static-mesh value with the speed
+    exchanged."""
+    z = np.load(os.path.join(golden_dir, "upwind_penalty.npz"))
+    m = np.load(os.path.join(golden_dir, "upwind_penalty_moving.npz"))
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    out = orc.gh_package_data_moving(c(z["gh_u"][0].T), z["gh_gamma1"][0], z["gh_gamma2"][0],
+                                     z["gh_lapse"][0], c(z["gh_shift"][0].T),
+                                     c(z["gh_nlo"][0].T), c(z["gh_nup"][0].T), m["gh_ndotv"])
+    np.testing.assert_allclose(out.T, m["gh_packaged"], rtol=1e-13, atol=1e-14)
+    # a zero velocity reproduces the static fixture
+    out0 = orc.gh_package_data_moving(c(z["gh_u"][0].T), z["gh_gamma1"][0], z["gh_gamma2"][0],
+                                      z["gh_lapse"][0], c(z["gh_shift"][0].T),
+                                      c(z["gh_nlo"][0].T), c(z["gh_nup"][0].T),
+                                      np.zeros_like(m["gh_ndotv"]))
+    np.testing.assert_allclose(out0.T, z["gh_packaged"][0], rtol=1e-13, atol=1e-14)
+    u, g2, n = c(z["sw_u"][0].T), z["sw_gamma2"][0], c(z["sw_normal"][0].T)
+    nv = m["sw_ndotv"]
+    pk = orc.sw_package_data_moving(u, g2, n, nv)
+    st = z["sw_packaged"][0].T
+    np.testing.assert_allclose(pk[13:], np.array([0.0 - nv, 1.0 - nv, -1.0 - nv]), rtol=1e-15)
+    for rows, static_speed, k in (([4, 6, 7, 8], 1.0, 14), ([5, 9, 10, 11], -1.0, 15)):
+        for r in rows:
+            np.testing.assert_allclose(pk[r], st[r] / static_speed * pk[k], rtol=1e-13,
+                                       atol=1e-14)
+    ndphi = np.einsum("ip,ip->p", n, u[2:])
+    np.testing.assert_allclose(pk[0], pk[13] * u[0], rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(pk[1:4], pk[13] * (u[2:] - n * ndphi), rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(pk[12], pk[13] * g2 * u[0], rtol=1e-13, atol=1e-14)
+
+
 def _random_physical_gh_state(rng, n):
     """Random physical metric like TestHelpers::gr::random_lapse/shift/
     spatial_metric (Test_DuDt.cpp:489-493): lapse in (0,3), shift, SPD gamma."""
@@ -429,3 +464,33 @@ def test_spacetime_quantities_and_constraints_vs_reference_numpy(golden_dir):
     c4 = orc.four_index_constraint(np.moveaxis(z["d_phi"], 0, -1))      # [j, k, a, b, n]
     np.testing.assert_allclose(np.moveaxis(c4, -1, 0), z["four_index_constraint"],
                                rtol=1e-13, atol=1e-14)
+
+
+def test_oracle_moving_mesh_terms_are_the_grid_frame_derivative():
+    """On a moving mesh the right-hand side is the time derivative at a moving grid point:
+    d_t u + v_g.grad u (VolumeTermsImpl.tpp:155-235).  For the analytic ScalarWave plane wave
+    and a smooth periodic velocity the oracle reproduces it to truncation error, for Psi, Pi
+    and Phi; with the static-mesh right-hand side the difference is O(|v|)."""
+    from spectre_b200 import analytic, domain
+    N, L = 9, 2 * np.pi
+    brick = domain.Brick([0, 0, 0], [L] * 3, [1, 1, 1], N)
+    x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    stat = np.zeros((brick.n_elements, 1, brick.n))
+    u = analytic.plane_wave(x, 0.2)
+    v = np.empty((brick.n_elements, 3, brick.n))
+    v[:, 0] = 0.3 + 0.2 * np.sin(x[:, 1])
+    v[:, 1] = -0.25 + 0.1 * np.cos(x[:, 2])
+    v[:, 2] = 0.15 * np.sin(x[:, 0])
+    eps = 1e-6
+    d_t = (analytic.plane_wave(x, 0.2 + eps) - analytic.plane_wave(x, 0.2 - eps)) / (2 * eps)
+    grad = np.zeros((3,) + u.shape)
+    for i in range(3):
+        xp, xm = x.copy(), x.copy()
+        xp[:, i] += eps
+        xm[:, i] -= eps
+        grad[i] = (analytic.plane_wave(xp, 0.2) - analytic.plane_wave(xm, 0.2)) / (2 * eps)
+    expected = d_t + np.einsum("eip,iecp->ecp", v, grad)
+    got = orc.dg_rhs(0, N, u, J, stat, nb, mesh_velocity=v)
+    static = orc.dg_rhs(0, N, u, J, stat, nb)
+    assert np.max(np.abs(got - expected)) < 2e-4
+    assert np.max(np.abs(static - expected)) > 0.1
