@@ -1,0 +1,151 @@
+"""Local time stepping, CPU side: the oracle's Adams LTS coefficients against the known
+answers of the reference's tests/Unit/Time/TimeSteppers/Test_AdamsLts.cpp:416-760 (explicit
+schemes), and properties of the oracle's LTS evolution (equal steps = the GTS oracle,
+conservation of the coupling, convergence with mixed steps)."""
+from fractions import Fraction as Fr
+
+import numpy as np
+import pytest
+
+from oracle import lts
+from oracle import oracle as orc
+
+
+def _check(got, expected):
+    assert set(got) == set((Fr(a), Fr(b)) for a, b in expected), (got, expected)
+    for (a, b), v in expected.items():
+        assert got[(Fr(a), Fr(b))] == pytest.approx(v, rel=1e-13, abs=1e-14)
+
+
+AB3 = [5.0 / 12.0, -4.0 / 3.0, 23.0 / 12.0]
+
+
+def test_gts_orders_1_and_3():
+    # Test_AdamsLts.cpp:431-467
+    _check(lts.lts_coefficients([0], [0], 0, 1, 1), {(0, 0): 1.0})
+    _check(lts.lts_coefficients([0, 1, 2], [0, 1, 2], 2, 3, 3),
+           {(0, 0): AB3[0], (1, 1): AB3[1], (2, 2): AB3[2]})
+
+
+def test_single_side_order_3():
+    # Test_AdamsLts.cpp:505-527: the remote side is first order (one value)
+    _check(lts.lts_coefficients([0, 1, 2], [0], 2, 3, 3, 1, 3),
+           {(0, 0): AB3[0], (1, 0): AB3[1], (2, 0): AB3[2]})
+
+
+def test_two_to_one_order_3():
+    # Test_AdamsLts.cpp:556-596
+    large, small = [-8, -4, 0], [-4, -2, 0, 2]
+    _check(lts.lts_coefficients(large, small, 0, 4, 3), {
+        (0, 2): 115.0 / 16.0, (0, 0): 7.0 / 6.0, (0, -2): -11.0 / 16.0, (-4, 2): -115.0 / 24.0,
+        (-4, -2): -11.0 / 8.0, (-4, -4): 5.0 / 6.0, (-8, 2): 23.0 / 16.0, (-8, -2): 11.0 / 48.0})
+    _check(lts.lts_coefficients(small, large, 0, 2, 3), {
+        (0, 0): 23.0 / 6.0, (-2, 0): -1.0, (-2, -4): -2.0, (-4, -4): 5.0 / 6.0,
+        (-2, -8): 1.0 / 3.0})
+    _check(lts.lts_coefficients(small, large, 2, 4, 3), {
+        (2, 0): 115.0 / 16.0, (0, 0): -8.0 / 3.0, (-2, 0): 5.0 / 16.0, (2, -4): -115.0 / 24.0,
+        (-2, -4): 5.0 / 8.0, (2, -8): 23.0 / 16.0, (-2, -8): -5.0 / 48.0})
+
+
+def test_lts_to_gts_order_2():
+    # Test_AdamsLts.cpp:598-613
+    _check(lts.lts_coefficients([-2, 0], [-1, 0], 0, 1, 2),
+           {(0, 0): 3.0 / 2.0, (0, -1): -1.0 / 4.0, (-2, -1): -1.0 / 4.0})
+
+
+def test_three_to_one_order_2():
+    # Test_AdamsLts.cpp:615-657
+    large, small = [-3, 0], [-1, 0, 1, 2]
+    _check(lts.lts_coefficients(large, small, 0, 3, 2), {
+        (-3, -1): -1.0 / 6.0, (-3, 1): -1.0 / 3.0, (-3, 2): -1.0, (0, -1): -1.0 / 3.0,
+        (0, 0): 1.0, (0, 1): 4.0 / 3.0, (0, 2): 5.0 / 2.0})
+    _check(lts.lts_coefficients(small, large, 0, 1, 2),
+           {(-1, -3): -1.0 / 6.0, (-1, 0): -1.0 / 3.0, (0, 0): 3.0 / 2.0})
+    _check(lts.lts_coefficients(small, large, 1, 2, 2),
+           {(0, 0): -1.0 / 2.0, (1, -3): -1.0 / 2.0, (1, 0): 2.0})
+    _check(lts.lts_coefficients(small, large, 2, 3, 2),
+           {(1, -3): 1.0 / 6.0, (1, 0): -2.0 / 3.0, (2, -3): -1.0, (2, 0): 5.0 / 2.0})
+
+
+def test_unaligned_order_2():
+    # Test_AdamsLts.cpp:685-700 (first case)
+    _check(lts.lts_coefficients([1, 3, 4], [2, 3, 5], 3, 4, 2),
+           {(1, 2): -1.0 / 4.0, (3, 2): -1.0 / 4.0, (3, 3): 3.0 / 2.0})
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_coefficients_are_conservative_and_consistent(order):
+    """What the reference's LTS design rests on (AdamsLts.hpp:90-125): over a common
+    interval the two sides integrate the same coupling terms, and for a coupling that does
+    not depend on its arguments the coefficients sum to the step."""
+    k = order
+    coarse = [4 * i for i in range(-(k - 1), 1)]
+    fine_all = [2 * i for i in range(-2 * (k - 1), 2)]
+    big = lts.lts_coefficients(coarse, fine_all, 0, 4, k, exact=True)
+    s1 = lts.lts_coefficients([t for t in fine_all if t <= 0], coarse, 0, 2, k, exact=True)
+    s2 = lts.lts_coefficients(fine_all, coarse, 2, 4, k, exact=True)
+    assert sum(big.values()) == 4
+    assert sum(s1.values()) == 2 and sum(s2.values()) == 2
+    both = {}
+    for part in (s1, s2):
+        for (a, b), v in part.items():
+            both[(b, a)] = both.get((b, a), 0) + v
+    both = {key: v for key, v in both.items() if v != 0}
+    assert both == {key: v for key, v in big.items() if v != 0}
+
+
+def _sw_problem(N, levels_of):
+    from spectre_b200 import analytic, domain
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    stat = np.zeros((brick.n_elements, 1, brick.n))
+    levels = np.array([levels_of(x[e].mean(axis=1)) for e in range(brick.n_elements)])
+    return analytic, x, J, nb, stat, levels
+
+
+def test_equal_levels_reproduce_the_gts_oracle():
+    """all elements on one level: every boundary is `lts_coefficients_for_gts`
+    (AdamsLts.cpp:307-327) and the evolution equals the GTS Adams-Bashforth one up to the
+    order of the additions (volume and boundary parts are added separately)"""
+    N, dt, order = 4, 2e-3, 3
+    analytic, x, J, nb, stat, levels = _sw_problem(N, lambda c: 0)
+    u0 = analytic.plane_wave(x, 0.0)
+    ev = lts.LtsEvolution(0, N, J, stat, nb, levels, order, 0.0, dt, u0,
+                          lambda j: analytic.plane_wave(x, -j * dt))
+    ev.take_coarse_steps(4)
+    # the same history start for the GTS evolution
+    hist = [(orc.dg_rhs(0, N, analytic.plane_wave(x, -j * dt), J, stat, nb)) for j in (2, 1)]
+    u = u0.copy()
+    for _ in range(4):
+        hist.append(orc.dg_rhs(0, N, u, J, stat, nb))
+        c = orc._AB_CONST[3]
+        u = u + dt * (c[0] * hist[-3] + c[1] * hist[-2] + c[2] * hist[-1])
+    assert np.max(np.abs(ev.u - u)) < 1e-13 * np.max(np.abs(u))
+
+
+def test_mixed_levels_converge_to_the_analytic_solution():
+    """half of the brick takes two (four) steps per coarse step; the error of the LTS
+    evolution is that of the spatial discretisation, as for the GTS evolution with the fine
+    step (TimeStepperTestUtils check_convergence_order's role for the coupled system)"""
+    N, dt, order = 6, 8e-3, 3
+    analytic, x, J, nb, stat, levels = _sw_problem(N, lambda c: int(c[0] > np.pi) + int(c[1] > np.pi))
+    assert sorted(set(levels)) == [0, 1, 2]
+    u0 = analytic.plane_wave(x, 0.0)
+    stride = 2 ** (levels.max() - levels)
+    tick = dt / 4
+
+    def past(j):
+        return np.stack([analytic.plane_wave(x[e], -j * stride[e] * tick)
+                         for e in range(len(levels))])
+    ev = lts.LtsEvolution(0, N, J, stat, nb, levels, order, 0.0, dt, u0, past)
+    ev.take_coarse_steps(5)
+    exact = analytic.plane_wave(x, 5 * dt)
+    err = np.max(np.abs(ev.u - exact))
+    # GTS with the fine step everywhere
+    ev_f = lts.LtsEvolution(0, N, J, stat, nb, 0 * levels, order, 0.0, tick, u0,
+                            lambda j: analytic.plane_wave(x, -j * tick))
+    ev_f.take_coarse_steps(20)
+    err_f = np.max(np.abs(ev_f.u - exact))
+    assert err < 3 * err_f + 1e-6 and err < 2e-3
+    # the coupling is evaluated more than once per face and step only at LTS boundaries
+    assert ev.corrections_evaluated > 0
