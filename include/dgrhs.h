@@ -112,6 +112,40 @@ int dgrhs_set_neighbor_orientations(dgrhs_ctx* ctx, const int32_t* neighbor_dire
  * GeneralizedHarmonic/Initialize.hpp:59-71).  host [n_elements][ncomp][n]. */
 int dgrhs_set_static_fields(dgrhs_ctx* ctx, const double* fields, int ncomp);
 
+/* ---- Local time stepping ---------------------------------------------
+ * TimeSteppers::adams_lts::lts_coefficients for explicit (Adams-Bashforth) schemes
+ * (src/Time/TimeSteppers/AdamsLts.cpp:330-437): the nonzero terms of the boundary
+ * contribution to the local side's step from start_tick to end_tick.  Times are integer ticks
+ * of tick_size after time_origin, in the order of insertion into the boundary history
+ * (ConstBoundaryHistoryTimes); term t couples local_ticks[local_index[t]] with
+ * remote_ticks[remote_index[t]], sorted like the reference's LtsCoefficients.  Host only. */
+int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_step_order,
+                                 int n_local, const long long* local_ticks, int n_remote,
+                                 const long long* remote_ticks, long long start_tick,
+                                 long long end_tick, double time_origin, double tick_size,
+                                 int max_terms, int* n_terms, int* local_index,
+                                 int* remote_index, double* coefficients);
+/* Adams-Bashforth local time stepping with fixed step sizes dt_coarse / 2^levels[e]
+ * (levels ascending in the element order: coarse steps first), replacing the action pair
+ * UpdateU + ApplyLtsBoundaryCorrections (Actions/UpdateU.hpp:44-120,
+ * ApplyBoundaryCorrections.hpp:1142-1192; AdamsBashforth::add_boundary_delta_impl,
+ * AdamsBashforth.cpp:264-281): the volume part of the time derivative incl. the external
+ * boundary conditions goes through each element's own history, the boundary corrections of
+ * internal faces are integrated from the histories of both sides.  The step sizes do not
+ * change (no step choosers), the histories start from given past states like
+ * TimeStepperTestUtils::initialize_history: after dgrhs_set_state(u(t0)) call
+ * dgrhs_lts_set_past_state for j = 1 .. order-1 with, for every element, its state at
+ * t0 - j * (its own step).  One GPU, conforming faces, ghost (DirichletAnalytic) boundary
+ * conditions with static data, static gauge fields, no filter.  Time runs in ticks of the
+ * finest step; the state is complete (all elements at the same time) after a multiple of
+ * dgrhs_lts_ticks_per_coarse_step ticks. */
+int dgrhs_lts_init(dgrhs_ctx* ctx, int order, double t0, double dt_coarse,
+                   const int32_t* levels);
+int dgrhs_lts_set_past_state(dgrhs_ctx* ctx, int j, const double* u_past);
+int dgrhs_lts_take_ticks(dgrhs_ctx* ctx, long long n_ticks);
+int dgrhs_lts_ticks_per_coarse_step(dgrhs_ctx* ctx, long long* n_ticks);
+int dgrhs_lts_time(dgrhs_ctx* ctx, double* time, long long* tick);
+
 /* Moving mesh: inertial mesh velocity v_g^i at the grid points, host [n_elements][3][n]
  * (Tags::MeshVelocity), or NULL for a static mesh (the default).  With a velocity set the
  * right-hand side gains the terms of a moving mesh for systems without fluxes: dt u += v_g^i

@@ -84,6 +84,7 @@ struct dgrhs_ctx {
   double* u_alt = nullptr;        // second state buffer for the fused update
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
   double* mesh_v = nullptr;       // [E][3][npad] inertial mesh velocity (moving mesh) or null
+  void* lts = nullptr;            // local-time-stepping state (lts.cu)
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
   double filterF_host[144] = {};  // the same on the host (kernel parameter of the filter pass)
   int num_sms = 148;
@@ -210,5 +211,23 @@ struct DgNOps {
   int (*constraints)(dgrhs_ctx* c, double* sums_dev);
   int (*partial_derivatives)(const dg::DerivArgs* a, int blocks, cudaStream_t stream);
   int (*mesh_velocity_terms)(dgrhs_ctx* c, double* dt, int eb, int ee);
+  // local time stepping (lts.cu): volume part + external boundary conditions of a range;
+  // face snapshot; boundary deltas of the elements that finish a step
+  int (*lts_evaluate)(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee);
+  int (*lts_snapshot)(dgrhs_ctx* c, double* fh, int depth, int slot, int eb, int ee);
+  int (*lts_boundary)(dgrhs_ctx* c, const dg::LtsBoundaryArgs* a);
 };
 const DgNOps* dgrhs_nops(int N);  // nullptr for an unsupported N
+
+// shared with lts.cu (defined in dgrhs.cu)
+// Adams-Bashforth coefficients of history times given in integer ticks of tick_size
+// (adams_coefficients::coefficients, AdamsCoefficients.hpp:64-104)
+std::vector<double> dgrhs_internal_ab_coefficients_ticks(const std::vector<long long>& ticks,
+                                                         long long start, long long end,
+                                                         double tick_size);
+// u[0, len) = a u + sum_j coef_j v_j[0, len) on the context's stream (len even)
+int dgrhs_internal_lincomb_range(dgrhs_ctx* c, double* u, double a,
+                                 const std::vector<double>& coef,
+                                 const std::vector<const double*>& v, size_t len);
+int dgrhs_internal_upload(dgrhs_ctx* c, double* dst, const double* src, int ncomp);
+void dgrhs_internal_lts_free(dgrhs_ctx* c);

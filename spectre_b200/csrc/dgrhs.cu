@@ -356,6 +356,41 @@ int lincomb(dgrhs_ctx* c, double* u, double a, const std::vector<double>& coef,
   return 0;
 }
 
+}  // namespace
+
+std::vector<double> dgrhs_internal_ab_coefficients_ticks(const std::vector<long long>& ticks,
+                                                         long long start, long long end,
+                                                         double tick_size) {
+  return ab_coefficients_ticks(ticks, start, end, 1, tick_size);
+}
+
+int dgrhs_internal_lincomb_range(dgrhs_ctx* c, double* u, double a,
+                                 const std::vector<double>& coef,
+                                 const std::vector<const double*>& v, size_t len) {
+  if (coef.size() > 8) return fail("too many terms in linear combination");
+  if (len == 0) return 0;
+  dg::LincombArgs p;
+  p.u = u;
+  p.a = a;
+  p.nterms = (int)coef.size();
+  for (size_t i = 0; i < coef.size(); ++i) {
+    p.c[i] = coef[i];
+    p.v[i] = v[i];
+  }
+  p.len2 = (long long)(len / 2);
+  const int blocks = (int)std::min<long long>((p.len2 + 255) / 256, 148LL * 16);
+  dg::lincomb_kernel<<<blocks, 256, 0, c->stream>>>(p);
+  ++g_launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int dgrhs_internal_upload(dgrhs_ctx* c, double* dst, const double* src, int ncomp) {
+  return upload(c, dst, src, ncomp);
+}
+
+namespace {
+
 int apply_filter(dgrhs_ctx* c) {
   if (!c->filterF) return 0;
   return dgrhs_nops(c->N)->filter(c);
@@ -546,6 +581,7 @@ int dgrhs_destroy(dgrhs_ctx* c) {
                     c->mesh_v})
     if (p) cudaFree(p);
   for (double* p : c->dt_slots) cudaFree(p);
+  dgrhs_internal_lts_free(c);
   if (c->nbr) cudaFree(c->nbr);
   if (c->nbr_face) cudaFree(c->nbr_face);
   if (c->violations) cudaFree(c->violations);

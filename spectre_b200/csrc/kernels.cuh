@@ -1334,6 +1334,217 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
 }
 
 // --------------------------------------------------------------------------
+// Local time stepping (ApplyBoundaryCorrections.hpp:797-1010 with
+// local_time_stepping == true, AdamsBashforth::add_boundary_delta_impl, AdamsBashforth.cpp:
+// 264-281).  The boundary history of a mortar is kept as raw face values of both elements at
+// their own step times (a ring of `depth` snapshots per element; the packaged data are a
+// pointwise function of them and of the static geometry):
+//   lts_snapshot_kernel   the faces of the elements that were just evaluated -> ring slot
+//   *_lts_boundary_kernel for the elements that finish a step: per internal face
+//                         acc = sum_terms coef * lift(dg_boundary_terms(local(t_i), remote(t_j)))
+//                         with the (i, j, coef) of adams_lts::lts_coefficients (host, one list
+//                         per step-size level of the neighbour), terms in the reference's
+//                         sorted order
+//   lts_add_kernel        u += acc on the slices (add_slice_to_data), directions in order
+// Not on the measured (GTS) path.
+// --------------------------------------------------------------------------
+struct LtsTerm {
+  int lslot, rslot;  // ring slots of the local / remote snapshot
+  double coef;
+};
+constexpr int kLtsMaxLevels = 8;
+
+struct LtsBoundaryArgs {
+  const double* fh;      // [E][depth][6][C][f]
+  const double* invjac;
+  const double* stat;
+  const int32_t* nbr;
+  const int32_t* nbr_face;
+  const int32_t* level;  // [E] step-size level of every element
+  const LtsTerm* terms;  // [levels][max_terms]
+  int nterms[kLtsMaxLevels];
+  int max_terms, depth, elem_begin, elem_end;
+  double* acc;           // [E][6][C][f]
+};
+
+template <int N, int C>
+__global__ void __launch_bounds__(128) lts_snapshot_kernel(const double* __restrict__ u,
+                                                           double* __restrict__ fh,
+                                                           const int32_t* __restrict__ nbr,
+                                                           int depth, int slot, int eb, int ee) {
+  constexpr int npad = Cfg<N>::npad, f = N * N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(ee - eb) * 6 * f) return;
+  const int q = (int)(idx % f), d = (int)((idx / f) % 6), e = eb + (int)(idx / (6 * f));
+  if (nbr[e * 6 + d] < 0) return;
+  const int p = face_point<N>(d, q % N, q / N);
+  const double* src = u + (size_t)e * C * npad + p;
+  double* dst = fh + ((((size_t)e * depth + slot) * 6 + d) * C) * f + q;
+#pragma unroll 5
+  for (int c = 0; c < C; ++c) dst[(size_t)c * f] = src[(size_t)c * npad];
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) gh_lts_boundary_kernel(LtsBoundaryArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, C = 50;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(a.elem_end - a.elem_begin) * 6 * f) return;
+  const int q = (int)(idx % f), d = (int)((idx / f) % 6);
+  const int e = a.elem_begin + (int)(idx / (6 * f));
+  const int nb = a.nbr[e * 6 + d];
+  if (nb < 0) return;
+  const int qa = q % N, qb = q / N;
+  const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
+  const int nd = nf & 7;
+  int na_, nb_;
+  orient_face_point<N>(nf >> 3, qa, qb, na_, nb_);
+  const int qn = na_ + N * nb_;
+  const int p_own = face_point<N>(d, qa, qb), p_nb = face_point<N>(nd, na_, nb_);
+  double unn_i[3], unn_e[3];
+  {
+    const double sign = (d & 1) ? 1.0 : -1.0, sign_n = (nd & 1) ? 1.0 : -1.0;
+    const double* jo = a.invjac + (size_t)e * 9 * npad + p_own;
+    const double* jn = a.invjac + (size_t)nb * 9 * npad + p_nb;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      unn_i[x] = sign * __ldg(jo + (size_t)((d >> 1) + 3 * x) * npad);
+      unn_e[x] = sign_n * __ldg(jn + (size_t)((nd >> 1) + 3 * x) * npad);
+    }
+  }
+  const double* so = a.stat + (size_t)e * 3 * npad + p_own;
+  const double* sn = a.stat + (size_t)nb * 3 * npad + p_nb;
+  const double g1i = __ldg(so + npad), g2i = __ldg(so + 2 * npad);
+  const double g1e = __ldg(sn + npad), g2e = __ldg(sn + 2 * npad);
+  double* __restrict__ acc = a.acc + ((size_t)(e * 6 + d) * C) * f + q;
+#pragma unroll 1
+  for (int c = 0; c < C; ++c) acc[(size_t)c * f] = 0.0;
+  const int cls = a.level[nb];
+  const LtsTerm* terms = a.terms + (size_t)cls * a.max_terms;
+#pragma unroll 1
+  for (int t = 0; t < a.nterms[cls]; ++t) {
+    const LtsTerm tm = terms[t];
+    const double* ul = a.fh + ((((size_t)e * a.depth + tm.lslot) * 6 + d) * C) * f + q;
+    const double* ur = a.fh + ((((size_t)nb * a.depth + tm.rslot) * 6 + nd) * C) * f + qn;
+    GhFaceSide si, se;
+    {
+      double g[10];
+#pragma unroll
+      for (int s = 0; s < 10; ++s) g[s] = ul[(size_t)s * f];
+      gh_face_side(g, unn_i, g1i, g2i, si);
+#pragma unroll
+      for (int s = 0; s < 10; ++s) g[s] = ur[(size_t)s * f];
+      gh_face_side(g, unn_e, g1e, g2e, se);
+    }
+    const double lift = -0.5 * (double)(N * (N - 1)) * si.mag;
+#pragma unroll 1
+    for (int s = 0; s < 10; ++s) {
+      double phi_i[3], phi_e[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        phi_i[m] = ul[(size_t)(20 + m + 3 * s) * f];
+        phi_e[m] = ur[(size_t)(20 + m + 3 * s) * f];
+      }
+      GhPairPackaged ki, ke;
+      gh_pair_package(si, ul[(size_t)s * f], ul[(size_t)(10 + s) * f], phi_i, ki);
+      gh_pair_package(se, ur[(size_t)s * f], ur[(size_t)(10 + s) * f], phi_e, ke);
+      double cg, cp, cph[3];
+      gh_pair_boundary_terms(si, se, ki, ke, cg, cp, cph);
+      acc[(size_t)s * f] += tm.coef * (cg * lift);
+      acc[(size_t)(10 + s) * f] += tm.coef * (cp * lift);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) acc[(size_t)(20 + m + 3 * s) * f] += tm.coef * (cph[m] * lift);
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) sw_lts_boundary_kernel(LtsBoundaryArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, C = 5;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(a.elem_end - a.elem_begin) * 6 * f) return;
+  const int q = (int)(idx % f), d = (int)((idx / f) % 6);
+  const int e = a.elem_begin + (int)(idx / (6 * f));
+  const int nb = a.nbr[e * 6 + d];
+  if (nb < 0) return;
+  const int qa = q % N, qb = q / N;
+  const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
+  const int nd = nf & 7;
+  int na_, nb_;
+  orient_face_point<N>(nf >> 3, qa, qb, na_, nb_);
+  const int qn = na_ + N * nb_;
+  const int p_own = face_point<N>(d, qa, qb), p_nb = face_point<N>(nd, na_, nb_);
+  double ni[3], ne[3];
+  {
+    const double sign = (d & 1) ? 1.0 : -1.0, sign_n = (nd & 1) ? 1.0 : -1.0;
+    const double* jo = a.invjac + (size_t)e * 9 * npad + p_own;
+    const double* jn = a.invjac + (size_t)nb * 9 * npad + p_nb;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      ni[x] = sign * __ldg(jo + (size_t)((d >> 1) + 3 * x) * npad);
+      ne[x] = sign_n * __ldg(jn + (size_t)((nd >> 1) + 3 * x) * npad);
+    }
+  }
+  const double g2i = __ldg(a.stat + (size_t)e * npad + p_own);
+  const double g2e = __ldg(a.stat + (size_t)nb * npad + p_nb);
+  const double mi = sqrt(ni[0] * ni[0] + ni[1] * ni[1] + ni[2] * ni[2]);
+  const double me = sqrt(ne[0] * ne[0] + ne[1] * ne[1] + ne[2] * ne[2]);
+  const double ii = 1.0 / mi, ie = 1.0 / me;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    ni[x] *= ii;
+    ne[x] *= ie;
+  }
+  const double lift = -0.5 * (double)(N * (N - 1)) * mi;
+  double sum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const int cls = a.level[nb];
+  const LtsTerm* terms = a.terms + (size_t)cls * a.max_terms;
+#pragma unroll 1
+  for (int t = 0; t < a.nterms[cls]; ++t) {
+    const LtsTerm tm = terms[t];
+    const double* ul = a.fh + ((((size_t)e * a.depth + tm.lslot) * 6 + d) * C) * f + q;
+    const double* ur = a.fh + ((((size_t)nb * a.depth + tm.rslot) * 6 + nd) * C) * f + qn;
+    double ui[5], ue[5], c5[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      ui[c] = ul[(size_t)c * f];
+      ue[c] = ur[(size_t)c * f];
+    }
+    sw_face_correction(ui, g2i, ni, ue, g2e, ne, c5);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) sum[c] += tm.coef * (c5[c] * lift);
+  }
+  double* __restrict__ acc = a.acc + ((size_t)(e * 6 + d) * C) * f + q;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) acc[(size_t)c * f] = sum[c];
+}
+
+// u += acc on the slices of the internal faces, directions in ascending order at the
+// points that several faces share (one thread per grid point: no race, fixed order)
+template <int N>
+__global__ void __launch_bounds__(256) lts_add_kernel(double* __restrict__ u,
+                                                      const double* __restrict__ acc,
+                                                      const int32_t* __restrict__ nbr, int C,
+                                                      int eb, int ee) {
+  constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, f = N * N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(ee - eb) * n) return;
+  const int p = (int)(idx % n), e = eb + (int)(idx / n);
+  const int i = p % N, j = (p / N) % N, k = p / (N * N);
+  if (i > 0 && i < N - 1 && j > 0 && j < N - 1 && k > 0 && k < N - 1) return;
+  const int ijk[3] = {i, j, k};
+#pragma unroll
+  for (int d = 0; d < 6; ++d) {
+    const int dim = d >> 1;
+    if (ijk[dim] != ((d & 1) ? N - 1 : 0)) continue;
+    if (nbr[e * 6 + d] < 0) continue;
+    const int q = dim == 0 ? j + N * k : dim == 1 ? i + N * k : i + N * j;
+    const double* src = acc + ((size_t)(e * 6 + d) * C) * f + q;
+    double* dst = u + (size_t)e * C * npad + p;
+    for (int c = 0; c < C; ++c) dst[(size_t)c * npad] += src[(size_t)c * f];
+  }
+}
+
+// --------------------------------------------------------------------------
 // Non-conforming (2:1 h-refined) mortars: one CTA per coarse face, one thread
 // per face / mortar point.  Reference data flow (InternalMortarDataImpl.hpp:
 // 230-320, ApplyBoundaryCorrections.hpp:797-1045, MortarHelpers.hpp:74-129):

@@ -1,0 +1,430 @@
+// Local time stepping with Adams-Bashforth: host logic.
+//   dgrhs_adams_lts_coefficients  TimeSteppers::adams_lts::lts_coefficients for explicit
+//                                 schemes (src/Time/TimeSteppers/AdamsLts.cpp:165-437)
+//   dgrhs_lts_*                   elements with step sizes dt_coarse / 2^level: the volume
+//                                 part of the time derivative (with the external boundary
+//                                 conditions, as ComputeTimeDerivative applies them) goes
+//                                 through the element's own Adams-Bashforth history
+//                                 (Actions/UpdateU.hpp:44-120); the boundary corrections of
+//                                 internal faces are integrated over the step from the
+//                                 histories of both sides (AdamsBashforth.cpp:264-281,
+//                                 ApplyBoundaryCorrections.hpp:797-1010 with
+//                                 local_time_stepping == true)
+// Schedule (one stream; the reference's asynchronous elements obey the same dependencies):
+// time runs in ticks of the finest step.  At tick T the elements with a step boundary at T
+// -- a suffix of the element order, elements are sorted by level -- are evaluated (volume
+// part into the history slot of their level, faces into their snapshot ring); then the
+// elements whose step ends at T + 1 are completed: u += sum_i c_i dt_i (volume history),
+// u += sum_ij c_ij lift(D(local_i, remote_j)) per internal face.  All remote values a
+// completing element needs have ticks <= T and are in the rings by then.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+#include "ctx.cuh"
+
+namespace {
+
+struct Term {
+  int li, ri;  // indices into the local / remote time lists
+  double coef;
+};
+
+using Ticks = std::vector<long long>;
+
+// AdamsLts.cpp:173-206 (find_relevant_ids, explicit scheme): by position
+bool relevant(const Ticks& times, long long end, int order, std::vector<int>* idx) {
+  int used_end = (int)times.size();
+  while (used_end > 0 && !(times[used_end - 1] < end)) --used_end;
+  if (used_end < order) return false;
+  idx->clear();
+  for (int i = used_end - order; i < used_end; ++i) idx->push_back(i);
+  return true;
+}
+
+// AdamsLts.cpp:280-305
+std::vector<double> interpolation_coefficients(const Ticks& control, long long t, double origin,
+                                               double tick_size) {
+  std::vector<double> c(control.size(), 0.0);
+  for (size_t i = 0; i < control.size(); ++i)
+    if (control[i] == t) {
+      c[i] = 1.0;
+      return c;
+    }
+  std::vector<double> fp(control.size());
+  for (size_t i = 0; i < control.size(); ++i) fp[i] = origin + (double)control[i] * tick_size;
+  const double x = origin + (double)t * tick_size;
+  for (size_t j = 0; j < control.size(); ++j) {
+    double r = 1.0;
+    for (size_t m = 0; m < control.size(); ++m)
+      if (m != j) r *= (fp[m] - x) / (fp[m] - fp[j]);
+    c[j] = r;
+  }
+  return c;
+}
+
+// lts_coefficients (AdamsLts.cpp:330-437), explicit schemes; false: insufficient data
+bool lts_coefficients(const Ticks& local, const Ticks& remote, long long start, long long end,
+                      int lo, int ro, int so, double origin, double tick_size,
+                      std::vector<Term>* out, const char** why) {
+  out->clear();
+  if (start == end) return true;
+  std::map<std::pair<int, int>, double> acc;  // sorted like the reference's (local, remote) ids
+  std::vector<std::tuple<int, int, double>> raw;
+  long long small_end = end;
+  for (;;) {
+    std::vector<int> li, ri;
+    if (!relevant(local, small_end, lo, &li) || !relevant(remote, small_end, ro, &ri)) {
+      *why = "Insufficient past data.";
+      return false;
+    }
+    Ticks lt, rt;
+    for (int i : li) lt.push_back(local[i]);
+    for (int i : ri) rt.push_back(remote[i]);
+    if (raw.empty() && so == lo && so == ro && lt == rt) {
+      // the sides step at the same rate: lts_coefficients_for_gts
+      const auto g = dgrhs_internal_ab_coefficients_ticks(lt, start, end, tick_size);
+      for (size_t s = 0; s < g.size(); ++s) out->push_back({li[s], ri[s], g[s]});
+      return true;
+    }
+    // merge_to_small_steps (AdamsLts.cpp:214-277)
+    Ticks small((size_t)so);
+    {
+      int a = (int)lt.size() - 1, b = (int)rt.size() - 1;
+      for (int o = so - 1; o >= 0; --o) {
+        if (a < 0) {
+          if (b < 0) {
+            *why = "Ran out of data";
+            return false;
+          }
+          small[o] = rt[b--];
+        } else if (b < 0) {
+          small[o] = lt[a--];
+        } else {
+          small[o] = std::max(lt[a], rt[b]);
+          if (lt[a] == small[o]) --a;
+          if (b >= 0 && rt[b] == small[o]) --b;
+        }
+      }
+    }
+    const long long current = small.back();
+    if (current < start) {
+      *why = "the start time is not a step boundary";
+      return false;
+    }
+    const auto sc = dgrhs_internal_ab_coefficients_ticks(small, current, small_end, tick_size);
+    for (size_t m = 0; m < small.size(); ++m) {
+      const auto lc = interpolation_coefficients(lt, small[m], origin, tick_size);
+      const auto rc = interpolation_coefficients(rt, small[m], origin, tick_size);
+      for (size_t a = 0; a < lc.size(); ++a) {
+        if (lc[a] == 0.0) continue;
+        for (size_t b = 0; b < rc.size(); ++b) {
+          if (rc[b] == 0.0) continue;
+          raw.emplace_back(li[a], ri[b], sc[m] * lc[a] * rc[b]);
+        }
+      }
+    }
+    if (current == start) break;
+    small_end = current;
+  }
+  // combine duplicate entries (stable in the order of generation, like the sorted merge)
+  std::stable_sort(raw.begin(), raw.end(), [&](const auto& x, const auto& y) {
+    const auto kx = std::make_pair(local[std::get<0>(x)], remote[std::get<1>(x)]);
+    const auto ky = std::make_pair(local[std::get<0>(y)], remote[std::get<1>(y)]);
+    return kx < ky;
+  });
+  for (const auto& t : raw) {
+    if (!out->empty() && out->back().li == std::get<0>(t) && out->back().ri == std::get<1>(t))
+      out->back().coef += std::get<2>(t);
+    else
+      out->push_back({std::get<0>(t), std::get<1>(t), std::get<2>(t)});
+  }
+  return true;
+}
+
+struct LtsState {
+  int order = 0, nlevels = 0, depth = 0, max_terms = 0;
+  std::vector<int> level_begin;        // [nlevels + 1] element ranges, coarse first
+  std::vector<long long> stride;       // ticks per step of each level
+  double t0 = 0.0, tick_size = 0.0;
+  long long tick = 0;
+  int past_set = 0;                    // bit j: past state j given
+  int32_t* level_dev = nullptr;        // [E]
+  int32_t* nbr_ext = nullptr;          // neighbour table with the internal faces masked
+  double* fh = nullptr;                // [E][depth][6][C][f]
+  double* acc = nullptr;               // [E][6][C][f]
+  dg::LtsTerm* terms_dev = nullptr;    // [nlevels][max_terms]
+  std::vector<double*> vol;            // [order] full-state derivative buffers
+  std::vector<std::vector<bool>> adjacent;  // level pairs that share a face
+};
+
+inline int mod(long long a, int m) { return (int)(((a % m) + m) % m); }
+
+LtsState* state(dgrhs_ctx* c) { return static_cast<LtsState*>(c->lts); }
+
+// volume part + face snapshots of the elements of `level` at step index m
+int evaluate_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
+  const DgNOps* ops = dgrhs_nops(c->N);
+  const int eb = s->level_begin[level], ee = s->level_begin[level + 1];
+  if (ops->lts_evaluate(c, s->nbr_ext, s->vol[mod(m, s->order)], eb, ee)) return 1;
+  return ops->lts_snapshot(c, s->fh, s->depth, mod(m, s->depth), eb, ee);
+}
+
+// the step of `level` from step index m to m + 1
+int complete_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
+  const DgNOps* ops = dgrhs_nops(c->N);
+  const int eb = s->level_begin[level], ee = s->level_begin[level + 1];
+  if (ee <= eb) return 0;
+  const int k = s->order;
+  const long long st = s->stride[level], start = m * st, end = start + st;
+  // UpdateU with the element's own history (oldest term first, like the GTS update)
+  {
+    Ticks ticks;
+    std::vector<const double*> v;
+    const size_t off = (size_t)eb * c->C * c->npad;
+    for (int i = k - 1; i >= 0; --i) {
+      ticks.push_back((m - i) * st);
+      v.push_back(s->vol[mod(m - i, k)] + off);
+    }
+    const auto coef = dgrhs_internal_ab_coefficients_ticks(ticks, start, end, s->tick_size);
+    if (dgrhs_internal_lincomb_range(c, c->u + off, 1.0, coef, v,
+                                     (size_t)(ee - eb) * c->C * c->npad))
+      return 1;
+  }
+  // boundary deltas: one coefficient list per level of the neighbour
+  dg::LtsBoundaryArgs a{};
+  a.fh = s->fh;
+  a.invjac = c->invjac;
+  a.stat = c->stat;
+  a.nbr = c->nbr;
+  a.nbr_face = c->nbr_face;
+  a.level = s->level_dev;
+  a.terms = s->terms_dev;
+  a.max_terms = s->max_terms;
+  a.depth = s->depth;
+  a.elem_begin = eb;
+  a.elem_end = ee;
+  a.acc = s->acc;
+  std::vector<dg::LtsTerm> host((size_t)s->nlevels * s->max_terms);
+  Ticks local;
+  for (int i = k - 1; i >= 0; --i) local.push_back((m - i) * st);
+  for (int nl = 0; nl < s->nlevels; ++nl) {
+    a.nterms[nl] = 0;
+    if (!s->adjacent[level][nl]) continue;
+    // the neighbour's snapshots before `end`: its step indices up to the last one that
+    // starts before `end`, as far back as the ring holds them
+    const long long sn = s->stride[nl];
+    const long long last = (end - 1 >= 0) ? (end - 1) / sn : -((-(end - 1) + sn - 1) / sn);
+    Ticks remote;
+    std::vector<long long> remote_m;
+    for (long long j = last - (s->depth - 1); j <= last; ++j) {
+      remote.push_back(j * sn);
+      remote_m.push_back(j);
+    }
+    std::vector<Term> terms;
+    const char* why = "";
+    if (!lts_coefficients(local, remote, start, end, k, k, k, s->t0, s->tick_size, &terms, &why))
+      return fail("LTS coefficients (levels %d / %d): %s", level, nl, why);
+    if ((int)terms.size() > s->max_terms)
+      return fail("internal error: %d LTS terms, room for %d", (int)terms.size(), s->max_terms);
+    for (size_t t = 0; t < terms.size(); ++t) {
+      // a snapshot older than the ring would alias a newer one
+      if (remote_m[terms[t].ri] <= last - s->depth)
+        return fail("internal error: LTS snapshot ring too short");
+      host[(size_t)nl * s->max_terms + t] = {mod(m - (k - 1) + terms[t].li, s->depth),
+                                             mod(remote_m[terms[t].ri], s->depth),
+                                             terms[t].coef};
+    }
+    a.nterms[nl] = (int)terms.size();
+  }
+  CU(cudaMemcpyAsync(s->terms_dev, host.data(), host.size() * sizeof(dg::LtsTerm),
+                     cudaMemcpyHostToDevice, c->stream));
+  // (pageable source: the copy is staged before the call returns)
+  return ops->lts_boundary(c, &a);
+}
+
+}  // namespace
+
+void dgrhs_internal_lts_free(dgrhs_ctx* c) {
+  LtsState* s = state(c);
+  if (!s) return;
+  for (double* p : s->vol) cudaFree(p);
+  if (s->level_dev) cudaFree(s->level_dev);
+  if (s->nbr_ext) cudaFree(s->nbr_ext);
+  if (s->fh) cudaFree(s->fh);
+  if (s->acc) cudaFree(s->acc);
+  if (s->terms_dev) cudaFree(s->terms_dev);
+  delete s;
+  c->lts = nullptr;
+}
+
+extern "C" {
+
+int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_step_order,
+                                 int n_local, const long long* local_ticks, int n_remote,
+                                 const long long* remote_ticks, long long start_tick,
+                                 long long end_tick, double time_origin, double tick_size,
+                                 int max_terms, int* n_terms, int* local_index,
+                                 int* remote_index, double* coefficients) {
+  for (int o : {local_order, remote_order, small_step_order})
+    if (o < 1 || o > 8) return fail("order must be in [1, 8]");
+  if (n_local < 1 || n_remote < 1) return fail("empty history");
+  const Ticks local(local_ticks, local_ticks + n_local);
+  const Ticks remote(remote_ticks, remote_ticks + n_remote);
+  std::vector<Term> terms;
+  const char* why = "";
+  if (!lts_coefficients(local, remote, start_tick, end_tick, local_order, remote_order,
+                        small_step_order, time_origin, tick_size, &terms, &why))
+    return fail("%s", why);
+  if ((int)terms.size() > max_terms)
+    return fail("%d terms, room for %d", (int)terms.size(), max_terms);
+  *n_terms = (int)terms.size();
+  for (size_t t = 0; t < terms.size(); ++t) {
+    local_index[t] = terms[t].li;
+    remote_index[t] = terms[t].ri;
+    coefficients[t] = terms[t].coef;
+  }
+  return 0;
+}
+
+int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const int32_t* levels) {
+  CHECK_CTX(c);
+  CU(cudaSetDevice(c->device));
+  if (order < 1 || order > 8) return fail("order must be in [1, 8]");
+  if (!(dt_coarse > 0.0)) return fail("time step must be positive");
+  if (c->n_send > 0 || c->nccl_comm)
+    return fail("local time stepping runs on one GPU (no halo exchange)");
+  if (c->n_bjorhus_faces > 0 || c->n_mortar_faces > 0 || c->n_pmortar_faces > 0)
+    return fail("local time stepping: Bjorhus faces and non-conforming mortars are not supported");
+  if (c->mesh_v) return fail("local time stepping on a moving mesh is not supported");
+  if (c->violations) return fail("local time stepping: DemandOutgoingCharSpeeds is not supported");
+  if (c->filterF) return fail("local time stepping: the exponential filter is not supported");
+  if (c->gauge == DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE)
+    return fail("local time stepping: time-dependent gauge fields are not supported");
+  if (c->nbr_host.empty()) return fail("dgrhs_lts_init needs dgrhs_set_geometry first");
+  if (!c->nbr_face && !c->aligned_table_ok)
+    return fail("neighbor table is not that of aligned blocks: call "
+                "dgrhs_set_neighbor_orientations");
+  dgrhs_internal_lts_free(c);
+  auto* s = new LtsState;
+  c->lts = s;
+  s->order = order;
+  int lmax = 0;
+  for (int e = 0; e < c->nelem; ++e) {
+    if (levels[e] < 0 || levels[e] >= dg::kLtsMaxLevels)
+      return fail("step-size level of element %d out of range [0, %d)", e, dg::kLtsMaxLevels);
+    if (e > 0 && levels[e] < levels[e - 1])
+      return fail("elements must be sorted by step-size level (coarse steps first)");
+    lmax = std::max(lmax, levels[e]);
+  }
+  s->nlevels = lmax + 1;
+  s->level_begin.assign(s->nlevels + 1, c->nelem);
+  for (int l = 0; l <= s->nlevels; ++l)
+    s->level_begin[l] = (int)(std::lower_bound(levels, levels + c->nelem, l) - levels);
+  s->stride.resize(s->nlevels);
+  for (int l = 0; l < s->nlevels; ++l) s->stride[l] = 1LL << (lmax - l);
+  s->t0 = t0;
+  s->tick_size = dt_coarse / (double)(1LL << lmax);
+  s->tick = 0;
+  // which levels meet at a face, and the largest step ratio across a face
+  s->adjacent.assign(s->nlevels, std::vector<bool>(s->nlevels, false));
+  long long ratio = 1;
+  for (int e = 0; e < c->nelem; ++e)
+    for (int d = 0; d < 6; ++d) {
+      const int nb = c->nbr_host[(size_t)e * 6 + d];
+      if (nb < 0) continue;
+      if (nb >= c->nelem) return fail("local time stepping: ghost elements are not supported");
+      s->adjacent[levels[e]][levels[nb]] = true;
+      ratio = std::max(ratio, 1LL << std::abs(levels[e] - levels[nb]));
+    }
+  // a coarse element completes its step with the fine neighbour's last order - 1 + ratio
+  // snapshots; one more slot so that the neighbour's next evaluation does not overwrite
+  s->depth = order + (int)ratio;
+  s->max_terms = order * (order + (int)ratio);
+  const size_t f = (size_t)c->N * c->N;
+  if (dev_alloc(&s->fh, (size_t)c->nelem * s->depth * 6 * c->C * f)) return 1;
+  if (dev_alloc(&s->acc, (size_t)c->nelem * 6 * c->C * f)) return 1;
+  if (dev_alloc(&s->level_dev, (size_t)c->nelem)) return 1;
+  if (dev_alloc(&s->nbr_ext, (size_t)c->nelem * 6)) return 1;
+  if (dev_alloc(&s->terms_dev, (size_t)s->nlevels * s->max_terms)) return 1;
+  for (int i = 0; i < order; ++i) {
+    double* p = nullptr;
+    if (dev_alloc(&p, c->state_len())) return 1;
+    s->vol.push_back(p);
+  }
+  std::vector<int32_t> ext(c->nbr_host);
+  for (auto& v : ext)
+    if (v >= 0) v = -1;
+  CU(cudaMemcpy(s->nbr_ext, ext.data(), ext.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->level_dev, levels, (size_t)c->nelem * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dgrhs_lts_set_past_state(dgrhs_ctx* c, int j, const double* u_past) {
+  CHECK_CTX(c);
+  LtsState* s = state(c);
+  if (!s) return fail("dgrhs_lts_init first");
+  if (j < 1 || j >= s->order) return fail("past state index must be in [1, order)");
+  if (s->tick != 0) return fail("past states belong to the start of the evolution");
+  CU(cudaSetDevice(c->device));
+  // evaluate on a scratch copy of the state: c->u holds the initial data
+  double* keep = nullptr;
+  if (dev_alloc(&keep, c->state_len())) return 1;
+  CU(cudaMemcpyAsync(keep, c->u, c->state_len() * 8, cudaMemcpyDeviceToDevice, c->stream));
+  int rc = dgrhs_internal_upload(c, c->u, u_past, c->C);
+  const DgNOps* ops = dgrhs_nops(c->N);
+  if (!rc) rc = ops->gauge(c, s->t0);
+  for (int l = 0; l < s->nlevels && !rc; ++l) rc = evaluate_level(c, s, l, -(long long)j);
+  if (cudaMemcpyAsync(c->u, keep, c->state_len() * 8, cudaMemcpyDeviceToDevice, c->stream) !=
+      cudaSuccess)
+    rc = 1;
+  cudaStreamSynchronize(c->stream);
+  cudaFree(keep);
+  if (!rc) s->past_set |= 1 << j;
+  return rc;
+}
+
+int dgrhs_lts_take_ticks(dgrhs_ctx* c, long long n_ticks) {
+  CHECK_CTX(c);
+  LtsState* s = state(c);
+  if (!s) return fail("dgrhs_lts_init first");
+  CU(cudaSetDevice(c->device));
+  for (int j = 1; j < s->order; ++j)
+    if (!(s->past_set & (1 << j)))
+      return fail("past state %d of the Adams-Bashforth history is missing "
+                  "(dgrhs_lts_set_past_state)", j);
+  const DgNOps* ops = dgrhs_nops(c->N);
+  for (long long it = 0; it < n_ticks; ++it) {
+    const long long T = s->tick;
+    if (ops->gauge(c, s->t0 + (double)T * s->tick_size)) return 1;
+    ++c->rhs_evals;
+    for (int l = 0; l < s->nlevels; ++l)
+      if (T % s->stride[l] == 0 && evaluate_level(c, s, l, T / s->stride[l])) return 1;
+    for (int l = 0; l < s->nlevels; ++l)
+      if ((T + 1) % s->stride[l] == 0 &&
+          complete_level(c, s, l, (T + 1) / s->stride[l] - 1))
+        return 1;
+    s->tick = T + 1;
+  }
+  return 0;
+}
+
+int dgrhs_lts_ticks_per_coarse_step(dgrhs_ctx* c, long long* n) {
+  CHECK_CTX(c);
+  LtsState* s = state(c);
+  if (!s) return fail("dgrhs_lts_init first");
+  *n = s->stride[0];
+  return 0;
+}
+
+int dgrhs_lts_time(dgrhs_ctx* c, double* time, long long* tick) {
+  CHECK_CTX(c);
+  LtsState* s = state(c);
+  if (!s) return fail("dgrhs_lts_init first");
+  if (time) *time = s->t0 + (double)s->tick * s->tick_size;
+  if (tick) *tick = s->tick;
+  return 0;
+}
+
+}  // extern "C"

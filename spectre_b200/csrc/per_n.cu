@@ -307,6 +307,63 @@ int launch_mesh_velocity_terms(dgrhs_ctx* c, double* dt, int eb, int ee) {
   return 0;
 }
 
+// LTS: the "volume" part of the time derivative in the reference's sense -- volume terms
+// plus the external boundary conditions (ComputeTimeDerivative applies them) -- of the
+// elements [eb, ee): the face kernel runs on a neighbour table whose internal faces are
+// marked "no correction"
+template <int N>
+int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee) {
+  if (ee <= eb) return 0;
+  dg::FaceArgs a{c->u, c->invjac, c->stat, nbr_external, c->nbr_face, c->halo_recv,
+                 c->corr, ee, ee, 0, eb, nullptr, nullptr};
+  const long long total = (long long)(ee - eb) * 6 * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::gh_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  else
+    dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  c->pdl_volume = false;
+  return launch_volume<N>(c, dt, eb, ee, true);
+}
+
+template <int N>
+int launch_lts_snapshot(dgrhs_ctx* c, double* fh, int depth, int slot, int eb, int ee) {
+  if (ee <= eb) return 0;
+  const long long total = (long long)(ee - eb) * 6 * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::lts_snapshot_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(c->u, fh, c->nbr, depth, slot,
+                                                                  eb, ee);
+  else
+    dg::lts_snapshot_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(c->u, fh, c->nbr, depth, slot,
+                                                                 eb, ee);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_lts_boundary(dgrhs_ctx* c, const dg::LtsBoundaryArgs* a) {
+  const int ne = a->elem_end - a->elem_begin;
+  if (ne <= 0) return 0;
+  const long long total = (long long)ne * 6 * N * N;
+  const int blocks = (int)((total + 127) / 128);
+  if (c->system == DGRHS_SYSTEM_GH)
+    dg::gh_lts_boundary_kernel<N><<<blocks, 128, 0, c->stream>>>(*a);
+  else
+    dg::sw_lts_boundary_kernel<N><<<blocks, 128, 0, c->stream>>>(*a);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  const long long pts = (long long)ne * c->n;
+  dg::lts_add_kernel<N><<<(int)((pts + 255) / 256), 256, 0, c->stream>>>(
+      c->u, a->acc, c->nbr, c->C, a->elem_begin, a->elem_end);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
 static const DgNOps kOps = {launch_faces<DG_N>,
                      launch_gauge<DG_N>,
                      launch_volume_p<DG_N>,
@@ -315,7 +372,10 @@ static const DgNOps kOps = {launch_faces<DG_N>,
                      launch_gauge_from_state<DG_N>,
                      launch_constraints<DG_N>,
                      launch_partial_derivatives<DG_N>,
-                     launch_mesh_velocity_terms<DG_N>};
+                     launch_mesh_velocity_terms<DG_N>,
+                     launch_lts_evaluate<DG_N>,
+                     launch_lts_snapshot<DG_N>,
+                     launch_lts_boundary<DG_N>};
 
 }  // namespace
 

@@ -46,6 +46,8 @@ EXPORTS = [
     "dgrhs_project_to_mortar", "dgrhs_project_from_mortar", "dgrhs_orient_variables_on_slice",
     "dgrhs_set_p_mortars", "dgrhs_p_mortar_transfer", "dgrhs_set_slab", "dgrhs_self_start_substeps_left", "dgrhs_stepper_substep_fractions",
     "dgrhs_set_mesh_velocity", "dgrhs_gh_package_data_moving", "dgrhs_sw_package_data_moving",
+    "dgrhs_adams_lts_coefficients", "dgrhs_lts_init", "dgrhs_lts_set_past_state",
+    "dgrhs_lts_take_ticks", "dgrhs_lts_ticks_per_coarse_step", "dgrhs_lts_time",
 ]
 
 _lib = None
@@ -86,6 +88,26 @@ def projection_matrix_meshes(n_parent, n_child, child_to_parent, size):
 
 class DgrhsError(RuntimeError):
     pass
+
+
+def adams_lts_coefficients(local_ticks, remote_ticks, start, end, local_order, remote_order=None,
+                           small_order=None, origin=0.0, tick_size=1.0):
+    """adams_lts::lts_coefficients for explicit schemes (AdamsLts.cpp:330-437), host only:
+    {(local tick, remote tick): coefficient}."""
+    remote_order = local_order if remote_order is None else remote_order
+    small_order = local_order if small_order is None else small_order
+    lt = np.ascontiguousarray(local_ticks, dtype=np.int64)
+    rt = np.ascontiguousarray(remote_ticks, dtype=np.int64)
+    cap = 256
+    li, ri = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+    cf = np.zeros(cap)
+    n = ctypes.c_int()
+    _check(load().dgrhs_adams_lts_coefficients(
+        int(local_order), int(remote_order), int(small_order), len(lt), _ptr(lt), len(rt),
+        _ptr(rt), ctypes.c_longlong(int(start)), ctypes.c_longlong(int(end)),
+        ctypes.c_double(origin), ctypes.c_double(tick_size), cap, ctypes.byref(n), _ptr(li),
+        _ptr(ri), _ptr(cf)))
+    return {(int(lt[li[t]]), int(rt[ri[t]])): float(cf[t]) for t in range(n.value)}
 
 
 def load():
@@ -276,6 +298,32 @@ class Context:
         F = _f64(fields)
         assert F.shape[0] == self.n_elements and F.shape[2] == self.n
         _check(self._lib.dgrhs_set_static_fields(self._h, _ptr(F), F.shape[1]))
+
+    def lts_init(self, order, t0, dt_coarse, levels):
+        """Adams-Bashforth local time stepping with steps dt_coarse / 2^levels[e] (levels
+        ascending in the element order)."""
+        lv = np.ascontiguousarray(levels, dtype=np.int32)
+        assert lv.shape == (self.n_elements,)
+        _check(self._lib.dgrhs_lts_init(self._h, int(order), ctypes.c_double(t0),
+                                        ctypes.c_double(dt_coarse), _ptr(lv)))
+
+    def lts_set_past_state(self, j, u):
+        U = _f64(u)
+        assert U.shape == (self.n_elements, self.n_vars, self.n)
+        _check(self._lib.dgrhs_lts_set_past_state(self._h, int(j), _ptr(U)))
+
+    def lts_take_ticks(self, n):
+        _check(self._lib.dgrhs_lts_take_ticks(self._h, ctypes.c_longlong(int(n))))
+
+    def lts_take_coarse_steps(self, n):
+        k = ctypes.c_longlong()
+        _check(self._lib.dgrhs_lts_ticks_per_coarse_step(self._h, ctypes.byref(k)))
+        self.lts_take_ticks(n * k.value)
+
+    def lts_time(self):
+        t, k = ctypes.c_double(), ctypes.c_longlong()
+        _check(self._lib.dgrhs_lts_time(self._h, ctypes.byref(t), ctypes.byref(k)))
+        return t.value, k.value
 
     def set_mesh_velocity(self, v):
         """Inertial mesh velocity [n_elements, 3, n] of a moving mesh, or None (static)."""

@@ -1,0 +1,176 @@
+"""Local time stepping on the GPU (dgrhs_lts_*) against the oracle's LtsEvolution, 1e-12:
+ScalarWave and GH on periodic bricks with two and three step-size levels, the Kerr-Schild
+shell with non-aligned wedges and ghost boundaries, and equal levels against the GTS path."""
+import numpy as np
+import pytest
+
+from oracle import lts as olts
+from oracle import oracle as orc
+from spectre_b200 import analytic, domain, evolution, lib
+from spectre_b200 import lts as hlts
+from tests.test_gpu_parity import GH_BLOCKS, SW_BLOCKS, TOL, _curved_jacobian, _relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _brick_levels(brick, x, rule):
+    levels = np.array([rule(x[e].mean(axis=1)) for e in range(brick.n_elements)])
+    perm, nb = hlts.order_by_level(levels, brick.neighbors())
+    return levels[perm], perm, nb
+
+
+def _run(system, N, J, stat, nb, levels, order, dt, u0, past, n_coarse, blocks, ostat=None,
+         gauge=None, ext_u=None, nbr_dir=None, face_perm=None, ctx=None):
+    own = ctx is None
+    if own:
+        ctx = lib.Context(system, N, len(levels))
+        ctx.set_geometry(J, None, nb)
+        if nbr_dir is not None:
+            ctx.set_neighbor_orientations(nbr_dir, face_perm)
+        ctx.set_static_fields(stat)
+        if gauge is not None:
+            ctx.set_gauge(lib.GAUGE_FIELDS)
+            ctx.set_gauge_fields(*gauge)
+    ctx.set_state(u0)
+    ctx.lts_init(order, 0.0, dt, levels)
+    for j in range(1, order):
+        ctx.lts_set_past_state(j, past(j))
+    np.testing.assert_array_equal(ctx.get_state(), u0)
+    ev = olts.LtsEvolution(system, N, J, stat if ostat is None else ostat, nb, levels, order,
+                           0.0, dt, u0, past,
+                           gauge_params=orc.GAUGE_HARMONIC if gauge is None else orc.GAUGE_GIVEN,
+                           ext_u=ext_u, nbr_dir=nbr_dir, face_perm=face_perm)
+    for _ in range(n_coarse):
+        ctx.lts_take_coarse_steps(1)
+        ev.take_coarse_steps(1)
+        assert _relerr(ctx.get_state(), ev.u, blocks) < TOL
+    t, tick = ctx.lts_time()
+    assert tick == ev.tick and t == pytest.approx(ev.time(), rel=1e-14)
+    if own:
+        ctx.close()
+    return ev
+
+
+@pytest.mark.parametrize("N,order,nlevels", [(4, 3, 2), (5, 2, 3), (6, 3, 3), (3, 4, 2), (8, 3, 2),
+                                             (12, 3, 2)])
+def test_scalar_wave_lts(N, order, nlevels):
+    rng = np.random.default_rng(40 + N)
+    L = 2 * np.pi
+    brick = domain.Brick([0, 0, 0], [L] * 3, [1, 1, 1], N)
+    x0 = brick.coords()
+    rule = (lambda c: int(c[0] > np.pi)) if nlevels == 2 else \
+        (lambda c: int(c[0] > np.pi) + int(c[1] > np.pi))
+    levels, perm, nb = _brick_levels(brick, x0, rule)
+    assert levels.max() == nlevels - 1
+    x = x0[perm]
+    J = _curved_jacobian(rng, brick)[perm]
+    stat = rng.uniform(0, 1, (brick.n_elements, 1, brick.n))
+    dt = 4e-3
+    stride = 2 ** (levels.max() - levels)
+    tick = dt / 2 ** levels.max()
+
+    def past(j):
+        return np.stack([analytic.plane_wave(x[e], -j * stride[e] * tick)
+                         for e in range(len(levels))])
+    u0 = analytic.plane_wave(x, 0.0) + 0.05 * rng.uniform(-1, 1, (brick.n_elements, 5, brick.n))
+    ev = _run(lib.SYSTEM_SCALAR_WAVE, N, J, stat, nb, levels, order, dt, u0, past, 3, SW_BLOCKS)
+    assert ev.corrections_evaluated > 0
+
+
+@pytest.mark.parametrize("N,order,nlevels,gauge", [(4, 3, 2, False), (5, 3, 3, True), (6, 2, 2, True),
+                                                   (10, 3, 2, True)])
+def test_gh_lts(N, order, nlevels, gauge):
+    rng = np.random.default_rng(60 + N)
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N)
+    x0 = brick.coords()
+    rule = (lambda c: int(c[2] > 0.5)) if nlevels == 2 else \
+        (lambda c: int(c[0] > 0.5) + int(c[2] > 0.5))
+    levels, perm, nb = _brick_levels(brick, x0, rule)
+    x = x0[perm]
+    J = _curved_jacobian(rng, brick)[perm]
+    stat = rng.uniform(-1, 1, (brick.n_elements, 3, brick.n))
+    dt = 4e-4
+    stride = 2 ** (levels.max() - levels)
+    tick = dt / 2 ** levels.max()
+    noise = 1e-2 * rng.uniform(-1, 1, (brick.n_elements, 50, brick.n))
+
+    def past(j):
+        return noise + np.stack([analytic.gauge_wave(x[e], 0.1 - j * stride[e] * tick)
+                                 for e in range(len(levels))])
+    u0 = noise + analytic.gauge_wave(x, 0.1)
+    g, ostat = None, None
+    if gauge:
+        H = rng.uniform(-1, 1, (brick.n_elements, 4, brick.n))
+        dH = rng.uniform(-1, 1, (brick.n_elements, 16, brick.n))
+        g, ostat = (H, dH), np.concatenate([stat, H, dH], axis=1)
+    _run(lib.SYSTEM_GH, N, J, stat, nb, levels, order, dt, u0, past, 2, GH_BLOCKS, ostat=ostat,
+         gauge=g)
+
+
+def test_gh_lts_on_kerr_schild_shell():
+    """Two radial layers of six non-aligned wedges with DirichletAnalytic ghosts on both
+    spheres; the outer layer takes two steps per step of the inner one (the element order of
+    the shell is inside-out and the levels must ascend: the parity does not care which layer
+    is the fine one)."""
+    from tests.test_gpu_shell import _gauge_fields
+    N, order, dt = 5, 3, 2e-3
+    problem = evolution.gh_kerr_schild_shell_problem((0, 1), N, order="radial")
+    ev0 = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, 1e-4)
+    ctx, part = ev0.ctx, ev0.part
+    ids = part.global_ids
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    r = np.sqrt((x ** 2).sum(axis=1)).mean(axis=1)
+    levels = (r > np.median(r)).astype(np.int32)
+    assert np.all(np.diff(levels) >= 0) and levels.max() == 1
+    ua = problem.u0(ids, 0.0)
+    rng = np.random.default_rng(5)
+    u0 = ua + 1e-3 * rng.uniform(-1, 1, ua.shape)
+    H, dH = _gauge_fields(N, x, J, ua)
+    ext = ev0.boundary_ghost_data(problem, 0.0)[:, :50]
+    _run(lib.SYSTEM_GH, N, J, stat, part.local_neighbors, levels, order, dt, u0, lambda j: u0, 2,
+         GH_BLOCKS, ostat=np.concatenate([stat, H, dH], axis=1), gauge=(H, dH), ext_u=ext,
+         nbr_dir=part.local_neighbor_direction, face_perm=part.local_face_permutation, ctx=ctx)
+    ctx.close()
+
+
+def test_equal_levels_match_the_gts_path():
+    """one level: the LTS entry points take the same steps as the GTS stepper of the library
+    (history started from the same past states), up to the order of the additions"""
+    N, order, dt = 6, 3, 2e-3
+    rng = np.random.default_rng(9)
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    x, J, nb = brick.coords(), brick.inverse_jacobian(), brick.neighbors()
+    stat = np.zeros((brick.n_elements, 1, brick.n))
+    levels = np.zeros(brick.n_elements, dtype=np.int32)
+    u0 = analytic.plane_wave(x, 0.0)
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u0)
+    ctx.lts_init(order, 0.0, dt, levels)
+    for j in range(1, order):
+        ctx.lts_set_past_state(j, analytic.plane_wave(x, -j * dt))
+    ctx.lts_take_coarse_steps(5)
+    got = ctx.get_state()
+    hist = [orc.dg_rhs(0, N, analytic.plane_wave(x, -j * dt), J, stat, nb) for j in (2, 1)]
+    u = u0.copy()
+    c = orc._AB_CONST[3]
+    for _ in range(5):
+        hist.append(orc.dg_rhs(0, N, u, J, stat, nb))
+        u = u + dt * (c[0] * hist[-3] + c[1] * hist[-2] + c[2] * hist[-1])
+    assert _relerr(got, u, SW_BLOCKS) < TOL
+    assert np.max(np.abs(got - analytic.plane_wave(x, 5 * dt))) < 1e-3
+    ctx.close()
+
+
+def test_lts_rejections():
+    N = 4
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N)
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(brick.inverse_jacobian(), brick.coords(), brick.neighbors())
+    with pytest.raises(lib.DgrhsError, match="sorted by step-size level"):
+        ctx.lts_init(3, 0.0, 1e-3, np.array([1, 0, 0, 0, 0, 0, 0, 0]))
+    ctx.lts_init(3, 0.0, 1e-3, np.zeros(8, dtype=np.int32))
+    with pytest.raises(lib.DgrhsError, match="past state 1"):
+        ctx.lts_take_ticks(1)
+    ctx.close()

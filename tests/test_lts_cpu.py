@@ -149,3 +149,32 @@ def test_mixed_levels_converge_to_the_analytic_solution():
     assert err < 3 * err_f + 1e-6 and err < 2e-3
     # the coupling is evaluated more than once per face and step only at LTS boundaries
     assert ev.corrections_evaluated > 0
+
+
+def test_library_lts_coefficients_match_the_oracle_and_the_reference():
+    """dgrhs_adams_lts_coefficients (host code of libdgrhs.so, doubles) against the oracle's
+    exact rationals on the reference's cases and on 2:1 / 4:1 / 8:1 steady-state patterns of
+    orders 1..8."""
+    from spectre_b200 import lib
+    cases = [([0, 1, 2], [0, 1, 2], 2, 3, 3, 3, 3), ([0, 1, 2], [0], 2, 3, 3, 1, 3),
+             ([-8, -4, 0], [-4, -2, 0, 2], 0, 4, 3, 3, 3),
+             ([-4, -2, 0, 2], [-8, -4, 0], 2, 4, 3, 3, 3), ([-2, 0], [-1, 0], 0, 1, 2, 2, 2),
+             ([-3, 0], [-1, 0, 1, 2], 0, 3, 2, 2, 2), ([1, 3, 4], [2, 3, 5], 3, 4, 2, 2, 2)]
+    for k in range(1, 9):
+        for r in (2, 4, 8):
+            coarse = [r * i for i in range(-(k - 1), 1)]
+            fine = list(range(-(k - 1), r))
+            cases.append((coarse, fine, 0, r, k, k, k))
+            cases.append((fine[:k + 1], coarse, 1, 2, k, k, k))
+    for local, remote, start, end, lo, ro, so in cases:
+        ref = lts.lts_coefficients(local, remote, start, end, lo, ro, so)
+        got = lib.adams_lts_coefficients(local, remote, start, end, lo, ro, so, origin=0.3,
+                                         tick_size=1.0)
+        assert set(got) == set((int(a), int(b)) for a, b in ref)
+        scale = max(abs(v) for v in ref.values())
+        for (a, b), v in ref.items():
+            assert abs(got[(int(a), int(b))] - v) < 1e-9 * scale, (local, remote, a, b)
+    # the terms come out in the reference's sorted order and scale with the tick size
+    got = lib.adams_lts_coefficients([-8, -4, 0], [-4, -2, 0, 2], 0, 4, 3, tick_size=0.25)
+    assert list(got) == sorted(got)
+    assert got[(0, 2)] == pytest.approx(0.25 * 115.0 / 16.0, rel=1e-13)
