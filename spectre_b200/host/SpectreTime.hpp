@@ -21,6 +21,7 @@
 #include <ostream>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/dgrhs.h"
@@ -392,6 +393,68 @@ inline TimeStepId next_time_id(int stepper, int order, const TimeStepId& current
   if (dgrhs_stepper_substep_fractions(stepper, fractions.data())) throw std::runtime_error(dgrhs_last_error());
   return current_id.next_substep(time_step, fractions[current_id.substep()]);
 }
+
+// ---- TimeSteppers::adams_lts (src/Time/TimeSteppers/AdamsLts.hpp:27-139) -----------------
+// lts_coefficients for explicit (Adams-Bashforth) schemes with the reference's argument
+// meaning: the ids of the local and the remote side of a mortar in the order of their
+// insertion into the BoundaryHistory, the step [start_time, end_time] of the local side, the
+// orders of the three schemes.  All times must lie in one slab (or in slabs of equal length
+// that follow each other: they are brought to integer ticks of a common denominator).
+namespace TimeSteppers::adams_lts {
+enum class SchemeType { Explicit, Implicit };
+struct AdamsScheme {
+  SchemeType type;
+  size_t order;
+};
+inline bool operator==(const AdamsScheme& a, const AdamsScheme& b) { return a.type == b.type && a.order == b.order; }
+using LtsCoefficients = std::vector<std::tuple<TimeStepId, TimeStepId, double>>;
+
+inline LtsCoefficients lts_coefficients(const std::vector<TimeStepId>& local_times,
+                                        const std::vector<TimeStepId>& remote_times, const Time& start_time,
+                                        const Time& end_time, const AdamsScheme& local_scheme,
+                                        const AdamsScheme& remote_scheme, const AdamsScheme& small_step_scheme) {
+  for (const auto* sch : {&local_scheme, &remote_scheme, &small_step_scheme})
+    if (sch->type != SchemeType::Explicit)
+      throw std::runtime_error("adams_lts::lts_coefficients: only explicit (Adams-Bashforth) schemes are built");
+  if (local_times.empty() || remote_times.empty()) throw std::runtime_error("adams_lts::lts_coefficients: empty history");
+  // common tick: slabs counted from the slab of start_time, fractions over one denominator
+  const Slab& base = start_time.slab();
+  const double length = base.end_value() - base.start_value();
+  std::int64_t den = 1;
+  const auto slab_offset = [&](const Time& t) -> std::int64_t {
+    const double k = (t.slab().start_value() - base.start_value()) / length;
+    const auto r = static_cast<std::int64_t>(std::llround(k));
+    if (std::abs(k - static_cast<double>(r)) > 1e-9 ||
+        std::abs((t.slab().end_value() - t.slab().start_value()) - length) > 1e-9 * std::abs(length))
+      throw std::runtime_error("adams_lts::lts_coefficients: slabs of different lengths");
+    return r;
+  };
+  std::vector<const Time*> all{&start_time, &end_time};
+  for (const auto& id : local_times) all.push_back(&id.step_time());
+  for (const auto& id : remote_times) all.push_back(&id.step_time());
+  for (const Time* t : all) den = std::lcm(den, static_cast<std::int64_t>(t->fraction().denominator()));
+  const auto tick = [&](const Time& t) -> long long {
+    return slab_offset(t) * den + static_cast<std::int64_t>(t.fraction().numerator()) *
+                                      (den / static_cast<std::int64_t>(t.fraction().denominator()));
+  };
+  std::vector<long long> lt, rt;
+  for (const auto& id : local_times) lt.push_back(tick(id.step_time()));
+  for (const auto& id : remote_times) rt.push_back(tick(id.step_time()));
+  const int cap = 8 * 16;
+  std::vector<int> li(cap), ri(cap);
+  std::vector<double> cf(cap);
+  int n = 0;
+  if (dgrhs_adams_lts_coefficients(static_cast<int>(local_scheme.order), static_cast<int>(remote_scheme.order),
+                                   static_cast<int>(small_step_scheme.order), static_cast<int>(lt.size()), lt.data(),
+                                   static_cast<int>(rt.size()), rt.data(), tick(start_time), tick(end_time),
+                                   base.start_value(), length / static_cast<double>(den), cap, &n, li.data(),
+                                   ri.data(), cf.data()) != 0)
+    throw std::runtime_error(dgrhs_last_error());
+  LtsCoefficients out;
+  for (int t = 0; t < n; ++t) out.emplace_back(local_times[li[t]], remote_times[ri[t]], cf[t]);
+  return out;
+}
+}  // namespace TimeSteppers::adams_lts
 
 // ---- the time loop of the evolution executables on a resident batch ------------------------
 // Global time stepping with a constant slab size and `steps_per_slab` equal steps per slab:

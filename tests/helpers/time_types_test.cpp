@@ -347,6 +347,58 @@ static int test_time_loop_gpu() {
   return 0;
 }
 
+
+// tests/Unit/Time/TimeSteppers/Test_AdamsLts.cpp:260-283 (make_time / make_id) and :556-596
+// ("AB 2:1 order 3"), :615-640 ("AB 3:1 order 2") on the shim's argument types
+static void test_adams_lts() {
+  namespace lts = TimeSteppers::adams_lts;
+  const int max_time = 16;
+  const Slab slab(-max_time, max_time);
+  const auto make_time = [&](int t) { return Time(slab, Rational(t + max_time, 2 * max_time)); };
+  const auto ids = [&](std::initializer_list<int> ts) {
+    std::vector<TimeStepId> v;
+    for (int t : ts) v.emplace_back(true, 0, make_time(t));
+    return v;
+  };
+  const auto find = [&](const lts::LtsCoefficients& c, int a, int b, double* out) {
+    for (const auto& term : c)
+      if (std::get<0>(term).step_time() == make_time(a) && std::get<1>(term).step_time() == make_time(b)) {
+        *out = std::get<2>(term);
+        return true;
+      }
+    return false;
+  };
+  const lts::AdamsScheme ab3{lts::SchemeType::Explicit, 3}, ab2{lts::SchemeType::Explicit, 2};
+  {
+    const auto large = ids({-8, -4, 0}), small = ids({-4, -2, 0, 2});
+    const auto c = lts::lts_coefficients(large, small, make_time(0), make_time(4), ab3, ab3, ab3);
+    const struct { int a, b; double v; } want[] = {
+        {0, 2, 115.0 / 16.0},  {0, 0, 7.0 / 6.0},    {0, -2, -11.0 / 16.0}, {-4, 2, -115.0 / 24.0},
+        {-4, -2, -11.0 / 8.0}, {-4, -4, 5.0 / 6.0},  {-8, 2, 23.0 / 16.0},  {-8, -2, 11.0 / 48.0}};
+    CHECK(c.size() == 8);
+    for (const auto& w : want) {
+      double v = 0.0;
+      CHECK(find(c, w.a, w.b, &v) && near(v, w.v));
+    }
+    const auto s2 = lts::lts_coefficients(small, large, make_time(2), make_time(4), ab3, ab3, ab3);
+    double v = 0.0;
+    CHECK(s2.size() == 7 && find(s2, 2, 0, &v) && near(v, 115.0 / 16.0) && find(s2, -2, -8, &v) &&
+          near(v, -5.0 / 48.0));
+  }
+  {
+    const auto large = ids({-3, 0}), small = ids({-1, 0, 1, 2});
+    const auto c = lts::lts_coefficients(large, small, make_time(0), make_time(3), ab2, ab2, ab2);
+    double v = 0.0;
+    CHECK(c.size() == 7 && find(c, -3, 2, &v) && near(v, -1.0) && find(c, 0, 2, &v) && near(v, 5.0 / 2.0) &&
+          find(c, 0, -1, &v) && near(v, -1.0 / 3.0));
+    // equal sides: the GTS coefficients on the diagonal
+    const auto g = lts::lts_coefficients(small, small, make_time(2), make_time(3), ab2, ab2, ab2);
+    CHECK(g.size() == 2 && find(g, 1, 1, &v) && near(v, -0.5) && find(g, 2, 2, &v) && near(v, 1.5));
+  }
+  const lts::AdamsScheme am3{lts::SchemeType::Implicit, 3};
+  CHECK_THROWS(lts::lts_coefficients(ids({0, 1}), ids({0, 1}), make_time(1), make_time(2), am3, am3, am3));
+}
+
 int main(int argc, char** argv) {
   try {
     test_rational();
@@ -355,6 +407,7 @@ int main(int argc, char** argv) {
     test_time_step_id(true);
     test_time_step_id(false);
     test_next_time_id();
+    test_adams_lts();
     if (argc > 1 && std::string(argv[1]) == "gpu" && test_time_loop_gpu()) {
       std::printf("FAILED: %s\n", dgrhs_last_error());
       return 1;
