@@ -1,0 +1,105 @@
+"""Round 2: local time stepping at scale (not the bench.py metric; a side measurement).
+GH Kerr-Schild on a thick shell (inner radius 1.9 M, outer radius 30.4 M, Logarithmic radial
+distribution: the radial element size grows 16x from the inside out), AB3.  GTS has to take the
+step of the innermost layer everywhere; LTS gives each radial layer the largest power-of-two
+multiple of it that its radial size allows (4 levels).  Both runs go through libdgrhs.so; the
+LTS kernels (snapshot / boundary / add) are not tuned.  Writes one JSON line.
+
+    python profiles/r02_lts_shell.py [--points 10] [--angular 1] [--radial 4]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spectre_b200 import evolution, lib  # noqa: E402
+from spectre_b200 import lts as hlts  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", type=int, default=10)
+    ap.add_argument("--angular", type=int, default=1)
+    ap.add_argument("--radial", type=int, default=4)
+    ap.add_argument("--coarse-steps", type=int, default=4)
+    ap.add_argument("--dt-fine", type=float, default=2e-4)
+    args = ap.parse_args()
+    N, order = args.points, 3
+    problem = evolution.gh_kerr_schild_shell_problem((args.angular, args.radial), N,
+                                                     inner_radius=1.9, outer_radius=30.4,
+                                                     order="radial")
+    ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, order, args.dt_fine)
+    part = ev.part
+    ids = part.global_ids
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    u0 = problem.u0(ids, 0.0)
+    nelem = len(ids)
+    # radial extent of every element -> level (0 = largest steps)
+    r = np.sqrt((x ** 2).sum(axis=1))
+    size = r.max(axis=1) - r.min(axis=1)
+    ratio = size / size.min()
+    steps = 2 ** np.floor(np.log2(ratio * (1 + 1e-9))).astype(int)   # multiples of the fine step
+    lmax = int(np.log2(steps.max()))
+    levels = (lmax - np.log2(steps)).astype(np.int32)
+    perm, nb = hlts.order_by_level(levels, part.local_neighbors)
+    levels = levels[perm]
+    dt_coarse = args.dt_fine * 2 ** lmax
+    ghost = ev.boundary_ghost_data(problem, 0.0)
+
+    # ---- GTS with the fine step (the tuned path), same number of simulated time units
+    ctx = ev.ctx
+    ctx.set_state(u0)
+    n_fine = args.coarse_steps * 2 ** lmax
+    ctx.take_steps(8)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    ctx.take_steps(n_fine)
+    ctx.synchronize()
+    gts_s = time.perf_counter() - t0
+    err_gts = float(np.max(np.abs(ctx.get_state() - u0)))
+    ctx.close()
+
+    # ---- LTS on the reordered elements
+    ctx = lib.Context(lib.SYSTEM_GH, N, nelem, len(part.external_faces))
+    ctx.set_geometry(J[perm], x[perm], nb)
+    ctx.set_neighbor_orientations(part.local_neighbor_direction[perm],
+                                  part.local_face_permutation[perm])
+    ctx.set_static_fields(stat[perm])
+    ctx.set_gauge(lib.GAUGE_FIELDS)
+    ctx.set_gauge_analytic_christoffel(u0[perm])
+    ctx.set_boundary_ghost_data(0, ghost)
+    ctx.set_state(u0[perm])
+    ctx.lts_init(order, 0.0, dt_coarse, levels)
+    for j in range(1, order):
+        ctx.lts_set_past_state(j, u0[perm])      # static solution
+    ctx.lts_take_coarse_steps(1)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    ctx.lts_take_coarse_steps(args.coarse_steps)
+    ctx.synchronize()
+    lts_s = time.perf_counter() - t0
+    err_lts = float(np.max(np.abs(ctx.get_state() - u0[perm])))
+    ctx.close()
+
+    counts = {int(l): int((levels == l).sum()) for l in sorted(set(levels.tolist()))}
+    updates_lts = sum(c * 2 ** l for l, c in counts.items()) * N ** 3 * args.coarse_steps
+    updates_gts = nelem * 2 ** lmax * N ** 3 * args.coarse_steps
+    print(json.dumps({
+        "workload": "GH Kerr-Schild, shell 1.9 M .. 30.4 M, Logarithmic, AB3, N=%d, %d elements"
+                    % (N, nelem),
+        "elements_per_level": counts, "dt_fine": args.dt_fine, "dt_coarse": dt_coarse,
+        "simulated_time": args.coarse_steps * dt_coarse,
+        "gts_seconds": gts_s, "lts_seconds": lts_s, "lts_speedup_wall": gts_s / lts_s,
+        "element_updates_gts": updates_gts, "element_updates_lts": updates_lts,
+        "work_ratio": updates_gts / updates_lts,
+        "gts_updates_per_s": updates_gts / gts_s, "lts_updates_per_s": updates_lts / lts_s,
+        "max_drift_from_static_solution": {"gts": err_gts, "lts": err_lts},
+        "launches": lib.kernel_launch_count()}))
+
+
+if __name__ == "__main__":
+    main()

@@ -174,3 +174,45 @@ def test_lts_rejections():
     with pytest.raises(lib.DgrhsError, match="past state 1"):
         ctx.lts_take_ticks(1)
     ctx.close()
+
+
+def test_lts_started_from_a_gts_phase():
+    """no analytic past states: (order - 1) coarse steps of self-started GTS with the finest
+    step provide the histories (spectre_b200.lts.start_from_gts); the oracle does the same
+    with its GTS Evolution and its LtsEvolution"""
+    N, order, dt = 6, 3, 8e-3
+    rng = np.random.default_rng(3)
+    L = 2 * np.pi
+    brick = domain.Brick([0, 0, 0], [L] * 3, [1, 1, 1], N)
+    levels, perm, nb = _brick_levels(brick, brick.coords(),
+                                     lambda c: int(c[0] > np.pi) + int(c[1] > np.pi))
+    x = brick.coords()[perm]
+    J = brick.inverse_jacobian()[perm]
+    stat = np.zeros((brick.n_elements, 1, brick.n))
+    u0 = analytic.plane_wave(x, 0.0)
+    ctx = lib.Context(lib.SYSTEM_SCALAR_WAVE, N, brick.n_elements)
+    ctx.set_geometry(J, x, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u0)
+    t_start = hlts.start_from_gts(ctx, order, 0.0, dt, levels)
+    assert t_start == pytest.approx(2 * dt)
+    # the oracle's version of the same procedure
+    tick, stride = dt / 4, 2 ** (2 - levels)
+    gts = orc.Evolution(lambda w, t: orc.dg_rhs(0, N, w, J, stat, nb), u0, 0.0, tick, "AB3")
+    snaps = {0: u0.copy()}
+    for T in range(1, 9):
+        gts.step()
+        snaps[T] = gts.u.copy()
+    np.testing.assert_allclose(ctx.get_state(), snaps[8], rtol=0, atol=1e-12)
+
+    def past(j):
+        return np.stack([snaps[8 - j * stride[e]][e] for e in range(len(levels))])
+    ev = olts.LtsEvolution(0, N, J, stat, nb, levels, order, t_start, dt, snaps[8], past)
+    ctx.lts_take_coarse_steps(3)
+    ev.take_coarse_steps(3)
+    got = ctx.get_state()
+    assert _relerr(got, ev.u, SW_BLOCKS) < TOL
+    t, _ = ctx.lts_time()
+    assert t == pytest.approx(5 * dt)
+    assert np.max(np.abs(got - analytic.plane_wave(x, t))) < 2e-3
+    ctx.close()
