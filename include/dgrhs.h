@@ -141,6 +141,13 @@ int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_st
  * dgrhs_lts_ticks_per_coarse_step ticks. */
 int dgrhs_lts_init(dgrhs_ctx* ctx, int order, double t0, double dt_coarse,
                    const int32_t* levels);
+/* Takes effect at the next dgrhs_lts_init.  0: every internal face goes through the boundary histories, the
+ * reference's formulation term by term.  1 (default): faces between elements of the same
+ * level are evaluated like GTS faces -- their corrections enter the volume history, which is
+ * what lts_coefficients_for_gts (AdamsLts.cpp:307-327) sums to, in another order of additions
+ * -- and the stepper update is fused into the volume kernel (orders <= 4); only faces between
+ * different levels keep histories. */
+int dgrhs_lts_set_mode(dgrhs_ctx* ctx, int same_level_faces_in_volume_history);
 int dgrhs_lts_set_past_state(dgrhs_ctx* ctx, int j, const double* u_past);
 int dgrhs_lts_take_ticks(dgrhs_ctx* ctx, long long n_ticks);
 int dgrhs_lts_ticks_per_coarse_step(dgrhs_ctx* ctx, long long* n_ticks);

@@ -85,6 +85,7 @@ struct dgrhs_ctx {
   double* ctxbuf = nullptr;       // [E][26][npad] output of gh_context_kernel
   double* mesh_v = nullptr;       // [E][3][npad] inertial mesh velocity (moving mesh) or null
   void* lts = nullptr;            // local-time-stepping state (lts.cu)
+  int lts_mode = 1;               // dgrhs_lts_set_mode
   double* filterF = nullptr;      // [N*N] exponential filter matrix (enabled if set)
   double filterF_host[144] = {};  // the same on the host (kernel parameter of the filter pass)
   int num_sms = 148;
@@ -213,8 +214,10 @@ struct DgNOps {
   int (*mesh_velocity_terms)(dgrhs_ctx* c, double* dt, int eb, int ee);
   // local time stepping (lts.cu): volume part + external boundary conditions of a range;
   // face snapshot; boundary deltas of the elements that finish a step
-  int (*lts_evaluate)(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee);
-  int (*lts_snapshot)(dgrhs_ctx* c, double* fh, int depth, int slot, int eb, int ee);
+  int (*lts_evaluate)(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee,
+                      const dg::UpdateArgs* upd);
+  int (*lts_snapshot)(dgrhs_ctx* c, double* fh, const int32_t* level, int same_level_in_volume,
+                      int depth, int slot, int eb, int ee);
   int (*lts_boundary)(dgrhs_ctx* c, const dg::LtsBoundaryArgs* a);
 };
 const DgNOps* dgrhs_nops(int N);  // nullptr for an unsupported N

@@ -1365,18 +1365,29 @@ struct LtsBoundaryArgs {
   int nterms[kLtsMaxLevels];
   int max_terms, depth, elem_begin, elem_end;
   double* acc;           // [E][6][C][f]
+  double* u;             // state buffer of the completing elements (lts_add_kernel)
+  // 1: faces between elements of the same level are not in the boundary histories (their
+  // corrections went into the volume history, which is what lts_coefficients_for_gts sums to)
+  int same_level_in_volume;
 };
+
+__device__ __forceinline__ bool lts_face_in_history(const int32_t* level, int same_level_in_volume,
+                                                    int e, int nb) {
+  return nb >= 0 && !(same_level_in_volume && level[nb] == level[e]);
+}
 
 template <int N, int C>
 __global__ void __launch_bounds__(128) lts_snapshot_kernel(const double* __restrict__ u,
                                                            double* __restrict__ fh,
                                                            const int32_t* __restrict__ nbr,
-                                                           int depth, int slot, int eb, int ee) {
+                                                           const int32_t* __restrict__ level,
+                                                           int same_level_in_volume, int depth,
+                                                           int slot, int eb, int ee) {
   constexpr int npad = Cfg<N>::npad, f = N * N;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)(ee - eb) * 6 * f) return;
   const int q = (int)(idx % f), d = (int)((idx / f) % 6), e = eb + (int)(idx / (6 * f));
-  if (nbr[e * 6 + d] < 0) return;
+  if (!lts_face_in_history(level, same_level_in_volume, e, nbr[e * 6 + d])) return;
   const int p = face_point<N>(d, q % N, q / N);
   const double* src = u + (size_t)e * C * npad + p;
   double* dst = fh + ((((size_t)e * depth + slot) * 6 + d) * C) * f + q;
@@ -1392,7 +1403,7 @@ __global__ void __launch_bounds__(128) gh_lts_boundary_kernel(LtsBoundaryArgs a)
   const int q = (int)(idx % f), d = (int)((idx / f) % 6);
   const int e = a.elem_begin + (int)(idx / (6 * f));
   const int nb = a.nbr[e * 6 + d];
-  if (nb < 0) return;
+  if (!lts_face_in_history(a.level, a.same_level_in_volume, e, nb)) return;
   const int qa = q % N, qb = q / N;
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
@@ -1465,7 +1476,7 @@ __global__ void __launch_bounds__(128) sw_lts_boundary_kernel(LtsBoundaryArgs a)
   const int q = (int)(idx % f), d = (int)((idx / f) % 6);
   const int e = a.elem_begin + (int)(idx / (6 * f));
   const int nb = a.nbr[e * 6 + d];
-  if (nb < 0) return;
+  if (!lts_face_in_history(a.level, a.same_level_in_volume, e, nb)) return;
   const int qa = q % N, qb = q / N;
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
@@ -1523,8 +1534,10 @@ __global__ void __launch_bounds__(128) sw_lts_boundary_kernel(LtsBoundaryArgs a)
 template <int N>
 __global__ void __launch_bounds__(256) lts_add_kernel(double* __restrict__ u,
                                                       const double* __restrict__ acc,
-                                                      const int32_t* __restrict__ nbr, int C,
-                                                      int eb, int ee) {
+                                                      const int32_t* __restrict__ nbr,
+                                                      const int32_t* __restrict__ level,
+                                                      int same_level_in_volume, int C, int eb,
+                                                      int ee) {
   constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, f = N * N;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)(ee - eb) * n) return;
@@ -1536,7 +1549,7 @@ __global__ void __launch_bounds__(256) lts_add_kernel(double* __restrict__ u,
   for (int d = 0; d < 6; ++d) {
     const int dim = d >> 1;
     if (ijk[dim] != ((d & 1) ? N - 1 : 0)) continue;
-    if (nbr[e * 6 + d] < 0) continue;
+    if (!lts_face_in_history(level, same_level_in_volume, e, nbr[e * 6 + d])) continue;
     const int q = dim == 0 ? j + N * k : dim == 1 ? i + N * k : i + N * j;
     const double* src = acc + ((size_t)(e * 6 + d) * C) * f + q;
     double* dst = u + (size_t)e * C * npad + p;

@@ -157,18 +157,57 @@ struct LtsState {
   dg::LtsTerm* terms_dev = nullptr;    // [nlevels][max_terms]
   std::vector<double*> vol;            // [order] full-state derivative buffers
   std::vector<std::vector<bool>> adjacent;  // level pairs that share a face
+  // mode 1: faces between elements of the same level are evaluated like GTS faces (their
+  // corrections enter the volume history) and the stepper update is fused into the volume
+  // kernel: the state of a level then alternates between the two state buffers
+  int same_level_in_volume = 1;
+  bool fused = false;
+  double* buf[2] = {nullptr, nullptr};
+  std::vector<int> parity;             // [nlevels] which buffer holds the level's state
 };
 
 inline int mod(long long a, int m) { return (int)(((a % m) + m) % m); }
 
 LtsState* state(dgrhs_ctx* c) { return static_cast<LtsState*>(c->lts); }
 
-// volume part + face snapshots of the elements of `level` at step index m
-int evaluate_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
+// Adams-Bashforth coefficients of the step m -> m + 1 of `level` (uniform history)
+std::vector<double> step_coefficients(const LtsState* s, int level, long long m) {
+  Ticks ticks;
+  const long long st = s->stride[level];
+  for (int i = s->order - 1; i >= 0; --i) ticks.push_back((m - i) * st);
+  return dgrhs_internal_ab_coefficients_ticks(ticks, m * st, (m + 1) * st, s->tick_size);
+}
+
+// volume part + face snapshots of the elements of `level` at step index m; with `update` (and
+// the fused mode) the volume kernel also writes u + sum_i c_i dt_i into the level's other
+// state buffer (UpdateU; the boundary deltas follow when the step completes)
+int evaluate_level(dgrhs_ctx* c, LtsState* s, int level, long long m, bool update) {
   const DgNOps* ops = dgrhs_nops(c->N);
   const int eb = s->level_begin[level], ee = s->level_begin[level + 1];
-  if (ops->lts_evaluate(c, s->nbr_ext, s->vol[mod(m, s->order)], eb, ee)) return 1;
-  return ops->lts_snapshot(c, s->fh, s->depth, mod(m, s->depth), eb, ee);
+  if (ee <= eb) return 0;
+  const int k = s->order;
+  double* const keep = c->u;
+  if (s->fused) c->u = s->buf[s->parity[level]];
+  int rc = ops->lts_snapshot(c, s->fh, s->level_dev, s->same_level_in_volume, s->depth,
+                             mod(m, s->depth), eb, ee);
+  if (!rc && update && s->fused) {
+    const auto coef = step_coefficients(s, level, m);
+    dg::UpdateArgs up{};
+    up.u_new = s->buf[1 - s->parity[level]];
+    up.a = 1.0;
+    up.nterms = k - 1;
+    for (int j = 0; j < k - 1; ++j) {
+      up.c[j] = coef[j];
+      up.v[j] = s->vol[mod(m - (k - 1) + j, k)];
+    }
+    up.c_new = coef[k - 1];
+    rc = ops->lts_evaluate(c, s->nbr_ext, s->vol[mod(m, k)], eb, ee, &up);
+    s->parity[level] ^= 1;
+  } else if (!rc) {
+    rc = ops->lts_evaluate(c, s->nbr_ext, s->vol[mod(m, k)], eb, ee, nullptr);
+  }
+  c->u = keep;
+  return rc;
 }
 
 // the step of `level` from step index m to m + 1
@@ -178,20 +217,22 @@ int complete_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
   if (ee <= eb) return 0;
   const int k = s->order;
   const long long st = s->stride[level], start = m * st, end = start + st;
-  // UpdateU with the element's own history (oldest term first, like the GTS update)
-  {
-    Ticks ticks;
+  double* const u_level = s->fused ? s->buf[s->parity[level]] : c->u;
+  // UpdateU with the element's own history (oldest term first, like the GTS update); in the
+  // fused mode the volume kernel did it when the step was evaluated
+  if (!s->fused) {
     std::vector<const double*> v;
     const size_t off = (size_t)eb * c->C * c->npad;
-    for (int i = k - 1; i >= 0; --i) {
-      ticks.push_back((m - i) * st);
-      v.push_back(s->vol[mod(m - i, k)] + off);
-    }
-    const auto coef = dgrhs_internal_ab_coefficients_ticks(ticks, start, end, s->tick_size);
-    if (dgrhs_internal_lincomb_range(c, c->u + off, 1.0, coef, v,
+    for (int i = k - 1; i >= 0; --i) v.push_back(s->vol[mod(m - i, k)] + off);
+    const auto coef = step_coefficients(s, level, m);
+    if (dgrhs_internal_lincomb_range(c, u_level + off, 1.0, coef, v,
                                      (size_t)(ee - eb) * c->C * c->npad))
       return 1;
   }
+  bool any = false;
+  for (int nl = 0; nl < s->nlevels; ++nl)
+    if (s->adjacent[level][nl] && !(s->same_level_in_volume && nl == level)) any = true;
+  if (!any) return 0;
   // boundary deltas: one coefficient list per level of the neighbour
   dg::LtsBoundaryArgs a{};
   a.fh = s->fh;
@@ -206,12 +247,14 @@ int complete_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
   a.elem_begin = eb;
   a.elem_end = ee;
   a.acc = s->acc;
+  a.u = u_level;
+  a.same_level_in_volume = s->same_level_in_volume;
   std::vector<dg::LtsTerm> host((size_t)s->nlevels * s->max_terms);
   Ticks local;
   for (int i = k - 1; i >= 0; --i) local.push_back((m - i) * st);
   for (int nl = 0; nl < s->nlevels; ++nl) {
     a.nterms[nl] = 0;
-    if (!s->adjacent[level][nl]) continue;
+    if (!s->adjacent[level][nl] || (s->same_level_in_volume && nl == level)) continue;
     // the neighbour's snapshots before `end`: its step indices up to the last one that
     // starts before `end`, as far back as the ring holds them
     const long long sn = s->stride[nl];
@@ -353,9 +396,21 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
     if (dev_alloc(&p, c->state_len())) return 1;
     s->vol.push_back(p);
   }
+  s->same_level_in_volume = c->lts_mode != 0;
+  s->fused = s->same_level_in_volume && c->fuse_update && order <= 4;
+  s->parity.assign(s->nlevels, 0);
+  if (s->fused) {
+    if (!c->u_alt && dev_alloc(&c->u_alt, c->state_len())) return 1;
+    s->buf[0] = c->u;
+    s->buf[1] = c->u_alt;
+  }
+  // the faces the face kernel does not evaluate read "no correction"
   std::vector<int32_t> ext(c->nbr_host);
-  for (auto& v : ext)
-    if (v >= 0) v = -1;
+  for (int e = 0; e < c->nelem; ++e)
+    for (int d = 0; d < 6; ++d) {
+      int32_t& v = ext[(size_t)e * 6 + d];
+      if (v >= 0 && !(s->same_level_in_volume && levels[v] == levels[e])) v = -1;
+    }
   CU(cudaMemcpy(s->nbr_ext, ext.data(), ext.size() * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(s->level_dev, levels, (size_t)c->nelem * 4, cudaMemcpyHostToDevice));
   return 0;
@@ -375,7 +430,7 @@ int dgrhs_lts_set_past_state(dgrhs_ctx* c, int j, const double* u_past) {
   int rc = dgrhs_internal_upload(c, c->u, u_past, c->C);
   const DgNOps* ops = dgrhs_nops(c->N);
   if (!rc) rc = ops->gauge(c, s->t0);
-  for (int l = 0; l < s->nlevels && !rc; ++l) rc = evaluate_level(c, s, l, -(long long)j);
+  for (int l = 0; l < s->nlevels && !rc; ++l) rc = evaluate_level(c, s, l, -(long long)j, false);
   if (cudaMemcpyAsync(c->u, keep, c->state_len() * 8, cudaMemcpyDeviceToDevice, c->stream) !=
       cudaSuccess)
     rc = 1;
@@ -400,13 +455,29 @@ int dgrhs_lts_take_ticks(dgrhs_ctx* c, long long n_ticks) {
     if (ops->gauge(c, s->t0 + (double)T * s->tick_size)) return 1;
     ++c->rhs_evals;
     for (int l = 0; l < s->nlevels; ++l)
-      if (T % s->stride[l] == 0 && evaluate_level(c, s, l, T / s->stride[l])) return 1;
+      if (T % s->stride[l] == 0 && evaluate_level(c, s, l, T / s->stride[l], true)) return 1;
     for (int l = 0; l < s->nlevels; ++l)
       if ((T + 1) % s->stride[l] == 0 &&
           complete_level(c, s, l, (T + 1) / s->stride[l] - 1))
         return 1;
     s->tick = T + 1;
   }
+  // the caller reads the state from c->u: bring the levels that sit in the other buffer back
+  if (s->fused)
+    for (int l = 0; l < s->nlevels; ++l) {
+      if (s->parity[l] == 0) continue;
+      const size_t off = (size_t)s->level_begin[l] * c->C * c->npad;
+      const size_t len = (size_t)(s->level_begin[l + 1] - s->level_begin[l]) * c->C * c->npad;
+      CU(cudaMemcpyAsync(s->buf[0] + off, s->buf[1] + off, len * 8, cudaMemcpyDeviceToDevice,
+                         c->stream));
+      s->parity[l] = 0;
+    }
+  return 0;
+}
+
+int dgrhs_lts_set_mode(dgrhs_ctx* c, int same_level_faces_in_volume_history) {
+  CHECK_CTX(c);
+  c->lts_mode = same_level_faces_in_volume_history ? 1 : 0;
   return 0;
 }
 

@@ -312,7 +312,8 @@ int launch_mesh_velocity_terms(dgrhs_ctx* c, double* dt, int eb, int ee) {
 // elements [eb, ee): the face kernel runs on a neighbour table whose internal faces are
 // marked "no correction"
 template <int N>
-int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee) {
+int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee,
+                        const dg::UpdateArgs* upd) {
   if (ee <= eb) return 0;
   dg::FaceArgs a{c->u, c->invjac, c->stat, nbr_external, c->nbr_face, c->halo_recv,
                  c->corr, ee, ee, 0, eb, nullptr, nullptr};
@@ -325,20 +326,21 @@ int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, i
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   c->pdl_volume = false;
-  return launch_volume<N>(c, dt, eb, ee, true);
+  return launch_volume<N>(c, dt, eb, ee, true, upd ? *upd : dg::UpdateArgs{});
 }
 
 template <int N>
-int launch_lts_snapshot(dgrhs_ctx* c, double* fh, int depth, int slot, int eb, int ee) {
+int launch_lts_snapshot(dgrhs_ctx* c, double* fh, const int32_t* level, int same_level_in_volume,
+                        int depth, int slot, int eb, int ee) {
   if (ee <= eb) return 0;
   const long long total = (long long)(ee - eb) * 6 * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)
-    dg::lts_snapshot_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(c->u, fh, c->nbr, depth, slot,
-                                                                  eb, ee);
+    dg::lts_snapshot_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(
+        c->u, fh, c->nbr, level, same_level_in_volume, depth, slot, eb, ee);
   else
-    dg::lts_snapshot_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(c->u, fh, c->nbr, depth, slot,
-                                                                 eb, ee);
+    dg::lts_snapshot_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(
+        c->u, fh, c->nbr, level, same_level_in_volume, depth, slot, eb, ee);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   return 0;
@@ -358,7 +360,7 @@ int launch_lts_boundary(dgrhs_ctx* c, const dg::LtsBoundaryArgs* a) {
   CU(cudaGetLastError());
   const long long pts = (long long)ne * c->n;
   dg::lts_add_kernel<N><<<(int)((pts + 255) / 256), 256, 0, c->stream>>>(
-      c->u, a->acc, c->nbr, c->C, a->elem_begin, a->elem_end);
+      a->u, a->acc, c->nbr, a->level, a->same_level_in_volume, c->C, a->elem_begin, a->elem_end);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   return 0;

@@ -48,6 +48,7 @@ EXPORTS = [
     "dgrhs_set_mesh_velocity", "dgrhs_gh_package_data_moving", "dgrhs_sw_package_data_moving",
     "dgrhs_adams_lts_coefficients", "dgrhs_lts_init", "dgrhs_lts_set_past_state",
     "dgrhs_lts_take_ticks", "dgrhs_lts_ticks_per_coarse_step", "dgrhs_lts_time",
+    "dgrhs_lts_set_mode",
 ]
 
 _lib = None
@@ -299,9 +300,10 @@ class Context:
         assert F.shape[0] == self.n_elements and F.shape[2] == self.n
         _check(self._lib.dgrhs_set_static_fields(self._h, _ptr(F), F.shape[1]))
 
-    def lts_init(self, order, t0, dt_coarse, levels):
+    def lts_init(self, order, t0, dt_coarse, levels, same_level_faces_in_volume_history=True):
         """Adams-Bashforth local time stepping with steps dt_coarse / 2^levels[e] (levels
         ascending in the element order)."""
+        _check(self._lib.dgrhs_lts_set_mode(self._h, int(same_level_faces_in_volume_history)))
         lv = np.ascontiguousarray(levels, dtype=np.int32)
         assert lv.shape == (self.n_elements,)
         _check(self._lib.dgrhs_lts_init(self._h, int(order), ctypes.c_double(t0),

@@ -20,7 +20,10 @@ def _brick_levels(brick, x, rule):
 
 
 def _run(system, N, J, stat, nb, levels, order, dt, u0, past, n_coarse, blocks, ostat=None,
-         gauge=None, ext_u=None, nbr_dir=None, face_perm=None, ctx=None):
+         gauge=None, ext_u=None, nbr_dir=None, face_perm=None, ctx=None, mode=1):
+    """mode 0: every internal face through the boundary histories (the reference's
+    formulation term by term); mode 1 (the library's default): same-level faces like GTS
+    faces, stepper update fused.  The oracle is the reference's formulation in both cases."""
     own = ctx is None
     if own:
         ctx = lib.Context(system, N, len(levels))
@@ -32,7 +35,7 @@ def _run(system, N, J, stat, nb, levels, order, dt, u0, past, n_coarse, blocks, 
             ctx.set_gauge(lib.GAUGE_FIELDS)
             ctx.set_gauge_fields(*gauge)
     ctx.set_state(u0)
-    ctx.lts_init(order, 0.0, dt, levels)
+    ctx.lts_init(order, 0.0, dt, levels, same_level_faces_in_volume_history=bool(mode))
     for j in range(1, order):
         ctx.lts_set_past_state(j, past(j))
     np.testing.assert_array_equal(ctx.get_state(), u0)
@@ -51,9 +54,10 @@ def _run(system, N, J, stat, nb, levels, order, dt, u0, past, n_coarse, blocks, 
     return ev
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("N,order,nlevels", [(4, 3, 2), (5, 2, 3), (6, 3, 3), (3, 4, 2), (8, 3, 2),
-                                             (12, 3, 2)])
-def test_scalar_wave_lts(N, order, nlevels):
+                                             (12, 3, 2), (4, 5, 2)])
+def test_scalar_wave_lts(N, order, nlevels, mode):
     rng = np.random.default_rng(40 + N)
     L = 2 * np.pi
     brick = domain.Brick([0, 0, 0], [L] * 3, [1, 1, 1], N)
@@ -73,13 +77,15 @@ def test_scalar_wave_lts(N, order, nlevels):
         return np.stack([analytic.plane_wave(x[e], -j * stride[e] * tick)
                          for e in range(len(levels))])
     u0 = analytic.plane_wave(x, 0.0) + 0.05 * rng.uniform(-1, 1, (brick.n_elements, 5, brick.n))
-    ev = _run(lib.SYSTEM_SCALAR_WAVE, N, J, stat, nb, levels, order, dt, u0, past, 3, SW_BLOCKS)
+    ev = _run(lib.SYSTEM_SCALAR_WAVE, N, J, stat, nb, levels, order, dt, u0, past, 3, SW_BLOCKS,
+              mode=mode)
     assert ev.corrections_evaluated > 0
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("N,order,nlevels,gauge", [(4, 3, 2, False), (5, 3, 3, True), (6, 2, 2, True),
-                                                   (10, 3, 2, True)])
-def test_gh_lts(N, order, nlevels, gauge):
+                                                   (10, 3, 2, True), (12, 4, 2, True)])
+def test_gh_lts(N, order, nlevels, gauge, mode):
     rng = np.random.default_rng(60 + N)
     brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N)
     x0 = brick.coords()
@@ -104,10 +110,11 @@ def test_gh_lts(N, order, nlevels, gauge):
         dH = rng.uniform(-1, 1, (brick.n_elements, 16, brick.n))
         g, ostat = (H, dH), np.concatenate([stat, H, dH], axis=1)
     _run(lib.SYSTEM_GH, N, J, stat, nb, levels, order, dt, u0, past, 2, GH_BLOCKS, ostat=ostat,
-         gauge=g)
+         gauge=g, mode=mode)
 
 
-def test_gh_lts_on_kerr_schild_shell():
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gh_lts_on_kerr_schild_shell(mode):
     """Two radial layers of six non-aligned wedges with DirichletAnalytic ghosts on both
     spheres; the outer layer takes two steps per step of the inner one (the element order of
     the shell is inside-out and the levels must ascend: the parity does not care which layer
@@ -129,7 +136,8 @@ def test_gh_lts_on_kerr_schild_shell():
     ext = ev0.boundary_ghost_data(problem, 0.0)[:, :50]
     _run(lib.SYSTEM_GH, N, J, stat, part.local_neighbors, levels, order, dt, u0, lambda j: u0, 2,
          GH_BLOCKS, ostat=np.concatenate([stat, H, dH], axis=1), gauge=(H, dH), ext_u=ext,
-         nbr_dir=part.local_neighbor_direction, face_perm=part.local_face_permutation, ctx=ctx)
+         nbr_dir=part.local_neighbor_direction, face_perm=part.local_face_permutation, ctx=ctx,
+         mode=mode)
     ctx.close()
 
 
