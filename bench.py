@@ -691,6 +691,15 @@ def main():
     torch.cuda.set_device(local_rank)
     pg = None
     if world > 1:
+        # one process per GPU: run on the CPUs next to that GPU, so that the pinned host
+        # buffers of the e2e leg are first touched on the GPU's NUMA node (the ranks otherwise
+        # share one node's memory controllers); the CPU baseline only runs at N = 1
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:   # no NVML / not permitted: keep the inherited affinity
+            pass
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))

@@ -1095,8 +1095,11 @@ __device__ __forceinline__ bool face_task(const FaceArgs& a, int e, int d, int n
   return true;
 }
 
+#ifndef DG_FACE_MIN_BLOCKS
+#define DG_FACE_MIN_BLOCKS 1
+#endif
 template <int N>
-__global__ void __launch_bounds__(128) gh_face_kernel(FaceArgs a) {
+__global__ void __launch_bounds__(128, DG_FACE_MIN_BLOCKS) gh_face_kernel(FaceArgs a) {
   constexpr int npad = Cfg<N>::npad, f = N * N, HC = 55;
   pdl_launch_dependents();  // the volume kernel may start its prologue (see pdl_wait_for_primary)
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

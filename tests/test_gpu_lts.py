@@ -224,3 +224,39 @@ def test_lts_started_from_a_gts_phase():
     assert t == pytest.approx(5 * dt)
     assert np.max(np.abs(got - analytic.plane_wave(x, t))) < 2e-3
     ctx.close()
+
+
+def test_cpp_lts_example_matches_oracle():
+    """spectre_b200/host/evolve_scalar_wave_lts.cpp: the plane wave with two step-size levels
+    driven entirely from C++20 through the C-ABI (dgrhs_lts_*); its ObserveNorms-style errors
+    equal those of the oracle's LtsEvolution of the same configuration."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "evolve_scalar_wave_lts")
+    src = os.path.join(root, "spectre_b200", "host", "evolve_scalar_wave_lts.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-o", exe, src, "-L",
+                           os.path.join(root, "spectre_b200"), "-ldgrhs",
+                           "-Wl,-rpath," + os.path.join(root, "spectre_b200")])
+    steps = 6
+    out = subprocess.run([exe, str(steps)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = {ln.split()[0]: float(ln.split()[1]) for ln in out.stdout.strip().splitlines()}
+    N, dt = 5, 2e-3
+    brick = domain.Brick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N)
+    levels, perm, nb = _brick_levels(brick, brick.coords(), lambda c: int(c[0] > np.pi))
+    x, J = brick.coords()[perm], brick.inverse_jacobian()[perm]
+    stat = np.zeros((brick.n_elements, 1, N ** 3))
+
+    def past(j):
+        return np.stack([analytic.plane_wave(x[e], -j * dt / 2 ** levels[e])
+                         for e in range(len(levels))])
+    ev = olts.LtsEvolution(0, N, J, stat, nb, levels, 3, 0.0, dt, analytic.plane_wave(x, 0.0), past)
+    ev.take_coarse_steps(steps)
+    assert got["time"] == pytest.approx(ev.time(), abs=1e-15)
+    exact = analytic.plane_wave(x, ev.time())
+    npts = exact.shape[0] * exact.shape[2]
+    for name, (a, b) in zip(("Psi", "Pi", "Phi"), ((0, 1), (1, 2), (2, 5))):
+        want = np.sqrt(np.sum((ev.u[:, a:b] - exact[:, a:b]) ** 2) / npts)
+        assert got[f"Error({name})"] == pytest.approx(want, rel=1e-8)
