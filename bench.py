@@ -646,6 +646,8 @@ def main():
     ap.add_argument("--cpu-sample-refine", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lts", action="store_true",
+                    help="skip the local-time-stepping side measurement (N = 1 only)")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the configs[1] measurement reported as `secondary`")
     ap.add_argument("--no-e2e-pipeline", action="store_true",
@@ -721,6 +723,22 @@ def main():
     if args.workload == "kerr-schild-shell" and not args.no_secondary:
         secondary = secondary_line(args, world, rank, local_rank, pg)
 
+    # local time stepping (not the metric: a side measurement of the same library, N = 1 only)
+    lts = None
+    if rank == 0 and world == 1 and args.workload == "kerr-schild-shell" and not args.no_lts:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "r02_lts_shell", os.path.join(ROOT, "profiles", "r02_lts_shell.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        try:
+            lts = mod.measure()
+            lts["what"] = ("Adams-Bashforth local time stepping (dgrhs_lts_*, DESIGN.md 3.6) "
+                           "against GTS with the finest step, wall time for the same simulated "
+                           "time on a shell whose radial element size grows 16x")
+        except Exception as e:   # the headline does not depend on this leg
+            lts = {"error": str(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         arm = CpuArm(args.workload, args.points, args.cpu_sample_refine, args.dt, run.use_filter)
@@ -736,7 +754,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "max_abs_error_vs_exact": err, "secondary": secondary,
+            "max_abs_error_vs_exact": err, "secondary": secondary, "lts": lts,
         }
         if run.phases:
             line["multi_gpu_timeline_ms"] = {

@@ -5,7 +5,7 @@ step of the innermost layer everywhere; LTS gives each radial layer the largest 
 multiple of it that its radial size allows (4 levels).  Both runs go through libdgrhs.so; the
 LTS kernels (snapshot / boundary / add) are not tuned.  Writes one JSON line.
 
-    python profiles/r02_lts_shell.py [--points 10] [--angular 1] [--radial 4]
+    python profiles/r02_lts_shell.py [--points 10] [--angular 3] [--radial 4]
 """
 import argparse
 import json
@@ -20,14 +20,11 @@ from spectre_b200 import evolution, lib  # noqa: E402
 from spectre_b200 import lts as hlts  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--points", type=int, default=10)
-    ap.add_argument("--angular", type=int, default=1)
-    ap.add_argument("--radial", type=int, default=4)
-    ap.add_argument("--coarse-steps", type=int, default=4)
-    ap.add_argument("--dt-fine", type=float, default=2e-4)
-    args = ap.parse_args()
+def measure(points=10, angular=3, radial=4, coarse_steps=2, dt_fine=2e-4):
+    """GTS (finest step everywhere) and LTS wall time for the same simulated time; returns the
+    dict that main() prints (bench.py reports it as its `lts` object at N = 1)."""
+    args = argparse.Namespace(points=points, angular=angular, radial=radial,
+                              coarse_steps=coarse_steps, dt_fine=dt_fine)
     N, order = args.points, 3
     problem = evolution.gh_kerr_schild_shell_problem((args.angular, args.radial), N,
                                                      inner_radius=1.9, outer_radius=30.4,
@@ -88,7 +85,7 @@ def main():
     counts = {int(l): int((levels == l).sum()) for l in sorted(set(levels.tolist()))}
     updates_lts = sum(c * 2 ** l for l, c in counts.items()) * N ** 3 * args.coarse_steps
     updates_gts = nelem * 2 ** lmax * N ** 3 * args.coarse_steps
-    print(json.dumps({
+    return {
         "workload": "GH Kerr-Schild, shell 1.9 M .. 30.4 M, Logarithmic, AB3, N=%d, %d elements"
                     % (N, nelem),
         "elements_per_level": counts, "dt_fine": args.dt_fine, "dt_coarse": dt_coarse,
@@ -97,8 +94,18 @@ def main():
         "element_updates_gts": updates_gts, "element_updates_lts": updates_lts,
         "work_ratio": updates_gts / updates_lts,
         "gts_updates_per_s": updates_gts / gts_s, "lts_updates_per_s": updates_lts / lts_s,
-        "max_drift_from_static_solution": {"gts": err_gts, "lts": err_lts},
-        "launches": lib.kernel_launch_count()}))
+        "max_drift_from_static_solution": {"gts": err_gts, "lts": err_lts}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", type=int, default=10)
+    ap.add_argument("--angular", type=int, default=3)
+    ap.add_argument("--radial", type=int, default=4)
+    ap.add_argument("--coarse-steps", type=int, default=2)
+    ap.add_argument("--dt-fine", type=float, default=2e-4)
+    a = ap.parse_args()
+    print(json.dumps(measure(a.points, a.angular, a.radial, a.coarse_steps, a.dt_fine)))
 
 
 if __name__ == "__main__":
