@@ -2,7 +2,7 @@
 GH Kerr-Schild on a thick shell (inner radius 1.9 M, outer radius 30.4 M, Logarithmic radial
 distribution: the radial element size grows 16x from the inside out), AB3.  GTS has to take the
 step of the innermost layer everywhere; LTS gives each radial layer the largest power-of-two
-multiple of it that its radial size allows (4 levels).  Both runs go through libdgrhs.so; the
+multiple of it that StepChoosers::ElementSizeCfl allows (evaluated once, at the start).  Both runs go through libdgrhs.so; the
 LTS kernels (snapshot / boundary / add) are not tuned.  Writes one JSON line.
 
     python profiles/r02_lts_shell.py [--points 10] [--angular 3] [--radial 4]
@@ -35,13 +35,15 @@ def measure(points=10, angular=3, radial=4, coarse_steps=2, dt_fine=2e-4):
     x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
     u0 = problem.u0(ids, 0.0)
     nelem = len(ids)
-    # radial extent of every element -> level (0 = largest steps)
-    r = np.sqrt((x ** 2).sum(axis=1))
-    size = r.max(axis=1) - r.min(axis=1)
-    ratio = size / size.min()
-    steps = 2 ** np.floor(np.log2(ratio * (1 + 1e-9))).astype(int)   # multiples of the fine step
-    lmax = int(np.log2(steps.max()))
-    levels = (lmax - np.log2(steps)).astype(np.int32)
+    # StepChoosers::ElementSizeCfl evaluated at the start gives the ratios of the element steps
+    # (spectre_b200/lts.py); the finest step is --dt-fine
+    speed = hlts.gh_largest_characteristic_speed(u0, stat[:, 1])
+    goal = hlts.element_size_cfl(hlts.size_of_element(problem.brick, ids), speed,
+                                 lib.stepper_properties(lib.STEPPER_ADAMS_BASHFORTH, order)[3],
+                                 1.0)
+    fine = np.floor(np.log2(goal / goal.min() * (1 + 1e-9))).astype(int)   # log2 of step / finest
+    lmax = int(fine.max())
+    levels = (lmax - fine).astype(np.int32)
     perm, nb = hlts.order_by_level(levels, part.local_neighbors)
     levels = levels[perm]
     dt_coarse = args.dt_fine * 2 ** lmax

@@ -60,3 +60,50 @@ def start_from_gts(ctx, order, t0, dt_coarse, levels, stepper=None):
             past[sel] = snaps[n_ticks - j * int(s)][sel]
         ctx.lts_set_past_state(j, past)
     return t_start
+
+
+# ---- step choosers evaluated once, at the start -------------------------------------------
+def size_of_element(dom, ids=None):
+    """domain::size_of_element (Domain/SizeOfElement.cpp:44-59): per element and logical
+    dimension the distance between the inertial centres of the two opposite faces.  Uses the
+    domain's exact map (`map_points`) when it has one, else the affine bounds of a Brick."""
+    ids = list(range(dom.n_elements)) if ids is None else list(ids)
+    out = np.zeros((len(ids), 3))
+    for k, e in enumerate(ids):
+        for d in range(3):
+            if hasattr(dom, "map_points"):
+                xi = np.zeros((3, 2))
+                xi[d] = (-1.0, 1.0)
+                x, _ = dom.map_points(e, xi)
+                out[k, d] = np.sqrt(((x[:, 1] - x[:, 0]) ** 2).sum())
+            else:
+                x = dom.coords([e])[0]
+                out[k, d] = x[d].max() - x[d].min()     # affine: face-to-face distance
+    return out
+
+
+def gh_largest_characteristic_speed(u, gamma1):
+    """gh::Tags::ComputeLargestCharacteristicSpeed (GeneralizedHarmonic/Characteristics.cpp:
+    188-196) per element: max(|1 + gamma1| |beta|, |beta| + lapse) over the grid points, with
+    lapse and shift from the spacetime metric.  u [nelem, 50, n], gamma1 [nelem, n]."""
+    sym = {}
+    s = 0
+    for a in range(4):
+        for b in range(a, 4):
+            sym[(a, b)] = sym[(b, a)] = s
+            s += 1
+    g = lambda a, b: u[:, sym[(a, b)]]
+    gam = np.stack([np.stack([g(i + 1, j + 1) for j in range(3)], axis=-1) for i in range(3)],
+                   axis=-2)                                    # [nelem, n, 3, 3]
+    beta_lo = np.stack([g(0, i + 1) for i in range(3)], axis=-1)
+    beta_up = np.linalg.solve(gam, beta_lo[..., None])[..., 0]
+    b2 = (beta_up * beta_lo).sum(axis=-1)
+    lapse = np.sqrt(b2 - g(0, 0))
+    mag = np.sqrt(b2)
+    return np.maximum((np.abs(1.0 + gamma1) * mag).max(axis=1), (mag + lapse).max(axis=1))
+
+
+def element_size_cfl(element_sizes, speed, stable_step, safety_factor):
+    """StepChoosers::ElementSizeCfl (Time/StepChoosers/ElementSizeCfl.hpp:76-92): the step
+    goal safety_factor * stable_step * min_d(size_d) / (speed * 3) of every element."""
+    return safety_factor * stable_step * np.min(element_sizes, axis=1) / (np.asarray(speed) * 3)

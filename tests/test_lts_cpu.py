@@ -178,3 +178,38 @@ def test_library_lts_coefficients_match_the_oracle_and_the_reference():
     got = lib.adams_lts_coefficients([-8, -4, 0], [-4, -2, 0, 2], 0, 4, 3, tick_size=0.25)
     assert list(got) == sorted(got)
     assert got[(0, 2)] == pytest.approx(0.25 * 115.0 / 16.0, rel=1e-13)
+
+
+def test_element_size_cfl_chooser_and_levels():
+    """StepChoosers::ElementSizeCfl evaluated at the start (ElementSizeCfl.hpp:76-92,
+    SizeOfElement.cpp:44-59, Characteristics.cpp:188-196) and the levels it gives on a thick
+    Kerr-Schild shell: the expected value of Test_ElementSizeCfl.cpp:73-95 is the formula
+    itself, safety * stable_step * min size / (speed * Dim)."""
+    from spectre_b200 import analytic, domain, lib
+    from spectre_b200 import lts as hlts
+    # size_of_element: affine brick and the exact wedge map
+    brick = domain.Brick([0, 0, 0], [2.0, 4.0, 8.0], [1, 1, 2], 4)
+    np.testing.assert_allclose(hlts.size_of_element(brick), [[1.0, 2.0, 2.0]] * brick.n_elements,
+                               rtol=1e-14)
+    shell = domain.SphericalShell(2.0, 32.0, (0, 2), 5, radial_distribution="Logarithmic",
+                                  order="radial")
+    size = hlts.size_of_element(shell)
+    # radial face centres lie on the wedge axis: four layers 2-4-8-16-32
+    np.testing.assert_allclose(sorted(set(np.round(size[:, 2], 10))), [2.0, 4.0, 8.0, 16.0])
+    # the formula
+    goal = hlts.element_size_cfl(np.array([[1.0, 2.0, 0.5]]), [2.0], 3.0 / 11.0, 0.8)
+    assert goal[0] == pytest.approx(0.8 * (3.0 / 11.0) * 0.5 / (2.0 * 3.0), rel=1e-15)
+    # largest characteristic speed of Kerr-Schild (M = 1): lapse^2 = 1/(1+2/r), |beta| =
+    # (2/r) lapse -> |beta| + lapse = sqrt(1 + 2/r) at the innermost point, gamma1 = -1
+    x = shell.coords()
+    u = analytic.kerr_schild(x, 1.0)
+    speed = hlts.gh_largest_characteristic_speed(u, -np.ones((shell.n_elements, shell.n)))
+    r = np.sqrt((x ** 2).sum(axis=1))
+    lapse = 1.0 / np.sqrt(1.0 + 2.0 / r)
+    np.testing.assert_allclose(speed, ((2.0 / r) * lapse + lapse).max(axis=1), rtol=1e-12)
+    stable = lib.stepper_properties(lib.STEPPER_ADAMS_BASHFORTH, 3)[3]
+    goal = hlts.element_size_cfl(size, speed, stable, 0.5)
+    levels = hlts.levels_from_step_limit(goal, dt_coarse=goal.max())
+    assert levels.min() == 0 and len(set(levels.tolist())) == 4   # one level per radial layer
+    assert np.all(np.diff(levels) <= 0)    # inside-out element order: finer steps inside
+    assert np.all(goal.max() / 2.0 ** levels <= goal * (1 + 1e-12))
