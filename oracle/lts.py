@@ -153,7 +153,7 @@ class LtsEvolution:
 
     def __init__(self, system, N, invjac, static_fields, nbr, levels, order, t0, dt_coarse,
                  u0, past_states, gauge_params=orc.GAUGE_HARMONIC, ext_u=None, nbr_dir=None,
-                 face_perm=None, static_face=None):
+                 face_perm=None, static_face=None, mortars=None):
         self.system, self.N, self.k = system, N, int(order)
         self.J, self.stat = invjac, static_fields
         self.nbr = np.asarray(nbr, dtype=np.int64)
@@ -169,8 +169,18 @@ class LtsEvolution:
         self.face_perm = face_perm if face_perm is not None else np.zeros((self.nelem, 6), int)
         # the static fields that enter dg_package_data: SW gamma2; GH gamma1, gamma2
         self.static_face = static_fields if static_face is None else static_face
+        # non-conforming (2:1) mortars between aligned blocks: rows (coarse element, direction,
+        # fine element, direction, size_a, size_b) as in oracle.dg_rhs; both faces read HANGING
+        self.mortars = [] if mortars is None else [tuple(int(v) for v in m) for m in mortars]
+        assert all(m[3] >> 3 == 0 for m in self.mortars), "aligned mortars only"
+        self.hanging = self.nbr == orc.HANGING
+        if self.mortars:
+            self.P = [np.eye(N)] + [orc.projection_matrix_parent_to_child(N, N, sz)
+                                    for sz in (orc.MORTAR_LOWER_HALF, orc.MORTAR_UPPER_HALF)]
+            self.R = [np.eye(N)] + [orc.projection_matrix_child_to_parent(N, N, sz)
+                                    for sz in (orc.MORTAR_LOWER_HALF, orc.MORTAR_UPPER_HALF)]
         # external faces keep their boundary condition inside the "volume" part
-        self.nbr_ext = np.where(self.nbr >= 0, -1, self.nbr).astype(np.int32)
+        self.nbr_ext = np.where((self.nbr >= 0) | self.hanging, -1, self.nbr).astype(np.int32)
         self.u = u0.copy()
         self.tick = 0
         self.vol_hist = [[] for _ in range(self.nelem)]      # (tick, dt_u)
@@ -197,7 +207,7 @@ class LtsEvolution:
         for a, e in enumerate(elems):
             self.vol_hist[e].append((int(ticks[e]), dt[a]))
             for d in range(6):
-                if self.nbr[e, d] >= 0:
+                if self.nbr[e, d] >= 0 or self.hanging[e, d]:
                     pk, mag = orc.face_packaged_data(self.system, self.N, u_all[e], self.J[e],
                                                      self.static_face[e], d)
                     self.face_hist[e][d].append((int(ticks[e]), pk, mag))
@@ -219,6 +229,42 @@ class LtsEvolution:
             L.orc_gh_boundary_terms(f, orc._p(pk_int), orc._p(pk_ext), orc._p(corr))
         self.corrections_evaluated += 1
         return corr * (-0.5 * self.N * (self.N - 1) * local[2])     # LiftFlux.hpp:57-61
+
+    def _to_mortar(self, pk, sa, sb):
+        """project_to_mortar (MortarHelpers.hpp:74-101): first face dimension, then the
+        second, of every packaged component (the characteristic speeds included)"""
+        N = self.N
+        x = pk.reshape(pk.shape[0], N, N)          # [c, b, a]
+        x = np.einsum("ta,cba->cbt", self.P[sa], x)
+        x = np.einsum("tb,cba->cta", self.P[sb], x)
+        return np.ascontiguousarray(x.reshape(pk.shape[0], N * N))
+
+    def _boundary_terms(self, pk_int, pk_ext):
+        C = 5 if self.system == 0 else 50
+        f = self.N * self.N
+        corr = np.zeros((C, f))
+        L = orc.lib()
+        a, b = np.ascontiguousarray(pk_int), np.ascontiguousarray(pk_ext)
+        if self.system == 0:
+            L.orc_sw_boundary_terms(f, orc._p(a), orc._p(b), orc._p(corr))
+        else:
+            L.orc_gh_boundary_terms(f, orc._p(a), orc._p(b), orc._p(corr))
+        self.corrections_evaluated += 1
+        return corr
+
+    def _mortar_coupling(self, m, fine_side, local, remote):
+        """coupling across the mortar m for the fine element (its face is the mortar) or
+        for the coarse one (correction on the mortar, project_from_mortar, lift on its face)"""
+        _, _, _, _, sa, sb = m
+        N = self.N
+        if fine_side:
+            corr = self._boundary_terms(local[1], self._to_mortar(remote[1], sa, sb))
+            return corr * (-0.5 * N * (N - 1) * local[2])
+        corr = self._boundary_terms(self._to_mortar(local[1], sa, sb), remote[1])
+        x = corr.reshape(corr.shape[0], N, N)
+        x = np.einsum("at,cbt->cba", self.R[sa], x)
+        x = np.einsum("bt,cta->cba", self.R[sb], x)
+        return x.reshape(corr.shape[0], N * N) * (-0.5 * N * (N - 1) * local[2])
 
     def _finalize(self, e, end_tick):
         """the step of element e that ends at end_tick: UpdateU with the volume history,
@@ -248,6 +294,23 @@ class LtsEvolution:
                 lifted = lifted + (c * self.tick_size) * self._coupling(
                     e, d, by_tick_l[int(tl)], by_tick_r[int(tr)])
             u[:, orc.face_point_indices(self.N, d)] += lifted
+        for m in self.mortars:
+            ec, dc, ef, df = m[0], m[1], m[2], m[3] & 7
+            for fine_side, (own, d, other, od) in ((False, (ec, dc, ef, df)),
+                                                   (True, (ef, df, ec, dc))):
+                if own != e:
+                    continue
+                local = self.face_hist[e][d][-k:]
+                remote = [h for h in self.face_hist[other][od] if h[0] < end_tick]
+                terms = lts_coefficients([h[0] for h in local], [h[0] for h in remote], start,
+                                         end_tick, k)
+                by_tick_l = {h[0]: h for h in local}
+                by_tick_r = {h[0]: h for h in remote}
+                lifted = 0.0
+                for (tl, tr), c in terms.items():
+                    lifted = lifted + (c * self.tick_size) * self._mortar_coupling(
+                        m, fine_side, by_tick_l[int(tl)], by_tick_r[int(tr)])
+                u[:, orc.face_point_indices(self.N, d)] += lifted
         return u
 
     def _prune(self):

@@ -213,3 +213,63 @@ def test_element_size_cfl_chooser_and_levels():
     assert levels.min() == 0 and len(set(levels.tolist())) == 4   # one level per radial layer
     assert np.all(np.diff(levels) <= 0)    # inside-out element order: finer steps inside
     assert np.all(goal.max() / 2.0 ** levels <= goal * (1 + 1e-12))
+
+
+def _refined_sw_problem(N):
+    from spectre_b200 import analytic, domain
+    rb = domain.RefinedBrick([0, 0, 0], [2 * np.pi] * 3, [1, 1, 1], N, [(0, 0, 0)])
+    x, J, nb, mt = rb.coords(), rb.inverse_jacobian(), rb.neighbors(), rb.mortars()
+    stat = np.zeros((rb.n_elements, 1, N ** 3))
+    size = x[:, 0].max(axis=1) - x[:, 0].min(axis=1)
+    return analytic, rb, x, J, nb, mt, stat, size
+
+
+def test_lts_with_mortars_equal_levels_reproduce_the_gts_oracle():
+    """h-refined brick (one cell split into eight), every element on one level: the mortar
+    couplings through the boundary histories sum to the GTS right-hand side with mortars"""
+    N, dt, order = 4, 1e-3, 3
+    analytic, rb, x, J, nb, mt, stat, _ = _refined_sw_problem(N)
+    assert len(mt) > 0
+    u0 = analytic.plane_wave(x, 0.0)
+    ev = lts.LtsEvolution(0, N, J, stat, nb, np.zeros(rb.n_elements, int), order, 0.0, dt, u0,
+                          lambda j: analytic.plane_wave(x, -j * dt), mortars=mt)
+    ev.take_coarse_steps(3)
+    hist = [orc.dg_rhs(0, N, analytic.plane_wave(x, -j * dt), J, stat, nb, mortars=mt)
+            for j in (2, 1)]
+    u = u0.copy()
+    c = orc._AB_CONST[3]
+    for _ in range(3):
+        hist.append(orc.dg_rhs(0, N, u, J, stat, nb, mortars=mt))
+        u = u + dt * (c[0] * hist[-3] + c[1] * hist[-2] + c[2] * hist[-1])
+    assert np.max(np.abs(ev.u - u)) < 1e-13 * np.max(np.abs(u))
+
+
+def test_lts_with_mortars_fine_elements_take_half_steps():
+    """the canonical LTS set-up: the eight children of the refined cell take two steps per
+    step of the unrefined elements; the solution stays as close to the analytic one as the
+    GTS evolution with the fine step everywhere"""
+    N, dt, order = 6, 8e-3, 3
+    analytic, rb, x, J, nb, mt, stat, size = _refined_sw_problem(N)
+    levels = (size < 0.75 * size.max()).astype(int)
+    assert levels.sum() == 8
+    from spectre_b200 import lts as hlts
+    perm, nbp = hlts.order_by_level(levels, nb)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    mtp = np.array(mt).copy()
+    mtp[:, 0], mtp[:, 2] = inv[mtp[:, 0]], inv[mtp[:, 2]]
+    x, J, levels = x[perm], J[perm], levels[perm]
+    u0 = analytic.plane_wave(x, 0.0)
+
+    def past(j):
+        return np.stack([analytic.plane_wave(x[e], -j * dt / 2 ** levels[e])
+                         for e in range(len(levels))])
+    ev = lts.LtsEvolution(0, N, J, stat, nbp, levels, order, 0.0, dt, u0, past, mortars=mtp)
+    ev.take_coarse_steps(4)
+    exact = analytic.plane_wave(x, 4 * dt)
+    err = np.max(np.abs(ev.u - exact))
+    ev_f = lts.LtsEvolution(0, N, J, stat, nbp, 0 * levels, order, 0.0, dt / 2, u0,
+                            lambda j: analytic.plane_wave(x, -j * dt / 2), mortars=mtp)
+    ev_f.take_coarse_steps(8)
+    err_f = np.max(np.abs(ev_f.u - exact))
+    assert err < 3 * err_f + 1e-6 and err < 5e-3
