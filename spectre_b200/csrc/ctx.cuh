@@ -106,6 +106,7 @@ struct dgrhs_ctx {
   int n_mortar_faces_local = 0;      // groups without a remote side come first
   int32_t* mortar_faces = nullptr;   // [n_mortar_faces][4]
   int32_t* mortar_table = nullptr;   // [n_mortars][4]
+  std::vector<int32_t> mortar_faces_host, mortar_table_host;  // the same on the host (lts.cu)
   double* mortar_P = nullptr;        // [3][N*N]
   double* mortar_R = nullptr;        // [3][N*N]
   // faces to a neighbour with a different N (another context): dgrhs_set_p_mortars
@@ -214,11 +215,12 @@ struct DgNOps {
   int (*mesh_velocity_terms)(dgrhs_ctx* c, double* dt, int eb, int ee);
   // local time stepping (lts.cu): volume part + external boundary conditions of a range;
   // face snapshot; boundary deltas of the elements that finish a step
-  int (*lts_evaluate)(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee,
-                      const dg::UpdateArgs* upd);
-  int (*lts_snapshot)(dgrhs_ctx* c, double* fh, const int32_t* level, int same_level_in_volume,
-                      int depth, int slot, int eb, int ee);
+  int (*lts_evaluate)(dgrhs_ctx* c, const int32_t* nbr_external, const uint8_t* mortar_skip,
+                      double* dt, int eb, int ee, const dg::UpdateArgs* upd);
+  int (*lts_snapshot)(dgrhs_ctx* c, double* fh, const uint8_t* in_history, int depth, int slot,
+                      int eb, int ee);
   int (*lts_boundary)(dgrhs_ctx* c, const dg::LtsBoundaryArgs* a);
+  int (*lts_mortar)(dgrhs_ctx* c, const dg::LtsMortarArgs* a, int n_groups);
 };
 const DgNOps* dgrhs_nops(int N);  // nullptr for an unsupported N
 

@@ -1112,6 +1112,8 @@ int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
   if (hanging != local_coarse + local_fine)
     return fail("%zu faces are marked hanging but the mortar table covers %zu", hanging,
                 local_coarse + local_fine);
+  c->mortar_faces_host = faces;
+  c->mortar_table_host = table;
   if (c->mortar_faces) cudaFree(c->mortar_faces);
   if (c->mortar_table) cudaFree(c->mortar_table);
   c->mortar_faces = c->mortar_table = nullptr;

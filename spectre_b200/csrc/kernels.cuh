@@ -1369,28 +1369,22 @@ struct LtsBoundaryArgs {
   int max_terms, depth, elem_begin, elem_end;
   double* acc;           // [E][6][C][f]
   double* u;             // state buffer of the completing elements (lts_add_kernel)
-  // 1: faces between elements of the same level are not in the boundary histories (their
-  // corrections went into the volume history, which is what lts_coefficients_for_gts sums to)
-  int same_level_in_volume;
+  // [E][6]: 1 = the face is in the boundary histories (mode 1: the neighbour has another
+  // level; faces between elements of the same level went into the volume history, which is
+  // what lts_coefficients_for_gts sums to)
+  const uint8_t* in_history;
 };
-
-__device__ __forceinline__ bool lts_face_in_history(const int32_t* level, int same_level_in_volume,
-                                                    int e, int nb) {
-  return nb >= 0 && !(same_level_in_volume && level[nb] == level[e]);
-}
 
 template <int N, int C>
 __global__ void __launch_bounds__(128) lts_snapshot_kernel(const double* __restrict__ u,
                                                            double* __restrict__ fh,
-                                                           const int32_t* __restrict__ nbr,
-                                                           const int32_t* __restrict__ level,
-                                                           int same_level_in_volume, int depth,
-                                                           int slot, int eb, int ee) {
+                                                           const uint8_t* __restrict__ in_history,
+                                                           int depth, int slot, int eb, int ee) {
   constexpr int npad = Cfg<N>::npad, f = N * N;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)(ee - eb) * 6 * f) return;
   const int q = (int)(idx % f), d = (int)((idx / f) % 6), e = eb + (int)(idx / (6 * f));
-  if (!lts_face_in_history(level, same_level_in_volume, e, nbr[e * 6 + d])) return;
+  if (!in_history[e * 6 + d]) return;
   const int p = face_point<N>(d, q % N, q / N);
   const double* src = u + (size_t)e * C * npad + p;
   double* dst = fh + ((((size_t)e * depth + slot) * 6 + d) * C) * f + q;
@@ -1406,7 +1400,7 @@ __global__ void __launch_bounds__(128) gh_lts_boundary_kernel(LtsBoundaryArgs a)
   const int q = (int)(idx % f), d = (int)((idx / f) % 6);
   const int e = a.elem_begin + (int)(idx / (6 * f));
   const int nb = a.nbr[e * 6 + d];
-  if (!lts_face_in_history(a.level, a.same_level_in_volume, e, nb)) return;
+  if (nb < 0 || !a.in_history[e * 6 + d]) return;  // (hanging faces: lts_mortar_kernel)
   const int qa = q % N, qb = q / N;
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
@@ -1479,7 +1473,7 @@ __global__ void __launch_bounds__(128) sw_lts_boundary_kernel(LtsBoundaryArgs a)
   const int q = (int)(idx % f), d = (int)((idx / f) % 6);
   const int e = a.elem_begin + (int)(idx / (6 * f));
   const int nb = a.nbr[e * 6 + d];
-  if (!lts_face_in_history(a.level, a.same_level_in_volume, e, nb)) return;
+  if (nb < 0 || !a.in_history[e * 6 + d]) return;  // (hanging faces: lts_mortar_kernel)
   const int qa = q % N, qb = q / N;
   const int nf = a.nbr_face ? a.nbr_face[e * 6 + d] : (d ^ 1);
   const int nd = nf & 7;
@@ -1537,10 +1531,8 @@ __global__ void __launch_bounds__(128) sw_lts_boundary_kernel(LtsBoundaryArgs a)
 template <int N>
 __global__ void __launch_bounds__(256) lts_add_kernel(double* __restrict__ u,
                                                       const double* __restrict__ acc,
-                                                      const int32_t* __restrict__ nbr,
-                                                      const int32_t* __restrict__ level,
-                                                      int same_level_in_volume, int C, int eb,
-                                                      int ee) {
+                                                      const uint8_t* __restrict__ in_history,
+                                                      int C, int eb, int ee) {
   constexpr int n = Cfg<N>::n, npad = Cfg<N>::npad, f = N * N;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)(ee - eb) * n) return;
@@ -1552,7 +1544,7 @@ __global__ void __launch_bounds__(256) lts_add_kernel(double* __restrict__ u,
   for (int d = 0; d < 6; ++d) {
     const int dim = d >> 1;
     if (ijk[dim] != ((d & 1) ? N - 1 : 0)) continue;
-    if (!lts_face_in_history(level, same_level_in_volume, e, nbr[e * 6 + d])) continue;
+    if (!in_history[e * 6 + d]) continue;
     const int q = dim == 0 ? j + N * k : dim == 1 ? i + N * k : i + N * j;
     const double* src = acc + ((size_t)(e * 6 + d) * C) * f + q;
     double* dst = u + (size_t)e * C * npad + p;
@@ -1588,6 +1580,10 @@ struct MortarArgs {
   // ghost slot `slot` [HC][f] (u | J row | gammas, like every cut face)
   const double* ghost;
   int face_begin;          // first coarse-face group of this launch
+  // local time stepping (lts.cu): mortars kept in the boundary histories are skipped here
+  // (nullptr: none); elem_end > 0: only the groups whose coarse element is in the range
+  const uint8_t* skip;
+  int elem_begin, elem_end;
 };
 
 // dg_boundary_terms of one pair from PACKAGED values (the n_i v^+- fields are
@@ -1633,6 +1629,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
   const int qa = tid % N, qb = active ? tid / N : 0;
   const int32_t* fc = a.faces + 4 * (a.face_begin + blockIdx.x);
   const int ec = fc[0], dc = fc[1], m0 = fc[2], nm = fc[3];
+  if (a.elem_end > 0 && (ec < a.elem_begin || ec >= a.elem_end)) return;
   constexpr int HC = C + 3 + (kSystem == 1 ? 2 : 1);
   for (int i = tid; i < 3 * N * N; i += T) {
     (&sP[0][0])[i] = a.P[i];
@@ -1727,10 +1724,20 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
     for (int x = 0; x < 4; ++x) sA[13 + x][tid] = sC.speed[x];
   }
   const double liftC = active ? -0.5 * (double)(N * (N - 1)) * sC.mag : 0.0;
+  // the coarse face's correction is the sum over its mortars: start from zero
+  if (active && ec >= 0) {
+#pragma unroll 1
+    for (int s = 0; s < NP; ++s) {
+      double* cc = corr_ptr(ec, s, dc) + tid;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) cc[(size_t)c * f] = 0.0;
+    }
+  }
   __syncthreads();
 
 #pragma unroll 1
   for (int mi = 0; mi < nm; ++mi) {
+    if (a.skip && a.skip[m0 + mi]) continue;
     const int32_t* mt = a.mortars + 4 * (m0 + mi);
     // mt[1] = fine direction | perm << 3: perm takes this thread's mortar point, given
     // in the coarse element's face frame, to the fine element's face point (blocks that
@@ -1820,10 +1827,238 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32) mortar_kernel(MortarAr
 #pragma unroll
           for (int m = 0; m < N; ++m) v += Rb[qb * N + m] * sF[c][qa + N * m];
           v *= liftC;
-          if (mi == 0)
-            cc[(size_t)c * f] = v;
-          else
-            cc[(size_t)c * f] += v;
+          cc[(size_t)c * f] += v;
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Local time stepping across non-conforming (2:1) mortars: mortar_kernel's data flow with
+// both sides read from the snapshot rings at the slots of a coefficient list, for the side
+// that completes a step (role 0: the coarse elements of [elem_begin, elem_end), role 1: the
+// fine ones).  Per mortar and term, in the reference's order: package on each face,
+// project_to_mortar, dg_boundary_terms, (coarse side: project_from_mortar,) lift, times the
+// coefficient, summed (AdamsBashforth.cpp:264-281 on the mortar's BoundaryHistory; a coarse
+// face sums over its mortars as the reference adds one mortar's delta after the other).
+// --------------------------------------------------------------------------
+struct LtsMortarArgs {
+  const double* fh;        // [E][depth][6][C][f]
+  const double* invjac;
+  const double* stat;
+  const int32_t* faces;    // [groups][4] as MortarArgs
+  const int32_t* mortars;  // [n_mortars][4]
+  const uint8_t* mortar_in_history;  // [n_mortars]
+  const double* P;
+  const double* R;
+  const int32_t* level;
+  const LtsTerm* terms;    // [levels][max_terms]: local = the completing side
+  int nterms[kLtsMaxLevels];
+  int max_terms, depth, elem_begin, elem_end, role;
+  double* acc;             // [E][6][C][f]
+};
+
+template <int N, int kSystem>
+__global__ void __launch_bounds__((N * N + 31) / 32 * 32) lts_mortar_kernel(LtsMortarArgs a) {
+  constexpr int npad = Cfg<N>::npad, f = N * N, T = (N * N + 31) / 32 * 32;
+  constexpr int C = kSystem == 1 ? 50 : 5, NP = kSystem == 1 ? 10 : 1;
+  constexpr int S = kSystem == 1 ? 3 : 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using Mat = double[N * N];
+  using Row = double[f];
+  Mat* sP = reinterpret_cast<Mat*>(smem_raw);  // [3]
+  Mat* sR = sP + 3;                            // [3]
+  Row* sA = reinterpret_cast<Row*>(sR + 3);    // [17]
+  Row* sB = sA + 17;                           // [17]
+  Row* sE = sB + 17;                           // [5]
+  Row* sF = sE + 5;                            // [5]
+  const int tid = threadIdx.x;
+  const bool active = tid < f;
+  const int qa = tid % N, qb = active ? tid / N : 0;
+  const int32_t* fc = a.faces + 4 * blockIdx.x;
+  const int ec = fc[0], dc = fc[1], m0 = fc[2], nm = fc[3];
+  const bool coarse_completes = a.role == 0;
+  if (coarse_completes && (ec < a.elem_begin || ec >= a.elem_end)) return;
+  for (int i = tid; i < 3 * N * N; i += T) {
+    (&sP[0][0])[i] = a.P[i];
+    (&sR[0][0])[i] = a.R[i];
+  }
+  auto snapshot = [&](int e, int d, int slot) {
+    return a.fh + ((((size_t)e * a.depth + slot) * 6 + d) * C) * f;
+  };
+  // one side at this thread's point (p volume index for the static geometry, q face index)
+  auto make_side = [&](int e, int d, int p, int q, const double* face, GhFaceSide& sd) {
+    const double sign = (d & 1) ? 1.0 : -1.0;
+    const int dim = d >> 1;
+    double unn[3];
+    const double* jo = a.invjac + (size_t)e * 9 * npad + p;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) unn[x] = sign * __ldg(jo + (size_t)(dim + 3 * x) * npad);
+    const double* so = a.stat + (size_t)e * S * npad + p;
+    if constexpr (kSystem == 1) {
+      double g[10];
+#pragma unroll
+      for (int s = 0; s < 10; ++s) g[s] = face[(size_t)s * f + q];
+      gh_face_side(g, unn, __ldg(so + npad), __ldg(so + 2 * npad), sd);
+    } else {
+      sd.mag = sqrt(unn[0] * unn[0] + unn[1] * unn[1] + unn[2] * unn[2]);
+      const double inv = 1.0 / sd.mag;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) sd.n_lo[x] = sd.n_up[x] = unn[x] * inv;
+      sd.gamma2 = __ldg(so);
+      sd.speed[0] = 0.0;
+      sd.speed[1] = 0.0;
+      sd.speed[2] = 1.0;
+      sd.speed[3] = -1.0;
+    }
+  };
+  auto package = [&](const GhFaceSide& sd, const double* face, int q, int s, double (&pk)[13]) {
+    double g, pi, ph[3];
+    if constexpr (kSystem == 1) {
+      g = face[(size_t)s * f + q];
+      pi = face[(size_t)(10 + s) * f + q];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) ph[m] = face[(size_t)(20 + m + 3 * s) * f + q];
+    } else {
+      g = face[q];
+      pi = face[(size_t)f + q];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) ph[m] = face[(size_t)(2 + m) * f + q];
+    }
+    GhPairPackaged k;
+    gh_pair_package(sd, g, pi, ph, k);
+    pk[0] = k.v_g;
+    pk[1] = k.g2_v_g;
+    pk[2] = k.v_plus;
+    pk[3] = k.v_minus;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      pk[4 + m] = k.v_zero[m];
+      pk[7 + m] = k.v_plus * sd.n_lo[m];
+      pk[10 + m] = k.v_minus * sd.n_lo[m];
+    }
+  };
+  // component c of pair s in the [E][6][C][f] accumulator
+  auto comp = [&](int s, int c) {
+    if constexpr (kSystem == 1)
+      return c == 0 ? s : c == 1 ? 10 + s : 20 + (c - 2) + 3 * s;
+    else
+      return c;
+  };
+  const int pC = active ? face_point<N>(dc, qa, qb) : 0;
+  double* accC = a.acc + ((size_t)(ec * 6 + dc) * C) * f + tid;
+  if (coarse_completes && active)
+    for (int c = 0; c < C; ++c) accC[(size_t)c * f] = 0.0;
+  __syncthreads();
+
+#pragma unroll 1
+  for (int mi = 0; mi < nm; ++mi) {
+    if (!a.mortar_in_history[m0 + mi]) continue;
+    const int32_t* mt = a.mortars + 4 * (m0 + mi);
+    const int ef = mt[0], df = mt[1] & 7, sa = mt[2], sb = mt[3];
+    if (!coarse_completes && (ef < a.elem_begin || ef >= a.elem_end)) continue;
+    int fa = qa, fb = qb;
+    if (mt[1] >> 3) orient_face_point<N>(mt[1] >> 3, qa, qb, fa, fb);
+    const int qF = active ? fa + N * fb : 0;
+    const int pF = active ? face_point<N>(df, fa, fb) : 0;
+    const double* Pa = sP[sa];
+    const double* Pb = sP[sb];
+    const double* Ra = sR[sa];
+    const double* Rb = sR[sb];
+    double* accF = a.acc + ((size_t)(ef * 6 + df) * C) * f + qF;
+    if (!coarse_completes && active)
+      for (int c = 0; c < C; ++c) accF[(size_t)c * f] = 0.0;
+    // the coefficient list of the completing side against the other side's level
+    const int cls = a.level[coarse_completes ? ef : ec];
+    const LtsTerm* terms = a.terms + (size_t)cls * a.max_terms;
+#pragma unroll 1
+    for (int t = 0; t < a.nterms[cls]; ++t) {
+      const LtsTerm tm = terms[t];
+      const double* faceC = snapshot(ec, dc, coarse_completes ? tm.lslot : tm.rslot);
+      const double* faceF = snapshot(ef, df, coarse_completes ? tm.rslot : tm.lslot);
+      GhFaceSide sC, sFn;
+      if (active) {
+        make_side(ec, dc, pC, tid, faceC, sC);
+        make_side(ef, df, pF, qF, faceF, sFn);
+      }
+      __syncthreads();   // the previous term is done with sA
+      if (active) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) sA[13 + x][tid] = sC.speed[x];
+      }
+      const double liftC = active ? -0.5 * (double)(N * (N - 1)) * sC.mag : 0.0;
+      const double liftF = active ? -0.5 * (double)(N * (N - 1)) * sFn.mag : 0.0;
+      double spC[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+      for (int s = 0; s < NP; ++s) {
+        const int c_hi = s == 0 ? 17 : 13;
+        if (active) {
+          double pk[13];
+          package(sC, faceC, tid, s, pk);
+#pragma unroll
+          for (int c = 0; c < 13; ++c) sA[c][tid] = pk[c];
+        }
+        __syncthreads();
+        if (active) {
+          for (int c = 0; c < c_hi; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) v += Pa[qa * N + m] * sA[c][m + N * qb];
+            sB[c][tid] = v;
+          }
+        }
+        __syncthreads();
+        if (active) {
+          double pkC[13];
+#pragma unroll
+          for (int c = 0; c < 13; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) v += Pb[qb * N + m] * sB[c][qa + N * m];
+            pkC[c] = v;
+          }
+          if (s == 0) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              double v = 0.0;
+#pragma unroll
+              for (int m = 0; m < N; ++m) v += Pb[qb * N + m] * sB[13 + x][qa + N * m];
+              spC[x] = v;
+            }
+          }
+          double pkF[13], cc[5];
+          package(sFn, faceF, qF, s, pkF);
+          if (coarse_completes) {
+            pair_boundary_terms_packaged(spC, pkC, sFn.speed, pkF, cc);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) sE[c][tid] = cc[c];
+          } else {
+            pair_boundary_terms_packaged(sFn.speed, pkF, spC, pkC, cc);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) accF[(size_t)comp(s, c) * f] += tm.coef * (cc[c] * liftF);
+          }
+        }
+        __syncthreads();
+        if (!coarse_completes) continue;
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) v += Ra[qa * N + m] * sE[c][m + N * qb];
+            sF[c][tid] = v;
+          }
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) v += Rb[qb * N + m] * sF[c][qa + N * m];
+            accC[(size_t)comp(s, c) * f] += tm.coef * (v * liftC);
+          }
         }
       }
     }

@@ -164,6 +164,10 @@ struct LtsState {
   bool fused = false;
   double* buf[2] = {nullptr, nullptr};
   std::vector<int> parity;             // [nlevels] which buffer holds the level's state
+  uint8_t* in_history = nullptr;         // [E][6] faces kept in the boundary histories
+  uint8_t* mortar_in_history = nullptr;  // [n_mortars] (order of the context's mortar table)
+  int n_groups = 0;
+  std::vector<char> level_has_conforming, level_is_coarse_side, level_is_fine_side;
 };
 
 inline int mod(long long a, int m) { return (int)(((a % m) + m) % m); }
@@ -188,8 +192,7 @@ int evaluate_level(dgrhs_ctx* c, LtsState* s, int level, long long m, bool updat
   const int k = s->order;
   double* const keep = c->u;
   if (s->fused) c->u = s->buf[s->parity[level]];
-  int rc = ops->lts_snapshot(c, s->fh, s->level_dev, s->same_level_in_volume, s->depth,
-                             mod(m, s->depth), eb, ee);
+  int rc = ops->lts_snapshot(c, s->fh, s->in_history, s->depth, mod(m, s->depth), eb, ee);
   if (!rc && update && s->fused) {
     const auto coef = step_coefficients(s, level, m);
     dg::UpdateArgs up{};
@@ -201,10 +204,11 @@ int evaluate_level(dgrhs_ctx* c, LtsState* s, int level, long long m, bool updat
       up.v[j] = s->vol[mod(m - (k - 1) + j, k)];
     }
     up.c_new = coef[k - 1];
-    rc = ops->lts_evaluate(c, s->nbr_ext, s->vol[mod(m, k)], eb, ee, &up);
+    rc = ops->lts_evaluate(c, s->nbr_ext, s->mortar_in_history, s->vol[mod(m, k)], eb, ee, &up);
     s->parity[level] ^= 1;
   } else if (!rc) {
-    rc = ops->lts_evaluate(c, s->nbr_ext, s->vol[mod(m, k)], eb, ee, nullptr);
+    rc = ops->lts_evaluate(c, s->nbr_ext, s->mortar_in_history, s->vol[mod(m, k)], eb, ee,
+                           nullptr);
   }
   c->u = keep;
   return rc;
@@ -248,7 +252,7 @@ int complete_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
   a.elem_end = ee;
   a.acc = s->acc;
   a.u = u_level;
-  a.same_level_in_volume = s->same_level_in_volume;
+  a.in_history = s->in_history;
   std::vector<dg::LtsTerm> host((size_t)s->nlevels * s->max_terms);
   Ticks local;
   for (int i = k - 1; i >= 0; --i) local.push_back((m - i) * st);
@@ -284,6 +288,32 @@ int complete_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
   CU(cudaMemcpyAsync(s->terms_dev, host.data(), host.size() * sizeof(dg::LtsTerm),
                      cudaMemcpyHostToDevice, c->stream));
   // (pageable source: the copy is staged before the call returns)
+  if (s->level_has_conforming[level] && ops->lts_boundary(c, &a)) return 1;
+  if (s->level_is_coarse_side[level] || s->level_is_fine_side[level]) {
+    dg::LtsMortarArgs ma{};
+    ma.fh = s->fh;
+    ma.invjac = c->invjac;
+    ma.stat = c->stat;
+    ma.faces = c->mortar_faces;
+    ma.mortars = c->mortar_table;
+    ma.mortar_in_history = s->mortar_in_history;
+    ma.P = c->mortar_P;
+    ma.R = c->mortar_R;
+    ma.level = s->level_dev;
+    ma.terms = s->terms_dev;
+    for (int nl = 0; nl < dg::kLtsMaxLevels; ++nl) ma.nterms[nl] = a.nterms[nl];
+    ma.max_terms = s->max_terms;
+    ma.depth = s->depth;
+    ma.elem_begin = eb;
+    ma.elem_end = ee;
+    ma.acc = s->acc;
+    for (int role = 0; role < 2; ++role) {
+      if (!(role == 0 ? s->level_is_coarse_side[level] : s->level_is_fine_side[level])) continue;
+      ma.role = role;
+      if (ops->lts_mortar(c, &ma, s->n_groups)) return 1;
+    }
+  }
+  a.terms = nullptr;   // u += acc on the faces in the histories
   return ops->lts_boundary(c, &a);
 }
 
@@ -298,6 +328,8 @@ void dgrhs_internal_lts_free(dgrhs_ctx* c) {
   if (s->fh) cudaFree(s->fh);
   if (s->acc) cudaFree(s->acc);
   if (s->terms_dev) cudaFree(s->terms_dev);
+  if (s->in_history) cudaFree(s->in_history);
+  if (s->mortar_in_history) cudaFree(s->mortar_in_history);
   delete s;
   c->lts = nullptr;
 }
@@ -338,8 +370,10 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
   if (!(dt_coarse > 0.0)) return fail("time step must be positive");
   if (c->n_send > 0 || c->nccl_comm)
     return fail("local time stepping runs on one GPU (no halo exchange)");
-  if (c->n_bjorhus_faces > 0 || c->n_mortar_faces > 0 || c->n_pmortar_faces > 0)
-    return fail("local time stepping: Bjorhus faces and non-conforming mortars are not supported");
+  if (c->n_bjorhus_faces > 0 || c->n_pmortar_faces > 0)
+    return fail("local time stepping: Bjorhus faces and p-mortars are not supported");
+  if (c->n_mortar_faces != c->n_mortar_faces_local)
+    return fail("local time stepping: mortars with a remote side are not supported");
   if (c->mesh_v) return fail("local time stepping on a moving mesh is not supported");
   if (c->violations) return fail("local time stepping: DemandOutgoingCharSpeeds is not supported");
   if (c->filterF) return fail("local time stepping: the exponential filter is not supported");
@@ -370,9 +404,18 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
   s->t0 = t0;
   s->tick_size = dt_coarse / (double)(1LL << lmax);
   s->tick = 0;
-  // which levels meet at a face, and the largest step ratio across a face
+  // which levels meet at a face, the largest step ratio across a face, and the faces /
+  // mortars that are kept in the boundary histories
+  s->same_level_in_volume = c->lts_mode != 0;
   s->adjacent.assign(s->nlevels, std::vector<bool>(s->nlevels, false));
+  s->level_has_conforming.assign(s->nlevels, 0);
+  s->level_is_coarse_side.assign(s->nlevels, 0);
+  s->level_is_fine_side.assign(s->nlevels, 0);
   long long ratio = 1;
+  std::vector<uint8_t> hist((size_t)c->nelem * 6, 0);
+  const auto in_hist = [&](int e, int nb) {
+    return !(s->same_level_in_volume && levels[e] == levels[nb]);
+  };
   for (int e = 0; e < c->nelem; ++e)
     for (int d = 0; d < 6; ++d) {
       const int nb = c->nbr_host[(size_t)e * 6 + d];
@@ -380,7 +423,32 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
       if (nb >= c->nelem) return fail("local time stepping: ghost elements are not supported");
       s->adjacent[levels[e]][levels[nb]] = true;
       ratio = std::max(ratio, 1LL << std::abs(levels[e] - levels[nb]));
+      if (in_hist(e, nb)) {
+        hist[(size_t)e * 6 + d] = 1;
+        s->level_has_conforming[levels[e]] = 1;
+      }
     }
+  s->n_groups = (int)c->mortar_faces_host.size() / 4;
+  const int n_mortars = (int)c->mortar_table_host.size() / 4;
+  std::vector<uint8_t> mhist(std::max(n_mortars, 1), 0);
+  for (int g = 0; g < s->n_groups; ++g) {
+    const int32_t* fc = c->mortar_faces_host.data() + 4 * (size_t)g;
+    const int ec = fc[0], dc = fc[1];
+    for (int m = fc[2]; m < fc[2] + fc[3]; ++m) {
+      const int32_t* mt = c->mortar_table_host.data() + 4 * (size_t)m;
+      const int ef = mt[0], df = mt[1] & 7;
+      if (ec < 0 || ef < 0) return fail("local time stepping: mortars with a remote side");
+      s->adjacent[levels[ec]][levels[ef]] = true;
+      s->adjacent[levels[ef]][levels[ec]] = true;
+      ratio = std::max(ratio, 1LL << std::abs(levels[ec] - levels[ef]));
+      if (in_hist(ec, ef)) {
+        mhist[m] = 1;
+        hist[(size_t)ec * 6 + dc] = hist[(size_t)ef * 6 + df] = 1;
+        s->level_is_coarse_side[levels[ec]] = 1;
+        s->level_is_fine_side[levels[ef]] = 1;
+      }
+    }
+  }
   // a coarse element completes its step with the fine neighbour's last order - 1 + ratio
   // snapshots; one more slot so that the neighbour's next evaluation does not overwrite
   s->depth = order + (int)ratio;
@@ -396,7 +464,6 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
     if (dev_alloc(&p, c->state_len())) return 1;
     s->vol.push_back(p);
   }
-  s->same_level_in_volume = c->lts_mode != 0;
   s->fused = s->same_level_in_volume && c->fuse_update && order <= 4;
   s->parity.assign(s->nlevels, 0);
   if (s->fused) {
@@ -413,6 +480,13 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
     }
   CU(cudaMemcpy(s->nbr_ext, ext.data(), ext.size() * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(s->level_dev, levels, (size_t)c->nelem * 4, cudaMemcpyHostToDevice));
+  if (dev_alloc(&s->in_history, hist.size())) return 1;
+  if (dev_alloc(&s->mortar_in_history, mhist.size())) return 1;
+  CU(cudaMemcpy(s->in_history, hist.data(), hist.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->mortar_in_history, mhist.data(), mhist.size(), cudaMemcpyHostToDevice));
+  // correction slots of faces in the histories are never written by the face / mortar kernels
+  // of an evaluation: they must read zero (the volume kernel adds all six slots)
+  CU(cudaMemset(c->corr, 0, (size_t)c->nelem * 6 * c->C * c->N * c->N * sizeof(double)));
   return 0;
 }
 

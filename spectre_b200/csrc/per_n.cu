@@ -312,8 +312,8 @@ int launch_mesh_velocity_terms(dgrhs_ctx* c, double* dt, int eb, int ee) {
 // elements [eb, ee): the face kernel runs on a neighbour table whose internal faces are
 // marked "no correction"
 template <int N>
-int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, int eb, int ee,
-                        const dg::UpdateArgs* upd) {
+int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, const uint8_t* mortar_skip,
+                        double* dt, int eb, int ee, const dg::UpdateArgs* upd) {
   if (ee <= eb) return 0;
   dg::FaceArgs a{c->u, c->invjac, c->stat, nbr_external, c->nbr_face, c->halo_recv,
                  c->corr, ee, ee, 0, eb, nullptr, nullptr};
@@ -325,22 +325,40 @@ int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, double* dt, i
     dg::sw_face_kernel<N><<<blocks, 128, 0, c->stream>>>(a);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
+  // non-conforming mortars that are not in the boundary histories (both sides on this level)
+  if (c->n_mortar_faces > 0) {
+    dg::MortarArgs m{c->u, c->invjac, c->stat, c->corr, c->mortar_faces, c->mortar_table,
+                     c->mortar_P, c->mortar_R, c->halo_recv, 0, mortar_skip, eb, ee};
+    constexpr int msmem = dg::mortar_smem_bytes<N>();
+    constexpr int mT = (N * N + 31) / 32 * 32;
+    if (c->system == DGRHS_SYSTEM_GH) {
+      auto k = dg::mortar_kernel<N, 1>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+      k<<<c->n_mortar_faces, mT, msmem, c->stream>>>(m);
+    } else {
+      auto k = dg::mortar_kernel<N, 0>;
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+      k<<<c->n_mortar_faces, mT, msmem, c->stream>>>(m);
+    }
+    dgrhs_internal_count_launch();
+    CU(cudaGetLastError());
+  }
   c->pdl_volume = false;
   return launch_volume<N>(c, dt, eb, ee, true, upd ? *upd : dg::UpdateArgs{});
 }
 
 template <int N>
-int launch_lts_snapshot(dgrhs_ctx* c, double* fh, const int32_t* level, int same_level_in_volume,
-                        int depth, int slot, int eb, int ee) {
+int launch_lts_snapshot(dgrhs_ctx* c, double* fh, const uint8_t* in_history, int depth, int slot,
+                        int eb, int ee) {
   if (ee <= eb) return 0;
   const long long total = (long long)(ee - eb) * 6 * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)
-    dg::lts_snapshot_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(
-        c->u, fh, c->nbr, level, same_level_in_volume, depth, slot, eb, ee);
+    dg::lts_snapshot_kernel<N, 50><<<blocks, 128, 0, c->stream>>>(c->u, fh, in_history, depth,
+                                                                  slot, eb, ee);
   else
-    dg::lts_snapshot_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(
-        c->u, fh, c->nbr, level, same_level_in_volume, depth, slot, eb, ee);
+    dg::lts_snapshot_kernel<N, 5><<<blocks, 128, 0, c->stream>>>(c->u, fh, in_history, depth,
+                                                                 slot, eb, ee);
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   return 0;
@@ -350,17 +368,39 @@ template <int N>
 int launch_lts_boundary(dgrhs_ctx* c, const dg::LtsBoundaryArgs* a) {
   const int ne = a->elem_end - a->elem_begin;
   if (ne <= 0) return 0;
-  const long long total = (long long)ne * 6 * N * N;
-  const int blocks = (int)((total + 127) / 128);
-  if (c->system == DGRHS_SYSTEM_GH)
-    dg::gh_lts_boundary_kernel<N><<<blocks, 128, 0, c->stream>>>(*a);
-  else
-    dg::sw_lts_boundary_kernel<N><<<blocks, 128, 0, c->stream>>>(*a);
-  dgrhs_internal_count_launch();
-  CU(cudaGetLastError());
+  if (a->terms) {   // conforming faces in the histories (nullptr: only the final add)
+    const long long total = (long long)ne * 6 * N * N;
+    const int blocks = (int)((total + 127) / 128);
+    if (c->system == DGRHS_SYSTEM_GH)
+      dg::gh_lts_boundary_kernel<N><<<blocks, 128, 0, c->stream>>>(*a);
+    else
+      dg::sw_lts_boundary_kernel<N><<<blocks, 128, 0, c->stream>>>(*a);
+    dgrhs_internal_count_launch();
+    CU(cudaGetLastError());
+    return 0;
+  }
   const long long pts = (long long)ne * c->n;
   dg::lts_add_kernel<N><<<(int)((pts + 255) / 256), 256, 0, c->stream>>>(
-      a->u, a->acc, c->nbr, a->level, a->same_level_in_volume, c->C, a->elem_begin, a->elem_end);
+      a->u, a->acc, a->in_history, c->C, a->elem_begin, a->elem_end);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int launch_lts_mortar(dgrhs_ctx* c, const dg::LtsMortarArgs* a, int n_groups) {
+  if (n_groups <= 0) return 0;
+  constexpr int msmem = dg::mortar_smem_bytes<N>();
+  constexpr int mT = (N * N + 31) / 32 * 32;
+  if (c->system == DGRHS_SYSTEM_GH) {
+    auto k = dg::lts_mortar_kernel<N, 1>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+    k<<<n_groups, mT, msmem, c->stream>>>(*a);
+  } else {
+    auto k = dg::lts_mortar_kernel<N, 0>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+    k<<<n_groups, mT, msmem, c->stream>>>(*a);
+  }
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   return 0;
@@ -377,7 +417,8 @@ static const DgNOps kOps = {launch_faces<DG_N>,
                      launch_mesh_velocity_terms<DG_N>,
                      launch_lts_evaluate<DG_N>,
                      launch_lts_snapshot<DG_N>,
-                     launch_lts_boundary<DG_N>};
+                     launch_lts_boundary<DG_N>,
+                     launch_lts_mortar<DG_N>};
 
 }  // namespace
 

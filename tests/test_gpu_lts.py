@@ -260,3 +260,74 @@ def test_cpp_lts_example_matches_oracle():
     for name, (a, b) in zip(("Psi", "Pi", "Phi"), ((0, 1), (1, 2), (2, 5))):
         want = np.sqrt(np.sum((ev.u[:, a:b] - exact[:, a:b]) ** 2) / npts)
         assert got[f"Error({name})"] == pytest.approx(want, rel=1e-8)
+
+
+def _refined_problem(system, N, refined, rng, rule):
+    """h-refined periodic brick with its mortar table, elements sorted by the step-size level
+    that `rule(element size)` gives"""
+    L = 2 * np.pi if system == lib.SYSTEM_SCALAR_WAVE else 1.0
+    rb = domain.RefinedBrick([0, 0, 0], [L] * 3, [1, 1, 1], N, refined)
+    x, nb, mt = rb.coords(), rb.neighbors(), np.array(rb.mortars())
+    size = x[:, 0].max(axis=1) - x[:, 0].min(axis=1)
+    levels = np.array([rule(sz / size.max()) for sz in size])
+    perm, nbp = hlts.order_by_level(levels, nb)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    mtp = mt.copy()
+    mtp[:, 0], mtp[:, 2] = inv[mt[:, 0]], inv[mt[:, 2]]
+    J = rb.inverse_jacobian() + 0.05 * rng.uniform(-1, 1, (rb.n_elements, 9, N ** 3))
+    return rb, x[perm], J[perm], nbp, mtp.astype(np.int32), levels[perm]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("system,N,order,rule", [
+    ("sw", 4, 3, "fine"), ("sw", 6, 2, "fine"), ("sw", 5, 3, "mixed"), ("gh", 4, 3, "fine"),
+    ("gh", 6, 3, "mixed"), ("gh", 3, 4, "coarse")])
+def test_lts_with_mortars(system, N, order, rule, mode):
+    """h-refinement with local time stepping: 'fine' = the children of the refined cells take
+    two steps per step of the unrefined elements (the canonical set-up), 'coarse' = the other
+    way round, 'mixed' = three levels that cut through the refined cells, so that one coarse
+    face has mortars inside and outside the boundary histories"""
+    sysid = lib.SYSTEM_GH if system == "gh" else lib.SYSTEM_SCALAR_WAVE
+    rng = np.random.default_rng(17 * N + order)
+    rules = {"fine": lambda s: int(s < 0.75), "coarse": lambda s: int(s > 0.75)}
+    if rule == "mixed":
+        counter = iter(range(10 ** 6))
+        rules["mixed"] = lambda s: (next(counter) % 2) + int(s < 0.75)
+    rb, x, J, nb, mt, levels = _refined_problem(sysid, N, [(0, 0, 0), (1, 1, 0)], rng, rules[rule])
+    assert len(mt) > 0 and len(set(levels.tolist())) >= 2
+    nelem = len(levels)
+    stride = 2 ** (levels.max() - levels)
+    if system == "gh":
+        dt = 4e-4
+        tick = dt / 2 ** levels.max()
+        noise = 1e-2 * rng.uniform(-1, 1, (nelem, 50, N ** 3))
+        wave = lambda xe, t: analytic.gauge_wave(xe, 0.1 + t)
+        stat = rng.uniform(-1, 1, (nelem, 3, N ** 3))
+        blocks = GH_BLOCKS
+    else:
+        dt = 4e-3
+        tick = dt / 2 ** levels.max()
+        noise = 0.05 * rng.uniform(-1, 1, (nelem, 5, N ** 3))
+        wave = analytic.plane_wave
+        stat = rng.uniform(0, 1, (nelem, 1, N ** 3))
+        blocks = SW_BLOCKS
+
+    def past(j):
+        return noise + np.stack([wave(x[e], -j * stride[e] * tick) for e in range(nelem)])
+    u0 = noise + np.stack([wave(x[e], 0.0) for e in range(nelem)])
+    ctx = lib.Context(sysid, N, nelem)
+    ctx.set_geometry(J, None, nb)
+    ctx.set_mortars(mt)
+    ctx.set_static_fields(stat)
+    ctx.set_state(u0)
+    ctx.lts_init(order, 0.0, dt, levels, same_level_faces_in_volume_history=bool(mode))
+    for j in range(1, order):
+        ctx.lts_set_past_state(j, past(j))
+    ev = olts.LtsEvolution(0 if system == "sw" else 1, N, J, stat, nb, levels, order, 0.0, dt, u0,
+                           past, mortars=mt)
+    for _ in range(2):
+        ctx.lts_take_coarse_steps(1)
+        ev.take_coarse_steps(1)
+        assert _relerr(ctx.get_state(), ev.u, blocks) < TOL
+    ctx.close()
