@@ -153,7 +153,7 @@ class LtsEvolution:
 
     def __init__(self, system, N, invjac, static_fields, nbr, levels, order, t0, dt_coarse,
                  u0, past_states, gauge_params=orc.GAUGE_HARMONIC, ext_u=None, nbr_dir=None,
-                 face_perm=None, static_face=None, mortars=None):
+                 face_perm=None, static_face=None, mortars=None, post_update=None):
         self.system, self.N, self.k = system, N, int(order)
         self.J, self.stat = invjac, static_fields
         self.nbr = np.asarray(nbr, dtype=np.int64)
@@ -181,6 +181,8 @@ class LtsEvolution:
                                     for sz in (orc.MORTAR_LOWER_HALF, orc.MORTAR_UPPER_HALF)]
         # external faces keep their boundary condition inside the "volume" part
         self.nbr_ext = np.where((self.nbr >= 0) | self.hanging, -1, self.nbr).astype(np.int32)
+        # action after the step of an element (dg::Actions::Filter in the LTS action list)
+        self.post = post_update if post_update is not None else (lambda v: v)
         self.u = u0.copy()
         self.tick = 0
         self.vol_hist = [[] for _ in range(self.nelem)]      # (tick, dt_u)
@@ -328,7 +330,7 @@ class LtsEvolution:
             active = np.nonzero(T % self.stride == 0)[0]
             self._evaluate(active, self.u, T)
             ending = np.nonzero((T + 1) % self.stride == 0)[0]
-            new = {e: self._finalize(e, T + 1) for e in ending}
+            new = {e: self.post(self._finalize(e, T + 1)) for e in ending}
             for e, v in new.items():
                 self.u[e] = v
             self.tick = T + 1

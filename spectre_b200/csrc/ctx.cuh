@@ -221,6 +221,8 @@ struct DgNOps {
                       int eb, int ee);
   int (*lts_boundary)(dgrhs_ctx* c, const dg::LtsBoundaryArgs* a);
   int (*lts_mortar)(dgrhs_ctx* c, const dg::LtsMortarArgs* a, int n_groups);
+  // exponential filter on ntiles component blocks starting at u (a range of elements)
+  int (*filter_range)(dgrhs_ctx* c, double* u, int ntiles);
 };
 const DgNOps* dgrhs_nops(int N);  // nullptr for an unsupported N
 

@@ -317,6 +317,17 @@ int complete_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
   return ops->lts_boundary(c, &a);
 }
 
+// the step of `level` m -> m + 1 with the action that follows it in the reference's LTS
+// action list: dg::Actions::Filter on the elements that took the step
+int complete_level_and_filter(dgrhs_ctx* c, LtsState* s, int level, long long m) {
+  if (complete_level(c, s, level, m)) return 1;
+  if (!c->filterF) return 0;
+  const int eb = s->level_begin[level], ee = s->level_begin[level + 1];
+  double* const u_level = s->fused ? s->buf[s->parity[level]] : c->u;
+  return dgrhs_nops(c->N)->filter_range(c, u_level + (size_t)eb * c->C * c->npad,
+                                        (ee - eb) * c->C);
+}
+
 }  // namespace
 
 void dgrhs_internal_lts_free(dgrhs_ctx* c) {
@@ -376,7 +387,6 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
     return fail("local time stepping: mortars with a remote side are not supported");
   if (c->mesh_v) return fail("local time stepping on a moving mesh is not supported");
   if (c->violations) return fail("local time stepping: DemandOutgoingCharSpeeds is not supported");
-  if (c->filterF) return fail("local time stepping: the exponential filter is not supported");
   if (c->gauge == DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE)
     return fail("local time stepping: time-dependent gauge fields are not supported");
   if (c->nbr_host.empty()) return fail("dgrhs_lts_init needs dgrhs_set_geometry first");
@@ -532,7 +542,7 @@ int dgrhs_lts_take_ticks(dgrhs_ctx* c, long long n_ticks) {
       if (T % s->stride[l] == 0 && evaluate_level(c, s, l, T / s->stride[l], true)) return 1;
     for (int l = 0; l < s->nlevels; ++l)
       if ((T + 1) % s->stride[l] == 0 &&
-          complete_level(c, s, l, (T + 1) / s->stride[l] - 1))
+          complete_level_and_filter(c, s, l, (T + 1) / s->stride[l] - 1))
         return 1;
     s->tick = T + 1;
   }

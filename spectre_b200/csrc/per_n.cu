@@ -243,10 +243,11 @@ int launch_volume_p(dgrhs_ctx* c, double* dt, int eb, int ee, bool with_corr,
 }
 
 template <int N>
-int launch_filter(dgrhs_ctx* c) {
+int launch_filter_range(dgrhs_ctx* c, double* u, int ntiles) {
+  if (ntiles <= 0) return 0;
   dg::FilterArgs a;
-  a.u = c->u;
-  a.ntiles = c->nelem * c->C;
+  a.u = u;
+  a.ntiles = ntiles;
   for (int k = 0; k < N * N; ++k) a.Fm[k] = c->filterF_host[k];
   using F = dg::FilterCfg<N>;
   const int ngroups = (a.ntiles + F::G - 1) / F::G;
@@ -257,6 +258,11 @@ int launch_filter(dgrhs_ctx* c) {
   dgrhs_internal_count_launch();
   CU(cudaGetLastError());
   return 0;
+}
+
+template <int N>
+int launch_filter(dgrhs_ctx* c) {
+  return launch_filter_range<N>(c, c->u, c->nelem * c->C);
 }
 
 // H_a = -Gamma_a of a given state and its spatial derivatives (AnalyticChristoffel
@@ -418,7 +424,8 @@ static const DgNOps kOps = {launch_faces<DG_N>,
                      launch_lts_evaluate<DG_N>,
                      launch_lts_snapshot<DG_N>,
                      launch_lts_boundary<DG_N>,
-                     launch_lts_mortar<DG_N>};
+                     launch_lts_mortar<DG_N>,
+                     launch_filter_range<DG_N>};
 
 }  // namespace
 

@@ -331,3 +331,42 @@ def test_lts_with_mortars(system, N, order, rule, mode):
         ev.take_coarse_steps(1)
         assert _relerr(ctx.get_state(), ev.u, blocks) < TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gh_lts_with_exponential_filter(mode):
+    """dg::Actions::Filter after every element's step (KerrSchild.yaml's filter), two levels"""
+    N, order, dt = 6, 3, 4e-4
+    rng = np.random.default_rng(23)
+    brick = domain.Brick([0, 0, 0], [1.0] * 3, [1, 1, 1], N)
+    levels, perm, nb = _brick_levels(brick, brick.coords(), lambda c: int(c[1] > 0.5))
+    x = brick.coords()[perm]
+    J = _curved_jacobian(rng, brick)[perm]
+    stat = rng.uniform(-1, 1, (brick.n_elements, 3, brick.n))
+    noise = 1e-2 * rng.uniform(-1, 1, (brick.n_elements, 50, brick.n))
+    stride = 2 ** (levels.max() - levels)
+
+    def past(j):
+        return noise + np.stack([analytic.gauge_wave(x[e], 0.1 - j * stride[e] * dt / 2)
+                                 for e in range(len(levels))])
+    u0 = noise + analytic.gauge_wave(x, 0.1)
+    alpha, half_power = 36.0, 4      # a low half power: the filter changes every mode visibly
+    ctx = lib.Context(lib.SYSTEM_GH, N, brick.n_elements)
+    ctx.set_geometry(J, None, nb)
+    ctx.set_static_fields(stat)
+    ctx.set_exponential_filter(True, alpha, half_power)
+    ctx.set_state(u0)
+    ctx.lts_init(order, 0.0, dt, levels, same_level_faces_in_volume_history=bool(mode))
+    for j in range(1, order):
+        ctx.lts_set_past_state(j, past(j))
+    F = orc.exponential_filter_matrix(N, alpha, half_power)
+    ev = olts.LtsEvolution(1, N, J, stat, nb, levels, order, 0.0, dt, u0, past,
+                           post_update=lambda v: orc.apply_filter(N, v, F))
+    plain = olts.LtsEvolution(1, N, J, stat, nb, levels, order, 0.0, dt, u0, past)
+    for _ in range(2):
+        ctx.lts_take_coarse_steps(1)
+        ev.take_coarse_steps(1)
+        assert _relerr(ctx.get_state(), ev.u, GH_BLOCKS) < TOL
+    plain.take_coarse_steps(2)
+    assert _relerr(plain.u, ev.u, GH_BLOCKS) > 1e-6     # the filter matters
+    ctx.close()
