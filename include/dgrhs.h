@@ -136,9 +136,9 @@ int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_st
  * TimeStepperTestUtils::initialize_history: after dgrhs_set_state(u(t0)) call
  * dgrhs_lts_set_past_state for j = 1 .. order-1 with, for every element, its state at
  * t0 - j * (its own step).  One GPU; conforming faces (aligned or oriented) and non-conforming
- * 2:1 mortars (dgrhs_set_mortars), ghost (DirichletAnalytic) boundary conditions with static
- * data, static gauge fields, the exponential filter after each element's step, no Bjorhus
- * faces, no p-mortars.  Time runs in ticks of the
+ * 2:1 mortars (dgrhs_set_mortars); ghost (DirichletAnalytic) boundary conditions with static
+ * data, ConstraintPreservingBjorhus and DemandOutgoingCharSpeeds faces; static gauge fields;
+ * the exponential filter after each element's step; no p-mortars, no moving mesh.  Time runs in ticks of the
  * finest step; the state is complete (all elements at the same time) after a multiple of
  * dgrhs_lts_ticks_per_coarse_step ticks. */
 int dgrhs_lts_init(dgrhs_ctx* ctx, int order, double t0, double dt_coarse,

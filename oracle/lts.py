@@ -153,7 +153,7 @@ class LtsEvolution:
 
     def __init__(self, system, N, invjac, static_fields, nbr, levels, order, t0, dt_coarse,
                  u0, past_states, gauge_params=orc.GAUGE_HARMONIC, ext_u=None, nbr_dir=None,
-                 face_perm=None, static_face=None, mortars=None, post_update=None):
+                 face_perm=None, static_face=None, mortars=None, post_update=None, coords=None):
         self.system, self.N, self.k = system, N, int(order)
         self.J, self.stat = invjac, static_fields
         self.nbr = np.asarray(nbr, dtype=np.int64)
@@ -164,6 +164,7 @@ class LtsEvolution:
         self.tick_size = dt_coarse / 2 ** self.lmax
         self.t0 = t0
         self.gp, self.ext_u = gauge_params, ext_u
+        self.coords = coords       # for Bjorhus external faces / coordinate-dependent gauges
         self.nbr_dir = nbr_dir if nbr_dir is not None else np.tile(
             np.array([1, 0, 3, 2, 5, 4]), (self.nelem, 1))
         self.face_perm = face_perm if face_perm is not None else np.zeros((self.nelem, 6), int)
@@ -204,6 +205,7 @@ class LtsEvolution:
             self.nelem, ticks)
         dt = orc.dg_rhs(self.system, self.N, u_all[elems], self.J[elems], self.stat[elems],
                         self.nbr_ext[elems], gauge_params=self.gp, ext_u=self.ext_u,
+                        coords=None if self.coords is None else self.coords[elems],
                         nbr_dir=np.ascontiguousarray(self.nbr_dir[elems], dtype=np.int32),
                         face_perm=np.ascontiguousarray(self.face_perm[elems], dtype=np.int32))
         for a, e in enumerate(elems):

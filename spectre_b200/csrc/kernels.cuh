@@ -1066,6 +1066,10 @@ constexpr int32_t kHangingFace = INT32_MIN;
 constexpr int32_t kBjorhusFace = INT32_MIN + 1;          // Type ConstraintPreserving
 constexpr int32_t kBjorhusPhysicalFace = INT32_MIN + 2;  // Type ConstraintPreservingPhysical
 constexpr int32_t kPMortarFace = INT32_MIN + 3;  // neighbour with a different N (pmortar_kernel)
+// local time stepping: an internal face whose correction comes from the boundary histories;
+// the face kernels write a zero correction (like an external face without a boundary
+// condition, but without the DemandOutgoingCharSpeeds check)
+constexpr int32_t kLtsHistoryFace = INT32_MIN + 4;
 
 // neighbour-side face coordinates of our face point (qa, qb)
 template <int N>
@@ -1131,13 +1135,13 @@ __global__ void __launch_bounds__(128, DG_FACE_MIN_BLOCKS) gh_face_kernel(FaceAr
   const double sign_n = (nd & 1) ? 1.0 : -1.0;
   const int p_own = face_point<N>(d, qa, qb);
   const double* __restrict__ uo = a.u + (size_t)e * 50 * npad + p_own;
-  if (nb == -1) {
+  if (nb == -1 || nb == kLtsHistoryFace) {
     // no boundary correction on this face (outflow)
 #pragma unroll 1
     for (int s = 0; s < 10; ++s)
 #pragma unroll
       for (int c = 0; c < 5; ++c) corr[((size_t)s * 30 + c) * f] = 0.0;
-    if (a.violations) {
+    if (a.violations && nb == -1) {
       double g[10], unn[3];
       const double* jo = a.invjac + (size_t)e * 9 * npad + p_own;
 #pragma unroll
@@ -1267,7 +1271,7 @@ __global__ void __launch_bounds__(128) sw_face_kernel(FaceArgs a) {
   bool two_sided;
   if (!face_task(a, e, d, nb, nd, two_sided)) return;
   double* __restrict__ corr = a.corr + ((size_t)e * 6 + d) * 5 * f + q;
-  if (nb == -1) {
+  if (nb == -1 || nb == kLtsHistoryFace) {
 #pragma unroll
     for (int c = 0; c < 5; ++c) corr[(size_t)c * f] = 0.0;
     return;
@@ -2323,6 +2327,7 @@ struct BjorhusArgs {
   double* corr;
   const int32_t* faces;  // [n][3] = element, direction, physical (0/1)
   DampedHarmonicParams dh;
+  int elem_begin, elem_end;  // elem_end > 0: only the faces of these elements (lts.cu)
 };
 
 // Everything that does not depend on N: volume time derivative at the point,
@@ -2448,6 +2453,7 @@ __global__ void __launch_bounds__((N * N + 31) / 32 * 32)
   const int tid = threadIdx.x;
   if (tid >= f) return;
   const int e = a.faces[3 * blockIdx.x], d = a.faces[3 * blockIdx.x + 1];
+  if (a.elem_end > 0 && (e < a.elem_begin || e >= a.elem_end)) return;
   const bool physical = a.faces[3 * blockIdx.x + 2] != 0;
   const int qa = tid % N, qb = tid / N;
   const int p = face_point<N>(d, qa, qb);

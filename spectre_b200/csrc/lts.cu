@@ -381,12 +381,10 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
   if (!(dt_coarse > 0.0)) return fail("time step must be positive");
   if (c->n_send > 0 || c->nccl_comm)
     return fail("local time stepping runs on one GPU (no halo exchange)");
-  if (c->n_bjorhus_faces > 0 || c->n_pmortar_faces > 0)
-    return fail("local time stepping: Bjorhus faces and p-mortars are not supported");
+  if (c->n_pmortar_faces > 0) return fail("local time stepping: p-mortars are not supported");
   if (c->n_mortar_faces != c->n_mortar_faces_local)
     return fail("local time stepping: mortars with a remote side are not supported");
   if (c->mesh_v) return fail("local time stepping on a moving mesh is not supported");
-  if (c->violations) return fail("local time stepping: DemandOutgoingCharSpeeds is not supported");
   if (c->gauge == DGRHS_GAUGE_ANALYTIC_GAUGE_WAVE)
     return fail("local time stepping: time-dependent gauge fields are not supported");
   if (c->nbr_host.empty()) return fail("dgrhs_lts_init needs dgrhs_set_geometry first");
@@ -486,7 +484,8 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
   for (int e = 0; e < c->nelem; ++e)
     for (int d = 0; d < 6; ++d) {
       int32_t& v = ext[(size_t)e * 6 + d];
-      if (v >= 0 && !(s->same_level_in_volume && levels[v] == levels[e])) v = -1;
+      if (v >= 0 && !(s->same_level_in_volume && levels[v] == levels[e]))
+        v = dg::kLtsHistoryFace;
     }
   CU(cudaMemcpy(s->nbr_ext, ext.data(), ext.size() * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(s->level_dev, levels, (size_t)c->nelem * 4, cudaMemcpyHostToDevice));

@@ -10,6 +10,25 @@
 
 namespace {
 
+// ConstraintPreservingBjorhus faces (of the elements [eb, ee) if ee > 0)
+template <int N>
+int launch_bjorhus(dgrhs_ctx* c, cudaStream_t stream, int eb, int ee) {
+  dg::BjorhusArgs b{c->u, c->invjac, c->stat, c->gH, c->gdH, c->coords, c->D, c->corr,
+                    c->bjorhus_faces, {}, eb, ee};
+  int gauge_mode = 1;
+  if (c->gauge == DGRHS_GAUGE_HARMONIC) gauge_mode = 0;
+  if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
+    const double* p = c->gauge_params;
+    b.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
+    gauge_mode = 2;
+  }
+  constexpr int bT = (N * N + 31) / 32 * 32;
+  dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, stream>>>(b, gauge_mode);
+  dgrhs_internal_count_launch();
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <int N>
 int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   if (ee <= eb) return 0;
@@ -44,19 +63,7 @@ int launch_faces(dgrhs_ctx* c, int eb, int ee) {
   if (bjorhus_now) {
     CU(cudaEventRecord(c->aux_fork, c->stream));
     CU(cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
-    dg::BjorhusArgs b{c->u, c->invjac, c->stat, c->gH, c->gdH, c->coords, c->D, c->corr,
-                      c->bjorhus_faces, {}};
-    int gauge_mode = 1;
-    if (c->gauge == DGRHS_GAUGE_HARMONIC) gauge_mode = 0;
-    if (c->gauge == DGRHS_GAUGE_DAMPED_HARMONIC) {
-      const double* p = c->gauge_params;
-      b.dh = {p[0], p[1], p[2], p[3], (int)p[4], (int)p[5], (int)p[6]};
-      gauge_mode = 2;
-    }
-    constexpr int bT = (N * N + 31) / 32 * 32;
-    dg::gh_bjorhus_kernel<N><<<c->n_bjorhus_faces, bT, 0, c->aux_stream>>>(b, gauge_mode);
-    dgrhs_internal_count_launch();
-    CU(cudaGetLastError());
+    if (launch_bjorhus<N>(c, c->aux_stream, 0, 0)) return 1;
     CU(cudaEventRecord(c->aux_join, c->aux_stream));
   }
   const long long total = (long long)(c->nelem - a.elem_begin) * 6 * N * N;
@@ -322,7 +329,8 @@ int launch_lts_evaluate(dgrhs_ctx* c, const int32_t* nbr_external, const uint8_t
                         double* dt, int eb, int ee, const dg::UpdateArgs* upd) {
   if (ee <= eb) return 0;
   dg::FaceArgs a{c->u, c->invjac, c->stat, nbr_external, c->nbr_face, c->halo_recv,
-                 c->corr, ee, ee, 0, eb, nullptr, nullptr};
+                 c->corr, ee, ee, 0, eb, c->violations, nullptr};
+  if (c->n_bjorhus_faces > 0 && launch_bjorhus<N>(c, c->stream, eb, ee)) return 1;
   const long long total = (long long)(ee - eb) * 6 * N * N;
   const int blocks = (int)((total + 127) / 128);
   if (c->system == DGRHS_SYSTEM_GH)

@@ -370,3 +370,51 @@ def test_gh_lts_with_exponential_filter(mode):
     plain.take_coarse_steps(2)
     assert _relerr(plain.u, ev.u, GH_BLOCKS) > 1e-6     # the filter matters
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gh_lts_with_the_single_black_hole_boundary_conditions(mode):
+    """the boundary conditions of EvolveGhSingleBlackHole (an LTS executable in the reference):
+    DemandOutgoingCharSpeeds on the excision sphere, ConstraintPreservingBjorhus (physical) on
+    the outer sphere -- external boundary conditions are part of the time derivative that
+    enters the element's own history (ComputeTimeDerivative applies them); two radial layers
+    with different steps"""
+    from tests.test_gpu_shell import _gauge_fields
+    N, order, dt = 5, 3, 2e-3
+    problem = evolution.gh_kerr_schild_shell_problem(
+        (0, 1), N, inner_radius=1.9, outer_radius=6.0, order="radial",
+        inner_boundary="DemandOutgoingCharSpeeds", outer_boundary="ConstraintPreservingPhysical")
+    ev0 = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, 3, 1e-4)
+    ctx, part = ev0.ctx, ev0.part
+    assert (part.local_neighbors == lib.BJORHUS_PHYSICAL).sum() == 6 and not part.external_faces
+    ids = part.global_ids
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    r = np.sqrt((x ** 2).sum(axis=1)).mean(axis=1)
+    levels = (r > np.median(r)).astype(np.int32)
+    assert np.all(np.diff(levels) >= 0) and levels.max() == 1
+    ua = problem.u0(ids, 0.0)
+    u0 = ua + 1e-3 * np.random.default_rng(6).uniform(-1, 1, ua.shape)
+    H, dH = _gauge_fields(N, x, J, ua)
+    ctx.set_state(u0)
+    ctx.lts_init(order, 0.0, dt, levels, same_level_faces_in_volume_history=bool(mode))
+    for j in range(1, order):
+        ctx.lts_set_past_state(j, u0)
+    ev = olts.LtsEvolution(1, N, J, np.concatenate([stat, H, dH], axis=1), part.local_neighbors,
+                           levels, order, 0.0, dt, u0, lambda j: u0,
+                           gauge_params=orc.GAUGE_GIVEN, nbr_dir=part.local_neighbor_direction,
+                           face_perm=part.local_face_permutation, coords=x)
+    for _ in range(2):
+        ctx.lts_take_coarse_steps(1)
+        ev.take_coarse_steps(1)
+        assert _relerr(ctx.get_state(), ev.u, GH_BLOCKS) < TOL
+    ctx.check_outgoing_char_speeds()
+    # without the Bjorhus condition the outer layer would evolve differently
+    free = olts.LtsEvolution(1, N, J, np.concatenate([stat, H, dH], axis=1),
+                             np.where(part.local_neighbors == lib.BJORHUS_PHYSICAL, -1,
+                                      part.local_neighbors), levels, order, 0.0, dt, u0,
+                             lambda j: u0, gauge_params=orc.GAUGE_GIVEN,
+                             nbr_dir=part.local_neighbor_direction,
+                             face_perm=part.local_face_permutation, coords=x)
+    free.take_coarse_steps(2)
+    assert _relerr(free.u, ev.u, GH_BLOCKS) > 1e-9
+    ctx.close()
