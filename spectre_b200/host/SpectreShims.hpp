@@ -1051,6 +1051,30 @@ class DgEvolution {
   }
   void apply_exponential_filter() { check(dgrhs_apply_exponential_filter(ctx_)); }
   double time() const { return dgrhs_time(ctx_); }
+  // Adams-Bashforth local time stepping with fixed step sizes dt_coarse / 2^levels[e] (the
+  // LTS executables' take_step + ApplyLtsBoundaryCorrections, ApplyBoundaryCorrections.hpp:
+  // 1142-1192): past_states[j - 1] holds, for every element, its state at t0 - j * (its step)
+  void start_local_time_stepping(size_t order, double t0, double dt_coarse,
+                                 const std::vector<int32_t>& levels,
+                                 const std::vector<const double*>& past_states) {
+    if (past_states.size() + 1 != order)
+      throw std::runtime_error("start_local_time_stepping needs order - 1 past states");
+    check(dgrhs_lts_init(ctx_, static_cast<int>(order), t0, dt_coarse, levels.data()));
+    for (size_t j = 1; j < order; ++j)
+      check(dgrhs_lts_set_past_state(ctx_, static_cast<int>(j), past_states[j - 1]));
+  }
+  void take_lts_coarse_steps(long long n) {
+    long long per_step = 0;
+    check(dgrhs_lts_ticks_per_coarse_step(ctx_, &per_step));
+    check(dgrhs_lts_take_ticks(ctx_, n * per_step));
+  }
+  double lts_time() const {
+    double t = 0.0;
+    check(dgrhs_lts_time(ctx_, &t, nullptr));
+    return t;
+  }
+  // moving mesh: inertial mesh velocity of the current time (nullptr: static mesh)
+  void set_mesh_velocity(const double* mesh_velocity) { check(dgrhs_set_mesh_velocity(ctx_, mesh_velocity)); }
   dgrhs_ctx* handle() { return ctx_; }
 
  private:

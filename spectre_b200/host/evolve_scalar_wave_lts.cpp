@@ -71,17 +71,15 @@ int main(int argc, char** argv) {
     std::vector<double> u, exact;
     solution(0.0, 0, &u);
     evolution.set_variables(u.data());
-    dgrhs_ctx* ctx = evolution.handle();
-    check(dgrhs_lts_init(ctx, order, 0.0, dt_coarse, levels.data()));
+    std::vector<std::vector<double>> past(order - 1);
+    std::vector<const double*> past_ptr;
     for (int j = 1; j < order; ++j) {
-      solution(0.0, j, &exact);
-      check(dgrhs_lts_set_past_state(ctx, j, exact.data()));
+      solution(0.0, j, &past[j - 1]);
+      past_ptr.push_back(past[j - 1].data());
     }
-    long long per_coarse = 0;
-    check(dgrhs_lts_ticks_per_coarse_step(ctx, &per_coarse));
-    check(dgrhs_lts_take_ticks(ctx, coarse_steps * per_coarse));
-    double time = 0.0;
-    check(dgrhs_lts_time(ctx, &time, nullptr));
+    evolution.start_local_time_stepping(order, 0.0, dt_coarse, levels, past_ptr);
+    evolution.take_lts_coarse_steps(coarse_steps);
+    const double time = evolution.lts_time();
     evolution.get_variables(u.data());
     solution(time, 0, &exact);
     const char* names[3] = {"Psi", "Pi", "Phi"};
