@@ -551,19 +551,23 @@ class GpuRun:
             # batch i+1 uploads while batch i steps and downloads (PCIe is full duplex);
             # every batch still crosses the bus both ways inside the timed region
             serial = e2e["value"]
-            ev_b = self.new_evolution()
-            ev_b.take_steps(args.warmup)          # self-start outside the timed region
-            host_b = torch.empty(state.size, dtype=torch.float64, pin_memory=True)
-            host_b_np = host_b.numpy().reshape(state.shape)
-            host_b_np[...] = state
-            lanes = [(ev, host_np), (ev_b, host_b_np)]
-            k_pipe = 2 * k_e2e
+            n_lanes = max(2, args.e2e_lanes)
+            lanes = [(ev, host_np)]
+            for _ in range(n_lanes - 1):
+                ev_x = self.new_evolution()
+                ev_x.take_steps(args.warmup)          # self-start outside the timed region
+                host_x = torch.empty(state.size, dtype=torch.float64, pin_memory=True)
+                host_x_np = host_x.numpy().reshape(state.shape)
+                host_x_np[...] = state
+                lanes.append((ev_x, host_x_np))
+                self._pinned = getattr(self, "_pinned", []) + [host_x]
+            k_pipe = n_lanes * k_e2e
             for e, _ in lanes:
                 e.ctx.synchronize()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(k_pipe):
-                e, h = lanes[i % 2]
+                e, h = lanes[i % n_lanes]
                 e.ctx.synchronize()               # this lane's previous batch is back on the host
                 e.ctx.set_state_async(h)
                 e.take_steps(1)
@@ -571,14 +575,17 @@ class GpuRun:
             for e, _ in lanes:
                 e.ctx.synchronize()
             el = time.perf_counter() - t0
-            assert np.isfinite(host_np).all() and np.isfinite(host_b_np).all()
+            assert all(np.isfinite(h).all() for _, h in lanes)
             e2e.update({"value": total_points * k_pipe / el, "steps": k_pipe,
-                        "serial_value": serial,
+                        "serial_value": serial, "lanes": n_lanes,
                         "what": "per batch: dgrhs_set_state_async(pinned host) + one AB3 step + "
-                                "dgrhs_get_state_async, two contexts double-buffered so one "
-                                "batch uploads while the other steps and downloads; "
-                                "serial_value = one context, blocking calls"})
-            ev_b.ctx.close()
+                                "dgrhs_get_state_async, %d contexts in rotation so that one "
+                                "batch uploads while another steps and a third downloads (PCIe "
+                                "is full duplex); every batch crosses the bus both ways inside "
+                                "the timed region; serial_value = one context, blocking calls"
+                                % n_lanes})
+            for e, _ in lanes[1:]:
+                e.ctx.close()
         return e2e
 
     def verify(self, steps_total):
@@ -650,6 +657,8 @@ def main():
                     help="skip the local-time-stepping side measurement (N = 1 only)")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the configs[1] measurement reported as `secondary`")
+    ap.add_argument("--e2e-lanes", type=int, default=3,
+                    help="contexts in rotation in the pipelined e2e measurement (N = 1)")
     ap.add_argument("--no-e2e-pipeline", action="store_true",
                     help="measure e2e with blocking calls on one context only")
     ap.add_argument("--outer-boundary", default="DirichletAnalytic",
