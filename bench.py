@@ -547,8 +547,8 @@ class GpuRun:
                "steps": k_e2e,
                "what": "dgrhs_set_state(pinned host) + one AB3 step + dgrhs_get_state per step"}
         if world == 1 and not args.no_e2e_pipeline:
-            # the same three calls per batch in their stream-ordered form on two contexts:
-            # batch i+1 uploads while batch i steps and downloads (PCIe is full duplex);
+            # the same three calls per batch in their stream-ordered form on several contexts
+            # in rotation: one batch uploads while another steps or downloads (PCIe is full duplex);
             # every batch still crosses the bus both ways inside the timed region
             serial = e2e["value"]
             n_lanes = max(2, args.e2e_lanes)
