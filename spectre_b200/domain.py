@@ -781,3 +781,25 @@ class Partition:
             self.send_map[slot] = (le, d)
             self.send_counts[peer] += 1
         assert len(send) == len(recv) or world > 1  # symmetric on periodic bricks
+
+    def reorder(self, perm):
+        """Single-rank partition: put the local elements into the order perm (new -> old), e.g.
+        sorted by step-size level for local time stepping; every table follows."""
+        if self.world != 1:
+            raise ValueError("Partition.reorder: single-rank partitions only")
+        perm = np.asarray(perm)
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(perm))
+        self.global_ids = self.global_ids[perm]
+        nb = self.local_neighbors[perm].copy()
+        m = nb >= 0
+        nb[m] = inv[nb[m]]
+        self.local_neighbors = nb.astype(np.int32)
+        self.local_neighbor_direction = self.local_neighbor_direction[perm]
+        self.local_face_permutation = self.local_face_permutation[perm]
+        if len(self.local_mortars):
+            lm = self.local_mortars.copy()
+            lm[:, 0], lm[:, 2] = inv[lm[:, 0]], inv[lm[:, 2]]
+            self.local_mortars = lm.astype(np.int32)
+        self.external_faces = [(int(inv[le]), d, slot) for le, d, slot in self.external_faces]
+        self.send_map = np.zeros((0, 2), dtype=np.int32)

@@ -256,7 +256,9 @@ class Evolution:
 
     def __init__(self, problem, stepper=lib.STEPPER_ADAMS_BASHFORTH, order=3, dt=2e-4,
                  t0=0.0, gauge=lib.GAUGE_HARMONIC, gauge_params=(), device=0, world=1, rank=0,
-                 process_group=None, native_exchange=True):
+                 process_group=None, native_exchange=True, element_order=None):
+        """element_order(partition, problem) -> permutation (new -> old) of the local elements
+        (single rank), e.g. sorted by step-size level for local time stepping."""
         self.world, self.rank = world, rank
         self.native_exchange = False
         self.problem = problem
@@ -265,6 +267,8 @@ class Evolution:
                                      neighbor_direction=problem.orientations[0],
                                      face_permutation=problem.orientations[1],
                                      mortars=problem.mortars)
+        if element_order is not None:
+            self.part.reorder(element_order(self.part, problem))
         ids = self.part.global_ids
         self.ctx = lib.Context(problem.system, problem.N, self.part.n_local,
                                self.part.n_ghost, device)

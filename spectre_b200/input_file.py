@@ -116,7 +116,7 @@ class Run:
 
     LTS_EXECUTABLES = ("EvolveGhSingleBlackHole", "EvolveGhBinaryBlackHole")
 
-    def __init__(self, metadata, options, allow_gts_fixed_step=False):
+    def __init__(self, metadata, options, allow_gts_fixed_step=False, lts_fixed_levels=False):
         self.metadata, self.options = metadata or {}, options
         exe = str(self.metadata.get("Executable", ""))
         self.system = lib.SYSTEM_SCALAR_WAVE if "ScalarWave" in exe else lib.SYSTEM_GH
@@ -133,7 +133,23 @@ class Run:
             self.step_choosers_ignored = [list(c)[0] if isinstance(c, dict) else str(c)
                                           for c in ev["StepChoosers"]]
         self.lts_executable = any(exe.startswith(name) for name in self.LTS_EXECUTABLES)
-        if (self.lts_executable or self.step_choosers_ignored) and not allow_gts_fixed_step:
+        # local time stepping with the step sizes fixed at the start (run_lts): what the
+        # reference's LTS executable starts with -- the largest step slab / 2^n below
+        # InitialTimeStep and, if listed, below the ElementSizeCfl goal -- without the
+        # later step-size changes of the choosers (LimitIncrease, ErrorControl, ...)
+        self.lts_fixed_levels = bool(lts_fixed_levels)
+        self.slab_size = float(ev.get("InitialSlabSize", self.dt))
+        self.element_size_cfl = None
+        for ch in ev.get("StepChoosers") or []:
+            if isinstance(ch, dict) and "ElementSizeCfl" in ch:
+                self.element_size_cfl = float(ch["ElementSizeCfl"]["SafetyFactor"])
+        if self.lts_fixed_levels:
+            if name != "AdamsBashforth":
+                raise InputFileError("local time stepping is implemented for AdamsBashforth")
+            self.step_choosers_ignored = [c for c in self.step_choosers_ignored
+                                          if c != "ElementSizeCfl"]
+        if (self.lts_executable or self.step_choosers_ignored) and not allow_gts_fixed_step \
+                and not self.lts_fixed_levels:
             why = []
             if self.lts_executable:
                 why.append(f"executable {exe} uses local time stepping")
@@ -446,12 +462,57 @@ class Run:
         return out
 
 
-def load(path, allow_gts_fixed_step=False):
+    def run_lts(self, n_slabs=None, device=0):
+        """Evolve with Adams-Bashforth local time stepping, the element steps fixed at the
+        start (see __init__), and return [(slab, time, {name: L2 error norm})] observed at the
+        slab boundaries (all elements are at the same time there)."""
+        from . import lts
+        if n_slabs is None:
+            if self.n_steps is None:
+                raise InputFileError("no Completion trigger with a specified slab or time")
+            n_slabs = max(1, self.n_steps // self.steps_per_slab)
+        if self.gauge not in (lib.GAUGE_HARMONIC, lib.GAUGE_DAMPED_HARMONIC):
+            raise InputFileError("local time stepping: this gauge is not implemented")
+        problem = self.problem()
+        n_el = problem.brick.n_elements
+        ev = lts.LtsEvolution(
+            problem, self.order, self.slab_size, self.t0,
+            step_goal=None if self.element_size_cfl is not None else np.full(n_el, self.dt),
+            safety_factor=self.element_size_cfl or 1.0, max_step=self.dt, past="analytic",
+            gauge=self.gauge, gauge_params=self.gauge_params, device=device,
+            filter_params=self.filter)
+        names = ("Psi", "Pi", "Phi") if self.system == lib.SYSTEM_SCALAR_WAVE else \
+            ("SpacetimeMetric", "Pi", "Phi")
+        blocks = ((0, 1), (1, 2), (2, 5)) if self.system == lib.SYSTEM_SCALAR_WAVE else \
+            ((0, 10), (10, 20), (20, 50))
+        out = []
+        per_slab = int(round(self.slab_size / ev.dt_coarse))
+
+        def observe_now(k):
+            ids, state = ev.state()
+            exact = problem.u0(ids, ev.time)
+            npts = state.shape[0] * state.shape[2]
+            norms = {f"Error({nm})": float(np.sqrt(np.sum((state[:, a:b] - exact[:, a:b]) ** 2)
+                                                   / npts)) for nm, (a, b) in zip(names, blocks)}
+            out.append((k, ev.time, norms))
+        observe_now(0)
+        for k in range(n_slabs):
+            ev.take_coarse_steps(per_slab)
+            observe_now(k + 1)
+        if self.outgoing:
+            ev.ctx.check_outgoing_char_speeds()
+        self.lts_levels = ev.levels
+        self.lts_dt_coarse = ev.dt_coarse
+        ev.ctx.close()
+        return out
+
+
+def load(path, allow_gts_fixed_step=False, lts_fixed_levels=False):
     with open(path) as f:
         docs = list(yaml.safe_load_all(f))
     if len(docs) == 1:
-        return Run({}, docs[0], allow_gts_fixed_step)
-    return Run(docs[0], docs[1], allow_gts_fixed_step)
+        return Run({}, docs[0], allow_gts_fixed_step, lts_fixed_levels)
+    return Run(docs[0], docs[1], allow_gts_fixed_step, lts_fixed_levels)
 
 
 def main():
@@ -461,8 +522,22 @@ def main():
     ap.add_argument("--allow-gts-fixed-step", action="store_true",
                     help="run an LTS / step-chooser input file with fixed global steps (NOT "
                          "numerically equivalent to the reference executable)")
+    ap.add_argument("--lts-fixed-levels", action="store_true",
+                    help="run with Adams-Bashforth local time stepping, the element steps fixed "
+                         "at what InitialTimeStep / ElementSizeCfl give at the start (the other "
+                         "step choosers are ignored and printed)")
     args = ap.parse_args()
-    run = load(args.input_file, args.allow_gts_fixed_step)
+    run = load(args.input_file, args.allow_gts_fixed_step, args.lts_fixed_levels)
+    if args.lts_fixed_levels:
+        print(f"local time stepping with fixed steps; ignored StepChoosers: "
+              f"{run.step_choosers_ignored or 'none'} -- the reference's run changes its steps "
+              "with them")
+        for slab, t, norms in run.run_lts():
+            print(f"slab {slab:6d}  t = {t:.6f}  " +
+                  "  ".join(f"{k} = {v:.6e}" for k, v in norms.items()))
+        print("steps:", {int(l): f"{run.lts_dt_coarse / 2 ** int(l):.6g}"
+                         for l in sorted(set(run.lts_levels.tolist()))})
+        return
     if run.lts_executable or run.step_choosers_ignored:
         print("WARNING: fixed global time steps; ignored StepChoosers: "
               f"{run.step_choosers_ignored or 'none'}; LTS executable: {run.lts_executable} "

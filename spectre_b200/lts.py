@@ -107,3 +107,88 @@ def element_size_cfl(element_sizes, speed, stable_step, safety_factor):
     """StepChoosers::ElementSizeCfl (Time/StepChoosers/ElementSizeCfl.hpp:76-92): the step
     goal safety_factor * stable_step * min_d(size_d) / (speed * 3) of every element."""
     return safety_factor * stable_step * np.min(element_sizes, axis=1) / (np.asarray(speed) * 3)
+
+
+class LtsEvolution:
+    """Adams-Bashforth local time stepping of a `evolution.Problem` on one GPU: the elements are
+    put into the order of their step-size levels, the library's context is set up like the GTS
+    `evolution.Evolution` (geometry, orientations, mortars, boundary conditions, gauge), the
+    histories start from the problem's analytic data at the elements' own past step times
+    (past="analytic") or from a GTS phase with the finest step (past="gts").
+
+    step_goal: per-element upper bound of the step (array in the problem's element order), or
+    None for StepChoosers::ElementSizeCfl with `safety_factor`, evaluated once at t0; every
+    element takes the largest step slab / 2^n that does not exceed min(step_goal, max_step)."""
+
+    def __init__(self, problem, order, slab, t0=0.0, step_goal=None, safety_factor=0.5,
+                 max_step=None, past="analytic", gauge=None, gauge_params=(), device=0,
+                 filter_params=None):
+        from . import evolution, lib
+        self.problem, self.order, self.t0 = problem, int(order), float(t0)
+        box = {}
+
+        def order_elements(part, prob):
+            ids = part.global_ids
+            if step_goal is None:
+                if prob.system != lib.SYSTEM_GH:
+                    speed = np.ones(len(ids))       # ScalarWave: unit characteristic speed
+                else:
+                    speed = gh_largest_characteristic_speed(prob.u0(ids, t0),
+                                                            prob.static(ids)[:, 1])
+                stable = lib.stepper_properties(lib.STEPPER_ADAMS_BASHFORTH, self.order)[3]
+                goal = element_size_cfl(size_of_element(prob.brick, ids), speed, stable,
+                                        safety_factor)
+            else:
+                goal = np.asarray(step_goal, dtype=float)[ids]
+            if max_step is not None:
+                goal = np.minimum(goal, max_step)
+            n = levels_from_step_limit(goal, slab, max_level=60)     # step = slab / 2^n
+            box["n_min"] = int(n.min())
+            levels = n - box["n_min"]
+            if levels.max() > 7:
+                raise ValueError("more than eight step-size levels")
+            perm = np.argsort(levels, kind="stable")
+            box["levels"] = levels[perm].astype(np.int32)
+            return perm
+        kw = {} if gauge is None else {"gauge": gauge, "gauge_params": gauge_params}
+        self.dt_coarse = None
+        self.ev = evolution.Evolution(problem, lib.STEPPER_ADAMS_BASHFORTH, self.order,
+                                      slab, t0, device=device, element_order=order_elements, **kw)
+        self.levels = box["levels"]
+        self.dt_coarse = slab / 2 ** box["n_min"]
+        self.ctx, self.part = self.ev.ctx, self.ev.part
+        if filter_params:
+            self.ctx.set_exponential_filter(True, *filter_params)
+        ids = self.part.global_ids
+        if past == "gts":
+            self.ctx.set_stepper(lib.STEPPER_ADAMS_BASHFORTH, self.order, t0,
+                                 self.dt_coarse / 2 ** int(self.levels.max()))
+            self.t_start = start_from_gts(self.ctx, self.order, t0, self.dt_coarse, self.levels)
+        else:
+            self.ctx.lts_init(self.order, t0, self.dt_coarse, self.levels)
+            for j in range(1, self.order):
+                u = np.empty((len(ids), self.ctx.n_vars, self.ctx.n))
+                for lv in sorted(set(self.levels.tolist())):
+                    sel = self.levels == lv
+                    u[sel] = problem.u0(ids[sel], t0 - j * self.dt_coarse / 2 ** lv)
+                self.ctx.lts_set_past_state(j, u)
+            self.t_start = t0
+
+    @property
+    def time(self):
+        return self.ctx.lts_time()[0]
+
+    def take_coarse_steps(self, n):
+        if self.part.external_faces and self.problem.boundary_time_dependent:
+            # time-dependent ghost data: refresh at every tick of the finest step
+            per = 2 ** int(self.levels.max())
+            for _ in range(n * per):
+                self.ctx.set_boundary_ghost_data(
+                    self.part.n_recv, self.ev.boundary_ghost_data(self.problem, self.time))
+                self.ctx.lts_take_ticks(1)
+        else:
+            self.ctx.lts_take_coarse_steps(n)
+
+    def state(self):
+        """(global element ids, state) in the library's element order"""
+        return self.part.global_ids, self.ctx.get_state()

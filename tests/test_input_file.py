@@ -315,3 +315,76 @@ def test_binary_compact_object_creator_options(tmp_path):
                           "envelope radius is too small")):
         with pytest.raises(input_file.InputFileError, match=msg):
             load_with(**changes)
+
+
+@pytest.mark.gpu
+def test_run_kerr_schild_with_local_time_stepping(tmp_path):
+    """KerrSchild.yaml belongs to an LTS executable: --lts-fixed-levels runs it through the LTS
+    entry points with the steps the reference starts with (largest slab / 2^n below
+    InitialTimeStep and the ElementSizeCfl goal; the later step changes of LimitIncrease /
+    ErrorControl are not reproduced and are reported as ignored).  The original file has one
+    step-size level; a thick-shell variant of it (outer radius 30.4 M, four radial layers) has
+    several.  The oracle's LtsEvolution of the same set-up gives the same error norms."""
+    import yaml
+    from oracle import lts as olts
+    from oracle import oracle as orc
+    from spectre_b200 import evolution
+    from spectre_b200 import lts as hlts
+    path = _reference_input("GeneralizedHarmonic/KerrSchild.yaml")
+    ks = input_file.load(path, lts_fixed_levels=True)
+    assert ks.step_choosers_ignored == ["LimitIncrease", "ErrorControl"]
+    obs = ks.run_lts()
+    assert [o[0] for o in obs] == [0, 1, 2, 3] and obs[-1][1] == pytest.approx(0.003)
+    assert set(ks.lts_levels.tolist()) == {0} and ks.lts_dt_coarse == pytest.approx(1.25e-4)
+    assert all(np.isfinite(v) and v < 0.2 for v in obs[-1][2].values())
+    # thick shell: several levels
+    with open(path) as f:
+        meta, opts = list(yaml.safe_load_all(f))
+    sph = opts["DomainCreator"]["Sphere"]
+    sph["OuterRadius"] = 30.4
+    sph["InitialRefinement"] = [0, 0, 2]
+    opts["Evolution"]["InitialTimeStep"] = 0.1     # the ElementSizeCfl goals lie below it
+    opts["Evolution"]["InitialSlabSize"] = 0.1
+    thick = tmp_path / "KerrSchildThick.yaml"
+    with open(thick, "w") as f:
+        yaml.safe_dump_all([meta, opts], f)
+    run = input_file.load(str(thick), lts_fixed_levels=True)
+    obs = run.run_lts(n_slabs=2)
+    levels = run.lts_levels
+    assert len(set(levels.tolist())) >= 2 and np.all(np.diff(levels) >= 0)
+    assert all(np.isfinite(v) and v < 0.2 for v in obs[-1][2].values())
+    # the oracle on the same elements, levels and past states
+    problem = run.problem()
+    lev = hlts.LtsEvolution.__new__(hlts.LtsEvolution)   # only for its element order
+    part = domain.Partition(problem.neighbors, 1, 0, boundary_slots=problem.dirichlet_analytic,
+                            neighbor_direction=problem.orientations[0],
+                            face_permutation=problem.orientations[1], mortars=problem.mortars)
+    ids0 = part.global_ids
+    speed = hlts.gh_largest_characteristic_speed(problem.u0(ids0, 0.0), problem.static(ids0)[:, 1])
+    stable = lib.stepper_properties(lib.STEPPER_ADAMS_BASHFORTH, run.order)[3]
+    goal = np.minimum(hlts.element_size_cfl(hlts.size_of_element(problem.brick, ids0), speed,
+                                            stable, run.element_size_cfl), run.dt)
+    n = hlts.levels_from_step_limit(goal, run.slab_size, max_level=60)
+    part.reorder(np.argsort(n - n.min(), kind="stable"))
+    ids, N = part.global_ids, problem.N
+    np.testing.assert_array_equal(np.sort(n - n.min()), levels)
+    x, J, stat = problem.coords(ids), problem.inverse_jacobian(ids), problem.static(ids)
+    u0 = problem.u0(ids, 0.0)
+    H = np.zeros((len(ids), 4, N ** 3))
+    dH = np.zeros((len(ids), 16, N ** 3))
+    for e in range(len(ids)):
+        H[e], dH[e] = orc.analytic_christoffel_gauge(N, u0[e], J[e])
+    ext = evolution.boundary_ghost_data(problem, part, 0.0, 55)[:, :50]
+    F = orc.exponential_filter_matrix(N, *run.filter)
+    ev = olts.LtsEvolution(1, N, J, np.concatenate([stat, H, dH], axis=1), part.local_neighbors,
+                           levels, run.order, 0.0, run.lts_dt_coarse, u0, lambda j: u0,
+                           gauge_params=orc.GAUGE_GIVEN, ext_u=ext,
+                           nbr_dir=part.local_neighbor_direction,
+                           face_perm=part.local_face_permutation,
+                           post_update=lambda v: orc.apply_filter(N, v, F))
+    ev.take_coarse_steps(2 * int(round(run.slab_size / run.lts_dt_coarse)))
+    assert ev.time() == pytest.approx(obs[-1][1], rel=1e-13)
+    npts = u0.shape[0] * u0.shape[2]
+    for nm, (a, b) in zip(("SpacetimeMetric", "Pi", "Phi"), ((0, 10), (10, 20), (20, 50))):
+        want = float(np.sqrt(np.sum((ev.u[:, a:b] - u0[:, a:b]) ** 2) / npts))
+        assert obs[-1][2][f"Error({nm})"] == pytest.approx(want, rel=1e-8, abs=1e-15), nm
