@@ -273,3 +273,28 @@ def test_lts_with_mortars_fine_elements_take_half_steps():
     ev_f.take_coarse_steps(8)
     err_f = np.max(np.abs(ev_f.u - exact))
     assert err < 3 * err_f + 1e-6 and err < 5e-3
+
+
+def test_partition_reorder_keeps_the_connectivity():
+    """Partition.reorder (elements sorted by step-size level): neighbours, orientations,
+    mortars and boundary slots name the same faces as before"""
+    from spectre_b200 import domain
+    rb = domain.RefinedBrick([0, 0, 0], [1, 1, 1], [1, 1, 1], 3, [(0, 0, 0)],
+                             periodic=(True, True, False))
+    part0 = domain.Partition(rb.neighbors(), 1, 0, boundary_slots=True, mortars=rb.mortars())
+    part = domain.Partition(rb.neighbors(), 1, 0, boundary_slots=True, mortars=rb.mortars())
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(part.n_local)
+    part.reorder(perm)
+    old_of = perm                                  # new -> old
+    np.testing.assert_array_equal(part.global_ids, part0.global_ids[perm])
+    for new in range(part.n_local):
+        for d in range(6):
+            a, b = part.local_neighbors[new, d], part0.local_neighbors[old_of[new], d]
+            assert (a < 0 and a == b) or (a >= 0 and old_of[a] == b)
+    for row, row0 in zip(part.local_mortars, part0.local_mortars):
+        assert (old_of[row[0]], row[1], old_of[row[2]], row[3], row[4], row[5]) == tuple(row0)
+    assert sorted((int(old_of[le]), d, s) for le, d, s in part.external_faces) == \
+        sorted(part0.external_faces)
+    with pytest.raises(ValueError):
+        domain.Partition(rb.neighbors(), 2, 0, mortars=rb.mortars()).reorder(perm[:4])
