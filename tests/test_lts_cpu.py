@@ -68,9 +68,25 @@ def test_three_to_one_order_2():
 
 
 def test_unaligned_order_2():
-    # Test_AdamsLts.cpp:685-700 (first case)
-    _check(lts.lts_coefficients([1, 3, 4], [2, 3, 5], 3, 4, 2),
+    # Test_AdamsLts.cpp:685-725
+    a, b = [1, 3, 4], [2, 3, 5]
+    _check(lts.lts_coefficients(a, b, 3, 4, 2),
            {(1, 2): -1.0 / 4.0, (3, 2): -1.0 / 4.0, (3, 3): 3.0 / 2.0})
+    _check(lts.lts_coefficients(a, b, 4, 6, 2),
+           {(3, 3): -1.0 / 2.0, (3, 5): -3.0 / 2.0, (4, 2): -3.0 / 2.0, (4, 3): 11.0 / 4.0,
+            (4, 5): 11.0 / 4.0})
+    _check(lts.lts_coefficients(b, a, 3, 5, 2),
+           {(2, 1): -1.0 / 4.0, (2, 3): -1.0 / 4.0, (2, 4): -3.0 / 2.0, (3, 3): 1.0, (3, 4): 3.0})
+    _check(lts.lts_coefficients(b, a, 5, 6, 2),
+           {(3, 4): -1.0 / 4.0, (5, 3): -3.0 / 2.0, (5, 4): 11.0 / 4.0})
+
+
+def test_self_start_history_order_4():
+    # Test_AdamsLts.cpp:778-795: the history after self-start is not sorted in time (the
+    # values at 2 and 3 come from the self-start slab and precede those at 0 and 1)
+    steps = [2, 3, 0, 1]
+    _check(lts.lts_coefficients(steps, steps, 1, 2, 4),
+           {(2, 2): 13.0 / 24.0, (3, 3): -1.0 / 24.0, (0, 0): -1.0 / 24.0, (1, 1): 13.0 / 24.0})
 
 
 @pytest.mark.parametrize("order", [2, 3, 4])
@@ -159,7 +175,9 @@ def test_library_lts_coefficients_match_the_oracle_and_the_reference():
     cases = [([0, 1, 2], [0, 1, 2], 2, 3, 3, 3, 3), ([0, 1, 2], [0], 2, 3, 3, 1, 3),
              ([-8, -4, 0], [-4, -2, 0, 2], 0, 4, 3, 3, 3),
              ([-4, -2, 0, 2], [-8, -4, 0], 2, 4, 3, 3, 3), ([-2, 0], [-1, 0], 0, 1, 2, 2, 2),
-             ([-3, 0], [-1, 0, 1, 2], 0, 3, 2, 2, 2), ([1, 3, 4], [2, 3, 5], 3, 4, 2, 2, 2)]
+             ([-3, 0], [-1, 0, 1, 2], 0, 3, 2, 2, 2), ([1, 3, 4], [2, 3, 5], 3, 4, 2, 2, 2),
+             ([1, 3, 4], [2, 3, 5], 4, 6, 2, 2, 2), ([2, 3, 5], [1, 3, 4], 3, 5, 2, 2, 2),
+             ([2, 3, 5], [1, 3, 4], 5, 6, 2, 2, 2), ([2, 3, 0, 1], [2, 3, 0, 1], 1, 2, 4, 4, 4)]
     for k in range(1, 9):
         for r in (2, 4, 8):
             coarse = [r * i for i in range(-(k - 1), 1)]
