@@ -113,7 +113,7 @@ int dgrhs_set_neighbor_orientations(dgrhs_ctx* ctx, const int32_t* neighbor_dire
 int dgrhs_set_static_fields(dgrhs_ctx* ctx, const double* fields, int ncomp);
 
 /* ---- Local time stepping ---------------------------------------------
- * TimeSteppers::adams_lts::lts_coefficients for explicit (Adams-Bashforth) schemes
+ * TimeSteppers::adams_lts::lts_coefficients, explicit (Adams-Bashforth) schemes
  * (src/Time/TimeSteppers/AdamsLts.cpp:330-437): the nonzero terms of the boundary
  * contribution to the local side's step from start_tick to end_tick.  Times are integer ticks
  * of tick_size after time_origin, in the order of insertion into the boundary history
@@ -125,6 +125,18 @@ int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_st
                                  long long end_tick, double time_origin, double tick_size,
                                  int max_terms, int* n_terms, int* local_index,
                                  int* remote_index, double* coefficients);
+/* The same with the scheme types of AdamsLts.hpp:84-89: *_implicit != 0 selects an
+ * Adams-Moulton (implicit) scheme for that side / for the small steps.  An id is the step id
+ * at ticks[i] when substep_sizes[i] == 0 (or substep_sizes == NULL), else the substep
+ * (predictor) id of the step from ticks[i] to ticks[i] + substep_sizes[i], listed after its
+ * step id like BoundaryHistory holds it. */
+int dgrhs_adams_lts_coefficients_general(
+    int local_implicit, int local_order, int remote_implicit, int remote_order,
+    int small_step_implicit, int small_step_order, int n_local, const long long* local_ticks,
+    const long long* local_substep_sizes, int n_remote, const long long* remote_ticks,
+    const long long* remote_substep_sizes, long long start_tick, long long end_tick,
+    double time_origin, double tick_size, int max_terms, int* n_terms, int* local_index,
+    int* remote_index, double* coefficients);
 /* Adams-Bashforth local time stepping with fixed step sizes dt_coarse / 2^levels[e]
  * (levels ascending in the element order: coarse steps first), replacing the action pair
  * UpdateU + ApplyLtsBoundaryCorrections (Actions/UpdateU.hpp:44-120,

@@ -65,20 +65,62 @@ def _lagrange_exact(control, x):
     return out
 
 
-def _relevant(times, end, order):
-    """AdamsLts.cpp:173-206 (find_relevant_ids, explicit scheme): the `order` most recent
-    entries before `end`, by position (the times need not be sorted during self-start)"""
-    used_end = len(times)
-    while used_end > 0 and not times[used_end - 1] < end:
+def _exact_time(entry):
+    """adams_lts::exact_substep_time (AdamsLts.cpp:29-38): a step id (t, 0) is at t, the
+    substep id (t, size) of the step that starts at t is at its end t + size"""
+    return entry[0] + entry[1]
+
+
+def _steps_of(entries):
+    """the BoundaryHistory view of a flat list of ids: [(step entry, its substep entry or
+    None)] in insertion order"""
+    steps = []
+    for en in entries:
+        if en[1] == 0:
+            steps.append([en, None])
+        else:
+            assert steps and steps[-1][0][0] == en[0], "substep without its step"
+            steps[-1][1] = en
+    return steps
+
+
+def _relevant(entries, end, order, implicit=False):
+    """AdamsLts.cpp:173-206 (find_relevant_ids): the most recent step ids before `end`, by
+    position (the times need not be sorted during self-start) -- `order` of them for an
+    explicit scheme, order - 1 plus the predictor value (substep) of the last one for an
+    implicit scheme"""
+    steps = _steps_of(entries)
+    used_end = len(steps)
+    while used_end > 0 and not steps[used_end - 1][0][0] < end:
         used_end -= 1
-    assert used_end >= order, "Insufficient past data."
-    return list(times[used_end - order:used_end])
+    past = order - (1 if implicit else 0)
+    assert used_end >= past, "Insufficient past data."
+    ids = [st[0] for st in steps[used_end - past:used_end]]
+    if implicit:
+        assert steps[used_end - 1][1] is not None, "Must have substep data for implicit stepping."
+        ids.append(steps[used_end - 1][1])
+    return ids
 
 
-def _merge_to_small_steps(local, remote, small_order):
-    """AdamsLts.cpp:214-277 for explicit schemes: the most recent values of the union"""
-    out = []
+def _merge_to_small_steps(local, remote, local_implicit, remote_implicit, small_order,
+                          small_implicit):
+    """AdamsLts.cpp:214-277: the most recent values of the union of the control times, without
+    the values that are only used for interpolation"""
     li, ri = len(local) - 1, len(remote) - 1
+    if not small_implicit:
+        # don't use implicit interpolation points for an explicit step
+        if local_implicit:
+            li -= 1
+        if remote_implicit:
+            ri -= 1
+    elif local_implicit and remote_implicit:
+        # two times after the small step, one from each side: one of them (if they differ)
+        # belongs to a later small step
+        if local[li] < remote[ri]:
+            ri -= 1
+        else:
+            li -= 1
+    out = []
     for _ in range(small_order):
         if li < 0:
             assert ri >= 0, "Ran out of data"
@@ -97,48 +139,60 @@ def _merge_to_small_steps(local, remote, small_order):
     return out[::-1]
 
 
+def _as_entries(times):
+    return [(Fr(t[0]), Fr(t[1])) if isinstance(t, tuple) else (Fr(t), Fr(0)) for t in times]
+
+
 def lts_coefficients(local_times, remote_times, start, end, local_order, remote_order=None,
-                     small_order=None, exact=False):
-    """{(local time, remote time): coefficient} of the boundary contribution to the local
-    side's step from `start` to `end` (AdamsLts.cpp:330-437).  Times: integers or Fractions
-    in insertion order; explicit (Adams-Bashforth) schemes of the given orders."""
+                     small_order=None, exact=False, local_implicit=False, remote_implicit=False,
+                     small_implicit=False):
+    """{(local id, remote id): coefficient} of the boundary contribution to the local side's
+    step from `start` to `end` (AdamsLts.cpp:330-437).  Ids in insertion order: a number t is
+    the step id at t, a pair (t, size) the substep (predictor) id of the step from t to
+    t + size (needed by the implicit, Adams-Moulton, schemes); integers or Fractions.  In the
+    result a step id is keyed by its time, a substep id by the pair."""
     remote_order = local_order if remote_order is None else remote_order
     small_order = local_order if small_order is None else small_order
-    local_times = [Fr(t) for t in local_times]
-    remote_times = [Fr(t) for t in remote_times]
+    local_entries, remote_entries = _as_entries(local_times), _as_entries(remote_times)
     start, end = Fr(start), Fr(end)
     if start == end:
         return {}
+    key = lambda en: en[0] if en[1] == 0 else en
     coefs = {}
     small_end = end
     while True:
-        lids = _relevant(local_times, small_end, local_order)
-        rids = _relevant(remote_times, small_end, remote_order)
-        if not coefs and small_order == local_order == remote_order and lids == rids:
+        lids = _relevant(local_entries, small_end, local_order, local_implicit)
+        rids = _relevant(remote_entries, small_end, remote_order, remote_implicit)
+        if not coefs and (small_order, small_implicit) == (local_order, local_implicit) == \
+                (remote_order, remote_implicit) and lids == rids:
             # no local time stepping at this boundary (lts_coefficients_for_gts)
-            coefs = {(t, t): c for t, c in zip(lids, _ab_exact(lids, start, end))}
+            ct = [_exact_time(en) for en in lids]
+            coefs = {(key(en), key(en)): c for en, c in zip(lids, _ab_exact(ct, start, end))}
             break
-        small = _merge_to_small_steps(lids, rids, small_order)
-        current = small[-1]
+        lct = [_exact_time(en) for en in lids]
+        rct = [_exact_time(en) for en in rids]
+        small = _merge_to_small_steps(lct, rct, local_implicit, remote_implicit, small_order,
+                                      small_implicit)
+        current = small[-2] if small_implicit else small[-1]
         assert current >= start, "the start time is not a step boundary"
         small_coefs = _ab_exact(small, current, small_end)
         for m, tm in enumerate(small):
-            li = _lagrange_exact(lids, tm)
-            ri = _lagrange_exact(rids, tm)
+            li = _lagrange_exact(lct, tm)
+            ri = _lagrange_exact(rct, tm)
             for a, la in zip(lids, li):
                 if la == 0:
                     continue
                 for b, rb in zip(rids, ri):
                     if rb == 0:
                         continue
-                    coefs[(a, b)] = coefs.get((a, b), Fr(0)) + small_coefs[m] * la * rb
+                    k2 = (key(a), key(b))
+                    coefs[k2] = coefs.get(k2, Fr(0)) + small_coefs[m] * la * rb
         if current == start:
             break
         small_end = current
-    items = sorted(coefs.items())
     if exact:
-        return dict(items)
-    return {k: float(v) for k, v in items}
+        return dict(coefs)
+    return {k: float(v) for k, v in coefs.items()}
 
 
 # --------------------------------------------------------------------------------------

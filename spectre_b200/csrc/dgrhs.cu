@@ -358,9 +358,36 @@ int lincomb(dgrhs_ctx* c, double* u, double a, const std::vector<double>& coef,
 
 }  // namespace
 
+// constant_adams_moulton_coefficients (AdamsCoefficients.cpp:44-72), oldest value first, the
+// value at the end of the step last
+static const double kAmConst[9][8] = {
+    {},
+    {1.0},
+    {0.5, 0.5},
+    {-1.0 / 12.0, 2.0 / 3.0, 5.0 / 12.0},
+    {1.0 / 24.0, -5.0 / 24.0, 19.0 / 24.0, 3.0 / 8.0},
+    {-19.0 / 720.0, 53.0 / 360.0, -11.0 / 30.0, 323.0 / 360.0, 251.0 / 720.0},
+    {3.0 / 160.0, -173.0 / 1440.0, 241.0 / 720.0, -133.0 / 240.0, 1427.0 / 1440.0, 95.0 / 288.0},
+    {-863.0 / 60480.0, 263.0 / 2520.0, -6737.0 / 20160.0, 586.0 / 945.0, -15487.0 / 20160.0,
+     2713.0 / 2520.0, 19087.0 / 60480.0},
+    {275.0 / 24192.0, -11351.0 / 120960.0, 1537.0 / 4480.0, -88547.0 / 120960.0,
+     123133.0 / 120960.0, -4511.0 / 4480.0, 139849.0 / 120960.0, 5257.0 / 17280.0}};
+
+// adams_coefficients::coefficients (AdamsCoefficients.hpp:64-104): the constant-step tables
+// when the control times are equally spaced by the step and the step starts (Adams-Bashforth)
+// or ends (Adams-Moulton) at the last of them, else the integrals of the Lagrange polynomials
 std::vector<double> dgrhs_internal_ab_coefficients_ticks(const std::vector<long long>& ticks,
                                                          long long start, long long end,
                                                          double tick_size) {
+  const size_t order = ticks.size();
+  bool uniform = true;
+  for (size_t i = 0; i + 1 < order; ++i)
+    if (ticks[i + 1] - ticks[i] != end - start) uniform = false;
+  if (uniform && order <= 8 && ticks.back() == end && ticks.back() != start) {
+    std::vector<double> c(order);
+    for (size_t i = 0; i < order; ++i) c[i] = kAmConst[order][i] * ((double)(end - start) * tick_size);
+    return c;
+  }
   return ab_coefficients_ticks(ticks, start, end, 1, tick_size);
 }
 

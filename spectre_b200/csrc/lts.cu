@@ -27,19 +27,57 @@
 namespace {
 
 struct Term {
-  int li, ri;  // indices into the local / remote time lists
+  int li, ri;  // indices into the local / remote id lists
   double coef;
 };
 
 using Ticks = std::vector<long long>;
 
-// AdamsLts.cpp:173-206 (find_relevant_ids, explicit scheme): by position
-bool relevant(const Ticks& times, long long end, int order, std::vector<int>* idx) {
-  int used_end = (int)times.size();
-  while (used_end > 0 && !(times[used_end - 1] < end)) --used_end;
-  if (used_end < order) return false;
+// an id of a boundary history: the step id at `tick` (sub == 0) or the substep (predictor) id
+// of the step from tick to tick + sub; adams_lts::exact_substep_time (AdamsLts.cpp:29-38)
+struct Id {
+  long long tick, sub;
+  long long time() const { return tick + sub; }
+  bool operator==(const Id& o) const { return tick == o.tick && sub == o.sub; }
+};
+struct Scheme {
+  bool implicit;
+  int order;
+  bool operator==(const Scheme& o) const { return implicit == o.implicit && order == o.order; }
+};
+
+// AdamsLts.cpp:173-206 (find_relevant_ids): by position; indices into `ids`
+bool relevant(const std::vector<Id>& ids, long long end, const Scheme& sch,
+              std::vector<int>* idx, const char** why) {
+  std::vector<int> steps, substep_of;  // step entries and the substep entry of each (or -1)
+  for (int i = 0; i < (int)ids.size(); ++i) {
+    if (ids[i].sub == 0) {
+      steps.push_back(i);
+      substep_of.push_back(-1);
+    } else {
+      if (steps.empty() || ids[steps.back()].tick != ids[i].tick) {
+        *why = "substep id without its step id";
+        return false;
+      }
+      substep_of.back() = i;
+    }
+  }
+  int used_end = (int)steps.size();
+  while (used_end > 0 && !(ids[steps[used_end - 1]].tick < end)) --used_end;
+  const int past = sch.order - (sch.implicit ? 1 : 0);
+  if (used_end < past) {
+    *why = "Insufficient past data.";
+    return false;
+  }
   idx->clear();
-  for (int i = used_end - order; i < used_end; ++i) idx->push_back(i);
+  for (int i = used_end - past; i < used_end; ++i) idx->push_back(steps[i]);
+  if (sch.implicit) {
+    if (used_end < 1 || substep_of[used_end - 1] < 0) {
+      *why = "Must have substep data for implicit stepping.";
+      return false;
+    }
+    idx->push_back(substep_of[used_end - 1]);
+  }
   return true;
 }
 
@@ -64,35 +102,46 @@ std::vector<double> interpolation_coefficients(const Ticks& control, long long t
   return c;
 }
 
-// lts_coefficients (AdamsLts.cpp:330-437), explicit schemes; false: insufficient data
-bool lts_coefficients(const Ticks& local, const Ticks& remote, long long start, long long end,
-                      int lo, int ro, int so, double origin, double tick_size,
-                      std::vector<Term>* out, const char** why) {
+// lts_coefficients (AdamsLts.cpp:330-437); false: insufficient data
+bool lts_coefficients(const std::vector<Id>& local, const std::vector<Id>& remote,
+                      long long start, long long end, const Scheme& lo, const Scheme& ro,
+                      const Scheme& so, double origin, double tick_size, std::vector<Term>* out,
+                      const char** why) {
   out->clear();
   if (start == end) return true;
-  std::map<std::pair<int, int>, double> acc;  // sorted like the reference's (local, remote) ids
   std::vector<std::tuple<int, int, double>> raw;
   long long small_end = end;
   for (;;) {
     std::vector<int> li, ri;
-    if (!relevant(local, small_end, lo, &li) || !relevant(remote, small_end, ro, &ri)) {
-      *why = "Insufficient past data.";
+    if (!relevant(local, small_end, lo, &li, why) || !relevant(remote, small_end, ro, &ri, why))
       return false;
-    }
     Ticks lt, rt;
-    for (int i : li) lt.push_back(local[i]);
-    for (int i : ri) rt.push_back(remote[i]);
-    if (raw.empty() && so == lo && so == ro && lt == rt) {
+    bool same_ids = li.size() == ri.size();
+    for (int i : li) lt.push_back(local[i].time());
+    for (int i : ri) rt.push_back(remote[i].time());
+    for (size_t i = 0; same_ids && i < li.size(); ++i) same_ids = local[li[i]] == remote[ri[i]];
+    if (raw.empty() && so == lo && so == ro && same_ids) {
       // the sides step at the same rate: lts_coefficients_for_gts
       const auto g = dgrhs_internal_ab_coefficients_ticks(lt, start, end, tick_size);
       for (size_t s = 0; s < g.size(); ++s) out->push_back({li[s], ri[s], g[s]});
       return true;
     }
     // merge_to_small_steps (AdamsLts.cpp:214-277)
-    Ticks small((size_t)so);
+    Ticks small((size_t)so.order);
     {
       int a = (int)lt.size() - 1, b = (int)rt.size() - 1;
-      for (int o = so - 1; o >= 0; --o) {
+      if (!so.implicit) {
+        // don't use implicit interpolation points for an explicit step
+        if (lo.implicit) --a;
+        if (ro.implicit) --b;
+      } else if (lo.implicit && ro.implicit) {
+        // of the two times after the small step one belongs to a later small step
+        if (lt[a] < rt[b])
+          --b;
+        else
+          --a;
+      }
+      for (int o = so.order - 1; o >= 0; --o) {
         if (a < 0) {
           if (b < 0) {
             *why = "Ran out of data";
@@ -103,12 +152,17 @@ bool lts_coefficients(const Ticks& local, const Ticks& remote, long long start, 
           small[o] = lt[a--];
         } else {
           small[o] = std::max(lt[a], rt[b]);
-          if (lt[a] == small[o]) --a;
-          if (b >= 0 && rt[b] == small[o]) --b;
+          const bool la = lt[a] == small[o], rb = rt[b] == small[o];
+          if (la) --a;
+          if (rb) --b;
         }
       }
     }
-    const long long current = small.back();
+    if (so.implicit && small.size() < 2) {
+      *why = "implicit small-step scheme of order 1";
+      return false;
+    }
+    const long long current = small[small.size() - (so.implicit ? 2 : 1)];
     if (current < start) {
       *why = "the start time is not a step boundary";
       return false;
@@ -128,12 +182,14 @@ bool lts_coefficients(const Ticks& local, const Ticks& remote, long long start, 
     if (current == start) break;
     small_end = current;
   }
-  // combine duplicate entries (stable in the order of generation, like the sorted merge)
-  std::stable_sort(raw.begin(), raw.end(), [&](const auto& x, const auto& y) {
-    const auto kx = std::make_pair(local[std::get<0>(x)], remote[std::get<1>(x)]);
-    const auto ky = std::make_pair(local[std::get<0>(y)], remote[std::get<1>(y)]);
-    return kx < ky;
-  });
+  // combine duplicate entries, sorted like the reference's (local id, remote id): a step id
+  // before its substep id
+  const auto key = [&](const std::tuple<int, int, double>& x) {
+    const Id &a = local[std::get<0>(x)], &b = remote[std::get<1>(x)];
+    return std::make_tuple(a.tick, a.sub != 0, b.tick, b.sub != 0);
+  };
+  std::stable_sort(raw.begin(), raw.end(),
+                   [&](const auto& x, const auto& y) { return key(x) < key(y); });
   for (const auto& t : raw) {
     if (!out->empty() && out->back().li == std::get<0>(t) && out->back().ri == std::get<1>(t))
       out->back().coef += std::get<2>(t);
@@ -141,6 +197,12 @@ bool lts_coefficients(const Ticks& local, const Ticks& remote, long long start, 
       out->push_back({std::get<0>(t), std::get<1>(t), std::get<2>(t)});
   }
   return true;
+}
+
+std::vector<Id> step_ids(const Ticks& ticks) {
+  std::vector<Id> ids;
+  for (long long t : ticks) ids.push_back({t, 0});
+  return ids;
 }
 
 struct LtsState {
@@ -271,7 +333,9 @@ int complete_level(dgrhs_ctx* c, LtsState* s, int level, long long m) {
     }
     std::vector<Term> terms;
     const char* why = "";
-    if (!lts_coefficients(local, remote, start, end, k, k, k, s->t0, s->tick_size, &terms, &why))
+    const Scheme ab{false, k};
+    if (!lts_coefficients(step_ids(local), step_ids(remote), start, end, ab, ab, ab, s->t0,
+                          s->tick_size, &terms, &why))
       return fail("LTS coefficients (levels %d / %d): %s", level, nl, why);
     if ((int)terms.size() > s->max_terms)
       return fail("internal error: %d LTS terms, room for %d", (int)terms.size(), s->max_terms);
@@ -347,21 +411,28 @@ void dgrhs_internal_lts_free(dgrhs_ctx* c) {
 
 extern "C" {
 
-int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_step_order,
-                                 int n_local, const long long* local_ticks, int n_remote,
-                                 const long long* remote_ticks, long long start_tick,
-                                 long long end_tick, double time_origin, double tick_size,
-                                 int max_terms, int* n_terms, int* local_index,
-                                 int* remote_index, double* coefficients) {
+int dgrhs_adams_lts_coefficients_general(
+    int local_implicit, int local_order, int remote_implicit, int remote_order,
+    int small_step_implicit, int small_step_order, int n_local, const long long* local_ticks,
+    const long long* local_substep_sizes, int n_remote, const long long* remote_ticks,
+    const long long* remote_substep_sizes, long long start_tick, long long end_tick,
+    double time_origin, double tick_size, int max_terms, int* n_terms, int* local_index,
+    int* remote_index, double* coefficients) {
   for (int o : {local_order, remote_order, small_step_order})
     if (o < 1 || o > 8) return fail("order must be in [1, 8]");
   if (n_local < 1 || n_remote < 1) return fail("empty history");
-  const Ticks local(local_ticks, local_ticks + n_local);
-  const Ticks remote(remote_ticks, remote_ticks + n_remote);
+  std::vector<Id> local, remote;
+  for (int i = 0; i < n_local; ++i)
+    local.push_back({local_ticks[i], local_substep_sizes ? local_substep_sizes[i] : 0});
+  for (int i = 0; i < n_remote; ++i)
+    remote.push_back({remote_ticks[i], remote_substep_sizes ? remote_substep_sizes[i] : 0});
   std::vector<Term> terms;
   const char* why = "";
-  if (!lts_coefficients(local, remote, start_tick, end_tick, local_order, remote_order,
-                        small_step_order, time_origin, tick_size, &terms, &why))
+  if (!lts_coefficients(local, remote, start_tick, end_tick,
+                        Scheme{local_implicit != 0, local_order},
+                        Scheme{remote_implicit != 0, remote_order},
+                        Scheme{small_step_implicit != 0, small_step_order}, time_origin,
+                        tick_size, &terms, &why))
     return fail("%s", why);
   if ((int)terms.size() > max_terms)
     return fail("%d terms, room for %d", (int)terms.size(), max_terms);
@@ -372,6 +443,18 @@ int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_st
     coefficients[t] = terms[t].coef;
   }
   return 0;
+}
+
+int dgrhs_adams_lts_coefficients(int local_order, int remote_order, int small_step_order,
+                                 int n_local, const long long* local_ticks, int n_remote,
+                                 const long long* remote_ticks, long long start_tick,
+                                 long long end_tick, double time_origin, double tick_size,
+                                 int max_terms, int* n_terms, int* local_index,
+                                 int* remote_index, double* coefficients) {
+  return dgrhs_adams_lts_coefficients_general(
+      0, local_order, 0, remote_order, 0, small_step_order, n_local, local_ticks, nullptr,
+      n_remote, remote_ticks, nullptr, start_tick, end_tick, time_origin, tick_size, max_terms,
+      n_terms, local_index, remote_index, coefficients);
 }
 
 int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const int32_t* levels) {

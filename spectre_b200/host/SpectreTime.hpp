@@ -395,8 +395,9 @@ inline TimeStepId next_time_id(int stepper, int order, const TimeStepId& current
 }
 
 // ---- TimeSteppers::adams_lts (src/Time/TimeSteppers/AdamsLts.hpp:27-139) -----------------
-// lts_coefficients for explicit (Adams-Bashforth) schemes with the reference's argument
-// meaning: the ids of the local and the remote side of a mortar in the order of their
+// lts_coefficients with the reference's argument meaning (explicit = Adams-Bashforth and
+// implicit = Adams-Moulton schemes; a TimeStepId with substep() == 1 is the predictor value of
+// its step): the ids of the local and the remote side of a mortar in the order of their
 // insertion into the BoundaryHistory, the step [start_time, end_time] of the local side, the
 // orders of the three schemes.  All times must lie in one slab (or in slabs of equal length
 // that follow each other: they are brought to integer ticks of a common denominator).
@@ -413,9 +414,6 @@ inline LtsCoefficients lts_coefficients(const std::vector<TimeStepId>& local_tim
                                         const std::vector<TimeStepId>& remote_times, const Time& start_time,
                                         const Time& end_time, const AdamsScheme& local_scheme,
                                         const AdamsScheme& remote_scheme, const AdamsScheme& small_step_scheme) {
-  for (const auto* sch : {&local_scheme, &remote_scheme, &small_step_scheme})
-    if (sch->type != SchemeType::Explicit)
-      throw std::runtime_error("adams_lts::lts_coefficients: only explicit (Adams-Bashforth) schemes are built");
   if (local_times.empty() || remote_times.empty()) throw std::runtime_error("adams_lts::lts_coefficients: empty history");
   // common tick: slabs counted from the slab of start_time, fractions over one denominator
   const Slab& base = start_time.slab();
@@ -437,18 +435,37 @@ inline LtsCoefficients lts_coefficients(const std::vector<TimeStepId>& local_tim
     return slab_offset(t) * den + static_cast<std::int64_t>(t.fraction().numerator()) *
                                       (den / static_cast<std::int64_t>(t.fraction().denominator()));
   };
-  std::vector<long long> lt, rt;
-  for (const auto& id : local_times) lt.push_back(tick(id.step_time()));
-  for (const auto& id : remote_times) rt.push_back(tick(id.step_time()));
+  for (const auto* ids : {&local_times, &remote_times})
+    for (const auto& id : *ids)
+      if (id.substep() != 0)
+        den = std::lcm(den, static_cast<std::int64_t>(id.step_size().fraction().denominator()));
+  std::vector<long long> lt, rt, ls, rs;
+  const auto substep_size = [&](const TimeStepId& id) -> long long {
+    if (id.substep() == 0) return 0;
+    if (id.substep() != 1) throw std::runtime_error("adams_lts::lts_coefficients: substep > 1");
+    const auto f = id.step_size().fraction();
+    return static_cast<std::int64_t>(f.numerator()) * (den / static_cast<std::int64_t>(f.denominator()));
+  };
+  for (const auto& id : local_times) {
+    lt.push_back(tick(id.step_time()));
+    ls.push_back(substep_size(id));
+  }
+  for (const auto& id : remote_times) {
+    rt.push_back(tick(id.step_time()));
+    rs.push_back(substep_size(id));
+  }
   const int cap = 8 * 16;
   std::vector<int> li(cap), ri(cap);
   std::vector<double> cf(cap);
   int n = 0;
-  if (dgrhs_adams_lts_coefficients(static_cast<int>(local_scheme.order), static_cast<int>(remote_scheme.order),
-                                   static_cast<int>(small_step_scheme.order), static_cast<int>(lt.size()), lt.data(),
-                                   static_cast<int>(rt.size()), rt.data(), tick(start_time), tick(end_time),
-                                   base.start_value(), length / static_cast<double>(den), cap, &n, li.data(),
-                                   ri.data(), cf.data()) != 0)
+  const auto imp = [](const AdamsScheme& sch) { return sch.type == SchemeType::Implicit ? 1 : 0; };
+  if (dgrhs_adams_lts_coefficients_general(
+          imp(local_scheme), static_cast<int>(local_scheme.order), imp(remote_scheme),
+          static_cast<int>(remote_scheme.order), imp(small_step_scheme),
+          static_cast<int>(small_step_scheme.order), static_cast<int>(lt.size()), lt.data(), ls.data(),
+          static_cast<int>(rt.size()), rt.data(), rs.data(), tick(start_time), tick(end_time),
+          base.start_value(), length / static_cast<double>(den), cap, &n, li.data(), ri.data(),
+          cf.data()) != 0)
     throw std::runtime_error(dgrhs_last_error());
   LtsCoefficients out;
   for (int t = 0; t < n; ++t) out.emplace_back(local_times[li[t]], remote_times[ri[t]], cf[t]);

@@ -48,7 +48,7 @@ EXPORTS = [
     "dgrhs_set_mesh_velocity", "dgrhs_gh_package_data_moving", "dgrhs_sw_package_data_moving",
     "dgrhs_adams_lts_coefficients", "dgrhs_lts_init", "dgrhs_lts_set_past_state",
     "dgrhs_lts_take_ticks", "dgrhs_lts_ticks_per_coarse_step", "dgrhs_lts_time",
-    "dgrhs_lts_set_mode",
+    "dgrhs_lts_set_mode", "dgrhs_adams_lts_coefficients_general",
 ]
 
 _lib = None
@@ -92,23 +92,32 @@ class DgrhsError(RuntimeError):
 
 
 def adams_lts_coefficients(local_ticks, remote_ticks, start, end, local_order, remote_order=None,
-                           small_order=None, origin=0.0, tick_size=1.0):
-    """adams_lts::lts_coefficients for explicit schemes (AdamsLts.cpp:330-437), host only:
-    {(local tick, remote tick): coefficient}."""
+                           small_order=None, origin=0.0, tick_size=1.0, local_implicit=False,
+                           remote_implicit=False, small_implicit=False):
+    """adams_lts::lts_coefficients (AdamsLts.cpp:330-437), host only: {(local id, remote id):
+    coefficient}.  An id is a tick (step id) or a pair (tick, step size): the substep
+    (predictor) id of that step, which the implicit (Adams-Moulton) schemes use."""
     remote_order = local_order if remote_order is None else remote_order
     small_order = local_order if small_order is None else small_order
-    lt = np.ascontiguousarray(local_ticks, dtype=np.int64)
-    rt = np.ascontiguousarray(remote_ticks, dtype=np.int64)
+
+    def split(ids):
+        t = np.ascontiguousarray([i[0] if isinstance(i, tuple) else i for i in ids], dtype=np.int64)
+        s = np.ascontiguousarray([i[1] if isinstance(i, tuple) else 0 for i in ids], dtype=np.int64)
+        return t, s
+    lt, ls = split(local_ticks)
+    rt, rs = split(remote_ticks)
     cap = 256
     li, ri = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
     cf = np.zeros(cap)
     n = ctypes.c_int()
-    _check(load().dgrhs_adams_lts_coefficients(
-        int(local_order), int(remote_order), int(small_order), len(lt), _ptr(lt), len(rt),
-        _ptr(rt), ctypes.c_longlong(int(start)), ctypes.c_longlong(int(end)),
+    _check(load().dgrhs_adams_lts_coefficients_general(
+        int(local_implicit), int(local_order), int(remote_implicit), int(remote_order),
+        int(small_implicit), int(small_order), len(lt), _ptr(lt), _ptr(ls), len(rt), _ptr(rt),
+        _ptr(rs), ctypes.c_longlong(int(start)), ctypes.c_longlong(int(end)),
         ctypes.c_double(origin), ctypes.c_double(tick_size), cap, ctypes.byref(n), _ptr(li),
         _ptr(ri), _ptr(cf)))
-    return {(int(lt[li[t]]), int(rt[ri[t]])): float(cf[t]) for t in range(n.value)}
+    key = lambda t, s, i: int(t[i]) if s[i] == 0 else (int(t[i]), int(s[i]))
+    return {(key(lt, ls, li[t]), key(rt, rs, ri[t])): float(cf[t]) for t in range(n.value)}
 
 
 def load():

@@ -395,7 +395,28 @@ static void test_adams_lts() {
     const auto g = lts::lts_coefficients(small, small, make_time(2), make_time(3), ab2, ab2, ab2);
     CHECK(g.size() == 2 && find(g, 1, 1, &v) && near(v, -0.5) && find(g, 2, 2, &v) && near(v, 1.5));
   }
+  // "AM GTS order 3" (:469-503): steps {0}, {1} and the predictor value {1, 1} of the step
+  // from 1 to 2 (make_id with step_size_if_substep, :266-281)
   const lts::AdamsScheme am3{lts::SchemeType::Implicit, 3};
+  {
+    auto steps = ids({0, 1});
+    const TimeDelta unit = slab.duration() / (2 * max_time);
+    steps.emplace_back(true, 0, make_time(1), 1, unit, 2.0);
+    const auto c = lts::lts_coefficients(steps, steps, make_time(1), make_time(2), am3, am3, am3);
+    CHECK(c.size() == 3);
+    double v = 0.0;
+    CHECK(find(c, 0, 0, &v) && near(v, -1.0 / 12.0));
+    bool found_predictor = false, found_step = false;
+    for (const auto& term : c) {
+      if (std::get<0>(term).step_time() != make_time(1)) continue;
+      if (std::get<0>(term).substep() == 1 && std::get<1>(term).substep() == 1)
+        found_predictor = near(std::get<2>(term), 5.0 / 12.0);
+      if (std::get<0>(term).substep() == 0 && std::get<1>(term).substep() == 0)
+        found_step = near(std::get<2>(term), 2.0 / 3.0);
+    }
+    CHECK(found_predictor && found_step);
+  }
+  // an implicit scheme needs the predictor value
   CHECK_THROWS(lts::lts_coefficients(ids({0, 1}), ids({0, 1}), make_time(1), make_time(2), am3, am3, am3));
 }
 

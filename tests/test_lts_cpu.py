@@ -316,3 +316,80 @@ def test_partition_reorder_keeps_the_connectivity():
         sorted(part0.external_faces)
     with pytest.raises(ValueError):
         domain.Partition(rb.neighbors(), 2, 0, mortars=rb.mortars()).reorder(perm[:4])
+
+
+def _check_ids(got, expected):
+    norm = lambda k: (Fr(k[0]), Fr(k[1])) if isinstance(k, tuple) else Fr(k)
+    want = {(norm(a), norm(b)): v for (a, b), v in expected.items()}
+    assert set(got) == set(want), (got, want)
+    for k, v in want.items():
+        assert got[k] == pytest.approx(v, rel=1e-13, abs=1e-14)
+
+
+def test_implicit_schemes_reference_known_answers():
+    """Adams-Moulton (implicit) schemes of lts_coefficients, the predictor value of a step
+    written as the pair (step time, step size): Test_AdamsLts.cpp:469-503 (AM GTS order 3),
+    :529-554 (AM single-side order 3), :727-776 (AM 2:1 order 2)"""
+    am = dict(local_implicit=True, remote_implicit=True, small_implicit=True)
+    steps = [0, 1, (1, 1)]
+    am3 = [-1.0 / 12.0, 2.0 / 3.0, 5.0 / 12.0]
+    _check_ids(lts.lts_coefficients(steps, steps, 1, 2, 3, **am),
+               {(0, 0): am3[0], (1, 1): am3[1], ((1, 1), (1, 1)): am3[2]})
+    # the predictor of the same step is an explicit step of one order less
+    _check_ids(lts.lts_coefficients(steps, steps, 1, 2, 2), {(0, 0): -0.5, (1, 1): 1.5})
+    _check_ids(lts.lts_coefficients(steps, [0], 1, 2, 3, 1, 3, local_implicit=True,
+                                    small_implicit=True),
+               {(0, 0): am3[0], (1, 0): am3[1], ((1, 1), 0): am3[2]})
+    _check_ids(lts.lts_coefficients(steps, [0], 1, 2, 2, 1, 2), {(0, 0): -0.5, (1, 0): 1.5})
+    large, small = [0, (0, 2)], [0, (0, 1), 1, (1, 1)]
+    _check_ids(lts.lts_coefficients(large, [0], 0, 2, 1), {(0, 0): 2.0})
+    _check_ids(lts.lts_coefficients(large, small, 0, 2, 2, **am),
+               {(0, 0): 0.5, (0, (0, 1)): 0.25, ((0, 2), (0, 1)): 0.25, (0, 1): 0.25,
+                ((0, 2), 1): 0.25, ((0, 2), (1, 1)): 0.5})
+    _check_ids(lts.lts_coefficients(small, large, 0, 1, 1), {(0, 0): 1.0})
+    _check_ids(lts.lts_coefficients(small, large, 0, 1, 2, **am),
+               {(0, 0): 0.5, ((0, 1), 0): 0.25, ((0, 1), (0, 2)): 0.25})
+    _check_ids(lts.lts_coefficients(small, large, 1, 2, 1), {(1, 0): 1.0})
+    _check_ids(lts.lts_coefficients(small, large, 1, 2, 2, **am),
+               {(1, 0): 0.25, (1, (0, 2)): 0.25, ((1, 1), (0, 2)): 0.5})
+
+
+def test_library_implicit_schemes_match_the_oracle_and_the_reference():
+    """dgrhs_adams_lts_coefficients_general with Adams-Moulton schemes: the reference's cases
+    (Test_AdamsLts.cpp:469-503, :529-554, :727-776) and 2:1 / 4:1 predictor-corrector
+    patterns of orders 2..8 against the oracle's exact rationals"""
+    from spectre_b200 import lib
+    am = dict(local_implicit=True, remote_implicit=True, small_implicit=True)
+    got = lib.adams_lts_coefficients([0, 1, (1, 1)], [0, 1, (1, 1)], 1, 2, 3, **am)
+    assert got == pytest.approx({(0, 0): -1.0 / 12.0, (1, 1): 2.0 / 3.0,
+                                 ((1, 1), (1, 1)): 5.0 / 12.0}, rel=1e-14)
+    large, small = [0, (0, 2)], [0, (0, 1), 1, (1, 1)]
+    got = lib.adams_lts_coefficients(large, small, 0, 2, 2, **am)
+    assert got == pytest.approx({(0, 0): 0.5, (0, (0, 1)): 0.25, ((0, 2), (0, 1)): 0.25,
+                                 (0, 1): 0.25, ((0, 2), 1): 0.25, ((0, 2), (1, 1)): 0.5},
+                                rel=1e-14)
+    assert list(got) == sorted(got, key=lambda k: tuple(
+        (i, 0, 0) if not isinstance(i, tuple) else (i[0], 1, i[1]) for i in k))
+    cases = []
+    for k in range(2, 9):
+        for r in (2, 4):
+            # steady state: coarse steps of r ticks with the predictor value of the current
+            # step, fine steps of one tick with theirs
+            coarse = [r * i for i in range(-(k - 2), 1)] + [(0, r)]
+            fine = []
+            for t in range(-(k - 2), r):
+                fine += [t, (t, 1)]
+            cases.append((coarse, fine, 0, r, k))                       # the coarse corrector
+            cases.append(([i for i in fine if (i[0] if isinstance(i, tuple) else i) <= 0],
+                          coarse, 0, 1, k))                             # first fine corrector
+    for local, remote, start, end, k in cases:
+        ref = lts.lts_coefficients(local, remote, start, end, k, **am)
+        got = lib.adams_lts_coefficients(local, remote, start, end, k, origin=-0.7,
+                                         tick_size=0.5, **am)
+        norm = lambda i: (Fr(i[0]), Fr(i[1])) if isinstance(i, tuple) else Fr(i)
+        assert {(norm(a), norm(b)) for a, b in got} == set(ref)
+        scale = max(abs(v) for v in ref.values())
+        for (a, b), v in got.items():
+            assert abs(v - 0.5 * ref[(norm(a), norm(b))]) < 1e-9 * scale, (local, remote, a, b)
+    with pytest.raises(lib.DgrhsError, match="substep data"):
+        lib.adams_lts_coefficients([0, 1], [0, 1], 1, 2, 3, **am)
