@@ -394,6 +394,21 @@ inline TimeStepId next_time_id(int stepper, int order, const TimeStepId& current
   return current_id.next_substep(time_step, fractions[current_id.substep()]);
 }
 
+// ---- choose_lts_step_size (src/Time/ChooseLtsStepSize.cpp:14-39) -------------------------
+// the step slab / 2^n closest to (not above) the desired step that still hits the slab boundary
+// from `time`, a binary-fraction time of its slab; negative desired steps run backwards
+inline TimeDelta choose_lts_step_size(const Time& time, double desired_step) {
+  const auto den = time.fraction().denominator();
+  if ((den & (den - 1)) != 0) throw std::logic_error("Not at a binary-fraction time within slab");
+  const TimeDelta full_slab = desired_step > 0.0 ? time.slab().duration() : -time.slab().duration();
+  const double desired_step_count = full_slab.value() / desired_step;
+  // log2(2^n + eps) may give n: the inner ceil avoids that
+  const std::size_t power =
+      desired_step_count == 0.0 ? 0 : static_cast<std::size_t>(std::ceil(std::log2(std::ceil(desired_step_count))));
+  const auto step_count = std::max(static_cast<decltype(den)>(1) << power, den);
+  return full_slab / step_count;
+}
+
 // ---- TimeSteppers::adams_lts (src/Time/TimeSteppers/AdamsLts.hpp:27-139) -----------------
 // lts_coefficients with the reference's argument meaning (explicit = Adams-Bashforth and
 // implicit = Adams-Moulton schemes; a TimeStepId with substep() == 1 is the predictor value of

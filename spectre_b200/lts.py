@@ -20,13 +20,23 @@ def order_by_level(levels, neighbors):
     return perm, nb.astype(np.int32)
 
 
+def choose_lts_step_power(desired_step, slab_duration, fraction_denominator=1):
+    """choose_lts_step_size (Time/ChooseLtsStepSize.cpp:14-39) for forward steps: n such that
+    the step is slab / 2^n -- the largest binary fraction of the slab that does not exceed the
+    desired step, but no larger than the position inside the slab (a time whose slab fraction
+    has the denominator 2^m) allows.  Works on arrays."""
+    count = slab_duration / np.asarray(desired_step, dtype=float)
+    power = np.where(count == 0.0, 0.0, np.ceil(np.log2(np.maximum(np.ceil(count), 1.0))))
+    steps = np.maximum(2.0 ** power, float(fraction_denominator))
+    return np.log2(steps).astype(int)
+
+
 def levels_from_step_limit(step_limit, dt_coarse, max_level=7):
-    """Smallest level whose step dt_coarse / 2^level does not exceed the element's step limit
-    (the role of the reference's StepChoosers::ElementSizeCfl / Cfl, which bound the step by
-    the element size over the characteristic speed; here evaluated once, at the start)."""
-    lim = np.asarray(step_limit, dtype=float)
-    lv = np.ceil(np.log2(np.maximum(dt_coarse / lim, 1.0)) - 1e-12).astype(int)
-    return np.clip(lv, 0, max_level)
+    """Step-size level of every element for a per-element step limit (the goal of
+    StepChoosers::ElementSizeCfl / Cfl, evaluated once, at the start): the element takes the
+    steps dt_coarse / 2^level that choose_lts_step_size picks at the start of a slab of length
+    dt_coarse."""
+    return np.clip(choose_lts_step_power(step_limit, dt_coarse), 0, max_level)
 
 
 def start_from_gts(ctx, order, t0, dt_coarse, levels, stepper=None):

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -348,6 +349,19 @@ static int test_time_loop_gpu() {
 }
 
 
+// tests/Unit/Time/Test_ChooseLtsStepSize.cpp:12-31
+static void test_choose_lts_step_size() {
+  const Slab slab(1., 4.);
+  CHECK(choose_lts_step_size(slab.start(), 4.) == slab.duration());
+  CHECK(choose_lts_step_size(slab.start(), 10.) == slab.duration());
+  CHECK(choose_lts_step_size(slab.start(), 2.) == slab.duration() / 2);
+  CHECK(choose_lts_step_size(slab.start(), 1.4) == slab.duration() / 4);
+  CHECK(choose_lts_step_size(slab.start() + slab.duration() / 4, 2.) == slab.duration() / 4);
+  CHECK(choose_lts_step_size(slab.end(), -2.) == -slab.duration() / 2);
+  CHECK(choose_lts_step_size(slab.start(), std::numeric_limits<double>::infinity()) == slab.duration());
+  CHECK_THROWS(choose_lts_step_size(slab.start() + slab.duration() / 3, 1.));
+}
+
 // tests/Unit/Time/TimeSteppers/Test_AdamsLts.cpp:260-283 (make_time / make_id) and :556-596
 // ("AB 2:1 order 3"), :615-640 ("AB 3:1 order 2") on the shim's argument types
 static void test_adams_lts() {
@@ -429,6 +443,7 @@ int main(int argc, char** argv) {
     test_time_step_id(false);
     test_next_time_id();
     test_adams_lts();
+    test_choose_lts_step_size();
     if (argc > 1 && std::string(argv[1]) == "gpu" && test_time_loop_gpu()) {
       std::printf("FAILED: %s\n", dgrhs_last_error());
       return 1;

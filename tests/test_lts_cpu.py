@@ -393,3 +393,20 @@ def test_library_implicit_schemes_match_the_oracle_and_the_reference():
             assert abs(v - 0.5 * ref[(norm(a), norm(b))]) < 1e-9 * scale, (local, remote, a, b)
     with pytest.raises(lib.DgrhsError, match="substep data"):
         lib.adams_lts_coefficients([0, 1], [0, 1], 1, 2, 3, **am)
+
+
+def test_choose_lts_step_size_known_answers():
+    """Test_ChooseLtsStepSize.cpp:12-24 (slab [1, 4], duration 3): the step is slab / 2^n"""
+    from spectre_b200 import lts as hlts
+    dur = 3.0
+    assert hlts.choose_lts_step_power(4.0, dur) == 0
+    assert hlts.choose_lts_step_power(10.0, dur) == 0
+    assert hlts.choose_lts_step_power(2.0, dur) == 1
+    assert hlts.choose_lts_step_power(1.4, dur) == 2
+    assert hlts.choose_lts_step_power(2.0, dur, fraction_denominator=4) == 2   # at start + 1/4
+    assert hlts.choose_lts_step_power(np.inf, dur) == 0
+    # arrays, exact powers of two (log2(2^n + eps) must not round up twice)
+    np.testing.assert_array_equal(
+        hlts.choose_lts_step_power(np.array([1.0, 0.5, 0.25, 0.125, 0.1249]), 1.0),
+        [0, 1, 2, 3, 4])
+    np.testing.assert_array_equal(hlts.levels_from_step_limit([0.3, 0.06, 1.0], 0.25), [0, 3, 0])
