@@ -170,9 +170,22 @@ int dev_alloc(T** p, size_t count) {
     CU(cudaMalloc((void**)p, bytes));
   }
   CU(cudaMemset(*p, 0, bytes));
+  // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which
+  // the context's non-blocking streams do not wait for: finish it before anyone can queue
+  // work on the new buffer (allocation happens at set-up time, never inside a step)
+  CU(cudaStreamSynchronize(cudaStreamLegacy));
   return 0;
 }
 
+
+// Blocking host-to-device copy of a set-up table.  cudaMemcpy from pageable memory may return
+// while the DMA is still in flight on the legacy default stream, which the context's
+// non-blocking streams do not wait for: finish it before a kernel can be queued.
+inline cudaError_t h2d_table(void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(cudaStreamLegacy);
+}
 
 // DGRHS_NO_PDL=1 in the environment turns programmatic dependent launch off
 static const bool g_pdl = [] {

@@ -581,9 +581,9 @@ int dgrhs_create(dgrhs_ctx** out, int system, int N, int nelem, int nghost, int 
   }
   std::vector<double> D;
   diff_matrix(N, D);
-  CU(cudaMemcpy(c->D, D.data(), D.size() * 8, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->D, D.data(), D.size() * 8));
   std::vector<int32_t> nb((size_t)nelem * 6, -1);
-  CU(cudaMemcpy(c->nbr, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->nbr, nb.data(), nb.size() * 4));
   if (ensure_slots(c, 1)) return 1;
   c->dt_last = c->dt_slots[0];
   *out = c;
@@ -664,7 +664,7 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
     if (!c->coords && dev_alloc(&c->coords, (size_t)c->nelem * 3 * c->npad)) return 1;
     if (upload(c, c->coords, coords, 3)) return 1;
   }
-  CU(cudaMemcpy(c->nbr, neighbors, (size_t)c->nelem * 6 * 4, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->nbr, neighbors, (size_t)c->nelem * 6 * 4));
   c->nbr_host.assign(neighbors, neighbors + (size_t)c->nelem * 6);
   // a new neighbour table resets the orientations to "aligned" and drops the mortars
   if (c->nbr_face) cudaFree(c->nbr_face);
@@ -708,7 +708,7 @@ int dgrhs_set_geometry(dgrhs_ctx* c, const double* inv_jacobian, const double* c
   }
   if (!bj.empty()) {
     CU(cudaMalloc(&c->bjorhus_faces, bj.size() * 4));
-    CU(cudaMemcpy(c->bjorhus_faces, bj.data(), bj.size() * 4, cudaMemcpyHostToDevice));
+    CU(h2d_table(c->bjorhus_faces, bj.data(), bj.size() * 4));
   }
   return 0;
 }
@@ -751,7 +751,7 @@ int dgrhs_set_neighbor_orientations(dgrhs_ctx* c, const int32_t* neighbor_direct
   // the aligned default needs the opposite-face rule checked in set_geometry;
   // with explicit orientations that check is replaced by the one above
   if (!c->nbr_face && dev_alloc(&c->nbr_face, packed.size())) return 1;
-  CU(cudaMemcpy(c->nbr_face, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->nbr_face, packed.data(), packed.size() * 4));
   return 0;
 }
 
@@ -998,7 +998,7 @@ int dgrhs_set_p_mortars(dgrhs_ctx* c, int n_faces, const int32_t* table) {
   c->n_pmortar_faces = n_faces;
   if (n_faces == 0) return 0;
   CU(cudaMalloc(&c->pm_faces, (size_t)n_faces * 16));
-  CU(cudaMemcpy(c->pm_faces, table, (size_t)n_faces * 16, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->pm_faces, table, (size_t)n_faces * 16));
   if (dev_alloc(&c->pm_ghost, (size_t)n_faces * c->HC * 144)) return 1;
   // mortar mesh = the larger extents (MortarHelpers.cpp:22-49): interpolation of the side
   // with fewer points up to it, L2 projection back (Projection.cpp:57-362)
@@ -1013,8 +1013,8 @@ int dgrhs_set_p_mortars(dgrhs_ctx* c, int n_faces, const int32_t* table) {
   }
   if (!c->pm_P && dev_alloc(&c->pm_P, P.size())) return 1;
   if (!c->pm_R && dev_alloc(&c->pm_R, R.size())) return 1;
-  CU(cudaMemcpy(c->pm_P, P.data(), P.size() * 8, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->pm_R, R.data(), R.size() * 8, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->pm_P, P.data(), P.size() * 8));
+  CU(h2d_table(c->pm_R, R.data(), R.size() * 8));
   if (!c->pm_event) CU(cudaEventCreateWithFlags(&c->pm_event, cudaEventDisableTiming));
   return 0;
 }
@@ -1148,8 +1148,8 @@ int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
   if (n_mortars == 0) return 0;
   CU(cudaMalloc(&c->mortar_faces, faces.size() * 4));
   CU(cudaMalloc(&c->mortar_table, table.size() * 4));
-  CU(cudaMemcpy(c->mortar_faces, faces.data(), faces.size() * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->mortar_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->mortar_faces, faces.data(), faces.size() * 4));
+  CU(h2d_table(c->mortar_table, table.data(), table.size() * 4));
   const int N = c->N;
   std::vector<double> P, R, M;
   for (int size = 0; size < 3; ++size) {
@@ -1160,8 +1160,8 @@ int dgrhs_set_mortars(dgrhs_ctx* c, int n_mortars, const int32_t* mortars) {
   }
   if (!c->mortar_P && dev_alloc(&c->mortar_P, P.size())) return 1;
   if (!c->mortar_R && dev_alloc(&c->mortar_R, R.size())) return 1;
-  CU(cudaMemcpy(c->mortar_P, P.data(), P.size() * 8, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->mortar_R, R.data(), R.size() * 8, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->mortar_P, P.data(), P.size() * 8));
+  CU(h2d_table(c->mortar_R, R.data(), R.size() * 8));
   return 0;
 }
 
@@ -1292,7 +1292,7 @@ int dgrhs_set_halo_map(dgrhs_ctx* c, const int32_t* map, int n_send) {
   for (int i = 0; i < n_send; ++i)
     if (map[2 * i] < 0 || map[2 * i] >= c->nelem || map[2 * i + 1] < 0 || map[2 * i + 1] > 5)
       return fail("bad halo map entry %d", i);
-  CU(cudaMemcpy(c->halo_map, map, (size_t)n_send * 8, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->halo_map, map, (size_t)n_send * 8));
   return 0;
 }
 
@@ -1499,7 +1499,7 @@ int dgrhs_set_exponential_filter(dgrhs_ctx* c, int enable, double alpha, int hal
   std::vector<double> F;
   exponential_filter_matrix(c->N, alpha, (unsigned)half_power, F);
   if (!c->filterF && dev_alloc(&c->filterF, F.size())) return 1;
-  CU(cudaMemcpy(c->filterF, F.data(), F.size() * 8, cudaMemcpyHostToDevice));
+  CU(h2d_table(c->filterF, F.data(), F.size() * 8));
   std::memcpy(c->filterF_host, F.data(), F.size() * 8);
   return 0;
 }
@@ -2185,7 +2185,7 @@ int dgrhs_partial_derivatives(int N, int C, const double* u, const double* invja
     return 1;
   std::vector<double> D;
   diff_matrix(N, D);
-  CU(cudaMemcpy(D_d, D.data(), D.size() * 8, cudaMemcpyHostToDevice));
+  CU(h2d_table(D_d, D.data(), D.size() * 8));
   CU(cudaMemcpy2D(u_d, (size_t)npad * 8, u, (size_t)n * 8, (size_t)n * 8, C,
                   cudaMemcpyHostToDevice));
   CU(cudaMemcpy2D(j_d, (size_t)npad * 8, invjac, (size_t)n * 8, (size_t)n * 8, 9,

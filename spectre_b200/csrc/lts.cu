@@ -570,15 +570,19 @@ int dgrhs_lts_init(dgrhs_ctx* c, int order, double t0, double dt_coarse, const i
       if (v >= 0 && !(s->same_level_in_volume && levels[v] == levels[e]))
         v = dg::kLtsHistoryFace;
     }
-  CU(cudaMemcpy(s->nbr_ext, ext.data(), ext.size() * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(s->level_dev, levels, (size_t)c->nelem * 4, cudaMemcpyHostToDevice));
+  CU(h2d_table(s->nbr_ext, ext.data(), ext.size() * 4));
+  CU(h2d_table(s->level_dev, levels, (size_t)c->nelem * 4));
   if (dev_alloc(&s->in_history, hist.size())) return 1;
   if (dev_alloc(&s->mortar_in_history, mhist.size())) return 1;
-  CU(cudaMemcpy(s->in_history, hist.data(), hist.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(s->mortar_in_history, mhist.data(), mhist.size(), cudaMemcpyHostToDevice));
+  CU(h2d_table(s->in_history, hist.data(), hist.size()));
+  CU(h2d_table(s->mortar_in_history, mhist.data(), mhist.size()));
   // correction slots of faces in the histories are never written by the face / mortar kernels
   // of an evaluation: they must read zero (the volume kernel adds all six slots)
-  CU(cudaMemset(c->corr, 0, (size_t)c->nelem * 6 * c->C * c->N * c->N * sizeof(double)));
+  CU(cudaMemsetAsync(c->corr, 0, (size_t)c->nelem * 6 * c->C * c->N * c->N * sizeof(double),
+                     c->stream));
+  // the tables above went through the legacy default stream, which the context's
+  // non-blocking stream does not wait for: everything is in place before the first kernel
+  CU(cudaDeviceSynchronize());
   return 0;
 }
 
