@@ -619,10 +619,20 @@ def secondary_line(args, world, rank, local_rank, pg):
     total_points = run.ev.n_points * world
     value = total_points * steps / (ms * 1e-3)
     _, err = run.check_state()
+    # at two ranks: the gathered state against a single-GPU evolution of the whole domain, bit
+    # for bit (cheap on this workload; at more ranks the whole domain is not run on one GPU)
+    bit_identical = None
+    if world == 2:
+        try:
+            run.verify(3 + steps + run.extra_steps)
+            bit_identical = True
+        except AssertionError:
+            bit_identical = False
     roof = run.roofline(value)
     run.ctx.close()
     return {"config": workload_config(sub, world), "value": value, "unit": UNIT, "steps": steps,
             "ms_per_step": ms / steps, "gpu_launches": int(launches),
+            "two_rank_state_bit_identical_to_one_gpu": bit_identical,
             "roofline": {k: roof[k] for k in ("kernel", "achieved", "peak", "frac", "kernels_ms",
                                               "step")},
             "max_abs_error_vs_exact": err}
