@@ -202,3 +202,35 @@ class LtsEvolution:
     def state(self):
         """(global element ids, state) in the library's element order"""
         return self.part.global_ids, self.ctx.get_state()
+
+
+def minimum_grid_spacing(coords, N):
+    """domain::minimum_grid_spacing (Domain/MinimumGridSpacing.cpp:31-71) per element: the
+    smallest inertial distance between a grid point and one of its 26 index neighbours.
+    coords [nelem, 3, N^3], xi fastest."""
+    x = np.asarray(coords).reshape(len(coords), 3, N, N, N)      # [e, dim, k, j, i]
+    best = np.full(len(coords), np.inf)
+    for dk in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            for di in (-1, 0, 1):
+                if (dk, dj, di) <= (0, 0, 0):
+                    continue        # the opposite offsets are seen from the other point
+                a = x[:, :, max(0, -dk):N - max(0, dk), max(0, -dj):N - max(0, dj),
+                      max(0, -di):N - max(0, di)]
+                b = x[:, :, max(0, dk):N - max(0, -dk), max(0, dj):N - max(0, -dj),
+                      max(0, di):N - max(0, -di)]
+                d = np.sqrt(((a - b) ** 2).sum(axis=1)).reshape(len(coords), -1).min(axis=1)
+                best = np.minimum(best, d)
+    return best
+
+
+def cfl_step(min_grid_spacing, speed, stable_step, safety_factor):
+    """StepChoosers::Cfl (Time/StepChoosers/Cfl.hpp:69-79): safety_factor * stable_step *
+    minimum grid spacing / (speed * 3)."""
+    return safety_factor * stable_step * np.asarray(min_grid_spacing) / (np.asarray(speed) * 3)
+
+
+def limit_increase(last_step, factor):
+    """StepChoosers::LimitIncrease (LimitIncrease.hpp): the next step may be at most `factor`
+    times the last one (a size limit, not a goal)."""
+    return np.abs(last_step) * factor

@@ -410,3 +410,30 @@ def test_choose_lts_step_size_known_answers():
         hlts.choose_lts_step_power(np.array([1.0, 0.5, 0.25, 0.125, 0.1249]), 1.0),
         [0, 1, 2, 3, 4])
     np.testing.assert_array_equal(hlts.levels_from_step_limit([0.3, 0.06, 1.0], 0.25), [0, 3, 0])
+
+
+def test_cfl_step_chooser_and_minimum_grid_spacing():
+    """StepChoosers::Cfl (Cfl.hpp:69-79) on domain::minimum_grid_spacing
+    (MinimumGridSpacing.cpp:31-71): on an affine brick the smallest spacing is the first LGL
+    interval of the shortest side; on a wedge no pair of index neighbours is closer than the
+    value found by brute force over all pairs of the inner face"""
+    from spectre_b200 import domain, lib
+    from spectre_b200 import lts as hlts
+    N = 5
+    brick = domain.Brick([0, 0, 0], [2.0, 4.0, 8.0], [1, 1, 1], N)
+    xi, _ = lib.collocation_points_and_weights(N)
+    first = 0.5 * (xi[1] - xi[0])        # first LGL interval of a unit-length side
+    np.testing.assert_allclose(hlts.minimum_grid_spacing(brick.coords(), N), first * 1.0,
+                               rtol=1e-13)
+    shell = domain.SphericalShell(2.0, 6.0, (0, 0), N)
+    x = shell.coords()
+    got = hlts.minimum_grid_spacing(x, N)
+    for e in range(shell.n_elements):
+        pts = x[e].T
+        d = np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(axis=2))
+        np.fill_diagonal(d, np.inf)
+        assert got[e] == pytest.approx(d.min(), rel=1e-12)
+    step = hlts.cfl_step(np.array([0.1, 0.2]), np.array([1.0, 2.0]), 3.0 / 11.0, 0.8)
+    np.testing.assert_allclose(step, [0.8 * (3.0 / 11.0) * 0.1 / 3.0, 0.8 * (3.0 / 11.0) * 0.2 / 6.0],
+                               rtol=1e-15)
+    assert hlts.limit_increase(-0.25, 2.0) == 0.5
